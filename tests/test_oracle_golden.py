@@ -1,0 +1,122 @@
+"""CPU: pin the oracle (oracle/gnan_port.py, oracle/gnan_lut.py, oracle/apsp_oracle.c) against the golden
+vectors produced by the unmodified reference (oracle/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import apsp as oapsp
+from oracle import gnan_lut, gnan_port
+from tests import _golden as G
+
+TOL_PORT = 2e-6   # fp32 port vs fp32 reference (same op order; measured ~1e-7)
+TOL_LUT = 5e-6    # fp64 re-ordered restatement vs fp32 reference
+
+
+def run_port(z, dtype):
+    fs = gnan_port.to_torch(z["fs"], dtype, True)
+    rho = gnan_port.to_torch(z["rho"], dtype, True)
+    x = torch.tensor(z["x"]).to(dtype)
+    extra = {}
+    if z["variant"] == "batched":
+        out = gnan_port.tensor_gnan_batched(fs, rho, x, torch.tensor(z["dist_batch"]).to(dtype),
+                                            torch.tensor(z["batch_vector"]), z["is_graph_task"])
+    else:
+        nd = torch.tensor(z["node_distances"]).to(dtype)
+        nm = torch.tensor(z["normalization_matrix"]).to(dtype)
+        if z["variant"] == "gnanpy_tensor":
+            out = gnan_port.tensor_gnan_gnanpy(fs, rho, x, nd, nm, z["normalize_rho"], z["is_graph_task"])
+        elif z["variant"] == "models_tensor":
+            ro = gnan_port.to_torch(z["readout"], dtype, True) if "readout" in z else None
+            extra["readout"] = ro
+            out = gnan_port.tensor_gnan_models(fs, rho, x, nd, nm, z["normalize_rho"], z["is_graph_task"], ro)
+        else:
+            ids = z["node_ids"].tolist() if "node_ids" in z else None
+            out = gnan_port.gnan_rowloop(fs, rho, x, nd, nm, z["normalize_rho"], ids)
+    (out * torch.tensor(z["out_weight"]).to(dtype)).sum().backward()
+    return out, fs, rho, extra
+
+
+def check_grads(z, got, key, tol):
+    want = z[key]
+    has_bias = z["rho_has_bias"] if key == "grad_rho" else z["bias"]
+    for k in ("w1", "b1", "wh", "bh", "wo", "bo"):
+        if want[k] is None or want[k].size == 0:
+            continue
+        if k.startswith("b") and not has_bias:      # the reference has no such parameter (GNAN.py:36-37)
+            continue
+        g = got[k].grad
+        g = np.zeros_like(want[k]) if g is None else g.numpy()
+        if np.linalg.norm(want[k]) == 0:
+            assert np.abs(g).max() < 1e-6, (key, k)
+        else:
+            assert G.rel_err(g, want[k]) < tol, (z["name"], key, k, G.rel_err(g, want[k]))
+
+
+@pytest.mark.parametrize("name", G.MODEL_CASES + G.BATCHED_CASES)
+def test_port_matches_reference(name):
+    z = G.load(name)
+    out, fs, rho, extra = run_port(z, torch.float32)
+    assert out.shape == z["out"].shape
+    assert G.rel_err(out.detach().numpy(), z["out"]) < TOL_PORT
+    check_grads(z, fs, "grad_fs", 2e-5)
+    check_grads(z, rho, "grad_rho", 2e-5)
+    if extra.get("readout") is not None:
+        check_grads(z, extra["readout"], "grad_readout", 2e-5)
+
+
+def lut_mode(z):
+    if z["variant"] == "batched":
+        return "raw"
+    if not z["normalize_rho"]:
+        return "none"
+    return "input" if z["variant"] == "gnanpy_tensor" else "output"
+
+
+@pytest.mark.parametrize("name", [n for n in G.MODEL_CASES if "readout" not in n] + G.BATCHED_CASES)
+def test_lut_restatement_matches_reference(name):
+    z = G.load(name)
+    dt = torch.float64
+    fs = gnan_port.to_torch(z["fs"], dt, True)
+    rho = gnan_port.to_torch(z["rho"], dt, True)
+    x = torch.tensor(z["x"]).to(dt)
+    if z["variant"] == "batched":
+        hop = torch.tensor(z["dist_batch"]).long()           # -1 marks cross-graph / unreachable
+        cnt = None
+    else:
+        hop = gnan_lut.hops_from_reference(torch.tensor(z["node_distances"]))
+        cnt = gnan_lut.counts_from_hops(hop)
+        # the reference's normalisation matrix is exactly the gathered level sizes
+        idx = torch.where(hop < 0, torch.full_like(hop, cnt.shape[1] - 1), hop)
+        assert torch.equal(torch.gather(cnt, 1, idx).float(), torch.tensor(z["normalization_matrix"]))
+    rows = forward = None
+    if z["variant"] == "gnan_loop" and "node_ids" in z:
+        ids = torch.tensor(z["node_ids"])
+        hop, cnt = hop[ids], cnt[ids]
+    out = gnan_lut.forward_rows(fs, rho, x, hop, cnt, lut_mode(z))
+    if z["variant"] == "batched":
+        if z["is_graph_task"]:
+            B = int(z["batch_vector"].max()) + 1
+            out = torch.zeros(B, out.shape[1], dtype=dt).index_add(0, torch.tensor(z["batch_vector"]), out)
+    elif z["is_graph_task"]:
+        out = out.sum(0).view(-1, 1)
+    assert out.shape == z["out"].shape
+    assert G.rel_err(out.detach().numpy(), z["out"]) < TOL_LUT
+    (out * torch.tensor(z["out_weight"]).to(dt)).sum().backward()
+    check_grads(z, fs, "grad_fs", 2e-5)
+    check_grads(z, rho, "grad_rho", 2e-5)
+
+
+@pytest.mark.parametrize("name", G.PREPROCESS_CASES)
+def test_apsp_oracle_bit_exact(name):
+    z = G.load(name)
+    n = int(z["meta"][0])
+    node_task = bool(z["meta"][2])
+    ei = z["edge_index"].reshape(2, -1)
+    hop = oapsp.apsp(ei, n)
+    cnt = oapsp.level_counts(hop)
+    nd, nm = oapsp.reference_format(hop, cnt)
+    assert np.array_equal(nd, z["node_distances"])            # bit-exact float32
+    assert np.array_equal(nm, z["normalization_matrix"])
+    assert np.array_equal(z["x_out"][:, :-1], z["x"]) and np.all(z["x_out"][:, -1] == 1.0)   # :108 / :127
+    assert cnt.sum(axis=1).tolist() == [n] * n
+    del node_task
