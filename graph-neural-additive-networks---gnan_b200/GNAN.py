@@ -1,0 +1,108 @@
+"""Drop-in for the reference's GNAN.py: `TensorGNAN` (GNAN.py:9-79) and `GNAN` (GNAN.py:82-176) with the same
+constructor and forward signatures, computing on sm_100a kernels.
+
+    from gnan_b200.GNAN import GNAN, TensorGNAN      # instead of `from GNAN import GNAN, TensorGNAN`
+
+Semantics kept from the reference:
+  * TensorGNAN: rho has `out_channels` outputs; `normalize_rho` divides rho's INPUT (GNAN.py:65-67); rho has no bias
+    for graph tasks (:36-37); graph tasks return [C,1] (:76-79); init xavier_normal_(gain=0.01), zero biases (:49-53).
+  * GNAN: rho has 1 output unless `rho_per_feature`; `normalize_rho` divides rho's OUTPUT (:163-168); default
+    nn.Linear init; `forward(inputs, node_ids)` evaluates a row subset (:146-149).
+What differs: x and the distance data must end up on a CUDA device (no CPU path); dropout masks come from a
+counter-based generator (they cannot match torch's CPU stream; parity tests use p=0 / eval()).
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._inputs import resolve
+from ._stacked import StackedMLP
+
+
+class _Base(nn.Module):
+    precision = "fp32"      # "fp32" | "tf32x3" | "tf32": how the HxH hidden layers are contracted (see gnan_b200.h)
+
+    def _device(self):
+        return self.fs.wo.device
+
+    def _seed(self):
+        self._calls = getattr(self, "_calls", 0) + 1
+        return (torch.initial_seed() * 0x9E3779B97F4A7C15 + self._calls * 0xD1B54A32D192ED03) & (2 ** 63 - 1)
+
+    def _feature_sums(self, x):
+        if x.shape[1] != self.fs.groups:
+            raise ValueError(f"x has {x.shape[1]} features, model was built for {self.fs.groups}")
+        p = self.fs.dropout if self.training else 0.0
+        return ops.mlp(x, *self.fs.kernel_args(), dropout_p=p, seed=self._seed() if p > 0 else 0, precision=self.precision)
+
+    def _table(self, u):
+        """rho on a flat vector of scalar inputs -> [len(u), Cr]"""
+        return ops.mlp(u.reshape(-1, 1), *self.rho.kernel_args(), precision=self.precision)
+
+    def print_rho_params(self):
+        for name, param in self.rho.named_parameters():
+            print(name, param)
+
+
+class TensorGNAN(_Base):
+    def __init__(self, in_channels, out_channels, n_layers, hidden_channels=None, bias=True, dropout=0.0,
+                 device='cpu', rho_per_feature=False, normalize_rho=True, is_graph_task=False, readout_n_layers=1):
+        super().__init__()
+        self.device = device
+        self.out_channels = out_channels
+        self.hidden_channels = hidden_channels
+        self.n_layers = n_layers
+        self.bias = bias
+        self.dropout = dropout
+        self.rho_per_feature = rho_per_feature
+        self.normalize_rho = normalize_rho
+        self.is_graph_task = is_graph_task
+        self.fs = StackedMLP(in_channels, out_channels, n_layers, hidden_channels, bias, 3, dropout)
+        self.rho = StackedMLP(1, out_channels, n_layers, hidden_channels, not is_graph_task, 2, single=True)
+        self.fs.xavier_normal_(0.01)
+        self.rho.xavier_normal_(0.01)
+
+    def forward(self, inputs):
+        x, hd = resolve(inputs, self._device())
+        S = self._feature_sums(x)                                                    # [N,C]   GNAN.py:57-62 (+ :73 by linearity)
+        if self.normalize_rho:                                                       # GNAN.py:65-67: rho(nd / norm)
+            u = ops.rho_table_inputs(hd.nbins, x.device, cnt=hd.level_counts)        # [R,nbins]
+            T = self._table(u).view(hd.rows, hd.nbins, self.out_channels)
+            out = ops.aggregate_rows(hd.hop, T, S, per_row=True)
+        else:
+            T = self._table(ops.rho_table_inputs(hd.nbins, x.device))                # [nbins,C]
+            out = ops.aggregate_rows(hd.hop, T, S)
+        if self.is_graph_task:
+            out = out.sum(dim=0).view(1, -1).T                                        # [C,1]  GNAN.py:76-79
+        return out
+
+
+class GNAN(_Base):
+    def __init__(self, in_channels, out_channels, n_layers=None, hidden_channels=None, bias=True, dropout=0.0,
+                 device='cpu', normalize_rho=True, rho_per_feature=False, num_layers=None):
+        super().__init__()
+        if n_layers is None:
+            n_layers = num_layers                      # models.py:388 spells it num_layers (what main.py:79-83 passes)
+        if n_layers is None:
+            raise TypeError("n_layers (or num_layers) is required")
+        self.device = device
+        self.out_channels = out_channels
+        self.hidden_channels = hidden_channels
+        self.num_layers = n_layers
+        self.bias = bias
+        self.dropout = dropout
+        self.rho_per_feature = rho_per_feature
+        self.normalize_rho = normalize_rho
+        self.fs = StackedMLP(in_channels, out_channels, n_layers, hidden_channels, bias, 3, dropout)
+        self.rho = StackedMLP(1, out_channels if rho_per_feature else 1, n_layers, hidden_channels, bias, 2, single=True)
+
+    def forward(self, inputs, node_ids=None):
+        x, hd = resolve(inputs, self._device())
+        S = self._feature_sums(x)                                                    # f_sums, GNAN.py:150-157
+        T = self._table(ops.rho_table_inputs(hd.nbins, x.device))                    # [nbins,Cr]  rho(1/(1+d))
+        hop, cnt = hd.hop, hd.level_counts
+        if node_ids is not None:                                                     # row subset, GNAN.py:146-149
+            ids = torch.as_tensor(node_ids, device=x.device, dtype=torch.long)
+            hop, cnt = hop.index_select(0, ids), cnt.index_select(0, ids)
+        rs = ops.level_rscale(cnt) if self.normalize_rho else None                   # GNAN.py:163-168: rho(.) / norm
+        return ops.aggregate_rows(hop, T, S, rscale=rs)                              # [len(node_ids), C]

@@ -1,0 +1,32 @@
+// Error reporting, version and device queries of the C ABI (include/gnan_b200.h).
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void gnan_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int gnan_sm_count()
+{
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0)
+            n = v;
+        else
+            n = 148;
+    }
+    return n;
+}
+
+extern "C" const char *gnan_last_error(void) { return g_err; }
+extern "C" int gnan_version(void) { return GNAN_B200_VERSION; }

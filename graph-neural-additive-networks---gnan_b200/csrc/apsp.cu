@@ -1,0 +1,302 @@
+// All-pairs hop distances on the GPU (multi-source BFS) and the reference-format converters.
+//
+// Reference lines replaced: pre_process_datasets.py:109-121 / :128-140 (scipy dijkstra on unit weights + the per-element
+// Python normaliser loop) and batched_pyg_main.py:36-44 (networkx BFS per node).
+// Output: uint8 hop matrix (level, 255 = unreachable) and int32 level sizes cnt[i,d]; the reference's two fp32 [N,N]
+// matrices are node_distances = 1/(1+hop) and normalization_matrix = cnt[i, hop[i,j]] (gnan_hops_to_reference).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace {
+
+// ---- batched small graphs: one warp per graph, one lane per source, bitmask frontiers in registers ------------------
+constexpr int BW_MAX = 8;  // up to 256 nodes per graph
+
+__global__ void __launch_bounds__(256)
+apsp_batched_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, const int32_t *__restrict__ node_off,
+                    const int64_t *__restrict__ hop_off, int B, int max_n, uint8_t *__restrict__ hop, int32_t *__restrict__ cnt,
+                    int nbins, int32_t *__restrict__ overflow)
+{
+    extern __shared__ uint32_t sadj[];  // [8 warps][max_n][Wmax]
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int Wmax = (max_n + 31) / 32;
+    uint32_t *adj = sadj + (size_t)w * max_n * Wmax;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t b = warp; b < B; b += nwarps) {
+        const int n0 = node_off[b], n = node_off[b + 1] - n0;
+        const int W = (n + 31) / 32;
+        uint8_t *hb = hop + hop_off[b];
+        __syncwarp();
+        for (int v = lane; v < n; v += 32) {
+            for (int ww = 0; ww < W; ++ww) adj[v * W + ww] = 0u;
+            for (int e = rowptr[n0 + v]; e < rowptr[n0 + v + 1]; ++e) {
+                const int t = col[e] - n0;
+                if (t >= 0 && t < n) adj[v * W + (t >> 5)] |= 1u << (t & 31);
+            }
+        }
+        __syncwarp();
+        for (int s = lane; s < n; s += 32) {
+            uint32_t vis[BW_MAX], fr[BW_MAX], nx[BW_MAX];
+#pragma unroll
+            for (int ww = 0; ww < BW_MAX; ++ww) { vis[ww] = 0u; fr[ww] = 0u; }
+#pragma unroll
+            for (int ww = 0; ww < BW_MAX; ++ww)
+                if (ww == (s >> 5)) { vis[ww] = 1u << (s & 31); fr[ww] = vis[ww]; }
+            uint8_t *row = hb + (size_t)s * n;
+            for (int v = 0; v < n; ++v) row[v] = GNAN_HOP_UNREACHABLE;
+            row[s] = 0;
+            int32_t *crow = cnt ? cnt + (int64_t)(n0 + s) * nbins : nullptr;
+            if (crow) {
+                for (int d = 0; d < nbins; ++d) crow[d] = 0;
+                crow[0] = 1;
+            }
+            int reached = 1;
+            for (int level = 1; level <= n; ++level) {
+#pragma unroll
+                for (int ww = 0; ww < BW_MAX; ++ww) nx[ww] = 0u;
+#pragma unroll
+                for (int fw = 0; fw < BW_MAX; ++fw) {
+                    if (fw < W) {
+                        uint32_t m = fr[fw];
+                        while (m) {
+                            const int v = fw * 32 + __ffs(m) - 1;
+                            m &= m - 1;
+#pragma unroll
+                            for (int ww = 0; ww < BW_MAX; ++ww)
+                                if (ww < W) nx[ww] |= adj[v * W + ww];
+                        }
+                    }
+                }
+                int newc = 0;
+#pragma unroll
+                for (int ww = 0; ww < BW_MAX; ++ww) {
+                    nx[ww] &= ~vis[ww];
+                    vis[ww] |= nx[ww];
+                    newc += __popc(nx[ww]);
+                }
+                if (newc == 0) break;
+                if (level > 254 || level >= nbins - 1) { atomicExch(overflow, 1); }
+                const uint8_t lv = (uint8_t)min(level, 254);
+#pragma unroll
+                for (int ww = 0; ww < BW_MAX; ++ww) {
+                    uint32_t m = nx[ww];
+                    while (m) {
+                        row[ww * 32 + __ffs(m) - 1] = lv;
+                        m &= m - 1;
+                    }
+                    fr[ww] = nx[ww];
+                }
+                if (crow && level < nbins - 1) crow[level] = newc;
+                reached += newc;
+            }
+            if (crow) crow[nbins - 1] = n - reached;
+        }
+    }
+}
+
+// ---- one large graph: one warp per source, queue + bitmap in the workspace -----------------------------------------
+__global__ void __launch_bounds__(256)
+apsp_bfs_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, int N, int src_begin, int src_end,
+                uint8_t *__restrict__ hop, int64_t ld, int32_t *__restrict__ cnt, int nbins, int32_t *__restrict__ overflow,
+                int32_t *__restrict__ queues, uint32_t *__restrict__ bitmaps, int bm_words, int64_t nwarps)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp >= nwarps) return;  // queues / bitmaps are sized for nwarps warps
+    int32_t *q = queues + warp * (int64_t)N;
+    uint32_t *bm = bitmaps + warp * (int64_t)bm_words;
+    for (int64_t s = src_begin + warp; s < src_end; s += nwarps) {
+        uint8_t *row = hop + (s - src_begin) * ld;
+        for (int64_t v = lane * 16; v < ld; v += 512)
+            *reinterpret_cast<uint4 *>(row + v) = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        for (int t = lane; t < bm_words; t += 32) bm[t] = 0u;
+        int32_t *crow = cnt ? cnt + (s - src_begin) * nbins : nullptr;
+        if (crow)
+            for (int d = lane; d < nbins; d += 32) crow[d] = 0;
+        __syncwarp();
+        if (lane == 0) {
+            q[0] = (int32_t)s;
+            bm[s >> 5] = 1u << (s & 31);
+            row[s] = 0;
+            if (crow) crow[0] = 1;
+        }
+        __syncwarp();
+        int head = 0, tail = 1, level = 0;
+        while (head < tail) {
+            ++level;
+            const uint8_t lv = (uint8_t)min(level, 254);
+            int new_tail = tail;
+            for (int base = head; base < tail; base += 32) {
+                const int idx = base + lane;
+                int e0 = 0, e1 = 0;
+                if (idx < tail) {
+                    const int v = q[idx];
+                    e0 = rowptr[v];
+                    e1 = rowptr[v + 1];
+                }
+                // lanes walk their own adjacency lists; claims go through the warp-private bitmap
+                int maxdeg = e1 - e0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, o));
+                for (int k = 0; k < maxdeg; ++k) {
+                    bool won = false;
+                    int t = -1;
+                    if (e0 + k < e1) {
+                        t = col[e0 + k];
+                        const uint32_t bit = 1u << (t & 31);
+                        const uint32_t old = atomicOr(bm + (t >> 5), bit);
+                        won = !(old & bit);
+                    }
+                    const uint32_t mask = __ballot_sync(0xffffffffu, won);
+                    if (won) {
+                        q[new_tail + __popc(mask & ((1u << lane) - 1))] = t;
+                        row[t] = lv;
+                    }
+                    new_tail += __popc(mask);
+                }
+            }
+            __syncwarp();
+            const int newc = new_tail - tail;
+            if (newc > 0) {
+                if (lane == 0) {
+                    if (level > 254 || level >= nbins - 1) atomicExch(overflow, 1);
+                    else if (crow) crow[level] = newc;
+                }
+            }
+            head = tail;
+            tail = new_tail;
+        }
+        if (lane == 0 && crow) crow[nbins - 1] = N - tail;
+        __syncwarp();
+    }
+}
+
+// ---- converters ------------------------------------------------------------------------------------------------------
+__global__ void hops_to_reference_kernel(const uint8_t *__restrict__ hop, int64_t R, int64_t N, int64_t ld,
+                                         const int32_t *__restrict__ cnt, int nbins, float *__restrict__ nd, float *__restrict__ nm)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= R * N) return;
+    const int64_t i = t / N, j = t % N;
+    const int h = hop[i * ld + j];
+    if (nd) nd[t] = h == GNAN_HOP_UNREACHABLE ? 0.f : 1.0f / ((float)h + 1.0f);
+    if (nm) nm[t] = (float)cnt[i * nbins + min(h, nbins - 1)];
+}
+
+__global__ void hops_from_reference_kernel(const float *__restrict__ nd, const float *__restrict__ nm, int64_t R, int64_t N,
+                                           uint8_t *__restrict__ hop, int64_t ld, int32_t *__restrict__ cnt, int nbins,
+                                           int32_t *__restrict__ overflow)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= R * ld) return;
+    const int64_t i = t / ld, j = t % ld;
+    if (j >= N) { hop[t] = GNAN_HOP_UNREACHABLE; return; }
+    const float v = nd[i * N + j];
+    int h = GNAN_HOP_UNREACHABLE;
+    if (v > 0.f) {
+        const float hf = rintf(1.0f / v - 1.0f);
+        if (hf > 254.f || hf >= (float)(nbins - 1)) { atomicExch(overflow, 1); h = 254; }
+        else h = (int)hf;
+    }
+    hop[t] = (uint8_t)h;
+    if (cnt) {
+        const int b = min(h, nbins - 1);
+        if (nm) cnt[i * nbins + b] = (int32_t)rintf(nm[i * N + j]);   // every writer of a bin stores the same value
+        else atomicAdd(cnt + i * nbins + b, 1);
+    }
+}
+
+}  // namespace
+
+extern "C" size_t gnan_apsp_bfs_workspace_bytes(int32_t N, int32_t n_sources)
+{
+    if (N <= 0 || n_sources <= 0) return 0;
+    const int64_t nwarps = std::min<int64_t>(n_sources, (int64_t)gnan_sm_count() * 8);
+    const int64_t bm_words = (N + 31) / 32;
+    return (size_t)nwarps * ((size_t)N * 4 + (size_t)bm_words * 4);
+}
+
+extern "C" int gnan_apsp_bfs(const int32_t *rowptr, const int32_t *col, int32_t N, int32_t src_begin, int32_t src_end,
+                             uint8_t *hop, int64_t ld_hop, int32_t *cnt, int32_t nbins, int32_t *overflow_flag,
+                             void *workspace, size_t workspace_bytes, gnan_stream_t stream)
+{
+    GNAN_REQUIRE(N >= 0 && src_begin >= 0 && src_end >= src_begin && src_end <= N, "apsp_bfs: bad source range [%d,%d) N=%d", src_begin, src_end, N);
+    const int ns = src_end - src_begin;
+    if (ns == 0) return GNAN_OK;
+    GNAN_REQUIRE(rowptr && hop && overflow_flag, "apsp_bfs: NULL pointer");
+    GNAN_REQUIRE(ld_hop >= N && ld_hop % 16 == 0 && ((uintptr_t)hop % 16) == 0, "apsp_bfs: hop rows must be 16-byte aligned, ld %% 16 == 0");
+    GNAN_REQUIRE(!cnt || (nbins >= 2 && nbins <= 256), "apsp_bfs: nbins %d out of [2,256]", nbins);
+    const size_t need = gnan_apsp_bfs_workspace_bytes(N, ns);
+    if (!workspace || workspace_bytes < need) {
+        gnan_set_error("apsp_bfs: workspace %zu < %zu bytes", workspace_bytes, need);
+        return GNAN_ERR_WORKSPACE;
+    }
+    const int64_t nwarps = std::min<int64_t>(ns, (int64_t)gnan_sm_count() * 8);
+    const int bm_words = (N + 31) / 32;
+    int32_t *queues = (int32_t *)workspace;
+    uint32_t *bitmaps = (uint32_t *)(queues + nwarps * (int64_t)N);
+    const int blocks = (int)ceil_div64(nwarps, 8);
+    apsp_bfs_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rowptr, col, N, src_begin, src_end, hop, ld_hop, cnt,
+                                                               cnt ? nbins : 256, overflow_flag, queues, bitmaps, bm_words, nwarps);
+    GNAN_LAUNCH_OK();
+    return GNAN_OK;
+}
+
+// max_n is needed to size shared memory; exported variant with it explicit (the header-declared entry derives it on the host side)
+extern "C" int gnan_apsp_bfs_batched_n(const int32_t *rowptr, const int32_t *col, const int32_t *node_off, const int64_t *hop_off,
+                                       int32_t B, int32_t max_n, uint8_t *hop, int32_t *cnt, int32_t nbins,
+                                       int32_t *overflow_flag, gnan_stream_t stream)
+{
+    GNAN_REQUIRE(B >= 0, "apsp_bfs_batched: negative batch");
+    if (B == 0) return GNAN_OK;
+    GNAN_REQUIRE(rowptr && node_off && hop_off && hop && overflow_flag, "apsp_bfs_batched: NULL pointer");
+    GNAN_REQUIRE(!cnt || (nbins >= 2 && nbins <= 256), "apsp_bfs_batched: nbins %d out of [2,256]", nbins);
+    if (max_n < 1 || max_n > 32 * BW_MAX) {
+        gnan_set_error("apsp_bfs_batched: graphs with %d nodes unsupported (1..%d); use gnan_apsp_bfs", max_n, 32 * BW_MAX);
+        return GNAN_ERR_UNSUPPORTED;
+    }
+    const size_t smem = sizeof(uint32_t) * 8 * (size_t)max_n * ((max_n + 31) / 32);
+    GNAN_CUDA(cudaFuncSetAttribute(apsp_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int blocks = (int)std::min<int64_t>(ceil_div64(B, 8), 16 * gnan_sm_count());
+    apsp_batched_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(rowptr, col, node_off, hop_off, B, max_n, hop, cnt,
+                                                                     cnt ? nbins : 256, overflow_flag);
+    GNAN_LAUNCH_OK();
+    return GNAN_OK;
+}
+
+extern "C" int gnan_apsp_bfs_batched(const int32_t *rowptr, const int32_t *col, const int32_t *node_off, const int64_t *hop_off,
+                                     int32_t B, uint8_t *hop, int32_t *cnt, int32_t nbins, int32_t *overflow_flag,
+                                     gnan_stream_t stream)
+{
+    // without a host-side size hint assume the largest supported graph
+    return gnan_apsp_bfs_batched_n(rowptr, col, node_off, hop_off, B, 32 * BW_MAX, hop, cnt, nbins, overflow_flag, stream);
+}
+
+extern "C" int gnan_hops_to_reference(const uint8_t *hop, int64_t R, int64_t N, int64_t ld_hop, const int32_t *cnt,
+                                      int32_t nbins, float *node_distances, float *normalization_matrix, gnan_stream_t stream)
+{
+    GNAN_REQUIRE(R >= 0 && N >= 0 && ld_hop >= N, "hops_to_reference: bad shape");
+    if (R * N == 0) return GNAN_OK;
+    GNAN_REQUIRE(hop && (node_distances || normalization_matrix), "hops_to_reference: NULL pointer");
+    GNAN_REQUIRE(!normalization_matrix || (cnt && nbins >= 2), "hops_to_reference: cnt required for the normalisation matrix");
+    hops_to_reference_kernel<<<(unsigned)ceil_div64(R * N, 256), 256, 0, (cudaStream_t)stream>>>(hop, R, N, ld_hop, cnt, nbins,
+                                                                                                  node_distances, normalization_matrix);
+    GNAN_LAUNCH_OK();
+    return GNAN_OK;
+}
+
+extern "C" int gnan_hops_from_reference(const float *node_distances, const float *normalization_matrix, int64_t R, int64_t N,
+                                        uint8_t *hop, int64_t ld_hop, int32_t *cnt, int32_t nbins, int32_t *overflow_flag,
+                                        gnan_stream_t stream)
+{
+    GNAN_REQUIRE(R >= 0 && N >= 0 && ld_hop >= N, "hops_from_reference: bad shape");
+    if (R * N == 0) return GNAN_OK;
+    GNAN_REQUIRE(node_distances && hop && overflow_flag, "hops_from_reference: NULL pointer");
+    GNAN_REQUIRE(nbins >= 2 && nbins <= 256, "hops_from_reference: nbins %d out of [2,256]", nbins);
+    hops_from_reference_kernel<<<(unsigned)ceil_div64(R * ld_hop, 256), 256, 0, (cudaStream_t)stream>>>(
+        node_distances, normalization_matrix, R, N, hop, ld_hop, cnt, nbins, overflow_flag);
+    GNAN_LAUNCH_OK();
+    return GNAN_OK;
+}

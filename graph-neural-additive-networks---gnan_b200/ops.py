@@ -1,0 +1,274 @@
+"""torch.library ops over the C ABI (include/gnan_b200.h). Each op is a thin ctypes call on raw device pointers and the
+current stream; autograd is wired with register_autograd so the nn.Modules in modules.py compose them like any torch op.
+
+Nothing here computes on the CPU: non-CUDA inputs raise (see _lib.ptr)."""
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._lib import MlpGrads, MlpParams, check, load, ptr, stream_handle
+
+__all__ = ["mlp", "aggregate_rows", "aggregate_blockdiag", "rho_table_inputs", "level_rscale", "alloc_hop", "hop_ld"]
+
+
+def hop_ld(n: int) -> int:
+    """leading dimension (bytes per row) of a hop block with n columns: rows are 16-byte aligned for 128-bit loads"""
+    return max(16, (int(n) + 15) // 16 * 16)
+
+
+def alloc_hop(rows: int, n: int, device) -> Tensor:
+    return torch.full((rows, hop_ld(n)), _lib.HOP_UNREACHABLE, dtype=torch.uint8, device=device)
+
+
+def _ws(nbytes: int, device) -> Optional[Tensor]:
+    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+
+
+def _f32(t: Tensor, name: str) -> Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _mlp_params(w1, b1, wh, bh, wo, bo, n_layers):
+    G, C = wo.shape[0], wo.shape[1]
+    H = wo.shape[2] if n_layers >= 2 else 0
+    p = MlpParams(G, H, C, n_layers, ptr(w1), ptr(b1), ptr(wh), ptr(bh), ptr(wo), ptr(bo))
+    return p, G, H, C
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# grouped scalar-input MLP:  S[r,:] = sum_g f_g(u[r,g])
+# ---------------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("gnan_b200::mlp_fwd", mutates_args=())
+def mlp_fwd(u: Tensor, w1: Tensor, b1: Tensor, wh: Tensor, bh: Tensor, wo: Tensor, bo: Tensor, n_layers: int,
+            dropout_p: float, seed: int, precision: int) -> Tensor:
+    lib = load()
+    u, w1, b1, wh, bh, wo, bo = (_f32(t, n) for t, n in zip((u, w1, b1, wh, bh, wo, bo), "u w1 b1 wh bh wo bo".split()))
+    if u.dim() != 2 or u.shape[1] != wo.shape[0]:
+        raise ValueError(f"u must be [R,G] with G={wo.shape[0]}, got {tuple(u.shape)}")
+    p, G, H, C = _mlp_params(w1, b1, wh, bh, wo, bo, n_layers)
+    R = u.shape[0]
+    S = torch.empty(R, C, dtype=torch.float32, device=u.device)
+    ws = _ws(lib.gnan_mlp_workspace_bytes(R, p, 0, precision), u.device)
+    check(lib.gnan_mlp_fwd(ptr(u), R, u.shape[1], p, float(dropout_p), int(seed) & (2 ** 64 - 1), precision, ptr(S), ptr(ws),
+                           ws.numel(), stream_handle()), "gnan_mlp_fwd")
+    return S
+
+
+@mlp_fwd.register_fake
+def _(u, w1, b1, wh, bh, wo, bo, n_layers, dropout_p, seed, precision):
+    return u.new_empty(u.shape[0], wo.shape[1])
+
+
+@torch.library.custom_op("gnan_b200::mlp_bwd", mutates_args=())
+def mlp_bwd(u: Tensor, w1: Tensor, b1: Tensor, wh: Tensor, bh: Tensor, wo: Tensor, bo: Tensor, n_layers: int,
+            dropout_p: float, seed: int, precision: int, dS: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    lib = load()
+    u, w1, b1, wh, bh, wo, bo, dS = (_f32(t, n) for t, n in zip((u, w1, b1, wh, bh, wo, bo, dS), "u w1 b1 wh bh wo bo dS".split()))
+    p, G, H, C = _mlp_params(w1, b1, wh, bh, wo, bo, n_layers)
+    R = u.shape[0]
+    outs = [torch.empty_like(t) for t in (w1, b1, wh, bh, wo, bo)]
+    g = MlpGrads(*[ptr(t) for t in outs])
+    ws = _ws(lib.gnan_mlp_workspace_bytes(R, p, 1, precision), u.device)
+    check(lib.gnan_mlp_bwd(ptr(u), R, u.shape[1], p, float(dropout_p), int(seed) & (2 ** 64 - 1), precision, ptr(dS),
+                           g, ptr(ws), ws.numel(), stream_handle()), "gnan_mlp_bwd")
+    return tuple(outs)
+
+
+@mlp_bwd.register_fake
+def _(u, w1, b1, wh, bh, wo, bo, n_layers, dropout_p, seed, precision, dS):
+    return tuple(torch.empty_like(t) for t in (w1, b1, wh, bh, wo, bo))
+
+
+def _mlp_setup(ctx, inputs, output):
+    u, w1, b1, wh, bh, wo, bo, n_layers, dropout_p, seed, precision = inputs
+    ctx.save_for_backward(u, w1, b1, wh, bh, wo, bo)
+    ctx.cfg = (n_layers, dropout_p, seed, precision)
+
+
+def _mlp_backward(ctx, dS):
+    u, w1, b1, wh, bh, wo, bo = ctx.saved_tensors
+    n_layers, dropout_p, seed, precision = ctx.cfg
+    g = mlp_bwd(u, w1, b1, wh, bh, wo, bo, n_layers, dropout_p, seed, precision, dS.contiguous())
+    return (None,) + tuple(g) + (None, None, None, None)
+
+
+mlp_fwd.register_autograd(_mlp_backward, setup_context=_mlp_setup)
+
+
+def mlp(u, w1, b1, wh, bh, wo, bo, n_layers, dropout_p=0.0, seed=0, precision="fp32"):
+    """S[r,:] = sum_g f_g(u[r,g]); differentiable w.r.t. the weights (not u: inputs are data, GNAN.py:56)."""
+    return mlp_fwd(u, w1, b1, wh, bh, wo, bo, int(n_layers), float(dropout_p), int(seed), _lib.PRECISIONS[precision])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# dense row-block aggregation
+# ---------------------------------------------------------------------------------------------------------------------
+def _agg_dims(hop, T, S, per_row):
+    if hop.dtype != torch.uint8 or hop.dim() != 2:
+        raise TypeError("hop must be a uint8 [R, ld] matrix")
+    R, ld = hop.shape
+    N, C = S.shape
+    nbins, Cr = T.shape[-2], T.shape[-1]
+    if per_row and (T.dim() != 3 or T.shape[0] != R):
+        raise ValueError(f"per-row table must be [R,nbins,Cr], got {tuple(T.shape)}")
+    if not per_row and T.dim() != 2:
+        raise ValueError(f"global table must be [nbins,Cr], got {tuple(T.shape)}")
+    return R, ld, N, C, nbins, Cr
+
+
+@torch.library.custom_op("gnan_b200::agg_rows_fwd", mutates_args=())
+def agg_rows_fwd(hop: Tensor, T: Tensor, rscale: Optional[Tensor], S: Tensor, per_row: bool, save: bool) -> Tuple[Tensor, Tensor]:
+    lib = load()
+    T, S = _f32(T, "T"), _f32(S, "S")
+    rscale = None if rscale is None else _f32(rscale, "rscale")
+    R, ld, N, C, nbins, Cr = _agg_dims(hop, T, S, per_row)
+    out = torch.empty(R, C, dtype=torch.float32, device=S.device)
+    bsum = torch.empty((R, nbins, C) if save else (0,), dtype=torch.float32, device=S.device)
+    check(lib.gnan_aggregate_rows_fwd_save(ptr(hop), R, N, ld, ptr(T), int(per_row), nbins, Cr, ptr(rscale), ptr(S), C,
+                                           ptr(out), ptr(bsum), stream_handle()), "gnan_aggregate_rows_fwd")
+    return out, bsum
+
+
+@agg_rows_fwd.register_fake
+def _(hop, T, rscale, S, per_row, save):
+    R, C, nbins = hop.shape[0], S.shape[1], T.shape[-2]
+    return S.new_empty(R, C), S.new_empty((R, nbins, C) if save else (0,))
+
+
+@torch.library.custom_op("gnan_b200::agg_rows_bwd", mutates_args=())
+def agg_rows_bwd(hop: Tensor, T: Tensor, rscale: Optional[Tensor], S: Tensor, per_row: bool, g: Tensor,
+                 bsum: Tensor) -> Tuple[Tensor, Tensor]:
+    lib = load()
+    T, S, g = _f32(T, "T"), _f32(S, "S"), _f32(g, "g")
+    rscale = None if rscale is None else _f32(rscale, "rscale")
+    R, ld, N, C, nbins, Cr = _agg_dims(hop, T, S, per_row)
+    dS = torch.empty_like(S)
+    dT = torch.empty_like(T)
+    ws = _ws(lib.gnan_aggregate_rows_bwd_workspace_bytes(R, N, nbins, Cr, C), S.device)
+    check(lib.gnan_aggregate_rows_bwd_saved(ptr(hop), R, N, ld, ptr(T), int(per_row), nbins, Cr, ptr(rscale), ptr(S), C,
+                                            ptr(g), ptr(bsum) if bsum.numel() else None, ptr(dS), ptr(dT), ptr(ws),
+                                            ws.numel(), stream_handle()), "gnan_aggregate_rows_bwd")
+    return dS, dT
+
+
+@agg_rows_bwd.register_fake
+def _(hop, T, rscale, S, per_row, g, bsum):
+    return torch.empty_like(S), torch.empty_like(T)
+
+
+def _agg_setup(ctx, inputs, output):
+    hop, T, rscale, S, per_row, save = inputs
+    ctx.save_for_backward(hop, T, rscale, S, output[1])
+    ctx.per_row = per_row
+
+
+def _agg_backward(ctx, g, _g_bsum):
+    hop, T, rscale, S, bsum = ctx.saved_tensors
+    dS, dT = agg_rows_bwd(hop, T, rscale, S, ctx.per_row, g.contiguous(), bsum)
+    return None, dT, None, dS, None, None
+
+
+agg_rows_fwd.register_autograd(_agg_backward, setup_context=_agg_setup)
+
+
+def aggregate_rows(hop, T, S, rscale=None, per_row=False):
+    """out[i,c] = sum_j T[(i,) b(hop[i,j]), c'] * rscale[i,b] * S[j,c] over a [R, ld] uint8 hop block; see gnan_b200.h."""
+    save = torch.is_grad_enabled() and (T.requires_grad or S.requires_grad)
+    return agg_rows_fwd(hop, T, rscale, S, bool(per_row), bool(save))[0]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# block-diagonal (batched graphs) aggregation
+# ---------------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("gnan_b200::agg_blockdiag_fwd", mutates_args=())
+def agg_blockdiag_fwd(hop: Tensor, hop_off: Tensor, node_off: Tensor, T: Tensor, rscale: Optional[Tensor], S: Tensor,
+                      per_row: bool, reduce_graph: bool) -> Tensor:
+    lib = load()
+    T, S = _f32(T, "T"), _f32(S, "S")
+    rscale = None if rscale is None else _f32(rscale, "rscale")
+    if hop.dtype != torch.uint8 or hop_off.dtype != torch.int64 or node_off.dtype != torch.int32:
+        raise TypeError("hop uint8, hop_off int64, node_off int32 expected")
+    B = node_off.numel() - 1
+    N, C = S.shape
+    nbins, Cr = T.shape[-2], T.shape[-1]
+    out = torch.empty(B if reduce_graph else N, C, dtype=torch.float32, device=S.device)
+    check(lib.gnan_aggregate_blockdiag_fwd(ptr(hop), ptr(hop_off), ptr(node_off), B, ptr(T), int(per_row), nbins, Cr,
+                                           ptr(rscale), ptr(S), C, int(reduce_graph), ptr(out), stream_handle()),
+          "gnan_aggregate_blockdiag_fwd")
+    return out
+
+
+@agg_blockdiag_fwd.register_fake
+def _(hop, hop_off, node_off, T, rscale, S, per_row, reduce_graph):
+    return S.new_empty(node_off.numel() - 1 if reduce_graph else S.shape[0], S.shape[1])
+
+
+@torch.library.custom_op("gnan_b200::agg_blockdiag_bwd", mutates_args=())
+def agg_blockdiag_bwd(hop: Tensor, hop_off: Tensor, node_off: Tensor, T: Tensor, rscale: Optional[Tensor], S: Tensor,
+                      per_row: bool, reduce_graph: bool, g: Tensor) -> Tuple[Tensor, Tensor]:
+    lib = load()
+    T, S, g = _f32(T, "T"), _f32(S, "S"), _f32(g, "g")
+    rscale = None if rscale is None else _f32(rscale, "rscale")
+    B = node_off.numel() - 1
+    N, C = S.shape
+    nbins, Cr = T.shape[-2], T.shape[-1]
+    dS = torch.zeros_like(S)
+    dT = torch.zeros_like(T)
+    check(lib.gnan_aggregate_blockdiag_bwd(ptr(hop), ptr(hop_off), ptr(node_off), B, ptr(T), int(per_row), nbins, Cr,
+                                           ptr(rscale), ptr(S), C, int(reduce_graph), ptr(g), ptr(dS), ptr(dT),
+                                           stream_handle()), "gnan_aggregate_blockdiag_bwd")
+    return dS, dT
+
+
+@agg_blockdiag_bwd.register_fake
+def _(hop, hop_off, node_off, T, rscale, S, per_row, reduce_graph, g):
+    return torch.empty_like(S), torch.empty_like(T)
+
+
+def _bd_setup(ctx, inputs, output):
+    hop, hop_off, node_off, T, rscale, S, per_row, reduce_graph = inputs
+    ctx.save_for_backward(hop, hop_off, node_off, T, rscale, S)
+    ctx.flags = (per_row, reduce_graph)
+
+
+def _bd_backward(ctx, g):
+    hop, hop_off, node_off, T, rscale, S = ctx.saved_tensors
+    dS, dT = agg_blockdiag_bwd(hop, hop_off, node_off, T, rscale, S, ctx.flags[0], ctx.flags[1], g.contiguous())
+    return None, None, None, dT, None, dS, None, None
+
+
+agg_blockdiag_fwd.register_autograd(_bd_backward, setup_context=_bd_setup)
+
+
+def aggregate_blockdiag(hop, hop_off, node_off, T, S, rscale=None, per_row=False, reduce_graph=True):
+    return agg_blockdiag_fwd(hop, hop_off, node_off, T, rscale, S, bool(per_row), bool(reduce_graph))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# table inputs (no autograd: functions of the integer level counts only)
+# ---------------------------------------------------------------------------------------------------------------------
+def rho_table_inputs(nbins: int, device, cnt: Optional[Tensor] = None, raw: bool = False) -> Tensor:
+    """u[d] (global, [nbins]) or u[i,d] ([rows,nbins], divided by cnt): the scalar inputs rho is evaluated on."""
+    lib = load()
+    rows = 0 if cnt is None else cnt.shape[0]
+    if cnt is not None and (cnt.dtype != torch.int32 or cnt.shape[1] != nbins):
+        raise TypeError("cnt must be int32 [rows,nbins]")
+    u = torch.empty((max(rows, 1), nbins) if cnt is not None else (nbins,), dtype=torch.float32, device=device)
+    if cnt is not None and rows == 0:
+        return u[:0]
+    check(lib.gnan_rho_table_inputs(ptr(cnt.contiguous()) if cnt is not None else None, rows, nbins, int(raw), ptr(u),
+                                    stream_handle()), "gnan_rho_table_inputs")
+    return u
+
+
+def level_rscale(cnt: Tensor) -> Tensor:
+    lib = load()
+    if cnt.dtype != torch.int32 or cnt.dim() != 2:
+        raise TypeError("cnt must be int32 [rows,nbins]")
+    rs = torch.empty(cnt.shape, dtype=torch.float32, device=cnt.device)
+    check(lib.gnan_level_rscale(ptr(cnt.contiguous()), cnt.shape[0], cnt.shape[1], ptr(rs), stream_handle()), "gnan_level_rscale")
+    return rs

@@ -1,0 +1,186 @@
+/*
+ * gnan_b200 — C ABI of the B200 (sm_100a) GNAN hot path.
+ *
+ * The reference (mayabechlerspeicher/Graph-Neural-Additive-Networks---GNAN) is pure Python/PyTorch and
+ * defines no FFI of its own: the "plugin boundary" upstream is the nn.Module. This header
+ * is the boundary a maintainer binds instead of the stock ATen ops the reference modules run; each entry
+ * point names the reference lines it replaces. INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller (PyTorch) owns all
+ *     memory, the library never allocates, frees or retains a pointer;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - return value: GNAN_OK or an error code; gnan_last_error() returns a thread-local message;
+ *   - float tensors are contiguous fp32 row-major unless a leading dimension is given;
+ *   - no CPU fallback: a call on a machine without an sm_100 device fails with GNAN_ERR_CUDA.
+ */
+#ifndef GNAN_B200_H
+#define GNAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GNAN_B200_VERSION 100
+
+enum {
+    GNAN_OK = 0,
+    GNAN_ERR_INVALID = 1,     /* bad argument (shape, alignment, null pointer) */
+    GNAN_ERR_UNSUPPORTED = 2, /* valid but not implemented for this shape (e.g. hidden width) */
+    GNAN_ERR_CUDA = 3,        /* a CUDA runtime call failed; message has cudaGetErrorString */
+    GNAN_ERR_WORKSPACE = 4    /* workspace too small; query the matching *_workspace_bytes */
+};
+
+#define GNAN_HOP_UNREACHABLE 255 /* byte value of an unreachable / masked pair in a hop matrix */
+
+typedef void *gnan_stream_t;
+
+int gnan_version(void);
+const char *gnan_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Grouped scalar-input MLPs: G independent networks  R -> R^C,
+ *     Linear(1,H) ReLU [Dropout]  ( Linear(H,H) ReLU [Dropout] ) x n_hidden   Linear(H,C)
+ * n_layers = n_hidden + 2;  n_layers == 1 is the single Linear(1,C) (w1/b1/wh/bh unused, H ignored).
+ * Used for the K shape functions f_k (G = K, GNAN.py:24-34, models.py:321-331) and, with G = 1 and no
+ * dropout, for the distance function rho evaluated on a table of inputs (GNAN.py:38-47).
+ * Weight layout = torch.nn.Linear's [out,in], stacked over groups. Bias pointers may be NULL (bias=False).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t G, H, C, n_layers;
+    const float *w1; /* [G,H]            Linear(1,H).weight[:,0] */
+    const float *b1; /* [G,H] or NULL */
+    const float *wh; /* [n_hidden,G,H,H] */
+    const float *bh; /* [n_hidden,G,H] or NULL */
+    const float *wo; /* [G,C,H]  ([G,C,1] when n_layers == 1) */
+    const float *bo; /* [G,C] or NULL */
+} gnan_mlp_params;
+
+typedef struct { /* gradient outputs, same shapes; NULL = not wanted. Overwritten, not accumulated. */
+    float *w1, *b1, *wh, *bh, *wo, *bo;
+} gnan_mlp_grads;
+
+/* precision: how the HxH hidden contractions are computed */
+enum {
+    GNAN_PREC_FP32 = 0,     /* FFMA, fp32 throughout (bit-for-bit deterministic) */
+    GNAN_PREC_TF32X3 = 1,   /* tcgen05 kind::tf32, 3-term split (hi*hi + lo*hi + hi*lo), fp32 accumulate in TMEM:
+                               fp32-level accuracy (~1e-6 norm-wise); needs H == 64 */
+    GNAN_PREC_TF32 = 2      /* tcgen05 single-pass tf32 (~1e-3), stated looser bound */
+};
+
+size_t gnan_mlp_workspace_bytes(int64_t R, const gnan_mlp_params *p, int backward, int precision);
+
+/* S[r,:] = sum_g f_g(u[r*ldu + g])   (replaces the K-iteration module loop + slice assignment + feature sum:
+ * GNAN.py:57-62,157; models.py:360-365,455-460; batched_pyg_main.py:144-148,170).
+ * dropout_p > 0 applies inverted dropout after every hidden ReLU with a counter-based mask keyed on
+ * (seed, layer, group, row, unit); the same (dropout_p, seed) must be passed to gnan_mlp_bwd. */
+int gnan_mlp_fwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *p, float dropout_p, uint64_t seed,
+                 int precision, float *S /* [R,C] */, void *workspace, size_t workspace_bytes, gnan_stream_t stream);
+
+/* gradients of all weights given dS [R,C] (replaces autograd through the same lines; trainer.py:66).
+ * Activations are recomputed, nothing is saved by the forward. */
+int gnan_mlp_bwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *p, float dropout_p, uint64_t seed,
+                 int precision, const float *dS /* [R,C] */, const gnan_mlp_grads *grads, void *workspace,
+                 size_t workspace_bytes, gnan_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Distance-table inputs. u[i,d] = 1/(1+d) for d < nbins-1, 0 for the unreachable bin (nbins-1);
+ * with cnt != NULL divided by cnt[i,d] (GNAN.py:65-66: node_distances / normalization_matrix).
+ * raw != 0 writes u[d] = d instead (batched_pyg_main.py:154: rho is fed raw hop counts).
+ * rows == 0 / cnt == NULL -> one global row [nbins].
+ * ---------------------------------------------------------------------------------------------- */
+int gnan_rho_table_inputs(const int32_t *cnt /* [rows,nbins] or NULL */, int64_t rows, int32_t nbins, int raw,
+                          float *u /* [max(rows,1), nbins] */, gnan_stream_t stream);
+
+/* rscale[i,d] = 1/cnt[i,d] (0 where cnt == 0): the output normaliser of models.py:368-370 / GNAN.py:163-168 */
+int gnan_level_rscale(const int32_t *cnt, int64_t rows, int32_t nbins, float *rscale, gnan_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Aggregation over a dense row block of the uint8 hop matrix (node-level tasks):
+ *     out[i,c] = sum_j  T[ti, b(hop[i,j]), c'] * rscale[i, b(hop[i,j])] * S[j,c]
+ * b(h) = h for h <= nbins-2, nbins-1 for h == 255.  c' = c if Cr == C else 0 (Cr == 1: shared rho).
+ * table_per_row: T is [R,nbins,Cr] (input-normalised rho, GNAN.py:65-67) else [nbins,Cr]; rscale may be NULL.
+ * Replaces GNAN.py:67-73,159-170 and models.py:366-375 (the N*N rho evaluation, permutes, bmm and sums).
+ * ---------------------------------------------------------------------------------------------- */
+int gnan_aggregate_rows_fwd(const uint8_t *hop, int64_t R, int64_t N, int64_t ld_hop, const float *T,
+                            int table_per_row, int32_t nbins, int32_t Cr, const float *rscale, const float *S,
+                            int32_t C, float *out /* [R,C] */, gnan_stream_t stream);
+
+/* training-mode forward: additionally saves the per-row bin sums Bsum[i,d,c] = sum_{j: b(hop[i,j]) = d} S[j,c]
+ * ([R,nbins,C]; NULL = do not save) that the backward turns into dT without another pass over the hop block. */
+int gnan_aggregate_rows_fwd_save(const uint8_t *hop, int64_t R, int64_t N, int64_t ld_hop, const float *T,
+                                 int table_per_row, int32_t nbins, int32_t Cr, const float *rscale, const float *S,
+                                 int32_t C, float *out, float *Bsum, gnan_stream_t stream);
+
+size_t gnan_aggregate_rows_bwd_workspace_bytes(int64_t R, int64_t N, int32_t nbins, int32_t Cr, int32_t C);
+
+/* given g = dL/dout [R,C]:  dS[j,c] = sum_i W[i,j,c] g[i,c]   (overwritten; [N,C])
+ *                            dT (same shape as T; overwritten)  dT[ti,d,c'] = sum_{i in ti} rscale[i,d] * sum_c g[i,c] * Bsum[i,d,c]
+ * with Bsum[i,d,c] = sum_{j: b(hop[i,j]) = d} S[j,c]. One pass over the hop block. */
+int gnan_aggregate_rows_bwd(const uint8_t *hop, int64_t R, int64_t N, int64_t ld_hop, const float *T,
+                            int table_per_row, int32_t nbins, int32_t Cr, const float *rscale, const float *S,
+                            int32_t C, const float *g, float *dS, float *dT, void *workspace, size_t workspace_bytes,
+                            gnan_stream_t stream);
+
+/* same, given the Bsum saved by gnan_aggregate_rows_fwd_save (NULL = recompute it, one extra pass) */
+int gnan_aggregate_rows_bwd_saved(const uint8_t *hop, int64_t R, int64_t N, int64_t ld_hop, const float *T,
+                                  int table_per_row, int32_t nbins, int32_t Cr, const float *rscale, const float *S,
+                                  int32_t C, const float *g, const float *Bsum, float *dS, float *dT, void *workspace,
+                                  size_t workspace_bytes, gnan_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Block-diagonal (batched small graphs) aggregation. Graph b owns nodes [node_off[b], node_off[b+1]) and the
+ * packed n_b x n_b hop block at hop + hop_off[b] (row-major, row stride n_b). The dense (sum N)^2 matrix of
+ * batched_pyg_main.py:75-80 is never built. reduce_graph != 0 additionally sums over the graph's nodes
+ * (GNAN.py:76-78; batched_pyg_main.py:176-181): out is [B,C], else [sum N, C].
+ * T / rscale rows are indexed by global node id when table_per_row / rscale are given.
+ * ---------------------------------------------------------------------------------------------- */
+int gnan_aggregate_blockdiag_fwd(const uint8_t *hop, const int64_t *hop_off /* [B+1] */, const int32_t *node_off /* [B+1] */,
+                                 int32_t B, const float *T, int table_per_row, int32_t nbins, int32_t Cr,
+                                 const float *rscale, const float *S, int32_t C, int reduce_graph, float *out,
+                                 gnan_stream_t stream);
+
+int gnan_aggregate_blockdiag_bwd(const uint8_t *hop, const int64_t *hop_off, const int32_t *node_off, int32_t B,
+                                 const float *T, int table_per_row, int32_t nbins, int32_t Cr, const float *rscale,
+                                 const float *S, int32_t C, int reduce_graph, const float *g, float *dS,
+                                 float *dT /* zero-initialised by the callee; global table grads are atomically added */,
+                                 gnan_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * All-pairs hop distances (replaces scipy dijkstra + the per-element normaliser loop,
+ * pre_process_datasets.py:109-121,128-140; networkx BFS of batched_pyg_main.py:36-44).
+ * Directed CSR (edges followed src -> dst), simple graph, unit weights. hop bytes: level, 255 = unreachable;
+ * a finite level > 254 sets *overflow_flag (device int32) != 0.
+ * cnt[i,d] = #{j: hop[i,j] = d} for d < nbins-1, cnt[i,nbins-1] = #unreachable; levels >= nbins-1 also set the flag.
+ * ---------------------------------------------------------------------------------------------- */
+size_t gnan_apsp_bfs_workspace_bytes(int32_t N, int32_t n_sources);
+
+/* sources [src_begin, src_end) of one graph with N nodes -> hop rows [src_end-src_begin, N] (row stride ld_hop). */
+int gnan_apsp_bfs(const int32_t *rowptr /* [N+1] */, const int32_t *col /* [E] */, int32_t N, int32_t src_begin,
+                  int32_t src_end, uint8_t *hop, int64_t ld_hop, int32_t *cnt /* [rows,nbins] or NULL */,
+                  int32_t nbins, int32_t *overflow_flag, void *workspace, size_t workspace_bytes, gnan_stream_t stream);
+
+/* B small graphs in one launch; CSR over the concatenated node set with GLOBAL column ids. */
+int gnan_apsp_bfs_batched(const int32_t *rowptr /* [sumN+1] */, const int32_t *col, const int32_t *node_off /* [B+1] */,
+                          const int64_t *hop_off /* [B+1] */, int32_t B, uint8_t *hop, int32_t *cnt /* [sumN,nbins] or NULL */,
+                          int32_t nbins, int32_t *overflow_flag, gnan_stream_t stream);
+
+/* same with the largest graph size given (sizes shared memory; graphs of up to 256 nodes) */
+int gnan_apsp_bfs_batched_n(const int32_t *rowptr, const int32_t *col, const int32_t *node_off, const int64_t *hop_off,
+                            int32_t B, int32_t max_n, uint8_t *hop, int32_t *cnt, int32_t nbins, int32_t *overflow_flag,
+                            gnan_stream_t stream);
+
+/* reference-format converters (pre_process_datasets.py:112-121): fp32 node_distances / normalization_matrix <-> hops */
+int gnan_hops_to_reference(const uint8_t *hop, int64_t R, int64_t N, int64_t ld_hop, const int32_t *cnt, int32_t nbins,
+                           float *node_distances, float *normalization_matrix, gnan_stream_t stream);
+int gnan_hops_from_reference(const float *node_distances, const float *normalization_matrix /* or NULL */, int64_t R,
+                             int64_t N, uint8_t *hop, int64_t ld_hop, int32_t *cnt /* or NULL; zero-initialised by caller */,
+                             int32_t nbins, int32_t *overflow_flag, gnan_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNAN_B200_H */
