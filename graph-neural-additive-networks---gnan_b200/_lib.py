@@ -28,6 +28,7 @@ class MlpGrads(ctypes.Structure):
 SIGNATURES = {
     "gnan_version": (c_int, []),
     "gnan_last_error": (ctypes.c_char_p, []),
+    "gnan_launch_count": (c_uint64, []),
     "gnan_mlp_workspace_bytes": (c_size_t, [c_int64, ctypes.POINTER(MlpParams), c_int, c_int]),
     "gnan_mlp_fwd": (c_int, [c_void_p, c_int64, c_int64, ctypes.POINTER(MlpParams), c_float, c_uint64, c_int, c_void_p,
                              c_void_p, c_size_t, c_void_p]),

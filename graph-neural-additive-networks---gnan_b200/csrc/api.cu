@@ -28,5 +28,9 @@ int gnan_sm_count()
     return n;
 }
 
+static unsigned long long g_launches = 0;
+void gnan_count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
+extern "C" uint64_t gnan_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 extern "C" const char *gnan_last_error(void) { return g_err; }
 extern "C" int gnan_version(void) { return GNAN_B200_VERSION; }

@@ -24,7 +24,12 @@ void gnan_set_error(const char *fmt, ...);
         }                                                                                 \
     } while (0)
 
-#define GNAN_LAUNCH_OK() GNAN_CUDA(cudaGetLastError())
+void gnan_count_launch();
+#define GNAN_LAUNCH_OK()               \
+    do {                               \
+        gnan_count_launch();           \
+        GNAN_CUDA(cudaGetLastError()); \
+    } while (0)
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -547,10 +547,13 @@ __global__ void linear1_bwd_kernel(MlpKArgs a, const float *__restrict__ dS, flo
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------
+inline size_t pad4(size_t n) { return (n + 3) / 4 * 4; }
+
+// floats of one partial-gradient chunk; every segment starts 16-byte aligned (the kernel stores float4s)
 size_t grad_floats(const gnan_mlp_params *p)
 {
     const size_t G = p->G, H = p->H, C = p->C, nh = p->n_layers - 2;
-    return 2 * G * H + nh * G * H * H + nh * G * H + G * C * H + G * C;
+    return 2 * pad4(G * H) + pad4(nh * G * H * H) + pad4(nh * G * H) + pad4(G * C * H) + pad4(G * C);
 }
 
 struct FwdPlan { int KC; int nchunk; int64_t ntile; size_t smem; };
@@ -600,8 +603,8 @@ int check_params(const gnan_mlp_params *p, int64_t R, int64_t ldu)
     if (p->n_layers >= 2) {
         GNAN_REQUIRE(p->w1 != nullptr, "mlp: w1 is NULL");
         GNAN_REQUIRE(p->n_layers == 2 || p->wh != nullptr, "mlp: wh is NULL with n_layers=%d", p->n_layers);
-        if (!(p->H == 8 || p->H == 16 || p->H == 32 || p->H == 64 || p->H == 128)) {
-            gnan_set_error("mlp: hidden width %d unsupported (8,16,32,64,128)", p->H);
+        if (!(p->H == 8 || p->H == 16 || p->H == 32 || p->H == 64)) {
+            gnan_set_error("mlp: hidden width %d unsupported (8,16,32,64)", p->H);
             return GNAN_ERR_UNSUPPORTED;
         }
         if (p->n_layers > 5) {
@@ -722,7 +725,6 @@ extern "C" int gnan_mlp_fwd(const float *u, int64_t R, int64_t ldu, const gnan_m
         case 16: rc = launch_fwd<16>(a, pl, Spart, st); break;
         case 32: rc = launch_fwd<32>(a, pl, Spart, st); break;
         case 64: rc = launch_fwd<64>(a, pl, Spart, st); break;
-        case 128: rc = launch_fwd<128>(a, pl, Spart, st); break;
     }
     if (rc) return rc;
     if (pl.nchunk > 1) {
@@ -776,11 +778,11 @@ extern "C" int gnan_mlp_bwd(const float *u, int64_t R, int64_t ldu, const gnan_m
             return GNAN_ERR_WORKSPACE;
         }
         float *w = (float *)workspace;
-        gp.w1 = w; w += G * H;
-        gp.b1 = w; w += G * H;
-        gp.wh = w; w += nh * G * H * H;
-        gp.bh = w; w += nh * G * H;
-        gp.wo = w; w += G * C * H;
+        gp.w1 = w; w += pad4(G * H);
+        gp.b1 = w; w += pad4(G * H);
+        gp.wh = w; w += pad4(nh * G * H * H);
+        gp.bh = w; w += pad4(nh * G * H);
+        gp.wo = w; w += pad4(G * C * H);
         gp.bo = w;
         gp.chunk_stride = ntot;
     } else {
@@ -792,7 +794,6 @@ extern "C" int gnan_mlp_bwd(const float *u, int64_t R, int64_t ldu, const gnan_m
         case 16: rc = launch_bwd_h<16>(a, pl, dS, gp, st); break;
         case 32: rc = launch_bwd_h<32>(a, pl, dS, gp, st); break;
         case 64: rc = launch_bwd_h<64>(a, pl, dS, gp, st); break;
-        case 128: rc = launch_bwd_h<128>(a, pl, dS, gp, st); break;
     }
     if (rc) return rc;
     if (pl.nchunk > 1) {

@@ -13,6 +13,37 @@ from ._lib import MlpGrads, MlpParams, check, load, ptr, stream_handle
 __all__ = ["mlp", "aggregate_rows", "aggregate_blockdiag", "rho_table_inputs", "level_rscale", "alloc_hop", "hop_ld"]
 
 
+# ---- optional per-call CUDA-event timing (bench.py): events are recorded on the launching stream ----------------------
+_TIMING = None
+
+
+def enable_timing(on: bool):
+    global _TIMING
+    _TIMING = {} if on else None
+
+
+def timing_results():
+    """{op: (calls, total_ms)}; synchronises."""
+    torch.cuda.synchronize()
+    return {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in (_TIMING or {}).items()}
+
+
+class _timed:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _TIMING is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if _TIMING is not None:
+            self.b.record()
+            _TIMING.setdefault(self.name, []).append((self.a, self.b))
+
+
 def hop_ld(n: int) -> int:
     """leading dimension (bytes per row) of a hop block with n columns: rows are 16-byte aligned for 128-bit loads"""
     return max(16, (int(n) + 15) // 16 * 16)
@@ -53,8 +84,9 @@ def mlp_fwd(u: Tensor, w1: Tensor, b1: Tensor, wh: Tensor, bh: Tensor, wo: Tenso
     R = u.shape[0]
     S = torch.empty(R, C, dtype=torch.float32, device=u.device)
     ws = _ws(lib.gnan_mlp_workspace_bytes(R, p, 0, precision), u.device)
-    check(lib.gnan_mlp_fwd(ptr(u), R, u.shape[1], p, float(dropout_p), int(seed) & (2 ** 64 - 1), precision, ptr(S), ptr(ws),
-                           ws.numel(), stream_handle()), "gnan_mlp_fwd")
+    with _timed("mlp_fwd"):
+        check(lib.gnan_mlp_fwd(ptr(u), R, u.shape[1], p, float(dropout_p), int(seed) & (2 ** 64 - 1), precision, ptr(S), ptr(ws),
+                               ws.numel(), stream_handle()), "gnan_mlp_fwd")
     return S
 
 
@@ -73,8 +105,9 @@ def mlp_bwd(u: Tensor, w1: Tensor, b1: Tensor, wh: Tensor, bh: Tensor, wo: Tenso
     outs = [torch.empty_like(t) for t in (w1, b1, wh, bh, wo, bo)]
     g = MlpGrads(*[ptr(t) for t in outs])
     ws = _ws(lib.gnan_mlp_workspace_bytes(R, p, 1, precision), u.device)
-    check(lib.gnan_mlp_bwd(ptr(u), R, u.shape[1], p, float(dropout_p), int(seed) & (2 ** 64 - 1), precision, ptr(dS),
-                           g, ptr(ws), ws.numel(), stream_handle()), "gnan_mlp_bwd")
+    with _timed("mlp_bwd"):
+        check(lib.gnan_mlp_bwd(ptr(u), R, u.shape[1], p, float(dropout_p), int(seed) & (2 ** 64 - 1), precision, ptr(dS),
+                               g, ptr(ws), ws.numel(), stream_handle()), "gnan_mlp_bwd")
     return tuple(outs)
 
 
@@ -128,8 +161,9 @@ def agg_rows_fwd(hop: Tensor, T: Tensor, rscale: Optional[Tensor], S: Tensor, pe
     R, ld, N, C, nbins, Cr = _agg_dims(hop, T, S, per_row)
     out = torch.empty(R, C, dtype=torch.float32, device=S.device)
     bsum = torch.empty((R, nbins, C) if save else (0,), dtype=torch.float32, device=S.device)
-    check(lib.gnan_aggregate_rows_fwd_save(ptr(hop), R, N, ld, ptr(T), int(per_row), nbins, Cr, ptr(rscale), ptr(S), C,
-                                           ptr(out), ptr(bsum), stream_handle()), "gnan_aggregate_rows_fwd")
+    with _timed("aggregate_rows_fwd_save"):
+        check(lib.gnan_aggregate_rows_fwd_save(ptr(hop), R, N, ld, ptr(T), int(per_row), nbins, Cr, ptr(rscale), ptr(S), C,
+                                               ptr(out), ptr(bsum), stream_handle()), "gnan_aggregate_rows_fwd")
     return out, bsum
 
 
@@ -149,9 +183,10 @@ def agg_rows_bwd(hop: Tensor, T: Tensor, rscale: Optional[Tensor], S: Tensor, pe
     dS = torch.empty_like(S)
     dT = torch.empty_like(T)
     ws = _ws(lib.gnan_aggregate_rows_bwd_workspace_bytes(R, N, nbins, Cr, C), S.device)
-    check(lib.gnan_aggregate_rows_bwd_saved(ptr(hop), R, N, ld, ptr(T), int(per_row), nbins, Cr, ptr(rscale), ptr(S), C,
-                                            ptr(g), ptr(bsum) if bsum.numel() else None, ptr(dS), ptr(dT), ptr(ws),
-                                            ws.numel(), stream_handle()), "gnan_aggregate_rows_bwd")
+    with _timed("aggregate_rows_bwd_saved"):
+        check(lib.gnan_aggregate_rows_bwd_saved(ptr(hop), R, N, ld, ptr(T), int(per_row), nbins, Cr, ptr(rscale), ptr(S), C,
+                                                ptr(g), ptr(bsum) if bsum.numel() else None, ptr(dS), ptr(dT), ptr(ws),
+                                                ws.numel(), stream_handle()), "gnan_aggregate_rows_bwd")
     return dS, dT
 
 
@@ -196,9 +231,10 @@ def agg_blockdiag_fwd(hop: Tensor, hop_off: Tensor, node_off: Tensor, T: Tensor,
     N, C = S.shape
     nbins, Cr = T.shape[-2], T.shape[-1]
     out = torch.empty(B if reduce_graph else N, C, dtype=torch.float32, device=S.device)
-    check(lib.gnan_aggregate_blockdiag_fwd(ptr(hop), ptr(hop_off), ptr(node_off), B, ptr(T), int(per_row), nbins, Cr,
-                                           ptr(rscale), ptr(S), C, int(reduce_graph), ptr(out), stream_handle()),
-          "gnan_aggregate_blockdiag_fwd")
+    with _timed("aggregate_blockdiag_fwd"):
+        check(lib.gnan_aggregate_blockdiag_fwd(ptr(hop), ptr(hop_off), ptr(node_off), B, ptr(T), int(per_row), nbins, Cr,
+                                               ptr(rscale), ptr(S), C, int(reduce_graph), ptr(out), stream_handle()),
+              "gnan_aggregate_blockdiag_fwd")
     return out
 
 
@@ -218,9 +254,10 @@ def agg_blockdiag_bwd(hop: Tensor, hop_off: Tensor, node_off: Tensor, T: Tensor,
     nbins, Cr = T.shape[-2], T.shape[-1]
     dS = torch.zeros_like(S)
     dT = torch.zeros_like(T)
-    check(lib.gnan_aggregate_blockdiag_bwd(ptr(hop), ptr(hop_off), ptr(node_off), B, ptr(T), int(per_row), nbins, Cr,
-                                           ptr(rscale), ptr(S), C, int(reduce_graph), ptr(g), ptr(dS), ptr(dT),
-                                           stream_handle()), "gnan_aggregate_blockdiag_bwd")
+    with _timed("aggregate_blockdiag_bwd"):
+        check(lib.gnan_aggregate_blockdiag_bwd(ptr(hop), ptr(hop_off), ptr(node_off), B, ptr(T), int(per_row), nbins, Cr,
+                                               ptr(rscale), ptr(S), C, int(reduce_graph), ptr(g), ptr(dS), ptr(dT),
+                                               stream_handle()), "gnan_aggregate_blockdiag_bwd")
     return dS, dT
 
 

@@ -40,6 +40,8 @@ typedef void *gnan_stream_t;
 
 int gnan_version(void);
 const char *gnan_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches evidence) */
+uint64_t gnan_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Grouped scalar-input MLPs: G independent networks  R -> R^C,

@@ -1,0 +1,30 @@
+import sys, numpy as np, torch
+sys.path.insert(0, '/root/repo')
+from tests.test_gpu_parity import rand_mlp, oracle_params
+from tests import _golden as G
+from oracle import gnan_lut
+from gnan_b200 import ops
+DEV='cuda'
+def run(R,G_,H,C,L, seed):
+    rng = np.random.default_rng(seed)
+    p = rand_mlp(rng, G_, H, C, L)
+    u = torch.tensor(rng.normal(size=(R, G_)) * (rng.random((R, G_)) < 0.7)).float()
+    dS = torch.tensor(rng.normal(size=(R, C))).float()
+    q = oracle_params(p, L)
+    # fp64 pre-activation margins
+    x = u.double()
+    z1 = x.unsqueeze(-1) * q["w1"] + q["b1"]
+    h = torch.relu(z1)
+    z2 = torch.einsum("nki,kji->nkj", h, q["wh"][0]) + q["bh"][0]
+    m1 = z1.abs().amin(dim=(0,2)); m2 = z2.abs().amin(dim=(0,2))
+    want = gnan_lut.feature_sums(q, x)
+    (want * dS.double()).sum().backward()
+    d = {k: v.to(DEV).requires_grad_(v.numel() > 0) for k, v in p.items()}
+    got = ops.mlp(u.to(DEV), d["w1"], d["b1"], d["wh"], d["bh"], d["wo"], d["bo"], L)
+    (got * dS.to(DEV)).sum().backward()
+    a = d["wh"].grad.cpu().double(); b = q["wh"].grad
+    per_g = (a-b).abs().amax(dim=(0,2,3))
+    bad = (per_g > 1e-3).nonzero().flatten().tolist()
+    print("seed", seed, "bad groups", bad, "min|z2| of bad groups", [f"{float(m2[g]):.1e}" for g in bad], "global min|z2| %.1e min|z1| %.1e" % (float(m2.min()), float(m1.min())))
+for seed in (7040, 14040, 1, 2, 3, 4, 5, 6):
+    run(1000,40,64,3,3, seed)

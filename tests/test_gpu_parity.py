@@ -1,0 +1,338 @@
+"""GPU: parity of the CUDA path (through the C ABI) against the golden vectors of the unmodified reference and
+against the oracle on seeded inputs. Tolerances (norm-wise relative): 1e-5 for fp32 outputs and
+gradients; hop distances, level counts and the reference-format matrices are compared bit-exactly."""
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import apsp as oapsp
+from oracle import gnan_lut, gnan_port
+from tests import _golden as G
+from tests._build import build_module
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+DEV = "cuda"
+
+
+def grads_of(stacked):
+    out = {}
+    for n in ("w1", "b1", "wh", "bh", "wo", "bo"):
+        p = getattr(stacked, n)
+        out[n] = None if not isinstance(p, torch.nn.Parameter) or p.grad is None else p.grad.detach().cpu().numpy()
+    return out
+
+
+def check_grads(z, got, want, tag):
+    for k in ("w1", "b1", "wh", "bh", "wo", "bo"):
+        w = want[k]
+        if w is None or w.size == 0 or got[k] is None:
+            continue
+        if np.linalg.norm(w) == 0:
+            assert np.abs(got[k]).max() < 1e-6, (z["name"], tag, k)
+        else:
+            assert G.rel_err(got[k], w) < TOL, (z["name"], tag, k, G.rel_err(got[k], w))
+
+
+def run_case(z, compact):
+    m = build_module(z, DEV).eval()
+    w = torch.tensor(z["out_weight"], device=DEV)
+    if z["variant"] == "batched":
+        if compact:
+            from gnan_b200.batched import pack_dense
+            pk = pack_dense(torch.tensor(z["x"], device=DEV), torch.tensor(z["dist_batch"], device=DEV),
+                            torch.tensor(z["batch_vector"], device=DEV))
+            out = m(pk)
+        else:
+            out = m(torch.tensor(z["x"]), torch.tensor(z["dist_batch"]), torch.tensor(z["batch_vector"]))
+    else:
+        if compact:
+            from gnan_b200.preprocess import apsp
+            hd = apsp(torch.tensor(z["edge_index"]), z["N"], device=DEV)
+            data = SimpleNamespace(x=torch.tensor(z["x"]), edge_index=torch.tensor(z["edge_index"]), hop_data=hd)
+        else:
+            data = SimpleNamespace(x=torch.tensor(z["x"]), edge_index=torch.tensor(z["edge_index"]),
+                                   node_distances=torch.tensor(z["node_distances"]),
+                                   normalization_matrix=torch.tensor(z["normalization_matrix"]))
+        if z["variant"] == "gnan_loop" and "node_ids" in z:
+            out = m.forward(data, z["node_ids"].tolist())
+        else:
+            out = m.forward(data)
+    (out * w).sum().backward()
+    return m, out
+
+
+RUNNABLE = [n for n in G.MODEL_CASES + G.BATCHED_CASES if "readout" not in n]
+
+
+@pytest.mark.parametrize("compact", [False, True], ids=["reference_inputs", "compact_inputs"])
+@pytest.mark.parametrize("name", RUNNABLE)
+def test_module_matches_reference_golden(name, compact):
+    z = G.load(name)
+    m, out = run_case(z, compact)
+    assert tuple(out.shape) == z["out"].shape
+    assert G.rel_err(out.detach().cpu().numpy(), z["out"]) < TOL
+    check_grads(z, grads_of(m.fs), z["grad_fs"], "fs")
+    check_grads(z, grads_of(m.rho), z["grad_rho"], "rho")
+
+
+@pytest.mark.parametrize("name", G.PREPROCESS_CASES)
+def test_apsp_bit_exact_vs_reference_golden(name):
+    from gnan_b200.preprocess import apsp, from_reference_format
+    z = G.load(name)
+    n = int(z["meta"][0])
+    hd = apsp(torch.tensor(z["edge_index"].reshape(2, -1)), n, device=DEV)
+    nd, nm = hd.reference_format()
+    assert np.array_equal(nd.cpu().numpy(), z["node_distances"])
+    assert np.array_equal(nm.cpu().numpy(), z["normalization_matrix"])
+    back = from_reference_format(torch.tensor(z["node_distances"], device=DEV), torch.tensor(z["normalization_matrix"], device=DEV))
+    assert torch.equal(back.hop[:, :n], hd.hop[:, :n]) and torch.equal(back.level_counts, hd.level_counts)
+
+
+def random_graph(rng, n, avg_deg=3.0, directed=False, n_isolated=0):
+    m = n - n_isolated
+    E = int(m * avg_deg / (1 if directed else 2))
+    src = rng.integers(0, max(m, 1), size=E); dst = rng.integers(0, max(m, 1), size=E)
+    keep = src != dst
+    e = np.unique(np.stack([src[keep], dst[keep]], 1), axis=0)
+    if not directed:
+        e = np.unique(np.concatenate([e, e[:, ::-1]]), axis=0)
+    return e.T.astype(np.int64).reshape(2, -1)
+
+
+@pytest.mark.parametrize("n,deg,directed", [(1, 0, False), (2, 1, False), (257, 2.2, False), (1000, 3.0, True), (3001, 2.5, False)])
+def test_apsp_vs_oracle_random(n, deg, directed):
+    from gnan_b200.preprocess import apsp
+    rng = np.random.default_rng(n)
+    ei = random_graph(rng, n, deg, directed, n_isolated=min(3, n - 1))
+    hop = oapsp.apsp(ei, n)
+    cnt = oapsp.level_counts(hop)
+    hd = apsp(torch.tensor(ei), n, device=DEV)
+    got = hd.hop[:, :n].cpu().numpy().astype(np.int32)
+    got[got == 255] = -1
+    assert np.array_equal(got, hop)
+    assert np.array_equal(hd.level_counts.cpu().numpy(), cnt)
+    # row-sharded call == slice of the full matrix
+    if n > 10:
+        part = apsp(torch.tensor(ei), n, device=DEV, row_begin=n // 3, row_end=n // 3 + 7)
+        assert torch.equal(part.hop[:, :n], hd.hop[n // 3:n // 3 + 7, :n])
+
+
+def test_apsp_batched_vs_oracle():
+    from gnan_b200.preprocess import apsp_batched
+    rng = np.random.default_rng(5)
+    sizes = [1, 2, 5, 31, 32, 33, 64, 100, 17, 256, 3]
+    node_off = np.concatenate([[0], np.cumsum(sizes)])
+    eis = [random_graph(rng, n, 2.4, False, n_isolated=1 if n > 4 else 0) + node_off[i] for i, n in enumerate(sizes)]
+    ei = np.concatenate(eis, axis=1)
+    pk = apsp_batched(torch.tensor(ei), torch.tensor(node_off), device=DEV)
+    hop = pk.hop.cpu().numpy(); cnt = pk.level_counts.cpu().numpy(); ho = pk.hop_off.cpu().numpy()
+    for i, n in enumerate(sizes):
+        want = oapsp.apsp(eis[i] - node_off[i], n)
+        got = hop[ho[i]:ho[i + 1]].reshape(n, n).astype(np.int32)
+        got[got == 255] = -1
+        assert np.array_equal(got, want), i
+        wc = oapsp.level_counts(want, cnt.shape[1]) if want.max() + 2 <= cnt.shape[1] else None
+        wc = oapsp.level_counts(want)
+        full = np.zeros((n, cnt.shape[1]), dtype=np.int32)
+        full[:, :wc.shape[1] - 1] = wc[:, :-1]; full[:, -1] = wc[:, -1]
+        assert np.array_equal(cnt[node_off[i]:node_off[i + 1]], full), i
+
+
+# ---- kernel-level: grouped MLP ------------------------------------------------------------------------------------------
+def rand_mlp(rng, G_, H, C, L, bias=True):
+    g = lambda *s: torch.tensor(rng.normal(size=s)).float()
+    if L == 1:
+        return dict(w1=torch.zeros(0), b1=torch.zeros(0), wh=torch.zeros(0), bh=torch.zeros(0), wo=g(G_, C, 1), bo=g(G_, C) * 0.3 * bias)
+    nh = L - 2
+    return dict(w1=g(G_, H), b1=g(G_, H) * 0.3 * bias, wh=g(nh, G_, H, H) / H ** 0.5 * 1.3, bh=g(nh, G_, H) * 0.3 * bias,
+                wo=g(G_, C, H) / H ** 0.5, bo=g(G_, C) * 0.3 * bias)
+
+
+def relu_margin(p, u):
+    """smallest |pre-activation| over all rows, groups, layers and units, in float64"""
+    h = u.double().unsqueeze(-1) * p["w1"].double() + p["b1"].double()
+    m = float(h.abs().min())
+    h = torch.relu(h)
+    for l in range(p["wh"].shape[0]):
+        h = torch.einsum("nki,kji->nkj", h, p["wh"][l].double()) + p["bh"][l].double()
+        m = min(m, float(h.abs().min()))
+        h = torch.relu(h)
+    return m
+
+
+def oracle_params(p, L):
+    q = {k: v.double().clone().requires_grad_(v.numel() > 0) for k, v in p.items()}
+    if L == 1:
+        q["w1"] = None
+    return q
+
+
+@pytest.mark.parametrize("R,G_,H,C,L", [
+    (1, 1, 64, 1, 3), (127, 3, 64, 7, 3), (300, 15, 64, 1, 3), (1000, 40, 64, 3, 3), (257, 5, 32, 4, 3),
+    (130, 4, 16, 8, 2), (64, 3, 8, 2, 4), (90, 3, 64, 40, 3), (77, 6, 16, 9, 5), (50, 4, 64, 3, 1),
+    (4000, 70, 64, 7, 3)])
+def test_mlp_kernel_vs_oracle(R, G_, H, C, L):
+    from gnan_b200 import ops
+    # A pre-activation within fp32 rounding of 0 flips a ReLU mask between the fp32 kernel and the fp64 oracle and moves
+    # a gradient by a whole term (measured: one flip at |z| = 4e-8 -> 5e-4 norm-wise). The reference has the same kink;
+    # draw inputs whose float64 pre-activations all clear 2e-6 so the comparison is well-posed.
+    for attempt in range(50):
+        rng = np.random.default_rng(R * 7 + G_ + 1000 * attempt)
+        p = rand_mlp(rng, G_, H, C, L)
+        u = torch.tensor(rng.normal(size=(R, G_)) * (rng.random((R, G_)) < 0.7)).float()
+        dS = torch.tensor(rng.normal(size=(R, C))).float()
+        if L == 1 or relu_margin(p, u) > 2e-6:
+            break
+    else:
+        raise AssertionError("could not draw a kink-free case")
+    q = oracle_params(p, L)
+    want = gnan_lut.feature_sums(q, u.double())
+    (want * dS.double()).sum().backward()
+    d = {k: v.to(DEV).requires_grad_(v.numel() > 0) for k, v in p.items()}
+    got = ops.mlp(u.to(DEV), d["w1"], d["b1"], d["wh"], d["bh"], d["wo"], d["bo"], L)
+    (got * dS.to(DEV)).sum().backward()
+    assert G.rel_err(got.detach().cpu().numpy(), want.detach().numpy()) < TOL
+    for k in p:
+        if p[k].numel() and q[k] is not None:
+            assert G.rel_err(d[k].grad.cpu().numpy(), q[k].grad.numpy()) < TOL, k
+
+
+def test_mlp_dropout_is_consistent_between_forward_and_backward():
+    """With dropout on, S is linear in wo/bo and its gradient w.r.t. bo is R; finite differences through the SAME mask
+    (same seed) must match the analytic backward."""
+    from gnan_b200 import ops
+    rng = np.random.default_rng(0)
+    R, G_, H, C, L = 300, 4, 64, 3, 3
+    p = {k: v.to(DEV) for k, v in rand_mlp(rng, G_, H, C, L).items()}
+    u = torch.tensor(rng.normal(size=(R, G_))).float().to(DEV)
+    args = lambda q: (u, q["w1"], q["b1"], q["wh"], q["bh"], q["wo"], q["bo"], L)
+    S0 = ops.mlp(*args(p), dropout_p=0.5, seed=1234)
+    S1 = ops.mlp(*args(p), dropout_p=0.5, seed=1234)
+    S2 = ops.mlp(*args(p), dropout_p=0.5, seed=99)
+    Sn = ops.mlp(*args(p))
+    assert torch.equal(S0, S1) and not torch.equal(S0, S2)
+    assert abs(float((S0.mean() - Sn.mean()).abs()) / (float(Sn.abs().mean()) + 1e-9)) < 0.5   # same scale (inverted dropout)
+    dS = torch.tensor(rng.normal(size=(R, C))).float().to(DEV)
+    q = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    (ops.mlp(*args(q), dropout_p=0.5, seed=1234) * dS).sum().backward()
+    for name, idx in (("wh", (0, 1, 3, 5)), ("w1", (2, 7)), ("b1", (0, 9)), ("wo", (1, 2, 11))):
+        eps = 1e-2
+        pp = {k: v.clone() for k, v in p.items()}; pp[name][idx] += eps
+        pm = {k: v.clone() for k, v in p.items()}; pm[name][idx] -= eps
+        fd = float(((ops.mlp(*args(pp), dropout_p=0.5, seed=1234) - ops.mlp(*args(pm), dropout_p=0.5, seed=1234)).double() * dS.double()).sum()) / (2 * eps)
+        an = float(q[name].grad[idx])
+        assert abs(fd - an) <= 2e-2 * max(1.0, abs(an)), (name, fd, an)
+
+
+# ---- kernel-level: aggregation -----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("R,N,C,Cr,nbins,per_row,scale", [
+    (5, 7, 1, 1, 3, False, False), (37, 100, 3, 3, 6, True, False), (64, 2500, 7, 7, 12, False, True),
+    (33, 4099, 4, 1, 40, False, True), (20, 300, 2, 2, 70, True, True), (129, 515, 40, 40, 9, False, False),
+    (300, 300, 5, 1, 5, True, False)])
+def test_aggregate_rows_vs_oracle(R, N, C, Cr, nbins, per_row, scale):
+    from gnan_b200 import ops
+    rng = np.random.default_rng(R + N)
+    h = rng.integers(0, nbins, size=(R, N))
+    hop = ops.alloc_hop(R, N, DEV)
+    hb = h.copy(); hb[hb == nbins - 1] = 255
+    hop[:, :N] = torch.tensor(hb.astype(np.uint8), device=DEV)
+    T = torch.tensor(rng.normal(size=((R, nbins, Cr) if per_row else (nbins, Cr)))).float()
+    S = torch.tensor(rng.normal(size=(N, C))).float()
+    rs = torch.tensor(rng.random(size=(R, nbins)) + 0.1).float() if scale else None
+    gO = torch.tensor(rng.normal(size=(R, C))).float()
+    Td, Sd = T.double().requires_grad_(True), S.double().requires_grad_(True)
+    idx = torch.tensor(h)
+    W = (torch.gather(Td, 1, idx.unsqueeze(-1).expand(-1, -1, Cr)) if per_row else Td[idx])
+    if scale:
+        W = W * torch.gather(rs.double(), 1, idx).unsqueeze(-1)
+    want = (W * Sd.unsqueeze(0)).sum(1)
+    (want * gO.double()).sum().backward()
+    Tg, Sg = T.to(DEV).requires_grad_(True), S.to(DEV).requires_grad_(True)
+    got = ops.aggregate_rows(hop, Tg, Sg, rscale=None if rs is None else rs.to(DEV), per_row=per_row)
+    (got * gO.to(DEV)).sum().backward()
+    assert G.rel_err(got.detach().cpu().numpy(), want.detach().numpy()) < TOL
+    assert G.rel_err(Sg.grad.cpu().numpy(), Sd.grad.numpy()) < TOL
+    assert G.rel_err(Tg.grad.cpu().numpy(), Td.grad.numpy()) < TOL
+    with torch.no_grad():                                   # inference path (no bin sums saved)
+        assert torch.equal(ops.aggregate_rows(hop, Tg, Sg, rscale=None if rs is None else rs.to(DEV), per_row=per_row), got.detach())
+
+
+def test_blockdiag_equals_per_graph_dense_rows():
+    """Property: the block-diagonal batch equals looping the dense-row kernel over graphs."""
+    from gnan_b200 import ops
+    from gnan_b200.preprocess import apsp, apsp_batched
+    rng = np.random.default_rng(11)
+    sizes = [4, 30, 9, 64, 120, 1]
+    node_off = np.concatenate([[0], np.cumsum(sizes)])
+    eis = [random_graph(rng, n, 2.3, False, n_isolated=1 if n > 8 else 0) for n in sizes]
+    ei = np.concatenate([e + node_off[i] for i, e in enumerate(eis)], axis=1)
+    pk = apsp_batched(torch.tensor(ei), torch.tensor(node_off), device=DEV)
+    C, nb = 3, pk.nbins
+    T = torch.tensor(rng.normal(size=(nb, C))).float().to(DEV).requires_grad_(True)
+    S = torch.tensor(rng.normal(size=(node_off[-1], C))).float().to(DEV).requires_grad_(True)
+    rs = ops.level_rscale(pk.level_counts)
+    for reduce_graph in (True, False):
+        out = ops.aggregate_blockdiag(pk.hop, pk.hop_off, pk.node_off, T, S, rscale=rs, reduce_graph=reduce_graph)
+        w = torch.tensor(rng.normal(size=tuple(out.shape))).float().to(DEV)
+        gT, gS = torch.autograd.grad((out * w).sum(), (T, S))
+        ref = []
+        for i, n in enumerate(sizes):
+            hd = apsp(torch.tensor(eis[i]), n, device=DEV)
+            cnt = torch.zeros(n, nb, dtype=torch.int32, device=DEV)
+            cnt[:, :hd.nbins - 1] = hd.level_counts[:, :-1]; cnt[:, -1] = hd.level_counts[:, -1]
+            o = ops.aggregate_rows(hd.hop, T, S[node_off[i]:node_off[i + 1]].contiguous(), rscale=ops.level_rscale(cnt))
+            ref.append(o.sum(0, keepdim=True) if reduce_graph else o)
+        ref = torch.cat(ref)
+        rT, rS = torch.autograd.grad((ref * w).sum(), (T, S))
+        assert G.rel_err(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) < TOL
+        assert G.rel_err(gT.cpu().numpy(), rT.cpu().numpy()) < TOL and G.rel_err(gS.cpu().numpy(), rS.cpu().numpy()) < TOL
+
+
+def test_node_order_permutation_equivariance():
+    """Property: relabelling nodes permutes the node-level output rows and leaves parameter gradients unchanged."""
+    from gnan_b200.GNAN import TensorGNAN
+    from gnan_b200.preprocess import apsp
+    rng = np.random.default_rng(3)
+    n, K, C = 150, 6, 4
+    ei = random_graph(rng, n, 2.5, False, n_isolated=2)
+    x = torch.tensor(rng.normal(size=(n, K))).float()
+    perm = rng.permutation(n); inv = np.argsort(perm)
+    torch.manual_seed(0)
+    m = TensorGNAN(K, C, 3, 64).to(DEV)
+    m.fs.xavier_normal_(1.0); m.rho.xavier_normal_(1.0)
+    d1 = SimpleNamespace(x=x, hop_data=apsp(torch.tensor(ei), n, device=DEV))
+    d2 = SimpleNamespace(x=x[perm], hop_data=apsp(torch.tensor(inv[ei]), n, device=DEV))
+    o1 = m.forward(d1); o2 = m.forward(d2)
+    assert G.rel_err(o2.detach().cpu().numpy(), o1.detach().cpu().numpy()[perm]) < TOL
+
+
+def test_large_row_block_vs_lut_oracle():
+    """PubMed-like row block (the shipped forward cannot run at this shape: SURVEY §8c) against the float64 LUT oracle."""
+    from gnan_b200.models import GNAN
+    from gnan_b200.preprocess import apsp
+    rng = np.random.default_rng(8)
+    n, K, C = 5000, 33, 3
+    ei = random_graph(rng, n, 2.4, True, n_isolated=20)
+    x = torch.tensor(rng.random(size=(n, K)) * (rng.random((n, K)) < 0.1)).float()
+    torch.manual_seed(1)
+    m = GNAN(K, C, num_layers=3, hidden_channels=64, rho_per_feature=True).to(DEV)
+    ids = list(range(100, 164))
+    hd = apsp(torch.tensor(ei), n, device=DEV)
+    out = m.forward(SimpleNamespace(x=x, hop_data=hd), ids)
+    w = torch.tensor(rng.normal(size=tuple(out.shape))).float()
+    (out * w.to(DEV)).sum().backward()
+    hop = torch.tensor(oapsp.apsp(ei, n)).long()
+    cnt = gnan_lut.counts_from_hops(hop)
+    assert torch.equal(cnt.int(), hd.level_counts.cpu())
+    from oracle import params as P
+    sd = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+    fs = gnan_port.to_torch(P.stack_mlps(sd, [f"fs.{k}" for k in range(K)], 3, 3), torch.float64, True)
+    rho = gnan_port.to_torch(P.stack_mlps(sd, ["rho"], 3, 2), torch.float64, True)
+    want = gnan_lut.forward_rows(fs, rho, x.double(), hop[ids], cnt[ids], "output")
+    (want * w.double()).sum().backward()
+    assert G.rel_err(out.detach().cpu().numpy(), want.detach().numpy()) < TOL
+    assert G.rel_err(m.fs.wh.grad.cpu().numpy(), fs["wh"].grad.numpy()) < TOL
+    assert G.rel_err(m.rho.wo.grad.cpu().numpy(), rho["wo"].grad.numpy()) < TOL
