@@ -366,17 +366,6 @@ __global__ void level_rscale_kernel(const int32_t *__restrict__ cnt, int64_t tot
     rs[t] = c > 0 ? 1.0f / (float)c : 0.f;
 }
 
-__global__ void reduce_strided_kernel2(const float *__restrict__ part, int nchunk, size_t n, size_t stride, float *__restrict__ out)
-{
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t step = (size_t)gridDim.x * blockDim.x;
-    for (; i < n; i += step) {
-        float s = 0.f;
-        for (int c = 0; c < nchunk; ++c) s += part[(size_t)c * stride + i];
-        out[i] = s;
-    }
-}
-
 int check_agg(const char *who, const uint8_t *hop, int64_t R, int64_t N, int64_t ld, const float *T, int nbins, int Cr,
               const float *S, int C)
 {
@@ -525,8 +514,8 @@ extern "C" int gnan_aggregate_rows_bwd_saved(const uint8_t *hop, int64_t R, int6
         GNAN_LAUNCH_OK();
         if (p.nsb > 1) {
             const size_t n = (size_t)N * C;
-            reduce_strided_kernel2<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(dSpart, p.nsb, n, n, dS);
-            GNAN_LAUNCH_OK();
+            rc = gnan_reduce_chunks(dSpart, p.nsb, n, n, dS, st);
+            if (rc) return rc;
         }
     }
     return GNAN_OK;

@@ -34,3 +34,25 @@ extern "C" uint64_t gnan_launch_count(void) { return __atomic_load_n(&g_launches
 
 extern "C" const char *gnan_last_error(void) { return g_err; }
 extern "C" int gnan_version(void) { return GNAN_B200_VERSION; }
+
+// out[i] = sum_c part[c*stride + i] in fixed order (deterministic); shared by the partial-sum paths
+__global__ void gnan_reduce_chunks_kernel(const float *__restrict__ part, int nchunk, size_t n, size_t stride, float *__restrict__ out)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t step = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += step) {
+        float s = 0.f;
+        for (int c = 0; c < nchunk; ++c) s += part[(size_t)c * stride + i];
+        out[i] = s;
+    }
+}
+
+int gnan_reduce_chunks(const float *part, int nchunk, size_t n, size_t stride, float *out, cudaStream_t st)
+{
+    if (n == 0) return GNAN_OK;
+    size_t blocks = (n + 255) / 256;
+    if (blocks > (size_t)gnan_sm_count() * 8) blocks = (size_t)gnan_sm_count() * 8;
+    gnan_reduce_chunks_kernel<<<(unsigned)blocks, 256, 0, st>>>(part, nchunk, n, stride, out);
+    GNAN_LAUNCH_OK();
+    return GNAN_OK;
+}

@@ -251,19 +251,6 @@ mlp_fwd_kernel(MlpKArgs a, int KC, float *__restrict__ Spart)
     }
 }
 
-// out[i] = sum_c part[c*stride + i]  (fixed order: deterministic)
-__global__ void reduce_strided_kernel(const float *__restrict__ part, int nchunk, size_t n, size_t stride,
-                                      float *__restrict__ out)
-{
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t step = (size_t)gridDim.x * blockDim.x;
-    for (; i < n; i += step) {
-        float s = 0.f;
-        for (int c = 0; c < nchunk; ++c) s += part[(size_t)c * stride + i];
-        out[i] = s;
-    }
-}
-
 // ---- backward ------------------------------------------------------------------------------------------------
 struct MlpGradPtrs {
     float *w1, *b1, *wh, *bh, *wo, *bo;  // bases of chunk 0
@@ -667,6 +654,7 @@ int launch_bwd_h(const MlpKArgs &a, const BwdPlan &pl, const float *dS, const Ml
 
 // tcgen05 path (mlp_tc.cu)
 int gnan_mlp_tc_supported(const gnan_mlp_params *p, int precision);
+int gnan_mlp_tc_bwd_supported(const gnan_mlp_params *p, int precision);
 size_t gnan_mlp_tc_workspace_bytes(int64_t R, const gnan_mlp_params *p, int backward, int precision);
 int gnan_mlp_tc_fwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *p, float dropout_p, uint64_t seed,
                     int precision, float *S, void *ws, size_t ws_bytes, cudaStream_t st);
@@ -676,7 +664,7 @@ int gnan_mlp_tc_bwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_param
 extern "C" size_t gnan_mlp_workspace_bytes(int64_t R, const gnan_mlp_params *p, int backward, int precision)
 {
     if (!p || p->n_layers < 2 || R <= 0) return 0;
-    if (precision != GNAN_PREC_FP32 && gnan_mlp_tc_supported(p, precision))
+    if (precision != GNAN_PREC_FP32 && (backward ? gnan_mlp_tc_bwd_supported(p, precision) : gnan_mlp_tc_supported(p, precision)))
         return gnan_mlp_tc_workspace_bytes(R, p, backward, precision);
     if (!backward) {
         const FwdPlan pl = plan_fwd(R, p);
@@ -703,13 +691,9 @@ extern "C" int gnan_mlp_fwd(const float *u, int64_t R, int64_t ldu, const gnan_m
         GNAN_LAUNCH_OK();
         return GNAN_OK;
     }
-    if (precision != GNAN_PREC_FP32) {
-        if (!gnan_mlp_tc_supported(p, precision)) {
-            gnan_set_error("mlp_fwd: precision %d needs H == 64, n_layers == 3, C <= 64 (got H=%d L=%d C=%d)", precision, p->H, p->n_layers, p->C);
-            return GNAN_ERR_UNSUPPORTED;
-        }
+    // shapes the tensor-core path does not cover run the (more precise) fp32 kernel
+    if (precision != GNAN_PREC_FP32 && gnan_mlp_tc_supported(p, precision))
         return gnan_mlp_tc_fwd(u, R, ldu, p, dropout_p, seed, precision, S, workspace, workspace_bytes, st);
-    }
     const FwdPlan pl = plan_fwd(R, p);
     float *Spart = S;
     if (pl.nchunk > 1) {
@@ -729,8 +713,8 @@ extern "C" int gnan_mlp_fwd(const float *u, int64_t R, int64_t ldu, const gnan_m
     if (rc) return rc;
     if (pl.nchunk > 1) {
         const size_t n = (size_t)R * p->C;
-        reduce_strided_kernel<<<(unsigned)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(Spart, pl.nchunk, n, n, S);
-        GNAN_LAUNCH_OK();
+        rc = gnan_reduce_chunks(Spart, pl.nchunk, n, n, S, st);
+        if (rc) return rc;
     }
     return GNAN_OK;
 }
@@ -761,13 +745,8 @@ extern "C" int gnan_mlp_bwd(const float *u, int64_t R, int64_t ldu, const gnan_m
         if (grads->bo) GNAN_CUDA(cudaMemsetAsync(grads->bo, 0, sizeof(float) * G * C, st));
         return GNAN_OK;
     }
-    if (precision != GNAN_PREC_FP32) {
-        if (!gnan_mlp_tc_supported(p, precision)) {
-            gnan_set_error("mlp_bwd: precision %d needs H == 64, n_layers == 3, C <= 64 (got H=%d L=%d C=%d)", precision, p->H, p->n_layers, p->C);
-            return GNAN_ERR_UNSUPPORTED;
-        }
+    if (precision != GNAN_PREC_FP32 && gnan_mlp_tc_bwd_supported(p, precision))
         return gnan_mlp_tc_bwd(u, R, ldu, p, dropout_p, seed, precision, dS, grads, workspace, workspace_bytes, st);
-    }
     const BwdPlan pl = plan_bwd(R, p);
     MlpGradPtrs gp;
     const size_t ntot = grad_floats(p);
@@ -802,9 +781,8 @@ extern "C" int gnan_mlp_bwd(const float *u, int64_t R, int64_t ldu, const gnan_m
                              {gp.bh, grads->bh, nh * G * H}, {gp.wo, grads->wo, G * C * H}, {gp.bo, grads->bo, G * C}};
         for (const Seg &s : segs) {
             if (!s.dst || s.n == 0) continue;
-            const unsigned blocks = (unsigned)std::min<size_t>((s.n + 255) / 256, 148 * 8);
-            reduce_strided_kernel<<<blocks, 256, 0, st>>>(s.src, pl.nchunk, s.n, ntot, s.dst);
-            GNAN_LAUNCH_OK();
+            rc = gnan_reduce_chunks(s.src, pl.nchunk, s.n, ntot, s.dst, st);
+            if (rc) return rc;
         }
     }
     return GNAN_OK;

@@ -336,3 +336,40 @@ def test_large_row_block_vs_lut_oracle():
     assert G.rel_err(out.detach().cpu().numpy(), want.detach().numpy()) < TOL
     assert G.rel_err(m.fs.wh.grad.cpu().numpy(), fs["wh"].grad.numpy()) < TOL
     assert G.rel_err(m.rho.wo.grad.cpu().numpy(), rho["wo"].grad.numpy()) < TOL
+
+
+# ---- tensor-core (tcgen05) path of the grouped MLP -------------------------------------------------------------------
+@pytest.mark.parametrize("precision,tol", [("tf32x3", 1e-5), ("tf32", 5e-3)])
+@pytest.mark.parametrize("R,G_,C", [(1, 1, 1), (128, 2, 3), (129, 9, 7), (300, 15, 1), (1000, 40, 4), (2708, 70, 7), (5000, 3, 8)])
+def test_mlp_tensor_core_forward_vs_oracle(R, G_, C, precision, tol):
+    """3xTF32 split on tcgen05 keeps fp32-level accuracy (bound 1e-5, same as the fp32 path); single-pass tf32 has the
+    stated looser bound 5e-3."""
+    from gnan_b200 import ops
+    H, L = 64, 3
+    for attempt in range(50):
+        rng = np.random.default_rng(R * 11 + G_ + 1000 * attempt)
+        p = rand_mlp(rng, G_, H, C, L)
+        u = torch.tensor(rng.normal(size=(R, G_)) * (rng.random((R, G_)) < 0.7)).float()
+        if relu_margin(p, u) > 2e-6:
+            break
+    dS = torch.tensor(rng.normal(size=(R, C))).float()
+    q = oracle_params(p, L)
+    want = gnan_lut.feature_sums(q, u.double())
+    (want * dS.double()).sum().backward()
+    d = {k: v.to(DEV).requires_grad_(v.numel() > 0) for k, v in p.items()}
+    got = ops.mlp(u.to(DEV), d["w1"], d["b1"], d["wh"], d["bh"], d["wo"], d["bo"], L, precision=precision)
+    (got * dS.to(DEV)).sum().backward()
+    assert G.rel_err(got.detach().cpu().numpy(), want.detach().numpy()) < tol
+    for k in p:                                   # backward of this path (fp32 kernel until the tcgen05 backward lands)
+        assert G.rel_err(d[k].grad.cpu().numpy(), q[k].grad.numpy()) < max(tol, TOL), k
+
+
+def test_mlp_tensor_core_dropout_masks_match_fp32_path():
+    from gnan_b200 import ops
+    rng = np.random.default_rng(4)
+    R, G_, H, C, L = 700, 5, 64, 3, 3
+    p = {k: v.to(DEV) for k, v in rand_mlp(rng, G_, H, C, L).items()}
+    u = torch.tensor(rng.normal(size=(R, G_))).float().to(DEV)
+    a = ops.mlp(u, p["w1"], p["b1"], p["wh"], p["bh"], p["wo"], p["bo"], L, dropout_p=0.4, seed=77, precision="fp32")
+    b = ops.mlp(u, p["w1"], p["b1"], p["wh"], p["bh"], p["wo"], p["bo"], L, dropout_p=0.4, seed=77, precision="tf32x3")
+    assert G.rel_err(b.cpu().numpy(), a.cpu().numpy()) < 1e-4      # same masks; a ReLU kink may flip under a different rounding
