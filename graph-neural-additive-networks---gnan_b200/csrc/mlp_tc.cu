@@ -233,6 +233,386 @@ mlp_tc_fwd_kernel(TcArgs a, int KC, float *__restrict__ Spart)
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+
+// ---- backward ---------------------------------------------------------------------------------------------------------
+// CTA <-> (feature g, row chunk), 8 row warps + 1 MMA warp. A row warp owns 32 rows (one TMEM lane quadrant) x 32 of the
+// 64 hidden units (warps w and w+4 share a quadrant). Per 128-row tile:
+//   gen    a0 = relu(x w1 + b1) -> TMEM A (hi|lo)  and  -> smem sH (K-major over rows: B operand of MMA3)
+//   MMA1   z2 = a0 W2^T                                    (TS, 24 x [128x64x8])
+//   epiC   a1 = relu(z2+b2); dz2 = (g Wo) * 1[a1>0] -> TMEM A (hi|lo) and -> smem sZ (A operand of MMA3); db2 partial sums
+//   MMA2   d1 = dz2 W2                                     (TS, B = W2^T copy, 24 MMAs)
+//   MMA3   dW2 += [dz2_hi | dz2_lo]^T [a0_hi ; a0_lo]      (SS, M = 128 stacks hi/lo: all four split terms, 32 MMAs,
+//                                                           accumulator persistent in TMEM across the CTA's tiles)
+//   epiF   dz1 = d1 * 1[a0>0]; dw1/db1 partial sums
+//   dWo    a1 recomputed from TMEM, staged to smem (reusing sZ once MMA3 is done), dWo[c][j] += g[r][c] a1[r][j]
+// All smem operands are K-major with LBO = 144 B (a 16-byte skew per K chunk makes the transposing 4-byte stores of a
+// warp bank-conflict free); MN-major tf32 descriptors returned zeros on B200 (scratch/tc_probe3.cu), so they are avoided.
+constexpr int BWD_ROW_THREADS = 256;
+constexpr int BWD_THREADS = BWD_ROW_THREADS + 32;
+constexpr uint32_t T_LBO = 144;                    // bytes between K chunks (4 rows) of a transposed operand
+constexpr uint32_t T_SBO = 32 * T_LBO;             // 128 rows = 32 chunks per 8-unit block: 4608 B
+constexpr uint32_t T_KSTEP = 2 * T_LBO;            // one MMA K-step = 8 rows
+constexpr int T_BLK_FLOATS = T_SBO / 4;            // 1152 floats per 8-unit block
+
+struct BwdSmem {
+    float w_hi[HID * HID], w_lo[HID * HID];        // W2   [n=j][k=i]  (MMA1 B)
+    float wt_hi[HID * HID], wt_lo[HID * HID];      // W2^T [n=i][k=j]  (MMA2 B)
+    float sZ[16 * T_BLK_FLOATS];                   // dz2^T: 16 blocks of 8 units: 0-7 = hi, 8-15 = lo  (MMA3 A, M = 128); later scratch
+    float sH_hi[8 * T_BLK_FLOATS];                 // a0^T hi (MMA3 B, N = 64)
+    float sH_lo[8 * T_BLK_FLOATS];
+    float w1[HID], b1[HID], b2[HID];
+    float wo[CT_MAX][HID];
+    float sG[ROWS][CT_MAX];                        // dS tile
+    float red[8][HID];                             // cross-warp staging for the small reductions
+    uint64_t a1_full, a2_full, d1_full, d2_full, d3_full;
+    uint32_t tmem_base;
+};
+
+// float offset of (unit, row) inside a transposed K-major operand (unit = M/N index, row = K index)
+__device__ __forceinline__ int tidx(int unit, int row) { return (unit >> 3) * T_BLK_FLOATS + (row >> 2) * 36 + (unit & 7) * 4 + (row & 3); }
+
+// column sums over the 32 rows of a warp: on return lane l holds the sum of column l
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane)
+{
+#pragma unroll
+    for (int w = 16; w >= 1; w >>= 1) {
+        const bool up = (lane & w) != 0;
+#pragma unroll
+        for (int i = 0; i < w; ++i) {
+            const float send = up ? v[i] : v[i + w];
+            const float keep = up ? v[i + w] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+        }
+    }
+    return v[0];
+}
+
+struct TcGradPtrs { float *w1, *b1, *wh, *bh, *wo, *bo; size_t chunk_stride; };
+
+template <int CT, bool DROP>
+__global__ void __launch_bounds__(BWD_THREADS, 1)
+mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t ntiles)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    BwdSmem &sm = *reinterpret_cast<BwdSmem *>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = blockIdx.y;
+    const float dscale = DROP ? a.drop_scale : 1.f;
+
+    if (warp == 8) tmem_alloc(smem_u32(&sm.tmem_base), 512);
+    if (tid == 0) {
+        mbar_init(smem_u32(&sm.a1_full), BWD_ROW_THREADS);
+        mbar_init(smem_u32(&sm.a2_full), BWD_ROW_THREADS);
+        mbar_init(smem_u32(&sm.d1_full), 1);
+        mbar_init(smem_u32(&sm.d2_full), 1);
+        mbar_init(smem_u32(&sm.d3_full), 1);
+        mbar_init_fence();
+    }
+    // stage the feature's weights: W2 and W2^T split into hi/lo in the K-major core-matrix layout (LBO 128, SBO 2048)
+    {
+        const float *W = a.wh + (size_t)g * HID * HID;
+        for (int idx = tid; idx < HID * HID; idx += BWD_THREADS) {
+            const int j = idx >> 6, i = idx & 63;
+            uint32_t h, l;
+            split_tf32(__ldg(W + idx), h, l);
+            const int o = (j >> 3) * 512 + (i >> 2) * 32 + (j & 7) * 4 + (i & 3);       // (n=j, k=i)
+            const int ot = (i >> 3) * 512 + (j >> 2) * 32 + (i & 7) * 4 + (j & 3);      // (n=i, k=j)
+            sm.w_hi[o] = __uint_as_float(h); sm.w_lo[o] = __uint_as_float(l);
+            sm.wt_hi[ot] = __uint_as_float(h); sm.wt_lo[ot] = __uint_as_float(l);
+        }
+        if (tid < HID) {
+            sm.w1[tid] = __ldg(a.w1 + (size_t)g * HID + tid);
+            sm.b1[tid] = a.b1 ? __ldg(a.b1 + (size_t)g * HID + tid) : 0.f;
+            sm.b2[tid] = a.bh ? __ldg(a.bh + (size_t)g * HID + tid) : 0.f;
+            for (int c = 0; c < CT_MAX; ++c) sm.wo[c][tid] = c < a.C ? __ldg(a.wo + ((size_t)g * a.C + c) * HID + tid) : 0.f;
+        }
+        // the 16-byte gaps between K chunks are never read; zero the operand buffers once anyway (no NaN garbage)
+        for (int idx = tid; idx < 16 * T_BLK_FLOATS; idx += BWD_THREADS) sm.sZ[idx] = 0.f;
+        for (int idx = tid; idx < 8 * T_BLK_FLOATS; idx += BWD_THREADS) { sm.sH_hi[idx] = 0.f; sm.sH_lo[idx] = 0.f; }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+    const uint32_t colA_hi = 0, colA_lo = 64, colD1 = 128, colD2 = 192, colD3 = 256;
+
+    if (warp == 8) {
+        // ===== MMA issuer =====
+        const uint32_t idesc = umma_idesc_tf32(128, 64);
+        uint32_t it = 0;
+        for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const uint32_t ph = it & 1;
+            mbar_wait(smem_u32(&sm.a1_full), ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t bh = smem_u32(sm.w_hi), bl = smem_u32(sm.w_lo);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    umma_tf32_ts(tmem + colD1, tmem + colA_hi + ks * 8, umma_desc_kmajor(bh + ks * B_KSTEP, B_LBO, B_SBO), idesc, ks > 0);
+                if (!a.single_pass) {
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        umma_tf32_ts(tmem + colD1, tmem + colA_lo + ks * 8, umma_desc_kmajor(bh + ks * B_KSTEP, B_LBO, B_SBO), idesc, 1);
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        umma_tf32_ts(tmem + colD1, tmem + colA_hi + ks * 8, umma_desc_kmajor(bl + ks * B_KSTEP, B_LBO, B_SBO), idesc, 1);
+                }
+                umma_commit(smem_u32(&sm.d1_full));
+            }
+            __syncwarp();
+            mbar_wait(smem_u32(&sm.a2_full), ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t bh = smem_u32(sm.wt_hi), bl = smem_u32(sm.wt_lo);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    umma_tf32_ts(tmem + colD2, tmem + colA_hi + ks * 8, umma_desc_kmajor(bh + ks * B_KSTEP, B_LBO, B_SBO), idesc, ks > 0);
+                if (!a.single_pass) {
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        umma_tf32_ts(tmem + colD2, tmem + colA_lo + ks * 8, umma_desc_kmajor(bh + ks * B_KSTEP, B_LBO, B_SBO), idesc, 1);
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        umma_tf32_ts(tmem + colD2, tmem + colA_hi + ks * 8, umma_desc_kmajor(bl + ks * B_KSTEP, B_LBO, B_SBO), idesc, 1);
+                }
+                umma_commit(smem_u32(&sm.d2_full));
+                // dW2 accumulation over the 128 rows of the tile: A = sZ (M = 128: hi|lo), B = sH hi then lo
+                const uint32_t za = smem_u32(sm.sZ), hh = smem_u32(sm.sH_hi), hl = smem_u32(sm.sH_lo);
+#pragma unroll 4
+                for (int ks = 0; ks < 16; ++ks)
+                    umma_tf32_ss(tmem + colD3, umma_desc_kmajor(za + ks * T_KSTEP, T_LBO, T_SBO),
+                                 umma_desc_kmajor(hh + ks * T_KSTEP, T_LBO, T_SBO), idesc, (it > 0 || ks > 0) ? 1u : 0u);
+                if (!a.single_pass) {
+#pragma unroll 4
+                    for (int ks = 0; ks < 16; ++ks)
+                        umma_tf32_ss(tmem + colD3, umma_desc_kmajor(za + ks * T_KSTEP, T_LBO, T_SBO),
+                                     umma_desc_kmajor(hl + ks * T_KSTEP, T_LBO, T_SBO), idesc, 1);
+                }
+                umma_commit(smem_u32(&sm.d3_full));
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== row warps =====
+        const int q = warp & 3, half = warp >> 2;
+        const int r = q * 32 + lane;                       // row inside the tile == TMEM lane
+        const int c0 = half * 32;                          // this thread's 32 hidden units
+        const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
+        float acc_wo[CT];                                  // dWo[c][j = tid & 63] over rows (tid >> 6)*32..+31 of every tile
+#pragma unroll
+        for (int c = 0; c < CT; ++c) acc_wo[c] = 0.f;
+        float p_b2 = 0.f, p_b1 = 0.f, p_w1 = 0.f;          // column (c0 + lane) sums over this warp's rows
+        float p_bo = 0.f;                                  // dbo[tid] (tid < C)
+        uint32_t it = 0;
+        for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const uint32_t ph = it & 1;
+            const int64_t row = t * ROWS + r;
+            const bool row_ok = row < a.R;
+            const float x = row_ok ? __ldg(a.u + row * a.ldu + g) : 0.f;
+            float gv[CT];
+#pragma unroll
+            for (int c = 0; c < CT; ++c) gv[c] = (row_ok && c < a.C) ? __ldg(dS + row * a.C + c) : 0.f;
+            if (half == 0) {
+#pragma unroll
+                for (int c = 0; c < CT; ++c) sm.sG[r][c] = gv[c];
+            }
+            // ---- gen: a0 for units c0..c0+31
+            {
+                uint32_t hi[32], lo[32];
+#pragma unroll
+                for (int i4 = 0; i4 < 8; ++i4) {
+                    const float4 w = *reinterpret_cast<const float4 *>(sm.w1 + c0 + i4 * 4);
+                    const float4 b = *reinterpret_cast<const float4 *>(sm.b1 + c0 + i4 * 4);
+                    float v[4] = {fmaxf(fmaf(x, w.x, b.x), 0.f), fmaxf(fmaf(x, w.y, b.y), 0.f),
+                                  fmaxf(fmaf(x, w.z, b.z), 0.f), fmaxf(fmaf(x, w.w, b.w), 0.f)};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int i = c0 + i4 * 4 + e;
+                        if (DROP) v[e] *= gnan_dropout_mul(a.seed, tc_drop_key(a, 0, g, row, i), a.drop_thresh, a.drop_scale);
+                        split_tf32(v[e], hi[i4 * 4 + e], lo[i4 * 4 + e]);
+                        sm.sH_hi[tidx(i, r)] = __uint_as_float(hi[i4 * 4 + e]);
+                        sm.sH_lo[tidx(i, r)] = __uint_as_float(lo[i4 * 4 + e]);
+                    }
+                }
+                tmem_st32(lane_base + colA_hi + c0, hi);
+                if (!a.single_pass) tmem_st32(lane_base + colA_lo + c0, lo);
+            }
+            tmem_wait_st();
+            fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(smem_u32(&sm.a1_full));
+            // ---- epiC
+            mbar_wait(smem_u32(&sm.d1_full), ph);
+            tc_fence_after();
+            {
+                uint32_t d[32];
+                tmem_ld32(lane_base + colD1 + c0, d);
+                tmem_wait_ld();
+                uint32_t hi[32], lo[32];
+                float dz[32];
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 b = *reinterpret_cast<const float4 *>(sm.b2 + c0 + j4 * 4);
+                    const float bb[4] = {b.x, b.y, b.z, b.w};
+                    float dh[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int c = 0; c < CT; ++c) {
+                        const float4 w = *reinterpret_cast<const float4 *>(sm.wo[c] + c0 + j4 * 4);
+                        dh[0] = fmaf(gv[c], w.x, dh[0]); dh[1] = fmaf(gv[c], w.y, dh[1]);
+                        dh[2] = fmaf(gv[c], w.z, dh[2]); dh[3] = fmaf(gv[c], w.w, dh[3]);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int jj = j4 * 4 + e, j = c0 + jj;
+                        float act = fmaxf(__uint_as_float(d[jj]) + bb[e], 0.f);
+                        float m = act > 0.f ? 1.f : 0.f;
+                        if (DROP) m *= gnan_dropout_mul(a.seed, tc_drop_key(a, 1, g, row, j), a.drop_thresh, a.drop_scale);
+                        dz[jj] = dh[e] * m;
+                        split_tf32(dz[jj], hi[jj], lo[jj]);
+                        sm.sZ[tidx(j, r)] = __uint_as_float(hi[jj]);
+                        sm.sZ[tidx(64 + j, r)] = __uint_as_float(lo[jj]);
+                    }
+                }
+                tmem_st32(lane_base + colA_hi + c0, hi);
+                if (!a.single_pass) tmem_st32(lane_base + colA_lo + c0, lo);
+                tmem_wait_st();
+                fence_async_smem();
+                tc_fence_before();
+                mbar_arrive(smem_u32(&sm.a2_full));
+                p_b2 += warp_colsum32(dz, lane);
+            }
+            // ---- epiF
+            mbar_wait(smem_u32(&sm.d2_full), ph);
+            tc_fence_after();
+            {
+                uint32_t d[32];
+                tmem_ld32(lane_base + colD2 + c0, d);
+                tmem_wait_ld();
+                float z0[32], z1[32];
+#pragma unroll
+                for (int i4 = 0; i4 < 8; ++i4) {
+                    const float4 w = *reinterpret_cast<const float4 *>(sm.w1 + c0 + i4 * 4);
+                    const float4 b = *reinterpret_cast<const float4 *>(sm.b1 + c0 + i4 * 4);
+                    const float pre[4] = {fmaf(x, w.x, b.x), fmaf(x, w.y, b.y), fmaf(x, w.z, b.z), fmaf(x, w.w, b.w)};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int ii = i4 * 4 + e;
+                        float m = pre[e] > 0.f ? 1.f : 0.f;
+                        if (DROP) m *= gnan_dropout_mul(a.seed, tc_drop_key(a, 0, g, row, c0 + ii), a.drop_thresh, a.drop_scale);
+                        z0[ii] = __uint_as_float(d[ii]) * m;
+                        z1[ii] = z0[ii] * x;
+                    }
+                }
+                p_b1 += warp_colsum32(z0, lane);
+                p_w1 += warp_colsum32(z1, lane);
+            }
+            // ---- dWo: wait until MMA3 has consumed sZ / sH, then reuse sZ as an fp32 [row][unit] scratch tile (ld 68)
+            mbar_wait(smem_u32(&sm.d3_full), ph);
+            tc_fence_after();
+            {
+                uint32_t d[32];
+                tmem_ld32(lane_base + colD1 + c0, d);
+                tmem_wait_ld();
+                float *scr = sm.sZ;
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 b = *reinterpret_cast<const float4 *>(sm.b2 + c0 + j4 * 4);
+                    float v[4] = {fmaxf(__uint_as_float(d[j4 * 4 + 0]) + b.x, 0.f), fmaxf(__uint_as_float(d[j4 * 4 + 1]) + b.y, 0.f),
+                                  fmaxf(__uint_as_float(d[j4 * 4 + 2]) + b.z, 0.f), fmaxf(__uint_as_float(d[j4 * 4 + 3]) + b.w, 0.f)};
+                    if (DROP) {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            v[e] *= gnan_dropout_mul(a.seed, tc_drop_key(a, 1, g, row, c0 + j4 * 4 + e), a.drop_thresh, a.drop_scale);
+                    }
+                    *reinterpret_cast<float4 *>(scr + r * 68 + c0 + j4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
+                }
+                tc_fence_before();
+                named_bar_sync(1, BWD_ROW_THREADS);
+                const int j = tid & 63, r0 = (tid >> 6) * 32;
+#pragma unroll 4
+                for (int rr = 0; rr < 32; ++rr) {
+                    const float hv = scr[(r0 + rr) * 68 + j];
+                    const float4 g0 = *reinterpret_cast<const float4 *>(&sm.sG[r0 + rr][0]);
+                    const float4 g1 = *reinterpret_cast<const float4 *>(&sm.sG[r0 + rr][4]);
+                    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+                    for (int c = 0; c < CT; ++c) acc_wo[c] = fmaf(gg[c], hv, acc_wo[c]);
+                }
+                if (tid < a.C) {
+                    float s = 0.f;
+                    for (int rr = 0; rr < ROWS; ++rr) s += sm.sG[rr][tid];
+                    p_bo += s;
+                }
+                named_bar_sync(1, BWD_ROW_THREADS);      // scratch and sG are rewritten by the next tile
+            }
+        }
+        // ---- write this CTA's partial gradients (everything but dW2)
+        const size_t off = (size_t)blockIdx.x * gp.chunk_stride;
+        // cross-warp sums: red[warp][unit]
+        float *red = &sm.red[0][0];
+        named_bar_sync(1, BWD_ROW_THREADS);
+        red[warp * HID + lane] = p_b2; red[warp * HID + 32 + lane] = 0.f;
+        named_bar_sync(1, BWD_ROW_THREADS);
+        if (tid < HID && gp.bh) {   // unit tid lives in warps with half == tid/32: warps (tid>>5)*4 .. +3, lane tid&31
+            float s = 0.f;
+            for (int w = 0; w < 4; ++w) s += red[((tid >> 5) * 4 + w) * HID + (tid & 31)];
+            gp.bh[off + (size_t)g * HID + tid] = s;
+        }
+        named_bar_sync(1, BWD_ROW_THREADS);
+        red[warp * HID + lane] = p_b1; red[warp * HID + 32 + lane] = p_w1;
+        named_bar_sync(1, BWD_ROW_THREADS);
+        if (tid < HID) {
+            float s0 = 0.f, s1 = 0.f;
+            for (int w = 0; w < 4; ++w) {
+                s0 += red[((tid >> 5) * 4 + w) * HID + (tid & 31)];
+                s1 += red[((tid >> 5) * 4 + w) * HID + 32 + (tid & 31)];
+            }
+            if (gp.b1) gp.b1[off + (size_t)g * HID + tid] = s0;
+            if (gp.w1) gp.w1[off + (size_t)g * HID + tid] = s1;
+        }
+        named_bar_sync(1, BWD_ROW_THREADS);
+        // dWo: thread holds rows quarter (tid>>6) of unit (tid&63) -> sum the four quarters
+        float *scr = sm.sZ;
+#pragma unroll
+        for (int c = 0; c < CT; ++c) scr[(c * 4 + (tid >> 6)) * HID + (tid & 63)] = acc_wo[c];
+        named_bar_sync(1, BWD_ROW_THREADS);
+        if (gp.wo)
+            for (int idx = tid; idx < a.C * HID; idx += BWD_ROW_THREADS) {
+                const int c = idx >> 6, j = idx & 63;
+                gp.wo[off + (size_t)g * a.C * HID + idx] = scr[(c * 4 + 0) * HID + j] + scr[(c * 4 + 1) * HID + j] +
+                                                          scr[(c * 4 + 2) * HID + j] + scr[(c * 4 + 3) * HID + j];
+            }
+        if (tid < a.C && gp.bo) gp.bo[off + (size_t)g * a.C + tid] = p_bo;
+        named_bar_sync(1, BWD_ROW_THREADS);
+        // ---- dW2 = D3[lane j] + D3[lane 64 + j]  (hi and lo halves of the stacked A operand); all MMAs are complete (d3_full)
+        if (half == 0) {           // warps 0-3 cover all 128 lanes; 64 columns each
+            uint32_t d[64];
+            tmem_ld64(lane_base + colD3, d);
+            tmem_wait_ld();
+            if (r >= 64) {
+#pragma unroll
+                for (int i = 0; i < 64; i += 4)
+                    *reinterpret_cast<float4 *>(scr + (r - 64) * 68 + i) =
+                        make_float4(__uint_as_float(d[i]), __uint_as_float(d[i + 1]), __uint_as_float(d[i + 2]), __uint_as_float(d[i + 3]));
+            }
+            named_bar_sync(2, 128);
+            if (r < 64 && gp.wh) {
+                float *dst = gp.wh + off + ((size_t)g * HID + r) * HID;
+#pragma unroll
+                for (int i = 0; i < 64; i += 4) {
+                    const float4 o = *reinterpret_cast<const float4 *>(scr + r * 68 + i);
+                    *reinterpret_cast<float4 *>(dst + i) = make_float4(__uint_as_float(d[i]) + o.x, __uint_as_float(d[i + 1]) + o.y,
+                                                                       __uint_as_float(d[i + 2]) + o.z, __uint_as_float(d[i + 3]) + o.w);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(tmem, 512);
+}
+
 struct TcFwdPlan { int KC, nchunk; int64_t ntile; };
 
 TcFwdPlan plan_tc_fwd(int64_t R, const gnan_mlp_params *p)
@@ -277,13 +657,49 @@ int gnan_mlp_tc_supported(const gnan_mlp_params *p, int precision)
     return (precision == GNAN_PREC_TF32X3 || precision == GNAN_PREC_TF32) && p->H == HID && p->n_layers == 3 && p->C <= CT_MAX;
 }
 
-// forward only for now: the backward of the tensor-core path still runs the fp32 kernel (same dropout keys)
-int gnan_mlp_tc_bwd_supported(const gnan_mlp_params *, int) { return 0; }
+int gnan_mlp_tc_bwd_supported(const gnan_mlp_params *p, int precision) { return gnan_mlp_tc_supported(p, precision); }
+
+namespace {
+inline size_t pad4(size_t n) { return (n + 3) / 4 * 4; }
+size_t tc_grad_floats(const gnan_mlp_params *p)
+{
+    const size_t G = p->G, C = p->C;
+    return 2 * pad4(G * HID) + pad4(G * HID * HID) + pad4(G * HID) + pad4(G * C * HID) + pad4(G * C);
+}
+struct TcBwdPlan { int nchunk; int64_t ntile; };
+TcBwdPlan plan_tc_bwd(int64_t R, const gnan_mlp_params *p)
+{
+    TcBwdPlan pl;
+    pl.ntile = ceil_div64(R, ROWS);
+    int nchunk = (int)ceil_div64(2 * gnan_sm_count(), p->G);
+    if (nchunk > pl.ntile) nchunk = (int)pl.ntile;
+    pl.nchunk = std::max(nchunk, 1);
+    return pl;
+}
+template <int CT>
+int launch_tc_bwd(const TcArgs &a, const TcBwdPlan &pl, const float *dS, const TcGradPtrs &gp, cudaStream_t st)
+{
+    const size_t smem = sizeof(BwdSmem) + 1024;
+    dim3 grid((unsigned)pl.nchunk, (unsigned)a.G);
+    if (a.drop_thresh) {
+        GNAN_CUDA(cudaFuncSetAttribute(mlp_tc_bwd_kernel<CT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mlp_tc_bwd_kernel<CT, true><<<grid, BWD_THREADS, smem, st>>>(a, dS, gp, pl.ntile);
+    } else {
+        GNAN_CUDA(cudaFuncSetAttribute(mlp_tc_bwd_kernel<CT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mlp_tc_bwd_kernel<CT, false><<<grid, BWD_THREADS, smem, st>>>(a, dS, gp, pl.ntile);
+    }
+    GNAN_LAUNCH_OK();
+    return GNAN_OK;
+}
+}  // namespace
 
 size_t gnan_mlp_tc_workspace_bytes(int64_t R, const gnan_mlp_params *p, int backward, int precision)
 {
     (void)precision;
-    if (backward) return 0;
+    if (backward) {
+        const TcBwdPlan pl = plan_tc_bwd(R, p);
+        return pl.nchunk > 1 ? sizeof(float) * (size_t)pl.nchunk * tc_grad_floats(p) : 0;
+    }
     const TcFwdPlan pl = plan_tc_fwd(R, p);
     return pl.nchunk > 1 ? sizeof(float) * (size_t)pl.nchunk * R * p->C : 0;
 }
@@ -312,9 +728,46 @@ int gnan_mlp_tc_fwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_param
     return GNAN_OK;
 }
 
-int gnan_mlp_tc_bwd(const float *, int64_t, int64_t, const gnan_mlp_params *, float, uint64_t, int, const float *,
-                    const gnan_mlp_grads *, void *, size_t, cudaStream_t)
+int gnan_mlp_tc_bwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *p, float dropout_p, uint64_t seed,
+                    int precision, const float *dS, const gnan_mlp_grads *grads, void *ws, size_t ws_bytes, cudaStream_t st)
 {
-    gnan_set_error("tcgen05 mlp backward not built");
-    return GNAN_ERR_UNSUPPORTED;
+    const TcBwdPlan pl = plan_tc_bwd(R, p);
+    const size_t G = p->G, C = p->C, ntot = tc_grad_floats(p);
+    TcGradPtrs gp;
+    if (pl.nchunk > 1) {
+        const size_t need = sizeof(float) * (size_t)pl.nchunk * ntot;
+        if (!ws || ws_bytes < need) {
+            gnan_set_error("mlp_bwd(tc): workspace %zu < %zu bytes", ws_bytes, need);
+            return GNAN_ERR_WORKSPACE;
+        }
+        float *w = (float *)ws;
+        gp.w1 = w; w += pad4(G * HID);
+        gp.b1 = w; w += pad4(G * HID);
+        gp.wh = w; w += pad4(G * HID * HID);
+        gp.bh = w; w += pad4(G * HID);
+        gp.wo = w; w += pad4(G * C * HID);
+        gp.bo = w;
+        gp.chunk_stride = ntot;
+    } else {
+        gp.w1 = grads->w1; gp.b1 = grads->b1; gp.wh = grads->wh; gp.bh = grads->bh; gp.wo = grads->wo; gp.bo = grads->bo;
+        gp.chunk_stride = 0;
+    }
+    const TcArgs a = make_tc_args(u, R, ldu, p, dropout_p, seed, precision);
+    int rc;
+    if (p->C == 1) rc = launch_tc_bwd<1>(a, pl, dS, gp, st);
+    else if (p->C == 2) rc = launch_tc_bwd<2>(a, pl, dS, gp, st);
+    else if (p->C <= 4) rc = launch_tc_bwd<4>(a, pl, dS, gp, st);
+    else rc = launch_tc_bwd<8>(a, pl, dS, gp, st);
+    if (rc) return rc;
+    if (pl.nchunk > 1) {
+        struct Seg { const float *src; float *dst; size_t n; };
+        const Seg segs[6] = {{gp.w1, grads->w1, G * HID}, {gp.b1, grads->b1, G * HID}, {gp.wh, grads->wh, G * HID * HID},
+                             {gp.bh, grads->bh, G * HID}, {gp.wo, grads->wo, G * C * HID}, {gp.bo, grads->bo, G * C}};
+        for (const Seg &sg : segs) {
+            if (!sg.dst || sg.n == 0) continue;
+            rc = gnan_reduce_chunks(sg.src, pl.nchunk, sg.n, ntot, sg.dst, st);
+            if (rc) return rc;
+        }
+    }
+    return GNAN_OK;
 }

@@ -339,19 +339,23 @@ def test_large_row_block_vs_lut_oracle():
 
 
 # ---- tensor-core (tcgen05) path of the grouped MLP -------------------------------------------------------------------
-@pytest.mark.parametrize("precision,tol", [("tf32x3", 1e-5), ("tf32", 5e-3)])
-@pytest.mark.parametrize("R,G_,C", [(1, 1, 1), (128, 2, 3), (129, 9, 7), (300, 15, 1), (1000, 40, 4), (2708, 70, 7), (5000, 3, 8)])
-def test_mlp_tensor_core_forward_vs_oracle(R, G_, C, precision, tol):
-    """3xTF32 split on tcgen05 keeps fp32-level accuracy (bound 1e-5, same as the fp32 path); single-pass tf32 has the
-    stated looser bound 5e-3."""
+@pytest.mark.parametrize("precision,tol,gtol", [("tf32x3", 1e-5, 1e-5), ("tf32", 5e-3, 5e-2)])
+@pytest.mark.parametrize("R,G_,C", [(1, 1, 1), (128, 2, 3), (129, 9, 7), (300, 15, 1), (700, 40, 4), (1100, 6, 7), (600, 3, 8)])
+def test_mlp_tensor_core_vs_oracle(R, G_, C, precision, tol, gtol):
+    """Forward and backward on tcgen05. The 3xTF32 split keeps fp32-level accuracy: bound 1e-5 for outputs AND gradients
+    (measured 7e-7 / 3e-6). Single-pass tf32 has the stated looser bounds 5e-3 (outputs) / 5e-2 (gradients: its 1e-3
+    forward noise flips ReLU masks). Inputs are drawn with every float64 pre-activation at least 2e-5 from zero so that
+    no mask flips under the 1e-6 rounding differences of the split."""
     from gnan_b200 import ops
     H, L = 64, 3
-    for attempt in range(50):
+    for attempt in range(400):
         rng = np.random.default_rng(R * 11 + G_ + 1000 * attempt)
         p = rand_mlp(rng, G_, H, C, L)
         u = torch.tensor(rng.normal(size=(R, G_)) * (rng.random((R, G_)) < 0.7)).float()
-        if relu_margin(p, u) > 2e-6:
+        if relu_margin(p, u) > 2e-5:
             break
+    else:
+        raise AssertionError("could not draw a kink-free case")
     dS = torch.tensor(rng.normal(size=(R, C))).float()
     q = oracle_params(p, L)
     want = gnan_lut.feature_sums(q, u.double())
@@ -360,8 +364,30 @@ def test_mlp_tensor_core_forward_vs_oracle(R, G_, C, precision, tol):
     got = ops.mlp(u.to(DEV), d["w1"], d["b1"], d["wh"], d["bh"], d["wo"], d["bo"], L, precision=precision)
     (got * dS.to(DEV)).sum().backward()
     assert G.rel_err(got.detach().cpu().numpy(), want.detach().numpy()) < tol
-    for k in p:                                   # backward of this path (fp32 kernel until the tcgen05 backward lands)
-        assert G.rel_err(d[k].grad.cpu().numpy(), q[k].grad.numpy()) < max(tol, TOL), k
+    for k in p:
+        assert G.rel_err(d[k].grad.cpu().numpy(), q[k].grad.numpy()) < gtol, k
+
+
+def test_mlp_tensor_core_cora_sized_multi_tile():
+    """Cora-sized rows (22 tiles per CTA, partial-gradient chunks): outputs to 1e-5; gradients are compared with a bound that
+    tolerates the handful of ReLU-kink flips unavoidable among 12 M pre-activations (each flip moves ~3e-4 of one group)."""
+    from gnan_b200 import ops
+    R, G_, C, H, L = 2708, 70, 7, 64, 3
+    rng = np.random.default_rng(2)
+    p = rand_mlp(rng, G_, H, C, L)
+    u = torch.tensor(rng.normal(size=(R, G_)) * (rng.random((R, G_)) < 0.7)).float()
+    dS = torch.tensor(rng.normal(size=(R, C))).float()
+    q = oracle_params(p, L)
+    want = gnan_lut.feature_sums(q, u.double())
+    (want * dS.double()).sum().backward()
+    d = {k: v.to(DEV).requires_grad_(True) for k, v in p.items()}
+    got = ops.mlp(u.to(DEV), d["w1"], d["b1"], d["wh"], d["bh"], d["wo"], d["bo"], L, precision="tf32x3")
+    (got * dS.to(DEV)).sum().backward()
+    assert G.rel_err(got.detach().cpu().numpy(), want.detach().numpy()) < TOL
+    for k in ("wo", "bo"):
+        assert G.rel_err(d[k].grad.cpu().numpy(), q[k].grad.numpy()) < TOL, k          # not affected by mask flips
+    for k in ("w1", "b1", "wh", "bh"):
+        assert G.rel_err(d[k].grad.cpu().numpy(), q[k].grad.numpy()) < 1e-3, k
 
 
 def test_mlp_tensor_core_dropout_masks_match_fp32_path():
@@ -373,3 +399,20 @@ def test_mlp_tensor_core_dropout_masks_match_fp32_path():
     a = ops.mlp(u, p["w1"], p["b1"], p["wh"], p["bh"], p["wo"], p["bo"], L, dropout_p=0.4, seed=77, precision="fp32")
     b = ops.mlp(u, p["w1"], p["b1"], p["wh"], p["bh"], p["wo"], p["bo"], L, dropout_p=0.4, seed=77, precision="tf32x3")
     assert G.rel_err(b.cpu().numpy(), a.cpu().numpy()) < 1e-4      # same masks; a ReLU kink may flip under a different rounding
+
+
+def test_mlp_tensor_core_backward_with_dropout_matches_fp32_path():
+    from gnan_b200 import ops
+    rng = np.random.default_rng(6)
+    R, G_, H, C, L = 900, 6, 64, 7, 3
+    p = rand_mlp(rng, G_, H, C, L)
+    u = torch.tensor(rng.normal(size=(R, G_))).float().to(DEV)
+    dS = torch.tensor(rng.normal(size=(R, C))).float().to(DEV)
+    grads = {}
+    for prec in ("fp32", "tf32x3"):
+        d = {k: v.to(DEV).requires_grad_(True) for k, v in p.items()}
+        out = ops.mlp(u, d["w1"], d["b1"], d["wh"], d["bh"], d["wo"], d["bo"], L, dropout_p=0.3, seed=5, precision=prec)
+        (out * dS).sum().backward()
+        grads[prec] = {k: v.grad.cpu().numpy() for k, v in d.items()}
+    for k in p:
+        assert G.rel_err(grads["tf32x3"][k], grads["fp32"][k]) < 2e-4, k     # same masks; a kink may flip under different rounding
