@@ -1,15 +1,18 @@
 #!/usr/bin/env python
 """Benchmark of the GNAN hot path (BASELINE.json metric: fwd+bwd nodes/s on node tasks, graphs/s on graph tasks).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cora|pubmed|mutag] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cora|pubmed|mutag] [--precision tf32x3|fp32|tf32]
+                    [--impl reference]
 
 Default workload = BASELINE.json configs[1]: TensorGNAN (GNAN.py:9-79) node classification on a Cora-shaped synthetic
 graph (2708 nodes, 1433 features + the constant column, 7 classes, hidden 64, 3 layers), dense all-pairs hop distances.
-A step is forward + cross-entropy on the 140 train-mask rows + backward + Adam step (trainer.py:48-67).
+A step is forward + loss + backward + Adam step (trainer.py:48-67). Other workloads: `pubmed` (configs[2]; row-sharded
+with an all-gather of S when N > 1), `mutag` (configs[0]: 4337 Mutagenicity-shaped graphs per step in packed
+block-diagonal form, data-parallel with one gradient all-reduce when N > 1).
 
 One JSON line on stdout (rank 0). `value` times the step with inputs resident in HBM (CUDA events per step, L2 flushed
-between steps); `e2e` times the same step through the module API from pinned HOST buffers (x, hop bytes, level counts
-copied every step, loss read back every step). `roofline` describes the dominant kernel (the grouped shape-MLP
+between steps); `e2e` times the same step through the module API from pinned HOST buffers (features, hop bytes, level
+counts copied every step, loss read back every step). `roofline` describes the dominant kernel (the grouped shape-MLP
 backward), timed live with CUDA events on the launching stream. `cpu_baseline` / `--impl reference` time the oracle's
 port of the reference's own CPU path (oracle/gnan_port.py: the reference is pure Python and cannot travel to the GPU
 box) with all host threads.
@@ -55,18 +58,48 @@ def make_node_workload(name, seed=0):
         n, k_raw, c, e_und, iso, dens = 2708, 1433, 7, 5278, 54, 0.0127
         x = (rng.random((n, k_raw)) < dens).astype(np.float32)
         x /= np.maximum(x.sum(1, keepdims=True), 1.0)                       # row-normalised bag of words (datasets.py:94)
-    elif name == "pubmed":
+        desc = "cora-shape TensorGNAN node classification (BASELINE.json configs[1])"
+    else:
         n, k_raw, c, e_und, iso, dens = 19717, 500, 3, 44338, 0, 0.10
         x = ((rng.random((n, k_raw)) < dens) * rng.random((n, k_raw)) * 0.1).astype(np.float32)
-    else:
-        raise ValueError(name)
+        desc = "pubmed-shape TensorGNAN node classification (BASELINE.json configs[2])"
     x = np.concatenate([x, np.ones((n, 1), np.float32)], 1)                 # pre_process_datasets.py:127
     ei = random_simple_graph(rng, n, e_und, iso)
     y = rng.integers(0, c, size=n)
     mask = np.zeros(n, bool)
     mask[rng.permutation(n)[:140]] = True
-    return SimpleNamespace(name=name, n=n, K=k_raw + 1, C=c, x=torch.from_numpy(x), edge_index=torch.from_numpy(ei),
-                           y=torch.from_numpy(y), train_mask=torch.from_numpy(mask), unit="nodes/s", units_per_step=n)
+    return SimpleNamespace(kind="node", name=name, desc=desc, n=n, K=k_raw + 1, C=c, x=torch.from_numpy(x),
+                           edge_index=torch.from_numpy(ei), y=torch.from_numpy(y), train_mask=torch.from_numpy(mask),
+                           unit="nodes/s", units_per_step=n, evals_per_step=n * (k_raw + 1))
+
+
+def make_graph_workload(seed=0, n_graphs=4337):
+    """Mutagenicity-shaped batch: n_g = clip(round(N(30.3, 20)), 4, 120), random tree + ceil(n/10) extra edges, one-hot over
+    14 atom types + the constant column (K = 15), binary labels, C = 1 (main.py:347-349)."""
+    rng = np.random.default_rng(seed)
+    sizes = np.clip(np.round(rng.normal(30.3, 20.0, size=n_graphs)), 4, 120).astype(np.int64)
+    node_off = np.concatenate([[0], np.cumsum(sizes)])
+    src, dst = [], []
+    for g, n in enumerate(sizes):
+        par = np.array([rng.integers(0, v) for v in range(1, n)], dtype=np.int64)
+        e = set(zip(par.tolist(), range(1, n)))
+        extra = int(np.ceil(n / 10))
+        while extra > 0:
+            a, b = int(rng.integers(0, n)), int(rng.integers(0, n))
+            if a != b and (min(a, b), max(a, b)) not in e:
+                e.add((min(a, b), max(a, b))); extra -= 1
+        e = np.array(sorted(e), dtype=np.int64) + node_off[g]
+        src += [e[:, 0], e[:, 1]]; dst += [e[:, 1], e[:, 0]]
+    ei = np.stack([np.concatenate(src), np.concatenate(dst)])
+    tot = int(node_off[-1])
+    x = np.zeros((tot, 15), np.float32)
+    x[np.arange(tot), rng.integers(0, 14, size=tot)] = 1.0
+    x[:, 14] = 1.0
+    y = rng.integers(0, 2, size=n_graphs).astype(np.float32)
+    return SimpleNamespace(kind="graph", name="mutag", desc="Mutagenicity-shape TensorGNAN graph classification, 4337 graphs per "
+                           "step in packed block-diagonal form (BASELINE.json configs[0])", n=tot, K=15, C=1,
+                           x=torch.from_numpy(x), edge_index=torch.from_numpy(ei), node_off=torch.from_numpy(node_off),
+                           sizes=sizes, y=torch.from_numpy(y), unit="graphs/s", units_per_step=n_graphs, evals_per_step=tot * 15)
 
 
 def flops_per_eval(C):
@@ -78,7 +111,7 @@ def clocks_sampler():
     q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     try:
-        return subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200",
+        return subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
                                  "-i", os.environ.get("LOCAL_RANK", "0")], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
     except Exception:
         return None
@@ -118,77 +151,117 @@ def measured_peaks():
     return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
+def workload_config(wl, where, world=1):
+    par = {"cora": "replicas only (SURVEY.md §8e: small node-level graph)",
+           "pubmed": "hop rows sharded over ranks, all-gather of S, reduce-scatter of dS, all-reduce of gradients" if world > 1 else "single GPU",
+           "mutag": "data-parallel graphs, one fused gradient all-reduce per step" if world > 1 else "single GPU"}[wl.name]
+    return {"workload": wl.desc, "nodes": wl.n, "features": wl.K, "classes": wl.C, "hidden": H, "n_layers": L,
+            "step": "forward + loss + backward + Adam", "normalize_rho": True,
+            "timing": "CUDA events per step; 256 MiB L2 flush between timed steps" if where == "gpu" else "perf_counter",
+            "parallelism": par}
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle's port of the reference CPU path
 # ---------------------------------------------------------------------------------------------------------------------
 def reference_step_fn(wl, seed=0):
-    """Returns (step_fn, n_threads). One step == the GPU arm's step, run by oracle.gnan_port on the host cores."""
+    """Returns (step_fn, n_threads, units_per_call, note). Runs oracle.gnan_port on the host cores."""
     from oracle import apsp as oapsp
     from oracle import gnan_port
     from oracle import params as P
-    from gnan_b200.GNAN import TensorGNAN
     torch.manual_seed(seed)
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    m = TensorGNAN(wl.K, wl.C, L, H, normalize_rho=True, is_graph_task=False)
+    if wl.kind == "node":
+        from gnan_b200.GNAN import TensorGNAN
+        m = TensorGNAN(wl.K, wl.C, L, H, normalize_rho=True, is_graph_task=False)
+    else:
+        from gnan_b200.models import TensorGNAN
+        m = TensorGNAN(wl.K, wl.C, L, H, normalize_rho=True, is_graph_task=True, readout_n_layers=0)
     m.fs.xavier_normal_(1.0); m.rho.xavier_normal_(1.0)
     sd = {k: v.detach().numpy() for k, v in m.state_dict().items()}
     fs = gnan_port.to_torch(P.stack_mlps(sd, [f"fs.{k}" for k in range(wl.K)], L, 3), torch.float32, True)
-    rho = gnan_port.to_torch(P.stack_mlps(sd, ["rho"], L, 2), torch.float32, True)
-    hop = oapsp.apsp(wl.edge_index.numpy(), wl.n)
-    nd, nm = oapsp.reference_format(hop, oapsp.level_counts(hop))
-    nd, nm = torch.from_numpy(nd), torch.from_numpy(nm)
+    rho = gnan_port.to_torch(P.stack_mlps(sd, ["rho"], L, 2, wl.kind == "node"), torch.float32, True)
     params = [t for d in (fs, rho) for t in d.values() if t is not None and t.requires_grad]
     opt = torch.optim.Adam(params, lr=1e-3)
-    loss_fn = torch.nn.CrossEntropyLoss()
+    if wl.name == "cora":
+        hop = oapsp.apsp(wl.edge_index.numpy(), wl.n)
+        nd, nm = (torch.from_numpy(t) for t in oapsp.reference_format(hop, oapsp.level_counts(hop)))
+        loss_fn = torch.nn.CrossEntropyLoss()
+
+        def step():
+            opt.zero_grad()
+            out = gnan_port.tensor_gnan_gnanpy(fs, rho, wl.x, nd, nm, True, False)       # GNAN.py:55-79, full graph
+            loss = loss_fn(out[wl.train_mask], wl.y[wl.train_mask])
+            loss.backward(); opt.step()
+            return float(loss.item())
+        return step, threads, wl.n, f"full {wl.name}-shape step (fwd+CE+bwd+Adam), GNAN.py TensorGNAN port"
+    if wl.name == "pubmed":                     # the shipped TensorGNAN cannot run at this shape (99.5 GB activation): row loop on 64 rows
+        rows = 64
+        hop = oapsp.apsp(wl.edge_index.numpy(), wl.n)
+        cnt = oapsp.level_counts(hop)
+        nd, nm = (torch.from_numpy(t) for t in oapsp.reference_format(hop[:rows], cnt[:rows]))
+        loss_fn = torch.nn.CrossEntropyLoss()
+
+        def step():
+            opt.zero_grad()
+            out = gnan_port.gnan_rowloop(fs, rho, wl.x, nd, nm, True, list(range(rows)))    # GNAN.py:146-172 on a [64,N] slice
+            loss = loss_fn(out, wl.y[:rows])
+            loss.backward(); opt.step()
+            return float(loss.item())
+        return step, threads, rows, "GNAN.forward(node_ids=range(64)) port on a [64,N] slice: rows/s, NOT a full step (full shape not runnable)"
+    # mutag: one graph per step (datasets.py:339-341, batch_size=1), models.TensorGNAN (what main.py builds)
+    graphs = []
+    for g in range(min(200, len(wl.sizes))):
+        b, e = int(wl.node_off[g]), int(wl.node_off[g + 1])
+        sel = (wl.edge_index[0] >= b) & (wl.edge_index[0] < e)
+        hop = oapsp.apsp((wl.edge_index[:, sel] - b).numpy(), e - b)
+        nd, nm = (torch.from_numpy(t) for t in oapsp.reference_format(hop, oapsp.level_counts(hop)))
+        graphs.append((wl.x[b:e], nd, nm, wl.y[g:g + 1]))
+    loss_fn = torch.nn.BCEWithLogitsLoss()
+    state = {"i": 0}
 
     def step():
+        x, nd, nm, y = graphs[state["i"] % len(graphs)]
+        state["i"] += 1
         opt.zero_grad()
-        out = gnan_port.tensor_gnan_gnanpy(fs, rho, wl.x, nd, nm, True, False)
-        loss = loss_fn(out[wl.train_mask], wl.y[wl.train_mask])
-        loss.backward()
-        opt.step()
+        out = gnan_port.tensor_gnan_models(fs, rho, x, nd, nm, True, True, None)         # models.py:358-384
+        loss = loss_fn(out.flatten(), y)
+        loss.backward(); opt.step()
         return float(loss.item())
+    return step, threads, 1, "one graph per step (batch_size=1 as datasets.py:339), models.py TensorGNAN port, fwd+BCE+bwd+Adam"
 
-    return step, threads
 
-
-def run_reference(args, wl):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    step, threads = reference_step_fn(wl)
-    budget_s = 300.0
+def time_reference(wl, steps, warmup, budget_s):
+    step, threads, units, note = reference_step_fn(wl)
     t_begin = time.perf_counter()
     w_done = 0
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         if time.perf_counter() - t_begin > budget_s / 4:
             break
         step(); w_done += 1
     times = []
-    for _ in range(args.steps):
+    for _ in range(steps):
         t0 = time.perf_counter(); step(); times.append(time.perf_counter() - t0)
         if time.perf_counter() - t_begin > budget_s:
             break
     ms = 1e3 * sum(times) / len(times)
-    val = wl.units_per_step / (ms / 1e3)
-    sample = f"{len(times)} full {wl.name}-shape steps (fwd+CE+bwd+Adam) after {w_done} warm-up, oracle/gnan_port.py on torch CPU"
+    return units / (ms / 1e3), ms, len(times), w_done, threads, note
+
+
+def run_reference(args, wl):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    steps = args.steps * (50 if wl.name == "mutag" else 1)          # mutag reference steps are single graphs (~20 ms each)
+    val, ms, n, w, threads, note = time_reference(wl, steps, args.warmup, 300.0)
     print(json.dumps({
         "impl": "reference", "metric": f"GNAN fwd+bwd {wl.unit} ({wl.name}-shape TensorGNAN)", "value": val, "unit": wl.unit,
-        "n_gpus": args.gpus, "steps": len(times), "warmup": w_done, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(wl, "cpu"),
-        "cpu_baseline": {"value": val, "unit": wl.unit, "cores": threads, "kind": "port", "sample": sample},
+        "n_gpus": args.gpus, "steps": n, "warmup": w, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(wl, "cpu"),
+        "cpu_baseline": {"value": val, "unit": wl.unit, "cores": threads, "kind": "port",
+                         "sample": f"{n} steps after {w} warm-up: {note}; oracle/gnan_port.py on torch CPU"},
         "e2e": {"value": val, "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
-
-
-def workload_config(wl, where):
-    return {"workload": f"{wl.name}-shape TensorGNAN node classification (BASELINE.json configs[1])" if wl.name == "cora"
-            else f"{wl.name}-shape TensorGNAN", "nodes": wl.n, "features": wl.K, "classes": wl.C, "hidden": H, "n_layers": L,
-            "step": "forward + CE loss on 140 train rows + backward + Adam", "normalize_rho": True,
-            "timing": "CUDA events per step; 256 MiB L2 flush between timed steps" if where == "gpu" else "perf_counter",
-            "parallelism": "replicas only (SURVEY.md §8e: small node-level graph)"}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -198,56 +271,107 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="gnan_b200", choices=["gnan_b200", "reference"])
-    ap.add_argument("--workload", default="cora", choices=["cora", "pubmed"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3", "tf32"])
+    ap.add_argument("--workload", default="cora", choices=["cora", "pubmed", "mutag"])
+    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "gnan_b200" else args.warmup
-    wl = make_node_workload(args.workload)
-    if args.impl == "reference":
-        return run_reference(args, wl)
-
-    from gnan_b200 import _lib, ops
-    from gnan_b200.GNAN import TensorGNAN
-    from gnan_b200.preprocess import HopData, apsp
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = make_graph_workload(seed=rank) if args.workload == "mutag" else make_node_workload(args.workload)
+    if args.impl == "reference":
+        return run_reference(args, wl)
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    from gnan_b200 import _lib, ops
+    from gnan_b200 import dist as gdist
+    from gnan_b200.preprocess import HopData, PackedBatch, apsp, apsp_batched
+
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
-    barrier = (lambda: torch.distributed.barrier()) if world > 1 else (lambda: None)
+    barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
 
     torch.manual_seed(0)
-    model = TensorGNAN(wl.K, wl.C, L, H, normalize_rho=True, is_graph_task=False, device=dev).to(dev)
+    if wl.kind == "node":
+        from gnan_b200.GNAN import TensorGNAN
+        model = TensorGNAN(wl.K, wl.C, L, H, normalize_rho=True, is_graph_task=False, device=dev).to(dev)
+    else:
+        from gnan_b200.models import TensorGNAN
+        model = TensorGNAN(wl.K, wl.C, L, H, normalize_rho=True, is_graph_task=True, readout_n_layers=0, device=dev).to(dev)
     model.fs.xavier_normal_(1.0); model.rho.xavier_normal_(1.0)
     model.precision = args.precision
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
-    loss_fn = torch.nn.CrossEntropyLoss()
-    hd = apsp(wl.edge_index, wl.n, device=dev)                      # GPU preprocessing (not timed here)
-    x_d, y_d, mask_d = wl.x.to(dev), wl.y.to(dev), wl.train_mask.to(dev)
-    idx_d = mask_d.nonzero().flatten()
-    yl_d = y_d[idx_d]
-    data_d = SimpleNamespace(x=x_d, hop_data=hd)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    sharded = wl.name == "pubmed" and world > 1
+    scaling = "strong" if sharded else "weak"
 
-    def step(data):
-        opt.zero_grad(set_to_none=True)
-        out = model.forward(data)
-        loss = loss_fn(out.index_select(0, idx_d), yl_d)
-        loss.backward()
-        opt.step()
-        return loss
+    # ---- device-resident inputs and the step ------------------------------------------------------------------------
+    if wl.kind == "node":
+        loss_fn = torch.nn.CrossEntropyLoss(reduction="sum")
+        if sharded:
+            blocks = [gdist.row_block(wl.n, r, world) for r in range(world)]
+            sizes = [e - b for b, e in blocks]
+            b0, e0 = blocks[rank]
+            hd = apsp(wl.edge_index, wl.n, device=dev, row_begin=b0, row_end=e0)
+        else:
+            b0, e0, sizes = 0, wl.n, [wl.n]
+            hd = apsp(wl.edge_index, wl.n, device=dev)                  # GPU preprocessing (not part of the timed step)
+        x_h = wl.x[b0:e0].contiguous().pin_memory()
+        hop_h, cnt_h = hd.hop.cpu().pin_memory(), hd.level_counts.cpu().pin_memory()
+        idx_d = wl.train_mask[b0:e0].nonzero().flatten().to(dev)
+        yl_d = wl.y[b0:e0].to(dev)[idx_d]
+        n_train = float(wl.train_mask.sum())
+        data_d = (x_h.to(dev), hd)
+        h2d = x_h.numel() * 4 + hop_h.numel() + cnt_h.numel() * 4
+
+        def load_host():
+            return x_h.to(dev, non_blocking=True), HopData(hop_h.to(dev, non_blocking=True), cnt_h.to(dev, non_blocking=True), wl.n, b0)
+
+        def step(data):
+            x, h = data
+            opt.zero_grad(set_to_none=True)
+            if sharded:
+                out = gdist.row_sharded_forward(model, x, h, sizes)
+            else:
+                out = model.forward(SimpleNamespace(x=x, hop_data=h))
+            loss = loss_fn(out.index_select(0, idx_d), yl_d) / n_train
+            loss.backward()
+            if sharded:
+                gdist.allreduce_gradients(model.parameters())
+            opt.step()
+            return loss
+        rows_local = e0 - b0
+    else:
+        loss_fn = torch.nn.BCEWithLogitsLoss()
+        pk = apsp_batched(wl.edge_index, wl.node_off, device=dev, x=wl.x.to(dev), y=wl.y.to(dev))
+        host = PackedBatch(wl.x.pin_memory(), pk.hop.cpu().pin_memory(), pk.hop_off.cpu().pin_memory(), pk.node_off.cpu().pin_memory(),
+                           pk.level_counts.cpu().pin_memory(), wl.y.pin_memory(), pk.max_nodes)
+        data_d = pk
+        h2d = sum(t.numel() * t.element_size() for t in (host.x, host.hop, host.hop_off, host.node_off, host.level_counts, host.y))
+
+        def load_host():
+            return host.to(dev)
+
+        def step(data):
+            opt.zero_grad(set_to_none=True)
+            out = model(data)                                           # [B,1]
+            loss = loss_fn(out.flatten(), data.y)
+            loss.backward()
+            if world > 1:
+                gdist.allreduce_gradients(model.parameters(), average=True)
+            opt.step()
+            return loss
+        rows_local = wl.n
 
     lib = _lib.load()
     for _ in range(args.warmup):
         step(data_d)
     torch.cuda.synchronize()
 
-    # ---- device-resident timing --------------------------------------------------------------------------------
+    # ---- device-resident timing ---------------------------------------------------------------------------------------
     ops.enable_timing(True)
     clk = clocks_sampler() if rank == 0 else None
     launches0 = lib.gnan_launch_count()
@@ -264,20 +388,14 @@ def main():
     clocks = clocks_summary(clk)
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
-    value = wl.units_per_step * world / (ms_per_step / 1e3)
+    total_units = wl.units_per_step * (1 if sharded else world)
+    value = total_units / (ms_per_step / 1e3)
 
-    # ---- end to end from pinned host buffers --------------------------------------------------------------------
-    x_h = wl.x.pin_memory()
-    hop_h = hd.hop.cpu().pin_memory()
-    cnt_h = hd.level_counts.cpu().pin_memory()
-    h2d = x_h.numel() * 4 + hop_h.numel() + cnt_h.numel() * 4
-
+    # ---- end to end from pinned host buffers ----------------------------------------------------------------------------
     def e2e_step():
-        data = SimpleNamespace(x=x_h.to(dev, non_blocking=True),
-                               hop_data=HopData(hop_h.to(dev, non_blocking=True), cnt_h.to(dev, non_blocking=True), wl.n))
-        return float(step(data).item())                              # loss read back every step (trainer.py:72)
+        return float(step(load_host()).item())                      # loss read back every step (trainer.py:72)
 
     for _ in range(3):
         e2e_step()
@@ -289,43 +407,45 @@ def main():
     b.record(); torch.cuda.synchronize(); barrier()
     t = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
     if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    e2e_val = wl.units_per_step * world * args.steps / (float(t.item()) / 1e3)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_val = total_units * args.steps / (float(t.item()) / 1e3)
 
-    if rank != 0:
-        return
-    hbm, tflops, peak_src = measured_peaks()
-    calls, kms = kt.get("mlp_bwd", (0, 0.0))
-    fs_calls = args.steps                                              # one fs-backward per step; rho's is tiny (G=1)
-    alg_flops = 2.0 * flops_per_eval(wl.C) * wl.n * wl.K              # backward = 2x forward FLOPs; recompute not counted
-    # the op is called twice per step (fs and rho table); the rho call is ~1e-4 of the work, so per-launch time of the
-    # dominant (fs) launch ~= total / steps
-    dur_ms = kms / max(fs_calls, 1)
-    achieved = alg_flops / (dur_ms / 1e3) / 1e12 if dur_ms > 0 else 0.0
-    prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    traffic = json.load(open(prof)).get(f"{wl.name}:mlp_bwd:{args.precision}") if os.path.exists(prof) else None
-    line = {
-        "metric": f"GNAN fwd+bwd {wl.unit} ({wl.name}-shape TensorGNAN)", "value": value, "unit": wl.unit, "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32 tensor-core split, fp32 accumulate)", "tf32": "tf32"}[args.precision],
-        "data": "synthetic", "config": workload_config(wl, "gpu"),
-        "e2e": {"value": e2e_val, "unit": wl.unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-        "gpu_launches": int(launches),
-        "roofline": {"kernel": "mlp_bwd_kernel (grouped shape-MLP backward incl. partial-gradient reduce)",
-                     "bound": "tensor", "achieved": achieved, "peak": tflops, "unit": "TFLOP/s", "frac": achieved / tflops,
-                     "traffic": traffic, "peak_source": peak_src, "algorithmic_flops_per_launch": alg_flops,
-                     "avg_launch_ms": dur_ms, "pipe": "fp32 FFMA (CUDA cores)" if args.precision == "fp32" else "tcgen05 tf32",
-                     "kernel_ms_per_step": {k: v[1] / args.steps for k, v in kt.items()}},
-        "clocks": clocks,
-    }
-    if not args.no_cpu_baseline and world == 1:
-        stepf, threads = reference_step_fn(wl)
-        t0 = time.perf_counter(); stepf(); dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": wl.units_per_step / dt, "unit": wl.unit, "cores": threads, "kind": "port",
-                                "sample": f"1 full {wl.name}-shape step (fwd+CE+bwd+Adam), no warm-up, oracle/gnan_port.py on torch CPU, {dt:.1f} s"}
-    print(json.dumps(line), flush=True)
+    if rank == 0:
+        hbm, tflops, peak_src = measured_peaks()
+        calls, kms = kt.get("mlp_bwd", (0, 0.0))
+        # the op runs twice per step (shape functions, then the rho table); the rho call is <1e-3 of the work, so the
+        # dominant launch's duration ~= total / steps
+        dur_ms = kms / args.steps
+        alg_flops = 2.0 * flops_per_eval(wl.C) * rows_local * wl.K    # backward = 2x forward FLOPs; recompute not counted
+        achieved = alg_flops / (dur_ms / 1e3) / 1e12 if dur_ms > 0 else 0.0
+        prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        traffic = json.load(open(prof)).get(f"{wl.name}:mlp_bwd:{args.precision}") if os.path.exists(prof) else None
+        tc = args.precision != "fp32"
+        line = {
+            "metric": f"GNAN fwd+bwd {wl.unit} ({wl.name}-shape TensorGNAN)", "value": value, "unit": wl.unit, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
+            "vs_baseline": None,
+            "dtype": {"fp32": "f32", "tf32x3": "f32 (hidden layers as 3xTF32 split on tcgen05, fp32 accumulate; parity 1e-5)", "tf32": "tf32"}[args.precision],
+            "data": "synthetic", "config": workload_config(wl, "gpu", world),
+            "e2e": {"value": e2e_val, "unit": wl.unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": ("mlp_tc_bwd_kernel" if tc else "mlp_bwd_kernel") + " (grouped shape-MLP backward incl. partial-gradient reduce)",
+                         "bound": "tensor", "achieved": achieved, "peak": tflops, "unit": "TFLOP/s", "frac": achieved / tflops,
+                         "traffic": traffic, "peak_source": peak_src, "algorithmic_flops_per_launch": alg_flops,
+                         "avg_launch_ms": dur_ms,
+                         "pipe": "tcgen05 kind::tf32, 3-term split: executed tensor FLOPs = 3-4x algorithmic" if args.precision == "tf32x3"
+                                 else ("tcgen05 kind::tf32" if tc else "fp32 FFMA (CUDA cores)"),
+                         "kernel_ms_per_step": {k: v[1] / args.steps for k, v in kt.items()}},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            n_ref = 50 if wl.name == "mutag" else 1
+            val, ms, n, w, threads, note = time_reference(wl, n_ref, 0 if wl.name != "mutag" else 3, 120.0)
+            line["cpu_baseline"] = {"value": val, "unit": wl.unit, "cores": threads, "kind": "port",
+                                    "sample": f"{n} steps, {w} warm-up ({ms:.1f} ms each): {note}; oracle/gnan_port.py on torch CPU"}
+        print(json.dumps(line), flush=True)
     if world > 1:
-        torch.distributed.destroy_process_group()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

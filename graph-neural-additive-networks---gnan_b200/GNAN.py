@@ -17,6 +17,7 @@ import torch.nn as nn
 from . import ops
 from ._inputs import resolve
 from ._stacked import StackedMLP
+from .preprocess import PackedBatch
 
 
 class _Base(nn.Module):
@@ -63,6 +64,8 @@ class TensorGNAN(_Base):
         self.rho.xavier_normal_(0.01)
 
     def forward(self, inputs):
+        if isinstance(inputs, PackedBatch):
+            return self.forward_packed(inputs)
         x, hd = resolve(inputs, self._device())
         S = self._feature_sums(x)                                                    # [N,C]   GNAN.py:57-62 (+ :73 by linearity)
         if self.normalize_rho:                                                       # GNAN.py:65-67: rho(nd / norm)
@@ -75,6 +78,21 @@ class TensorGNAN(_Base):
         if self.is_graph_task:
             out = out.sum(dim=0).view(1, -1).T                                        # [C,1]  GNAN.py:76-79
         return out
+
+
+    def forward_packed(self, pk):
+        """Many graphs in one call (extension; the reference trains with batch_size=1, datasets.py:339-341): `pk` is a
+        preprocess.PackedBatch; returns [B,C] for graph tasks (row b == the reference's out.T for graph b) or [sumN,C]."""
+        dev = self._device()
+        if pk.x.device != dev:
+            pk = pk.to(dev)
+        S = self._feature_sums(pk.x.float().contiguous())
+        if self.normalize_rho:
+            u = ops.rho_table_inputs(pk.nbins, dev, cnt=pk.level_counts)
+            T = self._table(u).view(pk.x.shape[0], pk.nbins, self.out_channels)
+            return ops.aggregate_blockdiag(pk.hop, pk.hop_off, pk.node_off, T, S, per_row=True, reduce_graph=self.is_graph_task)
+        T = self._table(ops.rho_table_inputs(pk.nbins, dev))
+        return ops.aggregate_blockdiag(pk.hop, pk.hop_off, pk.node_off, T, S, reduce_graph=self.is_graph_task)
 
 
 class GNAN(_Base):

@@ -13,6 +13,7 @@ from . import ops
 from ._inputs import resolve
 from ._stacked import StackedMLP
 from .GNAN import GNAN as _GNAN, _Base
+from .preprocess import PackedBatch
 
 
 class TensorGNAN(_Base):
@@ -40,6 +41,8 @@ class TensorGNAN(_Base):
         self.rho.xavier_normal_(0.01)
 
     def forward(self, inputs):
+        if isinstance(inputs, PackedBatch):
+            return self.forward_packed(inputs)
         x, hd = resolve(inputs, self._device())
         S = self._feature_sums(x)
         T = self._table(ops.rho_table_inputs(hd.nbins, x.device))                    # [nbins,Cr]
@@ -48,6 +51,17 @@ class TensorGNAN(_Base):
         if self.is_graph_task:
             out = out.sum(dim=0).view(1, -1).T
         return out
+
+
+    def forward_packed(self, pk):
+        """Many graphs in one call (extension; see gnan_b200.GNAN.TensorGNAN.forward_packed): [B,C] for graph tasks."""
+        dev = self._device()
+        if pk.x.device != dev:
+            pk = pk.to(dev)
+        S = self._feature_sums(pk.x.float().contiguous())
+        T = self._table(ops.rho_table_inputs(pk.nbins, dev))
+        rs = ops.level_rscale(pk.level_counts) if self.normalize_rho else None
+        return ops.aggregate_blockdiag(pk.hop, pk.hop_off, pk.node_off, T, S, rscale=rs, reduce_graph=self.is_graph_task)
 
 
 class GNAN(_GNAN):
