@@ -14,6 +14,7 @@
 // Two producer warps stage the next feature's W2 split + small vectors into a double-buffered shared-memory slot while the
 // current feature is consumed; the two row groups alternate so one group's CUDA-core work overlaps the other's MMAs.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -51,6 +52,7 @@ struct TcArgs {
     float drop_scale;
     uint64_t seed;
     int single_pass;  // 1 = plain tf32 (no lo terms)
+    int prof;         // debug: accumulate phase cycle counters (GNAN_TC_PROF=1)
 };
 
 __device__ __forceinline__ uint64_t tc_drop_key(const TcArgs &a, int layer, int g, int64_t row, int unit)
@@ -247,7 +249,10 @@ mlp_tc_fwd_kernel(TcArgs a, int KC, float *__restrict__ Spart)
 //   dWo    a1 recomputed from TMEM, staged to smem (reusing sZ once MMA3 is done), dWo[c][j] += g[r][c] a1[r][j]
 // All smem operands are K-major with LBO = 144 B (a 16-byte skew per K chunk makes the transposing 4-byte stores of a
 // warp bank-conflict free); MN-major tf32 descriptors returned zeros on B200 (scratch/tc_probe3.cu), so they are avoided.
-constexpr int BWD_ROW_THREADS = 256;
+constexpr int BWD_NS = 4;                           // column split: a TMEM lane quadrant is shared by NS warps, 64/NS units each
+constexpr int BWD_COLS = HID / BWD_NS;              // hidden units per row thread
+constexpr int BWD_ROW_WARPS = 4 * BWD_NS;
+constexpr int BWD_ROW_THREADS = 32 * BWD_ROW_WARPS;
 constexpr int BWD_THREADS = BWD_ROW_THREADS + 32;
 constexpr uint32_t T_LBO = 144;                    // bytes between K chunks (4 rows) of a transposed operand
 constexpr uint32_t T_SBO = 32 * T_LBO;             // 128 rows = 32 chunks per 8-unit block: 4608 B
@@ -261,21 +266,23 @@ struct BwdSmem {
     float sH_hi[8 * T_BLK_FLOATS];                 // a0^T hi (MMA3 B, N = 64)
     float sH_lo[8 * T_BLK_FLOATS];
     float w1[HID], b1[HID], b2[HID];
-    float wo[CT_MAX][HID];
-    float sG[ROWS][CT_MAX];                        // dS tile
-    float red[8][HID];                             // cross-warp staging for the small reductions
-    uint64_t a1_full, a2_full, d1_full, d2_full, d3_full;
+    float wok_hi[HID * CT_MAX], wok_lo[HID * CT_MAX];  // Wo^T as a K-major B operand [n=j][k=c] (K = 8): dh = g Wo on the tensor core
+    float sG[2][ROWS][CT_MAX];                     // dS tile, double-buffered by tile parity (read one tile later by the dWo phase)
+    float red[BWD_ROW_WARPS][2 * BWD_COLS];        // cross-warp staging for the small reductions
+    uint64_t a1_full, a2_full, a3_full, d1_full, d2_full, d3_full;
     uint32_t tmem_base;
 };
 
 // float offset of (unit, row) inside a transposed K-major operand (unit = M/N index, row = K index)
 __device__ __forceinline__ int tidx(int unit, int row) { return (unit >> 3) * T_BLK_FLOATS + (row >> 2) * 36 + (unit & 7) * 4 + (row & 3); }
 
-// column sums over the 32 rows of a warp: on return lane l holds the sum of column l
-__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane)
+// column sums over the 32 rows of a warp for N = 32 or 16 columns held as v[N]: on return every lane holds the sum of
+// column (lane & (N-1))
+template <int N>
+__device__ __forceinline__ float warp_colsum(float (&v)[N], int lane)
 {
 #pragma unroll
-    for (int w = 16; w >= 1; w >>= 1) {
+    for (int w = N / 2; w >= 1; w >>= 1) {
         const bool up = (lane & w) != 0;
 #pragma unroll
         for (int i = 0; i < w; ++i) {
@@ -284,25 +291,47 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane)
             v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
         }
     }
-    return v[0];
+    float r = v[0];
+#pragma unroll
+    for (int w = N; w < 32; w <<= 1) r += __shfl_xor_sync(0xffffffffu, r, w);
+    return r;
 }
 
+template <int N> struct TmemIO;
+template <> struct TmemIO<32> {
+    static __device__ __forceinline__ void st(uint32_t t, const uint32_t (&v)[32]) { tmem_st32(t, v); }
+    static __device__ __forceinline__ void ld(uint32_t t, uint32_t (&v)[32]) { tmem_ld32(t, v); }
+};
+template <> struct TmemIO<16> {
+    static __device__ __forceinline__ void st(uint32_t t, const uint32_t (&v)[16]) { tmem_st16(t, v); }
+    static __device__ __forceinline__ void ld(uint32_t t, uint32_t (&v)[16]) { tmem_ld16(t, v); }
+};
+
 struct TcGradPtrs { float *w1, *b1, *wh, *bh, *wo, *bo; size_t chunk_stride; };
+
+// phase cycle counters of the backward kernel (debug aid, read with gnan_debug_tc_prof): summed over the tiles of CTA (0,0)
+__device__ long long g_tc_prof[16];
+#define TC_PROF(slot)                                                     \
+    do {                                                                  \
+        if (prof_on) { const long long now_ = clock64(); g_tc_prof[slot] += now_ - tprev; tprev = now_; } \
+    } while (0)
 
 template <int CT, bool DROP>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t ntiles)
 {
+    constexpr int NC = BWD_COLS;
+    using IO = TmemIO<NC>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     BwdSmem &sm = *reinterpret_cast<BwdSmem *>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.y;
-    const float dscale = DROP ? a.drop_scale : 1.f;
 
-    if (warp == 8) tmem_alloc(smem_u32(&sm.tmem_base), 512);
+    if (warp == BWD_ROW_WARPS) tmem_alloc(smem_u32(&sm.tmem_base), 512);
     if (tid == 0) {
         mbar_init(smem_u32(&sm.a1_full), BWD_ROW_THREADS);
         mbar_init(smem_u32(&sm.a2_full), BWD_ROW_THREADS);
+        mbar_init(smem_u32(&sm.a3_full), BWD_ROW_THREADS);
         mbar_init(smem_u32(&sm.d1_full), 1);
         mbar_init(smem_u32(&sm.d2_full), 1);
         mbar_init(smem_u32(&sm.d3_full), 1);
@@ -324,7 +353,13 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
             sm.w1[tid] = __ldg(a.w1 + (size_t)g * HID + tid);
             sm.b1[tid] = a.b1 ? __ldg(a.b1 + (size_t)g * HID + tid) : 0.f;
             sm.b2[tid] = a.bh ? __ldg(a.bh + (size_t)g * HID + tid) : 0.f;
-            for (int c = 0; c < CT_MAX; ++c) sm.wo[c][tid] = c < a.C ? __ldg(a.wo + ((size_t)g * a.C + c) * HID + tid) : 0.f;
+            for (int c = 0; c < CT_MAX; ++c) {
+                const float v = c < a.C ? __ldg(a.wo + ((size_t)g * a.C + c) * HID + tid) : 0.f;
+                uint32_t h, l;
+                split_tf32(v, h, l);
+                const int o = (tid >> 3) * 64 + (c >> 2) * 32 + (tid & 7) * 4 + (c & 3);   // (n=tid, k=c): LBO 128 B, SBO 256 B
+                sm.wok_hi[o] = __uint_as_float(h); sm.wok_lo[o] = __uint_as_float(l);
+            }
         }
         // the 16-byte gaps between K chunks are never read; zero the operand buffers once anyway (no NaN garbage)
         for (int idx = tid; idx < 16 * T_BLK_FLOATS; idx += BWD_THREADS) sm.sZ[idx] = 0.f;
@@ -335,9 +370,9 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
-    const uint32_t colA_hi = 0, colA_lo = 64, colD1 = 128, colD2 = 192, colD3 = 256;
+    const uint32_t colA_hi = 0, colA_lo = 64, colD1 = 128, colD2 = 192, colD3 = 256, colG_hi = 320, colG_lo = 328, colDH = 336, colD1b = 400;   // D1 is double-buffered (D1 / D1b by tile parity)
 
-    if (warp == 8) {
+    if (warp == BWD_ROW_WARPS) {
         // ===== MMA issuer =====
         const uint32_t idesc = umma_idesc_tf32(128, 64);
         uint32_t it = 0;
@@ -347,16 +382,24 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t bh = smem_u32(sm.w_hi), bl = smem_u32(sm.w_lo);
+                const uint32_t d1 = tmem + (ph ? colD1b : colD1);
 #pragma unroll
                 for (int ks = 0; ks < 8; ++ks)
-                    umma_tf32_ts(tmem + colD1, tmem + colA_hi + ks * 8, umma_desc_kmajor(bh + ks * B_KSTEP, B_LBO, B_SBO), idesc, ks > 0);
+                    umma_tf32_ts(d1, tmem + colA_hi + ks * 8, umma_desc_kmajor(bh + ks * B_KSTEP, B_LBO, B_SBO), idesc, ks > 0);
                 if (!a.single_pass) {
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks)
-                        umma_tf32_ts(tmem + colD1, tmem + colA_lo + ks * 8, umma_desc_kmajor(bh + ks * B_KSTEP, B_LBO, B_SBO), idesc, 1);
+                        umma_tf32_ts(d1, tmem + colA_lo + ks * 8, umma_desc_kmajor(bh + ks * B_KSTEP, B_LBO, B_SBO), idesc, 1);
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks)
-                        umma_tf32_ts(tmem + colD1, tmem + colA_hi + ks * 8, umma_desc_kmajor(bl + ks * B_KSTEP, B_LBO, B_SBO), idesc, 1);
+                        umma_tf32_ts(d1, tmem + colA_hi + ks * 8, umma_desc_kmajor(bl + ks * B_KSTEP, B_LBO, B_SBO), idesc, 1);
+                }
+                // dh[r][j] = sum_c g[r][c] wo[c][j]: one K-step (K = 8 channels) per split term
+                const uint32_t wkh = smem_u32(sm.wok_hi), wkl = smem_u32(sm.wok_lo);
+                umma_tf32_ts(tmem + colDH, tmem + colG_hi, umma_desc_kmajor(wkh, 128, 256), idesc, 0);
+                if (!a.single_pass) {
+                    umma_tf32_ts(tmem + colDH, tmem + colG_lo, umma_desc_kmajor(wkh, 128, 256), idesc, 1);
+                    umma_tf32_ts(tmem + colDH, tmem + colG_hi, umma_desc_kmajor(wkl, 128, 256), idesc, 1);
                 }
                 umma_commit(smem_u32(&sm.d1_full));
             }
@@ -377,6 +420,11 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
                         umma_tf32_ts(tmem + colD2, tmem + colA_hi + ks * 8, umma_desc_kmajor(bl + ks * B_KSTEP, B_LBO, B_SBO), idesc, 1);
                 }
                 umma_commit(smem_u32(&sm.d2_full));
+            }
+            __syncwarp();
+            mbar_wait(smem_u32(&sm.a3_full), ph);      // the transposed smem operands of MMA3 are staged off the MMA2 critical path
+            tc_fence_after();
+            if (lane == 0) {
                 // dW2 accumulation over the 128 rows of the tile: A = sZ (M = 128: hi|lo), B = sH hi then lo
                 const uint32_t za = smem_u32(sm.sZ), hh = smem_u32(sm.sH_hi), hl = smem_u32(sm.sH_lo);
 #pragma unroll 4
@@ -395,103 +443,169 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
         }
     } else {
         // ===== row warps =====
-        const int q = warp & 3, half = warp >> 2;
+        const int q = warp & 3, part = warp >> 2;          // TMEM lane quadrant, column part
         const int r = q * 32 + lane;                       // row inside the tile == TMEM lane
-        const int c0 = half * 32;                          // this thread's 32 hidden units
+        const int c0 = part * NC;                          // this thread's NC hidden units
         const uint32_t lane_base = tmem + ((uint32_t)(q * 32) << 16);
-        float acc_wo[CT];                                  // dWo[c][j = tid & 63] over rows (tid >> 6)*32..+31 of every tile
+        constexpr int DWO_ROWS = ROWS / (BWD_ROW_THREADS / 64);   // rows per thread in the dWo loop
+        float acc_wo[CT];                                  // dWo[c][j = tid & 63] over rows (tid >> 6)*DWO_ROWS.. of every tile
 #pragma unroll
         for (int c = 0; c < CT; ++c) acc_wo[c] = 0.f;
-        float p_b2 = 0.f, p_b1 = 0.f, p_w1 = 0.f;          // column (c0 + lane) sums over this warp's rows
-        float p_bo = 0.f;                                  // dbo[tid] (tid < C)
+        float p_b2 = 0.f, p_b1 = 0.f, p_w1 = 0.f;          // column (c0 + (lane & (NC-1))) sums over this warp's rows
+        const bool prof_on = a.prof && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0;
+        long long tprev = clock64();
         uint32_t it = 0;
+        // x and dS of the next tile are fetched one tile ahead (their ~700-cycle latency was exposed in the gen phase)
+        float x_n = 0.f, gv_n[CT];
+        {
+            const int64_t row = (int64_t)blockIdx.x * ROWS + r;
+            const bool ok = blockIdx.x < ntiles && row < a.R;
+            x_n = ok ? __ldg(a.u + row * a.ldu + g) : 0.f;
+#pragma unroll
+            for (int c = 0; c < CT; ++c) gv_n[c] = (ok && c < a.C) ? __ldg(dS + row * a.C + c) : 0.f;
+        }
+        // dWo phase of tile `tp` (parity php): a1 recomputed from D1[php], staged to the scratch tile (sZ, free once MMA3 of
+        // that tile is done), dWo[c][j] += g[r][c] a1[r][j]. Runs while the tensor core works on the NEXT tile's MMA1.
+        auto dwo_phase = [&](int64_t tp, uint32_t php) {
+            mbar_wait(smem_u32(&sm.d3_full), php);
+            tc_fence_after();
+            const int64_t rowp = tp * ROWS + r;
+            uint32_t d[NC];
+            IO::ld(lane_base + (php ? colD1b : colD1) + c0, d);
+            tmem_wait_ld();
+            float *scr = sm.sZ;
+#pragma unroll
+            for (int j4 = 0; j4 < NC / 4; ++j4) {
+                const float4 b = *reinterpret_cast<const float4 *>(sm.b2 + c0 + j4 * 4);
+                float v[4] = {fmaxf(__uint_as_float(d[j4 * 4 + 0]) + b.x, 0.f), fmaxf(__uint_as_float(d[j4 * 4 + 1]) + b.y, 0.f),
+                              fmaxf(__uint_as_float(d[j4 * 4 + 2]) + b.z, 0.f), fmaxf(__uint_as_float(d[j4 * 4 + 3]) + b.w, 0.f)};
+                if (DROP) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        v[e] *= gnan_dropout_mul(a.seed, tc_drop_key(a, 1, g, rowp, c0 + j4 * 4 + e), a.drop_thresh, a.drop_scale);
+                }
+                *reinterpret_cast<float4 *>(scr + r * 68 + c0 + j4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+            tc_fence_before();
+            named_bar_sync(1, BWD_ROW_THREADS);
+            const int j = tid & 63, r0 = (tid >> 6) * DWO_ROWS;
+#pragma unroll 4
+            for (int rr = 0; rr < DWO_ROWS; ++rr) {
+                const float hv = scr[(r0 + rr) * 68 + j];
+                const float4 g0 = *reinterpret_cast<const float4 *>(&sm.sG[php][r0 + rr][0]);
+                const float4 g1 = *reinterpret_cast<const float4 *>(&sm.sG[php][r0 + rr][4]);
+                const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+                for (int c = 0; c < CT; ++c) acc_wo[c] = fmaf(gg[c], hv, acc_wo[c]);
+            }
+            named_bar_sync(1, BWD_ROW_THREADS);          // the scratch tile is rewritten (as sZ) by the current tile's epiC
+        };
+
         for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
             const uint32_t ph = it & 1;
+            TC_PROF(7);
             const int64_t row = t * ROWS + r;
-            const bool row_ok = row < a.R;
-            const float x = row_ok ? __ldg(a.u + row * a.ldu + g) : 0.f;
+            const float x = x_n;
             float gv[CT];
 #pragma unroll
-            for (int c = 0; c < CT; ++c) gv[c] = (row_ok && c < a.C) ? __ldg(dS + row * a.C + c) : 0.f;
-            if (half == 0) {
-#pragma unroll
-                for (int c = 0; c < CT; ++c) sm.sG[r][c] = gv[c];
-            }
-            // ---- gen: a0 for units c0..c0+31
+            for (int c = 0; c < CT; ++c) gv[c] = gv_n[c];
             {
-                uint32_t hi[32], lo[32];
+                const int64_t tn = t + gridDim.x, rown = tn * ROWS + r;
+                const bool ok = tn < ntiles && rown < a.R;
+                x_n = ok ? __ldg(a.u + rown * a.ldu + g) : 0.f;
 #pragma unroll
-                for (int i4 = 0; i4 < 8; ++i4) {
-                    const float4 w = *reinterpret_cast<const float4 *>(sm.w1 + c0 + i4 * 4);
-                    const float4 b = *reinterpret_cast<const float4 *>(sm.b1 + c0 + i4 * 4);
-                    float v[4] = {fmaxf(fmaf(x, w.x, b.x), 0.f), fmaxf(fmaf(x, w.y, b.y), 0.f),
-                                  fmaxf(fmaf(x, w.z, b.z), 0.f), fmaxf(fmaf(x, w.w, b.w), 0.f)};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int i = c0 + i4 * 4 + e;
-                        if (DROP) v[e] *= gnan_dropout_mul(a.seed, tc_drop_key(a, 0, g, row, i), a.drop_thresh, a.drop_scale);
-                        split_tf32(v[e], hi[i4 * 4 + e], lo[i4 * 4 + e]);
-                        sm.sH_hi[tidx(i, r)] = __uint_as_float(hi[i4 * 4 + e]);
-                        sm.sH_lo[tidx(i, r)] = __uint_as_float(lo[i4 * 4 + e]);
-                    }
-                }
-                tmem_st32(lane_base + colA_hi + c0, hi);
-                if (!a.single_pass) tmem_st32(lane_base + colA_lo + c0, lo);
+                for (int c = 0; c < CT; ++c) gv_n[c] = (ok && c < a.C) ? __ldg(dS + rown * a.C + c) : 0.f;
             }
+            if (part == 0) {
+                uint32_t gh[CT_MAX], gl[CT_MAX];
+#pragma unroll
+                for (int c = 0; c < CT_MAX; ++c) {
+                    const float v = c < CT ? gv[c < CT ? c : 0] : 0.f;
+                    sm.sG[ph][r][c] = v;
+                    split_tf32(v, gh[c], gl[c]);
+                }
+                tmem_st8(lane_base + colG_hi, gh);
+                tmem_st8(lane_base + colG_lo, gl);
+            }
+            // ---- [A] gen: a0 for units c0..c0+NC-1 -> TMEM only (the A operand of MMA1); then release the tensor core
+            uint32_t hi[NC], lo[NC];
+#pragma unroll
+            for (int i4 = 0; i4 < NC / 4; ++i4) {
+                const float4 w = *reinterpret_cast<const float4 *>(sm.w1 + c0 + i4 * 4);
+                const float4 b = *reinterpret_cast<const float4 *>(sm.b1 + c0 + i4 * 4);
+                float v[4] = {fmaxf(fmaf(x, w.x, b.x), 0.f), fmaxf(fmaf(x, w.y, b.y), 0.f),
+                              fmaxf(fmaf(x, w.z, b.z), 0.f), fmaxf(fmaf(x, w.w, b.w), 0.f)};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (DROP) v[e] *= gnan_dropout_mul(a.seed, tc_drop_key(a, 0, g, row, c0 + i4 * 4 + e), a.drop_thresh, a.drop_scale);
+                    split_tf32(v[e], hi[i4 * 4 + e], lo[i4 * 4 + e]);
+                }
+            }
+            IO::st(lane_base + colA_hi + c0, hi);
+            if (!a.single_pass) IO::st(lane_base + colA_lo + c0, lo);
             tmem_wait_st();
-            fence_async_smem();
             tc_fence_before();
             mbar_arrive(smem_u32(&sm.a1_full));
-            // ---- epiC
+            TC_PROF(0);
+            // ---- [B] previous tile's dWo phase, under this tile's MMA1
+            if (it > 0) dwo_phase(t - gridDim.x, ph ^ 1);
+            TC_PROF(6);
+            // ---- [C] stage a0^T (B operand of MMA3) now that MMA3 of the previous tile is done (d3 waited in [B])
+#pragma unroll
+            for (int i = 0; i < NC; ++i) {
+                sm.sH_hi[tidx(c0 + i, r)] = __uint_as_float(hi[i]);
+                sm.sH_lo[tidx(c0 + i, r)] = __uint_as_float(lo[i]);
+            }
+            // ---- [D] epiC
             mbar_wait(smem_u32(&sm.d1_full), ph);
             tc_fence_after();
+            TC_PROF(1);
             {
-                uint32_t d[32];
-                tmem_ld32(lane_base + colD1 + c0, d);
+                uint32_t d[NC], dhv[NC];
+                IO::ld(lane_base + (ph ? colD1b : colD1) + c0, d);
+                IO::ld(lane_base + colDH + c0, dhv);
                 tmem_wait_ld();
-                uint32_t hi[32], lo[32];
-                float dz[32];
+                float dz[NC];
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
+                for (int j4 = 0; j4 < NC / 4; ++j4) {
                     const float4 b = *reinterpret_cast<const float4 *>(sm.b2 + c0 + j4 * 4);
                     const float bb[4] = {b.x, b.y, b.z, b.w};
-                    float dh[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                    for (int c = 0; c < CT; ++c) {
-                        const float4 w = *reinterpret_cast<const float4 *>(sm.wo[c] + c0 + j4 * 4);
-                        dh[0] = fmaf(gv[c], w.x, dh[0]); dh[1] = fmaf(gv[c], w.y, dh[1]);
-                        dh[2] = fmaf(gv[c], w.z, dh[2]); dh[3] = fmaf(gv[c], w.w, dh[3]);
-                    }
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const int jj = j4 * 4 + e, j = c0 + jj;
-                        float act = fmaxf(__uint_as_float(d[jj]) + bb[e], 0.f);
+                        const int jj = j4 * 4 + e;
+                        const float act = fmaxf(__uint_as_float(d[jj]) + bb[e], 0.f);
                         float m = act > 0.f ? 1.f : 0.f;
-                        if (DROP) m *= gnan_dropout_mul(a.seed, tc_drop_key(a, 1, g, row, j), a.drop_thresh, a.drop_scale);
-                        dz[jj] = dh[e] * m;
+                        if (DROP) m *= gnan_dropout_mul(a.seed, tc_drop_key(a, 1, g, row, c0 + jj), a.drop_thresh, a.drop_scale);
+                        dz[jj] = __uint_as_float(dhv[jj]) * m;
                         split_tf32(dz[jj], hi[jj], lo[jj]);
-                        sm.sZ[tidx(j, r)] = __uint_as_float(hi[jj]);
-                        sm.sZ[tidx(64 + j, r)] = __uint_as_float(lo[jj]);
                     }
                 }
-                tmem_st32(lane_base + colA_hi + c0, hi);
-                if (!a.single_pass) tmem_st32(lane_base + colA_lo + c0, lo);
+                IO::st(lane_base + colA_hi + c0, hi);
+                if (!a.single_pass) IO::st(lane_base + colA_lo + c0, lo);
                 tmem_wait_st();
-                fence_async_smem();
                 tc_fence_before();
-                mbar_arrive(smem_u32(&sm.a2_full));
-                p_b2 += warp_colsum32(dz, lane);
+                mbar_arrive(smem_u32(&sm.a2_full));                  // MMA2 may start
+#pragma unroll
+                for (int jj = 0; jj < NC; ++jj) {                     // transposed staging for MMA3 (off the MMA2 critical path)
+                    sm.sZ[tidx(c0 + jj, r)] = __uint_as_float(hi[jj]);
+                    sm.sZ[tidx(64 + c0 + jj, r)] = __uint_as_float(lo[jj]);
+                }
+                fence_async_smem();
+                mbar_arrive(smem_u32(&sm.a3_full));                  // MMA3 may start (after MMA2 in issue order)
+                p_b2 += warp_colsum<NC>(dz, lane);
             }
-            // ---- epiF
+            TC_PROF(2);
+            // ---- [E] epiF
             mbar_wait(smem_u32(&sm.d2_full), ph);
             tc_fence_after();
+            TC_PROF(3);
             {
-                uint32_t d[32];
-                tmem_ld32(lane_base + colD2 + c0, d);
+                uint32_t d[NC];
+                IO::ld(lane_base + colD2 + c0, d);
                 tmem_wait_ld();
-                float z0[32], z1[32];
+                float z0[NC], z1[NC];
 #pragma unroll
-                for (int i4 = 0; i4 < 8; ++i4) {
+                for (int i4 = 0; i4 < NC / 4; ++i4) {
                     const float4 w = *reinterpret_cast<const float4 *>(sm.w1 + c0 + i4 * 4);
                     const float4 b = *reinterpret_cast<const float4 *>(sm.b1 + c0 + i4 * 4);
                     const float pre[4] = {fmaf(x, w.x, b.x), fmaf(x, w.y, b.y), fmaf(x, w.z, b.z), fmaf(x, w.w, b.w)};
@@ -504,113 +618,103 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
                         z1[ii] = z0[ii] * x;
                     }
                 }
-                p_b1 += warp_colsum32(z0, lane);
-                p_w1 += warp_colsum32(z1, lane);
+                p_b1 += warp_colsum<NC>(z0, lane);
+                p_w1 += warp_colsum<NC>(z1, lane);
             }
-            // ---- dWo: wait until MMA3 has consumed sZ / sH, then reuse sZ as an fp32 [row][unit] scratch tile (ld 68)
-            mbar_wait(smem_u32(&sm.d3_full), ph);
-            tc_fence_after();
-            {
-                uint32_t d[32];
-                tmem_ld32(lane_base + colD1 + c0, d);
-                tmem_wait_ld();
-                float *scr = sm.sZ;
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 b = *reinterpret_cast<const float4 *>(sm.b2 + c0 + j4 * 4);
-                    float v[4] = {fmaxf(__uint_as_float(d[j4 * 4 + 0]) + b.x, 0.f), fmaxf(__uint_as_float(d[j4 * 4 + 1]) + b.y, 0.f),
-                                  fmaxf(__uint_as_float(d[j4 * 4 + 2]) + b.z, 0.f), fmaxf(__uint_as_float(d[j4 * 4 + 3]) + b.w, 0.f)};
-                    if (DROP) {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            v[e] *= gnan_dropout_mul(a.seed, tc_drop_key(a, 1, g, row, c0 + j4 * 4 + e), a.drop_thresh, a.drop_scale);
-                    }
-                    *reinterpret_cast<float4 *>(scr + r * 68 + c0 + j4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
-                }
-                tc_fence_before();
-                named_bar_sync(1, BWD_ROW_THREADS);
-                const int j = tid & 63, r0 = (tid >> 6) * 32;
-#pragma unroll 4
-                for (int rr = 0; rr < 32; ++rr) {
-                    const float hv = scr[(r0 + rr) * 68 + j];
-                    const float4 g0 = *reinterpret_cast<const float4 *>(&sm.sG[r0 + rr][0]);
-                    const float4 g1 = *reinterpret_cast<const float4 *>(&sm.sG[r0 + rr][4]);
-                    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-#pragma unroll
-                    for (int c = 0; c < CT; ++c) acc_wo[c] = fmaf(gg[c], hv, acc_wo[c]);
-                }
-                if (tid < a.C) {
-                    float s = 0.f;
-                    for (int rr = 0; rr < ROWS; ++rr) s += sm.sG[rr][tid];
-                    p_bo += s;
-                }
-                named_bar_sync(1, BWD_ROW_THREADS);      // scratch and sG are rewritten by the next tile
-            }
+            TC_PROF(4);
+            if (prof_on) g_tc_prof[8] += 1;
+        }
+        // the last tile's dWo phase
+        if (it > 0) {
+            const int64_t tl = (int64_t)blockIdx.x + (int64_t)(it - 1) * gridDim.x;
+            dwo_phase(tl, (it - 1) & 1);
         }
         // ---- write this CTA's partial gradients (everything but dW2)
         const size_t off = (size_t)blockIdx.x * gp.chunk_stride;
-        // cross-warp sums: red[warp][unit]
-        float *red = &sm.red[0][0];
+        float *red = &sm.red[0][0];                        // red[warp][0..NC) and [NC..2NC)
+        const int lc = lane & (NC - 1);
+        // unit u = part*NC + lc lives in the four warps part*4 + q, q = 0..3
         named_bar_sync(1, BWD_ROW_THREADS);
-        red[warp * HID + lane] = p_b2; red[warp * HID + 32 + lane] = 0.f;
+        if (lane < NC) red[warp * 2 * NC + lc] = p_b2;
         named_bar_sync(1, BWD_ROW_THREADS);
-        if (tid < HID && gp.bh) {   // unit tid lives in warps with half == tid/32: warps (tid>>5)*4 .. +3, lane tid&31
+        if (tid < HID && gp.bh) {
             float s = 0.f;
-            for (int w = 0; w < 4; ++w) s += red[((tid >> 5) * 4 + w) * HID + (tid & 31)];
+            for (int w = 0; w < 4; ++w) s += red[((tid / NC) * 4 + w) * 2 * NC + (tid % NC)];
             gp.bh[off + (size_t)g * HID + tid] = s;
         }
         named_bar_sync(1, BWD_ROW_THREADS);
-        red[warp * HID + lane] = p_b1; red[warp * HID + 32 + lane] = p_w1;
+        if (lane < NC) { red[warp * 2 * NC + lc] = p_b1; red[warp * 2 * NC + NC + lc] = p_w1; }
         named_bar_sync(1, BWD_ROW_THREADS);
         if (tid < HID) {
             float s0 = 0.f, s1 = 0.f;
             for (int w = 0; w < 4; ++w) {
-                s0 += red[((tid >> 5) * 4 + w) * HID + (tid & 31)];
-                s1 += red[((tid >> 5) * 4 + w) * HID + 32 + (tid & 31)];
+                s0 += red[((tid / NC) * 4 + w) * 2 * NC + (tid % NC)];
+                s1 += red[((tid / NC) * 4 + w) * 2 * NC + NC + (tid % NC)];
             }
             if (gp.b1) gp.b1[off + (size_t)g * HID + tid] = s0;
             if (gp.w1) gp.w1[off + (size_t)g * HID + tid] = s1;
         }
         named_bar_sync(1, BWD_ROW_THREADS);
-        // dWo: thread holds rows quarter (tid>>6) of unit (tid&63) -> sum the four quarters
+        // dWo: thread holds row group (tid>>6) of unit (tid&63) -> sum the row groups
+        constexpr int NRG = BWD_ROW_THREADS / 64;
         float *scr = sm.sZ;
 #pragma unroll
-        for (int c = 0; c < CT; ++c) scr[(c * 4 + (tid >> 6)) * HID + (tid & 63)] = acc_wo[c];
+        for (int c = 0; c < CT; ++c) scr[(c * NRG + (tid >> 6)) * HID + (tid & 63)] = acc_wo[c];
         named_bar_sync(1, BWD_ROW_THREADS);
         if (gp.wo)
             for (int idx = tid; idx < a.C * HID; idx += BWD_ROW_THREADS) {
                 const int c = idx >> 6, j = idx & 63;
-                gp.wo[off + (size_t)g * a.C * HID + idx] = scr[(c * 4 + 0) * HID + j] + scr[(c * 4 + 1) * HID + j] +
-                                                          scr[(c * 4 + 2) * HID + j] + scr[(c * 4 + 3) * HID + j];
+                float s = 0.f;
+                for (int k = 0; k < NRG; ++k) s += scr[(c * NRG + k) * HID + j];
+                gp.wo[off + (size_t)g * a.C * HID + idx] = s;
             }
-        if (tid < a.C && gp.bo) gp.bo[off + (size_t)g * a.C + tid] = p_bo;
         named_bar_sync(1, BWD_ROW_THREADS);
         // ---- dW2 = D3[lane j] + D3[lane 64 + j]  (hi and lo halves of the stacked A operand); all MMAs are complete (d3_full)
-        if (half == 0) {           // warps 0-3 cover all 128 lanes; 64 columns each
-            uint32_t d[64];
-            tmem_ld64(lane_base + colD3, d);
-            tmem_wait_ld();
-            if (r >= 64) {
+        if (part == 0) {           // warps 0-3 cover all 128 lanes
 #pragma unroll
-                for (int i = 0; i < 64; i += 4)
-                    *reinterpret_cast<float4 *>(scr + (r - 64) * 68 + i) =
-                        make_float4(__uint_as_float(d[i]), __uint_as_float(d[i + 1]), __uint_as_float(d[i + 2]), __uint_as_float(d[i + 3]));
-            }
-            named_bar_sync(2, 128);
-            if (r < 64 && gp.wh) {
-                float *dst = gp.wh + off + ((size_t)g * HID + r) * HID;
+            for (int hc = 0; hc < 2; ++hc) {       // two passes of 32 columns keep the register footprint small
+                uint32_t d[32];
+                tmem_ld32(lane_base + colD3 + hc * 32, d);
+                tmem_wait_ld();
+                if (r >= 64) {
 #pragma unroll
-                for (int i = 0; i < 64; i += 4) {
-                    const float4 o = *reinterpret_cast<const float4 *>(scr + r * 68 + i);
-                    *reinterpret_cast<float4 *>(dst + i) = make_float4(__uint_as_float(d[i]) + o.x, __uint_as_float(d[i + 1]) + o.y,
-                                                                       __uint_as_float(d[i + 2]) + o.z, __uint_as_float(d[i + 3]) + o.w);
+                    for (int i = 0; i < 32; i += 4)
+                        *reinterpret_cast<float4 *>(scr + (r - 64) * 36 + i) =
+                            make_float4(__uint_as_float(d[i]), __uint_as_float(d[i + 1]), __uint_as_float(d[i + 2]), __uint_as_float(d[i + 3]));
                 }
+                named_bar_sync(2, 128);
+                if (r < 64 && gp.wh) {
+                    float *dst = gp.wh + off + ((size_t)g * HID + r) * HID + hc * 32;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 o = *reinterpret_cast<const float4 *>(scr + r * 36 + i);
+                        *reinterpret_cast<float4 *>(dst + i) = make_float4(__uint_as_float(d[i]) + o.x, __uint_as_float(d[i + 1]) + o.y,
+                                                                           __uint_as_float(d[i + 2]) + o.z, __uint_as_float(d[i + 3]) + o.w);
+                    }
+                }
+                named_bar_sync(2, 128);
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(tmem, 512);
+    if (warp == BWD_ROW_WARPS) tmem_dealloc(tmem, 512);
+}
+
+// d bo[g][c] = sum_r dS[r][c] for every group g (the output bias gradient does not depend on the group)
+__global__ void dbo_colsum_kernel(const float *__restrict__ dS, int64_t R, int C, int G, float *__restrict__ dbo)
+{
+    __shared__ float red[256];
+    const int c = blockIdx.x;
+    float s = 0.f;
+    for (int64_t r = threadIdx.x; r < R; r += blockDim.x) s += dS[r * C + c];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) {
+        if ((int)threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
+        __syncthreads();
+    }
+    for (int g = threadIdx.x; g < G; g += blockDim.x) dbo[(size_t)g * C + c] = red[0];
 }
 
 struct TcFwdPlan { int KC, nchunk; int64_t ntile; };
@@ -636,6 +740,7 @@ TcArgs make_tc_args(const float *u, int64_t R, int64_t ldu, const gnan_mlp_param
     a.drop_scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
     a.seed = seed;
     a.single_pass = precision == GNAN_PREC_TF32;
+    a.prof = getenv("GNAN_TC_PROF") != nullptr;
     return a;
 }
 
@@ -761,13 +866,28 @@ int gnan_mlp_tc_bwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_param
     if (rc) return rc;
     if (pl.nchunk > 1) {
         struct Seg { const float *src; float *dst; size_t n; };
-        const Seg segs[6] = {{gp.w1, grads->w1, G * HID}, {gp.b1, grads->b1, G * HID}, {gp.wh, grads->wh, G * HID * HID},
-                             {gp.bh, grads->bh, G * HID}, {gp.wo, grads->wo, G * C * HID}, {gp.bo, grads->bo, G * C}};
+        const Seg segs[5] = {{gp.w1, grads->w1, G * HID}, {gp.b1, grads->b1, G * HID}, {gp.wh, grads->wh, G * HID * HID},
+                             {gp.bh, grads->bh, G * HID}, {gp.wo, grads->wo, G * C * HID}};
         for (const Seg &sg : segs) {
             if (!sg.dst || sg.n == 0) continue;
             rc = gnan_reduce_chunks(sg.src, pl.nchunk, sg.n, ntot, sg.dst, st);
             if (rc) return rc;
         }
     }
+    if (grads->bo) {
+        dbo_colsum_kernel<<<(unsigned)C, 256, 0, st>>>(dS, R, (int)C, (int)G, grads->bo);
+        GNAN_LAUNCH_OK();
+    }
+    return GNAN_OK;
+}
+
+// debug aid: read (and clear) the backward kernel's phase cycle counters; slots: 0 gen, 1 wait MMA1, 2 epiC, 3 wait MMA2,
+// 4 epiF, 5 wait MMA3, 6 dWo, 7 loop overhead, 8 tiles
+extern "C" int gnan_debug_tc_prof(long long *out_host16)
+{
+    GNAN_CUDA(cudaDeviceSynchronize());
+    GNAN_CUDA(cudaMemcpyFromSymbol(out_host16, g_tc_prof, sizeof(long long) * 16));
+    long long zero[16] = {0};
+    GNAN_CUDA(cudaMemcpyToSymbol(g_tc_prof, zero, sizeof(zero)));
     return GNAN_OK;
 }
