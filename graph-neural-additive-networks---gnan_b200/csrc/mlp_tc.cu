@@ -313,7 +313,7 @@ struct TcGradPtrs { float *w1, *b1, *wh, *bh, *wo, *bo; size_t chunk_stride; };
 __device__ long long g_tc_prof[16];
 #define TC_PROF(slot)                                                     \
     do {                                                                  \
-        if (prof_on) { const long long now_ = clock64(); g_tc_prof[slot] += now_ - tprev; tprev = now_; } \
+        if (prof_on) { const long long now_ = clock64(); pacc[slot] += now_ - tprev; tprev = now_; } \
     } while (0)
 
 template <int CT, bool DROP>
@@ -427,11 +427,13 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
             if (lane == 0) {
                 // dW2 accumulation over the 128 rows of the tile: A = sZ (M = 128: hi|lo), B = sH hi then lo
                 const uint32_t za = smem_u32(sm.sZ), hh = smem_u32(sm.sH_hi), hl = smem_u32(sm.sH_lo);
+                if (!(a.prof & 2)) {     // GNAN_TC_SKIP3: timing experiment only (dW2 is wrong)
 #pragma unroll 4
                 for (int ks = 0; ks < 16; ++ks)
                     umma_tf32_ss(tmem + colD3, umma_desc_kmajor(za + ks * T_KSTEP, T_LBO, T_SBO),
                                  umma_desc_kmajor(hh + ks * T_KSTEP, T_LBO, T_SBO), idesc, (it > 0 || ks > 0) ? 1u : 0u);
-                if (!a.single_pass) {
+                }
+                if (!a.single_pass && !(a.prof & 2)) {
 #pragma unroll 4
                     for (int ks = 0; ks < 16; ++ks)
                         umma_tf32_ss(tmem + colD3, umma_desc_kmajor(za + ks * T_KSTEP, T_LBO, T_SBO),
@@ -452,8 +454,11 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
 #pragma unroll
         for (int c = 0; c < CT; ++c) acc_wo[c] = 0.f;
         float p_b2 = 0.f, p_b1 = 0.f, p_w1 = 0.f;          // column (c0 + (lane & (NC-1))) sums over this warp's rows
-        const bool prof_on = a.prof && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0;
+        const bool prof_on = (a.prof & 1) && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0;
         long long tprev = clock64();
+        long long pacc[16];                                // register-resident phase counters (static indices only)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pacc[i] = 0;
         uint32_t it = 0;
         // x and dS of the next tile are fetched one tile ahead (their ~700-cycle latency was exposed in the gen phase)
         float x_n = 0.f, gv_n[CT];
@@ -512,9 +517,13 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
             {
                 const int64_t tn = t + gridDim.x, rown = tn * ROWS + r;
                 const bool ok = tn < ntiles && rown < a.R;
-                x_n = ok ? __ldg(a.u + rown * a.ldu + g) : 0.f;
+                x_n = 0.f;
+                if (ok) x_n = ldg_prefetch(a.u + rown * a.ldu + g);
 #pragma unroll
-                for (int c = 0; c < CT; ++c) gv_n[c] = (ok && c < a.C) ? __ldg(dS + rown * a.C + c) : 0.f;
+                for (int c = 0; c < CT; ++c) {
+                    gv_n[c] = 0.f;
+                    if (ok && c < a.C) gv_n[c] = ldg_prefetch(dS + rown * a.C + c);
+                }
             }
             if (part == 0) {
                 uint32_t gh[CT_MAX], gl[CT_MAX];
@@ -527,6 +536,7 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
                 tmem_st8(lane_base + colG_hi, gh);
                 tmem_st8(lane_base + colG_lo, gl);
             }
+            TC_PROF(9);
             // ---- [A] gen: a0 for units c0..c0+NC-1 -> TMEM only (the A operand of MMA1); then release the tensor core
             uint32_t hi[NC], lo[NC];
 #pragma unroll
@@ -541,9 +551,12 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
                     split_tf32(v[e], hi[i4 * 4 + e], lo[i4 * 4 + e]);
                 }
             }
+            TC_PROF(10);
             IO::st(lane_base + colA_hi + c0, hi);
             if (!a.single_pass) IO::st(lane_base + colA_lo + c0, lo);
+            TC_PROF(11);
             tmem_wait_st();
+            TC_PROF(12);
             tc_fence_before();
             mbar_arrive(smem_u32(&sm.a1_full));
             TC_PROF(0);
@@ -622,7 +635,11 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
                 p_w1 += warp_colsum<NC>(z1, lane);
             }
             TC_PROF(4);
-            if (prof_on) g_tc_prof[8] += 1;
+            if (prof_on) pacc[8] += 1;
+        }
+        if (prof_on) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) g_tc_prof[i] += pacc[i];
         }
         // the last tile's dWo phase
         if (it > 0) {
@@ -740,7 +757,7 @@ TcArgs make_tc_args(const float *u, int64_t R, int64_t ldu, const gnan_mlp_param
     a.drop_scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
     a.seed = seed;
     a.single_pass = precision == GNAN_PREC_TF32;
-    a.prof = getenv("GNAN_TC_PROF") != nullptr;
+    a.prof = (getenv("GNAN_TC_PROF") != nullptr ? 1 : 0) | (getenv("GNAN_TC_SKIP3") != nullptr ? 2 : 0);
     return a;
 }
 

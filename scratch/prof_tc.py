@@ -18,5 +18,5 @@ for it in range(3):
     lib.gnan_debug_tc_prof(buf)
     v = list(buf)
     n = max(v[8], 1)
-    names = ["gen", "wait MMA1", "epiC", "wait MMA2", "epiF", "wait MMA3", "dWo", "loop ovh"]
-    print("tiles", v[8], {nm: int(v[i] / n) for i, nm in enumerate(names)}, "sum/tile", int(sum(v[:8]) / n))
+    names = {9: "A.pre+g", 10: "A.compute", 11: "A.tmem_st", 12: "A.wait_st", 0: "A.fence+arrive", 6: "B.dWo(prev)", 1: "wait MMA1", 2: "D.epiC", 3: "wait MMA2", 4: "E.epiF", 7: "loop"}
+    print("tiles", v[8], {nm: int(v[i] / n) for i, nm in names.items()}, "sum/tile", int(sum(v[i] for i in names) / n))
