@@ -102,6 +102,36 @@ def make_graph_workload(seed=0, n_graphs=4337):
                            sizes=sizes, y=torch.from_numpy(y), unit="graphs/s", units_per_step=n_graphs, evals_per_step=tot * 15)
 
 
+def make_mol_workload(seed=0, n_graphs=32768, n_lo=10, n_hi=100):
+    """BASELINE.json configs[4]: molecular graphs with n ~ U{10..100}, random tree + ceil(n/10) extra edges, one-hot over 14
+    types + constant column, C = 1. Generated vectorised; one step = one batch of `n_graphs` graphs INCLUDING the GPU
+    all-pairs hop-distance preprocessing of that batch (edge list -> packed hop blocks + level counts)."""
+    rng = np.random.default_rng(seed)
+    sizes = rng.integers(n_lo, n_hi + 1, size=n_graphs).astype(np.int64)
+    node_off = np.concatenate([[0], np.cumsum(sizes)])
+    tot = int(node_off[-1])
+    gid = np.repeat(np.arange(n_graphs), sizes)
+    local = np.arange(tot) - node_off[gid]
+    child = np.nonzero(local > 0)[0]
+    parent = node_off[gid[child]] + np.floor(rng.random(child.shape[0]) * local[child]).astype(np.int64)
+    n_extra = np.ceil(sizes / 10).astype(np.int64)
+    eg = np.repeat(np.arange(n_graphs), n_extra)
+    ea = node_off[eg] + np.floor(rng.random(eg.shape[0]) * sizes[eg]).astype(np.int64)
+    eb = node_off[eg] + np.floor(rng.random(eg.shape[0]) * sizes[eg]).astype(np.int64)
+    a = np.concatenate([parent, np.minimum(ea, eb)]); b = np.concatenate([child, np.maximum(ea, eb)])
+    keep = a != b
+    und = np.unique(np.stack([a[keep], b[keep]], 1), axis=0)            # simple graph: drop self loops and duplicates
+    ei = np.concatenate([und, und[:, ::-1]]).T.copy()
+    x = np.zeros((tot, 15), np.float32)
+    x[np.arange(tot), rng.integers(0, 14, size=tot)] = 1.0
+    x[:, 14] = 1.0
+    y = rng.integers(0, 2, size=n_graphs).astype(np.float32)
+    return SimpleNamespace(kind="graph", name="mol", desc=f"molecule-shape TensorGNAN graph classification (BASELINE.json configs[4]): "
+                           f"{n_graphs} graphs of {n_lo}-{n_hi} nodes per step, GPU APSP preprocessing of the batch inside the step",
+                           n=tot, K=15, C=1, x=torch.from_numpy(x), edge_index=torch.from_numpy(ei), node_off=torch.from_numpy(node_off),
+                           sizes=sizes, y=torch.from_numpy(y), unit="graphs/s", units_per_step=n_graphs, evals_per_step=tot * 15)
+
+
 def flops_per_eval(C):
     return 2 * H + (L - 2) * 2 * H * H + 2 * H * C      # forward FLOPs of one shape-function evaluation (SURVEY §8d)
 
@@ -154,7 +184,8 @@ def measured_peaks():
 def workload_config(wl, where, world=1):
     par = {"cora": "replicas only (SURVEY.md §8e: small node-level graph)",
            "pubmed": "hop rows sharded over ranks, all-gather of S, reduce-scatter of dS, all-reduce of gradients" if world > 1 else "single GPU",
-           "mutag": "data-parallel graphs, one fused gradient all-reduce per step" if world > 1 else "single GPU"}[wl.name]
+           "mutag": "data-parallel graphs, one fused gradient all-reduce per step" if world > 1 else "single GPU",
+           "mol": "data-parallel graphs, one fused gradient all-reduce per step" if world > 1 else "single GPU"}[wl.name]
     return {"workload": wl.desc, "nodes": wl.n, "features": wl.K, "classes": wl.C, "hidden": H, "n_layers": L,
             "step": "forward + loss + backward + Adam", "normalize_rho": True,
             "timing": "CUDA events per step; 256 MiB L2 flush between timed steps" if where == "gpu" else "perf_counter",
@@ -252,7 +283,7 @@ def time_reference(wl, steps, warmup, budget_s):
 def run_reference(args, wl):
     if int(os.environ.get("RANK", "0")) != 0:
         return
-    steps = args.steps * (50 if wl.name == "mutag" else 1)          # mutag reference steps are single graphs (~20 ms each)
+    steps = args.steps * (50 if wl.kind == "graph" else 1)          # graph-task reference steps are single graphs (a few ms each)
     val, ms, n, w, threads, note = time_reference(wl, steps, args.warmup, 300.0)
     print(json.dumps({
         "impl": "reference", "metric": f"GNAN fwd+bwd {wl.unit} ({wl.name}-shape TensorGNAN)", "value": val, "unit": wl.unit,
@@ -271,14 +302,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="gnan_b200", choices=["gnan_b200", "reference"])
-    ap.add_argument("--workload", default="cora", choices=["cora", "pubmed", "mutag"])
+    ap.add_argument("--workload", default="cora", choices=["cora", "pubmed", "mutag", "mol"])
     ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    wl = make_graph_workload(seed=rank) if args.workload == "mutag" else make_node_workload(args.workload)
+    wl = (make_graph_workload(seed=rank) if args.workload == "mutag" else make_mol_workload(seed=rank) if args.workload == "mol"
+          else make_node_workload(args.workload))
     if args.impl == "reference":
         return run_reference(args, wl)
     args.warmup = max(args.warmup, 3)
@@ -352,10 +384,23 @@ def main():
         data_d = pk
         h2d = sum(t.numel() * t.element_size() for t in (host.x, host.hop, host.hop_off, host.node_off, host.level_counts, host.y))
 
+        in_step_apsp = wl.name == "mol"
+        if in_step_apsp:                                                # the step starts from the raw edge list
+            ei_d, noff_d, x_d, y_d = wl.edge_index.to(dev), wl.node_off.to(dev), wl.x.to(dev), wl.y.to(dev)
+            ei_h, noff_h = wl.edge_index.pin_memory(), wl.node_off.pin_memory()
+            data_d = (ei_d, noff_d, x_d, y_d)
+            h2d = sum(t.numel() * t.element_size() for t in (ei_h, noff_h, host.x, host.y))
+
         def load_host():
+            if in_step_apsp:
+                return (ei_h.to(dev, non_blocking=True), noff_h.to(dev, non_blocking=True), host.x.to(dev, non_blocking=True),
+                        host.y.to(dev, non_blocking=True))
             return host.to(dev)
 
         def step(data):
+            if in_step_apsp:                                            # GPU multi-source BFS on the batch (pre_process_datasets.py:106-122)
+                e, no, xx, yy = data
+                data = apsp_batched(e, no, device=dev, x=xx, y=yy)
             opt.zero_grad(set_to_none=True)
             out = model(data)                                           # [B,1]
             loss = loss_fn(out.flatten(), data.y)
@@ -439,8 +484,8 @@ def main():
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:
-            n_ref = 50 if wl.name == "mutag" else 1
-            val, ms, n, w, threads, note = time_reference(wl, n_ref, 0 if wl.name != "mutag" else 3, 120.0)
+            n_ref = 50 if wl.kind == "graph" else 1
+            val, ms, n, w, threads, note = time_reference(wl, n_ref, 3 if wl.kind == "graph" else 0, 120.0)
             line["cpu_baseline"] = {"value": val, "unit": wl.unit, "cores": threads, "kind": "port",
                                     "sample": f"{n} steps, {w} warm-up ({ms:.1f} ms each): {note}; oracle/gnan_port.py on torch CPU"}
         print(json.dumps(line), flush=True)
