@@ -23,23 +23,27 @@ namespace {
 
 constexpr int HID = 64;
 constexpr int ROWS = 128;                 // rows per group (= TMEM lanes)
-constexpr int ROW_THREADS = 256;          // two groups
+constexpr int FWD_GROUPS = 2;
+constexpr int FWD_GROUP_THREADS = 256;    // 8 warps per group: 4 TMEM lane quadrants x 2 column halves (32 hidden units per thread)
+constexpr int FWD_ROW_THREADS = FWD_GROUPS * FWD_GROUP_THREADS;
 constexpr int PROD_THREADS = 64;
-constexpr int FWD_THREADS = ROW_THREADS + PROD_THREADS;
-constexpr int CT_MAX = 8;                 // output channels held in registers
+constexpr int FWD_ISSUE_THREADS = 32 * FWD_GROUPS;      // one MMA-issuer warp per group
+constexpr int FWD_THREADS = FWD_ROW_THREADS + PROD_THREADS + FWD_ISSUE_THREADS;
+constexpr int CT_MAX = 8;                 // output channels supported by the tensor-core path
+constexpr int NY = 16;                    // N of the output-layer MMA (smallest legal N for M = 128)
 
-// shared-memory slot of one feature: B hi/lo in UMMA K-major no-swizzle core-matrix layout + small vectors
+// shared-memory slot of one feature: B operands (hi/lo, UMMA K-major no-swizzle core-matrix layout) + small vectors
 struct __align__(16) FeatSlot {
-    float bhi[HID * HID];
+    float bhi[HID * HID];                 // W2   [n=j][k=i]
     float blo[HID * HID];
+    float yw[NY * HID];                   // [n][k=j]: n = c -> Wo_hi[c], n = 8 + c -> Wo_lo[c]  (rows c >= C are zero)
     float w1[HID], b1[HID], b2[HID];
-    float wo[CT_MAX][HID];
-    float bo[CT_MAX];
 };
 
 struct FwdSmem {
     FeatSlot slot[2];
-    uint64_t b_full[2], b_empty[2], d_full[2];
+    float bo_sum[CT_MAX];                 // sum of the chunk's output biases
+    uint64_t b_full[2], b_empty[2], a1_full[FWD_GROUPS], a2_full[FWD_GROUPS], d1_full[FWD_GROUPS], dy_full[FWD_GROUPS];
     uint32_t tmem_base;
 };
 
@@ -52,7 +56,7 @@ struct TcArgs {
     float drop_scale;
     uint64_t seed;
     int single_pass;  // 1 = plain tf32 (no lo terms)
-    int prof;         // debug: accumulate phase cycle counters (GNAN_TC_PROF=1)
+    int prof;         // debug: bit 0 = accumulate phase cycle counters (GNAN_TC_PROF), bit 1 = skip MMA3 (GNAN_TC_SKIP3)
 };
 
 __device__ __forceinline__ uint64_t tc_drop_key(const TcArgs &a, int layer, int g, int64_t row, int unit)
@@ -60,20 +64,23 @@ __device__ __forceinline__ uint64_t tc_drop_key(const TcArgs &a, int layer, int 
     return ((((uint64_t)layer * a.G + g) * (uint64_t)a.R + (uint64_t)row) * HID) + unit;   // same keys as the fp32 path
 }
 
-// element (n,k) of a 64x64 K-major operand -> float offset in the core-matrix layout (LBO = 128 B, SBO = 2048 B)
-__device__ __forceinline__ int bidx(int n, int k) { return (n >> 3) * 512 + (k >> 2) * 32 + (n & 7) * 4 + (k & 3); }
 constexpr uint32_t B_LBO = 128, B_SBO = 2048, B_KSTEP = 256;   // bytes; one K-step = 8 tf32 = two 16-byte chunks
 
-__device__ __forceinline__ void produce_slot(FeatSlot &sl, const TcArgs &a, int g, int pt)
+__device__ __forceinline__ float produce_slot(FeatSlot &sl, const TcArgs &a, int g, int pt)
 {
     const float *W = a.wh + (size_t)g * HID * HID;     // [j][i] = [n][k]
-#pragma unroll 4
-    for (int t = 0; t < 16; ++t) {
+    float4 v[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {                      // all 16 loads in flight before the first use
         const int idx = pt + PROD_THREADS * t;          // 1024 float4 chunks: n fastest -> conflict-free 128-bit stores
+        v[t] = __ldg(reinterpret_cast<const float4 *>(W + (idx & 63) * HID + (idx >> 6) * 4));
+    }
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+        const int idx = pt + PROD_THREADS * t;
         const int n = idx & 63, kc = idx >> 6;
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(W + n * HID + kc * 4));
         uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-        split_tf32(v.x, h0, l0); split_tf32(v.y, h1, l1); split_tf32(v.z, h2, l2); split_tf32(v.w, h3, l3);
+        split_tf32(v[t].x, h0, l0); split_tf32(v[t].y, h1, l1); split_tf32(v[t].z, h2, l2); split_tf32(v[t].w, h3, l3);
         const int o = (n >> 3) * 512 + kc * 32 + (n & 7) * 4;
         *reinterpret_cast<uint4 *>(sl.bhi + o) = make_uint4(h0, h1, h2, h3);
         *reinterpret_cast<uint4 *>(sl.blo + o) = make_uint4(l0, l1, l2, l3);
@@ -81,12 +88,23 @@ __device__ __forceinline__ void produce_slot(FeatSlot &sl, const TcArgs &a, int 
     sl.w1[pt] = __ldg(a.w1 + (size_t)g * HID + pt);
     sl.b1[pt] = a.b1 ? __ldg(a.b1 + (size_t)g * HID + pt) : 0.f;
     sl.b2[pt] = a.bh ? __ldg(a.bh + (size_t)g * HID + pt) : 0.f;
-    for (int c = 0; c < a.C; ++c) sl.wo[c][pt] = __ldg(a.wo + ((size_t)g * a.C + c) * HID + pt);
-    if (pt < CT_MAX) sl.bo[pt] = (a.bo && pt < a.C) ? __ldg(a.bo + (size_t)g * a.C + pt) : 0.f;
+    // Wo[c][j = pt] -> K-major (n = c, k = j): (c/8)*512 + (j/4)*32 + (c%8)*4 + (j%4) floats
+    for (int c = 0; c < a.C; ++c) {
+        uint32_t h, l;
+        split_tf32(__ldg(a.wo + ((size_t)g * a.C + c) * HID + pt), h, l);
+        const int o = (pt >> 2) * 32 + (c & 7) * 4 + (pt & 3);      // n-block 0 = hi rows, n-block 1 (+512 floats) = lo rows
+        sl.yw[o] = __uint_as_float(h);
+        sl.yw[512 + o] = __uint_as_float(l);
+    }
+    return (a.bo && pt < a.C) ? __ldg(a.bo + (size_t)g * a.C + pt) : 0.f;
 }
 
 // grid (row-pair tiles, feature chunks); Spart[chunk][R][C]
-template <int CT>
+// Two 128-row groups per CTA; a row thread owns one row (TMEM lane) x 32 hidden units. Per feature and group:
+//   gen   a0 = relu(x w1 + b1) -> TMEM A (hi|lo)                      | MMA1: z = a0 W2^T           (24 x M128 N64 K8)
+//   epi   a1 = relu(z + b2)    -> TMEM A (hi|lo, overwriting a0)      | MMAy: Y += a1 Wo^T          (24 x M128 N16 K8)
+// Y accumulates over the chunk's features in TMEM (the sum over groups f_k never leaves the tensor core) and is read once.
+template <bool DROP>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 mlp_tc_fwd_kernel(TcArgs a, int KC, float *__restrict__ Spart)
 {
@@ -100,141 +118,174 @@ mlp_tc_fwd_kernel(TcArgs a, int KC, float *__restrict__ Spart)
     if (tid == 32) {
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&sm.b_full[s]), PROD_THREADS);
-            mbar_init(smem_u32(&sm.b_empty[s]), ROW_THREADS / 32);
-            mbar_init(smem_u32(&sm.d_full[s]), 1);
+            mbar_init(smem_u32(&sm.b_empty[s]), FWD_GROUPS);        // one tcgen05.commit per group
+        }
+        for (int gI = 0; gI < FWD_GROUPS; ++gI) {
+            mbar_init(smem_u32(&sm.a1_full[gI]), FWD_GROUP_THREADS);
+            mbar_init(smem_u32(&sm.a2_full[gI]), FWD_GROUP_THREADS);
+            mbar_init(smem_u32(&sm.d1_full[gI]), 1);
+            mbar_init(smem_u32(&sm.dy_full[gI]), 1);
         }
         mbar_init_fence();
     }
-    if (tid >= ROW_THREADS) {   // zero the unused output-channel rows once
-        const int pt = tid - ROW_THREADS;
+    if (tid >= FWD_ROW_THREADS && tid < FWD_ROW_THREADS + PROD_THREADS) {   // zero the output-layer operands once (rows c >= C stay zero)
+        const int pt = tid - FWD_ROW_THREADS;
         for (int s = 0; s < 2; ++s)
-            for (int c = a.C; c < CT_MAX; ++c) sm.slot[s].wo[c][pt] = 0.f;
+            for (int i = pt; i < NY * HID; i += PROD_THREADS) sm.slot[s].yw[i] = 0.f;
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = sm.tmem_base;
 
-    if (tid >= ROW_THREADS) {
+    if (tid >= FWD_ROW_THREADS + PROD_THREADS) {
+        // ===== MMA issuers: one warp per group =====
+        const int grp = (tid - FWD_ROW_THREADS - PROD_THREADS) >> 5;
+        const uint32_t gbase = tmem + (uint32_t)grp * 256;
+        const uint32_t colA_hi = 0, colA_lo = 64, colD = 128, colY = 192;
+        const uint32_t idesc = umma_idesc_tf32(128, 64), idesc_y = umma_idesc_tf32(128, NY);
+        for (int kk = 0; kk < ng; ++kk) {
+            const int s = kk & 1, n = kk >> 1;
+            const FeatSlot &sl = sm.slot[s];
+            mbar_wait(smem_u32(&sm.b_full[s]), n & 1);
+            mbar_wait(smem_u32(&sm.a1_full[grp]), kk & 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t bh = smem_u32(sl.bhi), bl = smem_u32(sl.blo);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    umma_tf32_ts(gbase + colD, gbase + colA_hi + ks * 8, umma_desc_kmajor(bh + ks * B_KSTEP, B_LBO, B_SBO), idesc, ks > 0);
+                if (!a.single_pass) {
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        umma_tf32_ts(gbase + colD, gbase + colA_lo + ks * 8, umma_desc_kmajor(bh + ks * B_KSTEP, B_LBO, B_SBO), idesc, 1);
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        umma_tf32_ts(gbase + colD, gbase + colA_hi + ks * 8, umma_desc_kmajor(bl + ks * B_KSTEP, B_LBO, B_SBO), idesc, 1);
+                }
+                umma_commit(smem_u32(&sm.d1_full[grp]));
+            }
+            __syncwarp();
+            mbar_wait(smem_u32(&sm.a2_full[grp]), kk & 1);
+            tc_fence_after();
+            if (lane == 0) {
+                // Y[:, c] += a1 Wo_hi[c], Y[:, 8+c] += a1 Wo_lo[c]: the hi|lo stacking along N gives hi*hi and hi*lo in one MMA
+                const uint32_t yw = smem_u32(sl.yw);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    umma_tf32_ts(gbase + colY, gbase + colA_hi + ks * 8, umma_desc_kmajor(yw + ks * B_KSTEP, B_LBO, B_SBO), idesc_y, (kk > 0 || ks > 0) ? 1u : 0u);
+                if (!a.single_pass) {
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        umma_tf32_ts(gbase + colY, gbase + colA_lo + ks * 8, umma_desc_kmajor(yw + ks * B_KSTEP, B_LBO, B_SBO), idesc_y, 1);
+                }
+                umma_commit(smem_u32(&sm.dy_full[grp]));
+                umma_commit(smem_u32(&sm.b_empty[s]));       // the slot is free once this group's MMAs on it are done
+            }
+            __syncwarp();
+        }
+    } else if (tid >= FWD_ROW_THREADS) {
         // ===== producers =====
-        const int pt = tid - ROW_THREADS;
+        const int pt = tid - FWD_ROW_THREADS;
+        float bsum = 0.f;
         for (int kk = 0; kk < ng; ++kk) {
             const int s = kk & 1, n = kk >> 1;
             mbar_wait(smem_u32(&sm.b_empty[s]), (n & 1) ^ 1);
-            produce_slot(sm.slot[s], a, g0 + kk, pt);
+            bsum += produce_slot(sm.slot[s], a, g0 + kk, pt);
+            if (kk == ng - 1 && pt < CT_MAX) sm.bo_sum[pt] = bsum;
             fence_async_smem();                      // make the generic-proxy writes visible to the tensor core
             mbar_arrive(smem_u32(&sm.b_full[s]));
         }
     } else {
         // ===== row threads =====
-        const int grp = tid >> 7, rt = tid & 127;
-        const int64_t row = ((int64_t)blockIdx.x * 2 + grp) * ROWS + rt;
+        const int grp = tid >> 8, wg = (tid >> 5) & 7;
+        const int q = wg & 3, half = wg >> 2;
+        const int rt = q * 32 + lane;                        // row inside the group's tile == TMEM lane
+        const int c0 = half * 32;
+        const int64_t row = ((int64_t)blockIdx.x * FWD_GROUPS + grp) * ROWS + rt;
         const bool row_ok = row < a.R;
-        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)grp * 256;
-        const uint32_t colA_hi = 0, colA_lo = 64, colD = 128;
-        const uint32_t idesc = umma_idesc_tf32(128, 64);
-        float Sacc[CT];
-#pragma unroll
-        for (int c = 0; c < CT; ++c) Sacc[c] = 0.f;
+        const uint32_t gbase = tmem + (uint32_t)grp * 256;   // this group's TMEM columns
+        const uint32_t lane_base = gbase + ((uint32_t)(q * 32) << 16);
+        const uint32_t colA_hi = 0, colA_lo = 64, colD = 128, colY = 192;
         float x_next = row_ok ? __ldg(a.u + row * a.ldu + g0) : 0.f;
 
         for (int kk = 0; kk < ng; ++kk) {
             const int s = kk & 1, n = kk >> 1, g = g0 + kk;
             const FeatSlot &sl = sm.slot[s];
             const float x = x_next;
-            if (kk + 1 < ng) x_next = row_ok ? __ldg(a.u + row * a.ldu + g + 1) : 0.f;
+            if (kk + 1 < ng && row_ok) x_next = ldg_prefetch(a.u + row * a.ldu + g + 1);
             mbar_wait(smem_u32(&sm.b_full[s]), n & 1);
-            // ---- layer 1 -> TMEM (A operand, hi | lo)
+            if (kk > 0) {                                   // A still holds a1 of the previous feature until its MMAy is done
+                mbar_wait(smem_u32(&sm.dy_full[grp]), (kk - 1) & 1);
+                tc_fence_after();
+            }
+            // ---- layer 1 -> TMEM (A operand, hi | lo), 16 units at a time
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                uint32_t hi[32], lo[32];
+            for (int p = 0; p < 2; ++p) {
+                uint32_t hi[16], lo[16];
 #pragma unroll
-                for (int i4 = 0; i4 < 8; ++i4) {
-                    const float4 w = *reinterpret_cast<const float4 *>(sl.w1 + q * 32 + i4 * 4);
-                    const float4 b = *reinterpret_cast<const float4 *>(sl.b1 + q * 32 + i4 * 4);
+                for (int i4 = 0; i4 < 4; ++i4) {
+                    const float4 w = *reinterpret_cast<const float4 *>(sl.w1 + c0 + p * 16 + i4 * 4);
+                    const float4 b = *reinterpret_cast<const float4 *>(sl.b1 + c0 + p * 16 + i4 * 4);
                     float v[4] = {fmaxf(fmaf(x, w.x, b.x), 0.f), fmaxf(fmaf(x, w.y, b.y), 0.f),
                                   fmaxf(fmaf(x, w.z, b.z), 0.f), fmaxf(fmaf(x, w.w, b.w), 0.f)};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        if (a.drop_thresh)
-                            v[e] *= gnan_dropout_mul(a.seed, tc_drop_key(a, 0, g, row, q * 32 + i4 * 4 + e), a.drop_thresh, a.drop_scale);
+                        if (DROP) v[e] *= gnan_dropout_mul(a.seed, tc_drop_key(a, 0, g, row, c0 + p * 16 + i4 * 4 + e), a.drop_thresh, a.drop_scale);
                         split_tf32(v[e], hi[i4 * 4 + e], lo[i4 * 4 + e]);
                     }
                 }
-                tmem_st32(lane_base + colA_hi + q * 32, hi);
-                if (!a.single_pass) tmem_st32(lane_base + colA_lo + q * 32, lo);
+                tmem_st16(lane_base + colA_hi + c0 + p * 16, hi);
+                if (!a.single_pass) tmem_st16(lane_base + colA_lo + c0 + p * 16, lo);
             }
             tmem_wait_st();
             tc_fence_before();
-            named_bar_sync(1 + grp, ROWS);
-            // ---- layer 2 on the tensor core
-            if (rt == 0) {
-                tc_fence_after();
-                const uint32_t d_t = tmem + (uint32_t)grp * 256 + colD;
-                const uint32_t a_hi = tmem + (uint32_t)grp * 256 + colA_hi, a_lo = tmem + (uint32_t)grp * 256 + colA_lo;
-                const uint32_t bh = smem_u32(sl.bhi), bl = smem_u32(sl.blo);
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks)
-                    umma_tf32_ts(d_t, a_hi + ks * 8, umma_desc_kmajor(bh + ks * B_KSTEP, B_LBO, B_SBO), idesc, ks > 0);
-                if (!a.single_pass) {
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks)
-                        umma_tf32_ts(d_t, a_lo + ks * 8, umma_desc_kmajor(bh + ks * B_KSTEP, B_LBO, B_SBO), idesc, 1);
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks)
-                        umma_tf32_ts(d_t, a_hi + ks * 8, umma_desc_kmajor(bl + ks * B_KSTEP, B_LBO, B_SBO), idesc, 1);
-                }
-                umma_commit(smem_u32(&sm.d_full[grp]));
-            }
-            __syncwarp();
-            mbar_wait(smem_u32(&sm.d_full[grp]), kk & 1);
+            mbar_arrive(smem_u32(&sm.a1_full[grp]));             // the group's issuer warp runs MMA1
+            mbar_wait(smem_u32(&sm.d1_full[grp]), kk & 1);
             tc_fence_after();
-            // ---- layer 3 in registers
-            float y[CT];
+            // ---- a1 = relu(z + b2) -> TMEM A (MMA1 has consumed a0), 16 units at a time
 #pragma unroll
-            for (int c = 0; c < CT; ++c) y[c] = 0.f;
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                uint32_t d[32];
-                tmem_ld32(lane_base + colD + q * 32, d);
+            for (int p = 0; p < 2; ++p) {
+                uint32_t d[16], hi[16], lo[16];
+                tmem_ld16(lane_base + colD + c0 + p * 16, d);
                 tmem_wait_ld();
 #pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 b = *reinterpret_cast<const float4 *>(sl.b2 + q * 32 + j4 * 4);
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const float4 b = *reinterpret_cast<const float4 *>(sl.b2 + c0 + p * 16 + j4 * 4);
                     float h[4] = {fmaxf(__uint_as_float(d[j4 * 4 + 0]) + b.x, 0.f), fmaxf(__uint_as_float(d[j4 * 4 + 1]) + b.y, 0.f),
                                   fmaxf(__uint_as_float(d[j4 * 4 + 2]) + b.z, 0.f), fmaxf(__uint_as_float(d[j4 * 4 + 3]) + b.w, 0.f)};
-                    if (a.drop_thresh) {
 #pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            h[e] *= gnan_dropout_mul(a.seed, tc_drop_key(a, 1, g, row, q * 32 + j4 * 4 + e), a.drop_thresh, a.drop_scale);
-                    }
-#pragma unroll
-                    for (int c = 0; c < CT; ++c) {
-                        const float4 w = *reinterpret_cast<const float4 *>(sl.wo[c] + q * 32 + j4 * 4);
-                        y[c] = fmaf(h[0], w.x, y[c]);
-                        y[c] = fmaf(h[1], w.y, y[c]);
-                        y[c] = fmaf(h[2], w.z, y[c]);
-                        y[c] = fmaf(h[3], w.w, y[c]);
+                    for (int e = 0; e < 4; ++e) {
+                        if (DROP) h[e] *= gnan_dropout_mul(a.seed, tc_drop_key(a, 1, g, row, c0 + p * 16 + j4 * 4 + e), a.drop_thresh, a.drop_scale);
+                        split_tf32(h[e], hi[j4 * 4 + e], lo[j4 * 4 + e]);
                     }
                 }
+                tmem_st16(lane_base + colA_hi + c0 + p * 16, hi);
+                if (!a.single_pass) tmem_st16(lane_base + colA_lo + c0 + p * 16, lo);
             }
-#pragma unroll
-            for (int c = 0; c < CT; ++c) Sacc[c] += y[c] + sl.bo[c];
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&sm.b_empty[s]));
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(smem_u32(&sm.a2_full[grp]));             // the group's issuer warp runs the output-layer MMAs
         }
-        if (row_ok) {
-            float *out = Spart + ((size_t)blockIdx.y * a.R + row) * a.C;
+        // ---- S[row, c] = Y + sum of output biases
+        mbar_wait(smem_u32(&sm.dy_full[grp]), (ng - 1) & 1);
+        tc_fence_after();
+        if (half == 0) {
+            uint32_t y[16];
+            tmem_ld16(lane_base + colY, y);
+            tmem_wait_ld();
+            if (row_ok) {
+                float *out = Spart + ((size_t)blockIdx.y * a.R + row) * a.C;
 #pragma unroll
-            for (int c = 0; c < CT; ++c)
-                if (c < a.C) out[c] = Sacc[c];
+                for (int c = 0; c < CT_MAX; ++c)
+                    if (c < a.C) out[c] = (__uint_as_float(y[c]) + __uint_as_float(y[8 + c])) + sm.bo_sum[c];
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
-
 
 // ---- backward ---------------------------------------------------------------------------------------------------------
 // CTA <-> (feature g, row chunk), 8 row warps + 1 MMA warp. A row warp owns 32 rows (one TMEM lane quadrant) x 32 of the
@@ -311,10 +362,14 @@ struct TcGradPtrs { float *w1, *b1, *wh, *bh, *wo, *bo; size_t chunk_stride; };
 
 // phase cycle counters of the backward kernel (debug aid, read with gnan_debug_tc_prof): summed over the tiles of CTA (0,0)
 __device__ long long g_tc_prof[16];
+#ifdef GNAN_TC_PROFILE   // build with -DGNAN_TC_PROFILE and run with GNAN_TC_PROF=1 (costs ~40 registers: not in the default build)
 #define TC_PROF(slot)                                                     \
     do {                                                                  \
         if (prof_on) { const long long now_ = clock64(); pacc[slot] += now_ - tprev; tprev = now_; } \
     } while (0)
+#else
+#define TC_PROF(slot) do { } while (0)
+#endif
 
 template <int CT, bool DROP>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
@@ -454,11 +509,13 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
 #pragma unroll
         for (int c = 0; c < CT; ++c) acc_wo[c] = 0.f;
         float p_b2 = 0.f, p_b1 = 0.f, p_w1 = 0.f;          // column (c0 + (lane & (NC-1))) sums over this warp's rows
+#ifdef GNAN_TC_PROFILE
         const bool prof_on = (a.prof & 1) && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0;
         long long tprev = clock64();
         long long pacc[16];                                // register-resident phase counters (static indices only)
 #pragma unroll
         for (int i = 0; i < 16; ++i) pacc[i] = 0;
+#endif
         uint32_t it = 0;
         // x and dS of the next tile are fetched one tile ahead (their ~700-cycle latency was exposed in the gen phase)
         float x_n = 0.f, gv_n[CT];
@@ -635,12 +692,16 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
                 p_w1 += warp_colsum<NC>(z1, lane);
             }
             TC_PROF(4);
+#ifdef GNAN_TC_PROFILE
             if (prof_on) pacc[8] += 1;
+#endif
         }
+#ifdef GNAN_TC_PROFILE
         if (prof_on) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) g_tc_prof[i] += pacc[i];
         }
+#endif
         // the last tile's dWo phase
         if (it > 0) {
             const int64_t tl = (int64_t)blockIdx.x + (int64_t)(it - 1) * gridDim.x;
@@ -739,7 +800,7 @@ struct TcFwdPlan { int KC, nchunk; int64_t ntile; };
 TcFwdPlan plan_tc_fwd(int64_t R, const gnan_mlp_params *p)
 {
     TcFwdPlan pl;
-    pl.ntile = ceil_div64(R, 2 * ROWS);
+    pl.ntile = ceil_div64(R, FWD_GROUPS * ROWS);
     const int target = 2 * gnan_sm_count();                    // ~2 waves of one CTA per SM
     int nchunk = (int)std::max<int64_t>(1, std::min<int64_t>(p->G, ceil_div64(target, pl.ntile)));
     pl.KC = (int)ceil_div64(p->G, nchunk);
@@ -761,13 +822,17 @@ TcArgs make_tc_args(const float *u, int64_t R, int64_t ldu, const gnan_mlp_param
     return a;
 }
 
-template <int CT>
 int launch_tc_fwd(const TcArgs &a, const TcFwdPlan &pl, float *Spart, cudaStream_t st)
 {
     const size_t smem = sizeof(FwdSmem) + 1024;
-    GNAN_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)pl.ntile, (unsigned)pl.nchunk);
-    mlp_tc_fwd_kernel<CT><<<grid, FWD_THREADS, smem, st>>>(a, pl.KC, Spart);
+    if (a.drop_thresh) {
+        GNAN_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mlp_tc_fwd_kernel<true><<<grid, FWD_THREADS, smem, st>>>(a, pl.KC, Spart);
+    } else {
+        GNAN_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mlp_tc_fwd_kernel<false><<<grid, FWD_THREADS, smem, st>>>(a, pl.KC, Spart);
+    }
     GNAN_LAUNCH_OK();
     return GNAN_OK;
 }
@@ -840,11 +905,7 @@ int gnan_mlp_tc_fwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_param
         Spart = (float *)ws;
     }
     const TcArgs a = make_tc_args(u, R, ldu, p, dropout_p, seed, precision);
-    int rc;
-    if (p->C == 1) rc = launch_tc_fwd<1>(a, pl, Spart, st);
-    else if (p->C == 2) rc = launch_tc_fwd<2>(a, pl, Spart, st);
-    else if (p->C <= 4) rc = launch_tc_fwd<4>(a, pl, Spart, st);
-    else rc = launch_tc_fwd<8>(a, pl, Spart, st);
+    int rc = launch_tc_fwd(a, pl, Spart, st);
     if (rc) return rc;
     if (pl.nchunk > 1) return gnan_reduce_chunks(Spart, pl.nchunk, (size_t)R * p->C, (size_t)R * p->C, S, st);
     return GNAN_OK;
