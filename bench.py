@@ -52,17 +52,23 @@ def random_simple_graph(rng, n, n_undirected_edges, n_isolated):
     return np.concatenate([got, got[:, ::-1]]).T.copy()
 
 
-def make_node_workload(name, seed=0):
+def make_node_workload(name, seed=0, classes=None):
     rng = np.random.default_rng(seed)
     if name == "cora":
         n, k_raw, c, e_und, iso, dens = 2708, 1433, 7, 5278, 54, 0.0127
         x = (rng.random((n, k_raw)) < dens).astype(np.float32)
         x /= np.maximum(x.sum(1, keepdims=True), 1.0)                       # row-normalised bag of words (datasets.py:94)
         desc = "cora-shape TensorGNAN node classification (BASELINE.json configs[1])"
+    elif name == "arxiv":
+        n, k_raw, c, e_und, iso = 169343, 128, 40, 583121, 0        # 1 166 243 directed edges ~ 583 k undirected pairs
+        x = rng.normal(size=(n, k_raw)).astype(np.float32)
+        desc = "ogbn-arxiv-shape TensorGNAN node classification (BASELINE.json configs[3]), 28.7 GB uint8 hop matrix"
     else:
         n, k_raw, c, e_und, iso, dens = 19717, 500, 3, 44338, 0, 0.10
         x = ((rng.random((n, k_raw)) < dens) * rng.random((n, k_raw)) * 0.1).astype(np.float32)
         desc = "pubmed-shape TensorGNAN node classification (BASELINE.json configs[2])"
+    if classes:
+        c = classes
     x = np.concatenate([x, np.ones((n, 1), np.float32)], 1)                 # pre_process_datasets.py:127
     ei = random_simple_graph(rng, n, e_und, iso)
     y = rng.integers(0, c, size=n)
@@ -184,6 +190,7 @@ def measured_peaks():
 def workload_config(wl, where, world=1):
     par = {"cora": "replicas only (SURVEY.md §8e: small node-level graph)",
            "pubmed": "hop rows sharded over ranks, all-gather of S, reduce-scatter of dS, all-reduce of gradients" if world > 1 else "single GPU",
+           "arxiv": "hop rows sharded over ranks, all-gather of S, reduce-scatter of dS, all-reduce of gradients" if world > 1 else "single GPU",
            "mutag": "data-parallel graphs, one fused gradient all-reduce per step" if world > 1 else "single GPU",
            "mol": "data-parallel graphs, one fused gradient all-reduce per step" if world > 1 else "single GPU"}[wl.name]
     return {"workload": wl.desc, "nodes": wl.n, "features": wl.K, "classes": wl.C, "hidden": H, "n_layers": L,
@@ -227,11 +234,11 @@ def reference_step_fn(wl, seed=0):
             loss.backward(); opt.step()
             return float(loss.item())
         return step, threads, wl.n, f"full {wl.name}-shape step (fwd+CE+bwd+Adam), GNAN.py TensorGNAN port"
-    if wl.name == "pubmed":                     # the shipped TensorGNAN cannot run at this shape (99.5 GB activation): row loop on 64 rows
+    if wl.name in ("pubmed", "arxiv"):          # the shipped TensorGNAN cannot run at this shape (99.5 GB activation): row loop on 64 rows
         rows = 64
-        hop = oapsp.apsp(wl.edge_index.numpy(), wl.n)
+        hop = oapsp.apsp_rows(wl.edge_index.numpy(), wl.n, rows)       # BFS from the first 64 sources only
         cnt = oapsp.level_counts(hop)
-        nd, nm = (torch.from_numpy(t) for t in oapsp.reference_format(hop[:rows], cnt[:rows]))
+        nd, nm = (torch.from_numpy(t) for t in oapsp.reference_format(hop, cnt))
         loss_fn = torch.nn.CrossEntropyLoss()
 
         def step():
@@ -302,7 +309,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="gnan_b200", choices=["gnan_b200", "reference"])
-    ap.add_argument("--workload", default="cora", choices=["cora", "pubmed", "mutag", "mol"])
+    ap.add_argument("--workload", default="cora", choices=["cora", "pubmed", "arxiv", "mutag", "mol"])
+    ap.add_argument("--classes", type=int, default=0, help="override the number of classes (arxiv: 40, or 1 = the reference's hard-coded value)")
     ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -310,7 +318,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     wl = (make_graph_workload(seed=rank) if args.workload == "mutag" else make_mol_workload(seed=rank) if args.workload == "mol"
-          else make_node_workload(args.workload))
+          else make_node_workload(args.workload, classes=args.classes))
     if args.impl == "reference":
         return run_reference(args, wl)
     args.warmup = max(args.warmup, 3)
@@ -337,7 +345,7 @@ def main():
     model.precision = args.precision
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    sharded = wl.name == "pubmed" and world > 1
+    sharded = wl.name in ("pubmed", "arxiv") and world > 1
     scaling = "strong" if sharded else "weak"
 
     # ---- device-resident inputs and the step ------------------------------------------------------------------------
@@ -352,15 +360,18 @@ def main():
             b0, e0, sizes = 0, wl.n, [wl.n]
             hd = apsp(wl.edge_index, wl.n, device=dev)                  # GPU preprocessing (not part of the timed step)
         x_h = wl.x[b0:e0].contiguous().pin_memory()
-        hop_h, cnt_h = hd.hop.cpu().pin_memory(), hd.level_counts.cpu().pin_memory()
+        big = hd.hop.numel() > (4 << 30)            # do not stage tens of GB in pinned host memory: no e2e leg for this shape
+        hop_h = None if big else hd.hop.cpu().pin_memory()
+        cnt_h = hd.level_counts.cpu().pin_memory()
         idx_d = wl.train_mask[b0:e0].nonzero().flatten().to(dev)
         yl_d = wl.y[b0:e0].to(dev)[idx_d]
         n_train = float(wl.train_mask.sum())
         data_d = (x_h.to(dev), hd)
-        h2d = x_h.numel() * 4 + hop_h.numel() + cnt_h.numel() * 4
+        h2d = x_h.numel() * 4 + (0 if big else hop_h.numel()) + cnt_h.numel() * 4
 
         def load_host():
-            return x_h.to(dev, non_blocking=True), HopData(hop_h.to(dev, non_blocking=True), cnt_h.to(dev, non_blocking=True), wl.n, b0)
+            hop_d = hd.hop if big else hop_h.to(dev, non_blocking=True)
+            return x_h.to(dev, non_blocking=True), HopData(hop_d, cnt_h.to(dev, non_blocking=True), wl.n, b0)
 
         def step(data):
             x, h = data
@@ -472,7 +483,8 @@ def main():
             "vs_baseline": None,
             "dtype": {"fp32": "f32", "tf32x3": "f32 (hidden layers as 3xTF32 split on tcgen05, fp32 accumulate; parity 1e-5)", "tf32": "tf32"}[args.precision],
             "data": "synthetic", "config": workload_config(wl, "gpu", world),
-            "e2e": {"value": e2e_val, "unit": wl.unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "e2e": {"value": e2e_val, "unit": wl.unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "note": "hop matrix kept device-resident in the e2e leg (too large to stage in pinned host memory)" if (wl.kind == "node" and big) else None},
             "gpu_launches": int(launches),
             "roofline": {"kernel": ("mlp_tc_bwd_kernel" if tc else "mlp_bwd_kernel") + " (grouped shape-MLP backward incl. partial-gradient reduce)",
                          "bound": "tensor", "achieved": achieved, "peak": tflops, "unit": "TFLOP/s", "frac": achieved / tflops,

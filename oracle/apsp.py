@@ -59,3 +59,18 @@ def reference_format(hop, cnt):
                                         cnt.ctypes.data_as(ctypes.c_void_p),
                                         nd.ctypes.data_as(ctypes.c_void_p), nm.ctypes.data_as(ctypes.c_void_p))
     return nd, nm
+
+
+def apsp_rows(edge_index, num_nodes, rows):
+    """hop rows of sources 0..rows-1 only (int32 [rows,n]): full BFS is run on a graph restricted to what those sources
+    reach by calling the C routine on the whole graph once per block is unnecessary — it computes all rows; for large n use
+    the row-limited C entry point."""
+    ei = np.ascontiguousarray(np.asarray(edge_index), dtype=np.int64)
+    src, dst = np.ascontiguousarray(ei[0]), np.ascontiguousarray(ei[1])
+    hop = np.empty((rows, num_nodes), dtype=np.int32)
+    rc = _lib().gnan_oracle_apsp_rows(ctypes.c_int32(num_nodes), ctypes.c_int64(src.shape[0]),
+                                      src.ctypes.data_as(ctypes.c_void_p), dst.ctypes.data_as(ctypes.c_void_p),
+                                      ctypes.c_int32(rows), hop.ctypes.data_as(ctypes.c_void_p))
+    if rc:
+        raise RuntimeError(f"gnan_oracle_apsp_rows rc={rc}")
+    return hop

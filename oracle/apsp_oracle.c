@@ -14,8 +14,16 @@
 #include <stdlib.h>
 #include <string.h>
 
+int gnan_oracle_apsp_rows(int32_t n, int64_t n_edges, const int64_t *src, const int64_t *dst, int32_t n_sources, int32_t *hop);
+
 /* hop: int32 [n*n], -1 = unreachable. returns 0 ok, 1 alloc failure, 2 bad edge. */
 int gnan_oracle_apsp(int32_t n, int64_t n_edges, const int64_t *src, const int64_t *dst, int32_t *hop)
+{
+    return gnan_oracle_apsp_rows(n, n_edges, src, dst, n, hop);
+}
+
+/* BFS from sources 0..n_sources-1 only: hop is int32 [n_sources*n]. */
+int gnan_oracle_apsp_rows(int32_t n, int64_t n_edges, const int64_t *src, const int64_t *dst, int32_t n_sources, int32_t *hop)
 {
     int64_t *rowptr = (int64_t *)calloc((size_t)n + 1, sizeof(int64_t));
     int32_t *col = (int32_t *)malloc((size_t)(n_edges > 0 ? n_edges : 1) * sizeof(int32_t));
@@ -31,7 +39,7 @@ int gnan_oracle_apsp(int32_t n, int64_t n_edges, const int64_t *src, const int64
     memcpy(fill, rowptr, (size_t)n * sizeof(int64_t));
     for (int64_t e = 0; e < n_edges; ++e) col[fill[src[e]]++] = (int32_t)dst[e];
     free(fill);
-    for (int32_t s = 0; s < n; ++s) {
+    for (int32_t s = 0; s < n_sources && s < n; ++s) {
         int32_t *row = hop + (int64_t)s * n;
         for (int32_t v = 0; v < n; ++v) row[v] = -1;
         int32_t head = 0, tail = 0;
