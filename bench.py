@@ -423,13 +423,13 @@ def main():
         rows_local = wl.n
 
     lib = _lib.load()
+    clk = clocks_sampler() if rank == 0 else None                  # sampled over warm-up + timed region + e2e leg (all under load)
     for _ in range(args.warmup):
         step(data_d)
     torch.cuda.synchronize()
 
     # ---- device-resident timing ---------------------------------------------------------------------------------------
     ops.enable_timing(True)
-    clk = clocks_sampler() if rank == 0 else None
     launches0 = lib.gnan_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier(); torch.cuda.synchronize()
@@ -441,7 +441,6 @@ def main():
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     kt = ops.timing_results()
     ops.enable_timing(False)
-    clocks = clocks_summary(clk)
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -465,6 +464,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_val = total_units * args.steps / (float(t.item()) / 1e3)
+    clocks = clocks_summary(clk)
 
     if rank == 0:
         hbm, tflops, peak_src = measured_peaks()

@@ -20,7 +20,7 @@
 namespace {
 
 constexpr int BINS_WARPS = 8;       // warps per CTA in the bins kernel (may be lowered to fit smem)
-constexpr int CHUNK = 2048;         // columns of S staged per sweep step
+constexpr int CHUNK_FLOATS = 4096;  // floats of S staged per sweep step: 4096 / CC columns
 constexpr int DS_THREADS = 256;
 constexpr int DS_RB = 8;            // rows per staged table group in the dS kernel
 
@@ -61,28 +61,36 @@ __device__ __forceinline__ float table_value(const AggArgs &a, int64_t i, int d,
 
 // ---- forward: bins --------------------------------------------------------------------------------------------
 // grid (row groups, channel chunks). Each warp: one row at a time; all warps sweep the same S chunk.
-template <int CC>
+// WAYS independent lane-private bin arrays break the load-add-store dependency chain of consecutive pairs
+template <int CC, int WAYS>
 __global__ void __launch_bounds__(BINS_WARPS * 32)
 agg_rows_bins_kernel(AggArgs a, int nwarps, float *__restrict__ out, float *__restrict__ Bsum)
 {
     using V = typename VecT<CC>::type;
+    constexpr int CHUNK = CHUNK_FLOATS / CC;
+    constexpr int SROW = CHUNK / 16 + 2;                       // +2: the transposing stash (lane -> (t&15, t>>4)) is conflict-free
     extern __shared__ __align__(16) float smem[];
-    V *sS = reinterpret_cast<V *>(smem);                       // [16][CHUNK/16]  permuted: (j%16, j/16)
-    V *sBins = sS + CHUNK;                                     // [nwarps][nbins][32]
+    V *sS = reinterpret_cast<V *>(smem);                       // [16][SROW]  permuted: column t of the chunk at (t%16, t/16)
+    V *sBins = sS + 16 * SROW;                                 // [nwarps][ways][nbins][32]
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int c0 = blockIdx.y * CC;
     const bool active_warp = w < nwarps;
     const int64_t i = (int64_t)blockIdx.x * nwarps + w;
     const bool has_row = active_warp && i < a.R;
-    V *bins = sBins + (size_t)w * a.nbins * 32;
+    const int way_stride = a.nbins * 32;                         // [way][bin][lane]
+    V *bins = sBins + (size_t)w * WAYS * way_stride;
     if (active_warp)
-        for (int d = 0; d < a.nbins; ++d) vzero(bins[d * 32 + lane]);
+        for (int d = 0; d < WAYS * a.nbins; ++d) vzero(bins[d * 32 + lane]);
     const uint8_t *hrow = a.hop + (has_row ? i : 0) * a.ld;
 
-    for (int64_t jb = 0; jb < a.N; jb += CHUNK) {
-        __syncthreads();
-        for (int t = threadIdx.x; t < CHUNK; t += blockDim.x) {
-            const int64_t j = jb + t;
+    // S chunks are double-buffered through registers: the next chunk's global loads are in flight while the current chunk is
+    // consumed from shared memory (their L2 latency used to be exposed at every chunk barrier)
+    constexpr int PER_T = CHUNK / (BINS_WARPS * 32);
+    V nxt[PER_T];
+    auto fetch = [&](int64_t jb) {
+#pragma unroll
+        for (int k = 0; k < PER_T; ++k) {
+            const int64_t j = jb + threadIdx.x + k * (BINS_WARPS * 32);
             V v;
             vzero(v);
             if (j < a.N) {
@@ -90,27 +98,66 @@ agg_rows_bins_kernel(AggArgs a, int nwarps, float *__restrict__ out, float *__re
                 for (int cc = 0; cc < CC; ++cc)
                     if (c0 + cc < a.C) vset(v, cc, __ldg(a.S + j * a.C + c0 + cc));
             }
-            sS[(t & 15) * (CHUNK / 16) + (t >> 4)] = v;
+            nxt[k] = v;
         }
-        __syncthreads();
+    };
+    auto stash = [&]() {
+#pragma unroll
+        for (int k = 0; k < PER_T; ++k) {
+            const int t = threadIdx.x + k * (BINS_WARPS * 32);
+            sS[(t & 15) * SROW + (t >> 4)] = nxt[k];
+        }
+    };
+    fetch(0);
+    stash();
+    __syncthreads();
+    for (int64_t jb = 0; jb < a.N; jb += CHUNK) {
+        const bool more = jb + CHUNK < a.N;
+        if (more) fetch(jb + CHUNK);
         if (has_row) {
             const int len = (int)min((int64_t)CHUNK, a.N - jb);
+            const int nb1 = a.nbins - 1;
+            V *mybins = bins + lane;                             // bin b of this lane lives at mybins[b * 32]
+            uint4 hv_n = make_uint4(0u, 0u, 0u, 0u);
+            if (lane * 16 < len) hv_n = __ldcs(reinterpret_cast<const uint4 *>(hrow + jb + lane * 16));
             for (int j0 = lane * 16; j0 < len; j0 += 512) {
-                const uint4 hv = __ldcs(reinterpret_cast<const uint4 *>(hrow + jb + j0));
+                const uint4 hv = hv_n;                           // hop bytes are fetched one step ahead (more bytes in flight)
+                if (j0 + 512 < len) hv_n = __ldcs(reinterpret_cast<const uint4 *>(hrow + jb + j0 + 512));
                 const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+                const V *sp = sS + (j0 >> 4);                    // S of column j0 + q sits at sp[q * SROW]
+                if (j0 + 16 <= len) {                            // fast path: 16 pairs, no bounds checks, WAYS pairs in flight
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    if (j0 + q < len) {
-                        const int h = (hw[q >> 2] >> ((q & 3) * 8)) & 0xff;
-                        const int b = min(h, a.nbins - 1);
-                        V s = sS[q * (CHUNK / 16) + (j0 >> 4)];
-                        V cur = bins[b * 32 + lane];
-                        vadd(cur, s);
-                        bins[b * 32 + lane] = cur;
+                    for (int q = 0; q < 16; q += WAYS) {
+                        int b[WAYS];
+                        V cur[WAYS];
+#pragma unroll
+                        for (int u = 0; u < WAYS; ++u) {
+                            const int h = (int)__byte_perm(hw[(q + u) >> 2], 0u, 0x4440u + ((q + u) & 3));
+                            b[u] = min(h, nb1) * 32 + u * way_stride;
+                            cur[u] = mybins[b[u]];
+                        }
+#pragma unroll
+                        for (int u = 0; u < WAYS; ++u) vadd(cur[u], sp[(q + u) * SROW]);
+#pragma unroll
+                        for (int u = 0; u < WAYS; ++u) mybins[b[u]] = cur[u];
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        if (j0 + q < len) {
+                            const int h = (int)__byte_perm(hw[q >> 2], 0u, 0x4440u + (q & 3));
+                            const int b = min(h, nb1);
+                            V cur = mybins[b * 32];
+                            vadd(cur, sp[q * SROW]);
+                            mybins[b * 32] = cur;
+                        }
                     }
                 }
             }
         }
+        __syncthreads();                 // everyone is done with the current chunk
+        if (more) stash();
+        __syncthreads();
     }
     if (!has_row) return;
     __syncwarp();
@@ -121,7 +168,8 @@ agg_rows_bins_kernel(AggArgs a, int nwarps, float *__restrict__ out, float *__re
     for (int d = lane; d < a.nbins; d += 32) {
         V tot;
         vzero(tot);
-        for (int k = 0; k < 32; ++k) vadd(tot, bins[d * 32 + ((k + lane) & 31)]);
+        for (int u = 0; u < WAYS; ++u)
+            for (int k = 0; k < 32; ++k) vadd(tot, bins[u * way_stride + d * 32 + ((k + lane) & 31)]);
 #pragma unroll
         for (int cc = 0; cc < CC; ++cc)
             if (c0 + cc < a.C) {
@@ -423,9 +471,10 @@ extern "C" int gnan_aggregate_rows_fwd_save(const uint8_t *hop, int64_t R, int64
     cudaStream_t st = (cudaStream_t)stream;
     AggArgs a{hop, R, N, ld_hop, T, table_per_row, nbins, Cr, rscale, S, C};
     const int CC = C >= 4 ? 4 : (C >= 2 ? 2 : 1);
+    const int WAYS = 2;
     int nwarps = BINS_WARPS;
-    auto smem_of = [&](int nw) { return sizeof(float) * CC * ((size_t)CHUNK + (size_t)nw * nbins * 32); };
-    while (nwarps > 1 && smem_of(nwarps) > 200 * 1024) nwarps >>= 1;
+    auto smem_of = [&](int nw) { return sizeof(float) * ((size_t)CHUNK_FLOATS + 32 * CC + (size_t)CC * nw * WAYS * nbins * 32); };
+    while (nwarps > 1 && smem_of(nwarps) > 100 * 1024) nwarps >>= 1;   // keep >= 2 CTAs per SM
     if (smem_of(nwarps) > 227 * 1024) {
         gnan_set_error("aggregate_rows_fwd: nbins %d too large for shared memory", nbins);
         return GNAN_ERR_UNSUPPORTED;
@@ -433,14 +482,14 @@ extern "C" int gnan_aggregate_rows_fwd_save(const uint8_t *hop, int64_t R, int64
     const size_t smem = smem_of(nwarps);
     dim3 grid((unsigned)ceil_div64(R, nwarps), (unsigned)((C + CC - 1) / CC));
     if (CC == 4) {
-        GNAN_CUDA(cudaFuncSetAttribute(agg_rows_bins_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        agg_rows_bins_kernel<4><<<grid, BINS_WARPS * 32, smem, st>>>(a, nwarps, out, Bsum);
+        GNAN_CUDA(cudaFuncSetAttribute(agg_rows_bins_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        agg_rows_bins_kernel<4, 2><<<grid, BINS_WARPS * 32, smem, st>>>(a, nwarps, out, Bsum);
     } else if (CC == 2) {
-        GNAN_CUDA(cudaFuncSetAttribute(agg_rows_bins_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        agg_rows_bins_kernel<2><<<grid, BINS_WARPS * 32, smem, st>>>(a, nwarps, out, Bsum);
+        GNAN_CUDA(cudaFuncSetAttribute(agg_rows_bins_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        agg_rows_bins_kernel<2, 2><<<grid, BINS_WARPS * 32, smem, st>>>(a, nwarps, out, Bsum);
     } else {
-        GNAN_CUDA(cudaFuncSetAttribute(agg_rows_bins_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        agg_rows_bins_kernel<1><<<grid, BINS_WARPS * 32, smem, st>>>(a, nwarps, out, Bsum);
+        GNAN_CUDA(cudaFuncSetAttribute(agg_rows_bins_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        agg_rows_bins_kernel<1, 2><<<grid, BINS_WARPS * 32, smem, st>>>(a, nwarps, out, Bsum);
     }
     GNAN_LAUNCH_OK();
     return GNAN_OK;
