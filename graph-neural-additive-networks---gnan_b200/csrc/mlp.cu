@@ -572,7 +572,7 @@ BwdPlan plan_bwd(int64_t R, const gnan_mlp_params *p)
     const int per_sm = (p->H <= 64 && nh <= 1) ? 2 : 1;
     const int target = 2 * per_sm * gnan_sm_count();
     int nchunk = (int)ceil_div64(target, p->G);
-    if (nchunk > pl.ntile) nchunk = (int)pl.ntile;
+    nchunk = (int)std::min<int64_t>(nchunk, std::max<int64_t>(1, pl.ntile / 4));   // >= 4 tiles per CTA: short partial reduction
     if (nchunk < 1) nchunk = 1;
     pl.nchunk = nchunk;
     const int H = p->H, LD = H + 4, CP = (p->C + 7) / 8 * 8, CG = CP + 4;

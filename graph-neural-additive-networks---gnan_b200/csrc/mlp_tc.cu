@@ -859,7 +859,9 @@ TcBwdPlan plan_tc_bwd(int64_t R, const gnan_mlp_params *p)
     TcBwdPlan pl;
     pl.ntile = ceil_div64(R, ROWS);
     int nchunk = (int)ceil_div64(2 * gnan_sm_count(), p->G);
-    if (nchunk > pl.ntile) nchunk = (int)pl.ntile;
+    // every CTA stages the feature's weights and writes a partial gradient set: give it at least 4 tiles, which also keeps
+    // the partial-gradient reduction short (G = 1, the rho table, used to produce 254 chunks of 4.6 k floats)
+    nchunk = (int)std::min<int64_t>(nchunk, std::max<int64_t>(1, pl.ntile / 4));
     pl.nchunk = std::max(nchunk, 1);
     return pl;
 }
