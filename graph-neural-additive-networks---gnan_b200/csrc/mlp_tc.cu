@@ -372,7 +372,7 @@ __device__ long long g_tc_prof[16];
 #endif
 
 template <int CT, bool DROP>
-__global__ void __launch_bounds__(BWD_THREADS, 1)
+__global__ void __launch_bounds__(BWD_THREADS, 1)   // 17 warps occupy 20 warp slots (5 per scheduler): 96 registers is the cap
 mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t ntiles)
 {
     constexpr int NC = BWD_COLS;
@@ -524,13 +524,11 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
             const bool ok = blockIdx.x < ntiles && row < a.R;
             x_n = ok ? __ldg(a.u + row * a.ldu + g) : 0.f;
 #pragma unroll
-            for (int c = 0; c < CT; ++c) gv_n[c] = (ok && c < a.C) ? __ldg(dS + row * a.C + c) : 0.f;
+            for (int c = 0; c < CT; ++c) gv_n[c] = (ok && c < a.C && part == 0) ? __ldg(dS + row * a.C + c) : 0.f;
         }
         // dWo phase of tile `tp` (parity php): a1 recomputed from D1[php], staged to the scratch tile (sZ, free once MMA3 of
         // that tile is done), dWo[c][j] += g[r][c] a1[r][j]. Runs while the tensor core works on the NEXT tile's MMA1.
-        auto dwo_phase = [&](int64_t tp, uint32_t php) {
-            mbar_wait(smem_u32(&sm.d3_full), php);
-            tc_fence_after();
+        auto dwo_phase = [&](int64_t tp, uint32_t php) {      // caller has waited d3_full of that tile
             const int64_t rowp = tp * ROWS + r;
             uint32_t d[NC];
             IO::ld(lane_base + (php ? colD1b : colD1) + c0, d);
@@ -568,30 +566,25 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
             TC_PROF(7);
             const int64_t row = t * ROWS + r;
             const float x = x_n;
-            float gv[CT];
-#pragma unroll
-            for (int c = 0; c < CT; ++c) gv[c] = gv_n[c];
-            {
-                const int64_t tn = t + gridDim.x, rown = tn * ROWS + r;
-                const bool ok = tn < ntiles && rown < a.R;
-                x_n = 0.f;
-                if (ok) x_n = ldg_prefetch(a.u + rown * a.ldu + g);
-#pragma unroll
-                for (int c = 0; c < CT; ++c) {
-                    gv_n[c] = 0.f;
-                    if (ok && c < a.C) gv_n[c] = ldg_prefetch(dS + rown * a.C + c);
-                }
-            }
-            if (part == 0) {
+            const int64_t tn = t + gridDim.x, rown = tn * ROWS + r;
+            const bool okn = tn < ntiles && rown < a.R;
+            x_n = 0.f;
+            if (okn) x_n = ldg_prefetch(a.u + rown * a.ldu + g);
+            if (part == 0) {                                   // only these threads need dS: stage it for the dh MMA and the dWo phase
                 uint32_t gh[CT_MAX], gl[CT_MAX];
 #pragma unroll
                 for (int c = 0; c < CT_MAX; ++c) {
-                    const float v = c < CT ? gv[c < CT ? c : 0] : 0.f;
+                    const float v = c < CT ? gv_n[c < CT ? c : 0] : 0.f;
                     sm.sG[ph][r][c] = v;
                     split_tf32(v, gh[c], gl[c]);
                 }
                 tmem_st8(lane_base + colG_hi, gh);
                 tmem_st8(lane_base + colG_lo, gl);
+#pragma unroll
+                for (int c = 0; c < CT; ++c) {
+                    gv_n[c] = 0.f;
+                    if (okn && c < a.C) gv_n[c] = ldg_prefetch(dS + rown * a.C + c);
+                }
             }
             TC_PROF(9);
             // ---- [A] gen: a0 for units c0..c0+NC-1 -> TMEM only (the A operand of MMA1); then release the tensor core
@@ -617,15 +610,19 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
             tc_fence_before();
             mbar_arrive(smem_u32(&sm.a1_full));
             TC_PROF(0);
-            // ---- [B] previous tile's dWo phase, under this tile's MMA1
-            if (it > 0) dwo_phase(t - gridDim.x, ph ^ 1);
-            TC_PROF(6);
-            // ---- [C] stage a0^T (B operand of MMA3) now that MMA3 of the previous tile is done (d3 waited in [B])
+            // ---- [B] under this tile's MMA1: once MMA3 of the previous tile is done (its smem operands are free) stage a0^T
+            //          (B operand of this tile's MMA3; hi/lo die here), then run the previous tile's dWo phase
+            if (it > 0) {
+                mbar_wait(smem_u32(&sm.d3_full), ph ^ 1);
+                tc_fence_after();
+            }
 #pragma unroll
             for (int i = 0; i < NC; ++i) {
                 sm.sH_hi[tidx(c0 + i, r)] = __uint_as_float(hi[i]);
                 sm.sH_lo[tidx(c0 + i, r)] = __uint_as_float(lo[i]);
             }
+            if (it > 0) dwo_phase(t - gridDim.x, ph ^ 1);
+            TC_PROF(6);
             // ---- [D] epiC
             mbar_wait(smem_u32(&sm.d1_full), ph);
             tc_fence_after();
@@ -705,6 +702,8 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
         // the last tile's dWo phase
         if (it > 0) {
             const int64_t tl = (int64_t)blockIdx.x + (int64_t)(it - 1) * gridDim.x;
+            mbar_wait(smem_u32(&sm.d3_full), (it - 1) & 1);
+            tc_fence_after();
             dwo_phase(tl, (it - 1) & 1);
         }
         // ---- write this CTA's partial gradients (everything but dW2)
