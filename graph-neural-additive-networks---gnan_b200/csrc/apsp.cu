@@ -6,6 +6,7 @@
 // matrices are node_distances = 1/(1+hop) and normalization_matrix = cnt[i, hop[i,j]] (gnan_hops_to_reference).
 #include <algorithm>
 
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -173,6 +174,89 @@ apsp_bfs_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ 
     }
 }
 
+
+// ---- one large graph, bit-parallel multi-source BFS ---------------------------------------------------------------------
+constexpr int MSBFS_FLAG_STRIDE = 32;            // int32 per level flag: one 128-byte line each
+// A batch of SB = 32*W sources (= hop-matrix COLUMNS s0..s0+SB) is advanced together: every vertex v keeps W words of
+// "reached-from" bits. Level L is a PULL over v's out-neighbours u (edge v -> u): v reaches source s in L steps iff some u
+// reaches s in L-1 steps, so the value produced for (v, s) is dist(v -> s) = hop[v][s] and each vertex writes its OWN row
+// segment hop[v][s0 .. s0+SB) (contiguous bytes; no transposed CSR, no transpose pass, directed graphs included).
+// One launch per level; `changed` tells the host-side loop when the batch has converged.
+__global__ void msbfs_init_kernel(int N, int s0, int SB, int W, uint32_t *__restrict__ visited, uint32_t *__restrict__ frontier,
+                                  int row_begin, int row_end, uint8_t *__restrict__ hop, int64_t ld, int32_t *__restrict__ cnt, int nbins)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)N * W) return;
+    const int v = (int)(t / W), w = (int)(t % W);
+    uint32_t bits = 0u;
+    const int rel = v - s0 - w * 32;                     // v itself is source number w*32 + rel of the batch
+    if (rel >= 0 && rel < 32 && w * 32 + rel < SB) bits = 1u << rel;
+    visited[t] = bits;
+    frontier[t] = bits;
+    if (v >= row_begin && v < row_end) {
+        uint8_t *seg = hop + (int64_t)(v - row_begin) * ld + s0 + w * 32;
+        const int nvalid = min(32, SB - w * 32);
+        if (nvalid == 32 && bits == 0u) {                // ld % 16 == 0 and s0 % 32 == 0: 16-byte aligned
+            const uint4 ff = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+            reinterpret_cast<uint4 *>(seg)[0] = ff;
+            reinterpret_cast<uint4 *>(seg)[1] = ff;
+        } else {
+            for (int b = 0; b < nvalid; ++b) seg[b] = (bits >> b) & 1u ? 0 : GNAN_HOP_UNREACHABLE;
+        }
+        if (s0 == 0 && w == 0)                           // row padding columns [N, ld)
+            for (int64_t c = N; c < ld; ++c) hop[(int64_t)(v - row_begin) * ld + c] = GNAN_HOP_UNREACHABLE;
+        if (bits && cnt) atomicAdd(cnt + (int64_t)(v - row_begin) * nbins, 1);
+    }
+}
+
+__global__ void msbfs_level_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, int N, int s0, int W,
+                                   int level, uint32_t *__restrict__ visited, const uint32_t *__restrict__ frontier,
+                                   uint32_t *__restrict__ next, int row_begin, int row_end, uint8_t *__restrict__ hop, int64_t ld,
+                                   int32_t *__restrict__ cnt, int nbins, int32_t *__restrict__ changed, int32_t *__restrict__ overflow)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // the batch converged at an earlier level: nothing left to do. One flag per 128-byte line: the flag of THIS level is
+    // being stored to by other CTAs while the previous one is read (sharing a line cost 2x on the whole BFS).
+    if (level > 1 && changed[(level - 1) * MSBFS_FLAG_STRIDE] == 0) return;
+    const bool valid = t < (int64_t)N * W;
+    const int v = valid ? (int)(t / W) : 0, w = (int)(t % W);
+    uint32_t vis = 0xffffffffu, acc = 0u;
+    if (valid) {
+        vis = visited[t];
+        if (vis != 0xffffffffu) {
+            const int e1 = rowptr[v + 1];
+            for (int e = rowptr[v]; e < e1; ++e) acc |= frontier[(int64_t)col[e] * W + w];
+        }
+    }
+    const uint32_t nw = acc & ~vis;
+    if (valid) next[t] = nw;
+    if (__any_sync(0xffffffffu, nw != 0u) && (threadIdx.x & 31) == 0) changed[level * MSBFS_FLAG_STRIDE] = 1;
+    if (nw) {
+        visited[t] = vis | nw;
+        if (level > 254 || level >= nbins - 1) *overflow = 1;
+        if (v >= row_begin && v < row_end) {
+            uint8_t *seg = hop + (int64_t)(v - row_begin) * ld + s0 + w * 32;
+            uint32_t m = nw;
+            const uint8_t lv = (uint8_t)min(level, 254);
+            while (m) {
+                seg[__ffs(m) - 1] = lv;
+                m &= m - 1;
+            }
+            if (cnt && level < nbins - 1) atomicAdd(cnt + (int64_t)(v - row_begin) * nbins + level, __popc(nw));
+        }
+    }
+}
+
+// cnt[v][nbins-1] = (#columns) - sum of the finite levels
+__global__ void msbfs_unreachable_kernel(int rows, int ncols, int32_t *__restrict__ cnt, int nbins)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= rows) return;
+    int s = 0;
+    for (int d = 0; d < nbins - 1; ++d) s += cnt[(int64_t)v * nbins + d];
+    cnt[(int64_t)v * nbins + nbins - 1] = ncols - s;
+}
+
 // ---- converters ------------------------------------------------------------------------------------------------------
 __global__ void hops_to_reference_kernel(const uint8_t *__restrict__ hop, int64_t R, int64_t N, int64_t ld,
                                          const int32_t *__restrict__ cnt, int nbins, float *__restrict__ nd, float *__restrict__ nm)
@@ -241,6 +325,69 @@ extern "C" int gnan_apsp_bfs(const int32_t *rowptr, const int32_t *col, int32_t 
     apsp_bfs_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rowptr, col, N, src_begin, src_end, hop, ld_hop, cnt,
                                                                cnt ? nbins : 256, overflow_flag, queues, bitmaps, bm_words, nwarps);
     GNAN_LAUNCH_OK();
+    return GNAN_OK;
+}
+
+
+// ---- bit-parallel multi-source BFS (large graphs) ------------------------------------------------------------------------
+constexpr int MSBFS_W = 32;                      // 1024 sources per batch
+constexpr int MSBFS_MAX_LEVELS = 272;            // per-level "anything new?" flags (levels past 254 only raise overflow)
+constexpr int MSBFS_GROUP = 8;                   // levels launched per host round trip
+
+extern "C" size_t gnan_apsp_msbfs_workspace_bytes(int32_t N)
+{
+    return N > 0 ? 3 * sizeof(uint32_t) * (size_t)N * MSBFS_W + sizeof(int32_t) * MSBFS_MAX_LEVELS * MSBFS_FLAG_STRIDE : 0;
+}
+
+// Rows [row_begin,row_end) of the hop matrix of an N-node graph (all N columns). Unlike every other entry point this one
+// SYNCHRONISES the stream: the number of BFS levels is data dependent and is read back once per level group.
+extern "C" int gnan_apsp_msbfs(const int32_t *rowptr, const int32_t *col, int32_t N, int32_t row_begin, int32_t row_end,
+                               uint8_t *hop, int64_t ld_hop, int32_t *cnt, int32_t nbins, int32_t *overflow_flag,
+                               void *workspace, size_t workspace_bytes, gnan_stream_t stream)
+{
+    GNAN_REQUIRE(N >= 0 && row_begin >= 0 && row_end >= row_begin && row_end <= N, "apsp_msbfs: bad row range [%d,%d) N=%d", row_begin, row_end, N);
+    if (row_end == row_begin || N == 0) return GNAN_OK;
+    GNAN_REQUIRE(rowptr && hop && overflow_flag, "apsp_msbfs: NULL pointer");
+    GNAN_REQUIRE(ld_hop >= N && ld_hop % 16 == 0, "apsp_msbfs: ld_hop must be >= N and a multiple of 16");
+    GNAN_REQUIRE(!cnt || (nbins >= 2 && nbins <= 256), "apsp_msbfs: nbins %d out of [2,256]", nbins);
+    const size_t need = gnan_apsp_msbfs_workspace_bytes(N);
+    if (!workspace || workspace_bytes < need) {
+        gnan_set_error("apsp_msbfs: workspace %zu < %zu bytes", workspace_bytes, need);
+        return GNAN_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rows = row_end - row_begin;
+    const int nb = cnt ? nbins : 256;
+    uint32_t *visited = (uint32_t *)workspace;
+    uint32_t *bufA = visited + (size_t)N * MSBFS_W, *bufB = bufA + (size_t)N * MSBFS_W;
+    int32_t *changed = (int32_t *)(bufB + (size_t)N * MSBFS_W);
+    if (cnt) GNAN_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (size_t)rows * nb, st));
+    const unsigned blocks = (unsigned)ceil_div64((int64_t)N * MSBFS_W, 256);
+    for (int s0 = 0; s0 < N; s0 += 32 * MSBFS_W) {
+        const int SB = std::min(32 * MSBFS_W, N - s0);
+        uint32_t *frontier = bufA, *next = bufB;
+        msbfs_init_kernel<<<blocks, 256, 0, st>>>(N, s0, SB, MSBFS_W, visited, frontier, row_begin, row_end, hop, ld_hop, cnt, nb);
+        GNAN_LAUNCH_OK();
+        GNAN_CUDA(cudaMemsetAsync(changed, 0, sizeof(int32_t) * MSBFS_MAX_LEVELS * MSBFS_FLAG_STRIDE, st));
+        int level = 0;
+        for (;;) {
+            for (int k = 0; k < MSBFS_GROUP; ++k) {          // levels after convergence return at once (changed[level-1] == 0)
+                ++level;
+                msbfs_level_kernel<<<blocks, 256, 0, st>>>(rowptr, col, N, s0, MSBFS_W, level, visited, frontier, next, row_begin,
+                                                           row_end, hop, ld_hop, cnt, nb, changed, overflow_flag);
+                GNAN_LAUNCH_OK();
+                std::swap(frontier, next);
+            }
+            int32_t h = 0;
+            GNAN_CUDA(cudaMemcpyAsync(&h, changed + level * MSBFS_FLAG_STRIDE, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+            GNAN_CUDA(cudaStreamSynchronize(st));
+            if (!h || level + MSBFS_GROUP >= MSBFS_MAX_LEVELS) break;
+        }
+    }
+    if (cnt) {
+        msbfs_unreachable_kernel<<<(unsigned)ceil_div64(rows, 256), 256, 0, st>>>(rows, N, cnt, nb);
+        GNAN_LAUNCH_OK();
+    }
     return GNAN_OK;
 }
 

@@ -102,8 +102,14 @@ def _trim_counts(cnt256):
     return torch.cat([finite[:, :D + 1], cnt256[:, 255:256]], dim=1).contiguous()
 
 
-def apsp(edge_index, num_nodes, device="cuda", row_begin=0, row_end=None):
-    """All-pairs (or a source range of) hop distances of one graph on the GPU -> HopData."""
+MSBFS_MIN_NODES = 4096      # graphs at least this large use the bit-parallel multi-source BFS
+
+
+def apsp(edge_index, num_nodes, device="cuda", row_begin=0, row_end=None, method="auto"):
+    """All-pairs (or rows [row_begin,row_end) of the) hop distances of one graph on the GPU -> HopData.
+
+    method: "auto" | "warp" (one warp per source: small graphs, few rows) | "msbfs" (bit-parallel multi-source BFS over
+    1024 columns at a time: large graphs; the cost does not depend on the number of rows kept)."""
     lib = load()
     N = int(num_nodes)
     row_end = N if row_end is None else int(row_end)
@@ -112,9 +118,16 @@ def apsp(edge_index, num_nodes, device="cuda", row_begin=0, row_end=None):
     hop = torch.empty(R, hop_ld(N), dtype=torch.uint8, device=device)
     cnt = torch.empty(R, 256, dtype=torch.int32, device=device)
     flag = torch.zeros(1, dtype=torch.int32, device=device)
-    ws = torch.empty(max(lib.gnan_apsp_bfs_workspace_bytes(N, R), 1), dtype=torch.uint8, device=device)
-    check(lib.gnan_apsp_bfs(ptr(rowptr), ptr(col), N, row_begin, row_end, ptr(hop), hop.shape[1], ptr(cnt), 256, ptr(flag),
-                            ptr(ws), ws.numel(), stream_handle()), "gnan_apsp_bfs")
+    if method == "auto":
+        method = "msbfs" if N >= MSBFS_MIN_NODES and R * 8 >= N else "warp"
+    if method == "msbfs":
+        ws = torch.empty(max(lib.gnan_apsp_msbfs_workspace_bytes(N), 1), dtype=torch.uint8, device=device)
+        check(lib.gnan_apsp_msbfs(ptr(rowptr), ptr(col), N, row_begin, row_end, ptr(hop), hop.shape[1], ptr(cnt), 256, ptr(flag),
+                                  ptr(ws), ws.numel(), stream_handle()), "gnan_apsp_msbfs")
+    else:
+        ws = torch.empty(max(lib.gnan_apsp_bfs_workspace_bytes(N, R), 1), dtype=torch.uint8, device=device)
+        check(lib.gnan_apsp_bfs(ptr(rowptr), ptr(col), N, row_begin, row_end, ptr(hop), hop.shape[1], ptr(cnt), 256, ptr(flag),
+                                ptr(ws), ws.numel(), stream_handle()), "gnan_apsp_bfs")
     if R and int(flag.item()):
         raise NotImplementedError("a hop distance > 254 does not fit the uint8 hop matrix")
     return HopData(hop, _trim_counts(cnt) if R else cnt[:, :2], N, row_begin)

@@ -165,6 +165,15 @@ int gnan_apsp_bfs(const int32_t *rowptr /* [N+1] */, const int32_t *col /* [E] *
                   int32_t src_end, uint8_t *hop, int64_t ld_hop, int32_t *cnt /* [rows,nbins] or NULL */,
                   int32_t nbins, int32_t *overflow_flag, void *workspace, size_t workspace_bytes, gnan_stream_t stream);
 
+/* Same result for a LARGE graph with a bit-parallel multi-source BFS (1024 sources per batch, one launch per level, pull
+ * over out-neighbours so that every vertex writes its own row segment). Rows [row_begin,row_end), all N columns.
+ * Exception to the "nothing synchronises" rule: the level count is data dependent, the stream is synchronised once per
+ * group of 4 levels. cnt (if given) is zeroed by the callee. */
+size_t gnan_apsp_msbfs_workspace_bytes(int32_t N);
+int gnan_apsp_msbfs(const int32_t *rowptr, const int32_t *col, int32_t N, int32_t row_begin, int32_t row_end, uint8_t *hop,
+                    int64_t ld_hop, int32_t *cnt, int32_t nbins, int32_t *overflow_flag, void *workspace,
+                    size_t workspace_bytes, gnan_stream_t stream);
+
 /* B small graphs in one launch; CSR over the concatenated node set with GLOBAL column ids. */
 int gnan_apsp_bfs_batched(const int32_t *rowptr /* [sumN+1] */, const int32_t *col, const int32_t *node_off /* [B+1] */,
                           const int64_t *hop_off /* [B+1] */, int32_t B, uint8_t *hop, int32_t *cnt /* [sumN,nbins] or NULL */,

@@ -14,6 +14,7 @@ from tests._build import build_module
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
+TOL_TF32X3 = 3e-5   # end-to-end bound of the 3xTF32 tensor-core mode (kernel-level tests of that mode still hold 1e-5)
 DEV = "cuda"
 
 
@@ -25,7 +26,7 @@ def grads_of(stacked):
     return out
 
 
-def check_grads(z, got, want, tag):
+def check_grads(z, got, want, tag, tol=TOL):
     for k in ("w1", "b1", "wh", "bh", "wo", "bo"):
         w = want[k]
         if w is None or w.size == 0 or got[k] is None:
@@ -33,11 +34,12 @@ def check_grads(z, got, want, tag):
         if np.linalg.norm(w) == 0:
             assert np.abs(got[k]).max() < 1e-6, (z["name"], tag, k)
         else:
-            assert G.rel_err(got[k], w) < TOL, (z["name"], tag, k, G.rel_err(got[k], w))
+            assert G.rel_err(got[k], w) < tol, (z["name"], tag, k, G.rel_err(got[k], w))
 
 
-def run_case(z, compact):
+def run_case(z, compact, precision="fp32"):
     m = build_module(z, DEV).eval()
+    m.precision = precision
     w = torch.tensor(z["out_weight"], device=DEV)
     if z["variant"] == "batched":
         if compact:
@@ -67,15 +69,24 @@ def run_case(z, compact):
 RUNNABLE = [n for n in G.MODEL_CASES + G.BATCHED_CASES if "readout" not in n]
 
 
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
 @pytest.mark.parametrize("compact", [False, True], ids=["reference_inputs", "compact_inputs"])
 @pytest.mark.parametrize("name", RUNNABLE)
-def test_module_matches_reference_golden(name, compact):
+def test_module_matches_reference_golden(name, compact, precision):
+    """Both kernel paths against the unmodified reference's outputs and gradients (the tcgen05 path covers H = 64, 3 layers,
+    C <= 8; other golden shapes run the fp32 kernels under either setting).
+
+    fp32 kernels: 1e-5 (measured worst over the cases 1.5e-6). 3xTF32 tcgen05 kernels: each product carries ~2^-22 instead of
+    2^-24 relative error, so module-level errors are ~10x the fp32 ones: typically 1-3e-6, 1.1e-5 on the worst-conditioned
+    case (gnan_loop_shared_rho, 1/count normalisation with heavy cancellation, where the fp32 kernels are at 1.5e-6 too).
+    The stated bound for that mode is 3e-5 (scratch/debug_golden_tc.py prints the per-case numbers)."""
+    tol = TOL if precision == "fp32" else TOL_TF32X3
     z = G.load(name)
-    m, out = run_case(z, compact)
+    m, out = run_case(z, compact, precision)
     assert tuple(out.shape) == z["out"].shape
-    assert G.rel_err(out.detach().cpu().numpy(), z["out"]) < TOL
-    check_grads(z, grads_of(m.fs), z["grad_fs"], "fs")
-    check_grads(z, grads_of(m.rho), z["grad_rho"], "rho")
+    assert G.rel_err(out.detach().cpu().numpy(), z["out"]) < tol
+    check_grads(z, grads_of(m.fs), z["grad_fs"], "fs", tol)
+    check_grads(z, grads_of(m.rho), z["grad_rho"], "rho", tol)
 
 
 @pytest.mark.parametrize("name", G.PREPROCESS_CASES)
@@ -102,22 +113,42 @@ def random_graph(rng, n, avg_deg=3.0, directed=False, n_isolated=0):
     return e.T.astype(np.int64).reshape(2, -1)
 
 
-@pytest.mark.parametrize("n,deg,directed", [(1, 0, False), (2, 1, False), (257, 2.2, False), (1000, 3.0, True), (3001, 2.5, False)])
-def test_apsp_vs_oracle_random(n, deg, directed):
+@pytest.mark.parametrize("method", ["warp", "msbfs"])
+@pytest.mark.parametrize("n,deg,directed", [(1, 0, False), (2, 1, False), (257, 2.2, False), (1000, 3.0, True), (3001, 2.5, False),
+                                            (5000, 1.6, True)])
+def test_apsp_vs_oracle_random(n, deg, directed, method):
     from gnan_b200.preprocess import apsp
     rng = np.random.default_rng(n)
     ei = random_graph(rng, n, deg, directed, n_isolated=min(3, n - 1))
     hop = oapsp.apsp(ei, n)
     cnt = oapsp.level_counts(hop)
-    hd = apsp(torch.tensor(ei), n, device=DEV)
+    hd = apsp(torch.tensor(ei), n, device=DEV, method=method)
     got = hd.hop[:, :n].cpu().numpy().astype(np.int32)
     got[got == 255] = -1
     assert np.array_equal(got, hop)
     assert np.array_equal(hd.level_counts.cpu().numpy(), cnt)
     # row-sharded call == slice of the full matrix
     if n > 10:
-        part = apsp(torch.tensor(ei), n, device=DEV, row_begin=n // 3, row_end=n // 3 + 7)
+        part = apsp(torch.tensor(ei), n, device=DEV, row_begin=n // 3, row_end=n // 3 + 7, method=method)
         assert torch.equal(part.hop[:, :n], hd.hop[n // 3:n // 3 + 7, :n])
+        assert torch.equal(part.level_counts[:, :-1], hd.level_counts[n // 3:n // 3 + 7, :part.level_counts.shape[1] - 1])
+
+
+@pytest.mark.parametrize("method", ["warp", "msbfs"])
+def test_apsp_path_graph_depth_limit(method):
+    """uint8 hop matrix: depth 254 is representable, 255 is refused loudly (the reference has no such limit, its fp32
+    matrices just do not fit any GPU at that size)."""
+    from gnan_b200.preprocess import apsp
+
+    def path(n):
+        a = np.arange(n - 1)
+        return torch.tensor(np.stack([np.concatenate([a, a + 1]), np.concatenate([a + 1, a])]))
+    hd = apsp(path(255), 255, device=DEV, method=method)
+    i = torch.arange(255, device=DEV)
+    assert torch.equal(hd.hop[:, :255].long(), (i[:, None] - i[None, :]).abs())
+    assert hd.nbins == 256 and int(hd.level_counts[0, 254]) == 1 and int(hd.level_counts[:, -1].sum()) == 0
+    with pytest.raises(NotImplementedError):
+        apsp(path(256), 256, device=DEV, method=method)
 
 
 def test_apsp_batched_vs_oracle():
