@@ -21,7 +21,8 @@ class MlpParams(ctypes.Structure):
 
 
 class MlpGrads(ctypes.Structure):
-    _fields_ = [("w1", c_void_p), ("b1", c_void_p), ("wh", c_void_p), ("bh", c_void_p), ("wo", c_void_p), ("bo", c_void_p)]
+    _fields_ = [("w1", c_void_p), ("b1", c_void_p), ("wh", c_void_p), ("bh", c_void_p), ("wo", c_void_p), ("bo", c_void_p),
+                ("du", c_void_p)]
 
 
 # name -> (restype, argtypes); must list every symbol include/gnan_b200.h declares (tests/test_cabi.py checks it)

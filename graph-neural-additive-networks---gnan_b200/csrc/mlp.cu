@@ -25,6 +25,7 @@ struct MlpKArgs {
     uint32_t drop_thresh;  // 0 = no dropout
     float drop_scale;
     uint64_t seed;
+    float *du;  // backward only: [R,G] gradient w.r.t. the inputs, or NULL
 };
 
 __device__ __forceinline__ float relu(float v) { return v > 0.f ? v : 0.f; }
@@ -467,6 +468,14 @@ mlp_bwd_kernel(MlpKArgs a, const float *__restrict__ dS, MlpGradPtrs gp, int64_t
             pw1 += s1;
             pb1 += s0;
         }
+        if (a.du && row0 + tid < a.R) {  // du[r,g] = sum_i dz_0[r][i] * w1[i]   (row tid; rotated start: no bank conflicts)
+            float s = 0.f;
+            for (int k = 0; k < H; ++k) {
+                const int i = (k + tid) & (H - 1);
+                s = fmaf(sAct[tid * LD + i], sW1[i], s);
+            }
+            a.du[(row0 + tid) * a.G + g] = s;
+        }
     }
     __syncthreads();
     // ---- write this CTA's partial gradients
@@ -531,6 +540,18 @@ __global__ void linear1_bwd_kernel(MlpKArgs a, const float *__restrict__ dS, flo
         }
         __syncthreads();
     }
+}
+
+// du[r,g] = sum_c dS[r,c] * wo[g,c]
+__global__ void linear1_du_kernel(MlpKArgs a, const float *__restrict__ dS)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.R * a.G) return;
+    const int64_t r = i / a.G;
+    const int g = (int)(i % a.G);
+    float s = 0.f;
+    for (int c = 0; c < a.C; ++c) s = fmaf(dS[r * a.C + c], a.wo[(size_t)g * a.C + c], s);
+    a.du[i] = s;
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------
@@ -614,6 +635,7 @@ MlpKArgs make_args(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params
     a.drop_thresh = dropout_p > 0.f ? gnan_dropout_thresh(dropout_p) : 0u;
     a.drop_scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
     a.seed = seed;
+    a.du = nullptr;
     return a;
 }
 
@@ -729,10 +751,15 @@ extern "C" int gnan_mlp_bwd(const float *u, int64_t R, int64_t ldu, const gnan_m
     GNAN_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "mlp_bwd: dropout_p %f out of [0,1)", dropout_p);
     cudaStream_t st = (cudaStream_t)stream;
     MlpKArgs a = make_args(u, R, ldu, p, dropout_p, seed);
+    a.du = grads->du;
     const size_t G = p->G, H = p->H, C = p->C;
     if (p->n_layers == 1) {
         linear1_bwd_kernel<<<p->G, 256, 0, st>>>(a, dS, grads->wo, grads->bo);
         GNAN_LAUNCH_OK();
+        if (a.du && R > 0) {
+            linear1_du_kernel<<<(unsigned)ceil_div64(R * p->G, 256), 256, 0, st>>>(a, dS);
+            GNAN_LAUNCH_OK();
+        }
         return GNAN_OK;
     }
     const size_t nh = p->n_layers - 2;
@@ -745,7 +772,7 @@ extern "C" int gnan_mlp_bwd(const float *u, int64_t R, int64_t ldu, const gnan_m
         if (grads->bo) GNAN_CUDA(cudaMemsetAsync(grads->bo, 0, sizeof(float) * G * C, st));
         return GNAN_OK;
     }
-    if (precision != GNAN_PREC_FP32 && gnan_mlp_tc_bwd_supported(p, precision))
+    if (precision != GNAN_PREC_FP32 && !grads->du && gnan_mlp_tc_bwd_supported(p, precision))   // input gradients: fp32 kernel only
         return gnan_mlp_tc_bwd(u, R, ldu, p, dropout_p, seed, precision, dS, grads, workspace, workspace_bytes, st);
     const BwdPlan pl = plan_bwd(R, p);
     MlpGradPtrs gp;

@@ -4,8 +4,10 @@
 Differences from GNAN.py's TensorGNAN that are honoured here (models.py:320-321,366-370):
   * rho has ONE output unless `rho_per_feature` (then out_channels);
   * `normalize_rho` divides rho's OUTPUT by the normalisation matrix;
-  * graph task with `readout_n_layers > 0` (a NAM over the per-feature pooled values, :348-350,380-381) is not on the
-    fused path yet and raises NotImplementedError; main.py's default is readout_n_layers=0.
+  * graph task with `readout_n_layers > 0`: shape functions and rho have ONE output, the aggregated value is kept per
+    feature (hidden[k] = sum_i sum_j W_ij f_k(x_jk), :374-379) and a `NAM` (:258-300) over those K values produces the
+    graph output (:380-381). The per-feature form runs on the same kernels: f's output layer is expanded to a
+    block-diagonal [K,K,H] weight so that "channel" k of the kernel's feature sum is f_k alone (K <= 64).
 """
 import torch
 
@@ -14,6 +16,23 @@ from ._inputs import resolve
 from ._stacked import StackedMLP
 from .GNAN import GNAN as _GNAN, _Base
 from .preprocess import PackedBatch
+
+
+class NAM(_Base):
+    """models.py:258-300: out[r,:] = sum_k g_k(x[r,k]) on the grouped-MLP kernel."""
+
+    def __init__(self, in_channels, out_channels, num_layers, hidden_channels=None, bias=True, dropout=0.0, device='cpu'):
+        super().__init__()
+        self.device = device
+        self.out_channels = out_channels
+        self.hidden_channels = hidden_channels
+        self.num_layers = num_layers
+        self.bias = bias
+        self.dropout = dropout
+        self.fs = StackedMLP(in_channels, out_channels, num_layers, hidden_channels, bias, 3, dropout)
+
+    def forward(self, x):
+        return self._feature_sums(x.to(self._device()).float().contiguous())
 
 
 class TensorGNAN(_Base):
@@ -30,24 +49,43 @@ class TensorGNAN(_Base):
         self.normalize_rho = normalize_rho
         self.is_graph_task = is_graph_task
         self.readout_n_layers = readout_n_layers
-        if is_graph_task and readout_n_layers > 0:
-            raise NotImplementedError("readout_n_layers > 0 (NAM readout, models.py:348-350) is not implemented in "
-                                      "gnan_b200 yet; main.py's default is 0")
-        self.actual_output_dim_f = out_channels
-        self.actual_output_dim_rho = out_channels if rho_per_feature else 1
+        self._readout = bool(is_graph_task and readout_n_layers > 0)
+        if self._readout and in_channels > 64:
+            raise NotImplementedError("the NAM readout keeps one kernel channel per feature: in_channels <= 64")
+        self.actual_output_dim_f = 1 if self._readout else out_channels                       # models.py:320-321
+        self.actual_output_dim_rho = 1 if (not rho_per_feature or self._readout) else out_channels
         self.fs = StackedMLP(in_channels, self.actual_output_dim_f, n_layers, hidden_channels, bias, 3, dropout)
         self.rho = StackedMLP(1, self.actual_output_dim_rho, n_layers, hidden_channels, not is_graph_task, 2, single=True)
+        if self._readout:
+            self.readout_nam = NAM(in_channels, out_channels, readout_n_layers, hidden_channels, bias, dropout, device)
+            self.readout_nam.fs.xavier_normal_(0.01)                                 # models.py:352-356 covers it too
         self.fs.xavier_normal_(0.01)
         self.rho.xavier_normal_(0.01)
+
+    def _per_feature(self, x):
+        """Y[j,k] = f_k(x_jk) (one output per shape function): the kernel sums over features per channel, so give feature
+        k its own channel through a block-diagonal output layer."""
+        if x.shape[1] != self.fs.groups:
+            raise ValueError(f"x has {x.shape[1]} features, model was built for {self.fs.groups}")
+        w1, b1, wh, bh, wo, bo, L = self.fs.kernel_args()
+        eye = torch.eye(self.fs.groups, device=wo.device, dtype=wo.dtype)
+        wo_x = eye.unsqueeze(-1) * wo[:, 0].unsqueeze(1)                             # [K,K,H]: row k nonzero only in channel k
+        bo_x = eye * bo[:, 0].unsqueeze(1)
+        p = self.fs.dropout if self.training else 0.0
+        return ops.mlp(x, w1, b1, wh, bh, wo_x, bo_x, L, dropout_p=p, seed=self._seed() if p > 0 else 0,
+                       precision=self.precision)
 
     def forward(self, inputs):
         if isinstance(inputs, PackedBatch):
             return self.forward_packed(inputs)
         x, hd = resolve(inputs, self._device())
-        S = self._feature_sums(x)
+        S = self._per_feature(x) if self._readout else self._feature_sums(x)
         T = self._table(ops.rho_table_inputs(hd.nbins, x.device))                    # [nbins,Cr]
         rs = ops.level_rscale(hd.level_counts) if self.normalize_rho else None       # models.py:368-370
         out = ops.aggregate_rows(hd.hop, T, S, rscale=rs)
+        if self._readout:
+            hidden = out.sum(dim=0).view(1, -1)                                      # [1,K]  models.py:379
+            return self.readout_nam(hidden).T                                        # [C,1]  models.py:380-384
         if self.is_graph_task:
             out = out.sum(dim=0).view(1, -1).T
         return out
@@ -58,10 +96,12 @@ class TensorGNAN(_Base):
         dev = self._device()
         if pk.x.device != dev:
             pk = pk.to(dev)
-        S = self._feature_sums(pk.x.float().contiguous())
+        x = pk.x.float().contiguous()
+        S = self._per_feature(x) if self._readout else self._feature_sums(x)
         T = self._table(ops.rho_table_inputs(pk.nbins, dev))
         rs = ops.level_rscale(pk.level_counts) if self.normalize_rho else None
-        return ops.aggregate_blockdiag(pk.hop, pk.hop_off, pk.node_off, T, S, rscale=rs, reduce_graph=self.is_graph_task)
+        out = ops.aggregate_blockdiag(pk.hop, pk.hop_off, pk.node_off, T, S, rscale=rs, reduce_graph=self.is_graph_task)
+        return self.readout_nam(out) if self._readout else out                       # [B,K] -> [B,C]
 
 
 class GNAN(_GNAN):

@@ -97,13 +97,15 @@ def _(u, w1, b1, wh, bh, wo, bo, n_layers, dropout_p, seed, precision):
 
 @torch.library.custom_op("gnan_b200::mlp_bwd", mutates_args=())
 def mlp_bwd(u: Tensor, w1: Tensor, b1: Tensor, wh: Tensor, bh: Tensor, wo: Tensor, bo: Tensor, n_layers: int,
-            dropout_p: float, seed: int, precision: int, dS: Tensor) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+            dropout_p: float, seed: int, precision: int, dS: Tensor,
+            need_du: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
     lib = load()
     u, w1, b1, wh, bh, wo, bo, dS = (_f32(t, n) for t, n in zip((u, w1, b1, wh, bh, wo, bo, dS), "u w1 b1 wh bh wo bo dS".split()))
     p, G, H, C = _mlp_params(w1, b1, wh, bh, wo, bo, n_layers)
     R = u.shape[0]
     outs = [torch.empty_like(t) for t in (w1, b1, wh, bh, wo, bo)]
-    g = MlpGrads(*[ptr(t) for t in outs])
+    outs.append(torch.empty((R, G) if need_du else (0,), dtype=torch.float32, device=u.device))
+    g = MlpGrads(*[ptr(t) for t in outs[:6]], ptr(outs[6]) if need_du else None)
     ws = _ws(lib.gnan_mlp_workspace_bytes(R, p, 1, precision), u.device)
     with _timed("mlp_bwd"):
         check(lib.gnan_mlp_bwd(ptr(u), R, u.shape[1], p, float(dropout_p), int(seed) & (2 ** 64 - 1), precision, ptr(dS),
@@ -112,8 +114,8 @@ def mlp_bwd(u: Tensor, w1: Tensor, b1: Tensor, wh: Tensor, bh: Tensor, wo: Tenso
 
 
 @mlp_bwd.register_fake
-def _(u, w1, b1, wh, bh, wo, bo, n_layers, dropout_p, seed, precision, dS):
-    return tuple(torch.empty_like(t) for t in (w1, b1, wh, bh, wo, bo))
+def _(u, w1, b1, wh, bh, wo, bo, n_layers, dropout_p, seed, precision, dS, need_du):
+    return tuple(torch.empty_like(t) for t in (w1, b1, wh, bh, wo, bo)) + (u.new_empty(u.shape if need_du else (0,)),)
 
 
 def _mlp_setup(ctx, inputs, output):
@@ -125,15 +127,17 @@ def _mlp_setup(ctx, inputs, output):
 def _mlp_backward(ctx, dS):
     u, w1, b1, wh, bh, wo, bo = ctx.saved_tensors
     n_layers, dropout_p, seed, precision = ctx.cfg
-    g = mlp_bwd(u, w1, b1, wh, bh, wo, bo, n_layers, dropout_p, seed, precision, dS.contiguous())
-    return (None,) + tuple(g) + (None, None, None, None)
+    need_du = bool(ctx.needs_input_grad[0])
+    g = mlp_bwd(u, w1, b1, wh, bh, wo, bo, n_layers, dropout_p, seed, precision, dS.contiguous(), need_du)
+    return (g[6] if need_du else None,) + tuple(g[:6]) + (None, None, None, None)
 
 
 mlp_fwd.register_autograd(_mlp_backward, setup_context=_mlp_setup)
 
 
 def mlp(u, w1, b1, wh, bh, wo, bo, n_layers, dropout_p=0.0, seed=0, precision="fp32"):
-    """S[r,:] = sum_g f_g(u[r,g]); differentiable w.r.t. the weights (not u: inputs are data, GNAN.py:56)."""
+    """S[r,:] = sum_g f_g(u[r,g]); differentiable w.r.t. the weights, and w.r.t. u when u requires grad (only the NAM
+    readout feeds computed values in; x itself is data, GNAN.py:56)."""
     return mlp_fwd(u, w1, b1, wh, bh, wo, bo, int(n_layers), float(dropout_p), int(seed), _lib.PRECISIONS[precision])
 
 

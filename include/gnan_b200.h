@@ -63,6 +63,8 @@ typedef struct {
 
 typedef struct { /* gradient outputs, same shapes; NULL = not wanted. Overwritten, not accumulated. */
     float *w1, *b1, *wh, *bh, *wo, *bo;
+    float *du; /* [R,G] gradient w.r.t. the scalar inputs u, or NULL. Only the NAM readout needs it (its inputs are the
+                  pooled per-feature values, models.py:379-381); requesting it selects the fp32 kernels. */
 } gnan_mlp_grads;
 
 /* precision: how the HxH hidden contractions are computed */

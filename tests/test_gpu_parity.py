@@ -66,7 +66,7 @@ def run_case(z, compact, precision="fp32"):
     return m, out
 
 
-RUNNABLE = [n for n in G.MODEL_CASES + G.BATCHED_CASES if "readout" not in n]
+RUNNABLE = G.MODEL_CASES + G.BATCHED_CASES
 
 
 @pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
@@ -87,6 +87,8 @@ def test_module_matches_reference_golden(name, compact, precision):
     assert G.rel_err(out.detach().cpu().numpy(), z["out"]) < tol
     check_grads(z, grads_of(m.fs), z["grad_fs"], "fs", tol)
     check_grads(z, grads_of(m.rho), z["grad_rho"], "rho", tol)
+    if "grad_readout" in z:                                   # models.py NAM readout (readout_n_layers > 0)
+        check_grads(z, grads_of(m.readout_nam.fs), z["grad_readout"], "readout", tol)
 
 
 @pytest.mark.parametrize("name", G.PREPROCESS_CASES)
@@ -149,6 +151,34 @@ def test_apsp_path_graph_depth_limit(method):
     assert hd.nbins == 256 and int(hd.level_counts[0, 254]) == 1 and int(hd.level_counts[:, -1].sum()) == 0
     with pytest.raises(NotImplementedError):
         apsp(path(256), 256, device=DEV, method=method)
+
+
+@pytest.mark.parametrize("G_,H,C,L", [(5, 64, 3, 3), (7, 16, 2, 2), (3, 32, 4, 4), (4, 8, 2, 1)])
+def test_mlp_input_gradient_vs_oracle(G_, H, C, L):
+    """du of gnan_mlp_bwd (needed by the NAM readout, whose inputs are computed values) against autograd of the port."""
+    from gnan_b200 import ops
+    gen = torch.Generator().manual_seed(G_ * 100 + H)
+    R = 300
+    nh, Hh = max(L - 2, 0), (H if L >= 2 else 1)
+    p = dict(w1=torch.randn(G_, Hh, generator=gen), b1=torch.randn(G_, Hh, generator=gen),
+             wh=torch.randn(nh, G_, Hh, Hh, generator=gen) / Hh ** 0.5, bh=torch.randn(nh, G_, Hh, generator=gen) * 0.1,
+             wo=torch.randn(G_, C, Hh, generator=gen) / Hh ** 0.5, bo=torch.randn(G_, C, generator=gen))
+    if L == 1:
+        p.update(w1=torch.zeros(0), b1=torch.zeros(0), wh=torch.zeros(0), bh=torch.zeros(0))
+    u = torch.randn(R, G_, generator=gen)
+    w = torch.randn(R, C, generator=gen)
+    uo = u.clone().requires_grad_(True)
+    q = {k: v.clone() for k, v in p.items()}
+    if L == 1:
+        q["w1"] = None
+    want = gnan_port.shape_functions(q, uo).sum(dim=1)
+    (want * w).sum().backward()
+    ud = u.to(DEV).requires_grad_(True)
+    d = {k: v.to(DEV).requires_grad_(True) for k, v in p.items()}
+    got = ops.mlp(ud, d["w1"], d["b1"], d["wh"], d["bh"], d["wo"], d["bo"], L)
+    (got * w.to(DEV)).sum().backward()
+    assert G.rel_err(got.detach().cpu().numpy(), want.detach().numpy()) < TOL
+    assert G.rel_err(ud.grad.cpu().numpy(), uo.grad.numpy()) < TOL
 
 
 def test_apsp_batched_vs_oracle():
@@ -374,6 +404,41 @@ def test_blockdiag_equals_per_graph_dense_rows():
         rT, rS = torch.autograd.grad((ref * w).sum(), (T, S))
         assert G.rel_err(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) < TOL
         assert G.rel_err(gT.cpu().numpy(), rT.cpu().numpy()) < TOL and G.rel_err(gS.cpu().numpy(), rS.cpu().numpy()) < TOL
+
+
+def test_readout_packed_batch_equals_per_graph_forward():
+    """models.TensorGNAN with the NAM readout: the packed many-graph call equals the reference-shaped per-graph forward
+    (rows of the [B,C] result == each graph's out.T), outputs and parameter gradients."""
+    from gnan_b200.models import TensorGNAN
+    from gnan_b200.preprocess import apsp, apsp_batched
+    rng = np.random.default_rng(21)
+    sizes = [5, 17, 40, 3, 26]
+    K, C = 6, 3
+    node_off = np.concatenate([[0], np.cumsum(sizes)])
+    eis = [random_graph(rng, n, 2.2, False, n_isolated=1 if n > 8 else 0) for n in sizes]
+    ei = np.concatenate([e + node_off[i] for i, e in enumerate(eis)], axis=1)
+    x = torch.tensor(rng.normal(size=(node_off[-1], K))).float()
+    torch.manual_seed(1)
+    m = TensorGNAN(K, C, 3, 64, is_graph_task=True, readout_n_layers=2).to(DEV)
+    m.fs.xavier_normal_(1.0); m.rho.xavier_normal_(1.0); m.readout_nam.fs.xavier_normal_(1.0)
+    pk = apsp_batched(torch.tensor(ei), torch.tensor(node_off), device=DEV)
+    pk.x = x.to(DEV)
+    w = torch.tensor(rng.normal(size=(len(sizes), C))).float().to(DEV)
+    out = m(pk)
+    assert tuple(out.shape) == (len(sizes), C)
+    params = list(m.parameters())
+    g_pk = torch.autograd.grad((out * w).sum(), params)
+    ref = []
+    for i, n in enumerate(sizes):
+        d = SimpleNamespace(x=x[node_off[i]:node_off[i + 1]], hop_data=apsp(torch.tensor(eis[i]), n, device=DEV))
+        o = m.forward(d)
+        assert tuple(o.shape) == (C, 1)
+        ref.append(o.T)
+    ref = torch.cat(ref)
+    g_ref = torch.autograd.grad((ref * w).sum(), params)
+    assert G.rel_err(out.detach().cpu().numpy(), ref.detach().cpu().numpy()) < TOL
+    for a, b in zip(g_pk, g_ref):
+        assert G.rel_err(a.cpu().numpy(), b.cpu().numpy()) < TOL
 
 
 def test_node_order_permutation_equivariance():

@@ -14,10 +14,6 @@ from tests._build import build_module
 @pytest.mark.parametrize("name", G.MODEL_CASES + G.BATCHED_CASES)
 def test_loads_reference_state_dict(name):
     z = G.load(name)
-    if z.get("readout_n_layers", 0) > 0 and z["is_graph_task"] and z["variant"] == "models_tensor":
-        with pytest.raises(NotImplementedError):
-            build_module(z)
-        return
     m = build_module(z)                      # strict load of the reference's own keys
     sd = m.state_dict()
     ref = {k: v for k, v in z["sd"].items() if not k.startswith("rhos.")}
