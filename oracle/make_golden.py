@@ -170,6 +170,88 @@ def preprocess_case(name, pre_py, rng, n, n_isolated, directed, node_task=False)
          normalization_matrix=d.normalization_matrix.numpy(), meta=np.array([n, int(directed), int(node_task)]))
 
 
+class _Data(types.SimpleNamespace):
+    """The slice of torch_geometric.data.Data that trainer.py touches (attributes + .to)."""
+
+    def to(self, device):
+        return self
+
+
+def trainer_case(name, models_py, pre_py, trainer_py, rng, *, graph_task, n_items, K_raw, C, H, epochs, lr, wd=0.0,
+                 compute_auc=False, pm1_labels=False):
+    """Run the UNMODIFIED trainer.train_epoch / test_epoch (trainer.py:23-160) with models.TensorGNAN (what main.py builds,
+    main.py:84-90) and Adam (main.py:141) on a tiny seeded dataset; record the per-epoch return tuples and final weights."""
+    items = []
+    if graph_task:
+        for _ in range(n_items):
+            n = int(rng.integers(5, 14))
+            ei = random_graph(rng, n, n_isolated=1 if n > 9 else 0)
+            x = np.eye(K_raw, dtype=np.float32)[rng.integers(0, K_raw, size=n)]
+            d = preprocess_with_reference(pre_py, x, ei, is_graph_task=True)
+            yv = float(rng.integers(0, 2))
+            y = torch.tensor([2 * yv - 1 if pm1_labels else yv])
+            items.append(_Data(x=d.x, edge_index=d.edge_index, node_distances=d.node_distances,
+                               normalization_matrix=d.normalization_matrix, y=y))
+        loss_fn = torch.nn.BCEWithLogitsLoss()
+    else:
+        n = 60
+        ei = random_graph(rng, n, n_isolated=2)
+        ei = np.concatenate([ei, np.array([[0, n - 1], [n - 1, 0]])], axis=1)
+        x = ((rng.random((n, K_raw)) < 0.5) * rng.normal(size=(n, K_raw))).astype(np.float32)
+        d = preprocess_with_reference(pre_py, x, ei, is_graph_task=False)
+        split = rng.permutation(n)
+        mk = lambda ids: torch.zeros(n, dtype=torch.bool).index_fill_(0, torch.tensor(ids), True)
+        items.append(_Data(x=d.x, edge_index=d.edge_index, node_distances=d.node_distances,
+                           normalization_matrix=d.normalization_matrix, y=torch.tensor(rng.integers(0, C, size=n)),
+                           train_mask=mk(split[:30]), val_mask=mk(split[30:45]), test_mask=mk(split[45:])))
+        loss_fn = torch.nn.CrossEntropyLoss()
+    K = K_raw + 1
+    model = models_py.TensorGNAN(in_channels=K, out_channels=C, n_layers=3, hidden_channels=H, bias=True, dropout=0.0,
+                                 device="cpu", normalize_rho=True, is_graph_task=graph_task, readout_n_layers=0)
+    reinit(model, int(rng.integers(0, 2 ** 31)))
+    sd0 = {k: v.detach().clone().numpy() for k, v in model.state_dict().items()}
+    opt = torch.optim.Adam(params=model.parameters(), lr=lr, weight_decay=wd)
+    hist = []
+    import io, contextlib
+    for _ in range(epochs):
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+            tr = trainer_py.train_epoch(model, dloader=items, loss_fn=loss_fn, optimizer=opt, classify=True, device="cpu",
+                                        compute_auc=compute_auc, is_graph_task=graph_task)
+            va = trainer_py.test_epoch(model, dloader=items, loss_fn=loss_fn, classify=True, device="cpu", val_mask=True,
+                                       compute_auc=compute_auc, is_graph_task=graph_task)
+        model.train()
+        hist.append([float(t) for t in tr] + [float(t) for t in va])
+    arrs = dict(history=np.array(hist, dtype=np.float64),
+                meta=np.array([int(graph_task), len(items), K, C, H, epochs, int(compute_auc), int(pm1_labels)], dtype=np.int64),
+                hyper=np.array([lr, wd], dtype=np.float64))
+    for i, it in enumerate(items):
+        arrs[f"item{i}.x"] = it.x.numpy()
+        arrs[f"item{i}.edge_index"] = it.edge_index.numpy()
+        arrs[f"item{i}.y"] = it.y.numpy()
+        if not graph_task:
+            for m in ("train_mask", "val_mask", "test_mask"):
+                arrs[f"item{i}.{m}"] = getattr(it, m).numpy()
+    arrs.update({f"sd0.{k}": v for k, v in sd0.items()})
+    arrs.update({f"sd1.{k}": v.detach().numpy() for k, v in model.state_dict().items()})
+    os.makedirs(OUT, exist_ok=True)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrs)
+    print("wrote", name, "history", np.array(hist)[-1])
+
+
+def trainer_cases():
+    """Separate entry (python -m oracle.make_golden trainer): own seed, leaves the other fixtures untouched."""
+    torch.manual_seed(0)
+    torch.set_num_threads(4)
+    _, models_py, pre_py, _ = import_reference()
+    import importlib
+    trainer_py = importlib.import_module("trainer")
+    rng = np.random.default_rng(20240917)
+    trainer_case("trainer_graph_bce", models_py, pre_py, trainer_py, rng, graph_task=True, n_items=10, K_raw=5, C=1, H=16,
+                 epochs=3, lr=5e-3, compute_auc=True, pm1_labels=True)
+    trainer_case("trainer_node_ce", models_py, pre_py, trainer_py, rng, graph_task=False, n_items=1, K_raw=6, C=3, H=64,
+                 epochs=6, lr=5e-3, wd=1e-4)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(4)
@@ -218,4 +300,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    trainer_cases() if sys.argv[1:] == ["trainer"] else main()

@@ -558,3 +558,87 @@ def test_mlp_tensor_core_backward_with_dropout_matches_fp32_path():
         grads[prec] = {k: v.grad.cpu().numpy() for k, v in d.items()}
     for k in p:
         assert G.rel_err(grads["tf32x3"][k], grads["fp32"][k]) < 2e-4, k     # same masks; a kink may flip under different rounding
+
+
+# ---- training loop around the path ----------------------------------------------------------------------
+def _trainer_items(z, graph_task, n_items):
+    from gnan_b200.preprocess import apsp
+    items = []
+    for i in range(n_items):
+        x = torch.tensor(z[f"item{i}.x"])
+        ei = torch.tensor(z[f"item{i}.edge_index"])
+        d = SimpleNamespace(x=x.to(DEV), edge_index=ei, hop_data=apsp(ei, x.shape[0], device=DEV), y=torch.tensor(z[f"item{i}.y"]))
+        if not graph_task:
+            for m in ("train_mask", "val_mask", "test_mask"):
+                setattr(d, m, torch.tensor(z[f"item{i}.{m}"]))
+        items.append(d)
+    return items
+
+
+@pytest.mark.parametrize("name", ["trainer_graph_bce", "trainer_node_ce"])
+def test_trainer_epochs_match_reference_trainer(name):
+    """gnan_b200.trainer.train_epoch / test_epoch against the UNMODIFIED trainer.py driving models.TensorGNAN + Adam
+    (tests/golden/trainer_*.npz): the per-epoch (loss, accuracy, auc) tuples and the weights after the last epoch.
+    Losses 1e-4 relative (Adam divides by sqrt(v): early steps amplify 1e-6 gradient differences); weights 2e-3."""
+    from gnan_b200 import trainer
+    from gnan_b200.models import TensorGNAN
+    z = dict(np.load(f"{G.GOLDEN_DIR}/{name}.npz"))
+    graph_task, n_items, K, C, H, epochs, compute_auc, _ = [int(t) for t in z["meta"]]
+    lr, wd = [float(t) for t in z["hyper"]]
+    m = TensorGNAN(K, C, 3, H, is_graph_task=bool(graph_task), readout_n_layers=0)
+    m.load_state_dict({k[4:]: torch.tensor(v) for k, v in z.items() if k.startswith("sd0.")}, strict=True)
+    m = m.to(DEV)
+    items = _trainer_items(z, bool(graph_task), n_items)
+    loss_fn = torch.nn.BCEWithLogitsLoss() if graph_task else torch.nn.CrossEntropyLoss()
+    opt = torch.optim.Adam(params=m.parameters(), lr=lr, weight_decay=wd)
+    hist = []
+    for _ in range(epochs):
+        tr = trainer.train_epoch(m, dloader=items, loss_fn=loss_fn, optimizer=opt, classify=True, device=DEV,
+                                 compute_auc=bool(compute_auc), is_graph_task=bool(graph_task))
+        va = trainer.test_epoch(m, dloader=items, loss_fn=loss_fn, classify=True, device=DEV, val_mask=True,
+                                compute_auc=bool(compute_auc), is_graph_task=bool(graph_task))
+        m.train()
+        hist.append(list(tr) + list(va))
+    hist = np.array(hist, dtype=np.float64)
+    want = z["history"]
+    assert hist.shape == want.shape
+    assert np.allclose(hist[:, [0, 3]], want[:, [0, 3]], rtol=1e-4, atol=0), (hist[:, [0, 3]], want[:, [0, 3]])   # losses
+    assert np.allclose(hist[:, [1, 4]], want[:, [1, 4]], atol=1e-6)                                              # accuracies
+    assert np.allclose(hist[:, [2, 5]], want[:, [2, 5]], atol=1e-6)                                              # auc / -1
+    sd = m.state_dict()
+    for k, v in z.items():
+        if k.startswith("sd1."):
+            assert G.rel_err(sd[k[4:]].cpu().numpy(), v) < 2e-3, k
+
+
+def test_captured_step_equals_eager_steps():
+    """trainer.CapturedStep (whole step replayed as one CUDA graph) follows the same trajectory as eager steps."""
+    from gnan_b200 import trainer
+    from gnan_b200.GNAN import TensorGNAN
+    from gnan_b200.preprocess import apsp
+    rng = np.random.default_rng(8)
+    n, K, C = 300, 9, 4
+    ei = torch.tensor(random_graph(rng, n, 2.5, False, n_isolated=3))
+    x = torch.tensor(rng.normal(size=(n, K))).float().to(DEV)
+    y = torch.tensor(rng.integers(0, C, size=n)).to(DEV)
+    hd = apsp(ei, n, device=DEV)
+    data = SimpleNamespace(x=x, hop_data=hd)
+    losses = {}
+    for mode in ("eager", "graph"):
+        torch.manual_seed(0)
+        m = TensorGNAN(K, C, 3, 64).to(DEV)
+        m.fs.xavier_normal_(1.0); m.rho.xavier_normal_(1.0)
+        opt = torch.optim.Adam(m.parameters(), lr=1e-3, capturable=True)
+        closure = lambda: torch.nn.functional.cross_entropy(m.forward(data), y)
+        if mode == "eager":
+            out = []
+            for _ in range(3 + 5):
+                opt.zero_grad(set_to_none=True)
+                l = closure(); l.backward(); opt.step()
+                out.append(float(l))
+            losses[mode] = out[3:]
+        else:
+            step = trainer.CapturedStep(closure, opt, warmup=2)      # 2 warm-up steps + 1 captured (capture does not execute)
+            assert step.kernel_launches > 0
+            losses[mode] = [float(step()) for _ in range(6)][1:]
+    assert np.allclose(losses["eager"], losses["graph"], rtol=1e-5), losses

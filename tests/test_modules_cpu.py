@@ -76,3 +76,33 @@ def test_no_cpu_fallback():
                            normalization_matrix=torch.tensor(z["normalization_matrix"]))
     with pytest.raises((GnanError, RuntimeError)):
         m.forward(data)
+
+
+def test_trainer_auc_matches_sklearn_and_signatures_match_reference():
+    import inspect
+    from sklearn.metrics import roc_auc_score
+    from gnan_b200 import trainer
+    rng = np.random.default_rng(0)
+    for n in (7, 200):
+        y = rng.integers(0, 2, size=n); y[0], y[1] = 0, 1
+        s = np.round(rng.random(n), 1 if n > 50 else 3)            # the coarse rounding creates ties
+        assert abs(trainer.roc_auc(torch.tensor(y), torch.tensor(s)) - roc_auc_score(y, s)) < 1e-12
+    assert list(inspect.signature(trainer.train_epoch).parameters) == [
+        "model", "dloader", "loss_fn", "optimizer", "device", "classify", "label_index", "compute_auc", "is_graph_task"]
+    assert list(inspect.signature(trainer.test_epoch).parameters) == [
+        "model", "dloader", "loss_fn", "device", "classify", "label_index", "compute_auc", "val_mask", "is_graph_task"]
+
+
+def test_trainer_label_handling_follows_reference():
+    from types import SimpleNamespace
+    from gnan_b200 import trainer
+    bce, ce = torch.nn.BCEWithLogitsLoss(), torch.nn.CrossEntropyLoss()
+    d = SimpleNamespace(y=torch.tensor([[-1.0, 1.0], [1.0, -1.0]]))
+    assert trainer._labels_of(d, bce, 0).tolist() == [0.0, 1.0]          # trainer.py:33-39 ({-1,1} -> {0,1}, column pick)
+    assert trainer._labels_of(d, bce, 1).tolist() == [1.0, 0.0]
+    d = SimpleNamespace(y=torch.tensor([2, 0, 1]))
+    lab = trainer._labels_of(d, ce, 0)
+    assert lab.dtype == torch.long and lab.tolist() == [2, 0, 1]
+    out = torch.tensor([[0.3], [-0.2], [2.0]])
+    assert trainer.get_accuracy(out, torch.tensor([1.0, 0.0, 0.0])) == 2  # trainer.py:5-12
+    assert int(trainer.get_accuracy(torch.tensor([[0.1, 0.9], [0.8, 0.2]]), torch.tensor([1, 1]))) == 1
