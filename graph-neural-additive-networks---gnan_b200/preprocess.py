@@ -198,8 +198,11 @@ def pre_process(data, is_graph_task, data_name=None, processed_data_dir=None, de
     Appends the constant-1 column to x (:108/:127) and attaches `.hop_data` (HopData, on `device`). With
     reference_format=True also attaches fp32 `.node_distances` / `.normalization_matrix` like the reference.
     Graph task: `data` is a list of graphs; node task: one graph (num_nodes inferred from edge_index like :128).
-    Saving to processed_data_dir is the caller's business (torch.save works on the returned objects).
+    With `processed_data_dir` (and `data_name`) the result is written once, like :144-148, but in the packed format of
+    gnan_b200.packed ({dir}/{name}.gnan_b200.pt: 1 byte per node pair instead of 8); read it back with
+    packed.PackedDataset.load (graph task) or packed.load_node (node task).
     """
+    import os
     graphs = list(data) if is_graph_task else [data]
     for g in graphs:
         g.x = torch.cat((g.x, torch.ones(g.x.size(0), 1, dtype=g.x.dtype, device=g.x.device)), dim=-1)
@@ -209,4 +212,13 @@ def pre_process(data, is_graph_task, data_name=None, processed_data_dir=None, de
         g.hop_data = hd
         if reference_format:
             g.node_distances, g.normalization_matrix = hd.reference_format()
+    if processed_data_dir is not None and data_name is not None:
+        path = os.path.join(processed_data_dir, f"{data_name}.gnan_b200.pt")
+        if not os.path.exists(path):
+            os.makedirs(processed_data_dir, exist_ok=True)
+            from . import packed
+            if is_graph_task:
+                packed.PackedDataset.from_graphs(graphs, device=device, add_constant_column=False).save(path)
+            else:
+                packed.save_node(data, path)
     return data

@@ -642,3 +642,89 @@ def test_captured_step_equals_eager_steps():
             assert step.kernel_launches > 0
             losses[mode] = [float(step()) for _ in range(6)][1:]
     assert np.allclose(losses["eager"], losses["graph"], rtol=1e-5), losses
+
+
+# ---- packed dataset format and loader ---------------------------------------------------------------------
+GRAPH_PRE = ["preprocess_tree_undirected", "preprocess_isolated_undirected", "preprocess_directed", "preprocess_single_node"]
+
+
+def test_packed_dataset_matches_reference_preprocess_bit_exactly(tmp_path):
+    """One batched GPU BFS over several graphs -> packed format -> the reference's per-graph fp32 tensors, compared
+    bit-for-bit with what the unmodified pre_process() produced (tests/golden/preprocess_*.npz); and the way back."""
+    from gnan_b200.packed import PackedDataset
+    zs = [G.load(n) for n in GRAPH_PRE]
+    graphs = [SimpleNamespace(x=torch.tensor(z["x"]), edge_index=torch.tensor(z["edge_index"].reshape(2, -1)),
+                              y=torch.tensor([i % 2])) for i, z in enumerate(zs)]
+    ds = PackedDataset.from_graphs(graphs, device=DEV)
+    assert len(ds) == len(zs) and ds.y.tolist() == [0, 1, 0, 1]
+    for g, z in zip(ds.to_reference(), zs):
+        assert np.array_equal(g.x.cpu().numpy(), z["x_out"])
+        assert np.array_equal(g.node_distances.cpu().numpy(), z["node_distances"])
+        assert np.array_equal(g.normalization_matrix.cpu().numpy(), z["normalization_matrix"])
+    ref_graphs = [SimpleNamespace(x=torch.tensor(z["x_out"]), node_distances=torch.tensor(z["node_distances"]),
+                                  normalization_matrix=torch.tensor(z["normalization_matrix"]), y=torch.tensor([i % 2]))
+                  for i, z in enumerate(zs)]
+    back = PackedDataset.from_reference(ref_graphs, device=DEV)
+    for k in ("x", "node_off", "hop", "hop_off", "level_counts", "y"):
+        assert torch.equal(getattr(back, k), getattr(ds, k)), k
+    path = tmp_path / "ds.gnan_b200.pt"
+    ds.save(path)
+    again = PackedDataset.load(path, device=DEV)
+    for k in ("x", "node_off", "hop", "hop_off", "level_counts", "y"):
+        assert torch.equal(getattr(again, k), getattr(ds, k)), k
+    fp32_bytes = sum(2 * 4 * z["node_distances"].size for z in zs)          # what processed_data/{name}.pt stores per pair
+    assert ds.hop.numel() * 8 == fp32_bytes
+
+
+def test_packed_loader_batches_equal_per_graph_forward_and_train(tmp_path):
+    from gnan_b200 import trainer
+    from gnan_b200.models import TensorGNAN
+    from gnan_b200.packed import PackedDataset
+    from gnan_b200.preprocess import pre_process
+    rng = np.random.default_rng(4)
+    graphs = []
+    for i in range(9):
+        n = int(rng.integers(3, 40))
+        graphs.append(SimpleNamespace(x=torch.tensor(rng.normal(size=(n, 4))).float(), y=torch.tensor([float(i % 2)]),
+                                      edge_index=torch.tensor(random_graph(rng, n, 2.2, False, n_isolated=1 if n > 8 else 0))))
+    pre_process(graphs, True, "toy", processed_data_dir=str(tmp_path), device=DEV)          # reference call shape; writes the file
+    ds = PackedDataset.load(tmp_path / "toy.gnan_b200.pt", device=DEV)
+    assert len(ds) == 9 and ds.x.shape[1] == 5
+    torch.manual_seed(0)
+    m = TensorGNAN(5, 1, 3, 64, is_graph_task=True, readout_n_layers=0).to(DEV)
+    m.fs.xavier_normal_(1.0); m.rho.xavier_normal_(1.0)
+    per_graph = torch.cat([m.forward(SimpleNamespace(x=g.x.to(DEV), hop_data=g.hop_data)).T for g in graphs])   # [9,1]
+    ids = [7, 2, 5, 0]
+    out = m(ds.batch(ids))
+    assert G.rel_err(out.detach().cpu().numpy(), per_graph[ids].detach().cpu().numpy()) < TOL
+    seen = torch.cat([m(pk).detach() for pk in ds.loader(4)])
+    assert G.rel_err(seen.cpu().numpy(), per_graph.detach().cpu().numpy()) < TOL
+    # an epoch of mini-batch training through the drop-in trainer == the same steps written out by hand
+    loss_fn = torch.nn.BCEWithLogitsLoss()
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    opt = torch.optim.Adam(m.parameters(), lr=1e-2)
+    l1, a1, _ = trainer.train_epoch(m, ds.loader(4), loss_fn, opt, DEV, is_graph_task=True)
+    w1 = m.fs.wh.detach().clone()
+    m.load_state_dict(sd0)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-2)
+    tot = 0.0
+    for pk in ds.loader(4):
+        opt.zero_grad()
+        l = loss_fn(m(pk).flatten(), pk.y.float()); l.backward(); opt.step(); tot += float(l)
+    assert abs(l1 - tot / 3) < 1e-6 * max(1.0, abs(l1)) and 0.0 <= a1 <= 1.0
+    assert torch.allclose(w1, m.fs.wh.detach(), rtol=0, atol=1e-7)
+
+
+def test_node_dataset_file_roundtrip(tmp_path):
+    from gnan_b200.packed import load_node
+    from gnan_b200.preprocess import pre_process
+    z = G.load("preprocess_node_task")
+    d = SimpleNamespace(x=torch.tensor(z["x"]), edge_index=torch.tensor(z["edge_index"].reshape(2, -1)),
+                        y=torch.arange(z["x"].shape[0]) % 3, train_mask=torch.arange(z["x"].shape[0]) % 2 == 0)
+    pre_process(d, False, "node", processed_data_dir=str(tmp_path), device=DEV)
+    back = load_node(tmp_path / "node.gnan_b200.pt", device=DEV)
+    n = back.hop_data.num_nodes
+    assert torch.equal(back.hop_data.hop[:, :n], d.hop_data.hop[:, :n]) and torch.equal(back.hop_data.level_counts, d.hop_data.level_counts)
+    assert torch.equal(back.x.cpu(), d.x) and torch.equal(back.y.cpu(), d.y) and torch.equal(back.train_mask.cpu(), d.train_mask)
+    nd, nm = back.hop_data.reference_format()
+    assert np.array_equal(nd.cpu().numpy(), z["node_distances"]) and np.array_equal(nm.cpu().numpy(), z["normalization_matrix"])

@@ -106,3 +106,43 @@ def test_trainer_label_handling_follows_reference():
     out = torch.tensor([[0.3], [-0.2], [2.0]])
     assert trainer.get_accuracy(out, torch.tensor([1.0, 0.0, 0.0])) == 2  # trainer.py:5-12
     assert int(trainer.get_accuracy(torch.tensor([[0.1, 0.9], [0.8, 0.2]]), torch.tensor([1, 1]))) == 1
+
+
+def _toy_packed():
+    from gnan_b200.packed import PackedDataset
+    sizes = [2, 3, 1]
+    hops = [torch.tensor([[0, 1], [1, 0]]), torch.tensor([[0, 1, 255], [1, 0, 255], [255, 255, 0]]), torch.tensor([[0]])]
+    node_off = torch.tensor([0, 2, 5, 6], dtype=torch.int32)
+    hop_off = torch.tensor([0, 4, 13, 14], dtype=torch.int64)
+    hop = torch.cat([h.reshape(-1) for h in hops]).to(torch.uint8)
+    cnt = torch.tensor([[1, 1, 0], [1, 1, 0], [1, 1, 1], [1, 1, 1], [1, 0, 2], [1, 0, 0]], dtype=torch.int32)
+    x = torch.arange(12, dtype=torch.float32).view(6, 2)
+    return PackedDataset(x, node_off, hop, hop_off, cnt, torch.tensor([1, 0, 1])), hops
+
+
+def test_packed_dataset_batch_gather_save_load_and_reference_view(tmp_path):
+    """Host logic of the packed format (pure tensor indexing: runs on any device)."""
+    from gnan_b200.packed import PackedDataset
+    ds, hops = _toy_packed()
+    assert len(ds) == 3 and ds.nbins == 3 and ds.max_nodes == 3
+    b = ds.batch([2, 0])
+    assert b.node_off.tolist() == [0, 1, 3] and b.hop_off.tolist() == [0, 1, 5]
+    assert b.hop.tolist() == [0, 0, 1, 1, 0] and b.x.tolist() == [[10.0, 11.0], [0.0, 1.0], [2.0, 3.0]]
+    assert b.level_counts.tolist() == [[1, 0, 0], [1, 1, 0], [1, 1, 0]] and b.y.tolist() == [1, 1] and b.max_nodes == 2
+    seen = []
+    for pk in ds.loader(2, shuffle=True, generator=torch.Generator().manual_seed(0)):
+        seen += pk.y.tolist()
+        assert pk.hop.numel() == int(pk.hop_off[-1])
+    assert sorted(seen) == [0, 1, 1]
+    path = tmp_path / "toy.gnan_b200.pt"
+    ds.save(path)
+    back = PackedDataset.load(path, device=None)
+    for k in ("x", "node_off", "hop", "hop_off", "level_counts", "y"):
+        assert torch.equal(getattr(back, k), getattr(ds, k)), k
+    with pytest.raises(ValueError):
+        torch.save({"format": "something else"}, tmp_path / "bad.pt")
+        PackedDataset.load(tmp_path / "bad.pt", device=None)
+    ref = ds.to_reference()
+    g = ref[1]                                                           # pre_process_datasets.py:112-121 on the 3-node graph
+    assert torch.equal(g.node_distances, torch.tensor([[1.0, 0.5, 0.0], [0.5, 1.0, 0.0], [0.0, 0.0, 1.0]]))
+    assert torch.equal(g.normalization_matrix, torch.tensor([[1.0, 1.0, 1.0], [1.0, 1.0, 1.0], [2.0, 2.0, 1.0]]))
