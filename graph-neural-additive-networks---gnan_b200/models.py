@@ -50,8 +50,6 @@ class TensorGNAN(_Base):
         self.is_graph_task = is_graph_task
         self.readout_n_layers = readout_n_layers
         self._readout = bool(is_graph_task and readout_n_layers > 0)
-        if self._readout and in_channels > 64:
-            raise NotImplementedError("the NAM readout keeps one kernel channel per feature: in_channels <= 64")
         self.actual_output_dim_f = 1 if self._readout else out_channels                       # models.py:320-321
         self.actual_output_dim_rho = 1 if (not rho_per_feature or self._readout) else out_channels
         self.fs = StackedMLP(in_channels, self.actual_output_dim_f, n_layers, hidden_channels, bias, 3, dropout)
@@ -64,16 +62,12 @@ class TensorGNAN(_Base):
 
     def _per_feature(self, x):
         """Y[j,k] = f_k(x_jk) (one output per shape function): the kernel sums over features per channel, so give feature
-        k its own channel through a block-diagonal output layer."""
+        k its own channel through a block-diagonal output layer (ops.mlp_per_group)."""
         if x.shape[1] != self.fs.groups:
             raise ValueError(f"x has {x.shape[1]} features, model was built for {self.fs.groups}")
-        w1, b1, wh, bh, wo, bo, L = self.fs.kernel_args()
-        eye = torch.eye(self.fs.groups, device=wo.device, dtype=wo.dtype)
-        wo_x = eye.unsqueeze(-1) * wo[:, 0].unsqueeze(1)                             # [K,K,H]: row k nonzero only in channel k
-        bo_x = eye * bo[:, 0].unsqueeze(1)
         p = self.fs.dropout if self.training else 0.0
-        return ops.mlp(x, w1, b1, wh, bh, wo_x, bo_x, L, dropout_p=p, seed=self._seed() if p > 0 else 0,
-                       precision=self.precision)
+        return ops.mlp_per_group(x, *self.fs.kernel_args(), dropout_p=p, seed=self._seed() if p > 0 else 0,
+                                 precision=self.precision).squeeze(-1)               # [N,K,1] -> [N,K]
 
     def forward(self, inputs):
         if isinstance(inputs, PackedBatch):

@@ -141,6 +141,39 @@ def mlp(u, w1, b1, wh, bh, wo, bo, n_layers, dropout_p=0.0, seed=0, precision="f
     return mlp_fwd(u, w1, b1, wh, bh, wo, bo, int(n_layers), float(dropout_p), int(seed), _lib.PRECISIONS[precision])
 
 
+MAX_KERNEL_CHANNELS = 64      # gnan_mlp_* limit on C
+
+
+def mlp_per_group(u, w1, b1, wh, bh, wo, bo, n_layers, dropout_p=0.0, seed=0, precision="fp32"):
+    """Y[r,g,:] = f_g(u[r,g]) WITHOUT the sum over groups -> [R,G,C] (the reference's `fx`, GNAN.py:57-62, which the NAM
+    readout, models.py:374-381, and the interpretability plots need per feature).
+
+    Same kernels: the output layer of a chunk of groups is expanded to a block-diagonal [Gc, Gc*C, H] weight, so group g
+    owns channels [g*C, (g+1)*C) of the kernel's feature sum and every other group contributes exactly 0 there. Differentiable
+    like `mlp`. Chunks keep Gc*C <= 64."""
+    R, G = u.shape
+    C = wo.shape[1]
+    if C > MAX_KERNEL_CHANNELS:
+        raise ValueError(f"out_channels {C} > {MAX_KERNEL_CHANNELS}")
+    gc_max = max(1, MAX_KERNEL_CHANNELS // C)
+    outs = []
+    for g0 in range(0, G, gc_max):
+        g1 = min(G, g0 + gc_max)
+        gc = g1 - g0
+        idx = torch.arange(gc, device=wo.device)
+        wo_x = wo.new_zeros(gc, gc, C, wo.shape[2])
+        wo_x[idx, idx] = wo[g0:g1]
+        bo_x = bo.new_zeros(gc, gc, C)
+        bo_x[idx, idx] = bo[g0:g1]
+        hid = n_layers >= 2
+        y = mlp(u[:, g0:g1].contiguous(), w1[g0:g1] if hid else w1, b1[g0:g1] if hid else b1,
+                wh[:, g0:g1].contiguous() if hid else wh, bh[:, g0:g1].contiguous() if hid else bh,
+                wo_x.view(gc, gc * C, -1), bo_x.view(gc, gc * C), n_layers, dropout_p=dropout_p,
+                seed=(seed + g0) if dropout_p > 0 else 0, precision=precision)
+        outs.append(y.view(R, gc, C))
+    return outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # dense row-block aggregation
 # ---------------------------------------------------------------------------------------------------------------------

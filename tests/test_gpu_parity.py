@@ -635,7 +635,7 @@ def test_captured_step_equals_eager_steps():
             for _ in range(3 + 5):
                 opt.zero_grad(set_to_none=True)
                 l = closure(); l.backward(); opt.step()
-                out.append(float(l))
+                out.append(float(l.detach()))
             losses[mode] = out[3:]
         else:
             step = trainer.CapturedStep(closure, opt, warmup=2)      # 2 warm-up steps + 1 captured (capture does not execute)
@@ -710,7 +710,7 @@ def test_packed_loader_batches_equal_per_graph_forward_and_train(tmp_path):
     tot = 0.0
     for pk in ds.loader(4):
         opt.zero_grad()
-        l = loss_fn(m(pk).flatten(), pk.y.float()); l.backward(); opt.step(); tot += float(l)
+        l = loss_fn(m(pk).flatten(), pk.y.float()); l.backward(); opt.step(); tot += float(l.detach())
     assert abs(l1 - tot / 3) < 1e-6 * max(1.0, abs(l1)) and 0.0 <= a1 <= 1.0
     assert torch.allclose(w1, m.fs.wh.detach(), rtol=0, atol=1e-7)
 
@@ -728,3 +728,51 @@ def test_node_dataset_file_roundtrip(tmp_path):
     assert torch.equal(back.x.cpu(), d.x) and torch.equal(back.y.cpu(), d.y) and torch.equal(back.train_mask.cpu(), d.train_mask)
     nd, nm = back.hop_data.reference_format()
     assert np.array_equal(nd.cpu().numpy(), z["node_distances"]) and np.array_equal(nm.cpu().numpy(), z["normalization_matrix"])
+
+
+# ---- interpretability export ------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["gnanpy_tensor_graph", "gnanpy_tensor_node", "gnanpy_tensor_node_l1", "gnanpy_tensor_node_l4",
+                                  "models_tensor_graph_readout", "batched_graph"])
+def test_interpretability_tables_match_reference_modules(name):
+    """What the notebook computes point by point with model.fs[i].forward / model.m.forward (cells 4, 6, 9), in bulk from
+    the kernels, against the port's scalar MLP on the golden weights."""
+    from gnan_b200 import interpret
+    z = G.load(name)
+    m = build_module(z, DEV).eval()
+    fs = gnan_port.to_torch(z["fs"]); rho = gnan_port.to_torch(z["rho"])
+    grid = torch.linspace(-1.5, 2.0, 23)
+    got = interpret.shape_function_table(m, grid).cpu()
+    want = torch.stack([gnan_port.scalar_mlp(fs, k, grid.view(-1, 1)) for k in range(z["K"])], dim=1)
+    assert tuple(got.shape) == (23, z["K"], want.shape[-1])
+    assert G.rel_err(got.numpy(), want.numpy()) < TOL
+    D = 9
+    d = torch.arange(D + 1).float()
+    u = d if z["variant"] == "batched" else 1.0 / (1.0 + d)
+    want_r = gnan_port.scalar_mlp(rho, 0, u.view(-1, 1))
+    got_r = interpret.distance_function_table(m, D).cpu()
+    assert G.rel_err(got_r.numpy(), want_r.numpy()) < TOL
+    hm = interpret.heatmap(m, D).cpu()
+    f1 = torch.stack([gnan_port.scalar_mlp(fs, k, torch.ones(1, 1))[0, 0] for k in range(z["K"])])
+    assert G.rel_err(hm.numpy(), torch.outer(f1, want_r[:, 0]).numpy()) < TOL
+
+
+def test_mlp_per_group_chunked_with_gradients():
+    """K*C > 64 forces several kernel calls; values and weight gradients against autograd of the port."""
+    from gnan_b200 import ops
+    gen = torch.Generator().manual_seed(5)
+    R, K, C, H, L = 70, 30, 7, 64, 3
+    p = dict(w1=torch.randn(K, H, generator=gen), b1=torch.randn(K, H, generator=gen),
+             wh=torch.randn(1, K, H, H, generator=gen) / 8, bh=torch.randn(1, K, H, generator=gen) * 0.1,
+             wo=torch.randn(K, C, H, generator=gen) / 8, bo=torch.randn(K, C, generator=gen))
+    u = torch.randn(R, K, generator=gen)
+    w = torch.randn(R, K, C, generator=gen)
+    q = {k: v.clone().requires_grad_(True) for k, v in p.items()}
+    want = gnan_port.shape_functions(q, u)
+    (want * w).sum().backward()
+    d = {k: v.to(DEV).requires_grad_(True) for k, v in p.items()}
+    got = ops.mlp_per_group(u.to(DEV), d["w1"], d["b1"], d["wh"], d["bh"], d["wo"], d["bo"], L)
+    (got * w.to(DEV)).sum().backward()
+    assert tuple(got.shape) == (R, K, C)
+    assert G.rel_err(got.detach().cpu().numpy(), want.detach().numpy()) < TOL
+    for k in p:
+        assert G.rel_err(d[k].grad.cpu().numpy(), q[k].grad.numpy()) < TOL, k
