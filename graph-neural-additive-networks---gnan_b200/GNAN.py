@@ -15,13 +15,15 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from ._inputs import resolve
+from ._inputs import compressed_of, resolve
 from ._stacked import StackedMLP
 from .preprocess import PackedBatch
 
 
 class _Base(nn.Module):
     precision = "fp32"      # "fp32" | "tf32x3" | "tf32": how the HxH hidden layers are contracted (see gnan_b200.h)
+    dedup = True            # share shape-function evaluations between rows with equal feature values (gnan_b200.sparse) when
+                            # dropout is off and the input is compressible (bag-of-words, one-hot, constant columns)
 
     def _device(self):
         return self.fs.wo.device
@@ -30,7 +32,24 @@ class _Base(nn.Module):
         self._calls = getattr(self, "_calls", 0) + 1
         return (torch.initial_seed() * 0x9E3779B97F4A7C15 + self._calls * 0xD1B54A32D192ED03) & (2 ** 63 - 1)
 
-    def _feature_sums(self, x):
+    def _dedup_ok(self):
+        return bool(self.dedup) and self.fs.n_layers >= 2 and not (self.training and self.fs.dropout > 0)
+
+    def _features(self, holder):
+        """(x on the device or None, CompressedFeatures or None) of an input object (reference Data-like or PackedBatch)."""
+        dev = self._device()
+        x = holder.x
+        cx = compressed_of(holder, x, dev, self._dedup_ok())
+        if cx is None:
+            if x is None:
+                raise ValueError("inputs.x is None and its compressed form cannot be used (dropout active or dedup disabled)")
+            x = x.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+        return (None if cx is not None else x), cx
+
+    def _feature_sums(self, x, cx=None):
+        if cx is not None:
+            from . import sparse
+            return sparse.feature_sums(cx, *self.fs.kernel_args())
         if x.shape[1] != self.fs.groups:
             raise ValueError(f"x has {x.shape[1]} features, model was built for {self.fs.groups}")
         p = self.fs.dropout if self.training else 0.0
@@ -66,14 +85,15 @@ class TensorGNAN(_Base):
     def forward(self, inputs):
         if isinstance(inputs, PackedBatch):
             return self.forward_packed(inputs)
-        x, hd = resolve(inputs, self._device())
-        S = self._feature_sums(x)                                                    # [N,C]   GNAN.py:57-62 (+ :73 by linearity)
+        dev = self._device()
+        _, hd = resolve(inputs, dev, need_x=False)
+        S = self._feature_sums(*self._features(inputs))                              # [N,C]   GNAN.py:57-62 (+ :73 by linearity)
         if self.normalize_rho:                                                       # GNAN.py:65-67: rho(nd / norm)
-            u = ops.rho_table_inputs(hd.nbins, x.device, cnt=hd.level_counts)        # [R,nbins]
+            u = ops.rho_table_inputs(hd.nbins, dev, cnt=hd.level_counts)             # [R,nbins]
             T = self._table(u).view(hd.rows, hd.nbins, self.out_channels)
             out = ops.aggregate_rows(hd.hop, T, S, per_row=True)
         else:
-            T = self._table(ops.rho_table_inputs(hd.nbins, x.device))                # [nbins,C]
+            T = self._table(ops.rho_table_inputs(hd.nbins, dev))                     # [nbins,C]
             out = ops.aggregate_rows(hd.hop, T, S)
         if self.is_graph_task:
             out = out.sum(dim=0).view(1, -1).T                                        # [C,1]  GNAN.py:76-79
@@ -84,12 +104,12 @@ class TensorGNAN(_Base):
         """Many graphs in one call (extension; the reference trains with batch_size=1, datasets.py:339-341): `pk` is a
         preprocess.PackedBatch; returns [B,C] for graph tasks (row b == the reference's out.T for graph b) or [sumN,C]."""
         dev = self._device()
-        if pk.x.device != dev:
+        if pk.hop.device != dev:
             pk = pk.to(dev)
-        S = self._feature_sums(pk.x.float().contiguous())
+        S = self._feature_sums(*self._features(pk))
         if self.normalize_rho:
             u = ops.rho_table_inputs(pk.nbins, dev, cnt=pk.level_counts)
-            T = self._table(u).view(pk.x.shape[0], pk.nbins, self.out_channels)
+            T = self._table(u).view(S.shape[0], pk.nbins, self.out_channels)
             return ops.aggregate_blockdiag(pk.hop, pk.hop_off, pk.node_off, T, S, per_row=True, reduce_graph=self.is_graph_task)
         T = self._table(ops.rho_table_inputs(pk.nbins, dev))
         return ops.aggregate_blockdiag(pk.hop, pk.hop_off, pk.node_off, T, S, reduce_graph=self.is_graph_task)
@@ -115,12 +135,13 @@ class GNAN(_Base):
         self.rho = StackedMLP(1, out_channels if rho_per_feature else 1, n_layers, hidden_channels, bias, 2, single=True)
 
     def forward(self, inputs, node_ids=None):
-        x, hd = resolve(inputs, self._device())
-        S = self._feature_sums(x)                                                    # f_sums, GNAN.py:150-157
-        T = self._table(ops.rho_table_inputs(hd.nbins, x.device))                    # [nbins,Cr]  rho(1/(1+d))
+        dev = self._device()
+        _, hd = resolve(inputs, dev, need_x=False)
+        S = self._feature_sums(*self._features(inputs))                              # f_sums, GNAN.py:150-157
+        T = self._table(ops.rho_table_inputs(hd.nbins, dev))                         # [nbins,Cr]  rho(1/(1+d))
         hop, cnt = hd.hop, hd.level_counts
         if node_ids is not None:                                                     # row subset, GNAN.py:146-149
-            ids = torch.as_tensor(node_ids, device=x.device, dtype=torch.long)
+            ids = torch.as_tensor(node_ids, device=dev, dtype=torch.long)
             hop, cnt = hop.index_select(0, ids), cnt.index_select(0, ids)
         rs = ops.level_rscale(cnt) if self.normalize_rho else None                   # GNAN.py:163-168: rho(.) / norm
         return ops.aggregate_rows(hop, T, S, rscale=rs)                              # [len(node_ids), C]

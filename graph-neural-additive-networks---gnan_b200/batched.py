@@ -63,10 +63,11 @@ class TensorGNAN(_Base):
         else:
             dev = self._device()
             pk = pack_dense(x_batch.to(dev), dist_batch.to(dev), batch_vector.to(dev))
+            pk._gnan_b200_no_dedup = True
         dev = self._device()
-        if pk.x.device != dev:
+        if pk.hop.device != dev:
             pk = pk.to(dev)
-        S = self._feature_sums(pk.x.float().contiguous())
+        S = self._feature_sums(*self._features(pk))
         nb = pk.nbins
         p = self.rho.dropout if self.training else 0.0
         T = ops.mlp(ops.rho_table_inputs(nb, dev, raw=True).reshape(-1, 1), *self.rho.kernel_args(), dropout_p=p,

@@ -1,0 +1,104 @@
+// Glue kernels of the compressed-feature ("entries") path: entry values <-> node rows. Deterministic (fixed summation
+// order, no atomics). See gnan_b200.h (gnan_mlp_entries_*) and gnan_b200/sparse.py.
+//
+// Layout: group g owns entries [grp_ptr[g], grp_ptr[g+1]); its FIRST entry is the feature's baseline value (shared by
+// every row that is not listed), the others are exceptions (row, value). S[r,:] = sum_g f_g(x[r,g]) becomes
+//   S[r,:] = sum_g Y[base_g,:] + sum_{e in exceptions of row r} (Y[e,:] - Y[base_{g(e)},:]).
+#include "common.cuh"
+
+namespace {
+
+// out[c] = sum_i src[idx(i), c] for i < n, fixed-order tree; one block per channel
+template <bool BASELINES>
+__global__ void colsum_kernel(const float *__restrict__ src, const int64_t *__restrict__ grp_ptr, int64_t n, int C,
+                              float *__restrict__ out)
+{
+    __shared__ float red[512];
+    const int c = blockIdx.x;
+    float s = 0.f;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += src[(BASELINES ? grp_ptr[i] : i) * C + c];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = blockDim.x / 2; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[c] = red[0];
+}
+
+__global__ void entries_to_rows_kernel(const float *__restrict__ Y, int64_t N, int C, const int64_t *__restrict__ grp_ptr,
+                                       const int64_t *__restrict__ csr_ptr, const int64_t *__restrict__ csr_eid,
+                                       const int32_t *__restrict__ ent_grp, const float *__restrict__ S0, float *__restrict__ S)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= N * C) return;
+    const int64_t r = t / C;
+    const int c = (int)(t % C);
+    float s = S0[c];
+    for (int64_t i = csr_ptr[r]; i < csr_ptr[r + 1]; ++i) {
+        const int64_t e = csr_eid[i];
+        s += Y[e * C + c] - Y[grp_ptr[ent_grp[e]] * C + c];
+    }
+    S[t] = s;
+}
+
+// dY of the exceptions: a gather of the owning row's dS
+__global__ void rows_to_exceptions_kernel(const float *__restrict__ dS, int64_t E, int C, const int64_t *__restrict__ ent_row,
+                                          float *__restrict__ dY)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= E * C) return;
+    const int64_t e = t / C;
+    const int64_t r = ent_row[e];
+    if (r >= 0) dY[t] = dS[r * C + (t % C)];
+}
+
+// dY of the baseline of group g = (sum of dS over all rows) - (sum over the rows listed as exceptions of g); one warp per (g, c)
+__global__ void rows_to_baselines_kernel(const float *__restrict__ dS, int G, int C, const int64_t *__restrict__ grp_ptr,
+                                         const int64_t *__restrict__ ent_row, const float *__restrict__ dStot,
+                                         float *__restrict__ dY)
+{
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= (int64_t)G * C) return;
+    const int g = (int)(w / C), c = (int)(w % C);
+    const int64_t e0 = grp_ptr[g], e1 = grp_ptr[g + 1];
+    float s = 0.f;
+    for (int64_t e = e0 + 1 + lane; e < e1; e += 32) s += dS[ent_row[e] * C + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) dY[e0 * C + c] = dStot[c] - s;
+}
+
+}  // namespace
+
+extern "C" int gnan_entries_to_rows(const float *Y, int64_t N, int32_t G, int32_t C, const int64_t *grp_ptr,
+                                    const int64_t *csr_ptr, const int64_t *csr_eid, const int32_t *ent_grp, float *S0,
+                                    float *S, gnan_stream_t stream)
+{
+    GNAN_REQUIRE(N >= 0 && G >= 1 && C >= 1, "entries_to_rows: bad sizes");
+    GNAN_REQUIRE(Y && grp_ptr && csr_ptr && ent_grp && S0 && (N == 0 || S), "entries_to_rows: NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    colsum_kernel<true><<<C, 512, 0, st>>>(Y, grp_ptr, G, C, S0);
+    GNAN_LAUNCH_OK();
+    if (N > 0) {
+        entries_to_rows_kernel<<<(unsigned)ceil_div64(N * C, 256), 256, 0, st>>>(Y, N, C, grp_ptr, csr_ptr, csr_eid, ent_grp, S0, S);
+        GNAN_LAUNCH_OK();
+    }
+    return GNAN_OK;
+}
+
+extern "C" int gnan_rows_to_entries(const float *dS, int64_t N, int32_t G, int32_t C, const int64_t *grp_ptr, int64_t E,
+                                    const int64_t *ent_row, float *dStot, float *dY, gnan_stream_t stream)
+{
+    GNAN_REQUIRE(N >= 0 && G >= 1 && C >= 1 && E >= G, "rows_to_entries: bad sizes");
+    GNAN_REQUIRE(grp_ptr && ent_row && dStot && dY && (N == 0 || dS), "rows_to_entries: NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    colsum_kernel<false><<<C, 512, 0, st>>>(dS, nullptr, N, C, dStot);
+    GNAN_LAUNCH_OK();
+    rows_to_exceptions_kernel<<<(unsigned)ceil_div64(E * C, 256), 256, 0, st>>>(dS, E, C, ent_row, dY);
+    GNAN_LAUNCH_OK();
+    rows_to_baselines_kernel<<<(unsigned)ceil_div64((int64_t)G * C * 32, 256), 256, 0, st>>>(dS, G, C, grp_ptr, ent_row, dStot, dY);
+    GNAN_LAUNCH_OK();
+    return GNAN_OK;
+}

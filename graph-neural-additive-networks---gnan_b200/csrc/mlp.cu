@@ -26,6 +26,10 @@ struct MlpKArgs {
     float drop_scale;
     uint64_t seed;
     float *du;  // backward only: [R,G] gradient w.r.t. the inputs, or NULL
+    // entries mode (gnan_mlp_entries_*): u is a flat value list grouped by feature, group g owns entries
+    // [grp_ptr[g], grp_ptr[g+1]); rows of a group are its entries, outputs / dY are indexed by entry. NULL = dense mode.
+    const int64_t *grp_ptr;
+    const int32_t *items;  // forward, entries mode: [n_items][2] = (group, 128-entry tile of that group), one CTA each
 };
 
 __device__ __forceinline__ float relu(float v) { return v > 0.f ? v : 0.f; }
@@ -176,14 +180,21 @@ mlp_fwd_kernel(MlpKArgs a, int KC, float *__restrict__ Spart)
     float *sBo = sBh + H;               // [CP]
 
     const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
-    const int64_t row0 = (int64_t)blockIdx.x * TM;
-    const int g0 = blockIdx.y * KC;
-    const int ng = min(KC, a.G - g0);
+    int64_t row0 = (int64_t)blockIdx.x * TM, nrow = a.R, ebase = 0;
+    int g0 = blockIdx.y * KC;
+    int ng = min(KC, a.G - g0);
+    if (a.items) {                       // entries mode: this CTA = one (group, tile) item; its rows are the group's entries
+        g0 = a.items[2 * blockIdx.x];
+        row0 = (int64_t)a.items[2 * blockIdx.x + 1] * TM;
+        ng = 1;
+        ebase = a.grp_ptr[g0];
+        nrow = a.grp_ptr[g0 + 1] - ebase;
+    }
 
     for (int i = tid; i < ng * TM; i += NT) {
         const int r = i / ng, kk = i % ng;
         const int64_t row = row0 + r;
-        sX[kk * TM + r] = row < a.R ? __ldg(a.u + row * a.ldu + g0 + kk) : 0.f;
+        sX[kk * TM + r] = row < nrow ? __ldg(a.items ? a.u + ebase + row : a.u + row * a.ldu + g0 + kk) : 0.f;
     }
     for (int i = tid; i < TM * CP; i += NT) sS[i] = 0.f;
     for (int i = tid; i < CP * LD; i += NT) sWo[i] = 0.f;
@@ -245,10 +256,10 @@ mlp_fwd_kernel(MlpKArgs a, int KC, float *__restrict__ Spart)
         }
         __syncthreads();  // sAct / sWo / small vectors are rewritten by the next group
     }
-    float *out = Spart + (size_t)blockIdx.y * a.R * a.C;
+    float *out = a.items ? Spart + ebase * a.C : Spart + (size_t)blockIdx.y * a.R * a.C;
     for (int i = tid; i < TM * a.C; i += NT) {
         const int r = i / a.C, c = i % a.C;
-        if (row0 + r < a.R) out[(row0 + r) * a.C + c] = sS[r * CP + c];
+        if (row0 + r < nrow) out[(row0 + r) * a.C + c] = sS[r * CP + c];
     }
 }
 
@@ -311,16 +322,23 @@ mlp_bwd_kernel(MlpKArgs a, const float *__restrict__ dS, MlpGradPtrs gp, int64_t
     float pw1 = 0.f, pb1 = 0.f;  // dw1[tid], db1[tid]
     float pbo = 0.f;             // dbo[tid]  (tid < C)
 
+    int64_t nrow = a.R, ebase = 0;
+    if (a.grp_ptr) {                     // entries mode: the rows of group g are its entries
+        ebase = a.grp_ptr[g];
+        nrow = a.grp_ptr[g + 1] - ebase;
+        ntiles = (nrow + TM - 1) / TM;
+        dS += ebase * a.C;
+    }
     for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int64_t row0 = t * TM;
         __syncthreads();  // previous tile fully consumed
         {
             const int64_t row = row0 + tid;
-            sX[tid] = row < a.R ? __ldg(a.u + row * a.ldu + g) : 0.f;
+            sX[tid] = row < nrow ? __ldg(a.grp_ptr ? a.u + ebase + row : a.u + row * a.ldu + g) : 0.f;
         }
         for (int i = tid; i < TM * CP; i += NT) {
             const int r = i / CP, c = i % CP;
-            sG[r * CG + c] = (row0 + r < a.R && c < a.C) ? __ldg(dS + (row0 + r) * a.C + c) : 0.f;
+            sG[r * CG + c] = (row0 + r < nrow && c < a.C) ? __ldg(dS + (row0 + r) * a.C + c) : 0.f;
         }
         __syncthreads();
         gen_layer1<H>(sAct, sW1, sB1, sX[tid], tid, a, g, row0 + tid);
@@ -636,6 +654,8 @@ MlpKArgs make_args(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params
     a.drop_scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
     a.seed = seed;
     a.du = nullptr;
+    a.grp_ptr = nullptr;
+    a.items = nullptr;
     return a;
 }
 
@@ -809,6 +829,107 @@ extern "C" int gnan_mlp_bwd(const float *u, int64_t R, int64_t ldu, const gnan_m
         for (const Seg &s : segs) {
             if (!s.dst || s.n == 0) continue;
             rc = gnan_reduce_chunks(s.src, pl.nchunk, s.n, ntot, s.dst, st);
+            if (rc) return rc;
+        }
+    }
+    return GNAN_OK;
+}
+
+
+// ---- entries mode: shape functions on a compressed feature matrix ---------------------------------------------------
+// A feature column that repeats one value (zeros of a bag-of-words matrix, the off entries of a one-hot encoding, the
+// constant column) needs ONE evaluation for that value when dropout is off; only the other entries need their own. The
+// caller lists the distinct work as `val[E]` grouped by feature (`grp_ptr[G+1]`) and gets Y[e,:] = f_g(val[e]) back.
+namespace {
+int check_entries(const gnan_mlp_params *p, const float *val, const int64_t *grp_ptr, int64_t E, const char *who)
+{
+    int rc = check_params(p, E, p ? p->G : 1);
+    if (rc) return rc;
+    GNAN_REQUIRE(p->n_layers >= 2, "%s: n_layers == 1 has no entries mode (a Linear(1,C) is cheaper evaluated densely)", who);
+    GNAN_REQUIRE(E >= 0 && (E == 0 || val != nullptr) && grp_ptr != nullptr, "%s: NULL val or grp_ptr", who);
+    return GNAN_OK;
+}
+}  // namespace
+
+extern "C" size_t gnan_mlp_entries_workspace_bytes(int64_t max_group_entries, const gnan_mlp_params *p, int backward)
+{
+    if (!p || p->n_layers < 2 || max_group_entries <= 0 || !backward) return 0;
+    const BwdPlan pl = plan_bwd(max_group_entries, p);
+    return pl.nchunk > 1 ? sizeof(float) * (size_t)pl.nchunk * grad_floats(p) : 0;
+}
+
+extern "C" int gnan_mlp_entries_fwd(const float *val, const int64_t *grp_ptr, int64_t E, const int32_t *items, int64_t n_items,
+                                    const gnan_mlp_params *p, float *Y, gnan_stream_t stream)
+{
+    int rc = check_entries(p, val, grp_ptr, E, "mlp_entries_fwd");
+    if (rc) return rc;
+    GNAN_REQUIRE(n_items >= 0 && (n_items == 0 || (items != nullptr && Y != nullptr)), "mlp_entries_fwd: NULL items or Y");
+    if (n_items == 0) return GNAN_OK;
+    MlpKArgs a = make_args(val, E, 1, p, 0.f, 0);
+    a.grp_ptr = grp_ptr;
+    a.items = items;
+    FwdPlan pl;
+    pl.KC = 1; pl.nchunk = 1; pl.ntile = n_items;
+    const int H = p->H, LD = H + 4, CP = (p->C + 7) / 8 * 8;
+    pl.smem = sizeof(float) * ((size_t)TM * LD + (size_t)H * LD + (size_t)CP * LD + (size_t)TM * CP + (size_t)TM + 3 * H + CP);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (p->H) {
+        case 8: return launch_fwd<8>(a, pl, Y, st);
+        case 16: return launch_fwd<16>(a, pl, Y, st);
+        case 32: return launch_fwd<32>(a, pl, Y, st);
+        case 64: return launch_fwd<64>(a, pl, Y, st);
+    }
+    return GNAN_ERR_UNSUPPORTED;
+}
+
+extern "C" int gnan_mlp_entries_bwd(const float *val, const int64_t *grp_ptr, int64_t E, int64_t max_group_entries,
+                                    const gnan_mlp_params *p, const float *dY, const gnan_mlp_grads *grads, void *workspace,
+                                    size_t workspace_bytes, gnan_stream_t stream)
+{
+    int rc = check_entries(p, val, grp_ptr, E, "mlp_entries_bwd");
+    if (rc) return rc;
+    GNAN_REQUIRE(grads != nullptr && (E == 0 || dY != nullptr), "mlp_entries_bwd: NULL dY or grads");
+    GNAN_REQUIRE(grads->du == nullptr, "mlp_entries_bwd: input gradients are not available in entries mode");
+    GNAN_REQUIRE(max_group_entries >= 0 && max_group_entries <= E, "mlp_entries_bwd: bad max_group_entries");
+    cudaStream_t st = (cudaStream_t)stream;
+    MlpKArgs a = make_args(val, E, 1, p, 0.f, 0);
+    a.grp_ptr = grp_ptr;
+    const size_t G = p->G, H = p->H, C = p->C, nh = p->n_layers - 2;
+    const BwdPlan pl = plan_bwd(std::max<int64_t>(max_group_entries, 1), p);   // groups without entries write zero gradients
+    MlpGradPtrs gp;
+    const size_t ntot = grad_floats(p);
+    if (pl.nchunk > 1) {
+        const size_t need = sizeof(float) * (size_t)pl.nchunk * ntot;
+        if (workspace == nullptr || workspace_bytes < need) {
+            gnan_set_error("mlp_entries_bwd: workspace %zu < %zu bytes", workspace_bytes, need);
+            return GNAN_ERR_WORKSPACE;
+        }
+        float *w = (float *)workspace;
+        gp.w1 = w; w += pad4(G * H);
+        gp.b1 = w; w += pad4(G * H);
+        gp.wh = w; w += pad4(nh * G * H * H);
+        gp.bh = w; w += pad4(nh * G * H);
+        gp.wo = w; w += pad4(G * C * H);
+        gp.bo = w;
+        gp.chunk_stride = ntot;
+    } else {
+        gp.w1 = grads->w1; gp.b1 = grads->b1; gp.wh = grads->wh; gp.bh = grads->bh; gp.wo = grads->wo; gp.bo = grads->bo;
+        gp.chunk_stride = 0;
+    }
+    switch (p->H) {
+        case 8: rc = launch_bwd_h<8>(a, pl, dY, gp, st); break;
+        case 16: rc = launch_bwd_h<16>(a, pl, dY, gp, st); break;
+        case 32: rc = launch_bwd_h<32>(a, pl, dY, gp, st); break;
+        case 64: rc = launch_bwd_h<64>(a, pl, dY, gp, st); break;
+    }
+    if (rc) return rc;
+    if (pl.nchunk > 1) {
+        struct Seg { const float *src; float *dst; size_t n; };
+        const Seg segs[6] = {{gp.w1, grads->w1, G * H}, {gp.b1, grads->b1, G * H}, {gp.wh, grads->wh, nh * G * H * H},
+                             {gp.bh, grads->bh, nh * G * H}, {gp.wo, grads->wo, G * C * H}, {gp.bo, grads->bo, G * C}};
+        for (const Seg &sg : segs) {
+            if (!sg.dst || sg.n == 0) continue;
+            rc = gnan_reduce_chunks(sg.src, pl.nchunk, sg.n, ntot, sg.dst, st);
             if (rc) return rc;
         }
     }

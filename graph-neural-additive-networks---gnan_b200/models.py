@@ -72,9 +72,14 @@ class TensorGNAN(_Base):
     def forward(self, inputs):
         if isinstance(inputs, PackedBatch):
             return self.forward_packed(inputs)
-        x, hd = resolve(inputs, self._device())
-        S = self._per_feature(x) if self._readout else self._feature_sums(x)
-        T = self._table(ops.rho_table_inputs(hd.nbins, x.device))                    # [nbins,Cr]
+        dev = self._device()
+        if self._readout:
+            x, hd = resolve(inputs, dev)
+            S = self._per_feature(x)
+        else:
+            _, hd = resolve(inputs, dev, need_x=False)
+            S = self._feature_sums(*self._features(inputs))
+        T = self._table(ops.rho_table_inputs(hd.nbins, dev))                         # [nbins,Cr]
         rs = ops.level_rscale(hd.level_counts) if self.normalize_rho else None       # models.py:368-370
         out = ops.aggregate_rows(hd.hop, T, S, rscale=rs)
         if self._readout:
@@ -88,10 +93,9 @@ class TensorGNAN(_Base):
     def forward_packed(self, pk):
         """Many graphs in one call (extension; see gnan_b200.GNAN.TensorGNAN.forward_packed): [B,C] for graph tasks."""
         dev = self._device()
-        if pk.x.device != dev:
+        if pk.hop.device != dev:
             pk = pk.to(dev)
-        x = pk.x.float().contiguous()
-        S = self._per_feature(x) if self._readout else self._feature_sums(x)
+        S = self._per_feature(pk.x.float().contiguous()) if self._readout else self._feature_sums(*self._features(pk))
         T = self._table(ops.rho_table_inputs(pk.nbins, dev))
         rs = ops.level_rscale(pk.level_counts) if self.normalize_rho else None
         out = ops.aggregate_blockdiag(pk.hop, pk.hop_off, pk.node_off, T, S, rscale=rs, reduce_graph=self.is_graph_task)

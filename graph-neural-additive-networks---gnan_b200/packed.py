@@ -111,8 +111,10 @@ class PackedDataset:
                              self.max_nodes)
 
     def as_batch(self) -> PackedBatch:
-        """The whole dataset as one batch (no copy)."""
-        return PackedBatch(self.x, self.hop, self.hop_off, self.node_off, self.level_counts, self.y, self.max_nodes)
+        """The whole dataset as one batch (no copy; the same object every time, so per-input caches stick to it)."""
+        if getattr(self, "_whole", None) is None:
+            self._whole = PackedBatch(self.x, self.hop, self.hop_off, self.node_off, self.level_counts, self.y, self.max_nodes)
+        return self._whole
 
     def batch(self, ids) -> PackedBatch:
         """Mini-batch of the graphs `ids` (any order, repeats allowed): a device gather of their blocks."""
@@ -127,8 +129,10 @@ class PackedDataset:
         cells = _ranges(self.hop_off[:-1][ids], n * n)
         hop = self.hop[cells] if cells.numel() else torch.zeros(1, dtype=torch.uint8, device=dev)
         y = None if self.y is None else self.y[ids]
-        return PackedBatch(self.x[rows], hop, hop_off, node_off.to(torch.int32), self.level_counts[rows], y,
-                           int(n.max().item()) if ids.numel() else 1)
+        pk = PackedBatch(self.x[rows], hop, hop_off, node_off.to(torch.int32), self.level_counts[rows], y,
+                         int(n.max().item()) if ids.numel() else 1)
+        pk._gnan_b200_no_dedup = True                # a fresh object per mini-batch: no feature compression (see _inputs.compressed_of)
+        return pk
 
     def loader(self, batch_size: int, shuffle: bool = False, generator: Optional[torch.Generator] = None,
                drop_last: bool = False) -> Iterator[PackedBatch]:
@@ -136,6 +140,9 @@ class PackedDataset:
         distance_collate_fn)` does at batched_pyg_main.py:193, minus the host collate)."""
         B = len(self)
         order = torch.randperm(B, generator=generator) if shuffle else torch.arange(B)
+        if batch_size >= B and not shuffle:
+            yield self.as_batch()
+            return
         for s in range(0, B, batch_size):
             ids = order[s:s + batch_size]
             if drop_last and ids.numel() < batch_size:

@@ -1,0 +1,233 @@
+"""Compressed feature matrix: evaluate every shape function once per DISTINCT work item instead of once per (node, feature).
+
+When dropout is off, all rows that carry the same value in feature column k see the same f_k output and (by linearity of
+the backward in dS) can share one backward evaluation fed the SUM of their dS rows. The reference's inputs are made for
+this: Cora / PubMed bag-of-words rows are ~99 % / ~90 % zeros (datasets.py:94), Mutagenicity atoms are one-hot, and
+pre_process() appends a constant column (pre_process_datasets.py:108,127). SURVEY.md §8d allows the shortcut as long as
+achieved FLOPs are counted on the evaluations actually executed (bench.py does).
+
+Representation (built once per dataset, cached next to the hop data): per feature k a baseline value base[k] (the
+column's most frequent value) plus the list of exceptions (row, value) that differ from it, in CSC order:
+
+    val      fp32  [E]    entries grouped by feature; group k = [base[k], exceptions of k sorted by row]
+    grp_ptr  int64 [K+1]
+    ent_row  int64 [E]    row of an exception, -1 for a baseline
+    ent_grp  int32 [E]    feature of an entry
+    csr_ptr  int64 [N+1], csr_eid int64 [n_exc]   the exception entries of each row (for the row gather)
+    items    int32 [n_items,2]                    (feature, 128-entry tile) work list of the forward kernel
+
+    S[r,:] = sum_k Y[base_k,:] + sum_{e in exceptions(r)} (Y[e,:] - Y[base_k(e),:]),     Y[e,:] = f_k(e)(val[e])
+
+The C ABI side is gnan_mlp_entries_fwd/bwd + gnan_entries_to_rows / gnan_rows_to_entries (include/gnan_b200.h); all fp32
+kernels, deterministic. With dropout active the modules fall back to the dense kernels (per-row masks break the sharing).
+"""
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import ops
+from ._lib import MlpGrads, check, load, ptr, stream_handle
+
+TILE = 128                  # entries per forward work item (rows per CTA tile of the MLP kernels)
+MAX_DENSITY = 0.25          # build a compressed form only if exceptions / (N*K) is below this
+
+
+class CompressedFeatures:
+    _FIELDS = ("base", "val", "grp_ptr", "ent_row", "ent_grp", "csr_ptr", "csr_eid", "items")
+
+    def __init__(self, num_rows, base, val, grp_ptr, ent_row, ent_grp, csr_ptr, csr_eid, items, max_group):
+        self.num_rows = int(num_rows)
+        self.base, self.val, self.grp_ptr, self.ent_row, self.ent_grp = base, val, grp_ptr, ent_row, ent_grp
+        self.csr_ptr, self.csr_eid, self.items = csr_ptr, csr_eid, items
+        self.max_group = int(max_group)
+
+    @property
+    def num_features(self):
+        return self.base.numel()
+
+    @property
+    def num_entries(self):
+        return self.val.numel()
+
+    @property
+    def device(self):
+        return self.val.device
+
+    def density(self):
+        return (self.num_entries - self.num_features) / max(1, self.num_rows * self.num_features)
+
+    def nbytes(self):
+        return sum(getattr(self, f).numel() * getattr(self, f).element_size() for f in self._FIELDS)
+
+    def to(self, device):
+        return CompressedFeatures(self.num_rows, *[getattr(self, f).to(device, non_blocking=True) for f in self._FIELDS], self.max_group)
+
+    def pin_memory(self):
+        return CompressedFeatures(self.num_rows, *[getattr(self, f).pin_memory() for f in self._FIELDS], self.max_group)
+
+    def to_dense(self):
+        """x [N,K] back (exactly)."""
+        x = self.base.unsqueeze(0).repeat(self.num_rows, 1)
+        exc = self.ent_row >= 0
+        x[self.ent_row[exc], self.ent_grp[exc].long()] = self.val[exc]
+        return x
+
+
+def compress_features(x: Tensor, max_density: Optional[float] = MAX_DENSITY) -> Optional[CompressedFeatures]:
+    """x [N,K] (any device) -> CompressedFeatures on x's device, or None when more than `max_density` of the entries differ
+    from their column's most frequent value (the dense kernels are the better choice then). One-off cost: a column-wise
+    mode and a few sorts; synchronises."""
+    if x.dim() != 2:
+        raise ValueError("x must be [N,K]")
+    x = x.detach().float()
+    N, K = x.shape
+    dev = x.device
+    if N == 0 or K == 0:
+        return None
+    base = torch.mode(x, dim=0).values.contiguous()                           # most frequent value of each column
+    mask = x != base.unsqueeze(0)
+    n_exc = int(mask.sum().item())
+    if max_density is not None and n_exc > max_density * N * K:
+        return None
+    cols, rows = mask.t().nonzero(as_tuple=True)                              # CSC order: by feature, then by row
+    counts = torch.bincount(cols, minlength=K)
+    sizes = counts + 1                                                        # + the baseline entry
+    grp_ptr = torch.zeros(K + 1, dtype=torch.int64, device=dev)
+    grp_ptr[1:] = torch.cumsum(sizes, 0)
+    E = K + n_exc
+    exc_start = torch.cumsum(counts, 0) - counts                              # first exception of each column in the CSC list
+    eid = grp_ptr[:-1][cols] + 1 + (torch.arange(n_exc, device=dev) - exc_start[cols])
+    val = torch.empty(E, dtype=torch.float32, device=dev)
+    val[grp_ptr[:-1]] = base
+    val[eid] = x[rows, cols]
+    ent_row = torch.full((E,), -1, dtype=torch.int64, device=dev)
+    ent_row[eid] = rows
+    ent_grp = torch.repeat_interleave(torch.arange(K, device=dev, dtype=torch.int32), sizes, output_size=E)
+    order = torch.sort(rows, stable=True).indices                             # CSR view of the same exceptions
+    csr_eid = eid[order].contiguous()
+    csr_ptr = torch.zeros(N + 1, dtype=torch.int64, device=dev)
+    csr_ptr[1:] = torch.cumsum(torch.bincount(rows, minlength=N), 0)
+    tiles = (sizes + TILE - 1) // TILE
+    n_items = int(tiles.sum().item())
+    item_grp = torch.repeat_interleave(torch.arange(K, device=dev), tiles, output_size=n_items)
+    item_tile = torch.arange(n_items, device=dev) - (torch.cumsum(tiles, 0) - tiles)[item_grp]
+    items = torch.stack([item_grp, item_tile], dim=1).to(torch.int32).contiguous()
+    return CompressedFeatures(N, base, val, grp_ptr, ent_row, ent_grp, csr_ptr, csr_eid, items, int(sizes.max().item()))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# ops
+# ---------------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("gnan_b200::mlp_entries_fwd", mutates_args=())
+def mlp_entries_fwd(val: Tensor, grp_ptr: Tensor, items: Tensor, w1: Tensor, b1: Tensor, wh: Tensor, bh: Tensor, wo: Tensor,
+                    bo: Tensor, n_layers: int, max_group: int) -> Tensor:
+    lib = load()
+    val, w1, b1, wh, bh, wo, bo = (ops._f32(t, n) for t, n in zip((val, w1, b1, wh, bh, wo, bo), "val w1 b1 wh bh wo bo".split()))
+    if grp_ptr.dtype != torch.int64 or items.dtype != torch.int32 or grp_ptr.numel() != wo.shape[0] + 1:
+        raise TypeError("grp_ptr must be int64 [G+1], items int32 [n,2]")
+    p, G, H, C = ops._mlp_params(w1, b1, wh, bh, wo, bo, n_layers)
+    E = val.numel()
+    Y = torch.empty(E, C, dtype=torch.float32, device=val.device)
+    with ops._timed("mlp_entries_fwd"):
+        check(lib.gnan_mlp_entries_fwd(ptr(val), ptr(grp_ptr), E, ptr(items.contiguous()), items.shape[0], p, ptr(Y), stream_handle()),
+              "gnan_mlp_entries_fwd")
+    return Y
+
+
+@mlp_entries_fwd.register_fake
+def _(val, grp_ptr, items, w1, b1, wh, bh, wo, bo, n_layers, max_group):
+    return val.new_empty(val.numel(), wo.shape[1])
+
+
+@torch.library.custom_op("gnan_b200::mlp_entries_bwd", mutates_args=())
+def mlp_entries_bwd(val: Tensor, grp_ptr: Tensor, w1: Tensor, b1: Tensor, wh: Tensor, bh: Tensor, wo: Tensor, bo: Tensor,
+                    n_layers: int, max_group: int, dY: Tensor) -> tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    lib = load()
+    val, w1, b1, wh, bh, wo, bo, dY = (ops._f32(t, n) for t, n in zip((val, w1, b1, wh, bh, wo, bo, dY), "val w1 b1 wh bh wo bo dY".split()))
+    p, G, H, C = ops._mlp_params(w1, b1, wh, bh, wo, bo, n_layers)
+    outs = [torch.empty_like(t) for t in (w1, b1, wh, bh, wo, bo)]
+    g = MlpGrads(*[ptr(t) for t in outs], None)
+    ws = ops._ws(lib.gnan_mlp_entries_workspace_bytes(max_group, p, 1), val.device)
+    with ops._timed("mlp_entries_bwd"):
+        check(lib.gnan_mlp_entries_bwd(ptr(val), ptr(grp_ptr), val.numel(), max_group, p, ptr(dY), g, ptr(ws), ws.numel(),
+                                       stream_handle()), "gnan_mlp_entries_bwd")
+    return tuple(outs)
+
+
+@mlp_entries_bwd.register_fake
+def _(val, grp_ptr, w1, b1, wh, bh, wo, bo, n_layers, max_group, dY):
+    return tuple(torch.empty_like(t) for t in (w1, b1, wh, bh, wo, bo))
+
+
+def _entries_setup(ctx, inputs, output):
+    val, grp_ptr, items, w1, b1, wh, bh, wo, bo, n_layers, max_group = inputs
+    ctx.save_for_backward(val, grp_ptr, w1, b1, wh, bh, wo, bo)
+    ctx.cfg = (n_layers, max_group)
+
+
+def _entries_backward(ctx, dY):
+    val, grp_ptr, w1, b1, wh, bh, wo, bo = ctx.saved_tensors
+    g = mlp_entries_bwd(val, grp_ptr, w1, b1, wh, bh, wo, bo, ctx.cfg[0], ctx.cfg[1], dY.contiguous())
+    return (None, None, None) + tuple(g) + (None, None)
+
+
+mlp_entries_fwd.register_autograd(_entries_backward, setup_context=_entries_setup)
+
+
+@torch.library.custom_op("gnan_b200::entries_to_rows", mutates_args=())
+def entries_to_rows(Y: Tensor, grp_ptr: Tensor, csr_ptr: Tensor, csr_eid: Tensor, ent_grp: Tensor, ent_row: Tensor) -> Tensor:
+    lib = load()
+    Y = ops._f32(Y, "Y")
+    N, G, C = csr_ptr.numel() - 1, grp_ptr.numel() - 1, Y.shape[1]
+    S = torch.empty(N, C, dtype=torch.float32, device=Y.device)
+    S0 = torch.empty(C, dtype=torch.float32, device=Y.device)
+    with ops._timed("entries_to_rows"):
+        check(lib.gnan_entries_to_rows(ptr(Y), N, G, C, ptr(grp_ptr), ptr(csr_ptr), ptr(csr_eid), ptr(ent_grp), ptr(S0), ptr(S),
+                                       stream_handle()), "gnan_entries_to_rows")
+    return S
+
+
+@entries_to_rows.register_fake
+def _(Y, grp_ptr, csr_ptr, csr_eid, ent_grp, ent_row):
+    return Y.new_empty(csr_ptr.numel() - 1, Y.shape[1])
+
+
+@torch.library.custom_op("gnan_b200::rows_to_entries", mutates_args=())
+def rows_to_entries(dS: Tensor, grp_ptr: Tensor, ent_row: Tensor) -> Tensor:
+    lib = load()
+    dS = ops._f32(dS, "dS")
+    N, C = dS.shape
+    G, E = grp_ptr.numel() - 1, ent_row.numel()
+    dY = torch.empty(E, C, dtype=torch.float32, device=dS.device)
+    tot = torch.empty(C, dtype=torch.float32, device=dS.device)
+    with ops._timed("rows_to_entries"):
+        check(lib.gnan_rows_to_entries(ptr(dS), N, G, C, ptr(grp_ptr), E, ptr(ent_row), ptr(tot), ptr(dY), stream_handle()),
+              "gnan_rows_to_entries")
+    return dY
+
+
+@rows_to_entries.register_fake
+def _(dS, grp_ptr, ent_row):
+    return dS.new_empty(ent_row.numel(), dS.shape[1])
+
+
+def _e2r_setup(ctx, inputs, output):
+    Y, grp_ptr, csr_ptr, csr_eid, ent_grp, ent_row = inputs
+    ctx.save_for_backward(grp_ptr, ent_row)
+
+
+def _e2r_backward(ctx, dS):
+    grp_ptr, ent_row = ctx.saved_tensors
+    return rows_to_entries(dS.contiguous(), grp_ptr, ent_row), None, None, None, None, None
+
+
+entries_to_rows.register_autograd(_e2r_backward, setup_context=_e2r_setup)
+
+
+def feature_sums(cx: CompressedFeatures, w1, b1, wh, bh, wo, bo, n_layers) -> Tensor:
+    """S [N,C] = sum_k f_k(x[:,k]) from the compressed form; differentiable w.r.t. the weights."""
+    if wo.shape[0] != cx.num_features:
+        raise ValueError(f"compressed x has {cx.num_features} features, the model {wo.shape[0]}")
+    Y = mlp_entries_fwd(cx.val, cx.grp_ptr, cx.items, w1, b1, wh, bh, wo, bo, int(n_layers), cx.max_group)
+    return entries_to_rows(Y, cx.grp_ptr, cx.csr_ptr, cx.csr_eid, cx.ent_grp, cx.ent_row)

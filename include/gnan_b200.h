@@ -90,6 +90,30 @@ int gnan_mlp_bwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *
                  int precision, const float *dS /* [R,C] */, const gnan_mlp_grads *grads, void *workspace,
                  size_t workspace_bytes, gnan_stream_t stream);
 
+/* Entries mode: the shape functions on a COMPRESSED feature matrix (same reference lines as gnan_mlp_fwd/bwd). When
+ * dropout is off, rows that carry the same value in a feature column share one evaluation of that feature's MLP (the zeros
+ * of a bag-of-words matrix, the off entries of a one-hot encoding, the constant column: datasets.py:94).
+ * The caller lists the distinct work as val[E] grouped by feature, group g owning entries [grp_ptr[g], grp_ptr[g+1]);
+ * Y[e,:] = f_g(val[e]) and the weight gradients given dY[E,C] come back; how entries map to rows of S is the caller's
+ * business (gnan_b200/sparse.py). items [n_items,2] = (group, 128-entry tile index inside the group): one CTA per item.
+ * fp32 kernels; n_layers >= 2; no dropout (the sharing would be wrong with per-row masks). */
+size_t gnan_mlp_entries_workspace_bytes(int64_t max_group_entries, const gnan_mlp_params *p, int backward);
+int gnan_mlp_entries_fwd(const float *val, const int64_t *grp_ptr /* [G+1] */, int64_t E, const int32_t *items, int64_t n_items,
+                         const gnan_mlp_params *p, float *Y /* [E,C] */, gnan_stream_t stream);
+int gnan_mlp_entries_bwd(const float *val, const int64_t *grp_ptr, int64_t E, int64_t max_group_entries,
+                         const gnan_mlp_params *p, const float *dY /* [E,C] */, const gnan_mlp_grads *grads, void *workspace,
+                         size_t workspace_bytes, gnan_stream_t stream);
+
+/* Entry values <-> node rows (deterministic, no atomics). Group g's FIRST entry is the feature's baseline value, shared by
+ * every row not listed among its exceptions:  S[r,:] = sum_g Y[base_g,:] + sum_{e in exceptions of row r} (Y[e,:] - Y[base_g(e),:]).
+ * csr_ptr/csr_eid list the exception entries of each row, ent_grp[e] / ent_row[e] are an entry's group and row (-1 for a
+ * baseline). S0 / dStot are [C] scratch outputs (sum of the baselines / of all dS rows). */
+int gnan_entries_to_rows(const float *Y /* [E,C] */, int64_t N, int32_t G, int32_t C, const int64_t *grp_ptr,
+                         const int64_t *csr_ptr /* [N+1] */, const int64_t *csr_eid, const int32_t *ent_grp /* [E] */,
+                         float *S0 /* [C] */, float *S /* [N,C] */, gnan_stream_t stream);
+int gnan_rows_to_entries(const float *dS /* [N,C] */, int64_t N, int32_t G, int32_t C, const int64_t *grp_ptr, int64_t E,
+                         const int64_t *ent_row /* [E] */, float *dStot /* [C] */, float *dY /* [E,C] */, gnan_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Distance-table inputs. u[i,d] = 1/(1+d) for d < nbins-1, 0 for the unreachable bin (nbins-1);
  * with cnt != NULL divided by cnt[i,d] (GNAN.py:65-66: node_distances / normalization_matrix).

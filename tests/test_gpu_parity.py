@@ -776,3 +776,97 @@ def test_mlp_per_group_chunked_with_gradients():
     assert G.rel_err(got.detach().cpu().numpy(), want.detach().numpy()) < TOL
     for k in p:
         assert G.rel_err(d[k].grad.cpu().numpy(), q[k].grad.numpy()) < TOL, k
+
+
+# ---- compressed features: shared shape-function evaluations (SURVEY §8d value dedup) --------------------------------------
+def _compressible_x(rng, N, K, kind):
+    x = np.zeros((N, K), np.float32)
+    if kind == "bow":                                            # Cora-like: ~1.3 % non-zeros, rows normalised, constant column
+        m = rng.random((N, K - 1)) < 0.013
+        x[:, :-1] = m / np.maximum(m.sum(1, keepdims=True), 1)
+        x[:, -1] = 1.0
+    elif kind == "onehot":                                       # Mutagenicity-like
+        x[np.arange(N), rng.integers(0, K - 1, N)] = 1.0
+        x[:, -1] = 1.0
+    else:                                                        # mixed: a dense-ish column, a two-valued one, an empty one
+        x[:, 0] = np.where(rng.random(N) < 0.2, rng.normal(size=N), 0.0)
+        x[:, 1] = np.where(rng.random(N) < 0.5, 2.0, -1.0)
+        x[rng.integers(0, N, 5), 3] = 7.0
+    return torch.tensor(x)
+
+
+@pytest.mark.parametrize("kind,N,K,H,C,L", [("bow", 700, 300, 64, 7, 3), ("onehot", 5000, 15, 64, 1, 3), ("mixed", 333, 5, 16, 3, 4),
+                                            ("onehot", 129, 6, 32, 2, 2)])
+def test_compressed_feature_sums_equal_dense_kernels(kind, N, K, H, C, L):
+    """sparse.feature_sums (one evaluation per distinct (feature, value) pair + row gather) against the dense fp32 kernels
+    and the float64 oracle on the same x: outputs and every weight gradient."""
+    from gnan_b200 import ops, sparse
+    rng = np.random.default_rng(N + K)
+    x = _compressible_x(rng, N, K, kind)
+    gen = torch.Generator().manual_seed(K)
+    nh = L - 2
+    p = dict(w1=torch.randn(K, H, generator=gen), b1=torch.randn(K, H, generator=gen) * 0.5,
+             wh=torch.randn(nh, K, H, H, generator=gen) / H ** 0.5, bh=torch.randn(nh, K, H, generator=gen) * 0.1,
+             wo=torch.randn(K, C, H, generator=gen) / H ** 0.5, bo=torch.randn(K, C, generator=gen))
+    w = torch.randn(N, C, generator=gen)
+    cx = sparse.compress_features(x.to(DEV))
+    assert cx is not None and torch.equal(cx.to_dense().cpu(), x)
+    res = {}
+    for mode in ("dense", "sparse"):
+        d = {k: v.to(DEV).requires_grad_(True) for k, v in p.items()}
+        args = (d["w1"], d["b1"], d["wh"], d["bh"], d["wo"], d["bo"], L)
+        S = ops.mlp(x.to(DEV), *args) if mode == "dense" else sparse.feature_sums(cx, *args)
+        (S * w.to(DEV)).sum().backward()
+        res[mode] = (S.detach().cpu().numpy(), {k: v.grad.cpu().numpy() for k, v in d.items()})
+    q = {k: v.double().requires_grad_(True) for k, v in p.items()}
+    want = gnan_port.shape_functions(q, x.double()).sum(dim=1)
+    (want * w.double()).sum().backward()
+    for mode in ("dense", "sparse"):
+        assert G.rel_err(res[mode][0], want.detach().numpy()) < TOL, mode
+        for k in p:
+            if p[k].numel():
+                assert G.rel_err(res[mode][1][k], q[k].grad.numpy()) < TOL, (mode, k)
+
+
+@pytest.mark.parametrize("name", ["gnanpy_tensor_graph", "models_tensor_graph", "gnanpy_tensor_graph_nonorm_disconnected"])
+def test_modules_dedup_on_and_off_match_reference_golden(name):
+    """One-hot golden cases run through the compressed path by default; both settings must reproduce the reference."""
+    z = G.load(name)
+    outs = {}
+    for dedup in (True, False):
+        m = build_module(z, DEV).eval()
+        m.dedup = dedup
+        data = SimpleNamespace(x=torch.tensor(z["x"]), edge_index=torch.tensor(z["edge_index"]),
+                               node_distances=torch.tensor(z["node_distances"]),
+                               normalization_matrix=torch.tensor(z["normalization_matrix"]))
+        out = m.forward(data)
+        (out * torch.tensor(z["out_weight"], device=DEV)).sum().backward()
+        assert (getattr(data, "_gnan_b200_cx_cache", None) is not None) == dedup
+        assert G.rel_err(out.detach().cpu().numpy(), z["out"]) < TOL
+        check_grads(z, grads_of(m.fs), z["grad_fs"], "fs")
+        check_grads(z, grads_of(m.rho), z["grad_rho"], "rho")
+        outs[dedup] = out.detach()
+    assert G.rel_err(outs[True].cpu().numpy(), outs[False].cpu().numpy()) < 1e-6
+
+
+def test_dropout_training_uses_the_dense_kernels():
+    """Per-row dropout masks make rows with equal inputs differ: with dropout active the compressed path must not be used."""
+    from gnan_b200.GNAN import TensorGNAN
+    from gnan_b200.preprocess import apsp
+    rng = np.random.default_rng(2)
+    n, K = 200, 12
+    x = _compressible_x(rng, n, K, "onehot")
+    data = SimpleNamespace(x=x, hop_data=apsp(torch.tensor(random_graph(rng, n, 2.5)), n, device=DEV))
+    torch.manual_seed(0)
+    m = TensorGNAN(K, 3, 3, 64, dropout=0.5).to(DEV)
+    m.fs.xavier_normal_(1.0); m.rho.xavier_normal_(1.0)
+    m.train()
+    a = m.forward(data)
+    assert getattr(data, "_gnan_b200_cx_cache", None) is None            # nothing was compressed
+    m.eval()
+    b = m.forward(data)
+    assert data._gnan_b200_cx_cache[1] is not None                        # eval: shared evaluations
+    m.dedup = False
+    c = m.forward(data)
+    assert G.rel_err(b.detach().cpu().numpy(), c.detach().cpu().numpy()) < 1e-6
+    assert G.rel_err(a.detach().cpu().numpy(), c.detach().cpu().numpy()) > 1e-3   # dropout really was active

@@ -146,3 +146,42 @@ def test_packed_dataset_batch_gather_save_load_and_reference_view(tmp_path):
     g = ref[1]                                                           # pre_process_datasets.py:112-121 on the 3-node graph
     assert torch.equal(g.node_distances, torch.tensor([[1.0, 0.5, 0.0], [0.5, 1.0, 0.0], [0.0, 0.0, 1.0]]))
     assert torch.equal(g.normalization_matrix, torch.tensor([[1.0, 1.0, 1.0], [1.0, 1.0, 1.0], [2.0, 2.0, 1.0]]))
+
+
+def test_compress_features_structure_and_roundtrip():
+    """Host logic of gnan_b200.sparse.compress_features (pure tensor ops): baseline = column mode, exceptions in CSC order,
+    CSR view, work items; exact reconstruction; density cut-off."""
+    from gnan_b200.sparse import TILE, compress_features
+    rng = np.random.default_rng(0)
+    N, K = 300, 7
+    x = np.zeros((N, K), np.float32)
+    x[:, 0] = 1.0                                                # constant column (pre_process_datasets.py:108)
+    x[rng.integers(0, N, 40), 1] = rng.normal(size=40)           # sparse column
+    x[:, 2] = rng.integers(0, 2, N)                              # binary column: baseline = the more frequent of {0,1}
+    x[np.arange(N), 3 + rng.integers(0, 3, N)] = 1.0             # one-hot over columns 3..5
+    x[:200, 6] = 2.5                                             # 200 x 2.5, the rest zeros -> baseline 2.5
+    xt = torch.tensor(x)
+    cx = compress_features(xt, max_density=0.5)
+    assert cx is not None and cx.num_rows == N and cx.num_features == K
+    assert torch.equal(cx.to_dense(), xt)
+    assert cx.base[0] == 1.0 and cx.base[6] == 2.5 and cx.base[1] == 0.0
+    gp = cx.grp_ptr.tolist()
+    assert gp[1] - gp[0] == 1                                    # constant column: the baseline only
+    assert gp[7] - gp[6] == 1 + 100
+    for k in range(K):
+        assert cx.ent_row[gp[k]] == -1 and float(cx.val[gp[k]]) == float(cx.base[k])
+        rows = cx.ent_row[gp[k] + 1:gp[k + 1]]
+        assert bool((rows[1:] > rows[:-1]).all())               # exceptions sorted by row inside a group
+        assert bool((cx.ent_grp[gp[k]:gp[k + 1]] == k).all())
+    # CSR view lists exactly the exceptions of each row
+    cp = cx.csr_ptr.tolist()
+    assert cp[-1] == cx.num_entries - K
+    for r in (0, 17, N - 1):
+        eids = cx.csr_eid[cp[r]:cp[r + 1]]
+        assert bool((cx.ent_row[eids] == r).all())
+        assert sorted(cx.ent_grp[eids].tolist()) == sorted(np.nonzero(x[r] != cx.base.numpy())[0].tolist())
+    # work items: every (group, tile) exactly once
+    want = [(k, t) for k in range(K) for t in range((gp[k + 1] - gp[k] + TILE - 1) // TILE)]
+    assert [tuple(i) for i in cx.items.tolist()] == want and cx.max_group == max(gp[k + 1] - gp[k] for k in range(K))
+    assert compress_features(torch.tensor(rng.normal(size=(50, 4)).astype(np.float32))) is None      # dense data: not worth it
+    assert compress_features(torch.tensor(rng.normal(size=(50, 4)).astype(np.float32)), max_density=None) is not None
