@@ -312,6 +312,8 @@ def main():
     ap.add_argument("--workload", default="cora", choices=["cora", "pubmed", "arxiv", "mutag", "mol"])
     ap.add_argument("--classes", type=int, default=0, help="override the number of classes (arxiv: 40, or 1 = the reference's hard-coded value)")
     ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32"])
+    ap.add_argument("--dedup", default="on", choices=["on", "off"],
+                    help="share shape-function evaluations between rows with equal feature values (gnan_b200.sparse; exact, dropout is 0 here)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true", help="run the step eagerly instead of replaying a captured CUDA graph")
     args = ap.parse_args()
@@ -345,6 +347,8 @@ def main():
         model = TensorGNAN(wl.K, wl.C, L, H, normalize_rho=True, is_graph_task=True, readout_n_layers=0, device=dev).to(dev)
     model.fs.xavier_normal_(1.0); model.rho.xavier_normal_(1.0)
     model.precision = args.precision
+    model.dedup = args.dedup == "on"
+    from gnan_b200.sparse import compress_features
     opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     sharded = wl.name in ("pubmed", "arxiv") and world > 1
@@ -368,19 +372,25 @@ def main():
         idx_d = wl.train_mask[b0:e0].nonzero().flatten().to(dev)
         yl_d = wl.y[b0:e0].to(dev)[idx_d]
         n_train = float(wl.train_mask.sum())
-        data_d = (x_h.to(dev), hd)
-        h2d = x_h.numel() * 4 + (0 if big else hop_h.numel()) + cnt_h.numel() * 4
+        x_d = x_h.to(dev)
+        cx = compress_features(x_d) if (model.dedup and not sharded) else None         # once per dataset, like the hop matrix
+        cx_h = None if cx is None else cx.to("cpu").pin_memory()
+        data_d = SimpleNamespace(x=x_d, hop_data=hd, x_compressed=cx)
+        x_bytes = x_h.numel() * 4 if cx is None else cx.nbytes()
+        h2d = x_bytes + (0 if big else hop_h.numel()) + cnt_h.numel() * 4
 
         def load_host():
             hop_d = hd.hop if big else hop_h.to(dev, non_blocking=True)
-            return x_h.to(dev, non_blocking=True), HopData(hop_d, cnt_h.to(dev, non_blocking=True), wl.n, b0)
+            h = HopData(hop_d, cnt_h.to(dev, non_blocking=True), wl.n, b0)
+            if cx is None:
+                return SimpleNamespace(x=x_h.to(dev, non_blocking=True), hop_data=h, x_compressed=None)
+            return SimpleNamespace(x=None, hop_data=h, x_compressed=cx_h.to(dev))
 
         def loss_of(data):
-            x, h = data
             if sharded:
-                out = gdist.row_sharded_forward(model, x, h, sizes)
+                out = gdist.row_sharded_forward(model, data.x, data.hop_data, sizes)
             else:
-                out = model.forward(SimpleNamespace(x=x, hop_data=h))
+                out = model.forward(data)
             return loss_fn(out.index_select(0, idx_d), yl_d) / n_train
 
         def step(data):
@@ -397,34 +407,46 @@ def main():
         pk = apsp_batched(wl.edge_index, wl.node_off, device=dev, x=wl.x.to(dev), y=wl.y.to(dev))
         host = PackedBatch(wl.x.pin_memory(), pk.hop.cpu().pin_memory(), pk.hop_off.cpu().pin_memory(), pk.node_off.cpu().pin_memory(),
                            pk.level_counts.cpu().pin_memory(), wl.y.pin_memory(), pk.max_nodes)
+        cx = compress_features(pk.x) if model.dedup else None
+        cx_h = None if cx is None else cx.to("cpu").pin_memory()
+        pk.x_compressed = cx
         data_d = pk
-        h2d = sum(t.numel() * t.element_size() for t in (host.x, host.hop, host.hop_off, host.node_off, host.level_counts, host.y))
+        x_bytes = host.x.numel() * 4 if cx is None else cx.nbytes()
+        h2d = x_bytes + sum(t.numel() * t.element_size() for t in (host.hop, host.hop_off, host.node_off, host.level_counts, host.y))
 
         in_step_apsp = wl.name == "mol"
         if in_step_apsp:                                                # the step starts from the raw edge list
             ei_d, noff_d, x_d, y_d = wl.edge_index.to(dev), wl.node_off.to(dev), wl.x.to(dev), wl.y.to(dev)
             ei_h, noff_h = wl.edge_index.pin_memory(), wl.node_off.pin_memory()
-            data_d = (ei_d, noff_d, x_d, y_d)
-            h2d = sum(t.numel() * t.element_size() for t in (ei_h, noff_h, host.x, host.y))
+            data_d = (ei_d, noff_d, x_d, y_d, cx)
+            h2d = x_bytes + sum(t.numel() * t.element_size() for t in (ei_h, noff_h, host.y))
 
         def load_host():
+            c = None if cx is None else cx_h.to(dev)
+            xx = host.x.to(dev, non_blocking=True) if cx is None else None
             if in_step_apsp:
-                return (ei_h.to(dev, non_blocking=True), noff_h.to(dev, non_blocking=True), host.x.to(dev, non_blocking=True),
-                        host.y.to(dev, non_blocking=True))
-            return host.to(dev)
+                return (ei_h.to(dev, non_blocking=True), noff_h.to(dev, non_blocking=True), xx, host.y.to(dev, non_blocking=True), c)
+            b = PackedBatch(xx, host.hop.to(dev, non_blocking=True), host.hop_off.to(dev, non_blocking=True),
+                            host.node_off.to(dev, non_blocking=True), host.level_counts.to(dev, non_blocking=True),
+                            host.y.to(dev, non_blocking=True), host.max_nodes)
+            b.x_compressed = c
+            return b
 
         def step(data):
             if in_step_apsp:                                            # GPU multi-source BFS on the batch (pre_process_datasets.py:106-122)
-                e, no, xx, yy = data
+                e, no, xx, yy, c = data
                 data = apsp_batched(e, no, device=dev, x=xx, y=yy)
+                data.x_compressed = c
             opt.zero_grad(set_to_none=True)
-            out = model(data)                                           # [B,1]
-            loss = loss_fn(out.flatten(), data.y)
+            loss = loss_of(data)
             loss.backward()
             if world > 1:
                 gdist.allreduce_gradients(model.parameters(), average=True)
             opt.step()
             return loss
+
+        def loss_of(data):
+            return loss_fn(model(data).flatten(), data.y)               # model(data): [B,1]
         rows_local = wl.n
 
     lib = _lib.load()
@@ -434,17 +456,24 @@ def main():
     torch.cuda.synchronize()
 
     # ---- capture the whole step (forward + loss + backward + Adam; ~40 launches) into one CUDA graph -------------------
-    # Node workloads without collectives only: the batched-graph step sizes buffers from device values (host syncs) and the
-    # sharded step issues NCCL collectives. Falls back to eager execution if capture is not possible.
+    # Steps without collectives and without in-step preprocessing only (the batched BFS sizes its buffers from device values,
+    # the sharded / data-parallel steps issue NCCL collectives). Falls back to eager execution if capture is not possible.
     graphed = None
     launches_per_step = None
-    if not args.no_cuda_graph and wl.kind == "node" and not sharded:
+    capturable = (wl.kind == "node" and not sharded) or (wl.kind == "graph" and not in_step_apsp and world == 1)
+    if not args.no_cuda_graph and capturable:
         try:
-            static_x = data_d[0].clone()
-            static_hop = HopData(data_d[1].hop.clone(), data_d[1].level_counts.clone(), wl.n, b0)
-            cap = CapturedStep(lambda: loss_of((static_x, static_hop)), opt, warmup=2)   # gnan_b200.trainer: the public API
+            scx = None if cx is None else cx.to(dev).clone_tensors()
+            if wl.kind == "node":
+                static_hop = HopData(data_d.hop_data.hop.clone(), data_d.hop_data.level_counts.clone(), wl.n, b0)
+                static_in = SimpleNamespace(x=None if cx is not None else data_d.x.clone(), hop_data=static_hop, x_compressed=scx)
+            else:
+                static_in = PackedBatch(None if cx is not None else data_d.x.clone(), data_d.hop.clone(), data_d.hop_off.clone(),
+                                        data_d.node_off.clone(), data_d.level_counts.clone(), data_d.y.clone(), data_d.max_nodes)
+                static_in.x_compressed = scx
+            cap = CapturedStep(lambda: loss_of(static_in), opt, warmup=2)              # gnan_b200.trainer: the public API
             g, static_loss, launches_per_step = cap.graph, cap.loss, cap.kernel_launches
-            graphed = (g, static_x, static_hop, static_loss)
+            graphed = (g, static_in, static_loss)
             for _ in range(3):
                 g.replay()
             torch.cuda.synchronize()
@@ -456,15 +485,22 @@ def main():
     def run_step(data):
         if graphed is None:
             return step(data)
-        g, sx, sh, sl = graphed
-        if data[0] is not sx:                                       # e2e leg: refresh the static inputs from the fresh copies
-            sx.copy_(data[0], non_blocking=True)
-            sh.hop.copy_(data[1].hop, non_blocking=True)
-            sh.level_counts.copy_(data[1].level_counts, non_blocking=True)
+        g, sin, sl = graphed
+        if data is not sin:                                         # e2e leg: refresh the static inputs from the fresh copies
+            if sin.x is not None:
+                sin.x.copy_(data.x, non_blocking=True)
+            else:
+                sin.x_compressed.copy_tensors_(data.x_compressed)
+            if wl.kind == "node":
+                sin.hop_data.hop.copy_(data.hop_data.hop, non_blocking=True)
+                sin.hop_data.level_counts.copy_(data.hop_data.level_counts, non_blocking=True)
+            else:
+                for f in ("hop", "hop_off", "node_off", "level_counts", "y"):
+                    getattr(sin, f).copy_(getattr(data, f), non_blocking=True)
         g.replay()
         return sl
     if graphed is not None:
-        data_d = (graphed[1], graphed[2])
+        data_d = graphed[1]
 
     # ---- device-resident timing ---------------------------------------------------------------------------------------
     ops.enable_timing(True)
@@ -552,15 +588,37 @@ def main():
 
     if rank == 0:
         hbm, tflops, peak_src = measured_peaks()
-        calls, kms = kt.get("mlp_bwd", (0, 0.0))
-        # the op runs twice per step (shape functions, then the rho table); the rho call is <1e-3 of the work, so the
-        # dominant launch's duration ~= total / steps
-        dur_ms = kms / args.steps
-        alg_flops = 2.0 * flops_per_eval(wl.C) * rows_local * wl.K    # backward = 2x forward FLOPs; recompute not counted
-        achieved = alg_flops / (dur_ms / 1e3) / 1e12 if dur_ms > 0 else 0.0
+        # ---- roofline of the DOMINANT kernel of this step (largest CUDA-event time among the library's ops) ----------------
+        per_step = {k: v[1] / args.steps for k, v in kt.items()}
+        dom = max(per_step, key=per_step.get) if per_step else "mlp_bwd"
+        dur_ms = per_step.get(dom, 0.0)
+        n_entries = None if cx is None else int(cx.num_entries)
+        evals = rows_local * wl.K if cx is None else n_entries          # shape-function evaluations actually executed per pass
+        pairs = float((wl.sizes.astype(np.float64) ** 2).sum()) if wl.kind == "graph" else float(rows_local) * wl.n
         prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        traffic = json.load(open(prof)).get(f"{wl.name}:mlp_bwd:{args.precision}") if os.path.exists(prof) else None
-        tc = args.precision != "fp32"
+        traffic = json.load(open(prof)).get(f"{wl.name}:{dom}:{args.precision}") if os.path.exists(prof) else None
+        if dom.startswith("mlp"):
+            # backward = 2x the forward FLOPs; recompute and padded tile rows are not counted (with shared
+            # evaluations the count is the evaluations actually executed)
+            alg = (2.0 if "bwd" in dom else 1.0) * flops_per_eval(wl.C) * evals
+            achieved = alg / (dur_ms / 1e3) / 1e12 if dur_ms > 0 else 0.0
+            entries = "entries" in dom
+            roof = {"kernel": {"mlp_bwd": "mlp_tc_bwd_kernel" if args.precision != "fp32" else "mlp_bwd_kernel", "mlp_fwd": "mlp_tc_fwd_kernel" if args.precision != "fp32" else "mlp_fwd_kernel",
+                               "mlp_entries_bwd": "mlp_bwd_kernel (entries mode)", "mlp_entries_fwd": "mlp_fwd_kernel (entries mode)"}.get(dom, dom),
+                    "bound": "tensor", "achieved": achieved, "peak": tflops, "unit": "TFLOP/s", "frac": achieved / tflops, "traffic": traffic,
+                    "peak_source": peak_src, "algorithmic_flops_per_launch": alg, "evaluations_per_launch": evals,
+                    "pipe": ("fp32 FFMA (CUDA cores), one 128-row tile per (feature, entry tile); most tiles are partly filled" if entries else
+                             "tcgen05 kind::tf32, 3-term split: executed tensor FLOPs = 3-4x algorithmic" if args.precision == "tf32x3" else
+                             "tcgen05 kind::tf32" if args.precision == "tf32" else "fp32 FFMA (CUDA cores)")}
+        else:
+            alg = pairs                                                 # 1 hop byte per ordered pair per pass
+            achieved = alg / (dur_ms / 1e3) / 1e9 if dur_ms > 0 else 0.0
+            roof = {"kernel": {"aggregate_rows_fwd_save": "agg_rows_bins_kernel", "aggregate_rows_bwd_saved": "agg_rows_ds_kernel + dT kernels",
+                               "aggregate_blockdiag_fwd": "agg_blockdiag_fwd_kernel", "aggregate_blockdiag_bwd": "agg_blockdiag_bwd_kernel"}.get(dom, dom),
+                    "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": alg}
+        roof["avg_launch_ms"] = dur_ms
+        roof["kernel_ms_per_step"] = per_step
         line = {
             "metric": f"GNAN fwd+bwd {wl.unit} ({wl.name}-shape TensorGNAN)", "value": value, "unit": wl.unit, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling,
@@ -573,13 +631,11 @@ def main():
             "strict_fp32": None if strict_ms is None else {
                 "ms_per_step": strict_ms, "value": total_units / (strict_ms / 1e3), "unit": wl.unit, "kernel_ms_per_step": strict_kt,
                 "note": "same step with precision='fp32' (FFMA kernels only, every golden case within 1.5e-6 of the reference), run eagerly; median step"},
-            "roofline": {"kernel": ("mlp_tc_bwd_kernel" if tc else "mlp_bwd_kernel") + " (grouped shape-MLP backward incl. partial-gradient reduce)",
-                         "bound": "tensor", "achieved": achieved, "peak": tflops, "unit": "TFLOP/s", "frac": achieved / tflops,
-                         "traffic": traffic, "peak_source": peak_src, "algorithmic_flops_per_launch": alg_flops,
-                         "avg_launch_ms": dur_ms,
-                         "pipe": "tcgen05 kind::tf32, 3-term split: executed tensor FLOPs = 3-4x algorithmic" if args.precision == "tf32x3"
-                                 else ("tcgen05 kind::tf32" if tc else "fp32 FFMA (CUDA cores)"),
-                         "kernel_ms_per_step": {k: v[1] / args.steps for k, v in kt.items()}},
+            "roofline": roof,
+            "dedup": None if cx is None else {
+                "entries": n_entries, "dense_evaluations": rows_local * wl.K, "exception_density": cx.density(),
+                "note": "rows with equal values in a feature column share one shape-function evaluation (exact; dropout is 0 here); "
+                        "the compressed form is built once per dataset like the hop matrix. --dedup off runs the dense kernels"},
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:

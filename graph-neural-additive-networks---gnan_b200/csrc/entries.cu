@@ -53,21 +53,24 @@ __global__ void rows_to_exceptions_kernel(const float *__restrict__ dS, int64_t 
     if (r >= 0) dY[t] = dS[r * C + (t % C)];
 }
 
-// dY of the baseline of group g = (sum of dS over all rows) - (sum over the rows listed as exceptions of g); one warp per (g, c)
+// dY of the baseline of group g = (sum of dS over all rows) - (sum over the rows listed as exceptions of g); one block per
+// (g, c), fixed-order strided partial sums + tree (deterministic)
 __global__ void rows_to_baselines_kernel(const float *__restrict__ dS, int G, int C, const int64_t *__restrict__ grp_ptr,
                                          const int64_t *__restrict__ ent_row, const float *__restrict__ dStot,
                                          float *__restrict__ dY)
 {
-    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (w >= (int64_t)G * C) return;
-    const int g = (int)(w / C), c = (int)(w % C);
+    __shared__ float red[512];
+    const int g = blockIdx.x / C, c = blockIdx.x % C;
     const int64_t e0 = grp_ptr[g], e1 = grp_ptr[g + 1];
     float s = 0.f;
-    for (int64_t e = e0 + 1 + lane; e < e1; e += 32) s += dS[ent_row[e] * C + c];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) dY[e0 * C + c] = dStot[c] - s;
+    for (int64_t e = e0 + 1 + threadIdx.x; e < e1; e += blockDim.x) s += dS[ent_row[e] * C + c];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = blockDim.x / 2; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) dY[e0 * C + c] = dStot[c] - red[0];
 }
 
 }  // namespace
@@ -98,7 +101,8 @@ extern "C" int gnan_rows_to_entries(const float *dS, int64_t N, int32_t G, int32
     GNAN_LAUNCH_OK();
     rows_to_exceptions_kernel<<<(unsigned)ceil_div64(E * C, 256), 256, 0, st>>>(dS, E, C, ent_row, dY);
     GNAN_LAUNCH_OK();
-    rows_to_baselines_kernel<<<(unsigned)ceil_div64((int64_t)G * C * 32, 256), 256, 0, st>>>(dS, G, C, grp_ptr, ent_row, dStot, dY);
+    const int bt = (E / G) > 2048 ? 512 : 64;          // long groups (few features, many exceptions) get wide blocks
+    rows_to_baselines_kernel<<<(unsigned)(G * C), bt, 0, st>>>(dS, G, C, grp_ptr, ent_row, dStot, dY);
     GNAN_LAUNCH_OK();
     return GNAN_OK;
 }

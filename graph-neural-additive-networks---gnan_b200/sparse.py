@@ -66,6 +66,15 @@ class CompressedFeatures:
     def pin_memory(self):
         return CompressedFeatures(self.num_rows, *[getattr(self, f).pin_memory() for f in self._FIELDS], self.max_group)
 
+    def clone_tensors(self):
+        return CompressedFeatures(self.num_rows, *[getattr(self, f).clone() for f in self._FIELDS], self.max_group)
+
+    def copy_tensors_(self, other):
+        """In-place refresh from another compressed form of the SAME structure sizes (static inputs of a CUDA graph)."""
+        for f in self._FIELDS:
+            getattr(self, f).copy_(getattr(other, f), non_blocking=True)
+        return self
+
     def to_dense(self):
         """x [N,K] back (exactly)."""
         x = self.base.unsqueeze(0).repeat(self.num_rows, 1)
