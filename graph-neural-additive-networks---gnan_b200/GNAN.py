@@ -49,7 +49,7 @@ class _Base(nn.Module):
     def _feature_sums(self, x, cx=None):
         if cx is not None:
             from . import sparse
-            return sparse.feature_sums(cx, *self.fs.kernel_args())
+            return sparse.feature_sums(cx, *self.fs.kernel_args(), precision=self.precision)
         if x.shape[1] != self.fs.groups:
             raise ValueError(f"x has {x.shape[1]} features, model was built for {self.fs.groups}")
         p = self.fs.dropout if self.training else 0.0

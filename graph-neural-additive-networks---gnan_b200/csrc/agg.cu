@@ -389,6 +389,52 @@ agg_blockdiag_bwd_kernel(BdArgs a, const float *__restrict__ g, float *__restric
     }
 }
 
+// backward for a GLOBAL table (models.py TensorGNAN, batched variant): one pass over the pairs gives both gradients, no atomics
+// in the pair loop. A lane owns columns j = lane, lane+32, ..: dS[j] accumulates in a register; dT accumulates in a lane-private
+// shared-memory column accT[t][lane] that persists over all graphs of the warp and is reduced over lanes once at the end.
+__global__ void __launch_bounds__(256)
+agg_blockdiag_bwd_global_kernel(BdArgs a, const float *__restrict__ g, float *__restrict__ dS, float *__restrict__ dT)
+{
+    extern __shared__ float sb[];                      // [nT] table copy, then [8 warps][nT][32] accumulators
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nT = a.nbins * a.Cr;
+    float *sT = sb;
+    float *acc = sb + nT + (size_t)w * nT * 32;
+    for (int t = threadIdx.x; t < nT; t += blockDim.x) sT[t] = a.T[t];
+    for (int t = lane; t < nT * 32; t += 32) acc[t] = 0.f;
+    __syncthreads();
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t b = warp; b < a.B; b += nwarps) {
+        const int n0 = a.node_off[b], n = a.node_off[b + 1] - n0;
+        const uint8_t *hb = a.hop + a.hop_off[b];
+        for (int c = 0; c < a.C; ++c) {
+            const int cr = a.Cr == 1 ? 0 : c;
+            const float gb = a.reduce_graph ? g[b * a.C + c] : 0.f;
+            for (int j = lane; j < n; j += 32) {
+                const float sj = a.S[(int64_t)(n0 + j) * a.C + c];
+                float ds = 0.f;
+                for (int i = 0; i < n; ++i) {
+                    const int d = min((int)hb[(size_t)i * n + j], a.nbins - 1);
+                    float r = a.reduce_graph ? gb : g[(int64_t)(n0 + i) * a.C + c];
+                    if (a.rscale) r *= a.rscale[(int64_t)(n0 + i) * a.nbins + d];
+                    const int t = d * a.Cr + cr;
+                    ds = fmaf(sT[t], r, ds);
+                    acc[t * 32 + lane] = fmaf(r, sj, acc[t * 32 + lane]);
+                }
+                dS[(int64_t)(n0 + j) * a.C + c] = ds;
+            }
+        }
+    }
+    __syncwarp();
+    for (int t = 0; t < nT; ++t) {
+        float v = acc[t * 32 + lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && v != 0.f) atomicAdd(dT + t, v);
+    }
+}
+
 // ---- small helpers ---------------------------------------------------------------------------------------------
 __global__ void rho_table_inputs_kernel(const int32_t *__restrict__ cnt, int64_t rows, int nbins, int raw, float *__restrict__ u)
 {
@@ -618,6 +664,13 @@ extern "C" int gnan_aggregate_blockdiag_bwd(const uint8_t *hop, const int64_t *h
     BdArgs a{hop, hop_off, node_off, B, T, table_per_row, nbins, Cr, rscale, S, C, reduce_graph};
     if (!table_per_row) GNAN_CUDA(cudaMemsetAsync(dT, 0, sizeof(float) * nbins * Cr, st));
     const int blocks = (int)std::min<int64_t>(ceil_div64(B, 8), 4 * gnan_sm_count());
+    const size_t smem_g = sizeof(float) * (size_t)nbins * Cr * (1 + 8 * 32);
+    if (!table_per_row && smem_g <= 200 * 1024) {       // global table: lane-private accumulators, one pass
+        GNAN_CUDA(cudaFuncSetAttribute(agg_blockdiag_bwd_global_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+        agg_blockdiag_bwd_global_kernel<<<blocks, 256, smem_g, st>>>(a, g, dS, dT);
+        GNAN_LAUNCH_OK();
+        return GNAN_OK;
+    }
     const size_t smem = sizeof(float) * (size_t)nbins * Cr * (table_per_row ? 8 : 1);
     agg_blockdiag_bwd_kernel<<<blocks, 256, smem, st>>>(a, g, dS, dT);
     GNAN_LAUNCH_OK();

@@ -17,7 +17,7 @@ constexpr int BW_MAX = 8;  // up to 256 nodes per graph
 __global__ void __launch_bounds__(256)
 apsp_batched_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, const int32_t *__restrict__ node_off,
                     const int64_t *__restrict__ hop_off, int B, int max_n, uint8_t *__restrict__ hop, int32_t *__restrict__ cnt,
-                    int nbins, int32_t *__restrict__ overflow)
+                    int nbins, int32_t *__restrict__ overflow, int prefilled, int32_t *__restrict__ max_level)
 {
     extern __shared__ uint32_t sadj[];  // [8 warps][max_n][Wmax]
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -25,6 +25,7 @@ apsp_batched_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restric
     uint32_t *adj = sadj + (size_t)w * max_n * Wmax;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    int lvl_max = 0;                                       // largest finite hop seen by this lane
     for (int64_t b = warp; b < B; b += nwarps) {
         const int n0 = node_off[b], n = node_off[b + 1] - n0;
         const int W = (n + 31) / 32;
@@ -46,11 +47,13 @@ apsp_batched_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restric
             for (int ww = 0; ww < BW_MAX; ++ww)
                 if (ww == (s >> 5)) { vis[ww] = 1u << (s & 31); fr[ww] = vis[ww]; }
             uint8_t *row = hb + (size_t)s * n;
-            for (int v = 0; v < n; ++v) row[v] = GNAN_HOP_UNREACHABLE;
+            if (!prefilled)                                  // (the host wrapper memsets hop / cnt when it knows their sizes)
+                for (int v = 0; v < n; ++v) row[v] = GNAN_HOP_UNREACHABLE;
             row[s] = 0;
             int32_t *crow = cnt ? cnt + (int64_t)(n0 + s) * nbins : nullptr;
             if (crow) {
-                for (int d = 0; d < nbins; ++d) crow[d] = 0;
+                if (!prefilled)
+                    for (int d = 0; d < nbins; ++d) crow[d] = 0;
                 crow[0] = 1;
             }
             int reached = 1;
@@ -91,9 +94,15 @@ apsp_batched_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restric
                 }
                 if (crow && level < nbins - 1) crow[level] = newc;
                 reached += newc;
+                lvl_max = max(lvl_max, level);
             }
             if (crow) crow[nbins - 1] = n - reached;
         }
+    }
+    if (max_level) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lvl_max = max(lvl_max, __shfl_xor_sync(0xffffffffu, lvl_max, o));
+        if (lane == 0 && lvl_max > 0) atomicMax(max_level, lvl_max);
     }
 }
 
@@ -393,8 +402,8 @@ extern "C" int gnan_apsp_msbfs(const int32_t *rowptr, const int32_t *col, int32_
 
 // max_n is needed to size shared memory; exported variant with it explicit (the header-declared entry derives it on the host side)
 extern "C" int gnan_apsp_bfs_batched_n(const int32_t *rowptr, const int32_t *col, const int32_t *node_off, const int64_t *hop_off,
-                                       int32_t B, int32_t max_n, uint8_t *hop, int32_t *cnt, int32_t nbins,
-                                       int32_t *overflow_flag, gnan_stream_t stream)
+                                       int32_t B, int32_t max_n, int64_t total_nodes, int64_t total_hop_bytes, uint8_t *hop,
+                                       int32_t *cnt, int32_t nbins, int32_t *overflow_flag, int32_t *max_level, gnan_stream_t stream)
 {
     GNAN_REQUIRE(B >= 0, "apsp_bfs_batched: negative batch");
     if (B == 0) return GNAN_OK;
@@ -407,8 +416,14 @@ extern "C" int gnan_apsp_bfs_batched_n(const int32_t *rowptr, const int32_t *col
     const size_t smem = sizeof(uint32_t) * 8 * (size_t)max_n * ((max_n + 31) / 32);
     GNAN_CUDA(cudaFuncSetAttribute(apsp_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int blocks = (int)std::min<int64_t>(ceil_div64(B, 8), 16 * gnan_sm_count());
+    // with the totals known on the host the 255 / 0 background is two memsets at HBM speed instead of per-lane store loops
+    const int prefilled = total_nodes > 0 && total_hop_bytes > 0;
+    if (prefilled) {
+        GNAN_CUDA(cudaMemsetAsync(hop, GNAN_HOP_UNREACHABLE, (size_t)total_hop_bytes, (cudaStream_t)stream));
+        if (cnt) GNAN_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (size_t)total_nodes * nbins, (cudaStream_t)stream));
+    }
     apsp_batched_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(rowptr, col, node_off, hop_off, B, max_n, hop, cnt,
-                                                                     cnt ? nbins : 256, overflow_flag);
+                                                                     cnt ? nbins : 256, overflow_flag, prefilled, max_level);
     GNAN_LAUNCH_OK();
     return GNAN_OK;
 }
@@ -418,7 +433,7 @@ extern "C" int gnan_apsp_bfs_batched(const int32_t *rowptr, const int32_t *col, 
                                      gnan_stream_t stream)
 {
     // without a host-side size hint assume the largest supported graph
-    return gnan_apsp_bfs_batched_n(rowptr, col, node_off, hop_off, B, 32 * BW_MAX, hop, cnt, nbins, overflow_flag, stream);
+    return gnan_apsp_bfs_batched_n(rowptr, col, node_off, hop_off, B, 32 * BW_MAX, 0, 0, hop, cnt, nbins, overflow_flag, nullptr, stream);
 }
 
 extern "C" int gnan_hops_to_reference(const uint8_t *hop, int64_t R, int64_t N, int64_t ld_hop, const int32_t *cnt,

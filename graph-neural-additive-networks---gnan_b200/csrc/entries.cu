@@ -4,6 +4,8 @@
 // Layout: group g owns entries [grp_ptr[g], grp_ptr[g+1]); its FIRST entry is the feature's baseline value (shared by
 // every row that is not listed), the others are exceptions (row, value). S[r,:] = sum_g f_g(x[r,g]) becomes
 //   S[r,:] = sum_g Y[base_g,:] + sum_{e in exceptions of row r} (Y[e,:] - Y[base_{g(e)},:]).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace {
@@ -24,6 +26,33 @@ __global__ void colsum_kernel(const float *__restrict__ src, const int64_t *__re
         __syncthreads();
     }
     if (threadIdx.x == 0) out[c] = red[0];
+}
+
+// two-stage deterministic column sum of a tall [n,C] matrix: partial[blk][c] over row slabs, then the fixed-order final sum
+constexpr int COLSUM_SLABS = 64;
+__global__ void colsum_partial_kernel(const float *__restrict__ src, int64_t n, int C, float *__restrict__ partial)
+{
+    __shared__ float red[256];
+    const int c = blockIdx.x, blk = blockIdx.y;
+    const int64_t per = (n + gridDim.y - 1) / gridDim.y, r0 = blk * per, r1 = min(n, r0 + per);
+    float s = 0.f;
+    for (int64_t i = r0 + threadIdx.x; i < r1; i += blockDim.x) s += src[i * C + c];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = blockDim.x / 2; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blk * C + c] = red[0];
+}
+
+__global__ void colsum_final_kernel(const float *__restrict__ partial, int nblk, int C, float *__restrict__ out)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float s = 0.f;
+    for (int b = 0; b < nblk; ++b) s += partial[b * C + c];
+    out[c] = s;
 }
 
 __global__ void entries_to_rows_kernel(const float *__restrict__ Y, int64_t N, int C, const int64_t *__restrict__ grp_ptr,
@@ -97,7 +126,10 @@ extern "C" int gnan_rows_to_entries(const float *dS, int64_t N, int32_t G, int32
     GNAN_REQUIRE(N >= 0 && G >= 1 && C >= 1 && E >= G, "rows_to_entries: bad sizes");
     GNAN_REQUIRE(grp_ptr && ent_row && dStot && dY && (N == 0 || dS), "rows_to_entries: NULL pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    colsum_kernel<false><<<C, 512, 0, st>>>(dS, nullptr, N, C, dStot);
+    const int nblk = (int)std::max<int64_t>(1, std::min<int64_t>(COLSUM_SLABS, N / 2048));
+    colsum_partial_kernel<<<dim3((unsigned)C, (unsigned)nblk), 256, 0, st>>>(dS, N, C, dStot + C);
+    GNAN_LAUNCH_OK();
+    colsum_final_kernel<<<(unsigned)ceil_div64(C, 64), 64, 0, st>>>(dStot + C, nblk, C, dStot);
     GNAN_LAUNCH_OK();
     rows_to_exceptions_kernel<<<(unsigned)ceil_div64(E * C, 256), 256, 0, st>>>(dS, E, C, ent_row, dY);
     GNAN_LAUNCH_OK();

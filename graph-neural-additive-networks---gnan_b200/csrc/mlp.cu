@@ -702,6 +702,9 @@ int gnan_mlp_tc_fwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_param
                     int precision, float *S, void *ws, size_t ws_bytes, cudaStream_t st);
 int gnan_mlp_tc_bwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *p, float dropout_p, uint64_t seed,
                     int precision, const float *dS, const gnan_mlp_grads *grads, void *ws, size_t ws_bytes, cudaStream_t st);
+int gnan_mlp_tc_bwd_ex(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *p, float dropout_p, uint64_t seed,
+                       int precision, const float *dS, const gnan_mlp_grads *grads, void *ws, size_t ws_bytes, cudaStream_t st,
+                       const int64_t *grp_ptr);
 
 extern "C" size_t gnan_mlp_workspace_bytes(int64_t R, const gnan_mlp_params *p, int backward, int precision)
 {
@@ -851,9 +854,11 @@ int check_entries(const gnan_mlp_params *p, const float *val, const int64_t *grp
 }
 }  // namespace
 
-extern "C" size_t gnan_mlp_entries_workspace_bytes(int64_t max_group_entries, const gnan_mlp_params *p, int backward)
+extern "C" size_t gnan_mlp_entries_workspace_bytes(int64_t max_group_entries, const gnan_mlp_params *p, int backward, int precision)
 {
     if (!p || p->n_layers < 2 || max_group_entries <= 0 || !backward) return 0;
+    if (precision != GNAN_PREC_FP32 && gnan_mlp_tc_bwd_supported(p, precision))
+        return gnan_mlp_tc_workspace_bytes(max_group_entries, p, 1, precision);
     const BwdPlan pl = plan_bwd(max_group_entries, p);
     return pl.nchunk > 1 ? sizeof(float) * (size_t)pl.nchunk * grad_floats(p) : 0;
 }
@@ -883,8 +888,8 @@ extern "C" int gnan_mlp_entries_fwd(const float *val, const int64_t *grp_ptr, in
 }
 
 extern "C" int gnan_mlp_entries_bwd(const float *val, const int64_t *grp_ptr, int64_t E, int64_t max_group_entries,
-                                    const gnan_mlp_params *p, const float *dY, const gnan_mlp_grads *grads, void *workspace,
-                                    size_t workspace_bytes, gnan_stream_t stream)
+                                    const gnan_mlp_params *p, int precision, const float *dY, const gnan_mlp_grads *grads,
+                                    void *workspace, size_t workspace_bytes, gnan_stream_t stream)
 {
     int rc = check_entries(p, val, grp_ptr, E, "mlp_entries_bwd");
     if (rc) return rc;
@@ -892,6 +897,9 @@ extern "C" int gnan_mlp_entries_bwd(const float *val, const int64_t *grp_ptr, in
     GNAN_REQUIRE(grads->du == nullptr, "mlp_entries_bwd: input gradients are not available in entries mode");
     GNAN_REQUIRE(max_group_entries >= 0 && max_group_entries <= E, "mlp_entries_bwd: bad max_group_entries");
     cudaStream_t st = (cudaStream_t)stream;
+    if (E > 0 && precision != GNAN_PREC_FP32 && gnan_mlp_tc_bwd_supported(p, precision))      // tcgen05 kernel, per-group row space
+        return gnan_mlp_tc_bwd_ex(val, std::max<int64_t>(max_group_entries, 1), 1, p, 0.f, 0, precision, dY, grads, workspace,
+                                  workspace_bytes, st, grp_ptr);
     MlpKArgs a = make_args(val, E, 1, p, 0.f, 0);
     a.grp_ptr = grp_ptr;
     const size_t G = p->G, H = p->H, C = p->C, nh = p->n_layers - 2;

@@ -57,6 +57,7 @@ struct TcArgs {
     uint64_t seed;
     int single_pass;  // 1 = plain tf32 (no lo terms)
     int prof;         // debug: bit 0 = accumulate phase cycle counters (GNAN_TC_PROF), bit 1 = skip MMA3 (GNAN_TC_SKIP3)
+    const int64_t *grp_ptr;   // backward, entries mode (gnan_mlp_entries_bwd): rows of group g = its entries; NULL = dense
 };
 
 __device__ __forceinline__ uint64_t tc_drop_key(const TcArgs &a, int layer, int g, int64_t row, int unit)
@@ -381,6 +382,17 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
     BwdSmem &sm = *reinterpret_cast<BwdSmem *>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = blockIdx.y;
+    // row space of this CTA's group: all R rows, column g of u (dense), or the group's own entries (entries mode)
+    int64_t nrow = a.R, ustride = a.ldu;
+    const float *ub = a.u + g;
+    if (a.grp_ptr) {
+        const int64_t ebase = a.grp_ptr[g];
+        nrow = a.grp_ptr[g + 1] - ebase;
+        ntiles = (nrow + ROWS - 1) / ROWS;
+        ub = a.u + ebase;
+        ustride = 1;
+        dS += ebase * a.C;
+    }
 
     if (warp == BWD_ROW_WARPS) tmem_alloc(smem_u32(&sm.tmem_base), 512);
     if (tid == 0) {
@@ -521,8 +533,8 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
         float x_n = 0.f, gv_n[CT];
         {
             const int64_t row = (int64_t)blockIdx.x * ROWS + r;
-            const bool ok = blockIdx.x < ntiles && row < a.R;
-            x_n = ok ? __ldg(a.u + row * a.ldu + g) : 0.f;
+            const bool ok = blockIdx.x < ntiles && row < nrow;
+            x_n = ok ? __ldg(ub + row * ustride) : 0.f;
 #pragma unroll
             for (int c = 0; c < CT; ++c) gv_n[c] = (ok && c < a.C && part == 0) ? __ldg(dS + row * a.C + c) : 0.f;
         }
@@ -567,9 +579,9 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
             const int64_t row = t * ROWS + r;
             const float x = x_n;
             const int64_t tn = t + gridDim.x, rown = tn * ROWS + r;
-            const bool okn = tn < ntiles && rown < a.R;
+            const bool okn = tn < ntiles && rown < nrow;
             x_n = 0.f;
-            if (okn) x_n = ldg_prefetch(a.u + rown * a.ldu + g);
+            if (okn) x_n = ldg_prefetch(ub + rown * ustride);
             if (part == 0) {                                   // only these threads need dS: stage it for the dh MMA and the dWo phase
                 uint32_t gh[CT_MAX], gl[CT_MAX];
 #pragma unroll
@@ -753,6 +765,10 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
                 uint32_t d[32];
                 tmem_ld32(lane_base + colD3 + hc * 32, d);
                 tmem_wait_ld();
+                if (it == 0) {                     // entries mode: a CTA beyond its group's tiles issued no MMA (D3 is undefined)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) d[i] = 0u;
+                }
                 if (r >= 64) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 4)
@@ -794,6 +810,22 @@ __global__ void dbo_colsum_kernel(const float *__restrict__ dS, int64_t R, int C
     for (int g = threadIdx.x; g < G; g += blockDim.x) dbo[(size_t)g * C + c] = red[0];
 }
 
+// entries mode: d bo[g][c] = sum over the entries of group g; one block per (g, c), fixed-order tree
+__global__ void dbo_entries_kernel(const float *__restrict__ dY, const int64_t *__restrict__ grp_ptr, int C, float *__restrict__ dbo)
+{
+    __shared__ float red[256];
+    const int g = blockIdx.x / C, c = blockIdx.x % C;
+    float s = 0.f;
+    for (int64_t e = grp_ptr[g] + threadIdx.x; e < grp_ptr[g + 1]; e += blockDim.x) s += dY[e * C + c];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int w = blockDim.x / 2; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) dbo[g * C + c] = red[0];
+}
+
 struct TcFwdPlan { int KC, nchunk; int64_t ntile; };
 
 TcFwdPlan plan_tc_fwd(int64_t R, const gnan_mlp_params *p)
@@ -818,6 +850,7 @@ TcArgs make_tc_args(const float *u, int64_t R, int64_t ldu, const gnan_mlp_param
     a.seed = seed;
     a.single_pass = precision == GNAN_PREC_TF32;
     a.prof = (getenv("GNAN_TC_PROF") != nullptr ? 1 : 0) | (getenv("GNAN_TC_SKIP3") != nullptr ? 2 : 0);
+    a.grp_ptr = nullptr;
     return a;
 }
 
@@ -912,8 +945,10 @@ int gnan_mlp_tc_fwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_param
     return GNAN_OK;
 }
 
-int gnan_mlp_tc_bwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *p, float dropout_p, uint64_t seed,
-                    int precision, const float *dS, const gnan_mlp_grads *grads, void *ws, size_t ws_bytes, cudaStream_t st)
+// grp_ptr != NULL: entries mode, u = val[E], R = the largest group (sizes the row chunks), dS = dY[E,C]
+int gnan_mlp_tc_bwd_ex(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *p, float dropout_p, uint64_t seed,
+                       int precision, const float *dS, const gnan_mlp_grads *grads, void *ws, size_t ws_bytes, cudaStream_t st,
+                       const int64_t *grp_ptr)
 {
     const TcBwdPlan pl = plan_tc_bwd(R, p);
     const size_t G = p->G, C = p->C, ntot = tc_grad_floats(p);
@@ -936,7 +971,8 @@ int gnan_mlp_tc_bwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_param
         gp.w1 = grads->w1; gp.b1 = grads->b1; gp.wh = grads->wh; gp.bh = grads->bh; gp.wo = grads->wo; gp.bo = grads->bo;
         gp.chunk_stride = 0;
     }
-    const TcArgs a = make_tc_args(u, R, ldu, p, dropout_p, seed, precision);
+    TcArgs a = make_tc_args(u, R, ldu, p, dropout_p, seed, precision);
+    a.grp_ptr = grp_ptr;
     int rc;
     if (p->C == 1) rc = launch_tc_bwd<1>(a, pl, dS, gp, st);
     else if (p->C == 2) rc = launch_tc_bwd<2>(a, pl, dS, gp, st);
@@ -954,10 +990,17 @@ int gnan_mlp_tc_bwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_param
         }
     }
     if (grads->bo) {
-        dbo_colsum_kernel<<<(unsigned)C, 256, 0, st>>>(dS, R, (int)C, (int)G, grads->bo);
+        if (grp_ptr) dbo_entries_kernel<<<(unsigned)(G * C), 256, 0, st>>>(dS, grp_ptr, (int)C, grads->bo);
+        else dbo_colsum_kernel<<<(unsigned)C, 256, 0, st>>>(dS, R, (int)C, (int)G, grads->bo);
         GNAN_LAUNCH_OK();
     }
     return GNAN_OK;
+}
+
+int gnan_mlp_tc_bwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *p, float dropout_p, uint64_t seed,
+                    int precision, const float *dS, const gnan_mlp_grads *grads, void *ws, size_t ws_bytes, cudaStream_t st)
+{
+    return gnan_mlp_tc_bwd_ex(u, R, ldu, p, dropout_p, seed, precision, dS, grads, ws, ws_bytes, st, nullptr);
 }
 
 // debug aid: read (and clear) the backward kernel's phase cycle counters; slots: 0 gen, 1 wait MMA1, 2 epiC, 3 wait MMA2,

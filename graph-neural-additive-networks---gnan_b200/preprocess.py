@@ -183,13 +183,18 @@ def apsp_batched(edge_index, node_off, device="cuda", x=None, y=None):
     total = int(hop_off[-1].item())
     rowptr, col = build_csr(edge_index, sumN, device)
     hop = torch.empty(max(total, 1), dtype=torch.uint8, device=device)
-    cnt = torch.empty(sumN, 256, dtype=torch.int32, device=device)
-    flag = torch.zeros(1, dtype=torch.int32, device=device)
-    check(lib.gnan_apsp_bfs_batched_n(ptr(rowptr), ptr(col), ptr(node_off), ptr(hop_off), B, max_n, ptr(hop), ptr(cnt), 256,
-                                      ptr(flag), stream_handle()), "gnan_apsp_bfs_batched")
-    if B and int(flag.item()):
+    nb = min(256, max_n + 1)                     # a finite hop inside a graph is at most max_n - 1; last column = unreachable
+    cnt = torch.empty(sumN, nb, dtype=torch.int32, device=device)
+    flag = torch.zeros(2, dtype=torch.int32, device=device)           # [overflow, largest finite hop]
+    check(lib.gnan_apsp_bfs_batched_n(ptr(rowptr), ptr(col), ptr(node_off), ptr(hop_off), B, max_n, sumN, total, ptr(hop), ptr(cnt), nb,
+                                      ptr(flag), flag.data_ptr() + 4, stream_handle()), "gnan_apsp_bfs_batched")
+    over, D = (int(v) for v in flag.tolist()) if B else (0, 0)
+    if over:
         raise NotImplementedError("a hop distance > 254 does not fit the uint8 hop matrix")
-    return PackedBatch(x, hop, hop_off, node_off, _trim_counts(cnt) if sumN else cnt[:, :2], y, max_n)
+    if sumN == 0:
+        return PackedBatch(x, hop, hop_off, node_off, cnt[:, :2], y, max_n)
+    lc = torch.cat([cnt[:, :D + 1], cnt[:, nb - 1:nb]], dim=1).contiguous()
+    return PackedBatch(x, hop, hop_off, node_off, lc, y, max_n)
 
 
 def pre_process(data, is_graph_task, data_name=None, processed_data_dir=None, device="cuda", reference_format=False):

@@ -130,7 +130,7 @@ def compress_features(x: Tensor, max_density: Optional[float] = MAX_DENSITY) -> 
 # ---------------------------------------------------------------------------------------------------------------------
 @torch.library.custom_op("gnan_b200::mlp_entries_fwd", mutates_args=())
 def mlp_entries_fwd(val: Tensor, grp_ptr: Tensor, items: Tensor, w1: Tensor, b1: Tensor, wh: Tensor, bh: Tensor, wo: Tensor,
-                    bo: Tensor, n_layers: int, max_group: int) -> Tensor:
+                    bo: Tensor, n_layers: int, max_group: int, precision: int) -> Tensor:
     lib = load()
     val, w1, b1, wh, bh, wo, bo = (ops._f32(t, n) for t, n in zip((val, w1, b1, wh, bh, wo, bo), "val w1 b1 wh bh wo bo".split()))
     if grp_ptr.dtype != torch.int64 or items.dtype != torch.int32 or grp_ptr.numel() != wo.shape[0] + 1:
@@ -145,40 +145,40 @@ def mlp_entries_fwd(val: Tensor, grp_ptr: Tensor, items: Tensor, w1: Tensor, b1:
 
 
 @mlp_entries_fwd.register_fake
-def _(val, grp_ptr, items, w1, b1, wh, bh, wo, bo, n_layers, max_group):
+def _(val, grp_ptr, items, w1, b1, wh, bh, wo, bo, n_layers, max_group, precision):
     return val.new_empty(val.numel(), wo.shape[1])
 
 
 @torch.library.custom_op("gnan_b200::mlp_entries_bwd", mutates_args=())
 def mlp_entries_bwd(val: Tensor, grp_ptr: Tensor, w1: Tensor, b1: Tensor, wh: Tensor, bh: Tensor, wo: Tensor, bo: Tensor,
-                    n_layers: int, max_group: int, dY: Tensor) -> tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+                    n_layers: int, max_group: int, precision: int, dY: Tensor) -> tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
     lib = load()
     val, w1, b1, wh, bh, wo, bo, dY = (ops._f32(t, n) for t, n in zip((val, w1, b1, wh, bh, wo, bo, dY), "val w1 b1 wh bh wo bo dY".split()))
     p, G, H, C = ops._mlp_params(w1, b1, wh, bh, wo, bo, n_layers)
     outs = [torch.empty_like(t) for t in (w1, b1, wh, bh, wo, bo)]
     g = MlpGrads(*[ptr(t) for t in outs], None)
-    ws = ops._ws(lib.gnan_mlp_entries_workspace_bytes(max_group, p, 1), val.device)
+    ws = ops._ws(lib.gnan_mlp_entries_workspace_bytes(max_group, p, 1, precision), val.device)
     with ops._timed("mlp_entries_bwd"):
-        check(lib.gnan_mlp_entries_bwd(ptr(val), ptr(grp_ptr), val.numel(), max_group, p, ptr(dY), g, ptr(ws), ws.numel(),
+        check(lib.gnan_mlp_entries_bwd(ptr(val), ptr(grp_ptr), val.numel(), max_group, p, precision, ptr(dY), g, ptr(ws), ws.numel(),
                                        stream_handle()), "gnan_mlp_entries_bwd")
     return tuple(outs)
 
 
 @mlp_entries_bwd.register_fake
-def _(val, grp_ptr, w1, b1, wh, bh, wo, bo, n_layers, max_group, dY):
+def _(val, grp_ptr, w1, b1, wh, bh, wo, bo, n_layers, max_group, precision, dY):
     return tuple(torch.empty_like(t) for t in (w1, b1, wh, bh, wo, bo))
 
 
 def _entries_setup(ctx, inputs, output):
-    val, grp_ptr, items, w1, b1, wh, bh, wo, bo, n_layers, max_group = inputs
+    val, grp_ptr, items, w1, b1, wh, bh, wo, bo, n_layers, max_group, precision = inputs
     ctx.save_for_backward(val, grp_ptr, w1, b1, wh, bh, wo, bo)
-    ctx.cfg = (n_layers, max_group)
+    ctx.cfg = (n_layers, max_group, precision)
 
 
 def _entries_backward(ctx, dY):
     val, grp_ptr, w1, b1, wh, bh, wo, bo = ctx.saved_tensors
-    g = mlp_entries_bwd(val, grp_ptr, w1, b1, wh, bh, wo, bo, ctx.cfg[0], ctx.cfg[1], dY.contiguous())
-    return (None, None, None) + tuple(g) + (None, None)
+    g = mlp_entries_bwd(val, grp_ptr, w1, b1, wh, bh, wo, bo, ctx.cfg[0], ctx.cfg[1], ctx.cfg[2], dY.contiguous())
+    return (None, None, None) + tuple(g) + (None, None, None)
 
 
 mlp_entries_fwd.register_autograd(_entries_backward, setup_context=_entries_setup)
@@ -209,7 +209,7 @@ def rows_to_entries(dS: Tensor, grp_ptr: Tensor, ent_row: Tensor) -> Tensor:
     N, C = dS.shape
     G, E = grp_ptr.numel() - 1, ent_row.numel()
     dY = torch.empty(E, C, dtype=torch.float32, device=dS.device)
-    tot = torch.empty(C, dtype=torch.float32, device=dS.device)
+    tot = torch.empty(65 * C, dtype=torch.float32, device=dS.device)
     with ops._timed("rows_to_entries"):
         check(lib.gnan_rows_to_entries(ptr(dS), N, G, C, ptr(grp_ptr), E, ptr(ent_row), ptr(tot), ptr(dY), stream_handle()),
               "gnan_rows_to_entries")
@@ -234,9 +234,11 @@ def _e2r_backward(ctx, dS):
 entries_to_rows.register_autograd(_e2r_backward, setup_context=_e2r_setup)
 
 
-def feature_sums(cx: CompressedFeatures, w1, b1, wh, bh, wo, bo, n_layers) -> Tensor:
-    """S [N,C] = sum_k f_k(x[:,k]) from the compressed form; differentiable w.r.t. the weights."""
+def feature_sums(cx: CompressedFeatures, w1, b1, wh, bh, wo, bo, n_layers, precision="fp32") -> Tensor:
+    """S [N,C] = sum_k f_k(x[:,k]) from the compressed form; differentiable w.r.t. the weights. `precision` selects the
+    backward kernel (fp32 FFMA, or the tcgen05 3xTF32 kernel for H = 64, 3 layers, C <= 8); the forward is fp32."""
     if wo.shape[0] != cx.num_features:
         raise ValueError(f"compressed x has {cx.num_features} features, the model {wo.shape[0]}")
-    Y = mlp_entries_fwd(cx.val, cx.grp_ptr, cx.items, w1, b1, wh, bh, wo, bo, int(n_layers), cx.max_group)
+    from ._lib import PRECISIONS
+    Y = mlp_entries_fwd(cx.val, cx.grp_ptr, cx.items, w1, b1, wh, bh, wo, bo, int(n_layers), cx.max_group, PRECISIONS[precision])
     return entries_to_rows(Y, cx.grp_ptr, cx.csr_ptr, cx.csr_eid, cx.ent_grp, cx.ent_row)

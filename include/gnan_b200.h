@@ -96,23 +96,26 @@ int gnan_mlp_bwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *
  * The caller lists the distinct work as val[E] grouped by feature, group g owning entries [grp_ptr[g], grp_ptr[g+1]);
  * Y[e,:] = f_g(val[e]) and the weight gradients given dY[E,C] come back; how entries map to rows of S is the caller's
  * business (gnan_b200/sparse.py). items [n_items,2] = (group, 128-entry tile index inside the group): one CTA per item.
- * fp32 kernels; n_layers >= 2; no dropout (the sharing would be wrong with per-row masks). */
-size_t gnan_mlp_entries_workspace_bytes(int64_t max_group_entries, const gnan_mlp_params *p, int backward);
+ * Forward: fp32 kernels; backward: fp32 or the tcgen05 kernel (`precision`); n_layers >= 2; no dropout (the sharing would
+ * be wrong with per-row masks). */
+size_t gnan_mlp_entries_workspace_bytes(int64_t max_group_entries, const gnan_mlp_params *p, int backward, int precision);
 int gnan_mlp_entries_fwd(const float *val, const int64_t *grp_ptr /* [G+1] */, int64_t E, const int32_t *items, int64_t n_items,
                          const gnan_mlp_params *p, float *Y /* [E,C] */, gnan_stream_t stream);
 int gnan_mlp_entries_bwd(const float *val, const int64_t *grp_ptr, int64_t E, int64_t max_group_entries,
-                         const gnan_mlp_params *p, const float *dY /* [E,C] */, const gnan_mlp_grads *grads, void *workspace,
-                         size_t workspace_bytes, gnan_stream_t stream);
+                         const gnan_mlp_params *p, int precision /* backward may run on tcgen05 like gnan_mlp_bwd */,
+                         const float *dY /* [E,C] */, const gnan_mlp_grads *grads, void *workspace, size_t workspace_bytes,
+                         gnan_stream_t stream);
 
 /* Entry values <-> node rows (deterministic, no atomics). Group g's FIRST entry is the feature's baseline value, shared by
  * every row not listed among its exceptions:  S[r,:] = sum_g Y[base_g,:] + sum_{e in exceptions of row r} (Y[e,:] - Y[base_g(e),:]).
  * csr_ptr/csr_eid list the exception entries of each row, ent_grp[e] / ent_row[e] are an entry's group and row (-1 for a
- * baseline). S0 / dStot are [C] scratch outputs (sum of the baselines / of all dS rows). */
+ * baseline). S0 [C] and dStot [65*C] are scratch outputs (sum of the baselines; sum of all dS rows in the first C floats,
+ * slab partial sums behind). */
 int gnan_entries_to_rows(const float *Y /* [E,C] */, int64_t N, int32_t G, int32_t C, const int64_t *grp_ptr,
                          const int64_t *csr_ptr /* [N+1] */, const int64_t *csr_eid, const int32_t *ent_grp /* [E] */,
                          float *S0 /* [C] */, float *S /* [N,C] */, gnan_stream_t stream);
 int gnan_rows_to_entries(const float *dS /* [N,C] */, int64_t N, int32_t G, int32_t C, const int64_t *grp_ptr, int64_t E,
-                         const int64_t *ent_row /* [E] */, float *dStot /* [C] */, float *dY /* [E,C] */, gnan_stream_t stream);
+                         const int64_t *ent_row /* [E] */, float *dStot /* [65*C] */, float *dY /* [E,C] */, gnan_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Distance-table inputs. u[i,d] = 1/(1+d) for d < nbins-1, 0 for the unreachable bin (nbins-1);
@@ -205,10 +208,13 @@ int gnan_apsp_bfs_batched(const int32_t *rowptr /* [sumN+1] */, const int32_t *c
                           const int64_t *hop_off /* [B+1] */, int32_t B, uint8_t *hop, int32_t *cnt /* [sumN,nbins] or NULL */,
                           int32_t nbins, int32_t *overflow_flag, gnan_stream_t stream);
 
-/* same with the largest graph size given (sizes shared memory; graphs of up to 256 nodes) */
+/* same with host-side size hints: max_n = the largest graph (sizes shared memory; graphs of up to 256 nodes); total_nodes =
+ * node_off[B] and total_hop_bytes = hop_off[B] (both > 0: the unreachable / zero background of hop and cnt is written by two
+ * memsets at HBM speed instead of per-source store loops; 0 = unknown); max_level (optional, zero-initialised by the caller)
+ * receives the largest finite hop of the batch (atomicMax), which sizes the trimmed level table */
 int gnan_apsp_bfs_batched_n(const int32_t *rowptr, const int32_t *col, const int32_t *node_off, const int64_t *hop_off,
-                            int32_t B, int32_t max_n, uint8_t *hop, int32_t *cnt, int32_t nbins, int32_t *overflow_flag,
-                            gnan_stream_t stream);
+                            int32_t B, int32_t max_n, int64_t total_nodes, int64_t total_hop_bytes, uint8_t *hop, int32_t *cnt,
+                            int32_t nbins, int32_t *overflow_flag, int32_t *max_level, gnan_stream_t stream);
 
 /* reference-format converters (pre_process_datasets.py:112-121): fp32 node_distances / normalization_matrix <-> hops */
 int gnan_hops_to_reference(const uint8_t *hop, int64_t R, int64_t N, int64_t ld_hop, const int32_t *cnt, int32_t nbins,

@@ -826,6 +826,19 @@ def test_compressed_feature_sums_equal_dense_kernels(kind, N, K, H, C, L):
         for k in p:
             if p[k].numel():
                 assert G.rel_err(res[mode][1][k], q[k].grad.numpy()) < TOL, (mode, k)
+    if H == 64 and L == 3 and C <= 8:
+        # backward on the tcgen05 kernel in entries mode against the same kernel on the dense matrix: a row's activations (and
+        # ReLU masks) do not depend on which tile it sits in, so the two differ only by fp32 summation order
+        tc = {}
+        for mode in ("dense", "sparse"):
+            d = {k: v.to(DEV).requires_grad_(True) for k, v in p.items()}
+            args = (d["w1"], d["b1"], d["wh"], d["bh"], d["wo"], d["bo"], L)
+            S = ops.mlp(x.to(DEV), *args, precision="tf32x3") if mode == "dense" else sparse.feature_sums(cx, *args, precision="tf32x3")
+            (S * w.to(DEV)).sum().backward()
+            tc[mode] = {k: v.grad.cpu().numpy() for k, v in d.items()}
+        for k in p:
+            assert G.rel_err(tc["sparse"][k], tc["dense"][k]) < TOL, ("tcgen05 entries", k)
+            assert G.rel_err(tc["sparse"][k], q[k].grad.numpy()) < 1e-3, ("tcgen05 entries vs oracle (no kink filtering)", k)
 
 
 @pytest.mark.parametrize("name", ["gnanpy_tensor_graph", "models_tensor_graph", "gnanpy_tensor_graph_nonorm_disconnected"])
