@@ -525,21 +525,32 @@ def main():
             step(data_d)
         kt = ops.timing_results()
     ops.enable_timing(False)
-    # the same step with precision="fp32" (FFMA kernels, the 1e-5 parity mode), eager, for comparison with the headline mode
-    strict_ms = None
+    # the same step with precision="fp32" (FFMA kernels only, the 1e-5 parity mode) for comparison with the headline mode:
+    # captured and replayed like the headline when that is a CUDA graph, eager otherwise
+    strict_ms, strict_kt, strict_mode = None, None, None
     if args.precision != "fp32" and world == 1:
         model.precision = "fp32"
         for _ in range(3):
             step(data_d)
-        sev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 10))]
         ops.enable_timing(True)
+        for _ in range(min(args.steps, 10)):
+            flush.fill_(1)
+            step(data_d)
+        strict_kt = {k: v[1] / min(args.steps, 10) for k, v in ops.timing_results().items()}
+        ops.enable_timing(False)
+        run2, strict_mode = (lambda: step(data_d)), "eager"
+        if graphed is not None:
+            try:
+                cap2 = CapturedStep(lambda: loss_of(graphed[1]), opt, warmup=1)
+                run2, strict_mode = cap2, "cuda graph"
+            except Exception as exc:                                # pragma: no cover
+                print(f"[bench] strict-fp32 capture failed, timing it eagerly: {exc}", file=sys.stderr)
+        sev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 10))]
         for a, b in sev:
             flush.fill_(1)
-            a.record(); step(data_d); b.record()
+            a.record(); run2(); b.record()
         torch.cuda.synchronize()
-        strict_kt = {k: v[1] / len(sev) for k, v in ops.timing_results().items()}
-        ops.enable_timing(False)
-        strict_ms = float(np.median([a.elapsed_time(b) for a, b in sev]))   # median: an eager step (~40 launches) is exposed to host-side hiccups
+        strict_ms = float(np.median([a.elapsed_time(b) for a, b in sev]))
         model.precision = args.precision
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -630,7 +641,8 @@ def main():
             "gpu_launches": int(launches), "cuda_graph": graphed is not None,
             "strict_fp32": None if strict_ms is None else {
                 "ms_per_step": strict_ms, "value": total_units / (strict_ms / 1e3), "unit": wl.unit, "kernel_ms_per_step": strict_kt,
-                "note": "same step with precision='fp32' (FFMA kernels only, every golden case within 1.5e-6 of the reference), run eagerly; median step"},
+                "mode": strict_mode,
+                "note": "same step with precision='fp32' (FFMA kernels only, every golden case within 1.5e-6 of the reference); median step"},
             "roofline": roof,
             "dedup": None if cx is None else {
                 "entries": n_entries, "dense_evaluations": rows_local * wl.K, "exception_density": cx.density(),

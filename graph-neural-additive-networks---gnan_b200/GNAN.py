@@ -59,9 +59,37 @@ class _Base(nn.Module):
         """rho on a flat vector of scalar inputs -> [len(u), Cr]"""
         return ops.mlp(u.reshape(-1, 1), *self.rho.kernel_args(), precision=self.precision)
 
+    def _row_tables(self, holder, u):
+        """rho on the per-row inputs u [R,nbins] (GNAN.py:65-67: node_distances / normalization_matrix) -> [R*nbins, Cr].
+        1/((1+d) * cnt) takes few distinct values (small integers): rho runs once per distinct value, rows gather."""
+        if not self.dedup:
+            return self._table(u)
+        uq, inv, order, seg_ptr = _unique_inputs(holder, u)
+        if uq.numel() * 2 > u.numel():
+            return self._table(u)
+        return ops.gather_rows(self._table(uq), inv, order, seg_ptr)
+
     def print_rho_params(self):
         for name, param in self.rho.named_parameters():
             print(name, param)
+
+
+def _unique_inputs(holder, u):
+    """(unique values, inverse, sort order, segment offsets) of the per-row rho inputs u [R,nbins]; they depend only on the
+    BFS level sizes, so they are computed once per hop-data object and cached on it."""
+    cache = getattr(holder, "_gnan_b200_rho_unique", None)
+    if cache is not None and cache[0] == (u.shape, u.device):
+        return cache[1]
+    uq, inv = torch.unique(u.reshape(-1), return_inverse=True)
+    order = torch.sort(inv, stable=True).indices
+    seg_ptr = torch.zeros(uq.numel() + 1, dtype=torch.int64, device=u.device)
+    seg_ptr[1:] = torch.cumsum(torch.bincount(inv, minlength=uq.numel()), 0)
+    out = (uq.contiguous(), inv.contiguous(), order.contiguous(), seg_ptr)
+    try:
+        holder._gnan_b200_rho_unique = ((u.shape, u.device), out)
+    except Exception:
+        pass
+    return out
 
 
 class TensorGNAN(_Base):
@@ -90,7 +118,7 @@ class TensorGNAN(_Base):
         S = self._feature_sums(*self._features(inputs))                              # [N,C]   GNAN.py:57-62 (+ :73 by linearity)
         if self.normalize_rho:                                                       # GNAN.py:65-67: rho(nd / norm)
             u = ops.rho_table_inputs(hd.nbins, dev, cnt=hd.level_counts)             # [R,nbins]
-            T = self._table(u).view(hd.rows, hd.nbins, self.out_channels)
+            T = self._row_tables(hd, u).view(hd.rows, hd.nbins, self.out_channels)
             out = ops.aggregate_rows(hd.hop, T, S, per_row=True)
         else:
             T = self._table(ops.rho_table_inputs(hd.nbins, dev))                     # [nbins,C]
@@ -109,7 +137,7 @@ class TensorGNAN(_Base):
         S = self._feature_sums(*self._features(pk))
         if self.normalize_rho:
             u = ops.rho_table_inputs(pk.nbins, dev, cnt=pk.level_counts)
-            T = self._table(u).view(S.shape[0], pk.nbins, self.out_channels)
+            T = self._row_tables(pk, u).view(S.shape[0], pk.nbins, self.out_channels)
             return ops.aggregate_blockdiag(pk.hop, pk.hop_off, pk.node_off, T, S, per_row=True, reduce_graph=self.is_graph_task)
         T = self._table(ops.rho_table_inputs(pk.nbins, dev))
         return ops.aggregate_blockdiag(pk.hop, pk.hop_off, pk.node_off, T, S, reduce_graph=self.is_graph_task)

@@ -102,7 +102,54 @@ __global__ void rows_to_baselines_kernel(const float *__restrict__ dS, int G, in
     if (threadIdx.x == 0) dY[e0 * C + c] = dStot[c] - red[0];
 }
 
+// out[s,:] = sum over k in [seg_ptr[s], seg_ptr[s+1]) of src[order[k],:]; one warp per (segment, channel block of 32 lanes is
+// not needed: lanes stride over the segment's elements, one channel at a time), fixed order -> deterministic
+__global__ void gather_segment_sum_kernel(const float *__restrict__ src, const int64_t *__restrict__ order,
+                                          const int64_t *__restrict__ seg_ptr, int64_t nseg, int C, float *__restrict__ out)
+{
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // one warp per (segment, channel)
+    const int lane = threadIdx.x & 31;
+    if (w >= nseg * C) return;
+    const int64_t sg = w / C;
+    const int c = (int)(w % C);
+    const int64_t k0 = seg_ptr[sg], k1 = seg_ptr[sg + 1];
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;                              // four independent gathers in flight per lane
+    int64_t k = k0 + lane;
+    if (order) {
+        for (; k + 96 < k1; k += 128) {
+            s0 += src[order[k] * C + c];
+            s1 += src[order[k + 32] * C + c];
+            s2 += src[order[k + 64] * C + c];
+            s3 += src[order[k + 96] * C + c];
+        }
+        for (; k < k1; k += 32) s0 += src[order[k] * C + c];
+    } else {                                                                     // rows already in segment order
+        for (; k + 96 < k1; k += 128) {
+            s0 += src[k * C + c];
+            s1 += src[(k + 32) * C + c];
+            s2 += src[(k + 64) * C + c];
+            s3 += src[(k + 96) * C + c];
+        }
+        for (; k < k1; k += 32) s0 += src[k * C + c];
+    }
+    float s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[w] = s;
+}
+
 }  // namespace
+
+extern "C" int gnan_gather_segment_sum(const float *src, const int64_t *order, const int64_t *seg_ptr, int64_t nseg, int32_t C,
+                                       float *out, gnan_stream_t stream)
+{
+    GNAN_REQUIRE(nseg >= 0 && C >= 1, "gather_segment_sum: bad sizes");
+    if (nseg == 0) return GNAN_OK;
+    GNAN_REQUIRE(src && seg_ptr && out, "gather_segment_sum: NULL pointer");
+    gather_segment_sum_kernel<<<(unsigned)ceil_div64(nseg * C * 32, 256), 256, 0, (cudaStream_t)stream>>>(src, order, seg_ptr, nseg, C, out);
+    GNAN_LAUNCH_OK();
+    return GNAN_OK;
+}
 
 extern "C" int gnan_entries_to_rows(const float *Y, int64_t N, int32_t G, int32_t C, const int64_t *grp_ptr,
                                     const int64_t *csr_ptr, const int64_t *csr_eid, const int32_t *ent_grp, float *S0,

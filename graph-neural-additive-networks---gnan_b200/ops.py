@@ -323,6 +323,42 @@ def aggregate_blockdiag(hop, hop_off, node_off, T, S, rscale=None, per_row=False
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# row gather with a deterministic backward
+# ---------------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("gnan_b200::gather_segment_sum", mutates_args=())
+def gather_segment_sum(src: Tensor, order: Optional[Tensor], seg_ptr: Tensor) -> Tensor:
+    lib = load()
+    src = _f32(src, "src")
+    nseg, C = seg_ptr.numel() - 1, src.shape[1]
+    out = torch.empty(nseg, C, dtype=torch.float32, device=src.device)
+    check(lib.gnan_gather_segment_sum(ptr(src), ptr(order), ptr(seg_ptr), nseg, C, ptr(out), stream_handle()), "gnan_gather_segment_sum")
+    return out
+
+
+@gather_segment_sum.register_fake
+def _(src, order, seg_ptr):
+    return src.new_empty(seg_ptr.numel() - 1, src.shape[1])
+
+
+class _GatherRows(torch.autograd.Function):
+    """T = Tq[inv]; backward = fixed-order segment sums over a precomputed sort of inv (no atomics)."""
+
+    @staticmethod
+    def forward(ctx, tq, inv, order, seg_ptr):
+        ctx.save_for_backward(order, seg_ptr)
+        return tq.index_select(0, inv)
+
+    @staticmethod
+    def backward(ctx, dT):
+        order, seg_ptr = ctx.saved_tensors
+        return gather_segment_sum(dT.index_select(0, order), None, seg_ptr), None, None, None    # coalesced copy, then contiguous segments
+
+
+def gather_rows(tq, inv, order, seg_ptr):
+    return _GatherRows.apply(tq, inv, order, seg_ptr)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # table inputs (no autograd: functions of the integer level counts only)
 # ---------------------------------------------------------------------------------------------------------------------
 def rho_table_inputs(nbins: int, device, cnt: Optional[Tensor] = None, raw: bool = False) -> Tensor:

@@ -117,6 +117,12 @@ int gnan_entries_to_rows(const float *Y /* [E,C] */, int64_t N, int32_t G, int32
 int gnan_rows_to_entries(const float *dS /* [N,C] */, int64_t N, int32_t G, int32_t C, const int64_t *grp_ptr, int64_t E,
                          const int64_t *ent_row /* [E] */, float *dStot /* [65*C] */, float *dY /* [E,C] */, gnan_stream_t stream);
 
+/* out[s,:] = sum_{k in [seg_ptr[s], seg_ptr[s+1])} src[order[k],:]  — the deterministic backward of a row gather T = Tq[inv]
+ * (the per-row rho inputs 1/((1+d)*cnt) of GNAN.py:65-67 take few distinct values: rho runs once per distinct value). */
+int gnan_gather_segment_sum(const float *src /* [M,C] */, const int64_t *order /* [M], or NULL = rows already in segment order */,
+                            const int64_t *seg_ptr /* [nseg+1] */,
+                            int64_t nseg, int32_t C, float *out /* [nseg,C] */, gnan_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Distance-table inputs. u[i,d] = 1/(1+d) for d < nbins-1, 0 for the unreachable bin (nbins-1);
  * with cnt != NULL divided by cnt[i,d] (GNAN.py:65-66: node_distances / normalization_matrix).
