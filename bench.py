@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Benchmark of the GNAN hot path (BASELINE.json metric: fwd+bwd nodes/s on node tasks, graphs/s on graph tasks).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cora|pubmed|mutag] [--precision tf32x3|fp32|tf32]
-                    [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cora|pubmed|arxiv|mutag|mol] [--precision tf32x3|fp32|tf32]
+                    [--dedup on|off] [--impl reference]
 
 Default workload = BASELINE.json configs[1]: TensorGNAN (GNAN.py:9-79) node classification on a Cora-shaped synthetic
 graph (2708 nodes, 1433 features + the constant column, 7 classes, hidden 64, 3 layers), dense all-pairs hop distances.
@@ -10,10 +10,16 @@ A step is forward + loss + backward + Adam step (trainer.py:48-67). Other worklo
 with an all-gather of S when N > 1), `mutag` (configs[0]: 4337 Mutagenicity-shaped graphs per step in packed
 block-diagonal form, data-parallel with one gradient all-reduce when N > 1).
 
+Dropout is 0 (parity configuration), so by default (`--dedup on`) the shape functions run on the compressed
+feature matrix (gnan_b200.sparse: one evaluation per distinct (feature, value) pair; exact); `--dedup off` runs the dense
+kernels on every (node, feature) pair, which is what training with dropout > 0 uses. The compressed form is built once per
+dataset, like the hop matrix, and is what the e2e leg copies from host memory instead of the dense x.
+
 One JSON line on stdout (rank 0). `value` times the step with inputs resident in HBM (CUDA events per step, L2 flushed
 between steps); `e2e` times the same step through the module API from pinned HOST buffers (features, hop bytes, level
-counts copied every step, loss read back every step). `roofline` describes the dominant kernel (the grouped shape-MLP
-backward), timed live with CUDA events on the launching stream. `cpu_baseline` / `--impl reference` time the oracle's
+counts copied every step, loss read back every step). `roofline` describes the dominant kernel of the step (the library op
+with the largest CUDA-event time, measured live on the launching stream), with FLOPs counted on the evaluations actually
+executed. `cpu_baseline` / `--impl reference` time the oracle's
 port of the reference's own CPU path (oracle/gnan_port.py: the reference is pure Python and cannot travel to the GPU
 box) with all host threads.
 """
@@ -194,7 +200,7 @@ def workload_config(wl, where, world=1):
            "mutag": "data-parallel graphs, one fused gradient all-reduce per step" if world > 1 else "single GPU",
            "mol": "data-parallel graphs, one fused gradient all-reduce per step" if world > 1 else "single GPU"}[wl.name]
     return {"workload": wl.desc, "nodes": wl.n, "features": wl.K, "classes": wl.C, "hidden": H, "n_layers": L,
-            "step": "forward + loss + backward + Adam", "normalize_rho": True,
+            "step": "forward + loss + backward + Adam", "normalize_rho": True, "dropout": 0.0,
             "timing": "CUDA events per step; 256 MiB L2 flush between timed steps" if where == "gpu" else "perf_counter",
             "parallelism": par}
 
@@ -373,7 +379,7 @@ def main():
         yl_d = wl.y[b0:e0].to(dev)[idx_d]
         n_train = float(wl.train_mask.sum())
         x_d = x_h.to(dev)
-        cx = compress_features(x_d) if (model.dedup and not sharded) else None         # once per dataset, like the hop matrix
+        cx = compress_features(x_d) if model.dedup else None                           # once per dataset (per row shard), like the hop matrix
         cx_h = None if cx is None else cx.to("cpu").pin_memory()
         data_d = SimpleNamespace(x=x_d, hop_data=hd, x_compressed=cx)
         x_bytes = x_h.numel() * 4 if cx is None else cx.nbytes()
@@ -388,7 +394,7 @@ def main():
 
         def loss_of(data):
             if sharded:
-                out = gdist.row_sharded_forward(model, data.x, data.hop_data, sizes)
+                out = gdist.row_sharded_forward(model, data.x, data.hop_data, sizes, x_compressed=data.x_compressed)
             else:
                 out = model.forward(data)
             return loss_fn(out.index_select(0, idx_d), yl_d) / n_train
@@ -460,7 +466,13 @@ def main():
     # the sharded / data-parallel steps issue NCCL collectives). Falls back to eager execution if capture is not possible.
     graphed = None
     launches_per_step = None
-    capturable = (wl.kind == "node" and not sharded) or (wl.kind == "graph" and not in_step_apsp and world == 1)
+    # collectives (row-sharded all-gather / reduce-scatter, gradient all-reduce) are captured with the kernels
+    capturable = wl.kind == "node" or (wl.kind == "graph" and not in_step_apsp)
+    after_bwd = None
+    if sharded:
+        after_bwd = lambda: gdist.allreduce_gradients(model.parameters())
+    elif wl.kind == "graph" and world > 1:
+        after_bwd = lambda: gdist.allreduce_gradients(model.parameters(), average=True)
     if not args.no_cuda_graph and capturable:
         try:
             scx = None if cx is None else cx.to(dev).clone_tensors()
@@ -471,7 +483,7 @@ def main():
                 static_in = PackedBatch(None if cx is not None else data_d.x.clone(), data_d.hop.clone(), data_d.hop_off.clone(),
                                         data_d.node_off.clone(), data_d.level_counts.clone(), data_d.y.clone(), data_d.max_nodes)
                 static_in.x_compressed = scx
-            cap = CapturedStep(lambda: loss_of(static_in), opt, warmup=2)              # gnan_b200.trainer: the public API
+            cap = CapturedStep(lambda: loss_of(static_in), opt, warmup=2, after_backward=after_bwd)   # gnan_b200.trainer: the public API
             g, static_loss, launches_per_step = cap.graph, cap.loss, cap.kernel_launches
             graphed = (g, static_in, static_loss)
             for _ in range(3):
@@ -541,7 +553,7 @@ def main():
         run2, strict_mode = (lambda: step(data_d)), "eager"
         if graphed is not None:
             try:
-                cap2 = CapturedStep(lambda: loss_of(graphed[1]), opt, warmup=1)
+                cap2 = CapturedStep(lambda: loss_of(graphed[1]), opt, warmup=1, after_backward=after_bwd)
                 run2, strict_mode = cap2, "cuda graph"
             except Exception as exc:                                # pragma: no cover
                 print(f"[bench] strict-fp32 capture failed, timing it eagerly: {exc}", file=sys.stderr)
@@ -615,10 +627,13 @@ def main():
             achieved = alg / (dur_ms / 1e3) / 1e12 if dur_ms > 0 else 0.0
             entries = "entries" in dom
             roof = {"kernel": {"mlp_bwd": "mlp_tc_bwd_kernel" if args.precision != "fp32" else "mlp_bwd_kernel", "mlp_fwd": "mlp_tc_fwd_kernel" if args.precision != "fp32" else "mlp_fwd_kernel",
-                               "mlp_entries_bwd": "mlp_bwd_kernel (entries mode)", "mlp_entries_fwd": "mlp_fwd_kernel (entries mode)"}.get(dom, dom),
+                               "mlp_entries_bwd": ("mlp_tc_bwd_kernel" if args.precision != "fp32" else "mlp_bwd_kernel") + " (entries mode)",
+                               "mlp_entries_fwd": "mlp_fwd_kernel (entries mode)"}.get(dom, dom),
                     "bound": "tensor", "achieved": achieved, "peak": tflops, "unit": "TFLOP/s", "frac": achieved / tflops, "traffic": traffic,
                     "peak_source": peak_src, "algorithmic_flops_per_launch": alg, "evaluations_per_launch": evals,
-                    "pipe": ("fp32 FFMA (CUDA cores), one 128-row tile per (feature, entry tile); most tiles are partly filled" if entries else
+                    "pipe": ("tcgen05 kind::tf32 3-term split, one 128-row tile per (feature, entry tile); tiles are partly filled (mean 35 of 128 rows at Cora shape)"
+                             if entries and "bwd" in dom and args.precision != "fp32" else
+                             "fp32 FFMA (CUDA cores), one 128-row tile per (feature, entry tile); tiles are partly filled" if entries else
                              "tcgen05 kind::tf32, 3-term split: executed tensor FLOPs = 3-4x algorithmic" if args.precision == "tf32x3" else
                              "tcgen05 kind::tf32" if args.precision == "tf32" else "fp32 FFMA (CUDA cores)")}
         else:
@@ -657,7 +672,13 @@ def main():
                                     "sample": f"{n} steps, {w} warm-up ({ms:.1f} ms each): {note}; oracle/gnan_port.py on torch CPU"}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # CUDA graphs that captured NCCL collectives keep the communicator referenced: tearing the process group down with them
+        # alive blocks (observed: the ranks hung in destroy_process_group after the JSON line was out). Everything is measured
+        # and printed: synchronise, meet at a barrier, and leave without running the teardown.
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

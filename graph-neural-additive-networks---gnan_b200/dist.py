@@ -108,11 +108,12 @@ def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None):
 # ---------------------------------------------------------------------------------------------------------------------
 # row-sharded node-level forward
 # ---------------------------------------------------------------------------------------------------------------------
-def row_sharded_forward(model, x_local: torch.Tensor, hop_data, sizes: Sequence[int], group=None) -> torch.Tensor:
+def row_sharded_forward(model, x_local: torch.Tensor, hop_data, sizes: Sequence[int], group=None, x_compressed=None) -> torch.Tensor:
     """out[V_r] for this rank's node block.
 
     model     a gnan_b200 GNAN / TensorGNAN module (replicated parameters)
-    x_local   [|V_r|, K] features of the owned nodes
+    x_local   [|V_r|, K] features of the owned nodes (may be None when x_compressed is given)
+    x_compressed  optional sparse.CompressedFeatures of x_local (used when dropout is off, like in the single-GPU modules)
     hop_data  preprocess.HopData holding the owned hop ROWS (all N columns) and their level counts
     sizes     block sizes of all ranks (sum = N)
 
@@ -120,13 +121,15 @@ def row_sharded_forward(model, x_local: torch.Tensor, hop_data, sizes: Sequence[
     MLP backward on the local rows only; call allreduce_gradients(model.parameters()) afterwards.
     """
     from . import ops
-    s_local = model._feature_sums(x_local)                                       # [|V_r|, C]
+    dev = hop_data.hop.device
+    cx = x_compressed if (x_compressed is not None and model._dedup_ok()) else None     # sparse.compress_features(x_local), built once
+    s_local = model._feature_sums(x_local, cx)                                  # [|V_r|, C]
     s_full = all_gather_rows(s_local, sizes, group)                             # [N, C]
     flavor_input_norm = model.__class__.__module__.endswith(".GNAN") and model.__class__.__name__ == "TensorGNAN"
     if model.normalize_rho and flavor_input_norm:                               # GNAN.py:65-67
-        u = ops.rho_table_inputs(hop_data.nbins, x_local.device, cnt=hop_data.level_counts)
-        T = model._table(u).view(hop_data.rows, hop_data.nbins, -1)
+        u = ops.rho_table_inputs(hop_data.nbins, dev, cnt=hop_data.level_counts)
+        T = model._row_tables(hop_data, u).view(hop_data.rows, hop_data.nbins, -1)
         return ops.aggregate_rows(hop_data.hop, T, s_full, per_row=True)
-    T = model._table(ops.rho_table_inputs(hop_data.nbins, x_local.device))
+    T = model._table(ops.rho_table_inputs(hop_data.nbins, dev))
     rs = ops.level_rscale(hop_data.level_counts) if model.normalize_rho else None
     return ops.aggregate_rows(hop_data.hop, T, s_full, rscale=rs)

@@ -174,8 +174,11 @@ class CapturedStep:
     Refresh the static input tensors in place (`copy_`) between replays to train on new values of the same shape.
     """
 
-    def __init__(self, loss_closure, optimizer, warmup=3):
-        self._closure, self._opt = loss_closure, optimizer
+    def __init__(self, loss_closure, optimizer, warmup=3, after_backward=None):
+        """after_backward: optional callable run between backward and the optimizer step INSIDE the captured step, e.g.
+        `lambda: dist.allreduce_gradients(model.parameters(), average=True)` for data-parallel training: NCCL collectives
+        are captured like kernels (every rank must capture the same sequence)."""
+        self._closure, self._opt, self._after = loss_closure, optimizer, after_backward
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):                           # warm-up off the capture stream: allocator + optimizer state
@@ -188,7 +191,8 @@ class CapturedStep:
         from ._lib import load
         lib = load()
         n0 = lib.gnan_launch_count()
-        with torch.cuda.graph(self.graph):
+        # thread_local: the NCCL watchdog thread polls CUDA events while this thread captures
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local" if after_backward is not None else "global"):
             self.loss = self._eager()
         self.kernel_launches = int(lib.gnan_launch_count() - n0)     # gnan_b200 kernels per replay (the counter is host-side)
 
@@ -196,6 +200,8 @@ class CapturedStep:
         self._opt.zero_grad(set_to_none=True)
         loss = self._closure()
         loss.backward()
+        if self._after is not None:
+            self._after()
         self._opt.step()
         return loss
 
