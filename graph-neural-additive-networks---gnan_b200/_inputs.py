@@ -7,15 +7,26 @@ import torch
 from .preprocess import HopData, from_reference_format
 
 
+AUTO_DEDUP_MIN_EVALUATIONS = 1 << 16     # below this many (row, feature) pairs the dense kernels are a single small launch
+
+
 def compressed_of(holder, x, device, enabled=True):
-    """CompressedFeatures of `holder` (its `.x_compressed`, else built from `x` once and cached on the object), or None when
-    the dense kernels should be used (disabled, or too many distinct values: sparse.compress_features returns None)."""
+    """CompressedFeatures to use for `holder`, or None for the dense kernels.
+
+    `holder.x_compressed` (built by the caller with sparse.compress_features) is always honoured. Otherwise the compressed
+    form is built from `x` on first use and cached on the object, but only where that pays: objects that persist across steps
+    (the reference's Data objects, PackedDataset.as_batch()) and carry at least AUTO_DEDUP_MIN_EVALUATIONS (row, feature)
+    pairs. A PackedBatch made per step (apsp_batched, PackedDataset.batch) is never analysed implicitly: the column modes and
+    sorts (plus a few host syncs) would cost more than they save."""
     if not enabled:
         return None
     cx = getattr(holder, "x_compressed", None)
-    if cx is None and getattr(holder, "_gnan_b200_no_dedup", False):
-        return None                      # a throw-away batch object: building (sorts, syncs) would cost more than it saves
     if cx is None and x is not None:
+        from .preprocess import PackedBatch
+        if isinstance(holder, PackedBatch) and not getattr(holder, "_gnan_b200_persistent", False):
+            return None
+        if x.shape[0] * x.shape[1] < AUTO_DEDUP_MIN_EVALUATIONS:
+            return None
         key = (x.data_ptr(), x._version, tuple(x.shape))
         cache = getattr(holder, "_gnan_b200_cx_cache", None)
         if cache is not None and cache[0] == key:

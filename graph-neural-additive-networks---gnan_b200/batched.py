@@ -63,7 +63,6 @@ class TensorGNAN(_Base):
         else:
             dev = self._device()
             pk = pack_dense(x_batch.to(dev), dist_batch.to(dev), batch_vector.to(dev))
-            pk._gnan_b200_no_dedup = True
         dev = self._device()
         if pk.hop.device != dev:
             pk = pk.to(dev)

@@ -114,6 +114,7 @@ class PackedDataset:
         """The whole dataset as one batch (no copy; the same object every time, so per-input caches stick to it)."""
         if getattr(self, "_whole", None) is None:
             self._whole = PackedBatch(self.x, self.hop, self.hop_off, self.node_off, self.level_counts, self.y, self.max_nodes)
+            self._whole._gnan_b200_persistent = True     # lives as long as the dataset: feature compression is cached on it
         return self._whole
 
     def batch(self, ids) -> PackedBatch:
@@ -129,10 +130,8 @@ class PackedDataset:
         cells = _ranges(self.hop_off[:-1][ids], n * n)
         hop = self.hop[cells] if cells.numel() else torch.zeros(1, dtype=torch.uint8, device=dev)
         y = None if self.y is None else self.y[ids]
-        pk = PackedBatch(self.x[rows], hop, hop_off, node_off.to(torch.int32), self.level_counts[rows], y,
-                         int(n.max().item()) if ids.numel() else 1)
-        pk._gnan_b200_no_dedup = True                # a fresh object per mini-batch: no feature compression (see _inputs.compressed_of)
-        return pk
+        return PackedBatch(self.x[rows], hop, hop_off, node_off.to(torch.int32), self.level_counts[rows], y,
+                           int(n.max().item()) if ids.numel() else 1)
 
     def loader(self, batch_size: int, shuffle: bool = False, generator: Optional[torch.Generator] = None,
                drop_last: bool = False) -> Iterator[PackedBatch]:

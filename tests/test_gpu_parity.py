@@ -844,19 +844,20 @@ def test_compressed_feature_sums_equal_dense_kernels(kind, N, K, H, C, L):
 @pytest.mark.parametrize("name", ["gnanpy_tensor_graph", "models_tensor_graph", "gnanpy_tensor_graph_nonorm_disconnected",
                                   "gnanpy_tensor_node", "gnanpy_tensor_node_directed_nobias"])
 def test_modules_dedup_on_and_off_match_reference_golden(name):
-    """One-hot golden cases run through the compressed path by default; both settings must reproduce the reference."""
+    """Golden cases through the compressed-feature path (explicit `x_compressed`: these graphs are far below the size where
+    the modules build it on their own) and through the dense kernels; both must reproduce the reference."""
+    from gnan_b200.sparse import compress_features
     z = G.load(name)
     outs = {}
     for dedup in (True, False):
         m = build_module(z, DEV).eval()
         m.dedup = dedup
-        data = SimpleNamespace(x=torch.tensor(z["x"]), edge_index=torch.tensor(z["edge_index"]),
-                               node_distances=torch.tensor(z["node_distances"]),
-                               normalization_matrix=torch.tensor(z["normalization_matrix"]))
+        x = torch.tensor(z["x"])
+        data = SimpleNamespace(x=x, edge_index=torch.tensor(z["edge_index"]), node_distances=torch.tensor(z["node_distances"]),
+                               normalization_matrix=torch.tensor(z["normalization_matrix"]),
+                               x_compressed=compress_features(x.to(DEV), max_density=None))
         out = m.forward(data)
         (out * torch.tensor(z["out_weight"], device=DEV)).sum().backward()
-        if "graph" in name:                                      # one-hot x: compressed; the node cases have 50 % dense x
-            assert (getattr(data, "_gnan_b200_cx_cache", None) is not None) == dedup
         assert G.rel_err(out.detach().cpu().numpy(), z["out"]) < TOL
         check_grads(z, grads_of(m.fs), z["grad_fs"], "fs")
         check_grads(z, grads_of(m.rho), z["grad_rho"], "rho")
@@ -864,12 +865,17 @@ def test_modules_dedup_on_and_off_match_reference_golden(name):
     assert G.rel_err(outs[True].cpu().numpy(), outs[False].cpu().numpy()) < 1e-6
 
 
-def test_dropout_training_uses_the_dense_kernels():
-    """Per-row dropout masks make rows with equal inputs differ: with dropout active the compressed path must not be used."""
+def test_dropout_training_uses_the_dense_kernels(monkeypatch):
+    """Per-row dropout masks make rows with equal inputs differ: with dropout active the compressed path must not be used.
+    Also: the modules compress a large enough persistent input on their own, and never a small one."""
+    from gnan_b200 import sparse
     from gnan_b200.GNAN import TensorGNAN
     from gnan_b200.preprocess import apsp
+    calls = []
+    real = sparse.feature_sums
+    monkeypatch.setattr(sparse, "feature_sums", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
     rng = np.random.default_rng(2)
-    n, K = 200, 12
+    n, K = 6000, 12                                                       # 72 000 (row, feature) pairs: above the auto threshold
     x = _compressible_x(rng, n, K, "onehot")
     data = SimpleNamespace(x=x, hop_data=apsp(torch.tensor(random_graph(rng, n, 2.5)), n, device=DEV))
     torch.manual_seed(0)
@@ -877,11 +883,18 @@ def test_dropout_training_uses_the_dense_kernels():
     m.fs.xavier_normal_(1.0); m.rho.xavier_normal_(1.0)
     m.train()
     a = m.forward(data)
-    assert getattr(data, "_gnan_b200_cx_cache", None) is None            # nothing was compressed
+    assert not calls and getattr(data, "_gnan_b200_cx_cache", None) is None   # dropout active: dense kernels, nothing compressed
     m.eval()
     b = m.forward(data)
-    assert data._gnan_b200_cx_cache[1] is not None                        # eval: shared evaluations
+    assert len(calls) == 1 and data._gnan_b200_cx_cache[1] is not None    # eval: built once, shared evaluations
+    m.forward(data)
+    assert len(calls) == 2
     m.dedup = False
     c = m.forward(data)
+    assert len(calls) == 2
     assert G.rel_err(b.detach().cpu().numpy(), c.detach().cpu().numpy()) < 1e-6
     assert G.rel_err(a.detach().cpu().numpy(), c.detach().cpu().numpy()) > 1e-3   # dropout really was active
+    small = SimpleNamespace(x=x[:100], hop_data=apsp(torch.tensor(random_graph(rng, 100, 2.5)), 100, device=DEV))
+    m.dedup = True
+    m.forward(small)
+    assert len(calls) == 2 and getattr(small, "_gnan_b200_cx_cache", None) is None   # too small to be worth analysing
