@@ -564,6 +564,40 @@ def main():
         torch.cuda.synchronize()
         strict_ms = float(np.median([a.elapsed_time(b) for a, b in sev]))
         model.precision = args.precision
+    # the same step on the DENSE kernels (every (node, feature) pair evaluated: what training with dropout > 0 runs), so that
+    # the line carries both regimes; eager per-kernel pass + CUDA-graph replay like the headline
+    dense = None
+    if cx is not None and world == 1 and wl.kind == "node":
+        model.dedup = False
+        dense_in = SimpleNamespace(x=x_d, hop_data=data_d.hop_data, x_compressed=None)
+        for _ in range(3):
+            step(dense_in)
+        ops.enable_timing(True)
+        for _ in range(min(args.steps, 10)):
+            flush.fill_(1)
+            step(dense_in)
+        dkt = {k: v[1] / min(args.steps, 10) for k, v in ops.timing_results().items()}
+        ops.enable_timing(False)
+        run3, dmode = (lambda: step(dense_in)), "eager"
+        if graphed is not None:
+            try:
+                cap3 = CapturedStep(lambda: loss_of(dense_in), opt, warmup=1)
+                run3, dmode = cap3, "cuda graph"
+            except Exception as exc:                                # pragma: no cover
+                print(f"[bench] dense-kernel capture failed, timing it eagerly: {exc}", file=sys.stderr)
+        dev_ = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 10))]
+        for a, b in dev_:
+            flush.fill_(1)
+            a.record(); run3(); b.record()
+        torch.cuda.synchronize()
+        dms = float(np.median([a.elapsed_time(b) for a, b in dev_]))
+        dflops = 2.0 * flops_per_eval(wl.C) * rows_local * wl.K
+        dbwd = dkt.get("mlp_bwd", 0.0)
+        dense = {"ms_per_step": dms, "value": wl.units_per_step / (dms / 1e3), "unit": wl.unit, "mode": dmode, "kernel_ms_per_step": dkt,
+                 "dominant_kernel": "mlp_tc_bwd_kernel" if args.precision != "fp32" else "mlp_bwd_kernel",
+                 "dominant_kernel_tflops": dflops / (dbwd / 1e3) / 1e12 if dbwd > 0 else None,
+                 "note": "--dedup off: all nodes x features evaluations executed (the regime of dropout training)"}
+        model.dedup = True
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -611,6 +645,8 @@ def main():
 
     if rank == 0:
         hbm, tflops, peak_src = measured_peaks()
+        if dense is not None and dense.get("dominant_kernel_tflops"):
+            dense["dominant_kernel_frac_of_bf16_peak"] = dense["dominant_kernel_tflops"] / tflops
         # ---- roofline of the DOMINANT kernel of this step (largest CUDA-event time among the library's ops) ----------------
         per_step = {k: v[1] / args.steps for k, v in kt.items()}
         dom = max(per_step, key=per_step.get) if per_step else "mlp_bwd"
@@ -659,6 +695,7 @@ def main():
                 "mode": strict_mode,
                 "note": "same step with precision='fp32' (FFMA kernels only, every golden case within 1.5e-6 of the reference); median step"},
             "roofline": roof,
+            "dense_kernels": dense,
             "dedup": None if cx is None else {
                 "entries": n_entries, "dense_evaluations": rows_local * wl.K, "exception_density": cx.density(),
                 "note": "rows with equal values in a feature column share one shape-function evaluation (exact; dropout is 0 here); "

@@ -898,3 +898,30 @@ def test_dropout_training_uses_the_dense_kernels(monkeypatch):
     m.dedup = True
     m.forward(small)
     assert len(calls) == 2 and getattr(small, "_gnan_b200_cx_cache", None) is None   # too small to be worth analysing
+
+
+def test_compressed_features_edge_cases():
+    """No exceptions at all (every column constant), a single row, and a column whose mode is not zero."""
+    from gnan_b200 import ops, sparse
+    gen = torch.Generator().manual_seed(3)
+    K, H, C, L = 4, 32, 2, 3
+    p = dict(w1=torch.randn(K, H, generator=gen), b1=torch.randn(K, H, generator=gen), wh=torch.randn(1, K, H, H, generator=gen) / 6,
+             bh=torch.randn(1, K, H, generator=gen) * 0.1, wo=torch.randn(K, C, H, generator=gen) / 6, bo=torch.randn(K, C, generator=gen))
+    cases = {"all_constant": torch.tensor([[1.0, 0.0, -2.0, 0.5]]).repeat(50, 1),
+             "single_row": torch.tensor([[0.3, 0.0, 1.0, 0.0]]),
+             "nonzero_mode": torch.cat([torch.full((40, K), 3.0), torch.zeros(3, K)])}
+    for name, x in cases.items():
+        cx = sparse.compress_features(x.to(DEV), max_density=None)
+        assert torch.equal(cx.to_dense().cpu(), x), name
+        if name == "all_constant":
+            assert cx.num_entries == K and cx.csr_eid.numel() == 0
+        res = {}
+        for mode in ("dense", "sparse"):
+            d = {k: v.to(DEV).requires_grad_(True) for k, v in p.items()}
+            args = (d["w1"], d["b1"], d["wh"], d["bh"], d["wo"], d["bo"], L)
+            S = ops.mlp(x.to(DEV), *args) if mode == "dense" else sparse.feature_sums(cx, *args)
+            S.square().sum().backward()
+            res[mode] = (S.detach().cpu().numpy(), {k: v.grad.cpu().numpy() for k, v in d.items()})
+        assert G.rel_err(res["sparse"][0], res["dense"][0]) < TOL, name
+        for k in p:
+            assert G.rel_err(res["sparse"][1][k], res["dense"][1][k]) < TOL, (name, k)
