@@ -289,8 +289,9 @@ mlp_tc_fwd_kernel(TcArgs a, int KC, float *__restrict__ Spart)
 }
 
 // ---- backward ---------------------------------------------------------------------------------------------------------
-// CTA <-> (feature g, row chunk), 8 row warps + 1 MMA warp. A row warp owns 32 rows (one TMEM lane quadrant) x 32 of the
-// 64 hidden units (warps w and w+4 share a quadrant). Per 128-row tile:
+// CTA <-> (feature g, row chunk), 16 row warps + 1 MMA warp. A row warp owns 32 rows (one TMEM lane quadrant) x 16 of the
+// 64 hidden units (warps w, w+4, w+8, w+12 share a quadrant). In entries mode (TcArgs::grp_ptr) the rows are the group's own
+// entries instead of column g of the dense matrix. Per 128-row tile:
 //   gen    a0 = relu(x w1 + b1) -> TMEM A (hi|lo)  and  -> smem sH (K-major over rows: B operand of MMA3)
 //   MMA1   z2 = a0 W2^T                                    (TS, 24 x [128x64x8])
 //   epiC   a1 = relu(z2+b2); dz2 = (g Wo) * 1[a1>0] -> TMEM A (hi|lo) and -> smem sZ (A operand of MMA3); db2 partial sums

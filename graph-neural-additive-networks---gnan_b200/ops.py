@@ -1,5 +1,5 @@
 """torch.library ops over the C ABI (include/gnan_b200.h). Each op is a thin ctypes call on raw device pointers and the
-current stream; autograd is wired with register_autograd so the nn.Modules in modules.py compose them like any torch op.
+current stream; autograd is wired with register_autograd so the nn.Modules (GNAN.py, models.py, batched.py) compose them like any torch op.
 
 Nothing here computes on the CPU: non-CUDA inputs raise (see _lib.ptr)."""
 from typing import Optional, Tuple
