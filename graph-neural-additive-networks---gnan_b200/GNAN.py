@@ -32,6 +32,18 @@ class _Base(nn.Module):
         self._calls = getattr(self, "_calls", 0) + 1
         return (torch.initial_seed() * 0x9E3779B97F4A7C15 + self._calls * 0xD1B54A32D192ED03) & (2 ** 63 - 1)
 
+    def _seed_word(self):
+        """Device-side half of the dropout seed: a counter advanced ON THE DEVICE by every dropout forward and snapshotted for
+        that call's backward. The by-value seed above is frozen when a step is captured into a CUDA graph; this word keeps
+        advancing with every replay, so captured training steps draw fresh masks."""
+        dev = self._device()
+        st = getattr(self, "_seed_state", None)
+        if st is None or st.device != dev:
+            st = torch.zeros(1, dtype=torch.int64, device=dev)
+            self._seed_state = st
+        st.add_(-0x61C8864680B583EB)               # += 0x9E3779B97F4A7C15 (mod 2^64)
+        return st.clone()
+
     def _dedup_ok(self):
         return bool(self.dedup) and self.fs.n_layers >= 2 and not (self.training and self.fs.dropout > 0)
 
@@ -53,7 +65,8 @@ class _Base(nn.Module):
         if x.shape[1] != self.fs.groups:
             raise ValueError(f"x has {x.shape[1]} features, model was built for {self.fs.groups}")
         p = self.fs.dropout if self.training else 0.0
-        return ops.mlp(x, *self.fs.kernel_args(), dropout_p=p, seed=self._seed() if p > 0 else 0, precision=self.precision)
+        return ops.mlp(x, *self.fs.kernel_args(), dropout_p=p, seed=self._seed() if p > 0 else 0, precision=self.precision,
+                       seed_dev=self._seed_word() if p > 0 else None)
 
     def _table(self, u):
         """rho on a flat vector of scalar inputs -> [len(u), Cr]"""

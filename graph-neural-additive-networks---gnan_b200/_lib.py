@@ -31,9 +31,9 @@ SIGNATURES = {
     "gnan_last_error": (ctypes.c_char_p, []),
     "gnan_launch_count": (c_uint64, []),
     "gnan_mlp_workspace_bytes": (c_size_t, [c_int64, ctypes.POINTER(MlpParams), c_int, c_int]),
-    "gnan_mlp_fwd": (c_int, [c_void_p, c_int64, c_int64, ctypes.POINTER(MlpParams), c_float, c_uint64, c_int, c_void_p,
+    "gnan_mlp_fwd": (c_int, [c_void_p, c_int64, c_int64, ctypes.POINTER(MlpParams), c_float, c_uint64, c_void_p, c_int, c_void_p,
                              c_void_p, c_size_t, c_void_p]),
-    "gnan_mlp_bwd": (c_int, [c_void_p, c_int64, c_int64, ctypes.POINTER(MlpParams), c_float, c_uint64, c_int, c_void_p,
+    "gnan_mlp_bwd": (c_int, [c_void_p, c_int64, c_int64, ctypes.POINTER(MlpParams), c_float, c_uint64, c_void_p, c_int, c_void_p,
                              ctypes.POINTER(MlpGrads), c_void_p, c_size_t, c_void_p]),
     "gnan_mlp_entries_workspace_bytes": (c_size_t, [c_int64, ctypes.POINTER(MlpParams), c_int, c_int]),
     "gnan_mlp_entries_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, ctypes.POINTER(MlpParams), c_void_p, c_void_p]),

@@ -70,7 +70,8 @@ class TensorGNAN(_Base):
         nb = pk.nbins
         p = self.rho.dropout if self.training else 0.0
         T = ops.mlp(ops.rho_table_inputs(nb, dev, raw=True).reshape(-1, 1), *self.rho.kernel_args(), dropout_p=p,
-                    seed=self._seed() if p > 0 else 0, precision=self.precision)          # rho(d), d = 0..nbins-2
+                    seed=self._seed() if p > 0 else 0, precision=self.precision,
+                    seed_dev=self._seed_word() if p > 0 else None)                        # rho(d), d = 0..nbins-2
         keep = torch.ones(nb, 1, device=dev)
         keep[-1] = 0.0                                                                    # masked pairs: :158-159
         T = T * keep

@@ -25,6 +25,7 @@ struct MlpKArgs {
     uint32_t drop_thresh;  // 0 = no dropout
     float drop_scale;
     uint64_t seed;
+    const uint64_t *seed_dev;  // optional device-resident seed word, XORed into `seed` at kernel start (CUDA-graph replays)
     float *du;  // backward only: [R,G] gradient w.r.t. the inputs, or NULL
     // entries mode (gnan_mlp_entries_*): u is a flat value list grouped by feature, group g owns entries
     // [grp_ptr[g], grp_ptr[g+1]); rows of a group are its entries, outputs / dY are indexed by entry. NULL = dense mode.
@@ -180,6 +181,7 @@ mlp_fwd_kernel(MlpKArgs a, int KC, float *__restrict__ Spart)
     float *sBo = sBh + H;               // [CP]
 
     const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
+    if (a.seed_dev) a.seed ^= *a.seed_dev;
     int64_t row0 = (int64_t)blockIdx.x * TM, nrow = a.R, ebase = 0;
     int g0 = blockIdx.y * KC;
     int ng = min(KC, a.G - g0);
@@ -292,6 +294,7 @@ mlp_bwd_kernel(MlpKArgs a, const float *__restrict__ dS, MlpGradPtrs gp, int64_t
 
     const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3, tx2 = tid & 15, ty2 = tid >> 4;
     const int g = blockIdx.y;
+    if (a.seed_dev) a.seed ^= *a.seed_dev;
     const float dscale = a.drop_thresh ? a.drop_scale : 1.f;
 
     // group constants
@@ -653,6 +656,7 @@ MlpKArgs make_args(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params
     a.drop_thresh = dropout_p > 0.f ? gnan_dropout_thresh(dropout_p) : 0u;
     a.drop_scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
     a.seed = seed;
+    a.seed_dev = nullptr;
     a.du = nullptr;
     a.grp_ptr = nullptr;
     a.items = nullptr;
@@ -699,12 +703,10 @@ int gnan_mlp_tc_supported(const gnan_mlp_params *p, int precision);
 int gnan_mlp_tc_bwd_supported(const gnan_mlp_params *p, int precision);
 size_t gnan_mlp_tc_workspace_bytes(int64_t R, const gnan_mlp_params *p, int backward, int precision);
 int gnan_mlp_tc_fwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *p, float dropout_p, uint64_t seed,
-                    int precision, float *S, void *ws, size_t ws_bytes, cudaStream_t st);
-int gnan_mlp_tc_bwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *p, float dropout_p, uint64_t seed,
-                    int precision, const float *dS, const gnan_mlp_grads *grads, void *ws, size_t ws_bytes, cudaStream_t st);
+                    int precision, float *S, void *ws, size_t ws_bytes, cudaStream_t st, const uint64_t *seed_dev);
 int gnan_mlp_tc_bwd_ex(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *p, float dropout_p, uint64_t seed,
                        int precision, const float *dS, const gnan_mlp_grads *grads, void *ws, size_t ws_bytes, cudaStream_t st,
-                       const int64_t *grp_ptr);
+                       const int64_t *grp_ptr, const uint64_t *seed_dev);
 
 extern "C" size_t gnan_mlp_workspace_bytes(int64_t R, const gnan_mlp_params *p, int backward, int precision)
 {
@@ -720,8 +722,8 @@ extern "C" size_t gnan_mlp_workspace_bytes(int64_t R, const gnan_mlp_params *p, 
 }
 
 extern "C" int gnan_mlp_fwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *p, float dropout_p,
-                            uint64_t seed, int precision, float *S, void *workspace, size_t workspace_bytes,
-                            gnan_stream_t stream)
+                            uint64_t seed, const uint64_t *seed_dev, int precision, float *S, void *workspace,
+                            size_t workspace_bytes, gnan_stream_t stream)
 {
     int rc = check_params(p, R, ldu);
     if (rc) return rc;
@@ -730,6 +732,7 @@ extern "C" int gnan_mlp_fwd(const float *u, int64_t R, int64_t ldu, const gnan_m
     cudaStream_t st = (cudaStream_t)stream;
     if (R == 0) return GNAN_OK;
     MlpKArgs a = make_args(u, R, ldu, p, dropout_p, seed);
+    a.seed_dev = dropout_p > 0.f ? seed_dev : nullptr;
     if (p->n_layers == 1) {
         const int64_t n = R * p->C;
         linear1_fwd_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(a, S);
@@ -738,7 +741,7 @@ extern "C" int gnan_mlp_fwd(const float *u, int64_t R, int64_t ldu, const gnan_m
     }
     // shapes the tensor-core path does not cover run the (more precise) fp32 kernel
     if (precision != GNAN_PREC_FP32 && gnan_mlp_tc_supported(p, precision))
-        return gnan_mlp_tc_fwd(u, R, ldu, p, dropout_p, seed, precision, S, workspace, workspace_bytes, st);
+        return gnan_mlp_tc_fwd(u, R, ldu, p, dropout_p, seed, precision, S, workspace, workspace_bytes, st, a.seed_dev);
     const FwdPlan pl = plan_fwd(R, p);
     float *Spart = S;
     if (pl.nchunk > 1) {
@@ -765,8 +768,8 @@ extern "C" int gnan_mlp_fwd(const float *u, int64_t R, int64_t ldu, const gnan_m
 }
 
 extern "C" int gnan_mlp_bwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *p, float dropout_p,
-                            uint64_t seed, int precision, const float *dS, const gnan_mlp_grads *grads, void *workspace,
-                            size_t workspace_bytes, gnan_stream_t stream)
+                            uint64_t seed, const uint64_t *seed_dev, int precision, const float *dS, const gnan_mlp_grads *grads,
+                            void *workspace, size_t workspace_bytes, gnan_stream_t stream)
 {
     int rc = check_params(p, R, ldu);
     if (rc) return rc;
@@ -774,6 +777,7 @@ extern "C" int gnan_mlp_bwd(const float *u, int64_t R, int64_t ldu, const gnan_m
     GNAN_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "mlp_bwd: dropout_p %f out of [0,1)", dropout_p);
     cudaStream_t st = (cudaStream_t)stream;
     MlpKArgs a = make_args(u, R, ldu, p, dropout_p, seed);
+    a.seed_dev = dropout_p > 0.f ? seed_dev : nullptr;
     a.du = grads->du;
     const size_t G = p->G, H = p->H, C = p->C;
     if (p->n_layers == 1) {
@@ -796,7 +800,7 @@ extern "C" int gnan_mlp_bwd(const float *u, int64_t R, int64_t ldu, const gnan_m
         return GNAN_OK;
     }
     if (precision != GNAN_PREC_FP32 && !grads->du && gnan_mlp_tc_bwd_supported(p, precision))   // input gradients: fp32 kernel only
-        return gnan_mlp_tc_bwd(u, R, ldu, p, dropout_p, seed, precision, dS, grads, workspace, workspace_bytes, st);
+        return gnan_mlp_tc_bwd_ex(u, R, ldu, p, dropout_p, seed, precision, dS, grads, workspace, workspace_bytes, st, nullptr, a.seed_dev);
     const BwdPlan pl = plan_bwd(R, p);
     MlpGradPtrs gp;
     const size_t ntot = grad_floats(p);
@@ -899,7 +903,7 @@ extern "C" int gnan_mlp_entries_bwd(const float *val, const int64_t *grp_ptr, in
     cudaStream_t st = (cudaStream_t)stream;
     if (E > 0 && precision != GNAN_PREC_FP32 && gnan_mlp_tc_bwd_supported(p, precision))      // tcgen05 kernel, per-group row space
         return gnan_mlp_tc_bwd_ex(val, std::max<int64_t>(max_group_entries, 1), 1, p, 0.f, 0, precision, dY, grads, workspace,
-                                  workspace_bytes, st, grp_ptr);
+                                  workspace_bytes, st, grp_ptr, nullptr);
     MlpKArgs a = make_args(val, E, 1, p, 0.f, 0);
     a.grp_ptr = grp_ptr;
     const size_t G = p->G, H = p->H, C = p->C, nh = p->n_layers - 2;

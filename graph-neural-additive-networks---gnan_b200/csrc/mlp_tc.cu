@@ -55,6 +55,7 @@ struct TcArgs {
     uint32_t drop_thresh;
     float drop_scale;
     uint64_t seed;
+    const uint64_t *seed_dev;   // optional device-resident seed word XORed into `seed` at kernel start (CUDA-graph replays)
     int single_pass;  // 1 = plain tf32 (no lo terms)
     int prof;         // debug: bit 0 = accumulate phase cycle counters (GNAN_TC_PROF), bit 1 = skip MMA3 (GNAN_TC_SKIP3)
     const int64_t *grp_ptr;   // backward, entries mode (gnan_mlp_entries_bwd): rows of group g = its entries; NULL = dense
@@ -109,6 +110,7 @@ template <bool DROP>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 mlp_tc_fwd_kernel(TcArgs a, int KC, float *__restrict__ Spart)
 {
+    if (DROP && a.seed_dev) a.seed ^= *a.seed_dev;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     FwdSmem &sm = *reinterpret_cast<FwdSmem *>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -377,6 +379,7 @@ template <int CT, bool DROP>
 __global__ void __launch_bounds__(BWD_THREADS, 1)   // 17 warps occupy 20 warp slots (5 per scheduler): 96 registers is the cap
 mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t ntiles)
 {
+    if (DROP && a.seed_dev) a.seed ^= *a.seed_dev;
     constexpr int NC = BWD_COLS;
     using IO = TmemIO<NC>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -849,6 +852,7 @@ TcArgs make_tc_args(const float *u, int64_t R, int64_t ldu, const gnan_mlp_param
     a.drop_thresh = dropout_p > 0.f ? gnan_dropout_thresh(dropout_p) : 0u;
     a.drop_scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
     a.seed = seed;
+    a.seed_dev = nullptr;
     a.single_pass = precision == GNAN_PREC_TF32;
     a.prof = (getenv("GNAN_TC_PROF") != nullptr ? 1 : 0) | (getenv("GNAN_TC_SKIP3") != nullptr ? 2 : 0);
     a.grp_ptr = nullptr;
@@ -927,7 +931,7 @@ size_t gnan_mlp_tc_workspace_bytes(int64_t R, const gnan_mlp_params *p, int back
 }
 
 int gnan_mlp_tc_fwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *p, float dropout_p, uint64_t seed,
-                    int precision, float *S, void *ws, size_t ws_bytes, cudaStream_t st)
+                    int precision, float *S, void *ws, size_t ws_bytes, cudaStream_t st, const uint64_t *seed_dev)
 {
     const TcFwdPlan pl = plan_tc_fwd(R, p);
     float *Spart = S;
@@ -939,7 +943,8 @@ int gnan_mlp_tc_fwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_param
         }
         Spart = (float *)ws;
     }
-    const TcArgs a = make_tc_args(u, R, ldu, p, dropout_p, seed, precision);
+    TcArgs a = make_tc_args(u, R, ldu, p, dropout_p, seed, precision);
+    a.seed_dev = seed_dev;
     int rc = launch_tc_fwd(a, pl, Spart, st);
     if (rc) return rc;
     if (pl.nchunk > 1) return gnan_reduce_chunks(Spart, pl.nchunk, (size_t)R * p->C, (size_t)R * p->C, S, st);
@@ -949,7 +954,7 @@ int gnan_mlp_tc_fwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_param
 // grp_ptr != NULL: entries mode, u = val[E], R = the largest group (sizes the row chunks), dS = dY[E,C]
 int gnan_mlp_tc_bwd_ex(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *p, float dropout_p, uint64_t seed,
                        int precision, const float *dS, const gnan_mlp_grads *grads, void *ws, size_t ws_bytes, cudaStream_t st,
-                       const int64_t *grp_ptr)
+                       const int64_t *grp_ptr, const uint64_t *seed_dev)
 {
     const TcBwdPlan pl = plan_tc_bwd(R, p);
     const size_t G = p->G, C = p->C, ntot = tc_grad_floats(p);
@@ -974,6 +979,7 @@ int gnan_mlp_tc_bwd_ex(const float *u, int64_t R, int64_t ldu, const gnan_mlp_pa
     }
     TcArgs a = make_tc_args(u, R, ldu, p, dropout_p, seed, precision);
     a.grp_ptr = grp_ptr;
+    a.seed_dev = seed_dev;
     int rc;
     if (p->C == 1) rc = launch_tc_bwd<1>(a, pl, dS, gp, st);
     else if (p->C == 2) rc = launch_tc_bwd<2>(a, pl, dS, gp, st);
@@ -996,12 +1002,6 @@ int gnan_mlp_tc_bwd_ex(const float *u, int64_t R, int64_t ldu, const gnan_mlp_pa
         GNAN_LAUNCH_OK();
     }
     return GNAN_OK;
-}
-
-int gnan_mlp_tc_bwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *p, float dropout_p, uint64_t seed,
-                    int precision, const float *dS, const gnan_mlp_grads *grads, void *ws, size_t ws_bytes, cudaStream_t st)
-{
-    return gnan_mlp_tc_bwd_ex(u, R, ldu, p, dropout_p, seed, precision, dS, grads, ws, ws_bytes, st, nullptr);
 }
 
 // debug aid: read (and clear) the backward kernel's phase cycle counters; slots: 0 gen, 1 wait MMA1, 2 epiC, 3 wait MMA2,

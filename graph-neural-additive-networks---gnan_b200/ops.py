@@ -75,7 +75,7 @@ def _mlp_params(w1, b1, wh, bh, wo, bo, n_layers):
 # ---------------------------------------------------------------------------------------------------------------------
 @torch.library.custom_op("gnan_b200::mlp_fwd", mutates_args=())
 def mlp_fwd(u: Tensor, w1: Tensor, b1: Tensor, wh: Tensor, bh: Tensor, wo: Tensor, bo: Tensor, n_layers: int,
-            dropout_p: float, seed: int, precision: int) -> Tensor:
+            dropout_p: float, seed: int, precision: int, seed_dev: Optional[Tensor] = None) -> Tensor:
     lib = load()
     u, w1, b1, wh, bh, wo, bo = (_f32(t, n) for t, n in zip((u, w1, b1, wh, bh, wo, bo), "u w1 b1 wh bh wo bo".split()))
     if u.dim() != 2 or u.shape[1] != wo.shape[0]:
@@ -85,20 +85,20 @@ def mlp_fwd(u: Tensor, w1: Tensor, b1: Tensor, wh: Tensor, bh: Tensor, wo: Tenso
     S = torch.empty(R, C, dtype=torch.float32, device=u.device)
     ws = _ws(lib.gnan_mlp_workspace_bytes(R, p, 0, precision), u.device)
     with _timed("mlp_fwd"):
-        check(lib.gnan_mlp_fwd(ptr(u), R, u.shape[1], p, float(dropout_p), int(seed) & (2 ** 64 - 1), precision, ptr(S), ptr(ws),
-                               ws.numel(), stream_handle()), "gnan_mlp_fwd")
+        check(lib.gnan_mlp_fwd(ptr(u), R, u.shape[1], p, float(dropout_p), int(seed) & (2 ** 64 - 1), ptr(seed_dev), precision, ptr(S),
+                               ptr(ws), ws.numel(), stream_handle()), "gnan_mlp_fwd")
     return S
 
 
 @mlp_fwd.register_fake
-def _(u, w1, b1, wh, bh, wo, bo, n_layers, dropout_p, seed, precision):
+def _(u, w1, b1, wh, bh, wo, bo, n_layers, dropout_p, seed, precision, seed_dev=None):
     return u.new_empty(u.shape[0], wo.shape[1])
 
 
 @torch.library.custom_op("gnan_b200::mlp_bwd", mutates_args=())
 def mlp_bwd(u: Tensor, w1: Tensor, b1: Tensor, wh: Tensor, bh: Tensor, wo: Tensor, bo: Tensor, n_layers: int,
             dropout_p: float, seed: int, precision: int, dS: Tensor,
-            need_du: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+            need_du: bool, seed_dev: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
     lib = load()
     u, w1, b1, wh, bh, wo, bo, dS = (_f32(t, n) for t, n in zip((u, w1, b1, wh, bh, wo, bo, dS), "u w1 b1 wh bh wo bo dS".split()))
     p, G, H, C = _mlp_params(w1, b1, wh, bh, wo, bo, n_layers)
@@ -108,19 +108,20 @@ def mlp_bwd(u: Tensor, w1: Tensor, b1: Tensor, wh: Tensor, bh: Tensor, wo: Tenso
     g = MlpGrads(*[ptr(t) for t in outs[:6]], ptr(outs[6]) if need_du else None)
     ws = _ws(lib.gnan_mlp_workspace_bytes(R, p, 1, precision), u.device)
     with _timed("mlp_bwd"):
-        check(lib.gnan_mlp_bwd(ptr(u), R, u.shape[1], p, float(dropout_p), int(seed) & (2 ** 64 - 1), precision, ptr(dS),
+        check(lib.gnan_mlp_bwd(ptr(u), R, u.shape[1], p, float(dropout_p), int(seed) & (2 ** 64 - 1), ptr(seed_dev), precision, ptr(dS),
                                g, ptr(ws), ws.numel(), stream_handle()), "gnan_mlp_bwd")
     return tuple(outs)
 
 
 @mlp_bwd.register_fake
-def _(u, w1, b1, wh, bh, wo, bo, n_layers, dropout_p, seed, precision, dS, need_du):
+def _(u, w1, b1, wh, bh, wo, bo, n_layers, dropout_p, seed, precision, dS, need_du, seed_dev=None):
     return tuple(torch.empty_like(t) for t in (w1, b1, wh, bh, wo, bo)) + (u.new_empty(u.shape if need_du else (0,)),)
 
 
 def _mlp_setup(ctx, inputs, output):
-    u, w1, b1, wh, bh, wo, bo, n_layers, dropout_p, seed, precision = inputs
+    u, w1, b1, wh, bh, wo, bo, n_layers, dropout_p, seed, precision, seed_dev = inputs
     ctx.save_for_backward(u, w1, b1, wh, bh, wo, bo)
+    ctx.seed_dev = seed_dev
     ctx.cfg = (n_layers, dropout_p, seed, precision)
 
 
@@ -128,17 +129,21 @@ def _mlp_backward(ctx, dS):
     u, w1, b1, wh, bh, wo, bo = ctx.saved_tensors
     n_layers, dropout_p, seed, precision = ctx.cfg
     need_du = bool(ctx.needs_input_grad[0])
-    g = mlp_bwd(u, w1, b1, wh, bh, wo, bo, n_layers, dropout_p, seed, precision, dS.contiguous(), need_du)
-    return (g[6] if need_du else None,) + tuple(g[:6]) + (None, None, None, None)
+    g = mlp_bwd(u, w1, b1, wh, bh, wo, bo, n_layers, dropout_p, seed, precision, dS.contiguous(), need_du, ctx.seed_dev)
+    return (g[6] if need_du else None,) + tuple(g[:6]) + (None, None, None, None, None)
 
 
 mlp_fwd.register_autograd(_mlp_backward, setup_context=_mlp_setup)
 
 
-def mlp(u, w1, b1, wh, bh, wo, bo, n_layers, dropout_p=0.0, seed=0, precision="fp32"):
+def mlp(u, w1, b1, wh, bh, wo, bo, n_layers, dropout_p=0.0, seed=0, precision="fp32", seed_dev=None):
     """S[r,:] = sum_g f_g(u[r,g]); differentiable w.r.t. the weights, and w.r.t. u when u requires grad (only the NAM
-    readout feeds computed values in; x itself is data, GNAN.py:56)."""
-    return mlp_fwd(u, w1, b1, wh, bh, wo, bo, int(n_layers), float(dropout_p), int(seed), _lib.PRECISIONS[precision])
+    readout feeds computed values in; x itself is data, GNAN.py:56). seed_dev: optional 1-element int64 CUDA tensor XORed
+    into the dropout seed on the device (fresh masks for every replay of a captured step)."""
+    if seed_dev is not None and (seed_dev.dtype != torch.int64 or seed_dev.numel() != 1):
+        raise TypeError("seed_dev must be a 1-element int64 CUDA tensor")
+    return mlp_fwd(u, w1, b1, wh, bh, wo, bo, int(n_layers), float(dropout_p), int(seed), _lib.PRECISIONS[precision],
+                   seed_dev if dropout_p > 0 else None)
 
 
 MAX_KERNEL_CHANNELS = 64      # gnan_mlp_* limit on C

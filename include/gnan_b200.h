@@ -80,15 +80,19 @@ size_t gnan_mlp_workspace_bytes(int64_t R, const gnan_mlp_params *p, int backwar
 /* S[r,:] = sum_g f_g(u[r*ldu + g])   (replaces the K-iteration module loop + slice assignment + feature sum:
  * GNAN.py:57-62,157; models.py:360-365,455-460; batched_pyg_main.py:144-148,170).
  * dropout_p > 0 applies inverted dropout after every hidden ReLU with a counter-based mask keyed on
- * (seed, layer, group, row, unit); the same (dropout_p, seed) must be passed to gnan_mlp_bwd. */
+ * (seed, layer, group, row, unit); the same (dropout_p, seed, seed_dev) must be passed to gnan_mlp_bwd.
+ * seed_dev (optional, NULL = unused): one device-resident 64-bit word XORed into `seed` when the kernel starts. A step that
+ * is captured into a CUDA graph bakes by-value arguments in; advancing this word on the device between replays gives every
+ * replay fresh masks. */
 int gnan_mlp_fwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *p, float dropout_p, uint64_t seed,
-                 int precision, float *S /* [R,C] */, void *workspace, size_t workspace_bytes, gnan_stream_t stream);
+                 const uint64_t *seed_dev, int precision, float *S /* [R,C] */, void *workspace, size_t workspace_bytes,
+                 gnan_stream_t stream);
 
 /* gradients of all weights given dS [R,C] (replaces autograd through the same lines; trainer.py:66).
  * Activations are recomputed, nothing is saved by the forward. */
 int gnan_mlp_bwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *p, float dropout_p, uint64_t seed,
-                 int precision, const float *dS /* [R,C] */, const gnan_mlp_grads *grads, void *workspace,
-                 size_t workspace_bytes, gnan_stream_t stream);
+                 const uint64_t *seed_dev, int precision, const float *dS /* [R,C] */, const gnan_mlp_grads *grads,
+                 void *workspace, size_t workspace_bytes, gnan_stream_t stream);
 
 /* Entries mode: the shape functions on a COMPRESSED feature matrix (same reference lines as gnan_mlp_fwd/bwd). When
  * dropout is off, rows that carry the same value in a feature column share one evaluation of that feature's MLP (the zeros

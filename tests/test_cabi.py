@@ -44,7 +44,7 @@ def test_argument_validation_without_gpu(lib_path):
     from gnan_b200 import _lib
     lib = _lib.load()
     p = _lib.MlpParams(3, 24, 2, 3, None, None, None, None, None, None)   # H=24 unsupported, wo NULL
-    rc = lib.gnan_mlp_fwd(None, 4, 3, ctypes.byref(p), 0.0, 0, 0, None, None, 0, None)
+    rc = lib.gnan_mlp_fwd(None, 4, 3, ctypes.byref(p), 0.0, 0, None, 0, None, None, 0, None)
     assert rc == 1 and b"wo" in lib.gnan_last_error()
     rc = lib.gnan_aggregate_rows_fwd(None, 4, 4, 16, None, 0, 5, 1, None, None, 1, None, None)
     assert rc == 1

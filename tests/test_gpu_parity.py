@@ -925,3 +925,50 @@ def test_compressed_features_edge_cases():
         assert G.rel_err(res["sparse"][0], res["dense"][0]) < TOL, name
         for k in p:
             assert G.rel_err(res["sparse"][1][k], res["dense"][1][k]) < TOL, (name, k)
+
+
+def test_device_seed_word_is_xored_into_the_dropout_seed():
+    """gnan_mlp_fwd/bwd(seed, seed_dev) == gnan_mlp_fwd/bwd(seed ^ *seed_dev): same masks, same gradients, both kernel paths."""
+    from gnan_b200 import ops
+    gen = torch.Generator().manual_seed(9)
+    R, K, H, C, L = 260, 5, 64, 3, 3
+    p = dict(w1=torch.randn(K, H, generator=gen), b1=torch.randn(K, H, generator=gen), wh=torch.randn(1, K, H, H, generator=gen) / 8,
+             bh=torch.randn(1, K, H, generator=gen) * 0.1, wo=torch.randn(K, C, H, generator=gen) / 8, bo=torch.randn(K, C, generator=gen))
+    u = torch.randn(R, K, generator=gen).to(DEV)
+    w = torch.randn(R, C, generator=gen).to(DEV)
+    s, word = 0x1234ABCD5678, 0x0F0F00FF1234567
+    for prec in ("fp32", "tf32x3"):
+        res = []
+        for seed, sd in ((s, torch.tensor([word], dtype=torch.int64, device=DEV)), (s ^ word, None)):
+            d = {k: v.to(DEV).requires_grad_(True) for k, v in p.items()}
+            out = ops.mlp(u, d["w1"], d["b1"], d["wh"], d["bh"], d["wo"], d["bo"], L, dropout_p=0.4, seed=seed, precision=prec, seed_dev=sd)
+            (out * w).sum().backward()
+            res.append((out.detach(), d["wh"].grad.clone(), d["w1"].grad.clone()))
+        for a, b in zip(*res):
+            assert torch.equal(a, b), prec
+        plain = ops.mlp(u, *[p[k].to(DEV) for k in ("w1", "b1", "wh", "bh", "wo", "bo")], L, dropout_p=0.4, seed=s, precision=prec)
+        assert not torch.equal(plain, res[0][0])                     # the word really changes the masks
+
+
+def test_captured_step_with_dropout_draws_fresh_masks():
+    """A captured training step replays by-value kernel arguments; the device-side seed word advances per replay, so two replays
+    from identical weights give different dropout masks (different losses), like two eager steps do."""
+    from gnan_b200 import trainer
+    from gnan_b200.GNAN import TensorGNAN
+    from gnan_b200.preprocess import apsp
+    rng = np.random.default_rng(12)
+    n, K, C = 400, 8, 3
+    x = torch.tensor(rng.normal(size=(n, K))).float().to(DEV)
+    y = torch.tensor(rng.integers(0, C, size=n)).to(DEV)
+    data = SimpleNamespace(x=x, hop_data=apsp(torch.tensor(random_graph(rng, n, 2.5)), n, device=DEV))
+    torch.manual_seed(0)
+    m = TensorGNAN(K, C, 3, 64, dropout=0.5).to(DEV)
+    m.fs.xavier_normal_(1.0); m.rho.xavier_normal_(1.0)
+    m.train()
+    opt = torch.optim.SGD(m.parameters(), lr=0.0)                    # lr 0: the weights stay put, only the masks change
+    step = trainer.CapturedStep(lambda: torch.nn.functional.cross_entropy(m.forward(data), y), opt, warmup=1)
+    losses = [float(step()) for _ in range(4)]
+    assert len(set(losses)) == 4, losses
+    g1 = m.fs.wh.grad.clone()
+    step()
+    assert not torch.equal(g1, m.fs.wh.grad)
