@@ -12,6 +12,8 @@ tasks, `[.,1]` outputs flattened for the loss), same return tuples. What is diff
     copied per step, cf. `data.to(device)` at trainer.py:46), or a preprocess.PackedBatch of many graphs (one step per batch);
   * the AUC (tolokers path, trainer.py:68-78) is computed on the device from the concatenated scores.
 """
+from types import SimpleNamespace
+
 import torch
 
 from .preprocess import PackedBatch
@@ -129,11 +131,27 @@ class _Running:
         return loss, -1
 
 
-def train_epoch(model, dloader, loss_fn, optimizer, device, classify=True, label_index=0, compute_auc=False, is_graph_task=True):
-    """trainer.py:23-86. One optimizer step per loader item; returns (mean loss, accuracy, auc | -1) or (mean loss, -1)."""
+def train_epoch(model, dloader, loss_fn, optimizer, device, classify=True, label_index=0, compute_auc=False, is_graph_task=True,
+                capture_steps=False):
+    """trainer.py:23-86. One optimizer step per loader item; returns (mean loss, accuracy, auc | -1) or (mean loss, -1).
+    capture_steps=True (extension, graph tasks with one graph per item): replay one captured CUDA graph per graph size
+    (SizeBucketedSteps) instead of launching every step's kernels from Python."""
     run = _Running(device)
+    buckets = None
+    if capture_steps and is_graph_task and not compute_auc:
+        key = (id(optimizer), id(loss_fn), bool(classify))
+        cache = model.__dict__.setdefault("_gnan_b200_step_cache", {})
+        buckets = cache.get(key)
+        if buckets is None:
+            buckets = cache[key] = SizeBucketedSteps(model, loss_fn, optimizer, device, bool(classify))
+        buckets.begin_epoch()
+        run.loss, run.correct = buckets.loss_sum, buckets.correct       # captured steps accumulate into the same tensors
     for data in dloader:
         labels = _labels_of(data, loss_fn, label_index)
+        if buckets is not None and buckets.step(data, labels):
+            run.steps += 1
+            run.n_samples += int(labels.shape[0])
+            continue
         optimizer.zero_grad(set_to_none=True)
         outputs, labels = _forward_item(model, data, labels, device, "train_mask", is_graph_task)
         loss = _loss(loss_fn, outputs, labels)
@@ -208,3 +226,138 @@ class CapturedStep:
     def __call__(self):
         self.graph.replay()
         return self.loss
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# per-graph steps (the reference's batch_size=1 loaders) replayed from one CUDA graph per graph size
+# ---------------------------------------------------------------------------------------------------------------------
+class SizeBucketedSteps:
+    """`train_epoch(..., capture_steps=True)`: one captured step (forward + loss + backward + optimizer step + metric
+    accumulation) per distinct graph size n; an item is copied into that size's static buffers and the graph is replayed.
+
+    The reference trains graph tasks one graph per step (datasets.py:339-341), which on a GPU is ~40 launches of
+    microsecond kernels per step: Python / launch bound. Graph sizes repeat (Mutagenicity: ~120 distinct n), so the launch
+    sequence is captured once per n. The level table is padded to n + 1 columns (levels 0..n-1 + unreachable; empty levels
+    have count 0 and are never indexed), which makes the captured shapes a function of n alone. Dropout stays correct
+    through the device-side seed word (GNAN._seed_word). Needs an optimizer that can be captured: torch.optim.Adam is
+    switched to capturable=True in place (its step counters move to the device); other optimizers -> eager steps.
+    Hyper-parameters are baked into a capture: a change of lr / betas / eps / weight_decay (LR schedulers) drops the cache.
+    """
+
+    def __init__(self, model, loss_fn, optimizer, device, classify):
+        self.model, self.loss_fn, self.opt, self.device, self.classify = model, loss_fn, optimizer, torch.device(device), classify
+        self.entries = {}
+        self.loss_sum = torch.zeros((), device=self.device, dtype=torch.float64)
+        self.correct = torch.zeros((), device=self.device, dtype=torch.float64)
+        self.hyper = self._hyper()
+        self.usable = self._make_capturable()
+
+    def _hyper(self):
+        return [tuple((k, float(v) if isinstance(v, (int, float)) else str(v)) for k, v in sorted(g.items())
+                      if k in ("lr", "betas", "eps", "weight_decay", "amsgrad", "maximize")) for g in self.opt.param_groups]
+
+    def _make_capturable(self):
+        if not isinstance(self.opt, torch.optim.Adam) or self.device.type != "cuda":
+            return False
+        for g in self.opt.param_groups:
+            if not g.get("capturable", False):
+                g["capturable"] = True
+                for p in g["params"]:
+                    st = self.opt.state.get(p)
+                    if st and "step" in st and torch.is_tensor(st["step"]) and not st["step"].is_cuda:
+                        st["step"] = st["step"].to(device=p.device, dtype=torch.float32)
+        return True
+
+    def begin_epoch(self):
+        if self._hyper() != self.hyper:                      # e.g. ReduceLROnPlateau (main.py:147-153) moved the learning rate
+            self.entries.clear()
+            self.hyper = self._hyper()
+        self.loss_sum.zero_()
+        self.correct.zero_()
+
+    def _capture(self, n, K, ld, label_like):
+        from .preprocess import HopData
+        dev = self.device
+        e = SimpleNamespace(x=torch.zeros(n, K, device=dev), hop=torch.full((n, ld), 255, dtype=torch.uint8, device=dev),
+                            cnt=torch.zeros(n, n + 1, dtype=torch.int32, device=dev),
+                            labels=torch.zeros_like(label_like, device=dev))
+        e.cnt[:, 0] = 1                                      # a valid placeholder graph for the warm-up steps: n isolated nodes
+        e.cnt[:, -1] = n - 1
+        e.hop.fill_(255)
+        e.hop[torch.arange(n), torch.arange(n)] = 0
+        data = SimpleNamespace(x=e.x, hop_data=HopData(e.hop, e.cnt, n))
+        model, loss_fn, opt = self.model, self.loss_fn, self.opt
+
+        def body():
+            opt.zero_grad(set_to_none=True)
+            outputs, labels = _forward_item(model, data, e.labels, dev, "train_mask", True)
+            loss = _loss(loss_fn, outputs, labels)
+            loss.backward()
+            opt.step()
+            self.loss_sum.add_(loss.detach())
+            if self.classify:
+                self.correct.add_(_correct(outputs.detach(), labels))
+            return loss
+
+        # warm-up steps would move the weights: run them on a snapshot and restore it (optimizer state included)
+        w0 = [p.detach().clone() for p in model.parameters()]
+        s0 = {k: ({kk: (vv.clone() if torch.is_tensor(vv) else vv) for kk, vv in v.items()}) for k, v in opt.state.items()}
+        keep_l, keep_c = self.loss_sum.clone(), self.correct.clone()
+        old_dedup, model.dedup = model.dedup, False          # static buffers change content: no per-object caches
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                body()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            e.graph = torch.cuda.CUDAGraph()
+            opt.zero_grad(set_to_none=True)
+            with torch.cuda.graph(e.graph):
+                body()
+        finally:
+            model.dedup = old_dedup
+        with torch.no_grad():                                # capture does not execute; undo the one warm-up step
+            for p, w in zip(model.parameters(), w0):
+                p.copy_(w)
+            for k, v in s0.items():
+                for kk, vv in v.items():
+                    if torch.is_tensor(vv):
+                        opt.state[k][kk].copy_(vv)
+            for k in list(opt.state.keys()):
+                if k not in s0:                              # state created by the warm-up step of a fresh optimizer
+                    for kk, vv in opt.state[k].items():
+                        if torch.is_tensor(vv):
+                            vv.zero_()
+            self.loss_sum.copy_(keep_l)
+            self.correct.copy_(keep_c)
+        return e
+
+    def step(self, data, labels):
+        """True if the item was trained through a captured step; False -> the caller runs it eagerly."""
+        from ._inputs import resolve
+        if not self.usable or isinstance(data, PackedBatch) or getattr(data, "x", None) is None:
+            return False
+        x, hd = resolve(data, self.device)
+        n, K = x.shape
+        if hd.rows != n or hd.nbins > n + 1 or n < 1:
+            return False
+        key = (n, K, tuple(labels.shape), labels.dtype)
+        e = self.entries.get(key)
+        if e is None:
+            e = self.entries[key] = self._capture(n, K, hd.hop.shape[1], labels)
+        pad = getattr(data, "_gnan_b200_cnt_pad", None)
+        if pad is None or pad.shape != e.cnt.shape or pad.device != self.device:
+            pad = torch.zeros_like(e.cnt)
+            pad[:, :hd.nbins - 1] = hd.level_counts[:, :-1]
+            pad[:, -1] = hd.level_counts[:, -1]
+            try:
+                data._gnan_b200_cnt_pad = pad
+            except Exception:
+                pass
+        e.x.copy_(x, non_blocking=True)
+        e.hop.copy_(hd.hop, non_blocking=True)
+        e.cnt.copy_(pad, non_blocking=True)
+        e.labels.copy_(labels.to(self.device, non_blocking=True), non_blocking=True)
+        e.graph.replay()
+        return True

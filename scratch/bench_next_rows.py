@@ -56,6 +56,23 @@ for prec in ("fp32", "tf32x3"):
         print(prec, bs, res[f"train_epoch[{prec},batch={bs}]"], flush=True)
     t, out = sync_time(lambda: trainer.test_epoch(model, ds.loader(4337), loss_fn, dev, is_graph_task=True))
     res[f"test_epoch[{prec},batch=4337]"] = {"s": t, "graphs_per_s": len(ds) / t}
+# the reference's mode (one graph per step) replayed from one captured CUDA graph per graph size, without and with dropout
+items = [SimpleNamespace(x=g.x, hop_data=None, y=g.y) for g in []]
+from gnan_b200.preprocess import apsp
+sub_items = []
+for b in range(1024):
+    g = graphs[b]
+    sub_items.append(SimpleNamespace(x=torch.cat([g.x, torch.ones(g.x.shape[0], 1)], 1).to(dev), hop_data=apsp(g.edge_index, g.x.shape[0], device=dev), y=g.y))
+for p_drop in (0.0, 0.6):
+    torch.manual_seed(0)
+    mm = TensorGNAN(15, 1, 3, 64, dropout=p_drop, is_graph_task=True, readout_n_layers=0).to(dev)
+    mm.fs.xavier_normal_(1.0); mm.rho.xavier_normal_(1.0); mm.train()
+    for cap in (False, True):
+        opt = torch.optim.Adam(mm.parameters(), lr=1e-3)
+        trainer.train_epoch(mm, sub_items, loss_fn, opt, dev, is_graph_task=True, capture_steps=cap)      # warm-up / capture epoch
+        t, out = sync_time(lambda: trainer.train_epoch(mm, sub_items, loss_fn, opt, dev, is_graph_task=True, capture_steps=cap))
+        res[f"train_epoch[batch=1,dropout={p_drop},captured={cap}]"] = {"graphs": len(sub_items), "s": t, "graphs_per_s": len(sub_items) / t, "loss": out[0]}
+        print("batch1", p_drop, cap, res[f"train_epoch[batch=1,dropout={p_drop},captured={cap}]"], flush=True)
 model.train()
 t, f = sync_time(lambda: interpret.shape_function_table(model, torch.linspace(-1, 1, 1001)), reps=5)
 res["shape_function_table_1001x15_s"] = t

@@ -972,3 +972,59 @@ def test_captured_step_with_dropout_draws_fresh_masks():
     g1 = m.fs.wh.grad.clone()
     step()
     assert not torch.equal(g1, m.fs.wh.grad)
+
+
+def test_size_bucketed_captured_steps_follow_the_eager_trajectory():
+    """train_epoch(capture_steps=True): per-graph steps replayed from one CUDA graph per graph size give the same epoch
+    results and weights as the eager per-graph steps (plain, non-capturable Adam as the reference builds it, main.py:141)."""
+    from gnan_b200 import trainer
+    from gnan_b200.models import TensorGNAN
+    z = dict(np.load(f"{G.GOLDEN_DIR}/trainer_graph_bce.npz"))
+    graph_task, n_items, K, C, H, epochs, _, _ = [int(t) for t in z["meta"]]
+    lr, wd = [float(t) for t in z["hyper"]]
+    hist, weights = {}, {}
+    for capture in (False, True):
+        m = TensorGNAN(K, C, 3, H, is_graph_task=True, readout_n_layers=0)
+        m.load_state_dict({k[4:]: torch.tensor(v) for k, v in z.items() if k.startswith("sd0.")}, strict=True)
+        m = m.to(DEV)
+        items = _trainer_items(z, True, n_items)
+        loss_fn = torch.nn.BCEWithLogitsLoss()
+        opt = torch.optim.Adam(params=m.parameters(), lr=lr, weight_decay=wd)
+        h = []
+        for ep in range(4):
+            if ep == 2:
+                for g in opt.param_groups:
+                    g["lr"] = lr * 0.5                                  # what an LR scheduler does between epochs
+            h.append(trainer.train_epoch(m, items, loss_fn, opt, DEV, classify=True, is_graph_task=True, capture_steps=capture))
+        hist[capture] = np.array(h, dtype=np.float64)
+        weights[capture] = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+        if capture:
+            cache = next(iter(m._gnan_b200_step_cache.values()))
+            assert cache.usable and 1 <= len(cache.entries) <= n_items
+    # capturable Adam evaluates its bias corrections in fp32 on the device (the eager one in Python floats) and Adam's
+    # g / sqrt(v) amplifies that in the first steps: measured 6e-6..3e-5 on the epoch losses
+    assert np.allclose(hist[True][:, 0], hist[False][:, 0], rtol=2e-4), (hist[True], hist[False])
+    assert np.allclose(hist[True][:, 1], hist[False][:, 1], atol=1e-9)
+    for k in weights[True]:
+        assert G.rel_err(weights[True][k], weights[False][k]) < 2e-3, k
+
+
+def test_size_bucketed_captured_steps_with_dropout_run_and_vary():
+    from gnan_b200 import trainer
+    from gnan_b200.models import TensorGNAN
+    from gnan_b200.preprocess import apsp
+    rng = np.random.default_rng(31)
+    items = []
+    for i in range(12):
+        n = int(rng.integers(5, 9))
+        ei = torch.tensor(random_graph(rng, n, 2.0))
+        items.append(SimpleNamespace(x=torch.tensor(rng.normal(size=(n, 4))).float().to(DEV), hop_data=apsp(ei, n, device=DEV),
+                                     y=torch.tensor([float(i % 2)])))
+    torch.manual_seed(0)
+    m = TensorGNAN(4, 1, 3, 64, dropout=0.5, is_graph_task=True, readout_n_layers=0).to(DEV)
+    m.fs.xavier_normal_(1.0); m.rho.xavier_normal_(1.0)
+    m.train()
+    opt = torch.optim.Adam(m.parameters(), lr=0.0)                      # lr 0: epochs differ only through the dropout masks
+    l1 = trainer.train_epoch(m, items, torch.nn.BCEWithLogitsLoss(), opt, DEV, is_graph_task=True, capture_steps=True)[0]
+    l2 = trainer.train_epoch(m, items, torch.nn.BCEWithLogitsLoss(), opt, DEV, is_graph_task=True, capture_steps=True)[0]
+    assert np.isfinite(l1) and np.isfinite(l2) and l1 != l2

@@ -88,7 +88,8 @@ def test_trainer_auc_matches_sklearn_and_signatures_match_reference():
         s = np.round(rng.random(n), 1 if n > 50 else 3)            # the coarse rounding creates ties
         assert abs(trainer.roc_auc(torch.tensor(y), torch.tensor(s)) - roc_auc_score(y, s)) < 1e-12
     assert list(inspect.signature(trainer.train_epoch).parameters) == [
-        "model", "dloader", "loss_fn", "optimizer", "device", "classify", "label_index", "compute_auc", "is_graph_task"]
+        "model", "dloader", "loss_fn", "optimizer", "device", "classify", "label_index", "compute_auc", "is_graph_task",
+        "capture_steps"]                                                  # the reference's nine (trainer.py:23) + one opt-in extension
     assert list(inspect.signature(trainer.test_epoch).parameters) == [
         "model", "dloader", "loss_fn", "device", "classify", "label_index", "compute_auc", "val_mask", "is_graph_task"]
 
