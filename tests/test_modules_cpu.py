@@ -186,3 +186,31 @@ def test_compress_features_structure_and_roundtrip():
     assert [tuple(i) for i in cx.items.tolist()] == want and cx.max_group == max(gp[k + 1] - gp[k] for k in range(K))
     assert compress_features(torch.tensor(rng.normal(size=(50, 4)).astype(np.float32))) is None      # dense data: not worth it
     assert compress_features(torch.tensor(rng.normal(size=(50, 4)).astype(np.float32)), max_density=None) is not None
+
+
+def test_feature_compression_policy():
+    """_inputs.compressed_of: explicit x_compressed is always honoured; implicit building only for persistent, large inputs."""
+    from types import SimpleNamespace
+    from gnan_b200 import _inputs
+    from gnan_b200.preprocess import PackedBatch
+    from gnan_b200.sparse import CompressedFeatures, compress_features
+    big = torch.zeros(_inputs.AUTO_DEDUP_MIN_EVALUATIONS // 8, 8)
+    big[::7, 3] = 1.0
+    small = big[:50]
+    holder = SimpleNamespace(x=big)
+    cx = _inputs.compressed_of(holder, big, "cpu")
+    assert isinstance(cx, CompressedFeatures) and holder._gnan_b200_cx_cache[1] is cx
+    assert _inputs.compressed_of(holder, big, "cpu") is cx                              # cached on the object
+    big[0, 0] = 5.0                                                                      # in-place edit bumps the version: rebuilt
+    assert _inputs.compressed_of(holder, big, "cpu") is not cx
+    assert _inputs.compressed_of(SimpleNamespace(x=small), small, "cpu") is None        # too small to be worth analysing
+    assert _inputs.compressed_of(holder, big, "cpu", enabled=False) is None             # dropout active / model.dedup = False
+    dense = torch.randn(big.shape)
+    h2 = SimpleNamespace(x=dense)
+    assert _inputs.compressed_of(h2, dense, "cpu") is None and h2._gnan_b200_cx_cache[1] is None   # analysed once, verdict cached
+    pk = PackedBatch(big, None, None, torch.tensor([0, big.shape[0]], dtype=torch.int32), None)
+    assert _inputs.compressed_of(pk, big, "cpu") is None                                # a per-step batch object is never analysed
+    pk._gnan_b200_persistent = True
+    assert _inputs.compressed_of(pk, big, "cpu") is not None
+    explicit = compress_features(small, max_density=None)
+    assert _inputs.compressed_of(SimpleNamespace(x=None, x_compressed=explicit), None, "cpu") is explicit
