@@ -320,6 +320,8 @@ def main():
     ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32"])
     ap.add_argument("--dedup", default="on", choices=["on", "off"],
                     help="share shape-function evaluations between rows with equal feature values (gnan_b200.sparse; exact, dropout is 0 here)")
+    ap.add_argument("--headline-only", action="store_true",
+                    help="skip the strict-fp32 and dense-kernel comparison legs (used for the ncu launch list: only the headline step's kernels)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cuda-graph", action="store_true", help="run the step eagerly instead of replaying a captured CUDA graph")
     args = ap.parse_args()
@@ -540,7 +542,7 @@ def main():
     # the same step with precision="fp32" (FFMA kernels only, the 1e-5 parity mode) for comparison with the headline mode:
     # captured and replayed like the headline when that is a CUDA graph, eager otherwise
     strict_ms, strict_kt, strict_mode = None, None, None
-    if args.precision != "fp32" and world == 1:
+    if args.precision != "fp32" and world == 1 and not args.headline_only:
         model.precision = "fp32"
         for _ in range(3):
             step(data_d)
@@ -567,7 +569,7 @@ def main():
     # the same step on the DENSE kernels (every (node, feature) pair evaluated: what training with dropout > 0 runs), so that
     # the line carries both regimes; eager per-kernel pass + CUDA-graph replay like the headline
     dense = None
-    if cx is not None and world == 1 and wl.kind == "node":
+    if cx is not None and world == 1 and wl.kind == "node" and not args.headline_only:
         model.dedup = False
         dense_in = SimpleNamespace(x=x_d, hop_data=data_d.hop_data, x_compressed=None)
         for _ in range(3):

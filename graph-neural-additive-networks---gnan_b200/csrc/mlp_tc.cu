@@ -814,20 +814,23 @@ __global__ void dbo_colsum_kernel(const float *__restrict__ dS, int64_t R, int C
     for (int g = threadIdx.x; g < G; g += blockDim.x) dbo[(size_t)g * C + c] = red[0];
 }
 
-// entries mode: d bo[g][c] = sum over the entries of group g; one block per (g, c), fixed-order tree
-__global__ void dbo_entries_kernel(const float *__restrict__ dY, const int64_t *__restrict__ grp_ptr, int C, float *__restrict__ dbo)
+// entries mode: d bo[g][c] = sum over the entries of group g; one warp per (g, c), fixed order (lane-strided partial sums, then
+// a butterfly): deterministic. Groups are short at bag-of-words shapes (35 entries) and long for one-hot ones (9 k).
+__global__ void dbo_entries_kernel(const float *__restrict__ dY, const int64_t *__restrict__ grp_ptr, int G, int C, float *__restrict__ dbo)
 {
-    __shared__ float red[256];
-    const int g = blockIdx.x / C, c = blockIdx.x % C;
-    float s = 0.f;
-    for (int64_t e = grp_ptr[g] + threadIdx.x; e < grp_ptr[g + 1]; e += blockDim.x) s += dY[e * C + c];
-    red[threadIdx.x] = s;
-    __syncthreads();
-    for (int w = blockDim.x / 2; w > 0; w >>= 1) {
-        if ((int)threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) dbo[g * C + c] = red[0];
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= (int64_t)G * C) return;
+    const int g = (int)(w / C), c = (int)(w % C);
+    float s0 = 0.f, s1 = 0.f;
+    const int64_t e1 = grp_ptr[g + 1];
+    int64_t e = grp_ptr[g] + lane;
+    for (; e + 32 < e1; e += 64) { s0 += dY[e * C + c]; s1 += dY[(e + 32) * C + c]; }
+    if (e < e1) s0 += dY[e * C + c];
+    float s = s0 + s1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) dbo[w] = s;
 }
 
 struct TcFwdPlan { int KC, nchunk; int64_t ntile; };
@@ -997,7 +1000,7 @@ int gnan_mlp_tc_bwd_ex(const float *u, int64_t R, int64_t ldu, const gnan_mlp_pa
         }
     }
     if (grads->bo) {
-        if (grp_ptr) dbo_entries_kernel<<<(unsigned)(G * C), 256, 0, st>>>(dS, grp_ptr, (int)C, grads->bo);
+        if (grp_ptr) dbo_entries_kernel<<<(unsigned)ceil_div64((int64_t)G * C * 32, 256), 256, 0, st>>>(dS, grp_ptr, (int)G, (int)C, grads->bo);
         else dbo_colsum_kernel<<<(unsigned)C, 256, 0, st>>>(dS, R, (int)C, (int)G, grads->bo);
         GNAN_LAUNCH_OK();
     }
