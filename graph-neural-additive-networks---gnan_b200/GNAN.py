@@ -72,12 +72,12 @@ class _Base(nn.Module):
         """rho on a flat vector of scalar inputs -> [len(u), Cr]"""
         return ops.mlp(u.reshape(-1, 1), *self.rho.kernel_args(), precision=self.precision)
 
-    def _row_tables(self, holder, u):
+    def _row_tables(self, holder, u, cnt=None):
         """rho on the per-row inputs u [R,nbins] (GNAN.py:65-67: node_distances / normalization_matrix) -> [R*nbins, Cr].
         1/((1+d) * cnt) takes few distinct values (small integers): rho runs once per distinct value, rows gather."""
         if not self.dedup:
             return self._table(u)
-        uq, inv, order, seg_ptr = _unique_inputs(holder, u)
+        uq, inv, order, seg_ptr = _unique_inputs(holder, u, cnt)
         if uq.numel() * 2 > u.numel():
             return self._table(u)
         return ops.gather_rows(self._table(uq), inv, order, seg_ptr)
@@ -87,11 +87,13 @@ class _Base(nn.Module):
             print(name, param)
 
 
-def _unique_inputs(holder, u):
+def _unique_inputs(holder, u, cnt=None):
     """(unique values, inverse, sort order, segment offsets) of the per-row rho inputs u [R,nbins]; they depend only on the
     BFS level sizes, so they are computed once per hop-data object and cached on it."""
+    # keyed on the level-count tensor's identity AND version: an in-place refresh of the counts invalidates the mapping
+    key = (tuple(u.shape), str(u.device)) + ((cnt.data_ptr(), cnt._version) if cnt is not None else ())
     cache = getattr(holder, "_gnan_b200_rho_unique", None)
-    if cache is not None and cache[0] == (u.shape, u.device):
+    if cache is not None and cache[0] == key:
         return cache[1]
     uq, inv = torch.unique(u.reshape(-1), return_inverse=True)
     order = torch.sort(inv, stable=True).indices
@@ -99,7 +101,7 @@ def _unique_inputs(holder, u):
     seg_ptr[1:] = torch.cumsum(torch.bincount(inv, minlength=uq.numel()), 0)
     out = (uq.contiguous(), inv.contiguous(), order.contiguous(), seg_ptr)
     try:
-        holder._gnan_b200_rho_unique = ((u.shape, u.device), out)
+        holder._gnan_b200_rho_unique = (key, out)
     except Exception:
         pass
     return out
@@ -131,7 +133,7 @@ class TensorGNAN(_Base):
         S = self._feature_sums(*self._features(inputs))                              # [N,C]   GNAN.py:57-62 (+ :73 by linearity)
         if self.normalize_rho:                                                       # GNAN.py:65-67: rho(nd / norm)
             u = ops.rho_table_inputs(hd.nbins, dev, cnt=hd.level_counts)             # [R,nbins]
-            T = self._row_tables(hd, u).view(hd.rows, hd.nbins, self.out_channels)
+            T = self._row_tables(hd, u, hd.level_counts).view(hd.rows, hd.nbins, self.out_channels)
             out = ops.aggregate_rows(hd.hop, T, S, per_row=True)
         else:
             T = self._table(ops.rho_table_inputs(hd.nbins, dev))                     # [nbins,C]
@@ -150,7 +152,7 @@ class TensorGNAN(_Base):
         S = self._feature_sums(*self._features(pk))
         if self.normalize_rho:
             u = ops.rho_table_inputs(pk.nbins, dev, cnt=pk.level_counts)
-            T = self._row_tables(pk, u).view(S.shape[0], pk.nbins, self.out_channels)
+            T = self._row_tables(pk, u, pk.level_counts).view(S.shape[0], pk.nbins, self.out_channels)
             return ops.aggregate_blockdiag(pk.hop, pk.hop_off, pk.node_off, T, S, per_row=True, reduce_graph=self.is_graph_task)
         T = self._table(ops.rho_table_inputs(pk.nbins, dev))
         return ops.aggregate_blockdiag(pk.hop, pk.hop_off, pk.node_off, T, S, reduce_graph=self.is_graph_task)

@@ -128,7 +128,7 @@ def row_sharded_forward(model, x_local: torch.Tensor, hop_data, sizes: Sequence[
     flavor_input_norm = model.__class__.__module__.endswith(".GNAN") and model.__class__.__name__ == "TensorGNAN"
     if model.normalize_rho and flavor_input_norm:                               # GNAN.py:65-67
         u = ops.rho_table_inputs(hop_data.nbins, dev, cnt=hop_data.level_counts)
-        T = model._row_tables(hop_data, u).view(hop_data.rows, hop_data.nbins, -1)
+        T = model._row_tables(hop_data, u, hop_data.level_counts).view(hop_data.rows, hop_data.nbins, -1)
         return ops.aggregate_rows(hop_data.hop, T, s_full, per_row=True)
     T = model._table(ops.rho_table_inputs(hop_data.nbins, dev))
     rs = ops.level_rscale(hop_data.level_counts) if model.normalize_rho else None
