@@ -79,7 +79,7 @@ def test_module_matches_reference_golden(name, compact, precision):
     fp32 kernels: 1e-5 (measured worst over the cases 1.5e-6). 3xTF32 tcgen05 kernels: each product carries ~2^-22 instead of
     2^-24 relative error, so module-level errors are ~10x the fp32 ones: typically 1-3e-6, 1.1e-5 on the worst-conditioned
     case (gnan_loop_shared_rho, 1/count normalisation with heavy cancellation, where the fp32 kernels are at 1.5e-6 too).
-    The stated bound for that mode is 3e-5 (scratch/debug_golden_tc.py prints the per-case numbers)."""
+    The stated bound for that mode is 3e-5 (tests/tools/debug_golden_tc.py prints the per-case numbers)."""
     tol = TOL if precision == "fp32" else TOL_TF32X3
     z = G.load(name)
     m, out = run_case(z, compact, precision)
