@@ -77,13 +77,18 @@ class _Base(nn.Module):
         1/((1+d) * cnt) takes few distinct values (small integers): rho runs once per distinct value, rows gather."""
         if not self.dedup:
             return self._table(u)
+        if torch.cuda.is_current_stream_capturing() and not getattr(holder, "static_level_counts", False):
+            # a captured step would bake the value -> row mapping of THIS call's level counts into the graph; an in-place
+            # refresh of the counts between replays would then silently gather the wrong table rows. Only objects that
+            # declare their level counts immutable (holder.static_level_counts = True) keep the shared evaluation.
+            return self._table(u)
         uq, inv, order, seg_ptr = _unique_inputs(holder, u, cnt)
         if uq.numel() * 2 > u.numel():
             return self._table(u)
         return ops.gather_rows(self._table(uq), inv, order, seg_ptr)
 
     def print_rho_params(self):
-        for name, param in self.rho.named_parameters():
+        for name, param in self.rho[0].named_parameters():     # reference key names ("0.weight", ...), GNAN.py:174-176
             print(name, param)
 
 
@@ -105,6 +110,27 @@ def _unique_inputs(holder, u, cnt=None):
     except Exception:
         pass
     return out
+
+
+def _emit_rhos(module, state_dict, prefix, local_metadata):
+    """state_dict hook of GNAN(rho_per_feature=True): `rhos.{k}.{i}.weight/bias` as the reference saves them. Entry K-1 IS
+    rho (shared tensors upstream); the others are what a loaded checkpoint held, else copies of rho."""
+    rho, K = module.rho, module.fs.groups
+    for k in range(K):
+        for i, (w, b) in zip(rho.linear_indices(), rho.layer_tensors(0)):
+            for nme, t in (("weight", w), ("bias", b)):
+                if t is None:
+                    continue
+                key = f"rhos.{k}.{i}.{nme}"
+                kept = module._rhos_extra.get(key) if k < K - 1 else None
+                state_dict[prefix + key] = kept if kept is not None else t.detach()
+    return state_dict
+
+
+def _absorb_rhos(module, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+    pre = prefix + "rhos."
+    for key in [k for k in state_dict if k.startswith(pre)]:
+        module._rhos_extra[key[len(prefix):]] = state_dict.pop(key).detach().clone()
 
 
 class TensorGNAN(_Base):
@@ -176,6 +202,12 @@ class GNAN(_Base):
         self.normalize_rho = normalize_rho
         self.fs = StackedMLP(in_channels, out_channels, n_layers, hidden_channels, bias, 3, dropout)
         self.rho = StackedMLP(1, out_channels if rho_per_feature else 1, n_layers, hidden_channels, bias, 2, single=True)
+        if rho_per_feature:
+            # the reference also registers `rhos`, K never-used copies of the distance MLP, the last one sharing its
+            # tensors with `rho` (GNAN.py:108-124,141): carried through state_dict so that checkpoints round-trip
+            self._rhos_extra = {}
+            self._register_state_dict_hook(_emit_rhos)
+            self.register_load_state_dict_pre_hook(_absorb_rhos)
 
     def forward(self, inputs, node_ids=None):
         dev = self._device()

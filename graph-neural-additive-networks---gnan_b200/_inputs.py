@@ -21,6 +21,9 @@ def compressed_of(holder, x, device, enabled=True):
     if not enabled:
         return None
     cx = getattr(holder, "x_compressed", None)
+    if cx is None and x is not None and torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+        return None        # an implicit (cached) compressed form would be baked into the CUDA graph and go stale when x is
+                           # refreshed in place between replays; pass x_compressed explicitly to share evaluations there
     if cx is None and x is not None:
         from .preprocess import PackedBatch
         if isinstance(holder, PackedBatch) and not getattr(holder, "_gnan_b200_persistent", False):

@@ -13,6 +13,8 @@ c_void_p, c_int, c_int32, c_int64, c_size_t, c_float, c_uint64 = (
 PREC_FP32, PREC_TF32X3, PREC_TF32 = 0, 1, 2
 PRECISIONS = {"fp32": PREC_FP32, "tf32x3": PREC_TF32X3, "tf32": PREC_TF32}
 HOP_UNREACHABLE = 255
+AGG_AUTO, AGG_CUDA_CORES, AGG_TENSOR_CORES = 0, 1, 2
+AGG_ALGOS = {"auto": AGG_AUTO, "cuda": AGG_CUDA_CORES, "tc": AGG_TENSOR_CORES}
 
 
 class MlpParams(ctypes.Structure):
@@ -49,6 +51,10 @@ SIGNATURES = {
                                         c_void_p, c_int32, c_void_p, c_void_p]),
     "gnan_aggregate_rows_fwd_save": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int32, c_int32, c_void_p,
                                              c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    "gnan_aggregate_rows_tc_supported": (c_int, [c_int64, c_int64, c_int64, c_int32, c_int32]),
+    "gnan_aggregate_rows_fwd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int32, c_int32]),
+    "gnan_aggregate_rows_fwd_ws": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int32, c_int32, c_void_p,
+                                           c_void_p, c_int32, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
     "gnan_aggregate_rows_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32, c_int32, c_int32]),
     "gnan_aggregate_rows_bwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int32, c_int32, c_void_p,
                                         c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

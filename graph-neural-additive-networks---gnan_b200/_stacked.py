@@ -104,10 +104,12 @@ class StackedMLP(nn.Module):
             raise TypeError("a list of shape functions is not callable; use fs[k](t)")
         return MLPView(self, 0)(t)
 
-    def named_parameters(self, prefix="", recurse=True, remove_duplicate=True):
-        if self._single and prefix == "":          # `model.rho.named_parameters()` as in GNAN.print_rho_params (GNAN.py:174-176)
-            return MLPView(self, 0).named_parameters()
-        return super().named_parameters(prefix=prefix, recurse=recurse, remove_duplicate=remove_duplicate)
+    def reference_named_parameters(self):
+        """(name, tensor) pairs under the reference's Sequential key names ("0.weight", "2.bias", ...) for a single MLP:
+        views of the stacked storage, for printing / inspection only. `named_parameters()` / `parameters()` keep
+        nn.Module semantics (the stacked leaf Parameters), so optimizers, zero_grad and clip_grad_norm_ work on
+        `model.rho.parameters()`."""
+        return MLPView(self, 0).named_parameters()
 
 
 class MLPView(nn.Module):

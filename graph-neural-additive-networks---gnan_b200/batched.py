@@ -69,10 +69,18 @@ class TensorGNAN(_Base):
         S = self._feature_sums(*self._features(pk))
         nb = pk.nbins
         p = self.rho.dropout if self.training else 0.0
-        T = ops.mlp(ops.rho_table_inputs(nb, dev, raw=True).reshape(-1, 1), *self.rho.kernel_args(), dropout_p=p,
-                    seed=self._seed() if p > 0 else 0, precision=self.precision,
-                    seed_dev=self._seed_word() if p > 0 else None)                        # rho(d), d = 0..nbins-2
         keep = torch.ones(nb, 1, device=dev)
         keep[-1] = 0.0                                                                    # masked pairs: :158-159
-        T = T * keep
+        u = ops.rho_table_inputs(nb, dev, raw=True)                                       # d = 0..nbins-2
+        if p > 0:
+            # The reference runs rho (with its Dropout) on every pair (:125-131,154): an independent mask per pair. A single
+            # [nbins] table would share ONE mask between all pairs at the same distance; here every ROW gets its own table
+            # (independent masks per (row, distance)), so pairs of different rows are independent and only a row's pairs at
+            # equal distance share a mask. Exact per-pair masks would need sum n_b^2 rho evaluations.
+            n_rows = S.shape[0]
+            T = ops.mlp(u.repeat(n_rows).reshape(-1, 1), *self.rho.kernel_args(), dropout_p=p, seed=self._seed(),
+                        precision=self.precision, seed_dev=self._seed_word())
+            T = (T.view(n_rows, nb, -1) * keep).contiguous()
+            return ops.aggregate_blockdiag(pk.hop, pk.hop_off, pk.node_off, T, S, per_row=True, reduce_graph=self.is_graph_task)
+        T = ops.mlp(u.reshape(-1, 1), *self.rho.kernel_args(), precision=self.precision) * keep
         return ops.aggregate_blockdiag(pk.hop, pk.hop_off, pk.node_off, T, S, reduce_graph=self.is_graph_task)

@@ -1,0 +1,490 @@
+// Tensor-core aggregation over the uint8 hop matrix: one pass over the hop bytes for ALL channels.
+//
+// Reference lines replaced: GNAN.py:64-73 (rho on N*N pairs, permute, matmul(m_dist_perm, fx_perm), sum), GNAN.py:159-170,
+// models.py:366-375; backward = autograd through the same.
+//
+// Distance-class form.  With b(h) the bin of a hop byte, the reference's [C,N,N] x [C,N,K] contraction is
+//     Bsum[i,d,c] = sum_j 1[b(hop[i,j]) = d] * S[j,c]            (a GEMM with a 0/1 operand)
+//     out[i,c]    = sum_d T[ti,d,c'] * rscale[i,d] * Bsum[i,d,c]
+// Bsum is also everything the backward needs for dT.  The 0/1 operand is generated on the fly and never exists in memory:
+//   * the hop tile [rows x 128 columns] lands in shared memory by TMA (cp.async.bulk.tensor.2d, uint8 tensor map);
+//   * a generator thread owns one TMEM lane = one (row, bin) pair. The hop bytes of its row are packed to 4-bit selectors
+//     once per tile (cooperatively), and ONE `prmt` with a per-thread 8-byte lookup table (0x01 at byte bin%8) turns four
+//     selectors into four int8 one-hot values (selector bit 3 = "other half of the bins" -> 0 through prmt's sign-replicate
+//     mode). The values go straight into tensor memory with tcgen05.st: the A operand never touches shared memory;
+//   * S is quantised per channel to ndig signed 8-bit digits of a common power-of-two scale (exact integer arithmetic:
+//     S*2^sh rounded once, abs. error <= 2^-31 (4 digits) or 2^-23 (3 digits) of the column maximum); the digit matrix is the
+//     B operand, pre-laid-out in the UMMA K-major core-matrix order by a small pre-pass so that a stage is one bulk copy;
+//   * tcgen05.mma kind::i8 accumulates int32 in TMEM over the whole row sweep: the bin sums are EXACT sums of the quantised
+//     values, independent of summation order (deterministic), and are rounded to fp32 once in the epilogue.
+// Cost per hop byte: ~0.5 ALU instructions per (pair, bin) + NP*NB/256 tensor cycles per 32 bytes, independent of C up to
+// NP = 16*ceil(C/4|5) accumulator columns.
+//
+// Backward dS[j,c] = sum_{i,d} 1[b(hop[i,j]) = d] * TG[i,d,c],  TG = T*rscale*g: the same machinery transposed (a TMEM lane
+// = a hop COLUMN j, the contraction index is (row, bin)); rows whose g is entirely zero are skipped (exact): with a
+// train-mask loss that is almost all of them.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace {
+
+constexpr int TCOLS = 128;        // hop columns per pipeline stage (TMA box inner extent, bytes)
+constexpr int MAX_STAGES = 16;
+
+// ---- PTX: TMA + the i8 MMA -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map)
+{
+    asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+// generic-mode prmt: selector nibble bit 3 replicates the msb of the selected byte (0 for our 0x00/0x01 table)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+// instruction descriptor, kind::i8: signed 8-bit A and B (K-major), int32 accumulate
+__host__ __device__ constexpr uint32_t umma_idesc_i8(int M, int N)
+{
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accum)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}\n"
+                 :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accum) : "memory");
+}
+
+// B operand of one stage: NP rows (accumulator columns) x 128 K-bytes, UMMA K-major no-swizzle core matrices
+// (8 rows x 16 bytes = 128 contiguous bytes); K-adjacent core matrices 128 B apart (LBO), 8-row groups 1024 B apart (SBO)
+constexpr uint32_t DG_LBO = 128, DG_SBO = 1024, DG_KSTEP = 256;
+__host__ __device__ inline size_t digit_offset(int n, int k) { return (size_t)(n >> 3) * 1024 + (k >> 4) * 128 + (n & 7) * 16 + (k & 15); }
+
+// digit layout along the accumulator columns: a 16-column chunk holds CPC channels x ndig digits (never straddles a chunk)
+struct DigitPlan { int ndig, cpc, NP; };
+inline DigitPlan digit_plan(int C)
+{
+    const int c4 = (C + 3) / 4, c5 = (C + 4) / 5;
+    DigitPlan p;
+    if (c4 == c5) { p.ndig = 4; p.cpc = 4; p.NP = 16 * c4; }
+    else { p.ndig = 3; p.cpc = 5; p.NP = 16 * c5; }
+    return p;
+}
+
+// ---- pre-pass: per-channel scale and the digit matrix -------------------------------------------------------------------
+__global__ void colmax_kernel(const float *__restrict__ S, int64_t n_rows, int C, uint32_t *__restrict__ colmax)
+{
+    // |x| as uint32 orders like the float for non-negative values; one atomicMax per warp and channel
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int c = 0; c < C; ++c) {
+        uint32_t m = 0;
+        for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_rows; j += stride)
+            m = max(m, __float_as_uint(fabsf(S[j * C + c])));
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, s));
+        if ((threadIdx.x & 31) == 0 && m) atomicMax(colmax + c, m);
+    }
+}
+
+// shift sh such that |x * 2^sh| <= 2^(8*ndig-2) for every |x| <= colmax
+__device__ __forceinline__ int digit_shift(uint32_t colmax_bits, int ndig)
+{
+    if (colmax_bits == 0) return 0;
+    const int e = (int)((colmax_bits >> 23) & 0xff) - 127 + 1;       // colmax < 2^e  (subnormal colmax: e = -126, harmless)
+    return 8 * ndig - 2 - e;
+}
+
+// one thread per (column block, accumulator column n, k): Sdig[blk][digit_offset(n,k)]; row_map (optional) gathers rows
+__global__ void digits_kernel(const float *__restrict__ X, int64_t n_rows, int C, int ld_x, const int32_t *__restrict__ row_map,
+                              const uint32_t *__restrict__ colmax, int ndig, int cpc, int NP, int8_t *__restrict__ dig,
+                              int32_t *__restrict__ colsh)
+{
+    const int blk = blockIdx.x;
+    if (blk == 0 && threadIdx.x < C) colsh[threadIdx.x] = digit_shift(colmax[threadIdx.x], ndig);
+    for (int t = threadIdx.x; t < NP * TCOLS; t += blockDim.x) {
+        const int n = t / TCOLS, k = t % TCOLS;
+        const int64_t j = (int64_t)blk * TCOLS + k;
+        const int chunk = n >> 4, w = n & 15, cc = w / ndig, kd = w % ndig;
+        const int c = chunk * cpc + cc;
+        int8_t v = 0;
+        if (j < n_rows && cc < cpc && c < C) {
+            const int64_t src = row_map ? row_map[j] : j;
+            const float x = X[src * ld_x + c];
+            const int sh = digit_shift(colmax[c], ndig);
+            long long q = __double2ll_rn(ldexp((double)x, sh));
+            for (int s = 0; s < kd; ++s) {                      // balanced base-256 digits in [-128, 127]
+                const long long b = ((q + 128) & 255) - 128;
+                q = (q - b) >> 8;
+            }
+            v = (int8_t)(((q + 128) & 255) - 128);
+            if (kd == ndig - 1) v = (int8_t)q;                   // top digit carries the rest (|q| <= 65 by construction)
+        }
+        dig[(size_t)blk * NP * TCOLS + digit_offset(n, k)] = v;
+    }
+}
+
+// ---- forward -------------------------------------------------------------------------------------------------------------
+struct AggTcArgs {
+    int64_t R, N;
+    int nbins, C, Cr, per_row, ndig, cpc, NP, nblk, stages;
+    const float *T, *rscale;
+    const int32_t *colsh;
+    const int8_t *dig;
+    float *out, *Bsum;
+};
+
+// 8 hop bytes -> 8 four-bit selectors (selector k in nibble k); NB = bins per row slot
+template <int NB>
+__device__ __forceinline__ uint32_t pack8(uint2 w, int stream)
+{
+    uint32_t a = w.x, b = w.y;
+    if (NB == 32) {
+        const uint32_t q = 0x01010101u * (uint32_t)stream;
+        const uint32_t a5 = a & 0x1f1f1f1fu, b5 = b & 0x1f1f1f1fu;
+        uint32_t xa = ((a5 >> 3) & 0x03030303u) ^ q, xb = ((b5 >> 3) & 0x03030303u) ^ q;
+        xa = (xa | (xa >> 1)) & 0x01010101u;
+        xb = (xb | (xb >> 1)) & 0x01010101u;
+        a = (a5 & 0x07070707u) | (xa << 3);
+        b = (b5 & 0x07070707u) | (xb << 3);
+    } else {
+        constexpr uint32_t M = NB == 16 ? 0x0f0f0f0fu : 0x07070707u;   // 255 (unreachable) -> the last slot
+        a &= M;
+        b &= M;
+    }
+    a |= a >> 4;
+    b |= b >> 4;
+    uint32_t p = prmt(a, b, 0x6420u);
+    if (NB == 16 && stream) p ^= 0x88888888u;
+    return p;
+}
+
+template <int NB, int NGR>
+struct TcCfg {
+    static constexpr int RG = 128 / NB;             // hop rows per generator group (one MMA: M = 128 = RG rows x NB bins)
+    static constexpr int ROWS = RG * NGR;           // hop rows per CTA
+    static constexpr int NSTREAM = NB / 8;          // selector streams (one per group of 8 bins)
+    static constexpr int HOPB = ROWS * TCOLS;       // hop bytes per stage
+    static constexpr int NIB_WORDS = 2 * NSTREAM * RG * 16;   // per group: [buf][stream][row][16 words]
+    static constexpr int ACC0 = NGR * 64;           // TMEM: A buffers [g][buf] 32 columns each, then the accumulators
+    static constexpr int THREADS = (NGR * 4 + 2) * 32;
+};
+
+template <int NB, int NGR>
+__global__ void __launch_bounds__(TcCfg<NB, NGR>::THREADS, 1)
+agg_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, AggTcArgs a)
+{
+    using Cfg = TcCfg<NB, NGR>;
+    constexpr int RG = Cfg::RG, NSTREAM = Cfg::NSTREAM, HOPB = Cfg::HOPB;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int BB = a.NP * TCOLS;
+    uint8_t *hop_s = smem;
+    uint8_t *b_s = hop_s + (size_t)a.stages * HOPB;
+    uint32_t *nib_s = reinterpret_cast<uint32_t *>(b_s + (size_t)a.stages * BB);
+    uint64_t *full = reinterpret_cast<uint64_t *>(nib_s + NGR * Cfg::NIB_WORDS);
+    uint64_t *empty = full + MAX_STAGES;
+    uint64_t *a_full = empty + MAX_STAGES;          // [NGR][2]
+    uint64_t *a_empty = a_full + NGR * 2;           // [NGR][2]
+    uint64_t *acc_full = a_empty + NGR * 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t row0 = (int64_t)blockIdx.x * Cfg::ROWS;
+
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (tid == 32) {
+        for (int s = 0; s < a.stages; ++s) {
+            mbar_init(smem_u32(&full[s]), 1);
+            mbar_init(smem_u32(&empty[s]), 1);
+        }
+        for (int g = 0; g < NGR * 2; ++g) {
+            mbar_init(smem_u32(&a_full[g]), 128);
+            mbar_init(smem_u32(&a_empty[g]), 1);
+        }
+        mbar_init(smem_u32(acc_full), 1);
+        mbar_init_fence();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < NGR * 4) {
+        // ===== generators: thread m of group g owns TMEM lane m = (row r, bin slot) =====
+        const int g = warp >> 2, m = tid & 127;
+        const int r = m / NB, slot = m % NB, strm = slot >> 3;
+        const uint32_t lut_lo = (slot & 7) < 4 ? 1u << (8 * (slot & 7)) : 0u;
+        const uint32_t lut_hi = (slot & 7) >= 4 ? 1u << (8 * ((slot & 7) - 4)) : 0u;
+        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        uint32_t *nib_g = nib_s + g * Cfg::NIB_WORDS;
+        for (int s = 0; s < a.nblk; ++s) {
+            const int st = s % a.stages, buf = s & 1;
+            mbar_wait(smem_u32(&full[st]), (uint32_t)(s / a.stages) & 1u);
+            uint32_t *nb = nib_g + buf * (NSTREAM * RG * 16);
+            const uint8_t *hs = hop_s + (size_t)st * HOPB + (size_t)g * RG * TCOLS;
+#pragma unroll
+            for (int ch = m; ch < RG * 16; ch += 128) {               // pack: 8 bytes -> one selector word per stream
+                const uint2 w = *reinterpret_cast<const uint2 *>(hs + ch * 8);
+#pragma unroll
+                for (int q = 0; q < NSTREAM; ++q) nb[q * (RG * 16) + ch] = pack8<NB>(w, q);
+            }
+            named_bar_sync(1 + g, 128);
+            if (s >= 2) {
+                mbar_wait(smem_u32(&a_empty[g * 2 + buf]), (uint32_t)((s >> 1) - 1) & 1u);
+                tc_fence_after();
+            }
+            const uint4 *src = reinterpret_cast<const uint4 *>(nb + strm * (RG * 16) + r * 16);
+            uint32_t v[32];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint4 p = src[q];
+                v[8 * q + 0] = prmt(lut_lo, lut_hi, p.x); v[8 * q + 1] = prmt(lut_lo, lut_hi, p.x >> 16);
+                v[8 * q + 2] = prmt(lut_lo, lut_hi, p.y); v[8 * q + 3] = prmt(lut_lo, lut_hi, p.y >> 16);
+                v[8 * q + 4] = prmt(lut_lo, lut_hi, p.z); v[8 * q + 5] = prmt(lut_lo, lut_hi, p.z >> 16);
+                v[8 * q + 6] = prmt(lut_lo, lut_hi, p.w); v[8 * q + 7] = prmt(lut_lo, lut_hi, p.w >> 16);
+            }
+            tmem_st32(lane_base + (uint32_t)((g * 2 + buf) * 32), v);
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(smem_u32(&a_full[g * 2 + buf]));
+        }
+        // ===== epilogue: Bsum (exact integer bin sums -> fp32) and out = sum_d T * rscale * Bsum =====
+        mbar_wait(smem_u32(acc_full), 0);
+        tc_fence_after();
+        const int64_t i = row0 + g * RG + r;
+        const bool slot_ok = slot < a.nbins - 1 || slot == NB - 1;
+        const int d = slot == NB - 1 ? a.nbins - 1 : slot;
+        const bool ok = i < a.R && slot_ok;
+        const float rs = (ok && a.rscale) ? a.rscale[i * a.nbins + d] : 1.f;
+        const float *Trow = a.T + ((a.per_row && ok) ? i * a.nbins * a.Cr : 0) + (ok ? d * a.Cr : 0);
+        for (int n0 = 0; n0 < a.NP; n0 += 16) {
+            uint32_t acc[16];
+            tmem_ld16(lane_base + (uint32_t)(Cfg::ACC0 + g * a.NP + n0), acc);
+            tmem_wait_ld();
+#pragma unroll
+            for (int cc = 0; cc < 5; ++cc) {
+                const int c = (n0 >> 4) * a.cpc + cc;
+                if (cc >= a.cpc || c >= a.C) break;
+                long long tot = 0;
+                if (a.ndig == 4) {
+#pragma unroll
+                    for (int k = 3; k >= 0; --k) tot = tot * 256 + (int)acc[(cc * 4 + k) & 15];
+                } else {
+#pragma unroll
+                    for (int k = 2; k >= 0; --k) tot = tot * 256 + (int)acc[(cc * 3 + k) & 15];
+                }
+                const float bs = (float)ldexp((double)tot, -a.colsh[c]);
+                if (ok && a.Bsum) a.Bsum[(i * a.nbins + d) * a.C + c] = bs;
+                float o = ok ? Trow[a.Cr == 1 ? 0 : c] * rs * bs : 0.f;
+#pragma unroll
+                for (int sft = NB / 2; sft > 0; sft >>= 1) o += __shfl_xor_sync(0xffffffffu, o, sft);
+                if (slot == 0 && i < a.R) a.out[i * a.C + c] = o;
+            }
+        }
+        tc_fence_before();
+    } else if (warp == NGR * 4) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            prefetch_tmap(&tmap);
+            for (int s = 0; s < a.nblk; ++s) {
+                const int st = s % a.stages;
+                if (s >= a.stages) mbar_wait(smem_u32(&empty[st]), (uint32_t)(s / a.stages - 1) & 1u);
+                const uint32_t bar = smem_u32(&full[st]);
+                mbar_expect_tx(bar, (uint32_t)(HOPB + BB));
+                tma_load_2d(smem_u32(hop_s + (size_t)st * HOPB), &tmap, s * TCOLS, (int)row0, bar);
+                bulk_load_1d(smem_u32(b_s + (size_t)st * BB), a.dig + (size_t)s * BB, (uint32_t)BB, bar);
+            }
+        }
+    } else {
+        // ===== MMA issuer =====
+        const uint32_t idesc = umma_idesc_i8(128, a.NP);
+        for (int s = 0; s < a.nblk; ++s) {
+            const int st = s % a.stages, buf = s & 1;
+            mbar_wait(smem_u32(&full[st]), (uint32_t)(s / a.stages) & 1u);
+            for (int g = 0; g < NGR; ++g) {
+                mbar_wait(smem_u32(&a_full[g * 2 + buf]), (uint32_t)(s >> 1) & 1u);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t bb = smem_u32(b_s + (size_t)st * BB);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma_i8_ts(tmem + (uint32_t)(Cfg::ACC0 + g * a.NP), tmem + (uint32_t)((g * 2 + buf) * 32 + ks * 8),
+                                   umma_desc_kmajor(bb + ks * DG_KSTEP, DG_LBO, DG_SBO), idesc, (s > 0 || ks > 0) ? 1u : 0u);
+                    umma_commit(smem_u32(&a_empty[g * 2 + buf]));
+                }
+                __syncwarp();
+            }
+            if (lane == 0) umma_commit(smem_u32(&empty[st]));
+            __syncwarp();
+        }
+        if (lane == 0) umma_commit(smem_u32(acc_full));
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// uint8 [rows, ld] matrix, box = [box_rows x 128 bytes]; out-of-range elements read as 0
+int make_hop_tmap(CUtensorMap *map, const uint8_t *hop, int64_t rows, int64_t ld, int box_rows)
+{
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) {
+        gnan_set_error("aggregate_rows (tensor-core path): cuTensorMapEncodeTiled is not available from this driver");
+        return GNAN_ERR_CUDA;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)ld};
+    const cuuint32_t box[2] = {(cuuint32_t)TCOLS, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult rc = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t *>(hop), gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        gnan_set_error("aggregate_rows (tensor-core path): cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld ld=%lld)", (int)rc,
+                       (long long)rows, (long long)ld);
+        return GNAN_ERR_CUDA;
+    }
+    return GNAN_OK;
+}
+
+inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+struct FwdWs { uint32_t *colmax; int32_t *colsh; int8_t *dig; size_t total; };
+FwdWs fwd_ws_layout(void *base, int64_t N, int C)
+{
+    const DigitPlan p = digit_plan(C);
+    const int64_t nblk = ceil_div64(N, TCOLS);
+    FwdWs w;
+    uint8_t *b = (uint8_t *)base;
+    w.colmax = (uint32_t *)b;
+    w.colsh = (int32_t *)(b + align256(sizeof(uint32_t) * C));
+    w.dig = (int8_t *)(b + 2 * align256(sizeof(uint32_t) * C));
+    w.total = 2 * align256(sizeof(uint32_t) * C) + (size_t)nblk * p.NP * TCOLS;
+    return w;
+}
+
+template <int NB, int NGR>
+int launch_fwd(const CUtensorMap &map, AggTcArgs a, cudaStream_t st)
+{
+    using Cfg = TcCfg<NB, NGR>;
+    const size_t per_stage = (size_t)Cfg::HOPB + (size_t)a.NP * TCOLS;
+    const size_t fixed = sizeof(uint32_t) * NGR * Cfg::NIB_WORDS + sizeof(uint64_t) * (2 * MAX_STAGES + 4 * NGR + 1) + 16;
+    int stages = (int)std::min<size_t>(MAX_STAGES, (200 * 1024 - fixed) / per_stage);
+    if (stages < 2) {
+        gnan_set_error("aggregate_rows (tensor-core path): stage of %zu bytes does not fit shared memory", per_stage);
+        return GNAN_ERR_UNSUPPORTED;
+    }
+    stages = std::min(stages, std::max(2, a.nblk));
+    a.stages = stages;
+    const size_t smem = fixed + per_stage * stages;
+    GNAN_CUDA(cudaFuncSetAttribute(agg_tc_fwd_kernel<NB, NGR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)ceil_div64(a.R, Cfg::ROWS);
+    agg_tc_fwd_kernel<NB, NGR><<<grid, Cfg::THREADS, smem, st>>>(map, a);
+    GNAN_LAUNCH_OK();
+    return GNAN_OK;
+}
+
+template <int NB>
+int launch_fwd_nb(const CUtensorMap &map, const AggTcArgs &a, int ngr, cudaStream_t st)
+{
+    if (ngr == 4) return launch_fwd<NB, 4>(map, a, st);
+    if (ngr == 2) return launch_fwd<NB, 2>(map, a, st);
+    return launch_fwd<NB, 1>(map, a, st);
+}
+
+}  // namespace
+
+// 1 when the tensor-core path covers the shape (nbins <= 32, accumulator columns <= 256, a matrix worth a TMA pipeline)
+extern "C" int gnan_aggregate_rows_tc_supported(int64_t R, int64_t N, int64_t ld_hop, int32_t nbins, int32_t C)
+{
+    if (R < 1 || N < 256 || ld_hop < TCOLS || nbins < 2 || nbins > 32 || C < 1) return 0;
+    return digit_plan(C).NP <= 256 ? 1 : 0;
+}
+
+extern "C" size_t gnan_aggregate_rows_fwd_workspace_bytes(int64_t R, int64_t N, int64_t ld_hop, int32_t nbins, int32_t C)
+{
+    if (!gnan_aggregate_rows_tc_supported(R, N, ld_hop, nbins, C)) return 0;
+    return fwd_ws_layout(nullptr, N, C).total;
+}
+
+extern "C" int gnan_aggregate_rows_fwd_ws(const uint8_t *hop, int64_t R, int64_t N, int64_t ld_hop, const float *T,
+                                          int table_per_row, int32_t nbins, int32_t Cr, const float *rscale, const float *S,
+                                          int32_t C, float *out, float *Bsum, int algo, void *workspace, size_t workspace_bytes,
+                                          gnan_stream_t stream)
+{
+    const bool can_tc = gnan_aggregate_rows_tc_supported(R, N, ld_hop, nbins, C) != 0;
+    if (algo == GNAN_AGG_CUDA_CORES || (algo == GNAN_AGG_AUTO && !can_tc))
+        return gnan_aggregate_rows_fwd_save(hop, R, N, ld_hop, T, table_per_row, nbins, Cr, rscale, S, C, out, Bsum, stream);
+    GNAN_REQUIRE(algo == GNAN_AGG_AUTO || algo == GNAN_AGG_TENSOR_CORES, "aggregate_rows_fwd_ws: unknown algo %d", algo);
+    if (!can_tc) {
+        gnan_set_error("aggregate_rows_fwd_ws: the tensor-core path needs N >= 256, nbins <= 32 and <= 256 accumulator columns "
+                       "(N=%lld nbins=%d C=%d)", (long long)N, nbins, C);
+        return GNAN_ERR_UNSUPPORTED;
+    }
+    GNAN_REQUIRE(hop && T && S && out, "aggregate_rows_fwd_ws: NULL hop/T/S/out");
+    GNAN_REQUIRE(ld_hop >= N && ld_hop % 16 == 0 && ((uintptr_t)hop % 16) == 0, "aggregate_rows_fwd_ws: hop rows must be 16-byte aligned with ld %% 16 == 0");
+    GNAN_REQUIRE(Cr == 1 || Cr == C, "aggregate_rows_fwd_ws: Cr must be 1 or C");
+    const FwdWs w = fwd_ws_layout(workspace, N, C);
+    if (!workspace || workspace_bytes < w.total) {
+        gnan_set_error("aggregate_rows_fwd_ws: workspace %zu < %zu bytes", workspace_bytes, w.total);
+        return GNAN_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const DigitPlan p = digit_plan(C);
+    const int nblk = (int)ceil_div64(N, TCOLS);
+    GNAN_CUDA(cudaMemsetAsync(w.colmax, 0, sizeof(uint32_t) * C, st));
+    colmax_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(N, 256), 4 * gnan_sm_count()), 256, 0, st>>>(S, N, C, w.colmax);
+    GNAN_LAUNCH_OK();
+    digits_kernel<<<nblk, 256, 0, st>>>(S, N, C, C, nullptr, w.colmax, p.ndig, p.cpc, p.NP, w.dig, w.colsh);
+    GNAN_LAUNCH_OK();
+
+    AggTcArgs a{R, N, nbins, C, Cr, table_per_row, p.ndig, p.cpc, p.NP, nblk, 0, T, rscale, w.colsh, w.dig, out, Bsum};
+    const int ngr = p.NP <= 64 ? 4 : (p.NP <= 192 ? 2 : 1);
+    const int nb = nbins <= 8 ? 8 : (nbins <= 16 ? 16 : 32);
+    CUtensorMap map;
+    int rc = make_hop_tmap(&map, hop, R, ld_hop, (128 / nb) * ngr);
+    if (rc) return rc;
+    if (nb == 8) return launch_fwd_nb<8>(map, a, ngr, st);
+    if (nb == 16) return launch_fwd_nb<16>(map, a, ngr, st);
+    return launch_fwd_nb<32>(map, a, ngr, st);
+}

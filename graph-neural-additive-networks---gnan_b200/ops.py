@@ -196,21 +196,25 @@ def _agg_dims(hop, T, S, per_row):
 
 
 @torch.library.custom_op("gnan_b200::agg_rows_fwd", mutates_args=())
-def agg_rows_fwd(hop: Tensor, T: Tensor, rscale: Optional[Tensor], S: Tensor, per_row: bool, save: bool) -> Tuple[Tensor, Tensor]:
+def agg_rows_fwd(hop: Tensor, T: Tensor, rscale: Optional[Tensor], S: Tensor, per_row: bool, save: bool,
+                 algo: int = 0) -> Tuple[Tensor, Tensor]:
     lib = load()
     T, S = _f32(T, "T"), _f32(S, "S")
     rscale = None if rscale is None else _f32(rscale, "rscale")
     R, ld, N, C, nbins, Cr = _agg_dims(hop, T, S, per_row)
     out = torch.empty(R, C, dtype=torch.float32, device=S.device)
     bsum = torch.empty((R, nbins, C) if save else (0,), dtype=torch.float32, device=S.device)
+    nws = 0 if algo == _lib.AGG_CUDA_CORES else lib.gnan_aggregate_rows_fwd_workspace_bytes(R, N, ld, nbins, C)
+    ws = _ws(nws, S.device)
     with _timed("aggregate_rows_fwd_save"):
-        check(lib.gnan_aggregate_rows_fwd_save(ptr(hop), R, N, ld, ptr(T), int(per_row), nbins, Cr, ptr(rscale), ptr(S), C,
-                                               ptr(out), ptr(bsum), stream_handle()), "gnan_aggregate_rows_fwd")
+        check(lib.gnan_aggregate_rows_fwd_ws(ptr(hop), R, N, ld, ptr(T), int(per_row), nbins, Cr, ptr(rscale), ptr(S), C,
+                                             ptr(out), ptr(bsum), int(algo), ptr(ws) if nws else None, nws, stream_handle()),
+              "gnan_aggregate_rows_fwd")
     return out, bsum
 
 
 @agg_rows_fwd.register_fake
-def _(hop, T, rscale, S, per_row, save):
+def _(hop, T, rscale, S, per_row, save, algo=0):
     R, C, nbins = hop.shape[0], S.shape[1], T.shape[-2]
     return S.new_empty(R, C), S.new_empty((R, nbins, C) if save else (0,))
 
@@ -238,24 +242,28 @@ def _(hop, T, rscale, S, per_row, g, bsum):
 
 
 def _agg_setup(ctx, inputs, output):
-    hop, T, rscale, S, per_row, save = inputs
+    hop, T, rscale, S, per_row, save, algo = inputs
     ctx.save_for_backward(hop, T, rscale, S, output[1])
     ctx.per_row = per_row
+    ctx.algo = algo
 
 
 def _agg_backward(ctx, g, _g_bsum):
     hop, T, rscale, S, bsum = ctx.saved_tensors
     dS, dT = agg_rows_bwd(hop, T, rscale, S, ctx.per_row, g.contiguous(), bsum)
-    return None, dT, None, dS, None, None
+    return None, dT, None, dS, None, None, None
 
 
 agg_rows_fwd.register_autograd(_agg_backward, setup_context=_agg_setup)
 
 
-def aggregate_rows(hop, T, S, rscale=None, per_row=False):
+AGG_ALGO = "auto"      # "auto" | "cuda" | "tc": kernel family of aggregate_rows (gnan_b200.h: GNAN_AGG_*); tests force each
+
+
+def aggregate_rows(hop, T, S, rscale=None, per_row=False, algo=None):
     """out[i,c] = sum_j T[(i,) b(hop[i,j]), c'] * rscale[i,b] * S[j,c] over a [R, ld] uint8 hop block; see gnan_b200.h."""
     save = torch.is_grad_enabled() and (T.requires_grad or S.requires_grad)
-    return agg_rows_fwd(hop, T, rscale, S, bool(per_row), bool(save))[0]
+    return agg_rows_fwd(hop, T, rscale, S, bool(per_row), bool(save), _lib.AGG_ALGOS[algo or AGG_ALGO])[0]
 
 
 # ---------------------------------------------------------------------------------------------------------------------

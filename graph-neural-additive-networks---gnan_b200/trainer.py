@@ -190,6 +190,11 @@ class CapturedStep:
         step = CapturedStep(lambda: loss_of(model(static_inputs)), optimizer)
         for epoch in ...: loss = step()                 # a device tensor, rewritten by every replay
     Refresh the static input tensors in place (`copy_`) between replays to train on new values of the same shape.
+    Shared evaluations (gnan_b200.sparse) inside a captured step are explicit only: the implicit per-object caches are
+    bypassed during capture (the dense kernels run), because a cached compressed form / value->row mapping would be baked
+    into the graph and go stale after an in-place refresh. To keep them, pass `x_compressed` (refresh it with
+    `CompressedFeatures.copy_tensors_`) and mark hop data whose level counts never change with
+    `hop_data.static_level_counts = True`.
     """
 
     def __init__(self, loss_closure, optimizer, warmup=3, after_backward=None):

@@ -156,6 +156,27 @@ int gnan_aggregate_rows_fwd_save(const uint8_t *hop, int64_t R, int64_t N, int64
                                  int table_per_row, int32_t nbins, int32_t Cr, const float *rscale, const float *S,
                                  int32_t C, float *out, float *Bsum, gnan_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Tensor-core form of the same aggregation (csrc/agg_tc.cu): the reference's matmul(m_dist_perm, fx_perm) (GNAN.py:70,
+ * models.py:371-372) as Bsum[(i,d), c] = sum_j 1[b(hop[i,j]) = d] * S[j,c] on tcgen05 (kind::i8, int32 accumulation in
+ * TMEM), the hop tiles streamed ONCE for all C channels by TMA and the 0/1 operand generated on the fly. S is quantised per
+ * channel to 3-4 signed 8-bit digits of a common power-of-two scale (absolute error <= 2^-23 / 2^-31 of the column's largest
+ * magnitude); the bin sums are exact integer sums of the quantised values (order-independent, deterministic), rounded to
+ * fp32 once. Covers nbins <= 32 and <= 256 accumulator columns; `algo` selects the kernel family.
+ * ---------------------------------------------------------------------------------------------- */
+enum {
+    GNAN_AGG_AUTO = 0,         /* tensor cores where the shape is covered, CUDA cores otherwise */
+    GNAN_AGG_CUDA_CORES = 1,   /* the fp32 bin-sum kernels of gnan_aggregate_rows_fwd_save / _bwd_saved */
+    GNAN_AGG_TENSOR_CORES = 2  /* fail with GNAN_ERR_UNSUPPORTED when the shape is not covered */
+};
+int gnan_aggregate_rows_tc_supported(int64_t R, int64_t N, int64_t ld_hop, int32_t nbins, int32_t C);
+size_t gnan_aggregate_rows_fwd_workspace_bytes(int64_t R, int64_t N, int64_t ld_hop, int32_t nbins, int32_t C);
+/* gnan_aggregate_rows_fwd_save with a kernel choice and a workspace (digit matrix of S; 0 bytes = CUDA-core path only) */
+int gnan_aggregate_rows_fwd_ws(const uint8_t *hop, int64_t R, int64_t N, int64_t ld_hop, const float *T, int table_per_row,
+                               int32_t nbins, int32_t Cr, const float *rscale, const float *S, int32_t C, float *out,
+                               float *Bsum /* or NULL */, int algo, void *workspace, size_t workspace_bytes,
+                               gnan_stream_t stream);
+
 size_t gnan_aggregate_rows_bwd_workspace_bytes(int64_t R, int64_t N, int32_t nbins, int32_t Cr, int32_t C);
 
 /* given g = dL/dout [R,C]:  dS[j,c] = sum_i W[i,j,c] g[i,c]   (overwritten; [N,C])

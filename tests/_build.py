@@ -4,7 +4,7 @@ import torch
 
 def build_module(z, device=None):
     v = z["variant"]
-    sd = {k: torch.tensor(val) for k, val in z["sd"].items() if not k.startswith("rhos.")}
+    sd = {k: torch.tensor(val) for k, val in z["sd"].items()}
     if v == "batched":
         from gnan_b200.batched import TensorGNAN
         m = TensorGNAN(z["K"], z["C"], 2, hidden_channels=z["H"], is_graph_task=z["is_graph_task"])

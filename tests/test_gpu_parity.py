@@ -375,6 +375,55 @@ def test_aggregate_rows_vs_oracle(R, N, C, Cr, nbins, per_row, scale):
         assert torch.equal(ops.aggregate_rows(hop, Tg, Sg, rscale=None if rs is None else rs.to(DEV), per_row=per_row), got.detach())
 
 
+# tensor-core form (csrc/agg_tc.cu): TMA-streamed hop tiles, on-the-fly 0/1 operand in TMEM, tcgen05 kind::i8 against the
+# digit matrix of S. NB = 8 / 16 / 32 bin slots, 1 / 2 / 4 generator groups (by accumulator width), ragged R and N.
+@pytest.mark.parametrize("R,N,C,Cr,nbins,per_row,scale", [
+    (37, 300, 3, 3, 6, True, False), (64, 2500, 7, 7, 12, False, True), (33, 4099, 4, 1, 16, False, True),
+    (20, 1000, 2, 2, 17, True, True), (129, 515, 40, 40, 9, False, False), (300, 700, 5, 1, 32, True, False),
+    (50, 260, 1, 1, 3, False, False), (70, 900, 64, 64, 14, True, True), (1, 256, 3, 3, 8, True, False)])
+def test_aggregate_rows_tensor_core_vs_oracle(R, N, C, Cr, nbins, per_row, scale):
+    from gnan_b200 import ops
+    rng = np.random.default_rng(R * 7 + N)
+    h = rng.integers(0, nbins, size=(R, N))
+    hop = torch.randint(0, 256, (R, ops.hop_ld(N)), dtype=torch.uint8, device=DEV)      # padding columns hold garbage
+    hb = h.copy(); hb[hb == nbins - 1] = 255
+    hop[:, :N] = torch.tensor(hb.astype(np.uint8), device=DEV)
+    T = torch.tensor(rng.normal(size=((R, nbins, Cr) if per_row else (nbins, Cr)))).float()
+    S = torch.tensor(rng.normal(size=(N, C)) * np.exp(rng.normal(size=(N, 1)) * 2)).float()   # magnitudes over ~4 decades
+    rs = torch.tensor(rng.random(size=(R, nbins)) + 0.1).float() if scale else None
+    gO = torch.tensor(rng.normal(size=(R, C))).float()
+    Td, Sd = T.double().requires_grad_(True), S.double().requires_grad_(True)
+    idx = torch.tensor(h)
+    W = (torch.gather(Td, 1, idx.unsqueeze(-1).expand(-1, -1, Cr)) if per_row else Td[idx])
+    if scale:
+        W = W * torch.gather(rs.double(), 1, idx).unsqueeze(-1)
+    want = (W * Sd.unsqueeze(0)).sum(1)
+    (want * gO.double()).sum().backward()
+    Tg, Sg = T.to(DEV).requires_grad_(True), S.to(DEV).requires_grad_(True)
+    got = ops.aggregate_rows(hop, Tg, Sg, rscale=None if rs is None else rs.to(DEV), per_row=per_row, algo="tc")
+    (got * gO.to(DEV)).sum().backward()
+    assert G.rel_err(got.detach().cpu().numpy(), want.detach().numpy()) < TOL
+    assert G.rel_err(Sg.grad.cpu().numpy(), Sd.grad.numpy()) < TOL
+    assert G.rel_err(Tg.grad.cpu().numpy(), Td.grad.numpy()) < TOL
+    # exact integer accumulation: bit-identical on a second run and under a column permutation of (hop, S)
+    with torch.no_grad():
+        again = ops.aggregate_rows(hop, Tg, Sg, rscale=None if rs is None else rs.to(DEV), per_row=per_row, algo="tc")
+        assert torch.equal(again, got.detach())
+        perm = torch.randperm(N, device=DEV)
+        hop_p = hop.clone(); hop_p[:, :N] = hop[:, :N][:, perm]
+        permuted = ops.aggregate_rows(hop_p, Tg, Sg[perm].contiguous(), rscale=None if rs is None else rs.to(DEV), per_row=per_row, algo="tc")
+        assert torch.equal(permuted, got.detach())
+
+
+def test_aggregate_rows_tensor_core_refuses_uncovered_shapes():
+    from gnan_b200 import ops
+    hop = ops.alloc_hop(8, 300, DEV)
+    with pytest.raises(NotImplementedError):
+        ops.aggregate_rows(hop, torch.zeros(40, 1, device=DEV), torch.zeros(300, 1, device=DEV), algo="tc")     # nbins > 32
+    out = ops.aggregate_rows(hop, torch.ones(40, 1, device=DEV), torch.ones(300, 1, device=DEV))                  # auto -> CUDA cores
+    assert float(out[0, 0]) == 300.0
+
+
 def test_blockdiag_equals_per_graph_dense_rows():
     """Property: the block-diagonal batch equals looping the dense-row kernel over graphs."""
     from gnan_b200 import ops

@@ -16,11 +16,11 @@ def test_loads_reference_state_dict(name):
     z = G.load(name)
     m = build_module(z)                      # strict load of the reference's own keys
     sd = m.state_dict()
-    ref = {k: v for k, v in z["sd"].items() if not k.startswith("rhos.")}
+    ref = z["sd"]                            # every key, incl. the never-used `rhos.{k}.*` of GNAN(rho_per_feature=True)
     assert sorted(sd) == sorted(ref)
     for k, v in ref.items():
         assert np.array_equal(sd[k].numpy(), v), k
-    n_ref = sum(v.size for v in ref.values())
+    n_ref = sum(v.size for k, v in ref.items() if not k.startswith("rhos."))     # rhos[K-1] shares rho's tensors upstream
     assert sum(p.numel() for p in m.parameters()) == n_ref
 
 
@@ -35,8 +35,11 @@ def test_shape_function_accessors_match_oracle(name):
         assert torch.allclose(m.fs[k].forward(t), gnan_port.scalar_mlp(fs, k, t), atol=1e-6)
     assert torch.allclose(m.rho(t), gnan_port.scalar_mlp(rho, 0, t), atol=1e-6)
     assert len(m.fs) == z["K"]
-    names = [n for n, _ in m.rho.named_parameters()]
+    names = [n for n, _ in m.rho.reference_named_parameters()]
     assert names[0] == "0.weight"
+    # nn.Module semantics are intact: leaf Parameters an optimizer can take
+    assert all(isinstance(p, torch.nn.Parameter) and p.is_leaf for p in m.rho.parameters())
+    torch.optim.Adam(m.rho.parameters(), lr=1e-3)
 
 
 def test_constructor_signatures_match_reference():
