@@ -55,6 +55,10 @@ SIGNATURES = {
     "gnan_aggregate_rows_fwd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int32, c_int32]),
     "gnan_aggregate_rows_fwd_ws": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int32, c_int32, c_void_p,
                                            c_void_p, c_int32, c_void_p, c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+    "gnan_aggregate_rows_bwd_ws_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_int]),
+    "gnan_aggregate_rows_bwd_ws": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int32, c_int32, c_void_p,
+                                           c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_size_t,
+                                           c_void_p]),
     "gnan_aggregate_rows_bwd_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32, c_int32, c_int32]),
     "gnan_aggregate_rows_bwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int32, c_int32, c_void_p,
                                         c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -65,6 +69,8 @@ SIGNATURES = {
                                              c_void_p, c_void_p, c_int32, c_int, c_void_p, c_void_p]),
     "gnan_aggregate_blockdiag_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int, c_int32, c_int32,
                                              c_void_p, c_void_p, c_int32, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gnan_build_csr_workspace_bytes": (c_size_t, [c_int32, c_int64]),
+    "gnan_build_csr": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "gnan_apsp_bfs_workspace_bytes": (c_size_t, [c_int32, c_int32]),
     "gnan_apsp_bfs": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int64, c_void_p, c_int32, c_void_p,
                               c_void_p, c_size_t, c_void_p]),

@@ -574,7 +574,7 @@ extern "C" int gnan_aggregate_rows_bwd_saved(const uint8_t *hop, int64_t R, int6
     }
     AggArgs a{hop, R, N, ld_hop, T, table_per_row, nbins, Cr, rscale, S, C};
     const DsPlan p = plan_ds(R, N);
-    const size_t need_ds = sizeof(float) * (size_t)p.nsb * N * C;
+    const size_t need_ds = dS ? sizeof(float) * (size_t)p.nsb * N * C : 0;
     const size_t need_bs = Bsum ? 0 : sizeof(float) * (size_t)R * nbins * C;
     if (workspace_bytes < need_ds + need_bs || (!workspace && need_ds + need_bs)) {
         gnan_set_error("aggregate_rows_bwd: workspace %zu < %zu bytes", workspace_bytes, need_ds + need_bs);

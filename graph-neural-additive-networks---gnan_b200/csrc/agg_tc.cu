@@ -345,6 +345,281 @@ agg_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, AggTcArgs a)
     }
 }
 
+// ---- backward: dS on the tensor cores, over the rows with a non-zero output gradient only --------------------------------
+// dS[j,c] = sum_i sum_d 1[b(hop[i,j]) = d] * TG[i,d,c],  TG[i,d,c] = T[ti,d,c'] * rscale[i,d] * g[i,c].
+// A row whose g is entirely zero contributes exactly nothing: a node task trained on a mask (trainer.py:52-58, main.py
+// train_mask) has a few hundred such rows out of N, so the rows are compacted first (ordered, deterministic) and only their
+// hop bytes are streamed. Layout: a TMEM lane = a hop COLUMN j, the contraction index is (active row, bin slot).
+
+__global__ void row_flags_kernel(const float *__restrict__ g, int64_t R, int C, uint8_t *__restrict__ flags)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    bool nz = false;
+    for (int c = 0; c < C; ++c) nz |= g[i * C + c] != 0.f;
+    flags[i] = nz ? 1 : 0;
+}
+
+// one CTA: ordered compaction of the flagged rows -> rows[0..nact), nact
+__global__ void __launch_bounds__(1024) compact_rows_kernel(const uint8_t *__restrict__ flags, int64_t R, int32_t *__restrict__ rows,
+                                                            int32_t *__restrict__ nact)
+{
+    __shared__ int wsum[32];
+    __shared__ int base_s;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) base_s = 0;
+    __syncthreads();
+    for (int64_t i0 = 0; i0 < R; i0 += 1024) {
+        const int64_t i = i0 + threadIdx.x;
+        const bool f = i < R && flags[i];
+        const unsigned b = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) wsum[w] = __popc(b);
+        __syncthreads();
+        int off = base_s;
+        for (int k = 0; k < w; ++k) off += wsum[k];
+        if (f) rows[off + __popc(b & ((1u << lane) - 1))] = (int32_t)i;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int k = 0; k < 32; ++k) t += wsum[k];
+            base_s += t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *nact = base_s;
+}
+
+struct TgArgs {
+    const float *T, *rscale, *g;
+    int per_row, nbins, Cr, C, NB;
+    const int32_t *rows, *nact;
+};
+
+// value of the B operand at (active row k, bin slot, channel c); slot NB-1 = the unreachable bin, slots in [nbins-1, NB-1) unused
+__device__ __forceinline__ float tg_value(const TgArgs &a, int k, int slot, int c)
+{
+    if (slot >= a.nbins - 1 && slot != a.NB - 1) return 0.f;
+    const int d = slot == a.NB - 1 ? a.nbins - 1 : slot;
+    const int64_t i = a.rows[k];
+    const int cr = a.Cr == 1 ? 0 : c;
+    float t = a.per_row ? a.T[(i * a.nbins + d) * a.Cr + cr] : a.T[d * a.Cr + cr];
+    if (a.rscale) t *= a.rscale[i * a.nbins + d];
+    return t * a.g[i * a.C + c];
+}
+
+__global__ void tg_colmax_kernel(TgArgs a, uint32_t *__restrict__ colmax)
+{
+    const int nact = *a.nact;
+    const int64_t total = (int64_t)nact * a.NB, stride = (int64_t)gridDim.x * blockDim.x;
+    for (int c = 0; c < a.C; ++c) {
+        uint32_t m = 0;
+        for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride)
+            m = max(m, __float_as_uint(fabsf(tg_value(a, (int)(t / a.NB), (int)(t % a.NB), c))));
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, s));
+        if ((threadIdx.x & 31) == 0 && m) atomicMax(colmax + c, m);
+    }
+}
+
+// digit matrix of TG: block = one pipeline stage = 128/NB active rows x NB slots = 128 contraction indices
+__global__ void tg_digits_kernel(TgArgs a, const uint32_t *__restrict__ colmax, int ndig, int cpc, int NP, int8_t *__restrict__ dig,
+                                 int32_t *__restrict__ colsh)
+{
+    const int blk = blockIdx.x, nact = *a.nact, RS = TCOLS / a.NB;
+    if (blk == 0 && threadIdx.x < a.C) colsh[threadIdx.x] = digit_shift(colmax[threadIdx.x], ndig);
+    if (blk * RS >= nact) return;
+    for (int t = threadIdx.x; t < NP * TCOLS; t += blockDim.x) {
+        const int n = t / TCOLS, k = t % TCOLS;
+        const int kk = blk * RS + k / a.NB, slot = k % a.NB;
+        const int chunk = n >> 4, w = n & 15, cc = w / ndig, kd = w % ndig;
+        const int c = chunk * cpc + cc;
+        int8_t v = 0;
+        if (kk < nact && cc < cpc && c < a.C) {
+            long long q = __double2ll_rn(ldexp((double)tg_value(a, kk, slot, c), digit_shift(colmax[c], ndig)));
+            for (int s = 0; s < kd; ++s) {
+                const long long b = ((q + 128) & 255) - 128;
+                q = (q - b) >> 8;
+            }
+            v = kd == ndig - 1 ? (int8_t)q : (int8_t)(((q + 128) & 255) - 128);
+        }
+        dig[(size_t)blk * NP * TCOLS + digit_offset(n, k)] = v;
+    }
+}
+
+struct DsTcArgs {
+    const uint8_t *hop;
+    int64_t N, ld;
+    int C, ndig, cpc, NP, stages;
+    const int32_t *rows, *nact, *colsh;
+    const int8_t *dig;
+    float *out;       // [gridDim.y][N][C] partial sums (or dS itself when gridDim.y == 1)
+};
+
+// one hop byte -> its NB one-hot int8 values (NB/4 TMEM columns)
+template <int NB>
+__device__ __forceinline__ void onehot_row(uint32_t h, uint32_t *v)
+{
+    if (NB == 8) {
+        const uint32_t H = (h & 7u) * 0x1111u;
+        v[0] = prmt(1u, 0u, H ^ 0x3210u); v[1] = prmt(1u, 0u, H ^ 0x7654u);
+    } else if (NB == 16) {
+        const uint32_t H = (h & 15u) * 0x1111u;
+        v[0] = prmt(1u, 0u, H ^ 0x3210u); v[1] = prmt(1u, 0u, H ^ 0x7654u);
+        v[2] = prmt(1u, 0u, H ^ 0xba98u); v[3] = prmt(1u, 0u, H ^ 0xfedcu);
+    } else {
+        const uint32_t hh = h & 31u, H = (hh & 7u) * 0x1111u, q = hh >> 3;
+        const uint32_t p0 = prmt(1u, 0u, H ^ 0x3210u), p1 = prmt(1u, 0u, H ^ 0x7654u);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            v[2 * w] = q == (uint32_t)w ? p0 : 0u;
+            v[2 * w + 1] = q == (uint32_t)w ? p1 : 0u;
+        }
+    }
+}
+
+// grid (column blocks of NGR*128, row super-blocks); the active-row list is split evenly over the super-blocks
+template <int NB, int NGR>
+__global__ void __launch_bounds__(TcCfg<NB, NGR>::THREADS, 1)
+agg_tc_ds_kernel(DsTcArgs a)
+{
+    using Cfg = TcCfg<NB, NGR>;
+    constexpr int RS = 128 / NB;                 // active hop rows per stage (RS * NB = 128 contraction indices)
+    constexpr int CW = NGR * 128;                // hop columns per CTA
+    constexpr int HOPB = RS * CW;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int BB = a.NP * TCOLS;
+    uint8_t *hop_s = smem;
+    uint8_t *b_s = hop_s + (size_t)a.stages * HOPB;
+    uint64_t *full = reinterpret_cast<uint64_t *>(b_s + (size_t)a.stages * BB);
+    uint64_t *empty = full + MAX_STAGES;
+    uint64_t *a_full = empty + MAX_STAGES;
+    uint64_t *a_empty = a_full + NGR * 2;
+    uint64_t *acc_full = a_empty + NGR * 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nact = *a.nact;
+    const int per = (((nact + (int)gridDim.y - 1) / (int)gridDim.y + RS - 1) / RS) * RS;
+    const int k0 = (int)blockIdx.y * per, k1 = min(nact, k0 + per);
+    const int nst = k1 > k0 ? (k1 - k0 + RS - 1) / RS : 0;
+    const int64_t col0 = (int64_t)blockIdx.x * CW;
+    const uint32_t wbytes = (uint32_t)min((int64_t)CW, a.ld - col0);      // ld % 16 == 0: a multiple of 16
+
+    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (tid == 32) {
+        for (int s = 0; s < a.stages; ++s) {
+            mbar_init(smem_u32(&full[s]), 1);
+            mbar_init(smem_u32(&empty[s]), 1);
+        }
+        for (int g = 0; g < NGR * 2; ++g) {
+            mbar_init(smem_u32(&a_full[g]), 128);
+            mbar_init(smem_u32(&a_empty[g]), 1);
+        }
+        mbar_init(smem_u32(acc_full), 1);
+        mbar_init_fence();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < NGR * 4) {
+        // ===== generators: thread m of group g owns TMEM lane m = hop column col0 + g*128 + m =====
+        const int g = warp >> 2, m = tid & 127;
+        const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        for (int s = 0; s < nst; ++s) {
+            const int st = s % a.stages, buf = s & 1;
+            mbar_wait(smem_u32(&full[st]), (uint32_t)(s / a.stages) & 1u);
+            if (s >= 2) {
+                mbar_wait(smem_u32(&a_empty[g * 2 + buf]), (uint32_t)((s >> 1) - 1) & 1u);
+                tc_fence_after();
+            }
+            const uint8_t *hs = hop_s + (size_t)st * HOPB + g * 128 + m;
+            uint32_t v[32];
+#pragma unroll
+            for (int r = 0; r < RS; ++r) onehot_row<NB>(hs[r * CW], &v[r * (NB / 4)]);
+            tmem_st32(lane_base + (uint32_t)((g * 2 + buf) * 32), v);
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(smem_u32(&a_full[g * 2 + buf]));
+        }
+        const int64_t j = col0 + g * 128 + m;
+        float *dst = a.out + ((size_t)blockIdx.y * a.N + (j < a.N ? j : 0)) * a.C;
+        if (nst > 0) {
+            mbar_wait(smem_u32(acc_full), 0);
+            tc_fence_after();
+        }
+        for (int n0 = 0; n0 < a.NP; n0 += 16) {
+            uint32_t acc[16];
+            if (nst > 0) {
+                tmem_ld16(lane_base + (uint32_t)(Cfg::ACC0 + g * a.NP + n0), acc);
+                tmem_wait_ld();
+            } else {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) acc[q] = 0u;
+            }
+#pragma unroll
+            for (int cc = 0; cc < 5; ++cc) {
+                const int c = (n0 >> 4) * a.cpc + cc;
+                if (cc >= a.cpc || c >= a.C) break;
+                long long tot = 0;
+                if (a.ndig == 4) {
+#pragma unroll
+                    for (int k = 3; k >= 0; --k) tot = tot * 256 + (int)acc[(cc * 4 + k) & 15];
+                } else {
+#pragma unroll
+                    for (int k = 2; k >= 0; --k) tot = tot * 256 + (int)acc[(cc * 3 + k) & 15];
+                }
+                if (j < a.N) dst[c] = (float)ldexp((double)tot, -a.colsh[c]);
+            }
+        }
+        tc_fence_before();
+    } else if (warp == NGR * 4) {
+        // ===== producer: one bulk copy per active row (the rows are gathered by index) + the digit block of the stage =====
+        if (lane == 0) {
+            for (int s = 0; s < nst; ++s) {
+                const int st = s % a.stages;
+                if (s >= a.stages) mbar_wait(smem_u32(&empty[st]), (uint32_t)(s / a.stages - 1) & 1u);
+                const uint32_t bar = smem_u32(&full[st]);
+                const int kb = k0 + s * RS, nr = min(RS, k1 - kb);
+                mbar_expect_tx(bar, (uint32_t)nr * wbytes + (uint32_t)BB);
+                for (int r = 0; r < nr; ++r)
+                    bulk_load_1d(smem_u32(hop_s + (size_t)st * HOPB + r * CW), a.hop + (int64_t)a.rows[kb + r] * a.ld + col0, wbytes, bar);
+                bulk_load_1d(smem_u32(b_s + (size_t)st * BB), a.dig + (size_t)(kb / RS) * BB, (uint32_t)BB, bar);
+            }
+        }
+    } else {
+        // ===== MMA issuer =====
+        const uint32_t idesc = umma_idesc_i8(128, a.NP);
+        for (int s = 0; s < nst; ++s) {
+            const int st = s % a.stages, buf = s & 1;
+            mbar_wait(smem_u32(&full[st]), (uint32_t)(s / a.stages) & 1u);
+            for (int g = 0; g < NGR; ++g) {
+                mbar_wait(smem_u32(&a_full[g * 2 + buf]), (uint32_t)(s >> 1) & 1u);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t bb = smem_u32(b_s + (size_t)st * BB);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma_i8_ts(tmem + (uint32_t)(Cfg::ACC0 + g * a.NP), tmem + (uint32_t)((g * 2 + buf) * 32 + ks * 8),
+                                   umma_desc_kmajor(bb + ks * DG_KSTEP, DG_LBO, DG_SBO), idesc, (s > 0 || ks > 0) ? 1u : 0u);
+                    umma_commit(smem_u32(&a_empty[g * 2 + buf]));
+                }
+                __syncwarp();
+            }
+            if (lane == 0) umma_commit(smem_u32(&empty[st]));
+            __syncwarp();
+        }
+        if (lane == 0 && nst > 0) umma_commit(smem_u32(acc_full));
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
 // ---- host side -------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -487,4 +762,127 @@ extern "C" int gnan_aggregate_rows_fwd_ws(const uint8_t *hop, int64_t R, int64_t
     if (nb == 8) return launch_fwd_nb<8>(map, a, ngr, st);
     if (nb == 16) return launch_fwd_nb<16>(map, a, ngr, st);
     return launch_fwd_nb<32>(map, a, ngr, st);
+}
+
+// ---- backward host side -------------------------------------------------------------------------------------------------------
+namespace {
+
+struct BwdPlan { int nb, ngr, RS, CW, ncol, nsb; DigitPlan dp; };
+BwdPlan bwd_plan(int64_t R, int64_t N, int nbins, int C)
+{
+    BwdPlan p;
+    p.dp = digit_plan(C);
+    p.nb = nbins <= 8 ? 8 : (nbins <= 16 ? 16 : 32);
+    p.ngr = p.dp.NP <= 64 ? 4 : (p.dp.NP <= 192 ? 2 : 1);
+    p.RS = 128 / p.nb;
+    p.CW = p.ngr * 128;
+    p.ncol = (int)ceil_div64(N, p.CW);
+    int nsb = (int)ceil_div64(2 * gnan_sm_count(), p.ncol);
+    const int64_t max_sb = std::max<int64_t>(1, ceil_div64(R, 4 * p.RS));       // at least 4 stages per super-block when all rows are active
+    p.nsb = (int)std::max<int64_t>(1, std::min<int64_t>(nsb, max_sb));
+    return p;
+}
+
+struct BwdWs { uint8_t *flags; int32_t *rows, *nact; uint32_t *colmax; int32_t *colsh; int8_t *dig; float *part; size_t total; };
+BwdWs bwd_ws_layout(void *base, int64_t R, int64_t N, int C, const BwdPlan &p)
+{
+    BwdWs w;
+    uint8_t *b = (uint8_t *)base;
+    size_t o = 0;
+    w.flags = b + o; o += align256((size_t)R);
+    w.rows = (int32_t *)(b + o); o += align256(sizeof(int32_t) * (size_t)R);
+    w.nact = (int32_t *)(b + o); o += 256;
+    w.colmax = (uint32_t *)(b + o); o += align256(sizeof(uint32_t) * C);
+    w.colsh = (int32_t *)(b + o); o += align256(sizeof(int32_t) * C);
+    w.dig = (int8_t *)(b + o); o += (size_t)ceil_div64(R, p.RS) * p.dp.NP * TCOLS;
+    w.part = (float *)(b + o); o += p.nsb > 1 ? sizeof(float) * (size_t)p.nsb * N * C : 0;
+    w.total = o;
+    return w;
+}
+
+template <int NB, int NGR>
+int launch_ds(DsTcArgs a, int ncol, int nsb, cudaStream_t st)
+{
+    using Cfg = TcCfg<NB, NGR>;
+    const size_t per_stage = (size_t)(128 / NB) * NGR * 128 + (size_t)a.NP * TCOLS;
+    const size_t fixed = sizeof(uint64_t) * (2 * MAX_STAGES + 4 * NGR + 1) + 16;
+    int stages = (int)std::min<size_t>(MAX_STAGES, (200 * 1024 - fixed) / per_stage);
+    if (stages < 2) {
+        gnan_set_error("aggregate_rows_bwd (tensor-core path): stage of %zu bytes does not fit shared memory", per_stage);
+        return GNAN_ERR_UNSUPPORTED;
+    }
+    a.stages = stages;
+    const size_t smem = fixed + per_stage * stages;
+    GNAN_CUDA(cudaFuncSetAttribute(agg_tc_ds_kernel<NB, NGR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    agg_tc_ds_kernel<NB, NGR><<<dim3((unsigned)ncol, (unsigned)nsb), Cfg::THREADS, smem, st>>>(a);
+    GNAN_LAUNCH_OK();
+    return GNAN_OK;
+}
+
+template <int NB>
+int launch_ds_nb(const DsTcArgs &a, const BwdPlan &p, cudaStream_t st)
+{
+    if (p.ngr == 4) return launch_ds<NB, 4>(a, p.ncol, p.nsb, st);
+    if (p.ngr == 2) return launch_ds<NB, 2>(a, p.ncol, p.nsb, st);
+    return launch_ds<NB, 1>(a, p.ncol, p.nsb, st);
+}
+
+}  // namespace
+
+extern "C" size_t gnan_aggregate_rows_bwd_ws_bytes(int64_t R, int64_t N, int64_t ld_hop, int32_t nbins, int32_t Cr, int32_t C, int algo)
+{
+    const size_t legacy = gnan_aggregate_rows_bwd_workspace_bytes(R, N, nbins, Cr, C);
+    if (algo == GNAN_AGG_CUDA_CORES || !gnan_aggregate_rows_tc_supported(R, N, ld_hop, nbins, C)) return legacy;
+    const BwdPlan p = bwd_plan(R, N, nbins, C);
+    return bwd_ws_layout(nullptr, R, N, C, p).total;       // dT needs no workspace when the bin sums were saved
+}
+
+extern "C" int gnan_aggregate_rows_bwd_ws(const uint8_t *hop, int64_t R, int64_t N, int64_t ld_hop, const float *T,
+                                          int table_per_row, int32_t nbins, int32_t Cr, const float *rscale, const float *S,
+                                          int32_t C, const float *g, const float *Bsum, float *dS, float *dT, int algo,
+                                          void *workspace, size_t workspace_bytes, gnan_stream_t stream)
+{
+    const bool can_tc = gnan_aggregate_rows_tc_supported(R, N, ld_hop, nbins, C) != 0 && Bsum != nullptr;
+    if (algo == GNAN_AGG_CUDA_CORES || (algo == GNAN_AGG_AUTO && !can_tc))
+        return gnan_aggregate_rows_bwd_saved(hop, R, N, ld_hop, T, table_per_row, nbins, Cr, rscale, S, C, g, Bsum, dS, dT, workspace,
+                                             workspace_bytes, stream);
+    GNAN_REQUIRE(algo == GNAN_AGG_AUTO || algo == GNAN_AGG_TENSOR_CORES, "aggregate_rows_bwd_ws: unknown algo %d", algo);
+    if (!can_tc) {
+        gnan_set_error("aggregate_rows_bwd_ws: the tensor-core path needs saved bin sums, N >= 256, nbins <= 32 and <= 256 accumulator "
+                       "columns (N=%lld nbins=%d C=%d)", (long long)N, nbins, C);
+        return GNAN_ERR_UNSUPPORTED;
+    }
+    GNAN_REQUIRE(hop && T && S && g, "aggregate_rows_bwd_ws: NULL hop/T/S/g");
+    GNAN_REQUIRE(ld_hop >= N && ld_hop % 16 == 0 && ((uintptr_t)hop % 16) == 0, "aggregate_rows_bwd_ws: hop rows must be 16-byte aligned with ld %% 16 == 0");
+    GNAN_REQUIRE(R < (int64_t)1 << 31, "aggregate_rows_bwd_ws: too many rows");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dT) {   // from the saved bin sums, no pass over the hop block (the CUDA-core helper with dS = NULL)
+        int rc = gnan_aggregate_rows_bwd_saved(hop, R, N, ld_hop, T, table_per_row, nbins, Cr, rscale, S, C, g, Bsum, nullptr, dT, nullptr, 0, stream);
+        if (rc) return rc;
+    }
+    if (!dS) return GNAN_OK;
+    const BwdPlan p = bwd_plan(R, N, nbins, C);
+    const BwdWs w = bwd_ws_layout(workspace, R, N, C, p);
+    if (!workspace || workspace_bytes < w.total) {
+        gnan_set_error("aggregate_rows_bwd_ws: workspace %zu < %zu bytes", workspace_bytes, w.total);
+        return GNAN_ERR_WORKSPACE;
+    }
+    row_flags_kernel<<<(unsigned)ceil_div64(R, 256), 256, 0, st>>>(g, R, C, w.flags);
+    GNAN_LAUNCH_OK();
+    compact_rows_kernel<<<1, 1024, 0, st>>>(w.flags, R, w.rows, w.nact);
+    GNAN_LAUNCH_OK();
+    GNAN_CUDA(cudaMemsetAsync(w.colmax, 0, sizeof(uint32_t) * C, st));
+    TgArgs ta{T, rscale, g, table_per_row, nbins, Cr, C, p.nb, w.rows, w.nact};
+    tg_colmax_kernel<<<(unsigned)std::min<int64_t>(ceil_div64(R * p.nb, 256), 2 * gnan_sm_count()), 256, 0, st>>>(ta, w.colmax);
+    GNAN_LAUNCH_OK();
+    tg_digits_kernel<<<(unsigned)ceil_div64(R, p.RS), 256, 0, st>>>(ta, w.colmax, p.dp.ndig, p.dp.cpc, p.dp.NP, w.dig, w.colsh);
+    GNAN_LAUNCH_OK();
+    DsTcArgs a{hop, N, ld_hop, C, p.dp.ndig, p.dp.cpc, p.dp.NP, 0, w.rows, w.nact, w.colsh, w.dig, p.nsb > 1 ? w.part : dS};
+    int rc = p.nb == 8 ? launch_ds_nb<8>(a, p, st) : (p.nb == 16 ? launch_ds_nb<16>(a, p, st) : launch_ds_nb<32>(a, p, st));
+    if (rc) return rc;
+    if (p.nsb > 1) {
+        const size_t n = (size_t)N * C;
+        rc = gnan_reduce_chunks(w.part, p.nsb, n, n, dS, st);
+    }
+    return rc;
 }

@@ -50,34 +50,60 @@ def row_block(num_nodes: int, rank: int, world: int, align: int = 16) -> Tuple[i
 # ---------------------------------------------------------------------------------------------------------------------
 # collectives with autograd
 # ---------------------------------------------------------------------------------------------------------------------
+def _timed(name):
+    from . import ops
+    return ops._timed(name)
+
+
 class _AllGatherRows(torch.autograd.Function):
-    """S_full = concat_r S_r along dim 0 (blocks may have different lengths). Backward: every rank holds a partial
-    dL/dS_full (it only aggregated its own rows), so the gradient of block r is the SUM over ranks of that slice:
-    a reduce-scatter (done as all-reduce + slice when block sizes are ragged)."""
+    """S_full = concat_r S_r along dim 0. Blocks are the `row_block` partition: every rank holds `nmax` rows except the
+    trailing ones, so the padded gather buffer [world * nmax, ...] holds the concatenation as a PREFIX: one
+    all_gather_into_tensor, no list gather, no concatenation. Backward: every rank holds a partial dL/dS_full (it only
+    aggregated its own rows), so the gradient of block r is the SUM over ranks of that slice: one reduce_scatter_tensor on the
+    zero-padded gradient."""
 
     @staticmethod
     def forward(ctx, s_local, sizes, group):
         ctx.sizes, ctx.group = list(sizes), group
         ctx.rank = dist.get_rank(group)
-        nmax = max(ctx.sizes)
+        world, nmax, total = len(ctx.sizes), max(ctx.sizes), sum(ctx.sizes)
+        ctx.prefix, short = True, False                            # concatenation == prefix of the padded buffer?
+        for n in ctx.sizes:
+            if short and n > 0:
+                ctx.prefix = False
+            short = short or n < nmax
         tail = tuple(s_local.shape[1:])
         mine = s_local.contiguous()
         if mine.shape[0] < nmax:                                   # ragged last block: pad to the common size
-            mine = torch.cat([mine, mine.new_zeros((nmax - mine.shape[0],) + tail)])
-        parts = [mine.new_empty((nmax,) + tail) for _ in ctx.sizes]
-        dist.all_gather(parts, mine, group=group)
-        return torch.cat([p[:n] for p, n in zip(parts, ctx.sizes)], dim=0)
+            pad = mine.new_zeros((nmax,) + tail)
+            pad[:mine.shape[0]] = mine
+            mine = pad
+        buf = mine.new_empty((world * nmax,) + tail)
+        with _timed("allgather_rows"):
+            dist.all_gather_into_tensor(buf, mine, group=group)
+        if ctx.prefix:
+            return buf[:total]
+        return torch.cat([buf[r * nmax:r * nmax + n] for r, n in enumerate(ctx.sizes)], dim=0)
 
     @staticmethod
     def backward(ctx, g_full):
-        g_full = g_full.contiguous()
-        if len(set(ctx.sizes)) == 1:
-            out = g_full.new_empty((ctx.sizes[0],) + tuple(g_full.shape[1:]))
-            dist.reduce_scatter_tensor(out, g_full, op=dist.ReduceOp.SUM, group=ctx.group)
-            return out, None, None
-        dist.all_reduce(g_full, op=dist.ReduceOp.SUM, group=ctx.group)
-        b = sum(ctx.sizes[:ctx.rank])
-        return g_full[b:b + ctx.sizes[ctx.rank]].clone(), None, None
+        world, nmax, total = len(ctx.sizes), max(ctx.sizes), sum(ctx.sizes)
+        tail = tuple(g_full.shape[1:])
+        if ctx.prefix and total == world * nmax:
+            padded = g_full.contiguous()
+        else:
+            padded = g_full.new_zeros((world * nmax,) + tail)
+            if ctx.prefix:
+                padded[:total] = g_full
+            else:
+                off = 0
+                for r, n in enumerate(ctx.sizes):
+                    padded[r * nmax:r * nmax + n] = g_full[off:off + n]
+                    off += n
+        out = g_full.new_empty((nmax,) + tail)
+        with _timed("reduce_scatter_rows"):
+            dist.reduce_scatter_tensor(out, padded, op=dist.ReduceOp.SUM, group=ctx.group)
+        return out[:ctx.sizes[ctx.rank]], None, None
 
 
 def all_gather_rows(s_local: torch.Tensor, sizes: Sequence[int], group=None) -> torch.Tensor:
@@ -85,12 +111,14 @@ def all_gather_rows(s_local: torch.Tensor, sizes: Sequence[int], group=None) -> 
 
 
 def allreduce_gradients(params, group=None, average: bool = False):
-    """One fused all-reduce of all parameter gradients (flat buffer), written back in place."""
+    """One fused all-reduce of all parameter gradients (flat buffer), written back in place. Prefer FlatGradients, which
+    needs neither the concatenation nor the copy back."""
     grads = [p.grad for p in params if p.grad is not None]
     if not grads:
         return
     flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    with _timed("allreduce_gradients"):
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     if average:
         flat /= dist.get_world_size(group)
     off = 0
@@ -98,6 +126,50 @@ def allreduce_gradients(params, group=None, average: bool = False):
         n = g.numel()
         g.copy_(flat[off:off + n].view_as(g))
         off += n
+
+
+class FlatGradients:
+    """All parameter gradients as views of ONE persistent flat buffer: backward accumulates straight into it, the
+    data-parallel reduction is a single all_reduce on that buffer and the optimizer reads the views. No per-step
+    concatenation or copy back.
+
+        fg = FlatGradients(model.parameters())
+        fg.zero(); loss.backward(); fg.all_reduce(average=True); optimizer.step()
+
+    Use `fg.zero()` instead of `optimizer.zero_grad()` (set_to_none would drop the views)."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        dev = self.params[0].device if self.params else "cpu"
+        self.flat = torch.zeros(n, dtype=self.params[0].dtype if self.params else torch.float32, device=dev)
+        self.attach()
+
+    def attach(self):
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            p.grad = self.flat[off:off + k].view_as(p)
+            off += k
+
+    def zero(self):
+        if any(p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + self.flat.element_size() * o for p, o in zip(self.params, self._offsets())):
+            self.attach()
+        self.flat.zero_()
+
+    def _offsets(self):
+        off = 0
+        for p in self.params:
+            yield off
+            off += p.numel()
+
+    def all_reduce(self, group=None, average: bool = False):
+        if not self.flat.numel():
+            return
+        with _timed("allreduce_gradients"):
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            self.flat.div_(dist.get_world_size(group))
 
 
 def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None):

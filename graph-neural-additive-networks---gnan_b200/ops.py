@@ -221,23 +221,25 @@ def _(hop, T, rscale, S, per_row, save, algo=0):
 
 @torch.library.custom_op("gnan_b200::agg_rows_bwd", mutates_args=())
 def agg_rows_bwd(hop: Tensor, T: Tensor, rscale: Optional[Tensor], S: Tensor, per_row: bool, g: Tensor,
-                 bsum: Tensor) -> Tuple[Tensor, Tensor]:
+                 bsum: Tensor, algo: int = 0) -> Tuple[Tensor, Tensor]:
     lib = load()
     T, S, g = _f32(T, "T"), _f32(S, "S"), _f32(g, "g")
     rscale = None if rscale is None else _f32(rscale, "rscale")
     R, ld, N, C, nbins, Cr = _agg_dims(hop, T, S, per_row)
     dS = torch.empty_like(S)
     dT = torch.empty_like(T)
-    ws = _ws(lib.gnan_aggregate_rows_bwd_workspace_bytes(R, N, nbins, Cr, C), S.device)
+    if not bsum.numel():
+        algo = _lib.AGG_CUDA_CORES          # nothing saved: the CUDA-core path rebuilds the bin sums with one extra pass
+    ws = _ws(lib.gnan_aggregate_rows_bwd_ws_bytes(R, N, ld, nbins, Cr, C, int(algo)), S.device)
     with _timed("aggregate_rows_bwd_saved"):
-        check(lib.gnan_aggregate_rows_bwd_saved(ptr(hop), R, N, ld, ptr(T), int(per_row), nbins, Cr, ptr(rscale), ptr(S), C,
-                                                ptr(g), ptr(bsum) if bsum.numel() else None, ptr(dS), ptr(dT), ptr(ws),
-                                                ws.numel(), stream_handle()), "gnan_aggregate_rows_bwd")
+        check(lib.gnan_aggregate_rows_bwd_ws(ptr(hop), R, N, ld, ptr(T), int(per_row), nbins, Cr, ptr(rscale), ptr(S), C,
+                                             ptr(g), ptr(bsum) if bsum.numel() else None, ptr(dS), ptr(dT), int(algo), ptr(ws),
+                                             ws.numel(), stream_handle()), "gnan_aggregate_rows_bwd")
     return dS, dT
 
 
 @agg_rows_bwd.register_fake
-def _(hop, T, rscale, S, per_row, g, bsum):
+def _(hop, T, rscale, S, per_row, g, bsum, algo=0):
     return torch.empty_like(S), torch.empty_like(T)
 
 
@@ -250,7 +252,7 @@ def _agg_setup(ctx, inputs, output):
 
 def _agg_backward(ctx, g, _g_bsum):
     hop, T, rscale, S, bsum = ctx.saved_tensors
-    dS, dT = agg_rows_bwd(hop, T, rscale, S, ctx.per_row, g.contiguous(), bsum)
+    dS, dT = agg_rows_bwd(hop, T, rscale, S, ctx.per_row, g.contiguous(), bsum, ctx.algo)
     return None, dT, None, dS, None, None, None
 
 

@@ -5,8 +5,10 @@ node_distances = 1/(1+d) with inf -> 0, normalization_matrix[i,j] = #{j': d(i,j'
 networkx BFS of batched_pyg_main.py:36-44. Here the distances stay integers: a uint8 hop matrix (255 = unreachable)
 plus int32 BFS level sizes; the reference's two fp32 [N,N] matrices are derived views (HopData.reference_format()).
 
-Graphs must be simple (no duplicate edges): the reference's COO->LIL conversion sums duplicates into weight 2
-(pre_process_datasets.py:109), which is not emulated.
+Duplicate edges: the reference's COO->LIL conversion sums a (src,dst) pair listed k times into ONE edge of weight k
+(pre_process_datasets.py:109,129), and its Dijkstra then returns weighted distances. The CSR builder detects duplicates and
+`apsp` / `apsp_batched` emulate that behaviour exactly by subdividing such an edge into a chain of k unit edges through
+k-1 virtual nodes (dropped from the result): distances stay integers, bit-exact with the reference (tested against scipy).
 """
 from typing import List, Optional, Sequence
 
@@ -75,23 +77,64 @@ def from_reference_format(node_distances, normalization_matrix=None):
     return HopData(hop, cnt, N)
 
 
-def build_csr(edge_index, num_nodes, device):
-    """Directed CSR (rowptr int32 [N+1], col int32 [E]) of edges followed source -> target, built on the device."""
-    ei = torch.as_tensor(edge_index).to(device=device, dtype=torch.int64)
-    if ei.numel() == 0:
-        return torch.zeros(num_nodes + 1, dtype=torch.int32, device=device), torch.zeros(1, dtype=torch.int32, device=device)
-    if int(ei.max().item()) >= num_nodes or int(ei.min().item()) < 0:
+def build_csr(edge_index, num_nodes, device, status=None):
+    """Directed CSR (rowptr int32 [N+1], col int32 [E]) of edges followed source -> target, built on the device by a counting
+    sort (csrc/csr.cu: no comparison sort, no host synchronisation). Returns (rowptr, col, status): status is a device int32
+    word, bit 0 = endpoint out of range, bit 1 = duplicate edges present (see _expand_multi_edges); the caller reads it together
+    with its own flags."""
+    lib = load()
+    ei = torch.as_tensor(edge_index).to(device=device, dtype=torch.int64, non_blocking=True).contiguous()
+    if ei.dim() != 2 or ei.shape[0] != 2:
+        raise ValueError("edge_index must be [2,E]")
+    E = ei.shape[1]
+    rowptr = torch.empty(num_nodes + 1, dtype=torch.int32, device=device)
+    col = torch.empty(max(E, 1), dtype=torch.int32, device=device)
+    if status is None:
+        status = torch.zeros(1, dtype=torch.int32, device=device)
+    ws = torch.empty(max(lib.gnan_build_csr_workspace_bytes(num_nodes, E), 1), dtype=torch.uint8, device=device)
+    with _timed("build_csr"):
+        check(lib.gnan_build_csr(ptr(ei[0]), ptr(ei[1]), E, num_nodes, ptr(rowptr), ptr(col), status.data_ptr(), ptr(ws), ws.numel(),
+                                 stream_handle()), "gnan_build_csr")
+    return rowptr, col, status
+
+
+def _timed(name):
+    from . import ops
+    return ops._timed(name)
+
+
+def _check_status(st):
+    if st & 1:
         raise ValueError("edge_index out of range")
-    order = torch.argsort(ei[0] * num_nodes + ei[1])
-    src, dst = ei[0][order], ei[1][order]
-    key = src * num_nodes + dst
-    if key.numel() > 1 and bool((key[1:] == key[:-1]).any().item()):
-        raise ValueError("duplicate edges: the reference sums them into weight 2 (pre_process_datasets.py:109); "
-                         "gnan_b200 needs a simple graph")
-    deg = torch.bincount(src, minlength=num_nodes)
-    rowptr = torch.zeros(num_nodes + 1, dtype=torch.int64, device=device)
-    rowptr[1:] = torch.cumsum(deg, 0)
-    return rowptr.to(torch.int32), dst.to(torch.int32).contiguous()
+
+
+def _expand_multi_edges(edge_index, num_nodes, device):
+    """(edge_index', N') with every (src,dst) pair listed k > 1 times replaced by a chain of k unit edges through k-1 virtual
+    nodes N, N+1, ...: unit-weight BFS on the result reproduces the reference's Dijkstra on the summed weights
+    (pre_process_datasets.py:109-110). Slow path (sort-based), only taken when the CSR builder reports duplicates."""
+    ei = torch.as_tensor(edge_index).to(device=device, dtype=torch.int64)
+    key, cnt = torch.unique(ei[0] * num_nodes + ei[1], return_counts=True)
+    s, d = key // num_nodes, key % num_nodes
+    single = cnt == 1
+    ms, md, mk = s[~single], d[~single], cnt[~single]
+    nv = mk - 1                                                         # virtual nodes per multi-edge
+    first = num_nodes + torch.cumsum(nv, 0) - nv                        # id of the first virtual node of each chain
+    eid = torch.repeat_interleave(torch.arange(ms.numel(), device=device), mk)    # one entry per unit edge of a chain
+    pos = torch.arange(eid.numel(), device=device) - torch.repeat_interleave(torch.cumsum(mk, 0) - mk, mk)
+    a = torch.where(pos == 0, ms[eid], first[eid] + pos - 1)
+    b = torch.where(pos == mk[eid] - 1, md[eid], first[eid] + pos)
+    out = torch.stack([torch.cat([s[single], a]), torch.cat([d[single], b])])
+    return out, num_nodes + int(nv.sum().item())
+
+
+def _recount_levels(hop, n_cols):
+    """[R,256] level histogram of the first n_cols columns (torch ops; multi-edge slow path only)"""
+    R = hop.shape[0]
+    cnt = torch.zeros(R, 256, dtype=torch.int32, device=hop.device)
+    for r0 in range(0, R, 2048):
+        blk = hop[r0:r0 + 2048, :n_cols].long()
+        cnt[r0:r0 + 2048].scatter_add_(1, blk, torch.ones_like(blk, dtype=torch.int32))
+    return cnt
 
 
 def _trim_counts(cnt256):
@@ -105,7 +148,7 @@ def _trim_counts(cnt256):
 MSBFS_MIN_NODES = 4096      # graphs at least this large use the bit-parallel multi-source BFS
 
 
-def apsp(edge_index, num_nodes, device="cuda", row_begin=0, row_end=None, method="auto"):
+def apsp(edge_index, num_nodes, device="cuda", row_begin=0, row_end=None, method="auto", _expanded=False):
     """All-pairs (or rows [row_begin,row_end) of the) hop distances of one graph on the GPU -> HopData.
 
     method: "auto" | "warp" (one warp per source: small graphs, few rows) | "msbfs" (bit-parallel multi-source BFS over
@@ -114,21 +157,32 @@ def apsp(edge_index, num_nodes, device="cuda", row_begin=0, row_end=None, method
     N = int(num_nodes)
     row_end = N if row_end is None else int(row_end)
     R = row_end - row_begin
-    rowptr, col = build_csr(edge_index, N, device)
+    st = torch.zeros(2, dtype=torch.int32, device=device)              # [csr status, hop overflow]
+    rowptr, col, _ = build_csr(edge_index, N, device, status=st[0:1])
     hop = torch.empty(R, hop_ld(N), dtype=torch.uint8, device=device)
     cnt = torch.empty(R, 256, dtype=torch.int32, device=device)
-    flag = torch.zeros(1, dtype=torch.int32, device=device)
+    flag = st[1:2]
     if method == "auto":
         method = "msbfs" if N >= MSBFS_MIN_NODES and R * 8 >= N else "warp"
     if method == "msbfs":
         ws = torch.empty(max(lib.gnan_apsp_msbfs_workspace_bytes(N), 1), dtype=torch.uint8, device=device)
-        check(lib.gnan_apsp_msbfs(ptr(rowptr), ptr(col), N, row_begin, row_end, ptr(hop), hop.shape[1], ptr(cnt), 256, ptr(flag),
-                                  ptr(ws), ws.numel(), stream_handle()), "gnan_apsp_msbfs")
+        with _timed("apsp_msbfs"):
+            check(lib.gnan_apsp_msbfs(ptr(rowptr), ptr(col), N, row_begin, row_end, ptr(hop), hop.shape[1], ptr(cnt), 256, flag.data_ptr(),
+                                      ptr(ws), ws.numel(), stream_handle()), "gnan_apsp_msbfs")
     else:
         ws = torch.empty(max(lib.gnan_apsp_bfs_workspace_bytes(N, R), 1), dtype=torch.uint8, device=device)
-        check(lib.gnan_apsp_bfs(ptr(rowptr), ptr(col), N, row_begin, row_end, ptr(hop), hop.shape[1], ptr(cnt), 256, ptr(flag),
-                                ptr(ws), ws.numel(), stream_handle()), "gnan_apsp_bfs")
-    if R and int(flag.item()):
+        with _timed("apsp_bfs"):
+            check(lib.gnan_apsp_bfs(ptr(rowptr), ptr(col), N, row_begin, row_end, ptr(hop), hop.shape[1], ptr(cnt), 256, flag.data_ptr(),
+                                    ptr(ws), ws.numel(), stream_handle()), "gnan_apsp_bfs")
+    status, over = (int(v) for v in st.tolist())
+    _check_status(status)
+    if status & 2 and not _expanded:                                   # duplicate edges: weight-k emulation, then drop the virtual nodes
+        ei2, n2 = _expand_multi_edges(edge_index, N, device)
+        big = apsp(ei2, n2, device=device, row_begin=row_begin, row_end=row_end, method=method, _expanded=True)
+        hop = torch.full((R, hop_ld(N)), _lib.HOP_UNREACHABLE, dtype=torch.uint8, device=device)
+        hop[:, :N] = big.hop[:, :N]
+        return HopData(hop, _trim_counts(_recount_levels(hop, N)) if R else cnt[:, :2], N, row_begin)
+    if R and over:
         raise NotImplementedError("a hop distance > 254 does not fit the uint8 hop matrix")
     return HopData(hop, _trim_counts(cnt) if R else cnt[:, :2], N, row_begin)
 
@@ -169,32 +223,73 @@ class PackedBatch:
                            self.max_nodes)
 
 
-def apsp_batched(edge_index, node_off, device="cuda", x=None, y=None):
+def apsp_batched(edge_index, node_off, device="cuda", x=None, y=None, node_off_device=None):
     """Hop blocks of B small graphs (<= 256 nodes each) in one launch. edge_index uses GLOBAL node ids of the
-    concatenated node set; node_off [B+1] are the graph boundaries."""
+    concatenated node set; node_off [B+1] are the graph boundaries.
+
+    Pass node_off as a HOST tensor / array (what a data loader has): block sizes and offsets are then computed on the host
+    and the call synchronises exactly once, at the end (overflow flag + largest hop, which sizes the level table).
+    node_off_device: optional int32 device copy of node_off (skips its upload)."""
+    import numpy as np
     lib = load()
-    node_off = torch.as_tensor(node_off).to(device=device, dtype=torch.int32)
-    B = node_off.numel() - 1
-    sumN = int(node_off[-1].item())
-    sizes = (node_off[1:] - node_off[:-1]).long()
-    max_n = int(sizes.max().item()) if B else 1
-    hop_off = torch.zeros(B + 1, dtype=torch.int64, device=device)
-    hop_off[1:] = torch.cumsum(sizes * sizes, 0)
-    total = int(hop_off[-1].item())
-    rowptr, col = build_csr(edge_index, sumN, device)
+    if torch.is_tensor(node_off) and node_off.is_cuda:
+        node_off_device = node_off.to(torch.int32) if node_off_device is None else node_off_device
+        no_h = node_off.cpu().numpy().astype(np.int64)                 # device-resident offsets cost one extra synchronisation
+    else:
+        no_h = np.asarray(node_off, dtype=np.int64)
+    B = no_h.shape[0] - 1
+    sumN = int(no_h[-1]) if B >= 0 and no_h.size else 0
+    sizes = no_h[1:] - no_h[:-1]
+    max_n = int(sizes.max()) if B > 0 else 1
+    hop_off_h = np.zeros(B + 1, dtype=np.int64)
+    np.cumsum(sizes * sizes, out=hop_off_h[1:])
+    total = int(hop_off_h[-1])
+    if node_off_device is None:
+        node_off_device = torch.from_numpy(no_h.astype(np.int32)).to(device, non_blocking=True)
+    node_off_d = node_off_device
+    hop_off = torch.from_numpy(hop_off_h).to(device, non_blocking=True)
+    st = torch.zeros(3, dtype=torch.int32, device=device)              # [csr status, overflow, largest finite hop]
+    rowptr, col, _ = build_csr(edge_index, sumN, device, status=st[0:1])
     hop = torch.empty(max(total, 1), dtype=torch.uint8, device=device)
     nb = min(256, max_n + 1)                     # a finite hop inside a graph is at most max_n - 1; last column = unreachable
     cnt = torch.empty(sumN, nb, dtype=torch.int32, device=device)
-    flag = torch.zeros(2, dtype=torch.int32, device=device)           # [overflow, largest finite hop]
-    check(lib.gnan_apsp_bfs_batched_n(ptr(rowptr), ptr(col), ptr(node_off), ptr(hop_off), B, max_n, sumN, total, ptr(hop), ptr(cnt), nb,
-                                      ptr(flag), flag.data_ptr() + 4, stream_handle()), "gnan_apsp_bfs_batched")
-    over, D = (int(v) for v in flag.tolist()) if B else (0, 0)
+    with _timed("apsp_bfs_batched"):
+        check(lib.gnan_apsp_bfs_batched_n(ptr(rowptr), ptr(col), ptr(node_off_d), ptr(hop_off), B, max_n, sumN, total, ptr(hop), ptr(cnt), nb,
+                                          st.data_ptr() + 4, st.data_ptr() + 8, stream_handle()), "gnan_apsp_bfs_batched")
+    status, over, D = (int(v) for v in st.tolist()) if B > 0 else (0, 0, 0)
+    _check_status(status)
+    if status & 2:
+        return _apsp_batched_multi_edges(edge_index, no_h, device, x, y)
     if over:
         raise NotImplementedError("a hop distance > 254 does not fit the uint8 hop matrix")
     if sumN == 0:
-        return PackedBatch(x, hop, hop_off, node_off, cnt[:, :2], y, max_n)
+        return PackedBatch(x, hop, hop_off, node_off_d, cnt[:, :2], y, max_n)
     lc = torch.cat([cnt[:, :D + 1], cnt[:, nb - 1:nb]], dim=1).contiguous()
-    return PackedBatch(x, hop, hop_off, node_off, lc, y, max_n)
+    return PackedBatch(x, hop, hop_off, node_off_d, lc, y, max_n)
+
+
+def _apsp_batched_multi_edges(edge_index, no_h, device, x, y):
+    """Slow path of apsp_batched for batches with duplicate edges: per-graph `apsp` (which emulates the reference's summed
+    weights), assembled into the packed form."""
+    import numpy as np
+    ei = torch.as_tensor(edge_index).to(device=device, dtype=torch.int64)
+    B = no_h.shape[0] - 1
+    hops, cnts, D = [], [], 0
+    for b in range(B):
+        lo, hi = int(no_h[b]), int(no_h[b + 1])
+        sel = (ei[0] >= lo) & (ei[0] < hi)
+        hd = apsp(ei[:, sel] - lo, hi - lo, device=device, method="warp")
+        hops.append(hd.hop[:, :hi - lo].reshape(-1))
+        cnts.append(hd.level_counts)
+        D = max(D, hd.nbins - 2)
+    lc = torch.zeros(int(no_h[-1]), D + 2, dtype=torch.int32, device=device)
+    for b, c in enumerate(cnts):
+        lc[int(no_h[b]):int(no_h[b + 1]), :c.shape[1] - 1] = c[:, :-1]
+        lc[int(no_h[b]):int(no_h[b + 1]), -1] = c[:, -1]
+    sizes = no_h[1:] - no_h[:-1]
+    hop_off = torch.from_numpy(np.concatenate([[0], np.cumsum(sizes * sizes)]).astype(np.int64)).to(device)
+    return PackedBatch(x, torch.cat(hops) if hops else torch.empty(1, dtype=torch.uint8, device=device), hop_off,
+                       torch.from_numpy(no_h.astype(np.int32)).to(device), lc, y, int(sizes.max()) if B else 1)
 
 
 def pre_process(data, is_graph_task, data_name=None, processed_data_dir=None, device="cuda", reference_format=False):

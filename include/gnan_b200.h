@@ -177,6 +177,16 @@ int gnan_aggregate_rows_fwd_ws(const uint8_t *hop, int64_t R, int64_t N, int64_t
                                float *Bsum /* or NULL */, int algo, void *workspace, size_t workspace_bytes,
                                gnan_stream_t stream);
 
+/* backward with a kernel choice. Tensor-core path (needs the saved Bsum): dT from the bin sums; dS[j,c] = sum_{i,d}
+ * 1[b(hop[i,j]) = d] * TG[i,d,c] with TG = T*rscale*g quantised like S above, contracted on tcgen05 with a TMEM lane per hop
+ * COLUMN. Rows whose g is entirely zero are skipped (their contribution is exactly zero): the hop bytes streamed are those of
+ * the rows that carry a loss (a train mask: trainer.py:52-58). */
+size_t gnan_aggregate_rows_bwd_ws_bytes(int64_t R, int64_t N, int64_t ld_hop, int32_t nbins, int32_t Cr, int32_t C, int algo);
+int gnan_aggregate_rows_bwd_ws(const uint8_t *hop, int64_t R, int64_t N, int64_t ld_hop, const float *T, int table_per_row,
+                               int32_t nbins, int32_t Cr, const float *rscale, const float *S, int32_t C, const float *g,
+                               const float *Bsum, float *dS, float *dT, int algo, void *workspace, size_t workspace_bytes,
+                               gnan_stream_t stream);
+
 size_t gnan_aggregate_rows_bwd_workspace_bytes(int64_t R, int64_t N, int32_t nbins, int32_t Cr, int32_t C);
 
 /* given g = dL/dout [R,C]:  dS[j,c] = sum_i W[i,j,c] g[i,c]   (overwritten; [N,C])
@@ -218,6 +228,14 @@ int gnan_aggregate_blockdiag_bwd(const uint8_t *hop, const int64_t *hop_off, con
  * a finite level > 254 sets *overflow_flag (device int32) != 0.
  * cnt[i,d] = #{j: hop[i,j] = d} for d < nbins-1, cnt[i,nbins-1] = #unreachable; levels >= nbins-1 also set the flag.
  * ---------------------------------------------------------------------------------------------- */
+/* Directed CSR (rowptr [N+1], col [E]) of the edge list src -> dst, built on the device by a counting sort on the source
+ * (replaces the COO -> LIL conversion of pre_process_datasets.py:109,129). Neighbour order inside a row is unspecified.
+ * *status (device int32): bit 0 = an endpoint outside [0,N) (that edge is dropped), bit 1 = duplicate (src,dst) pairs exist
+ * (the reference sums them into weight-2 edges; the caller must subdivide them, see gnan_b200/preprocess.py). */
+size_t gnan_build_csr_workspace_bytes(int32_t N, int64_t E);
+int gnan_build_csr(const int64_t *src, const int64_t *dst, int64_t E, int32_t N, int32_t *rowptr, int32_t *col, int32_t *status,
+                   void *workspace, size_t workspace_bytes, gnan_stream_t stream);
+
 size_t gnan_apsp_bfs_workspace_bytes(int32_t N, int32_t n_sources);
 
 /* sources [src_begin, src_end) of one graph with N nodes -> hop rows [src_end-src_begin, N] (row stride ld_hop). */

@@ -35,12 +35,13 @@ def to_torch(p, dtype=torch.float32, requires_grad=False):
 
 def scalar_mlp(p, g, t):
     """Group g's MLP on a column t [M,1] -> [M,C]. GNAN.py:24-34 (fs) / :38-47 (rho); dropout inactive."""
+    lin = torch.nn.functional.linear                      # the op nn.Linear runs (one addmm), as in the reference modules
     if p["w1"] is None:                                   # n_layers == 1: Linear(1, C)
-        return t @ p["wo"][g].T + p["bo"][g]
-    h = torch.relu(t @ p["w1"][g].view(1, -1) + p["b1"][g])
+        return lin(t, p["wo"][g], p["bo"][g])
+    h = torch.relu(lin(t, p["w1"][g].view(-1, 1), p["b1"][g]))
     for l in range(p["wh"].shape[0]):
-        h = torch.relu(h @ p["wh"][l, g].T + p["bh"][l, g])
-    return h @ p["wo"][g].T + p["bo"][g]
+        h = torch.relu(lin(h, p["wh"][l, g], p["bh"][l, g]))
+    return lin(h, p["wo"][g], p["bo"][g])
 
 
 def shape_functions(p_fs, x):

@@ -120,3 +120,37 @@ def test_balanced_ranges_properties():
     blocks = [row_block(169343, r, 8) for r in range(8)]
     assert blocks[0][0] == 0 and blocks[-1][1] == 169343 and all(b % 16 == 0 for b, _ in blocks)
     assert all(blocks[i][1] == blocks[i + 1][0] for i in range(7))
+
+
+def _flat_grads_three_ranks(rank, world):
+    """world 3, ragged blocks (one rank nearly empty), FlatGradients instead of the concatenating all-reduce"""
+    from gnan_b200.dist import FlatGradients, all_gather_rows, row_block
+    N, x, Wm, W, wout = _problem()
+    Wm = Wm.clone().requires_grad_(True)
+    bias = torch.zeros(3, dtype=torch.float64, requires_grad=True)
+    fg = FlatGradients([Wm, bias])
+    blocks = [row_block(N, r, world, align=16) for r in range(world)]          # 16 + 16 + 5 rows
+    sizes = [e - b for b, e in blocks]
+    b, e = blocks[rank]
+    for _ in range(2):                                                           # the second step must not accumulate
+        fg.zero()
+        s_local = torch.tanh(x[b:e]) @ Wm + bias
+        s_full = all_gather_rows(s_local, sizes)
+        out = (W[b:e] * s_full.unsqueeze(0)).sum(1)
+        (out * wout[b:e]).sum().backward()
+        fg.all_reduce()
+    assert Wm.grad.data_ptr() == fg.flat.data_ptr()
+    return out.detach(), Wm.grad.clone(), bias.grad.clone(), sizes
+
+
+def test_flat_gradients_and_ragged_gather_three_ranks():
+    res = run_world(_flat_grads_three_ranks, 3)
+    N, x, Wm, W, wout = _problem()
+    Wm = Wm.clone().requires_grad_(True)
+    bias = torch.zeros(3, dtype=torch.float64, requires_grad=True)
+    out = (W * (torch.tanh(x) @ Wm + bias).unsqueeze(0)).sum(1)
+    (out * wout).sum().backward()
+    assert res[0][3] == [16, 16, 5]
+    assert torch.allclose(torch.cat([res[r][0] for r in range(3)]), out.detach(), atol=1e-12)
+    for r in range(3):
+        assert torch.allclose(res[r][1], Wm.grad, atol=1e-12) and torch.allclose(res[r][2], bias.grad, atol=1e-12)

@@ -181,6 +181,72 @@ def test_mlp_input_gradient_vs_oracle(G_, H, C, L):
     assert G.rel_err(ud.grad.cpu().numpy(), uo.grad.numpy()) < TOL
 
 
+def test_build_csr_counting_sort():
+    """csrc/csr.cu: rowptr exact, every row holds the right neighbour SET (order unspecified), status bits."""
+    from gnan_b200.preprocess import build_csr
+    rng = np.random.default_rng(3)
+    n = 5000
+    ei = random_graph(rng, n, 3.1, True, n_isolated=40)
+    rowptr, col, st = build_csr(torch.tensor(ei), n, DEV)
+    rp, cl = rowptr.cpu().numpy(), col.cpu().numpy()
+    assert int(st.item()) == 0
+    deg = np.bincount(ei[0], minlength=n)
+    assert np.array_equal(rp, np.concatenate([[0], np.cumsum(deg)]))
+    order = np.lexsort((ei[1], ei[0]))
+    want = ei[1][order]
+    got = np.concatenate([np.sort(cl[rp[i]:rp[i + 1]]) for i in range(n)])
+    assert np.array_equal(got, want)
+    dup = np.concatenate([ei, ei[:, 7:8]], axis=1)
+    assert int(build_csr(torch.tensor(dup), n, DEV)[2].item()) == 2
+    bad = ei.copy(); bad[1, 3] = n
+    assert int(build_csr(torch.tensor(bad), n, DEV)[2].item()) & 1
+    rowptr, col, st = build_csr(torch.zeros(2, 0, dtype=torch.long), 4, DEV)
+    assert rowptr.tolist() == [0, 0, 0, 0, 0] and int(st.item()) == 0
+
+
+@pytest.mark.parametrize("batched", [False, True])
+def test_duplicate_edges_follow_the_reference_weighted_dijkstra(batched):
+    """pre_process_datasets.py:109-110: the COO -> LIL conversion SUMS duplicate edges, Dijkstra then runs on weights 2, 3, ...
+    Checked against scipy on the summed matrix (the reference's own two calls)."""
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import dijkstra
+    from gnan_b200.preprocess import apsp, apsp_batched
+    rng = np.random.default_rng(9)
+
+    def graph(n):
+        ei = random_graph(rng, n, 2.2, False, n_isolated=1)
+        pick = rng.choice(ei.shape[1], size=max(2, ei.shape[1] // 6), replace=False)
+        extra = np.concatenate([ei[:, pick], ei[:, pick[:2]]], axis=1)          # some edges twice, two of them three times
+        return np.concatenate([ei, extra], axis=1)
+
+    def want_of(ei, n):
+        adj = sp.lil_matrix(sp.coo_matrix((np.ones(ei.shape[1]), (ei[0], ei[1])), shape=(n, n)))
+        d = dijkstra(adj)
+        return np.where(np.isinf(d), -1, d).astype(np.int32)
+
+    if not batched:
+        n = 300
+        ei = graph(n)
+        hd = apsp(torch.tensor(ei), n, device=DEV)
+        got = hd.hop[:, :n].cpu().numpy().astype(np.int32); got[got == 255] = -1
+        want = want_of(ei, n)
+        assert np.array_equal(got, want)
+        assert np.array_equal(hd.level_counts.cpu().numpy(), oapsp.level_counts(want, hd.nbins))
+        nd, nm = hd.reference_format()
+        wnd, wnm = oapsp.reference_format(want, oapsp.level_counts(want))
+        assert np.array_equal(nd.cpu().numpy(), wnd) and np.array_equal(nm.cpu().numpy(), wnm)
+    else:
+        sizes = [12, 40, 7]
+        node_off = np.concatenate([[0], np.cumsum(sizes)])
+        eis = [graph(n) for n in sizes]
+        ei = np.concatenate([e + node_off[i] for i, e in enumerate(eis)], axis=1)
+        pk = apsp_batched(torch.tensor(ei), node_off, device=DEV)
+        hop, ho = pk.hop.cpu().numpy(), pk.hop_off.cpu().numpy()
+        for i, n in enumerate(sizes):
+            got = hop[ho[i]:ho[i + 1]].reshape(n, n).astype(np.int32); got[got == 255] = -1
+            assert np.array_equal(got, want_of(eis[i], n)), i
+
+
 def test_apsp_batched_vs_oracle():
     from gnan_b200.preprocess import apsp_batched
     rng = np.random.default_rng(5)

@@ -4,7 +4,7 @@ T=$1; shift
 for i in $(seq 1 30); do
   out=$(/usr/local/graft/bin/gpurun --timeout "$T" -- "$@" 2>&1)
   if echo "$out" | grep -q "status=transient\|nothing was charged\|no box or slot"; then
-    sleep 120; continue
+    sleep 45; continue
   fi
   echo "$out"; exit 0
 done
