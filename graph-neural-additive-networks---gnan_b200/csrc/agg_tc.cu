@@ -177,16 +177,90 @@ __device__ __forceinline__ uint32_t pack8(uint2 w, int stream)
     return p;
 }
 
+constexpr int NBUF = 3;            // A-operand buffers per generator group in tensor memory
+
 template <int NB, int NGR>
 struct TcCfg {
     static constexpr int RG = 128 / NB;             // hop rows per generator group (one MMA: M = 128 = RG rows x NB bins)
     static constexpr int ROWS = RG * NGR;           // hop rows per CTA
     static constexpr int NSTREAM = NB / 8;          // selector streams (one per group of 8 bins)
     static constexpr int HOPB = ROWS * TCOLS;       // hop bytes per stage
-    static constexpr int NIB_WORDS = 2 * NSTREAM * RG * 16;   // per group: [buf][stream][row][16 words]
-    static constexpr int ACC0 = NGR * 64;           // TMEM: A buffers [g][buf] 32 columns each, then the accumulators
-    static constexpr int THREADS = (NGR * 4 + 2) * 32;
+    static constexpr int NIB_BUF = NSTREAM * RG * 32;         // words per buffer: [stream][row][32 selector words]
+    static constexpr int NIB_WORDS = 2 * NIB_BUF;             // per group, double-buffered
+    static constexpr int ACC0 = NGR * NBUF * 32;    // TMEM: A buffers [g][buf] 32 columns each, then the accumulators
+    static constexpr int THREADS = (NGR * 5 + 1) * 32;        // 4 generator warps + 1 MMA-issuer warp per group, 1 TMA producer warp
 };
+
+struct PipeBars {
+    uint64_t *full, *empty, *a_full, *a_empty, *acc_full;
+    uint32_t *tmem_slot;
+};
+
+template <int NGR>
+__device__ __forceinline__ PipeBars carve_bars(void *base)
+{
+    PipeBars p;
+    p.full = reinterpret_cast<uint64_t *>(base);
+    p.empty = p.full + MAX_STAGES;
+    p.a_full = p.empty + MAX_STAGES;            // [NGR][NBUF]
+    p.a_empty = p.a_full + NGR * NBUF;          // [NGR][NBUF]
+    p.acc_full = p.a_empty + NGR * NBUF;        // [NGR]
+    p.tmem_slot = reinterpret_cast<uint32_t *>(p.acc_full + NGR);
+    return p;
+}
+constexpr size_t pipe_bar_bytes(int ngr) { return sizeof(uint64_t) * (2 * MAX_STAGES + 2 * ngr * NBUF + ngr) + 16; }
+
+template <int NGR>
+__device__ __forceinline__ uint32_t pipe_setup(const PipeBars &p, int stages)
+{
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) tmem_alloc(smem_u32(p.tmem_slot), 512);
+    if (tid == 32) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(smem_u32(&p.full[s]), 1);
+            mbar_init(smem_u32(&p.empty[s]), NGR);       // one tcgen05.commit per group
+        }
+        for (int g = 0; g < NGR * NBUF; ++g) {
+            mbar_init(smem_u32(&p.a_full[g]), 128);
+            mbar_init(smem_u32(&p.a_empty[g]), 1);
+        }
+        for (int g = 0; g < NGR; ++g) mbar_init(smem_u32(&p.acc_full[g]), 1);
+        mbar_init_fence();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    return *p.tmem_slot;
+}
+
+// the MMA issuer of group g: stage s -> 4 x (M128, N = NP, K32) on A buffer s % NBUF and the stage's B tile
+template <int NGR>
+__device__ __forceinline__ void issuer_loop(const PipeBars &p, uint32_t tmem, int g, int lane, int nst, int stages, int NP, int acc0,
+                                            const uint8_t *b_s, int BB)
+{
+    const uint32_t idesc = umma_idesc_i8(128, NP);
+    int st = 0, buf = 0;
+    uint32_t fph = 0, aph = 0;
+    for (int s = 0; s < nst; ++s) {
+        mbar_wait(smem_u32(&p.a_full[g * NBUF + buf]), aph);
+        mbar_wait(smem_u32(&p.full[st]), fph);           // complete long ago (the generators waited on it): orders the B tile for this thread
+        tc_fence_after();
+        if (lane == 0) {
+            const uint32_t bb = smem_u32(b_s + (size_t)st * BB);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+                umma_i8_ts(tmem + (uint32_t)(acc0 + g * NP), tmem + (uint32_t)((g * NBUF + buf) * 32 + ks * 8),
+                           umma_desc_kmajor(bb + ks * DG_KSTEP, DG_LBO, DG_SBO), idesc, (s > 0 || ks > 0) ? 1u : 0u);
+            umma_commit(smem_u32(&p.a_empty[g * NBUF + buf]));
+            umma_commit(smem_u32(&p.empty[st]));
+        }
+        __syncwarp();
+        if (++st == stages) { st = 0; fph ^= 1u; }
+        if (++buf == NBUF) { buf = 0; aph ^= 1u; }
+    }
+    if (lane == 0 && nst > 0) umma_commit(smem_u32(&p.acc_full[g]));
+    __syncwarp();
+}
 
 template <int NB, int NGR>
 __global__ void __launch_bounds__(TcCfg<NB, NGR>::THREADS, 1)
@@ -199,33 +273,11 @@ agg_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, AggTcArgs a)
     uint8_t *hop_s = smem;
     uint8_t *b_s = hop_s + (size_t)a.stages * HOPB;
     uint32_t *nib_s = reinterpret_cast<uint32_t *>(b_s + (size_t)a.stages * BB);
-    uint64_t *full = reinterpret_cast<uint64_t *>(nib_s + NGR * Cfg::NIB_WORDS);
-    uint64_t *empty = full + MAX_STAGES;
-    uint64_t *a_full = empty + MAX_STAGES;          // [NGR][2]
-    uint64_t *a_empty = a_full + NGR * 2;           // [NGR][2]
-    uint64_t *acc_full = a_empty + NGR * 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
+    const PipeBars pb = carve_bars<NGR>(nib_s + NGR * Cfg::NIB_WORDS);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t row0 = (int64_t)blockIdx.x * Cfg::ROWS;
-
-    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
-    if (tid == 32) {
-        for (int s = 0; s < a.stages; ++s) {
-            mbar_init(smem_u32(&full[s]), 1);
-            mbar_init(smem_u32(&empty[s]), 1);
-        }
-        for (int g = 0; g < NGR * 2; ++g) {
-            mbar_init(smem_u32(&a_full[g]), 128);
-            mbar_init(smem_u32(&a_empty[g]), 1);
-        }
-        mbar_init(smem_u32(acc_full), 1);
-        mbar_init_fence();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = pipe_setup<NGR>(pb, a.stages);
 
     if (warp < NGR * 4) {
         // ===== generators: thread m of group g owns TMEM lane m = (row r, bin slot) =====
@@ -235,39 +287,50 @@ agg_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, AggTcArgs a)
         const uint32_t lut_hi = (slot & 7) >= 4 ? 1u << (8 * ((slot & 7) - 4)) : 0u;
         const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         uint32_t *nib_g = nib_s + g * Cfg::NIB_WORDS;
+        int st = 0, buf = 0, prev_buf = 0;
+        uint32_t fph = 0, eph = 1;                                   // eph: parity of the a_empty completion that frees `buf` (lap - 1)
+        bool first_lap = true;
         for (int s = 0; s < a.nblk; ++s) {
-            const int st = s % a.stages, buf = s & 1;
-            mbar_wait(smem_u32(&full[st]), (uint32_t)(s / a.stages) & 1u);
-            uint32_t *nb = nib_g + buf * (NSTREAM * RG * 16);
+            mbar_wait(smem_u32(&pb.full[st]), fph);
+            uint32_t *nb = nib_g + (s & 1) * Cfg::NIB_BUF;
             const uint8_t *hs = hop_s + (size_t)st * HOPB + (size_t)g * RG * TCOLS;
 #pragma unroll
-            for (int ch = m; ch < RG * 16; ch += 128) {               // pack: 8 bytes -> one selector word per stream
+            for (int ch = m; ch < RG * 16; ch += 128) {               // pack: 8 hop bytes -> two 4-selector words per stream
                 const uint2 w = *reinterpret_cast<const uint2 *>(hs + ch * 8);
 #pragma unroll
-                for (int q = 0; q < NSTREAM; ++q) nb[q * (RG * 16) + ch] = pack8<NB>(w, q);
+                for (int q = 0; q < NSTREAM; ++q) {
+                    const uint32_t p = pack8<NB>(w, q);
+                    *reinterpret_cast<uint2 *>(nb + q * (RG * 32) + ch * 2) = make_uint2(p & 0xffffu, p >> 16);
+                }
+            }
+            if (s > 0) {                                              // the previous stage's TMEM store has had the pack to land
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(smem_u32(&pb.a_full[g * NBUF + prev_buf]));
             }
             named_bar_sync(1 + g, 128);
-            if (s >= 2) {
-                mbar_wait(smem_u32(&a_empty[g * 2 + buf]), (uint32_t)((s >> 1) - 1) & 1u);
+            if (!first_lap) {
+                mbar_wait(smem_u32(&pb.a_empty[g * NBUF + buf]), eph);
                 tc_fence_after();
             }
-            const uint4 *src = reinterpret_cast<const uint4 *>(nb + strm * (RG * 16) + r * 16);
+            const uint4 *src = reinterpret_cast<const uint4 *>(nb + strm * (RG * 32) + r * 32);
             uint32_t v[32];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < 8; ++q) {
                 const uint4 p = src[q];
-                v[8 * q + 0] = prmt(lut_lo, lut_hi, p.x); v[8 * q + 1] = prmt(lut_lo, lut_hi, p.x >> 16);
-                v[8 * q + 2] = prmt(lut_lo, lut_hi, p.y); v[8 * q + 3] = prmt(lut_lo, lut_hi, p.y >> 16);
-                v[8 * q + 4] = prmt(lut_lo, lut_hi, p.z); v[8 * q + 5] = prmt(lut_lo, lut_hi, p.z >> 16);
-                v[8 * q + 6] = prmt(lut_lo, lut_hi, p.w); v[8 * q + 7] = prmt(lut_lo, lut_hi, p.w >> 16);
+                v[4 * q + 0] = prmt(lut_lo, lut_hi, p.x); v[4 * q + 1] = prmt(lut_lo, lut_hi, p.y);
+                v[4 * q + 2] = prmt(lut_lo, lut_hi, p.z); v[4 * q + 3] = prmt(lut_lo, lut_hi, p.w);
             }
-            tmem_st32(lane_base + (uint32_t)((g * 2 + buf) * 32), v);
-            tmem_wait_st();
-            tc_fence_before();
-            mbar_arrive(smem_u32(&a_full[g * 2 + buf]));
+            tmem_st32(lane_base + (uint32_t)((g * NBUF + buf) * 32), v);
+            prev_buf = buf;
+            if (++st == a.stages) { st = 0; fph ^= 1u; }
+            if (++buf == NBUF) { buf = 0; eph ^= 1u; first_lap = false; }
         }
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(smem_u32(&pb.a_full[g * NBUF + prev_buf]));
         // ===== epilogue: Bsum (exact integer bin sums -> fp32) and out = sum_d T * rscale * Bsum =====
-        mbar_wait(smem_u32(acc_full), 0);
+        mbar_wait(smem_u32(&pb.acc_full[g]), 0);
         tc_fence_after();
         const int64_t i = row0 + g * RG + r;
         const bool slot_ok = slot < a.nbins - 1 || slot == NB - 1;
@@ -300,43 +363,24 @@ agg_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, AggTcArgs a)
             }
         }
         tc_fence_before();
-    } else if (warp == NGR * 4) {
+    } else if (warp < NGR * 5) {
+        issuer_loop<NGR>(pb, tmem, warp - NGR * 4, lane, a.nblk, a.stages, a.NP, Cfg::ACC0, b_s, BB);
+    } else {
         // ===== TMA producer =====
         if (lane == 0) {
             prefetch_tmap(&tmap);
+            int st = 0;
+            uint32_t eph = 1;
+            bool first_lap = true;
             for (int s = 0; s < a.nblk; ++s) {
-                const int st = s % a.stages;
-                if (s >= a.stages) mbar_wait(smem_u32(&empty[st]), (uint32_t)(s / a.stages - 1) & 1u);
-                const uint32_t bar = smem_u32(&full[st]);
+                if (!first_lap) mbar_wait(smem_u32(&pb.empty[st]), eph);
+                const uint32_t bar = smem_u32(&pb.full[st]);
                 mbar_expect_tx(bar, (uint32_t)(HOPB + BB));
                 tma_load_2d(smem_u32(hop_s + (size_t)st * HOPB), &tmap, s * TCOLS, (int)row0, bar);
                 bulk_load_1d(smem_u32(b_s + (size_t)st * BB), a.dig + (size_t)s * BB, (uint32_t)BB, bar);
+                if (++st == a.stages) { st = 0; eph ^= 1u; first_lap = false; }
             }
         }
-    } else {
-        // ===== MMA issuer =====
-        const uint32_t idesc = umma_idesc_i8(128, a.NP);
-        for (int s = 0; s < a.nblk; ++s) {
-            const int st = s % a.stages, buf = s & 1;
-            mbar_wait(smem_u32(&full[st]), (uint32_t)(s / a.stages) & 1u);
-            for (int g = 0; g < NGR; ++g) {
-                mbar_wait(smem_u32(&a_full[g * 2 + buf]), (uint32_t)(s >> 1) & 1u);
-                tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t bb = smem_u32(b_s + (size_t)st * BB);
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        umma_i8_ts(tmem + (uint32_t)(Cfg::ACC0 + g * a.NP), tmem + (uint32_t)((g * 2 + buf) * 32 + ks * 8),
-                                   umma_desc_kmajor(bb + ks * DG_KSTEP, DG_LBO, DG_SBO), idesc, (s > 0 || ks > 0) ? 1u : 0u);
-                    umma_commit(smem_u32(&a_empty[g * 2 + buf]));
-                }
-                __syncwarp();
-            }
-            if (lane == 0) umma_commit(smem_u32(&empty[st]));
-            __syncwarp();
-        }
-        if (lane == 0) umma_commit(smem_u32(acc_full));
-        __syncwarp();
     }
     __syncthreads();
     if (warp == 0) {
@@ -490,12 +534,7 @@ agg_tc_ds_kernel(DsTcArgs a)
     const int BB = a.NP * TCOLS;
     uint8_t *hop_s = smem;
     uint8_t *b_s = hop_s + (size_t)a.stages * HOPB;
-    uint64_t *full = reinterpret_cast<uint64_t *>(b_s + (size_t)a.stages * BB);
-    uint64_t *empty = full + MAX_STAGES;
-    uint64_t *a_full = empty + MAX_STAGES;
-    uint64_t *a_empty = a_full + NGR * 2;
-    uint64_t *acc_full = a_empty + NGR * 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_full + 1);
+    const PipeBars pb = carve_bars<NGR>(b_s + (size_t)a.stages * BB);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nact = *a.nact;
@@ -504,49 +543,48 @@ agg_tc_ds_kernel(DsTcArgs a)
     const int nst = k1 > k0 ? (k1 - k0 + RS - 1) / RS : 0;
     const int64_t col0 = (int64_t)blockIdx.x * CW;
     const uint32_t wbytes = (uint32_t)min((int64_t)CW, a.ld - col0);      // ld % 16 == 0: a multiple of 16
-
-    if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
-    if (tid == 32) {
-        for (int s = 0; s < a.stages; ++s) {
-            mbar_init(smem_u32(&full[s]), 1);
-            mbar_init(smem_u32(&empty[s]), 1);
-        }
-        for (int g = 0; g < NGR * 2; ++g) {
-            mbar_init(smem_u32(&a_full[g]), 128);
-            mbar_init(smem_u32(&a_empty[g]), 1);
-        }
-        mbar_init(smem_u32(acc_full), 1);
-        mbar_init_fence();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = pipe_setup<NGR>(pb, a.stages);
 
     if (warp < NGR * 4) {
         // ===== generators: thread m of group g owns TMEM lane m = hop column col0 + g*128 + m =====
         const int g = warp >> 2, m = tid & 127;
         const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        const uint8_t *hcol = hop_s + g * 128 + m;
+        int st = 0, buf = 0;
+        uint32_t fph = 0, eph = 1;
+        bool first_lap = true;
+        uint32_t h[RS];
+        if (nst > 0) {
+            mbar_wait(smem_u32(&pb.full[0]), 0);
+#pragma unroll
+            for (int r = 0; r < RS; ++r) h[r] = hcol[r * CW];
+        }
         for (int s = 0; s < nst; ++s) {
-            const int st = s % a.stages, buf = s & 1;
-            mbar_wait(smem_u32(&full[st]), (uint32_t)(s / a.stages) & 1u);
-            if (s >= 2) {
-                mbar_wait(smem_u32(&a_empty[g * 2 + buf]), (uint32_t)((s >> 1) - 1) & 1u);
-                tc_fence_after();
-            }
-            const uint8_t *hs = hop_s + (size_t)st * HOPB + g * 128 + m;
             uint32_t v[32];
 #pragma unroll
-            for (int r = 0; r < RS; ++r) onehot_row<NB>(hs[r * CW], &v[r * (NB / 4)]);
-            tmem_st32(lane_base + (uint32_t)((g * 2 + buf) * 32), v);
+            for (int r = 0; r < RS; ++r) onehot_row<NB>(h[r], &v[r * (NB / 4)]);
+            if (!first_lap) {
+                mbar_wait(smem_u32(&pb.a_empty[g * NBUF + buf]), eph);
+                tc_fence_after();
+            }
+            tmem_st32(lane_base + (uint32_t)((g * NBUF + buf) * 32), v);
+            const int cur = buf;
+            if (++st == a.stages) { st = 0; fph ^= 1u; }
+            if (++buf == NBUF) { buf = 0; eph ^= 1u; first_lap = false; }
+            if (s + 1 < nst) {                                        // the next stage's bytes load while the TMEM store lands
+                mbar_wait(smem_u32(&pb.full[st]), fph);
+                const uint8_t *hs = hcol + (size_t)st * HOPB;
+#pragma unroll
+                for (int r = 0; r < RS; ++r) h[r] = hs[r * CW];
+            }
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(smem_u32(&a_full[g * 2 + buf]));
+            mbar_arrive(smem_u32(&pb.a_full[g * NBUF + cur]));
         }
         const int64_t j = col0 + g * 128 + m;
         float *dst = a.out + ((size_t)blockIdx.y * a.N + (j < a.N ? j : 0)) * a.C;
         if (nst > 0) {
-            mbar_wait(smem_u32(acc_full), 0);
+            mbar_wait(smem_u32(&pb.acc_full[g]), 0);
             tc_fence_after();
         }
         for (int n0 = 0; n0 < a.NP; n0 += 16) {
@@ -574,44 +612,25 @@ agg_tc_ds_kernel(DsTcArgs a)
             }
         }
         tc_fence_before();
-    } else if (warp == NGR * 4) {
+    } else if (warp < NGR * 5) {
+        issuer_loop<NGR>(pb, tmem, warp - NGR * 4, lane, nst, a.stages, a.NP, Cfg::ACC0, b_s, BB);
+    } else {
         // ===== producer: one bulk copy per active row (the rows are gathered by index) + the digit block of the stage =====
         if (lane == 0) {
+            int st = 0;
+            uint32_t eph = 1;
+            bool first_lap = true;
             for (int s = 0; s < nst; ++s) {
-                const int st = s % a.stages;
-                if (s >= a.stages) mbar_wait(smem_u32(&empty[st]), (uint32_t)(s / a.stages - 1) & 1u);
-                const uint32_t bar = smem_u32(&full[st]);
+                if (!first_lap) mbar_wait(smem_u32(&pb.empty[st]), eph);
+                const uint32_t bar = smem_u32(&pb.full[st]);
                 const int kb = k0 + s * RS, nr = min(RS, k1 - kb);
                 mbar_expect_tx(bar, (uint32_t)nr * wbytes + (uint32_t)BB);
                 for (int r = 0; r < nr; ++r)
                     bulk_load_1d(smem_u32(hop_s + (size_t)st * HOPB + r * CW), a.hop + (int64_t)a.rows[kb + r] * a.ld + col0, wbytes, bar);
                 bulk_load_1d(smem_u32(b_s + (size_t)st * BB), a.dig + (size_t)(kb / RS) * BB, (uint32_t)BB, bar);
+                if (++st == a.stages) { st = 0; eph ^= 1u; first_lap = false; }
             }
         }
-    } else {
-        // ===== MMA issuer =====
-        const uint32_t idesc = umma_idesc_i8(128, a.NP);
-        for (int s = 0; s < nst; ++s) {
-            const int st = s % a.stages, buf = s & 1;
-            mbar_wait(smem_u32(&full[st]), (uint32_t)(s / a.stages) & 1u);
-            for (int g = 0; g < NGR; ++g) {
-                mbar_wait(smem_u32(&a_full[g * 2 + buf]), (uint32_t)(s >> 1) & 1u);
-                tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t bb = smem_u32(b_s + (size_t)st * BB);
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        umma_i8_ts(tmem + (uint32_t)(Cfg::ACC0 + g * a.NP), tmem + (uint32_t)((g * 2 + buf) * 32 + ks * 8),
-                                   umma_desc_kmajor(bb + ks * DG_KSTEP, DG_LBO, DG_SBO), idesc, (s > 0 || ks > 0) ? 1u : 0u);
-                    umma_commit(smem_u32(&a_empty[g * 2 + buf]));
-                }
-                __syncwarp();
-            }
-            if (lane == 0) umma_commit(smem_u32(&empty[st]));
-            __syncwarp();
-        }
-        if (lane == 0 && nst > 0) umma_commit(smem_u32(acc_full));
-        __syncwarp();
     }
     __syncthreads();
     if (warp == 0) {
@@ -664,6 +683,9 @@ int make_hop_tmap(CUtensorMap *map, const uint8_t *hop, int64_t rows, int64_t ld
 
 inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
+// generator groups per CTA: every group owns NBUF A buffers (32 TMEM columns each) and NP accumulator columns of the 512
+inline int groups_for(int NP) { return std::max(1, std::min(4, 512 / (NBUF * 32 + NP))); }
+
 struct FwdWs { uint32_t *colmax; int32_t *colsh; int8_t *dig; size_t total; };
 FwdWs fwd_ws_layout(void *base, int64_t N, int C)
 {
@@ -683,7 +705,7 @@ int launch_fwd(const CUtensorMap &map, AggTcArgs a, cudaStream_t st)
 {
     using Cfg = TcCfg<NB, NGR>;
     const size_t per_stage = (size_t)Cfg::HOPB + (size_t)a.NP * TCOLS;
-    const size_t fixed = sizeof(uint32_t) * NGR * Cfg::NIB_WORDS + sizeof(uint64_t) * (2 * MAX_STAGES + 4 * NGR + 1) + 16;
+    const size_t fixed = sizeof(uint32_t) * NGR * Cfg::NIB_WORDS + pipe_bar_bytes(NGR);
     int stages = (int)std::min<size_t>(MAX_STAGES, (200 * 1024 - fixed) / per_stage);
     if (stages < 2) {
         gnan_set_error("aggregate_rows (tensor-core path): stage of %zu bytes does not fit shared memory", per_stage);
@@ -703,6 +725,7 @@ template <int NB>
 int launch_fwd_nb(const CUtensorMap &map, const AggTcArgs &a, int ngr, cudaStream_t st)
 {
     if (ngr == 4) return launch_fwd<NB, 4>(map, a, st);
+    if (ngr == 3) return launch_fwd<NB, 3>(map, a, st);
     if (ngr == 2) return launch_fwd<NB, 2>(map, a, st);
     return launch_fwd<NB, 1>(map, a, st);
 }
@@ -754,7 +777,7 @@ extern "C" int gnan_aggregate_rows_fwd_ws(const uint8_t *hop, int64_t R, int64_t
     GNAN_LAUNCH_OK();
 
     AggTcArgs a{R, N, nbins, C, Cr, table_per_row, p.ndig, p.cpc, p.NP, nblk, 0, T, rscale, w.colsh, w.dig, out, Bsum};
-    const int ngr = p.NP <= 64 ? 4 : (p.NP <= 192 ? 2 : 1);
+    const int ngr = groups_for(p.NP);
     const int nb = nbins <= 8 ? 8 : (nbins <= 16 ? 16 : 32);
     CUtensorMap map;
     int rc = make_hop_tmap(&map, hop, R, ld_hop, (128 / nb) * ngr);
@@ -773,7 +796,7 @@ BwdPlan bwd_plan(int64_t R, int64_t N, int nbins, int C)
     BwdPlan p;
     p.dp = digit_plan(C);
     p.nb = nbins <= 8 ? 8 : (nbins <= 16 ? 16 : 32);
-    p.ngr = p.dp.NP <= 64 ? 4 : (p.dp.NP <= 192 ? 2 : 1);
+    p.ngr = groups_for(p.dp.NP);
     p.RS = 128 / p.nb;
     p.CW = p.ngr * 128;
     p.ncol = (int)ceil_div64(N, p.CW);
@@ -805,7 +828,7 @@ int launch_ds(DsTcArgs a, int ncol, int nsb, cudaStream_t st)
 {
     using Cfg = TcCfg<NB, NGR>;
     const size_t per_stage = (size_t)(128 / NB) * NGR * 128 + (size_t)a.NP * TCOLS;
-    const size_t fixed = sizeof(uint64_t) * (2 * MAX_STAGES + 4 * NGR + 1) + 16;
+    const size_t fixed = pipe_bar_bytes(NGR);
     int stages = (int)std::min<size_t>(MAX_STAGES, (200 * 1024 - fixed) / per_stage);
     if (stages < 2) {
         gnan_set_error("aggregate_rows_bwd (tensor-core path): stage of %zu bytes does not fit shared memory", per_stage);
@@ -823,6 +846,7 @@ template <int NB>
 int launch_ds_nb(const DsTcArgs &a, const BwdPlan &p, cudaStream_t st)
 {
     if (p.ngr == 4) return launch_ds<NB, 4>(a, p.ncol, p.nsb, st);
+    if (p.ngr == 3) return launch_ds<NB, 3>(a, p.ncol, p.nsb, st);
     if (p.ngr == 2) return launch_ds<NB, 2>(a, p.ncol, p.nsb, st);
     return launch_ds<NB, 1>(a, p.ncol, p.nsb, st);
 }

@@ -197,11 +197,14 @@ class CapturedStep:
     `hop_data.static_level_counts = True`.
     """
 
-    def __init__(self, loss_closure, optimizer, warmup=3, after_backward=None):
+    def __init__(self, loss_closure, optimizer, warmup=3, after_backward=None, zero_grad=None):
         """after_backward: optional callable run between backward and the optimizer step INSIDE the captured step, e.g.
-        `lambda: dist.allreduce_gradients(model.parameters(), average=True)` for data-parallel training: NCCL collectives
-        are captured like kernels (every rank must capture the same sequence)."""
+        `lambda: flat_grads.all_reduce(average=True)` for data-parallel training: NCCL collectives are captured like kernels
+        (every rank must capture the same sequence).
+        zero_grad: optional callable replacing `optimizer.zero_grad(set_to_none=True)`, e.g. `dist.FlatGradients.zero` (the
+        gradients are views of one persistent buffer that must not be dropped)."""
         self._closure, self._opt, self._after = loss_closure, optimizer, after_backward
+        self._zero = zero_grad if zero_grad is not None else (lambda: optimizer.zero_grad(set_to_none=True))
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):                           # warm-up off the capture stream: allocator + optimizer state
@@ -210,7 +213,7 @@ class CapturedStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        optimizer.zero_grad(set_to_none=True)
+        self._zero()
         from ._lib import load
         lib = load()
         n0 = lib.gnan_launch_count()
@@ -220,7 +223,7 @@ class CapturedStep:
         self.kernel_launches = int(lib.gnan_launch_count() - n0)     # gnan_b200 kernels per replay (the counter is host-side)
 
     def _eager(self):
-        self._opt.zero_grad(set_to_none=True)
+        self._zero()
         loss = self._closure()
         loss.backward()
         if self._after is not None:

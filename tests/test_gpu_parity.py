@@ -759,6 +759,44 @@ def test_captured_step_equals_eager_steps():
     assert np.allclose(losses["eager"], losses["graph"], rtol=1e-5), losses
 
 
+def test_captured_step_sees_inputs_refreshed_in_place():
+    """the implicit shared-evaluation caches (compressed features keyed on x, value -> row mapping of the
+    per-row rho inputs keyed on the level counts) must not be baked into a captured step: after x.copy_() /
+    level_counts.copy_() the replay has to compute on the NEW values."""
+    from gnan_b200 import trainer
+    from gnan_b200.GNAN import TensorGNAN
+    from gnan_b200.preprocess import HopData, apsp
+    rng = np.random.default_rng(21)
+    n, K, C = 600, 120, 3                                               # 72 000 (row, feature) pairs: above the auto-dedup threshold
+    mk = lambda: torch.tensor((rng.random((n, K)) < 0.1) * rng.integers(1, 4, size=(n, K))).float().to(DEV)
+    x_a, x_b = mk(), mk()
+    hd_a = apsp(torch.tensor(random_graph(rng, n, 2.5, False, n_isolated=3)), n, device=DEV)
+    hd_b = apsp(torch.tensor(random_graph(rng, n, 3.5, False, n_isolated=9)), n, device=DEV)
+    nb = max(hd_a.nbins, hd_b.nbins)
+
+    def padded(hd):                                                     # same level-table width for both graphs
+        cnt = torch.zeros(n, nb, dtype=torch.int32, device=DEV)
+        cnt[:, :hd.nbins - 1] = hd.level_counts[:, :-1]; cnt[:, -1] = hd.level_counts[:, -1]
+        return HopData(hd.hop.clone(), cnt, n)
+    hd_a, hd_b = padded(hd_a), padded(hd_b)
+    y = torch.tensor(rng.integers(0, C, size=n)).to(DEV)
+    torch.manual_seed(0)
+    m = TensorGNAN(K, C, 3, 64).to(DEV)
+    m.fs.xavier_normal_(1.0); m.rho.xavier_normal_(1.0)
+    opt = torch.optim.SGD(m.parameters(), lr=0.0)                       # weights stay put: the loss depends on the inputs only
+    static = SimpleNamespace(x=x_a.clone(), hop_data=HopData(hd_a.hop.clone(), hd_a.level_counts.clone(), n))
+    closure = lambda: torch.nn.functional.cross_entropy(m.forward(static), y)
+    step = trainer.CapturedStep(closure, opt, warmup=2)
+    loss_a = float(step())
+    static.x.copy_(x_b); static.hop_data.hop.copy_(hd_b.hop); static.hop_data.level_counts.copy_(hd_b.level_counts)
+    loss_b = float(step())
+    with torch.no_grad():
+        want_a = float(torch.nn.functional.cross_entropy(m.forward(SimpleNamespace(x=x_a, hop_data=hd_a)), y))
+        want_b = float(torch.nn.functional.cross_entropy(m.forward(SimpleNamespace(x=x_b, hop_data=hd_b)), y))
+    assert abs(want_a - want_b) > 1e-4 * abs(want_a)                    # the two inputs really differ
+    assert abs(loss_a - want_a) < 1e-5 * abs(want_a) and abs(loss_b - want_b) < 1e-5 * abs(want_b), (loss_a, want_a, loss_b, want_b)
+
+
 # ---- packed dataset format and loader (SURVEY §8f-2) ---------------------------------------------------------------------
 GRAPH_PRE = ["preprocess_tree_undirected", "preprocess_isolated_undirected", "preprocess_directed", "preprocess_single_node"]
 
