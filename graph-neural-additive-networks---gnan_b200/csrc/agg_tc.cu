@@ -152,9 +152,10 @@ struct AggTcArgs {
     float *out, *Bsum;
 };
 
-// 8 hop bytes -> 8 four-bit selectors (selector k in nibble k); NB = bins per row slot
+// 8 hop bytes -> the two 4-selector words of one stream (selector k of a word in nibble k, upper 16 bits zero: prmt reads only
+// the low 16 bits of its selector operand); NB = bins per row slot
 template <int NB>
-__device__ __forceinline__ uint32_t pack8(uint2 w, int stream)
+__device__ __forceinline__ uint2 pack8(uint2 w, int stream)
 {
     uint32_t a = w.x, b = w.y;
     if (NB == 32) {
@@ -165,16 +166,15 @@ __device__ __forceinline__ uint32_t pack8(uint2 w, int stream)
         xb = (xb | (xb >> 1)) & 0x01010101u;
         a = (a5 & 0x07070707u) | (xa << 3);
         b = (b5 & 0x07070707u) | (xb << 3);
-    } else {
-        constexpr uint32_t M = NB == 16 ? 0x0f0f0f0fu : 0x07070707u;   // 255 (unreachable) -> the last slot
-        a &= M;
-        b &= M;
     }
-    a |= a >> 4;
-    b |= b >> 4;
-    uint32_t p = prmt(a, b, 0x6420u);
-    if (NB == 16 && stream) p ^= 0x88888888u;
-    return p;
+    // byte k of a/b holds selector k in its low nibble (NB <= 16: hop & 15 / & 7; 255 = unreachable -> the last slot):
+    // merge neighbours into bytes 0 and 2 (low nibble = even selector, high nibble = odd selector), then gather those bytes
+    constexpr uint32_t LO = NB == 8 ? 0x07070707u : 0x0f0f0f0fu, HI = NB == 8 ? 0x70707070u : 0xf0f0f0f0u;
+    a = (a & LO) | ((a >> 4) & HI);
+    b = (b & LO) | ((b >> 4) & HI);
+    uint32_t lo = prmt(a, 0u, 0x4420u), hi = prmt(b, 0u, 0x4420u);
+    if (NB == 16 && stream) { lo ^= 0x8888u; hi ^= 0x8888u; }
+    return make_uint2(lo, hi);
 }
 
 constexpr int NBUF = 3;            // A-operand buffers per generator group in tensor memory
@@ -289,30 +289,29 @@ agg_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, AggTcArgs a)
         uint32_t *nib_g = nib_s + g * Cfg::NIB_WORDS;
         int st = 0, buf = 0, prev_buf = 0;
         uint32_t fph = 0, eph = 1;                                   // eph: parity of the a_empty completion that frees `buf` (lap - 1)
-        bool first_lap = true;
         for (int s = 0; s < a.nblk; ++s) {
             mbar_wait(smem_u32(&pb.full[st]), fph);
+            // pack: the 32 lanes of a warp are (32 / NB rows) x NB bin slots, so a warp packs exactly the rows its own lanes read:
+            // 8 hop bytes -> two 4-selector words per stream, through a warp-private slice of shared memory (__syncwarp only)
             uint32_t *nb = nib_g + (s & 1) * Cfg::NIB_BUF;
             const uint8_t *hs = hop_s + (size_t)st * HOPB + (size_t)g * RG * TCOLS;
+            constexpr int CH_W = (32 / NB) * 16;                      // 8-byte chunks of this warp's rows
+            const int ch0 = (warp & 3) * CH_W;
 #pragma unroll
-            for (int ch = m; ch < RG * 16; ch += 128) {               // pack: 8 hop bytes -> two 4-selector words per stream
+            for (int cw = lane; cw < CH_W; cw += 32) {
+                const int ch = ch0 + cw;
                 const uint2 w = *reinterpret_cast<const uint2 *>(hs + ch * 8);
 #pragma unroll
-                for (int q = 0; q < NSTREAM; ++q) {
-                    const uint32_t p = pack8<NB>(w, q);
-                    *reinterpret_cast<uint2 *>(nb + q * (RG * 32) + ch * 2) = make_uint2(p & 0xffffu, p >> 16);
-                }
+                for (int q = 0; q < NSTREAM; ++q) *reinterpret_cast<uint2 *>(nb + q * (RG * 32) + ch * 2) = pack8<NB>(w, q);
             }
             if (s > 0) {                                              // the previous stage's TMEM store has had the pack to land
                 tmem_wait_st();
                 tc_fence_before();
                 mbar_arrive(smem_u32(&pb.a_full[g * NBUF + prev_buf]));
             }
-            named_bar_sync(1 + g, 128);
-            if (!first_lap) {
-                mbar_wait(smem_u32(&pb.a_empty[g * NBUF + buf]), eph);
-                tc_fence_after();
-            }
+            __syncwarp();
+            mbar_wait(smem_u32(&pb.a_empty[g * NBUF + buf]), eph);   // first lap: a fresh barrier passes a wait on parity 1
+            tc_fence_after();
             const uint4 *src = reinterpret_cast<const uint4 *>(nb + strm * (RG * 32) + r * 32);
             uint32_t v[32];
 #pragma unroll
@@ -324,7 +323,7 @@ agg_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, AggTcArgs a)
             tmem_st32(lane_base + (uint32_t)((g * NBUF + buf) * 32), v);
             prev_buf = buf;
             if (++st == a.stages) { st = 0; fph ^= 1u; }
-            if (++buf == NBUF) { buf = 0; eph ^= 1u; first_lap = false; }
+            if (++buf == NBUF) { buf = 0; eph ^= 1u; }
         }
         tmem_wait_st();
         tc_fence_before();
@@ -371,14 +370,13 @@ agg_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, AggTcArgs a)
             prefetch_tmap(&tmap);
             int st = 0;
             uint32_t eph = 1;
-            bool first_lap = true;
             for (int s = 0; s < a.nblk; ++s) {
-                if (!first_lap) mbar_wait(smem_u32(&pb.empty[st]), eph);
+                mbar_wait(smem_u32(&pb.empty[st]), eph);
                 const uint32_t bar = smem_u32(&pb.full[st]);
                 mbar_expect_tx(bar, (uint32_t)(HOPB + BB));
                 tma_load_2d(smem_u32(hop_s + (size_t)st * HOPB), &tmap, s * TCOLS, (int)row0, bar);
                 bulk_load_1d(smem_u32(b_s + (size_t)st * BB), a.dig + (size_t)s * BB, (uint32_t)BB, bar);
-                if (++st == a.stages) { st = 0; eph ^= 1u; first_lap = false; }
+                if (++st == a.stages) { st = 0; eph ^= 1u; }
             }
         }
     }
@@ -500,19 +498,20 @@ struct DsTcArgs {
 };
 
 // one hop byte -> its NB one-hot int8 values (NB/4 TMEM columns)
+// `one` = 1 held in ONE register by the caller (an immediate would be re-materialised per prmt)
 template <int NB>
-__device__ __forceinline__ void onehot_row(uint32_t h, uint32_t *v)
+__device__ __forceinline__ void onehot_row(uint32_t h, uint32_t *v, uint32_t one)
 {
     if (NB == 8) {
         const uint32_t H = (h & 7u) * 0x1111u;
-        v[0] = prmt(1u, 0u, H ^ 0x3210u); v[1] = prmt(1u, 0u, H ^ 0x7654u);
+        v[0] = prmt(one, 0u, H ^ 0x3210u); v[1] = prmt(one, 0u, H ^ 0x7654u);
     } else if (NB == 16) {
         const uint32_t H = (h & 15u) * 0x1111u;
-        v[0] = prmt(1u, 0u, H ^ 0x3210u); v[1] = prmt(1u, 0u, H ^ 0x7654u);
-        v[2] = prmt(1u, 0u, H ^ 0xba98u); v[3] = prmt(1u, 0u, H ^ 0xfedcu);
+        v[0] = prmt(one, 0u, H ^ 0x3210u); v[1] = prmt(one, 0u, H ^ 0x7654u);
+        v[2] = prmt(one, 0u, H ^ 0xba98u); v[3] = prmt(one, 0u, H ^ 0xfedcu);
     } else {
         const uint32_t hh = h & 31u, H = (hh & 7u) * 0x1111u, q = hh >> 3;
-        const uint32_t p0 = prmt(1u, 0u, H ^ 0x3210u), p1 = prmt(1u, 0u, H ^ 0x7654u);
+        const uint32_t p0 = prmt(one, 0u, H ^ 0x3210u), p1 = prmt(one, 0u, H ^ 0x7654u);
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
             v[2 * w] = q == (uint32_t)w ? p0 : 0u;
@@ -552,8 +551,8 @@ agg_tc_ds_kernel(DsTcArgs a)
         const uint8_t *hcol = hop_s + g * 128 + m;
         int st = 0, buf = 0;
         uint32_t fph = 0, eph = 1;
-        bool first_lap = true;
-        uint32_t h[RS];
+        uint32_t h[RS], one;
+        asm volatile("mov.u32 %0, 1;" : "=r"(one));
         if (nst > 0) {
             mbar_wait(smem_u32(&pb.full[0]), 0);
 #pragma unroll
@@ -562,15 +561,13 @@ agg_tc_ds_kernel(DsTcArgs a)
         for (int s = 0; s < nst; ++s) {
             uint32_t v[32];
 #pragma unroll
-            for (int r = 0; r < RS; ++r) onehot_row<NB>(h[r], &v[r * (NB / 4)]);
-            if (!first_lap) {
-                mbar_wait(smem_u32(&pb.a_empty[g * NBUF + buf]), eph);
-                tc_fence_after();
-            }
+            for (int r = 0; r < RS; ++r) onehot_row<NB>(h[r], &v[r * (NB / 4)], one);
+            mbar_wait(smem_u32(&pb.a_empty[g * NBUF + buf]), eph);
+            tc_fence_after();
             tmem_st32(lane_base + (uint32_t)((g * NBUF + buf) * 32), v);
             const int cur = buf;
             if (++st == a.stages) { st = 0; fph ^= 1u; }
-            if (++buf == NBUF) { buf = 0; eph ^= 1u; first_lap = false; }
+            if (++buf == NBUF) { buf = 0; eph ^= 1u; }
             if (s + 1 < nst) {                                        // the next stage's bytes load while the TMEM store lands
                 mbar_wait(smem_u32(&pb.full[st]), fph);
                 const uint8_t *hs = hcol + (size_t)st * HOPB;
@@ -615,21 +612,23 @@ agg_tc_ds_kernel(DsTcArgs a)
     } else if (warp < NGR * 5) {
         issuer_loop<NGR>(pb, tmem, warp - NGR * 4, lane, nst, a.stages, a.NP, Cfg::ACC0, b_s, BB);
     } else {
-        // ===== producer: one bulk copy per active row (the rows are gathered by index) + the digit block of the stage =====
-        if (lane == 0) {
-            int st = 0;
-            uint32_t eph = 1;
-            bool first_lap = true;
-            for (int s = 0; s < nst; ++s) {
-                if (!first_lap) mbar_wait(smem_u32(&pb.empty[st]), eph);
-                const uint32_t bar = smem_u32(&pb.full[st]);
-                const int kb = k0 + s * RS, nr = min(RS, k1 - kb);
-                mbar_expect_tx(bar, (uint32_t)nr * wbytes + (uint32_t)BB);
-                for (int r = 0; r < nr; ++r)
-                    bulk_load_1d(smem_u32(hop_s + (size_t)st * HOPB + r * CW), a.hop + (int64_t)a.rows[kb + r] * a.ld + col0, wbytes, bar);
-                bulk_load_1d(smem_u32(b_s + (size_t)st * BB), a.dig + (size_t)(kb / RS) * BB, (uint32_t)BB, bar);
-                if (++st == a.stages) { st = 0; eph ^= 1u; first_lap = false; }
-            }
+        // ===== producer warp: lane r gathers active row r of the stage with one bulk copy (the row indices are read coalesced,
+        // one stage ahead), lane 31 brings the digit block =====
+        int st = 0;
+        uint32_t eph = 1;
+        int64_t row = (lane < RS && k0 + lane < k1) ? (int64_t)a.rows[k0 + lane] : 0;
+        for (int s = 0; s < nst; ++s) {
+            const int kb = k0 + s * RS, nr = min(RS, k1 - kb);
+            const int kn = kb + RS + lane;
+            const int64_t row_next = (lane < RS && kn < k1) ? (int64_t)a.rows[kn] : 0;
+            mbar_wait(smem_u32(&pb.empty[st]), eph);
+            const uint32_t bar = smem_u32(&pb.full[st]);
+            if (lane == 0) mbar_expect_tx(bar, (uint32_t)nr * wbytes + (uint32_t)BB);
+            __syncwarp();
+            if (lane < nr) bulk_load_1d(smem_u32(hop_s + (size_t)st * HOPB + lane * CW), a.hop + row * a.ld + col0, wbytes, bar);
+            if (lane == 31) bulk_load_1d(smem_u32(b_s + (size_t)st * BB), a.dig + (size_t)(kb / RS) * BB, (uint32_t)BB, bar);
+            row = row_next;
+            if (++st == a.stages) { st = 0; eph ^= 1u; }
         }
     }
     __syncthreads();
@@ -751,7 +750,9 @@ extern "C" int gnan_aggregate_rows_fwd_ws(const uint8_t *hop, int64_t R, int64_t
                                           gnan_stream_t stream)
 {
     const bool can_tc = gnan_aggregate_rows_tc_supported(R, N, ld_hop, nbins, C) != 0;
-    if (algo == GNAN_AGG_CUDA_CORES || (algo == GNAN_AGG_AUTO && !can_tc))
+    // auto: with a single channel the CUDA-core bin sums stream the hop bytes faster (measured 1.6 TB/s vs 1.0 TB/s at the
+    // ogbn-arxiv shape); from two channels on they re-stream per channel chunk and the tensor-core pass wins
+    if (algo == GNAN_AGG_CUDA_CORES || (algo == GNAN_AGG_AUTO && (!can_tc || C < 2)))
         return gnan_aggregate_rows_fwd_save(hop, R, N, ld_hop, T, table_per_row, nbins, Cr, rscale, S, C, out, Bsum, stream);
     GNAN_REQUIRE(algo == GNAN_AGG_AUTO || algo == GNAN_AGG_TENSOR_CORES, "aggregate_rows_fwd_ws: unknown algo %d", algo);
     if (!can_tc) {

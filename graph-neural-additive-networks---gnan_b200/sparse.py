@@ -33,14 +33,39 @@ TILE = 128                  # entries per forward work item (rows per CTA tile o
 MAX_DENSITY = 0.25          # build a compressed form only if exceptions / (N*K) is below this
 
 
+class ValueSharing:
+    """Second level of sharing: entries of a feature that carry the SAME value (every `1` of a one-hot column, the few
+    distinct 1/len values of a row-normalised bag of words) are one evaluation. uq_* describe the distinct (feature, value)
+    pairs like val / grp_ptr / items describe the entries; Y_entry = Y_distinct[inv], and the backward of that gather is a
+    fixed-order segment sum over `order` / `seg_ptr` (ops.gather_rows: deterministic)."""
+    _FIELDS = ("val", "grp_ptr", "items", "inv", "order", "seg_ptr")
+
+    def __init__(self, val, grp_ptr, items, inv, order, seg_ptr, max_group):
+        self.val, self.grp_ptr, self.items, self.inv, self.order, self.seg_ptr = val, grp_ptr, items, inv, order, seg_ptr
+        self.max_group = int(max_group)
+
+    def map(self, fn):
+        return ValueSharing(*[fn(getattr(self, f)) for f in self._FIELDS], self.max_group)
+
+
 class CompressedFeatures:
     _FIELDS = ("base", "val", "grp_ptr", "ent_row", "ent_grp", "csr_ptr", "csr_eid", "items")
 
-    def __init__(self, num_rows, base, val, grp_ptr, ent_row, ent_grp, csr_ptr, csr_eid, items, max_group):
+    def __init__(self, num_rows, base, val, grp_ptr, ent_row, ent_grp, csr_ptr, csr_eid, items, max_group, shared=None):
         self.num_rows = int(num_rows)
         self.base, self.val, self.grp_ptr, self.ent_row, self.ent_grp = base, val, grp_ptr, ent_row, ent_grp
         self.csr_ptr, self.csr_eid, self.items = csr_ptr, csr_eid, items
         self.max_group = int(max_group)
+        self.shared = shared            # ValueSharing or None
+
+    def _map(self, fn):
+        return CompressedFeatures(self.num_rows, *[fn(getattr(self, f)) for f in self._FIELDS], self.max_group,
+                                  None if self.shared is None else self.shared.map(fn))
+
+    @property
+    def num_evaluations(self):
+        """shape-function evaluations per pass: distinct (feature, value) pairs when values are shared, else the entries"""
+        return self.shared.val.numel() if self.shared is not None else self.val.numel()
 
     @property
     def num_features(self):
@@ -57,22 +82,28 @@ class CompressedFeatures:
     def density(self):
         return (self.num_entries - self.num_features) / max(1, self.num_rows * self.num_features)
 
+    def _tensors(self):
+        out = [getattr(self, f) for f in self._FIELDS]
+        if self.shared is not None:
+            out += [getattr(self.shared, f) for f in ValueSharing._FIELDS]
+        return out
+
     def nbytes(self):
-        return sum(getattr(self, f).numel() * getattr(self, f).element_size() for f in self._FIELDS)
+        return sum(t.numel() * t.element_size() for t in self._tensors())
 
     def to(self, device):
-        return CompressedFeatures(self.num_rows, *[getattr(self, f).to(device, non_blocking=True) for f in self._FIELDS], self.max_group)
+        return self._map(lambda t: t.to(device, non_blocking=True))
 
     def pin_memory(self):
-        return CompressedFeatures(self.num_rows, *[getattr(self, f).pin_memory() for f in self._FIELDS], self.max_group)
+        return self._map(lambda t: t.pin_memory())
 
     def clone_tensors(self):
-        return CompressedFeatures(self.num_rows, *[getattr(self, f).clone() for f in self._FIELDS], self.max_group)
+        return self._map(lambda t: t.clone())
 
     def copy_tensors_(self, other):
         """In-place refresh from another compressed form of the SAME structure sizes (static inputs of a CUDA graph)."""
-        for f in self._FIELDS:
-            getattr(self, f).copy_(getattr(other, f), non_blocking=True)
+        for dst, src in zip(self._tensors(), other._tensors()):
+            dst.copy_(src, non_blocking=True)
         return self
 
     def to_dense(self):
@@ -83,7 +114,38 @@ class CompressedFeatures:
         return x
 
 
-def compress_features(x: Tensor, max_density: Optional[float] = MAX_DENSITY) -> Optional[CompressedFeatures]:
+MAX_SHARED_FRACTION = 0.5   # share equal values only if the distinct (feature, value) pairs are at most this fraction of the entries
+
+
+def _tiles_of(sizes, K, dev):
+    tiles = (sizes + TILE - 1) // TILE
+    n_items = int(tiles.sum().item())
+    item_grp = torch.repeat_interleave(torch.arange(K, device=dev), tiles, output_size=n_items)
+    item_tile = torch.arange(n_items, device=dev) - (torch.cumsum(tiles, 0) - tiles)[item_grp]
+    return torch.stack([item_grp, item_tile], dim=1).to(torch.int32).contiguous()
+
+
+def _share_values(val, ent_grp, K):
+    """ValueSharing of the entries (val [E], ent_grp [E]) or None when too few entries coincide."""
+    dev = val.device
+    E = val.numel()
+    key = (ent_grp.long() << 32) | (val.view(torch.int32).long() & 0xFFFFFFFF)      # sorted by feature, then by value bits
+    uq, inv = torch.unique(key, sorted=True, return_inverse=True)
+    if uq.numel() > MAX_SHARED_FRACTION * E:
+        return None
+    uq_grp = uq >> 32
+    uq_val = (uq & 0xFFFFFFFF).to(torch.int32).view(torch.float32)
+    sizes = torch.bincount(uq_grp, minlength=K)
+    grp_ptr = torch.zeros(K + 1, dtype=torch.int64, device=dev)
+    grp_ptr[1:] = torch.cumsum(sizes, 0)
+    order = torch.sort(inv, stable=True).indices
+    seg_ptr = torch.zeros(uq.numel() + 1, dtype=torch.int64, device=dev)
+    seg_ptr[1:] = torch.cumsum(torch.bincount(inv, minlength=uq.numel()), 0)
+    return ValueSharing(uq_val.contiguous(), grp_ptr, _tiles_of(sizes, K, dev), inv.contiguous(), order.contiguous(), seg_ptr,
+                        int(sizes.max().item()))
+
+
+def compress_features(x: Tensor, max_density: Optional[float] = MAX_DENSITY, share_values: bool = True) -> Optional[CompressedFeatures]:
     """x [N,K] (any device) -> CompressedFeatures on x's device, or None when more than `max_density` of the entries differ
     from their column's most frequent value (the dense kernels are the better choice then). One-off cost: a column-wise
     mode and a few sorts; synchronises."""
@@ -117,12 +179,9 @@ def compress_features(x: Tensor, max_density: Optional[float] = MAX_DENSITY) -> 
     csr_eid = eid[order].contiguous()
     csr_ptr = torch.zeros(N + 1, dtype=torch.int64, device=dev)
     csr_ptr[1:] = torch.cumsum(torch.bincount(rows, minlength=N), 0)
-    tiles = (sizes + TILE - 1) // TILE
-    n_items = int(tiles.sum().item())
-    item_grp = torch.repeat_interleave(torch.arange(K, device=dev), tiles, output_size=n_items)
-    item_tile = torch.arange(n_items, device=dev) - (torch.cumsum(tiles, 0) - tiles)[item_grp]
-    items = torch.stack([item_grp, item_tile], dim=1).to(torch.int32).contiguous()
-    return CompressedFeatures(N, base, val, grp_ptr, ent_row, ent_grp, csr_ptr, csr_eid, items, int(sizes.max().item()))
+    items = _tiles_of(sizes, K, dev)
+    shared = _share_values(val, ent_grp, K) if share_values else None
+    return CompressedFeatures(N, base, val, grp_ptr, ent_row, ent_grp, csr_ptr, csr_eid, items, int(sizes.max().item()), shared)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -240,5 +299,10 @@ def feature_sums(cx: CompressedFeatures, w1, b1, wh, bh, wo, bo, n_layers, preci
     if wo.shape[0] != cx.num_features:
         raise ValueError(f"compressed x has {cx.num_features} features, the model {wo.shape[0]}")
     from ._lib import PRECISIONS
-    Y = mlp_entries_fwd(cx.val, cx.grp_ptr, cx.items, w1, b1, wh, bh, wo, bo, int(n_layers), cx.max_group, PRECISIONS[precision])
+    sh = cx.shared
+    if sh is not None:      # one evaluation per distinct (feature, value); entries gather it (backward: fixed-order segment sums)
+        Yq = mlp_entries_fwd(sh.val, sh.grp_ptr, sh.items, w1, b1, wh, bh, wo, bo, int(n_layers), sh.max_group, PRECISIONS[precision])
+        Y = ops.gather_rows(Yq, sh.inv, sh.order, sh.seg_ptr)
+    else:
+        Y = mlp_entries_fwd(cx.val, cx.grp_ptr, cx.items, w1, b1, wh, bh, wo, bo, int(n_layers), cx.max_group, PRECISIONS[precision])
     return entries_to_rows(Y, cx.grp_ptr, cx.csr_ptr, cx.csr_eid, cx.ent_grp, cx.ent_row)

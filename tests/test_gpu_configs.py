@@ -55,14 +55,26 @@ def collect_grads(model):
     return out
 
 
-def compare(tag, got_out, got_grads, want_out, want_grads, tol):
+# ReLU kinks at scale. A hidden pre-activation within rounding noise of 0 flips its ReLU mask between two CORRECT
+# implementations (the reference on another BLAS would do the same), and one flipped mask moves the gradient of everything
+# upstream of that ReLU by a whole term: measured 8e-5 .. 1.3e-4 on fs.wh / fs.w1 from one or two flips among the 6.3e7
+# pre-activations of the dense PubMed-shaped pass in the 3xTF32 mode (z noise ~5e-7 relative; tests/tools/
+# debug_mlp_bwd_shapes.py; the fp32 kernels, noise 6e-8, showed none in the same runs). Outputs, the output layer and rho are
+# not affected. The dense 3xTF32 passes therefore hold the parameters upstream of a shape-function ReLU to KINK_TOL.
+KINK_TOL = 5e-4
+UPSTREAM_OF_RELU = ("fs.w1", "fs.b1", "fs.wh", "fs.bh")
+
+
+def compare(tag, got_out, got_grads, want_out, want_grads, tol, kink_tol=None):
     errs = {"out": G.rel_err(got_out, want_out)}
     for k, w in want_grads.items():
         if k in got_grads and w.numel() and float(w.norm()) > 0:
             errs[k] = G.rel_err(got_grads[k].numpy(), w.numpy())
     worst = max(errs, key=errs.get)
     print(f"[config parity] {tag}: worst {worst} = {errs[worst]:.2e}   out = {errs['out']:.2e}")
-    assert errs[worst] < tol, (tag, errs)
+    for k, e in errs.items():
+        bound = kink_tol if (kink_tol is not None and k in UPSTREAM_OF_RELU) else tol
+        assert e < bound, (tag, k, e, errs)
 
 
 def want_grads_of(fs, rho):
@@ -101,7 +113,7 @@ def node_case(name, rows):
     want = (W * S.unsqueeze(0)).sum(dim=1)
     loss = torch.nn.functional.cross_entropy(want[idx], y, reduction="sum") / float(idx.numel())
     loss.backward()
-    return SimpleNamespace(wl=wl, model=model, hd=hd, idx=idx, y=y, want=want.detach().numpy(), loss=float(loss), grads=want_grads_of(fs, rho))
+    return SimpleNamespace(wl=wl, model=model, hd=hd, idx=idx, y=y, want=want.detach().numpy(), loss=float(loss.detach()), grads=want_grads_of(fs, rho))
 
 
 @pytest.fixture(scope="module")
@@ -143,10 +155,11 @@ def test_cora_shaped_step_vs_float64_oracle(cora_case, dedup, precision, algo):
 
 
 @pytest.mark.parametrize("dedup,precision,algo", [(True, "fp32", "auto"), (True, "tf32x3", "auto"), (False, "tf32x3", "auto"),
-                                                  (True, "fp32", "cuda")])
+                                                  (False, "fp32", "auto"), (True, "fp32", "cuda")])
 def test_pubmed_shaped_row_block_vs_float64_oracle(pubmed_case, dedup, precision, algo):
     out, grads = run_node(pubmed_case, dedup, precision, algo)
-    compare(f"pubmed[512 rows] dedup={dedup} {precision} agg={algo}", out, grads, pubmed_case.want, pubmed_case.grads, TOL[precision])
+    compare(f"pubmed[512 rows] dedup={dedup} {precision} agg={algo}", out, grads, pubmed_case.want, pubmed_case.grads, TOL[precision],
+            kink_tol=KINK_TOL if (precision == "tf32x3" and not dedup) else None)
 
 
 # ---- graph task ----------------------------------------------------------------------------------------------------------
@@ -181,7 +194,7 @@ def mutag_case():
             nd, nm = (torch.from_numpy(t).double() for t in oapsp.reference_format(hop, oapsp.level_counts(hop)))
             ref = gnan_port.tensor_gnan_models(fs, rho, wl.x[b:e].double(), nd, nm, True, True, None)
             assert abs(float(ref.flatten()[0]) - float(want[g, 0])) < 1e-9 * max(1.0, abs(float(want[g, 0])))
-    return SimpleNamespace(wl=wl, model=model, pk=pk, want=want.detach().numpy(), loss=float(loss), grads=want_grads_of(fs, rho))
+    return SimpleNamespace(wl=wl, model=model, pk=pk, want=want.detach().numpy(), loss=float(loss.detach()), grads=want_grads_of(fs, rho))
 
 
 @pytest.mark.parametrize("dedup,precision", [(True, "fp32"), (True, "tf32x3"), (False, "fp32"), (False, "tf32x3")])

@@ -217,3 +217,30 @@ def test_feature_compression_policy():
     assert _inputs.compressed_of(pk, big, "cpu") is not None
     explicit = compress_features(small, max_density=None)
     assert _inputs.compressed_of(SimpleNamespace(x=None, x_compressed=explicit), None, "cpu") is explicit
+
+
+def test_value_sharing_of_compressed_features_cpu():
+    """gnan_b200.sparse: entries of a feature with equal values collapse to one evaluation (one-hot columns, row-normalised
+    bags of words); the mapping reproduces the entries exactly and is skipped when nothing coincides."""
+    from gnan_b200.sparse import compress_features
+    g = torch.Generator().manual_seed(0)
+    n = 500
+    onehot = torch.zeros(n, 6)
+    onehot[torch.arange(n), torch.randint(0, 5, (n,), generator=g)] = 1.0
+    onehot[:, 5] = 1.0
+    cx = compress_features(onehot)
+    assert torch.equal(cx.to_dense(), onehot)
+    assert cx.shared is not None and cx.num_evaluations == 5 * 2 + 1 and cx.num_entries == n + 6
+    sh = cx.shared
+    assert torch.equal(sh.val[sh.inv], cx.val)
+    grp_of = torch.repeat_interleave(torch.arange(6), sh.grp_ptr[1:] - sh.grp_ptr[:-1])
+    assert torch.equal(grp_of[sh.inv].int(), cx.ent_grp)
+    assert torch.equal(torch.sort(sh.inv, stable=True).indices, sh.order)
+    assert int(sh.seg_ptr[-1]) == cx.num_entries and sh.seg_ptr.numel() == cx.num_evaluations + 1
+    cont = torch.rand(200, 4, generator=g) * (torch.rand(200, 4, generator=g) < 0.2)
+    c2 = compress_features(cont)
+    assert c2.shared is None and c2.num_evaluations == c2.num_entries
+    assert compress_features(onehot, share_values=False).shared is None
+    moved = cx.clone_tensors()
+    moved.copy_tensors_(cx)
+    assert torch.equal(moved.shared.inv, sh.inv) and moved.nbytes() == cx.nbytes()
