@@ -193,7 +193,7 @@ def mutag_case():
             hop = oapsp.apsp((wl.edge_index[:, sel] - b).numpy(), e - b)
             nd, nm = (torch.from_numpy(t).double() for t in oapsp.reference_format(hop, oapsp.level_counts(hop)))
             ref = gnan_port.tensor_gnan_models(fs, rho, wl.x[b:e].double(), nd, nm, True, True, None)
-            assert abs(float(ref.flatten()[0]) - float(want[g, 0])) < 1e-9 * max(1.0, abs(float(want[g, 0])))
+            assert abs(float(ref.flatten()[0]) - float(want[g, 0])) < 1e-6 * max(1.0, abs(float(want[g, 0])))      # nd, nm are fp32 (the reference format)
     return SimpleNamespace(wl=wl, model=model, pk=pk, want=want.detach().numpy(), loss=float(loss.detach()), grads=want_grads_of(fs, rho))
 
 
