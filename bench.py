@@ -755,9 +755,11 @@ def parity_vs_single_gpu(env):
     o = gdist.row_sharded_forward(m, x[b:e].contiguous(), hd, [q - p for p, q in blocks])
     (o * w[b:e]).sum().backward()
     fg.all_reduce()
-    errs = torch.tensor([rel(o, full[b:e].detach()) if e > b else 0.0, max(rel(p.grad, g) for p, g in zip(m.parameters(), g_full))], device=dev, dtype=torch.float64)
+    per = {k: rel(p.grad, g) for (k, p), g in zip(m.named_parameters(), g_full)}
+    worst = max(per, key=per.get)
+    errs = torch.tensor([rel(o, full[b:e].detach()) if e > b else 0.0, per[worst]], device=dev, dtype=torch.float64)
     dist.all_reduce(errs, op=dist.ReduceOp.MAX)
-    out["row_sharded"] = {"nodes": n, "out_rel_err": float(errs[0]), "max_param_grad_rel_err": float(errs[1])}
+    out["row_sharded"] = {"nodes": n, "out_rel_err": float(errs[0]), "max_param_grad_rel_err": float(errs[1]), "worst_param_rank0": worst}
     # (2) data-parallel graph batches vs one GPU holding the union batch
     from gnan_b200.models import TensorGNAN as GraphGNAN
     torch.manual_seed(2)

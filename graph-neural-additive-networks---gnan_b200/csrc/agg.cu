@@ -332,6 +332,65 @@ agg_blockdiag_fwd_kernel(BdArgs a, float *__restrict__ out)
     }
 }
 
+// v2 forward: one warp per graph, a lane owns ROWS i = lane, lane+32, .. and walks its own hop row (consecutive bytes of one
+// 32-byte sector: served by L1 after the first touch; the n x n block is at most 64 KB). All loads of a row are independent,
+// so many are in flight per lane, and nothing is reduced across lanes until the per-graph sum at the very end (the v1 kernel
+// paid a 5-step shuffle chain behind a dependent global load for every row). S[j,:] is a broadcast load.
+template <int CC>
+__global__ void __launch_bounds__(256)
+agg_blockdiag_fwd_rows_kernel(BdArgs a, float *__restrict__ out)
+{
+    extern __shared__ float sT[];                      // global table copy [nbins*Cr]
+    const int lane = threadIdx.x & 31;
+    if (!a.per_row) {
+        for (int t = threadIdx.x; t < a.nbins * a.Cr; t += blockDim.x) sT[t] = a.T[t];
+        __syncthreads();
+    }
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int nb1 = a.nbins - 1;
+    for (int64_t b = warp; b < a.B; b += nwarps) {
+        const int n0 = a.node_off[b], n = a.node_off[b + 1] - n0;
+        const uint8_t *hb = a.hop + a.hop_off[b];
+        for (int c0 = 0; c0 < a.C; c0 += CC) {
+            float gsum[CC];
+#pragma unroll
+            for (int cc = 0; cc < CC; ++cc) gsum[cc] = 0.f;
+            for (int i = lane; i < n; i += 32) {
+                const uint8_t *row = hb + (size_t)i * n;
+                const float *Ti = a.per_row ? a.T + (int64_t)(n0 + i) * a.nbins * a.Cr : sT;
+                const float *rsi = a.rscale ? a.rscale + (int64_t)(n0 + i) * a.nbins : nullptr;
+                float acc[CC];
+#pragma unroll
+                for (int cc = 0; cc < CC; ++cc) acc[cc] = 0.f;
+#pragma unroll 4
+                for (int j = 0; j < n; ++j) {
+                    const int d = min((int)row[j], nb1);
+                    const float r = rsi ? rsi[d] : 1.f;
+                    const float *Sj = a.S + (int64_t)(n0 + j) * a.C + c0;
+#pragma unroll
+                    for (int cc = 0; cc < CC; ++cc)
+                        if (c0 + cc < a.C) acc[cc] = fmaf(Ti[d * a.Cr + (a.Cr == 1 ? 0 : c0 + cc)] * r, Sj[cc], acc[cc]);
+                }
+#pragma unroll
+                for (int cc = 0; cc < CC; ++cc) {
+                    if (a.reduce_graph) gsum[cc] += acc[cc];
+                    else if (c0 + cc < a.C) out[(int64_t)(n0 + i) * a.C + c0 + cc] = acc[cc];
+                }
+            }
+            if (a.reduce_graph) {
+#pragma unroll
+                for (int cc = 0; cc < CC; ++cc) {
+                    float v = gsum[cc];
+#pragma unroll
+                    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+                    if (lane == 0 && c0 + cc < a.C) out[b * a.C + c0 + cc] = v;
+                }
+            }
+        }
+    }
+}
+
 // backward: dS (lane owns column j), dT via shared-memory bins (per CTA for a global table, per row otherwise)
 __global__ void __launch_bounds__(256)
 agg_blockdiag_bwd_kernel(BdArgs a, const float *__restrict__ g, float *__restrict__ dS, float *__restrict__ dT)
@@ -414,13 +473,29 @@ agg_blockdiag_bwd_global_kernel(BdArgs a, const float *__restrict__ g, float *__
             for (int j = lane; j < n; j += 32) {
                 const float sj = a.S[(int64_t)(n0 + j) * a.C + c];
                 float ds = 0.f;
-                for (int i = 0; i < n; ++i) {
-                    const int d = min((int)hb[(size_t)i * n + j], a.nbins - 1);
-                    float r = a.reduce_graph ? gb : g[(int64_t)(n0 + i) * a.C + c];
-                    if (a.rscale) r *= a.rscale[(int64_t)(n0 + i) * a.nbins + d];
-                    const int t = d * a.Cr + cr;
-                    ds = fmaf(sT[t], r, ds);
-                    acc[t * 32 + lane] = fmaf(r, sj, acc[t * 32 + lane]);
+                for (int i0 = 0; i0 < n; i0 += 8) {
+                    // 8 rows per step: their hop bytes and scale factors are all in flight before the first shared-memory
+                    // update (one dependent global load per row used to be exposed in full)
+                    int d[8];
+                    float r[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) d[u] = i0 + u < n ? min((int)hb[(size_t)(i0 + u) * n + j], a.nbins - 1) : -1;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        r[u] = 0.f;
+                        if (d[u] >= 0) {
+                            r[u] = a.reduce_graph ? gb : g[(int64_t)(n0 + i0 + u) * a.C + c];
+                            if (a.rscale) r[u] *= a.rscale[(int64_t)(n0 + i0 + u) * a.nbins + d[u]];
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        if (d[u] >= 0) {
+                            const int t = d[u] * a.Cr + cr;
+                            ds = fmaf(sT[t], r[u], ds);
+                            acc[t * 32 + lane] = fmaf(r[u], sj, acc[t * 32 + lane]);
+                        }
+                    }
                 }
                 dS[(int64_t)(n0 + j) * a.C + c] = ds;
             }
@@ -646,7 +721,14 @@ extern "C" int gnan_aggregate_blockdiag_fwd(const uint8_t *hop, const int64_t *h
     GNAN_REQUIRE(out != nullptr, "aggregate_blockdiag_fwd: NULL out");
     BdArgs a{hop, hop_off, node_off, B, T, table_per_row, nbins, Cr, rscale, S, C, reduce_graph};
     const int blocks = (int)std::min<int64_t>(ceil_div64(B, 8), 8 * gnan_sm_count());
-    agg_blockdiag_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, out);
+    const size_t smem = table_per_row ? 0 : sizeof(float) * (size_t)nbins * Cr;
+    if (smem <= 48 * 1024) {
+        if (C >= 4) agg_blockdiag_fwd_rows_kernel<4><<<blocks, 256, smem, (cudaStream_t)stream>>>(a, out);
+        else if (C >= 2) agg_blockdiag_fwd_rows_kernel<2><<<blocks, 256, smem, (cudaStream_t)stream>>>(a, out);
+        else agg_blockdiag_fwd_rows_kernel<1><<<blocks, 256, smem, (cudaStream_t)stream>>>(a, out);
+    } else {
+        agg_blockdiag_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(a, out);
+    }
     GNAN_LAUNCH_OK();
     return GNAN_OK;
 }

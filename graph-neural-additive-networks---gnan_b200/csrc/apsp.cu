@@ -106,6 +106,139 @@ apsp_batched_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restric
     }
 }
 
+// ---- batched small graphs, v2: one warp per graph, bit-parallel over SOURCES, hop block assembled in shared memory -------
+// A lane owns vertices v = lane, lane+32, .. and keeps, per vertex, the bitmask of sources that reach it (W = ceil(n/32)
+// words). Level L is a pull over v's out-neighbours u: new[v] = (OR_u frontier[u]) & ~visited[v]; a new bit s means
+// dist(v -> s) = L, i.e. hop[v][s] = L, and popc(new[v]) is row v's level-L count (no atomics). The n x n hop block lives in
+// shared memory (byte stores there), padded so that it is congruent to its global address mod 16, and leaves as 16-byte
+// vector stores: the global hop bytes are written exactly once, unreachable pairs included (no memset).
+constexpr int BV2_W = 4;   // up to 128 nodes per graph
+
+__global__ void __launch_bounds__(256)
+apsp_batched_v2_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, const int32_t *__restrict__ node_off,
+                       const int64_t *__restrict__ hop_off, int B, int max_n, int warps_per_cta, uint8_t *__restrict__ hop,
+                       int32_t *__restrict__ cnt, int nbins, int32_t *__restrict__ overflow, int32_t *__restrict__ max_level)
+{
+    extern __shared__ __align__(16) uint8_t sm2[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (w >= warps_per_cta) return;
+    const int Wmax = (max_n + 31) / 32;
+    const size_t hop_bytes = ((size_t)max_n * max_n + 16 + 15) / 16 * 16;
+    uint8_t *wbase = sm2 + (size_t)w * (hop_bytes + (size_t)2 * max_n * Wmax * 4);
+    uint32_t *frs = reinterpret_cast<uint32_t *>(wbase + hop_bytes);          // [2][n][W]
+    const int64_t warp = (int64_t)blockIdx.x * warps_per_cta + w;
+    const int64_t nwarps = (int64_t)gridDim.x * warps_per_cta;
+    int lvl_max = 0;
+    for (int64_t b = warp; b < B; b += nwarps) {
+        const int n0 = node_off[b], n = node_off[b + 1] - n0;
+        const int W = (n + 31) / 32;
+        uint8_t *gb = hop + hop_off[b];
+        const int pad = (int)(reinterpret_cast<uintptr_t>(gb) & 15);
+        uint8_t *hb = wbase + pad;                                             // hb + k  ==  gb + k  (mod 16)
+        const int total = n * n;
+        __syncwarp();
+        for (int t = lane * 16; t < total + 16; t += 512)
+            *reinterpret_cast<uint4 *>(wbase + t) = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        uint32_t vis[BV2_W][BV2_W];
+        int e0[BV2_W], e1[BV2_W];
+#pragma unroll
+        for (int k = 0; k < BV2_W; ++k) {
+            const int v = lane + 32 * k;
+            e0[k] = e1[k] = 0;
+#pragma unroll
+            for (int ww = 0; ww < BV2_W; ++ww) vis[k][ww] = 0u;
+            if (v < n) {
+                e0[k] = rowptr[n0 + v];
+                e1[k] = rowptr[n0 + v + 1];
+#pragma unroll
+                for (int ww = 0; ww < BV2_W; ++ww) {
+                    if (ww == k) vis[k][ww] = 1u << lane;
+                    if (ww < W) frs[v * W + ww] = ww == k ? 1u << lane : 0u;
+                }
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < BV2_W; ++k) {
+            const int v = lane + 32 * k;
+            if (v < n) {
+                hb[v * n + v] = 0;
+                if (cnt) cnt[(int64_t)(n0 + v) * nbins] = 1;
+            }
+        }
+        for (int level = 1; level <= n; ++level) {
+            const uint32_t *fc = frs + ((level - 1) & 1) * n * W;
+            uint32_t *fn = frs + (level & 1) * n * W;
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < BV2_W; ++k) {
+                const int v = lane + 32 * k;
+                if (v < n) {
+                    uint32_t acc[BV2_W];
+#pragma unroll
+                    for (int ww = 0; ww < BV2_W; ++ww) acc[ww] = 0u;
+                    for (int e = e0[k]; e < e1[k]; ++e) {
+                        const int u = __ldg(col + e) - n0;
+                        if (u >= 0 && u < n) {
+#pragma unroll
+                            for (int ww = 0; ww < BV2_W; ++ww)
+                                if (ww < W) acc[ww] |= fc[u * W + ww];
+                        }
+                    }
+                    int newc = 0;
+#pragma unroll
+                    for (int ww = 0; ww < BV2_W; ++ww) {
+                        const uint32_t nw = acc[ww] & ~vis[k][ww];
+                        vis[k][ww] |= nw;
+                        if (ww < W) fn[v * W + ww] = nw;
+                        newc += __popc(nw);
+                        uint32_t m = nw;
+                        const uint8_t lv = (uint8_t)min(level, 254);
+                        while (m) {
+                            hb[v * n + ww * 32 + __ffs(m) - 1] = lv;
+                            m &= m - 1;
+                        }
+                    }
+                    if (newc) {
+                        any = true;
+                        if (level > 254 || level >= nbins - 1) atomicExch(overflow, 1);
+                        else if (cnt) cnt[(int64_t)(n0 + v) * nbins + level] = newc;
+                    }
+                }
+            }
+            __syncwarp();
+            if (!__any_sync(0xffffffffu, any)) break;
+            lvl_max = max(lvl_max, level);
+        }
+        if (cnt) {
+#pragma unroll
+            for (int k = 0; k < BV2_W; ++k) {
+                const int v = lane + 32 * k;
+                if (v < n) {
+                    int reached = 0;
+#pragma unroll
+                    for (int ww = 0; ww < BV2_W; ++ww) reached += __popc(vis[k][ww]);
+                    cnt[(int64_t)(n0 + v) * nbins + nbins - 1] = n - reached;
+                }
+            }
+        }
+        __syncwarp();
+        // copy out: head bytes up to the first 16-byte boundary, vector body, tail bytes
+        const int head = min(total, (16 - pad) & 15);
+        if (lane < head) gb[lane] = hb[lane];
+        const int body = (total - head) / 16;
+        for (int t = lane; t < body; t += 32)
+            *reinterpret_cast<uint4 *>(gb + head + t * 16) = *reinterpret_cast<const uint4 *>(hb + head + t * 16);
+        const int tail0 = head + body * 16;
+        if (tail0 + lane < total) gb[tail0 + lane] = hb[tail0 + lane];
+    }
+    if (max_level) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lvl_max = max(lvl_max, __shfl_xor_sync(0xffffffffu, lvl_max, o));
+        if (lane == 0 && lvl_max > 0) atomicMax(max_level, lvl_max);
+    }
+}
+
 // ---- one large graph: one warp per source, queue + bitmap in the workspace -----------------------------------------
 __global__ void __launch_bounds__(256)
 apsp_bfs_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, int N, int src_begin, int src_end,
@@ -413,17 +546,33 @@ extern "C" int gnan_apsp_bfs_batched_n(const int32_t *rowptr, const int32_t *col
         gnan_set_error("apsp_bfs_batched: graphs with %d nodes unsupported (1..%d); use gnan_apsp_bfs", max_n, 32 * BW_MAX);
         return GNAN_ERR_UNSUPPORTED;
     }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (max_n <= 32 * BV2_W && total_nodes > 0) {
+        // v2: hop blocks assembled in shared memory and written once (no memset of hop); only the level table is zero-filled
+        const int Wmax = (max_n + 31) / 32;
+        const size_t per_warp = ((size_t)max_n * max_n + 16 + 15) / 16 * 16 + (size_t)2 * max_n * Wmax * 4;
+        int wpc = (int)std::min<size_t>(8, (100 * 1024) / per_warp);          // >= 2 CTAs per SM
+        if (wpc < 1) wpc = 1;
+        const size_t smem = per_warp * wpc;
+        GNAN_CUDA(cudaFuncSetAttribute(apsp_batched_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (cnt) GNAN_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (size_t)total_nodes * nbins, st));
+        const int blocks = (int)std::min<int64_t>(ceil_div64(B, wpc), 16 * gnan_sm_count());
+        apsp_batched_v2_kernel<<<blocks, 32 * wpc, smem, st>>>(rowptr, col, node_off, hop_off, B, max_n, wpc, hop, cnt, cnt ? nbins : 256,
+                                                              overflow_flag, max_level);
+        GNAN_LAUNCH_OK();
+        return GNAN_OK;
+    }
     const size_t smem = sizeof(uint32_t) * 8 * (size_t)max_n * ((max_n + 31) / 32);
     GNAN_CUDA(cudaFuncSetAttribute(apsp_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int blocks = (int)std::min<int64_t>(ceil_div64(B, 8), 16 * gnan_sm_count());
     // with the totals known on the host the 255 / 0 background is two memsets at HBM speed instead of per-lane store loops
     const int prefilled = total_nodes > 0 && total_hop_bytes > 0;
     if (prefilled) {
-        GNAN_CUDA(cudaMemsetAsync(hop, GNAN_HOP_UNREACHABLE, (size_t)total_hop_bytes, (cudaStream_t)stream));
-        if (cnt) GNAN_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (size_t)total_nodes * nbins, (cudaStream_t)stream));
+        GNAN_CUDA(cudaMemsetAsync(hop, GNAN_HOP_UNREACHABLE, (size_t)total_hop_bytes, st));
+        if (cnt) GNAN_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (size_t)total_nodes * nbins, st));
     }
-    apsp_batched_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(rowptr, col, node_off, hop_off, B, max_n, hop, cnt,
-                                                                     cnt ? nbins : 256, overflow_flag, prefilled, max_level);
+    apsp_batched_kernel<<<blocks, 256, smem, st>>>(rowptr, col, node_off, hop_off, B, max_n, hop, cnt,
+                                                   cnt ? nbins : 256, overflow_flag, prefilled, max_level);
     GNAN_LAUNCH_OK();
     return GNAN_OK;
 }

@@ -223,13 +223,15 @@ class PackedBatch:
                            self.max_nodes)
 
 
-def apsp_batched(edge_index, node_off, device="cuda", x=None, y=None, node_off_device=None):
+def apsp_batched(edge_index, node_off, device="cuda", x=None, y=None, node_off_device=None, _level_table_width=48):
     """Hop blocks of B small graphs (<= 256 nodes each) in one launch. edge_index uses GLOBAL node ids of the
     concatenated node set; node_off [B+1] are the graph boundaries.
 
     Pass node_off as a HOST tensor / array (what a data loader has): block sizes and offsets are then computed on the host
     and the call synchronises exactly once, at the end (overflow flag + largest hop, which sizes the level table).
-    node_off_device: optional int32 device copy of node_off (skips its upload)."""
+    node_off_device: optional int32 device copy of node_off (skips its upload).
+    The level table is first allocated 48 columns wide (hop distances inside small graphs rarely exceed that: the table is
+    sumN x width int32, zero-filled); a deeper batch is detected by the kernel and redone once with max_n + 1 columns."""
     import numpy as np
     lib = load()
     if torch.is_tensor(node_off) and node_off.is_cuda:
@@ -251,7 +253,8 @@ def apsp_batched(edge_index, node_off, device="cuda", x=None, y=None, node_off_d
     st = torch.zeros(3, dtype=torch.int32, device=device)              # [csr status, overflow, largest finite hop]
     rowptr, col, _ = build_csr(edge_index, sumN, device, status=st[0:1])
     hop = torch.empty(max(total, 1), dtype=torch.uint8, device=device)
-    nb = min(256, max_n + 1)                     # a finite hop inside a graph is at most max_n - 1; last column = unreachable
+    nb_full = min(256, max_n + 1)                # a finite hop inside a graph is at most max_n - 1; last column = unreachable
+    nb = min(nb_full, _level_table_width) if _level_table_width else nb_full
     cnt = torch.empty(sumN, nb, dtype=torch.int32, device=device)
     with _timed("apsp_bfs_batched"):
         check(lib.gnan_apsp_bfs_batched_n(ptr(rowptr), ptr(col), ptr(node_off_d), ptr(hop_off), B, max_n, sumN, total, ptr(hop), ptr(cnt), nb,
@@ -260,6 +263,8 @@ def apsp_batched(edge_index, node_off, device="cuda", x=None, y=None, node_off_d
     _check_status(status)
     if status & 2:
         return _apsp_batched_multi_edges(edge_index, no_h, device, x, y)
+    if over and nb < nb_full:                    # deeper than the narrow level table: once more with the full width
+        return apsp_batched(edge_index, node_off, device, x, y, node_off_device, _level_table_width=0)
     if over:
         raise NotImplementedError("a hop distance > 254 does not fit the uint8 hop matrix")
     if sumN == 0:

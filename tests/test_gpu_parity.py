@@ -247,6 +247,34 @@ def test_duplicate_edges_follow_the_reference_weighted_dijkstra(batched):
             assert np.array_equal(got, want_of(eis[i], n)), i
 
 
+@pytest.mark.parametrize("directed", [False, True])
+def test_apsp_batched_small_graph_kernel_vs_oracle(directed):
+    """graphs of <= 128 nodes take the bit-parallel-over-sources kernel (hop block assembled in shared memory, written once);
+    includes a path deeper than the narrow first-try level table (redo with the full width) and ragged block alignments."""
+    from gnan_b200.preprocess import apsp_batched
+    rng = np.random.default_rng(17)
+    sizes = [1, 2, 5, 31, 32, 33, 64, 100, 17, 128, 3, 70, 9]
+    node_off = np.concatenate([[0], np.cumsum(sizes)])
+    eis = [random_graph(rng, n, 2.2, directed, n_isolated=1 if n > 4 else 0) for n in sizes]
+    for deep in (False, True):
+        if deep:                                            # graph 6 (64 nodes) becomes a path: hop distances up to 63
+            eis[6] = np.stack([np.arange(63), np.arange(1, 64)]) if directed else np.concatenate(
+                [np.stack([np.arange(63), np.arange(1, 64)]), np.stack([np.arange(1, 64), np.arange(63)])], axis=1)
+        ei = np.concatenate([e + node_off[i] for i, e in enumerate(eis)], axis=1)
+        pk = apsp_batched(torch.tensor(ei), node_off, device=DEV)
+        hop, cnt, ho = pk.hop.cpu().numpy(), pk.level_counts.cpu().numpy(), pk.hop_off.cpu().numpy()
+        assert not deep or cnt.shape[1] == 65
+        for i, n in enumerate(sizes):
+            want = oapsp.apsp(eis[i], n)
+            got = hop[ho[i]:ho[i + 1]].reshape(n, n).astype(np.int32)
+            got[got == 255] = -1
+            assert np.array_equal(got, want), (i, deep)
+            wc = oapsp.level_counts(want)
+            full = np.zeros((n, cnt.shape[1]), dtype=np.int32)
+            full[:, :wc.shape[1] - 1] = wc[:, :-1]; full[:, -1] = wc[:, -1]
+            assert np.array_equal(cnt[node_off[i]:node_off[i + 1]], full), (i, deep)
+
+
 def test_apsp_batched_vs_oracle():
     from gnan_b200.preprocess import apsp_batched
     rng = np.random.default_rng(5)
