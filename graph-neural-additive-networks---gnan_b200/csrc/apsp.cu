@@ -124,7 +124,8 @@ apsp_batched_v2_kernel(const int32_t *__restrict__ rowptr, const int32_t *__rest
     if (w >= warps_per_cta) return;
     const int Wmax = (max_n + 31) / 32;
     const size_t hop_bytes = ((size_t)max_n * max_n + 16 + 15) / 16 * 16;
-    uint8_t *wbase = sm2 + (size_t)w * (hop_bytes + (size_t)2 * max_n * Wmax * 4);
+    const size_t fr_bytes = ((size_t)2 * max_n * Wmax * 4 + 15) / 16 * 16;    // keeps every warp's slice 16-byte aligned
+    uint8_t *wbase = sm2 + (size_t)w * (hop_bytes + fr_bytes);
     uint32_t *frs = reinterpret_cast<uint32_t *>(wbase + hop_bytes);          // [2][n][W]
     const int64_t warp = (int64_t)blockIdx.x * warps_per_cta + w;
     const int64_t nwarps = (int64_t)gridDim.x * warps_per_cta;
@@ -550,7 +551,7 @@ extern "C" int gnan_apsp_bfs_batched_n(const int32_t *rowptr, const int32_t *col
     if (max_n <= 32 * BV2_W && total_nodes > 0) {
         // v2: hop blocks assembled in shared memory and written once (no memset of hop); only the level table is zero-filled
         const int Wmax = (max_n + 31) / 32;
-        const size_t per_warp = ((size_t)max_n * max_n + 16 + 15) / 16 * 16 + (size_t)2 * max_n * Wmax * 4;
+        const size_t per_warp = ((size_t)max_n * max_n + 16 + 15) / 16 * 16 + ((size_t)2 * max_n * Wmax * 4 + 15) / 16 * 16;
         int wpc = (int)std::min<size_t>(8, (100 * 1024) / per_warp);          // >= 2 CTAs per SM
         if (wpc < 1) wpc = 1;
         const size_t smem = per_warp * wpc;

@@ -275,6 +275,24 @@ def test_apsp_batched_small_graph_kernel_vs_oracle(directed):
             assert np.array_equal(cnt[node_off[i]:node_off[i + 1]], full), (i, deep)
 
 
+@pytest.mark.parametrize("max_n", [31, 95, 27])
+def test_apsp_batched_odd_maximum_sizes(max_n):
+    """odd max_n with an odd number of source words (31 -> 1 word, 95 -> 3 words): the per-warp shared-memory slices of the
+    small-graph kernel must stay 16-byte aligned (a Mutagenicity-shaped batch whose largest graph had 95 nodes faulted)."""
+    from gnan_b200.preprocess import apsp_batched
+    rng = np.random.default_rng(max_n)
+    sizes = [max_n] + [int(v) for v in rng.integers(1, max_n + 1, size=40)]
+    node_off = np.concatenate([[0], np.cumsum(sizes)])
+    eis = [random_graph(rng, n, 2.2, False, n_isolated=1 if n > 4 else 0) for n in sizes]
+    ei = np.concatenate([e + node_off[i] for i, e in enumerate(eis)], axis=1)
+    pk = apsp_batched(torch.tensor(ei), node_off, device=DEV)
+    hop, ho = pk.hop.cpu().numpy(), pk.hop_off.cpu().numpy()
+    for i, n in enumerate(sizes):
+        got = hop[ho[i]:ho[i + 1]].reshape(n, n).astype(np.int32)
+        got[got == 255] = -1
+        assert np.array_equal(got, oapsp.apsp(eis[i], n)), i
+
+
 def test_apsp_batched_vs_oracle():
     from gnan_b200.preprocess import apsp_batched
     rng = np.random.default_rng(5)
