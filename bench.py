@@ -42,6 +42,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 H, L = 64, 3   # run.sh:10-11
+MOL_NBINS = 48 # fixed level-table width of the in-step BFS of the molecule workload (47 hop levels + the unreachable bin)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -459,16 +460,18 @@ def run_workload(args, env, name, *, steps, warmup, classes=0, compare_legs=Fals
         x_bytes = host.x.numel() * 4 if cx is None else cx.nbytes()
         h2d = x_bytes + sum(t.numel() * t.element_size() for t in (host.hop, host.hop_off, host.node_off, host.level_counts, host.y))
         if in_step_apsp:                                                # the step starts from the raw edge list
-            ei_d, noff_d, x_d, y_d = wl.edge_index.to(dev), pk.node_off, wl.x.to(dev), wl.y.to(dev)
-            ei_h, noff_h = wl.edge_index.pin_memory(), pk.node_off.cpu().pin_memory()
-            data_d = (ei_d, noff_d, x_d, y_d, cx)
-            h2d = x_bytes + sum(t.numel() * t.element_size() for t in (ei_h, noff_h, host.y))
+            ei_d, noff_d, hoff_d, x_d, y_d = wl.edge_index.to(dev), pk.node_off, pk.hop_off, wl.x.to(dev), wl.y.to(dev)
+            ei_h, noff_h, hoff_h = wl.edge_index.pin_memory(), pk.node_off.cpu().pin_memory(), pk.hop_off.cpu().pin_memory()
+            data_d = (ei_d, noff_d, hoff_d, x_d, y_d, cx)
+            h2d = x_bytes + sum(t.numel() * t.element_size() for t in (ei_h, noff_h, hoff_h, host.y))
+            apsp_status = []
 
         def load_host():
             c = None if cx is None else cx_h.to(dev)
             xx = host.x.to(dev, non_blocking=True) if cx is None else None
             if in_step_apsp:
-                return (ei_h.to(dev, non_blocking=True), noff_h.to(dev, non_blocking=True), xx, host.y.to(dev, non_blocking=True), c)
+                return (ei_h.to(dev, non_blocking=True), noff_h.to(dev, non_blocking=True), hoff_h.to(dev, non_blocking=True), xx,
+                        host.y.to(dev, non_blocking=True), c)
             b = PackedBatch(xx, host.hop.to(dev, non_blocking=True), host.hop_off.to(dev, non_blocking=True),
                             host.node_off.to(dev, non_blocking=True), host.level_counts.to(dev, non_blocking=True),
                             host.y.to(dev, non_blocking=True), host.max_nodes)
@@ -477,9 +480,12 @@ def run_workload(args, env, name, *, steps, warmup, classes=0, compare_legs=Fals
 
         def loss_of(data):
             if in_step_apsp:                                            # GPU BFS of the batch (pre_process_datasets.py:106-122); the graph
-                e, no, xx, yy, c = data                                 # boundaries are host metadata of the loader, like the batch size
-                data = apsp_batched(e, node_off_h, device=dev, x=xx, y=yy, node_off_device=no)
+                e, no, ho, xx, yy, c = data                             # boundaries are host metadata of the loader, like the batch size
+                # fixed-width level table (48 levels; deeper batches raise the overflow flag, checked after the timed loop):
+                # no host synchronisation inside the step, so CSR build + BFS + model step replay as ONE CUDA graph
+                data = apsp_batched(e, node_off_h, device=dev, x=xx, y=yy, node_off_device=no, hop_off_device=ho, nbins=MOL_NBINS)
                 data.x_compressed = c
+                apsp_status[:] = [data.status]
             return loss_fn(model(data).flatten(), data.y)               # model(data): [B,1]
         after_bwd = (lambda: fg.all_reduce(average=True)) if world > 1 else None
         rows_local = wl.n
@@ -500,8 +506,7 @@ def run_workload(args, env, name, *, steps, warmup, classes=0, compare_legs=Fals
 
     # ---- capture the whole step (forward + loss + backward [+ collectives] + Adam) into one CUDA graph ----------------------
     graphed, launches_per_step = None, None
-    capturable = wl.kind == "node" or not in_step_apsp          # the in-step BFS sizes its level table from a device value
-    if not args.no_cuda_graph and capturable:
+    if not args.no_cuda_graph:
         try:
             scx = None if cx is None else cx.to(dev).clone_tensors()
             if wl.kind == "node":
@@ -509,6 +514,8 @@ def run_workload(args, env, name, *, steps, warmup, classes=0, compare_legs=Fals
                 static_hop = HopData(hop_static, data_d.hop_data.level_counts.clone(), wl.n, b0)
                 static_hop.static_level_counts = True          # the level counts are refreshed with the same values only (see trainer.CapturedStep)
                 static_in = SimpleNamespace(x=None if cx is not None else data_d.x.clone(), hop_data=static_hop, x_compressed=scx)
+            elif in_step_apsp:
+                static_in = (ei_d.clone(), noff_d.clone(), hoff_d.clone(), None if cx is not None else x_d.clone(), y_d.clone(), scx)
             else:
                 static_in = PackedBatch(None if cx is not None else data_d.x.clone(), data_d.hop.clone(), data_d.hop_off.clone(),
                                         data_d.node_off.clone(), data_d.level_counts.clone(), data_d.y.clone(), data_d.max_nodes)
@@ -528,7 +535,13 @@ def run_workload(args, env, name, *, steps, warmup, classes=0, compare_legs=Fals
         if graphed is None:
             return step(data)
         cap, sin = graphed
-        if data is not sin:                                         # e2e leg: refresh the static inputs from the fresh copies
+        if data is not sin and in_step_apsp:                        # e2e leg: refresh the static inputs from the fresh copies
+            for dst, src in zip(sin[:5], data[:5]):
+                if dst is not None:
+                    dst.copy_(src, non_blocking=True)
+            if sin[5] is not None:
+                sin[5].copy_tensors_(data[5])
+        elif data is not sin:
             if sin.x is not None:
                 sin.x.copy_(data.x, non_blocking=True)
             else:

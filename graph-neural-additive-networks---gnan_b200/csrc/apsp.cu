@@ -111,8 +111,12 @@ apsp_batched_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restric
 // words). Level L is a pull over v's out-neighbours u: new[v] = (OR_u frontier[u]) & ~visited[v]; a new bit s means
 // dist(v -> s) = L, i.e. hop[v][s] = L, and popc(new[v]) is row v's level-L count (no atomics). The n x n hop block lives in
 // shared memory (byte stores there), padded so that it is congruent to its global address mod 16, and leaves as 16-byte
-// vector stores: the global hop bytes are written exactly once, unreachable pairs included (no memset).
+// vector stores: the global hop bytes are written exactly once, unreachable pairs included (no memset). The level counts
+// (<= 127 per entry) are collected in a uint8 [n][nbins] shared-memory table and leave as one coalesced int32 block per
+// graph, zeros included: no memset of the level table and no scattered 4-byte global stores per (vertex, level), which
+// cost a 32-byte sector each and dominated the kernel.
 constexpr int BV2_W = 4;   // up to 128 nodes per graph
+__host__ __device__ inline size_t bv2_round16(size_t x) { return (x + 15) / 16 * 16; }
 
 __global__ void __launch_bounds__(256)
 apsp_batched_v2_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, const int32_t *__restrict__ node_off,
@@ -123,10 +127,12 @@ apsp_batched_v2_kernel(const int32_t *__restrict__ rowptr, const int32_t *__rest
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     if (w >= warps_per_cta) return;
     const int Wmax = (max_n + 31) / 32;
-    const size_t hop_bytes = ((size_t)max_n * max_n + 16 + 15) / 16 * 16;
-    const size_t fr_bytes = ((size_t)2 * max_n * Wmax * 4 + 15) / 16 * 16;    // keeps every warp's slice 16-byte aligned
-    uint8_t *wbase = sm2 + (size_t)w * (hop_bytes + fr_bytes);
+    const size_t hop_bytes = bv2_round16((size_t)max_n * max_n + 16);
+    const size_t fr_bytes = bv2_round16((size_t)2 * max_n * Wmax * 4);        // keeps every warp's slice 16-byte aligned
+    const size_t cnt_bytes = cnt ? bv2_round16((size_t)max_n * nbins) : 0;
+    uint8_t *wbase = sm2 + (size_t)w * (hop_bytes + fr_bytes + cnt_bytes);
     uint32_t *frs = reinterpret_cast<uint32_t *>(wbase + hop_bytes);          // [2][n][W]
+    uint8_t *cs = wbase + hop_bytes + fr_bytes;                               // [n][nbins] level counts
     const int64_t warp = (int64_t)blockIdx.x * warps_per_cta + w;
     const int64_t nwarps = (int64_t)gridDim.x * warps_per_cta;
     int lvl_max = 0;
@@ -140,6 +146,8 @@ apsp_batched_v2_kernel(const int32_t *__restrict__ rowptr, const int32_t *__rest
         __syncwarp();
         for (int t = lane * 16; t < total + 16; t += 512)
             *reinterpret_cast<uint4 *>(wbase + t) = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+        if (cnt)
+            for (int t = lane * 16; t < n * nbins; t += 512) *reinterpret_cast<uint4 *>(cs + t) = make_uint4(0u, 0u, 0u, 0u);
         uint32_t vis[BV2_W][BV2_W];
         int e0[BV2_W], e1[BV2_W];
 #pragma unroll
@@ -164,7 +172,7 @@ apsp_batched_v2_kernel(const int32_t *__restrict__ rowptr, const int32_t *__rest
             const int v = lane + 32 * k;
             if (v < n) {
                 hb[v * n + v] = 0;
-                if (cnt) cnt[(int64_t)(n0 + v) * nbins] = 1;
+                if (cnt) cs[v * nbins] = 1;
             }
         }
         for (int level = 1; level <= n; ++level) {
@@ -203,7 +211,7 @@ apsp_batched_v2_kernel(const int32_t *__restrict__ rowptr, const int32_t *__rest
                     if (newc) {
                         any = true;
                         if (level > 254 || level >= nbins - 1) atomicExch(overflow, 1);
-                        else if (cnt) cnt[(int64_t)(n0 + v) * nbins + level] = newc;
+                        else if (cnt) cs[v * nbins + level] = (uint8_t)newc;
                     }
                 }
             }
@@ -219,9 +227,12 @@ apsp_batched_v2_kernel(const int32_t *__restrict__ rowptr, const int32_t *__rest
                     int reached = 0;
 #pragma unroll
                     for (int ww = 0; ww < BV2_W; ++ww) reached += __popc(vis[k][ww]);
-                    cnt[(int64_t)(n0 + v) * nbins + nbins - 1] = n - reached;
+                    cs[v * nbins + nbins - 1] = (uint8_t)(n - reached);
                 }
             }
+            __syncwarp();
+            int32_t *gc = cnt + (int64_t)n0 * nbins;                          // the graph's [n][nbins] block is contiguous
+            for (int t = lane; t < n * nbins; t += 32) gc[t] = cs[t];
         }
         __syncwarp();
         // copy out: head bytes up to the first 16-byte boundary, vector body, tail bytes
@@ -551,12 +562,12 @@ extern "C" int gnan_apsp_bfs_batched_n(const int32_t *rowptr, const int32_t *col
     if (max_n <= 32 * BV2_W && total_nodes > 0) {
         // v2: hop blocks assembled in shared memory and written once (no memset of hop); only the level table is zero-filled
         const int Wmax = (max_n + 31) / 32;
-        const size_t per_warp = ((size_t)max_n * max_n + 16 + 15) / 16 * 16 + ((size_t)2 * max_n * Wmax * 4 + 15) / 16 * 16;
+        const size_t per_warp = bv2_round16((size_t)max_n * max_n + 16) + bv2_round16((size_t)2 * max_n * Wmax * 4) +
+                                (cnt ? bv2_round16((size_t)max_n * nbins) : 0);
         int wpc = (int)std::min<size_t>(8, (100 * 1024) / per_warp);          // >= 2 CTAs per SM
         if (wpc < 1) wpc = 1;
         const size_t smem = per_warp * wpc;
         GNAN_CUDA(cudaFuncSetAttribute(apsp_batched_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (cnt) GNAN_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (size_t)total_nodes * nbins, st));
         const int blocks = (int)std::min<int64_t>(ceil_div64(B, wpc), 16 * gnan_sm_count());
         apsp_batched_v2_kernel<<<blocks, 32 * wpc, smem, st>>>(rowptr, col, node_off, hop_off, B, max_n, wpc, hop, cnt, cnt ? nbins : 256,
                                                               overflow_flag, max_level);

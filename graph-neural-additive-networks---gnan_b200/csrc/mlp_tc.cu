@@ -29,20 +29,31 @@ constexpr int FWD_ROW_THREADS = FWD_GROUPS * FWD_GROUP_THREADS;
 constexpr int PROD_THREADS = 64;
 constexpr int FWD_ISSUE_THREADS = 32 * FWD_GROUPS;      // one MMA-issuer warp per group
 constexpr int FWD_THREADS = FWD_ROW_THREADS + PROD_THREADS + FWD_ISSUE_THREADS;
-constexpr int CT_MAX = 8;                 // output channels supported by the tensor-core path
-constexpr int NY = 16;                    // N of the output-layer MMA (smallest legal N for M = 128)
+constexpr int CT_MAX = 8;                 // output channels of the backward kernel and of the stacked (hi|lo along N) forward form
+constexpr int CF_MAX = 64;                // output channels supported by the forward kernel (Y has 64 TMEM columns per group)
+
+// Output-layer operand of the forward kernel, by padded channel count CP:
+//   CP = 8 (C <= 8): ONE N = 16 MMA per K-step, rows n = c -> Wo_hi[c], n = 8 + c -> Wo_lo[c] (hi*hi and hi*lo in one instruction);
+//   CP = 16/32/48/64: N = CP, separate hi and lo blocks, three MMA sets (a_hi Wo_hi + a_lo Wo_hi + a_hi Wo_lo) into the same Y.
+template <int CP> struct YwCfg {
+    static constexpr int N = CP <= 8 ? 16 : CP;            // N of the output-layer MMA (smallest legal N for M = 128 is 16)
+    static constexpr int ROWS = CP <= 8 ? 16 : 2 * CP;     // operand rows held in the slot
+    static constexpr int LO = CP <= 8 ? 8 * HID : CP * HID; // float offset of the lo rows (n-block 1 / the second block)
+};
 
 // shared-memory slot of one feature: B operands (hi/lo, UMMA K-major no-swizzle core-matrix layout) + small vectors
+template <int CP>
 struct __align__(16) FeatSlot {
     float bhi[HID * HID];                 // W2   [n=j][k=i]
     float blo[HID * HID];
-    float yw[NY * HID];                   // [n][k=j]: n = c -> Wo_hi[c], n = 8 + c -> Wo_lo[c]  (rows c >= C are zero)
+    float yw[YwCfg<CP>::ROWS * HID];      // [n][k=j] (rows c >= C are zero)
     float w1[HID], b1[HID], b2[HID];
 };
 
+template <int CP>
 struct FwdSmem {
-    FeatSlot slot[2];
-    float bo_sum[CT_MAX];                 // sum of the chunk's output biases
+    FeatSlot<CP> slot[2];
+    float bo_sum[CF_MAX];                 // sum of the chunk's output biases
     uint64_t b_full[2], b_empty[2], a1_full[FWD_GROUPS], a2_full[FWD_GROUPS], d1_full[FWD_GROUPS], dy_full[FWD_GROUPS];
     uint32_t tmem_base;
 };
@@ -59,6 +70,9 @@ struct TcArgs {
     int single_pass;  // 1 = plain tf32 (no lo terms)
     int prof;         // debug: bit 0 = accumulate phase cycle counters (GNAN_TC_PROF), bit 1 = skip MMA3 (GNAN_TC_SKIP3)
     const int64_t *grp_ptr;   // backward, entries mode (gnan_mlp_entries_bwd): rows of group g = its entries; NULL = dense
+    // backward over a channel slice [c_off, c_off + C) of Ctot channels (C > 8 runs as ceil(C/8) passes whose gradients add up:
+    // everything downstream of dh = sum_c g_c wo_c is linear in g); chunk_off = first partial-gradient slot of the pass
+    int Ctot, c_off, chunk_off;
 };
 
 __device__ __forceinline__ uint64_t tc_drop_key(const TcArgs &a, int layer, int g, int64_t row, int unit)
@@ -68,7 +82,8 @@ __device__ __forceinline__ uint64_t tc_drop_key(const TcArgs &a, int layer, int 
 
 constexpr uint32_t B_LBO = 128, B_SBO = 2048, B_KSTEP = 256;   // bytes; one K-step = 8 tf32 = two 16-byte chunks
 
-__device__ __forceinline__ float produce_slot(FeatSlot &sl, const TcArgs &a, int g, int pt)
+template <int CP>
+__device__ __forceinline__ float produce_slot(FeatSlot<CP> &sl, const TcArgs &a, int g, int pt)
 {
     const float *W = a.wh + (size_t)g * HID * HID;     // [j][i] = [n][k]
     float4 v[16];
@@ -94,9 +109,9 @@ __device__ __forceinline__ float produce_slot(FeatSlot &sl, const TcArgs &a, int
     for (int c = 0; c < a.C; ++c) {
         uint32_t h, l;
         split_tf32(__ldg(a.wo + ((size_t)g * a.C + c) * HID + pt), h, l);
-        const int o = (pt >> 2) * 32 + (c & 7) * 4 + (pt & 3);      // n-block 0 = hi rows, n-block 1 (+512 floats) = lo rows
+        const int o = (c >> 3) * 512 + (pt >> 2) * 32 + (c & 7) * 4 + (pt & 3);      // hi rows first, lo rows YwCfg::LO floats later
         sl.yw[o] = __uint_as_float(h);
-        sl.yw[512 + o] = __uint_as_float(l);
+        sl.yw[YwCfg<CP>::LO + o] = __uint_as_float(l);
     }
     return (a.bo && pt < a.C) ? __ldg(a.bo + (size_t)g * a.C + pt) : 0.f;
 }
@@ -106,13 +121,14 @@ __device__ __forceinline__ float produce_slot(FeatSlot &sl, const TcArgs &a, int
 //   gen   a0 = relu(x w1 + b1) -> TMEM A (hi|lo)                      | MMA1: z = a0 W2^T           (24 x M128 N64 K8)
 //   epi   a1 = relu(z + b2)    -> TMEM A (hi|lo, overwriting a0)      | MMAy: Y += a1 Wo^T          (24 x M128 N16 K8)
 // Y accumulates over the chunk's features in TMEM (the sum over groups f_k never leaves the tensor core) and is read once.
-template <bool DROP>
+template <bool DROP, int CP>
 __global__ void __launch_bounds__(FWD_THREADS, 1)
 mlp_tc_fwd_kernel(TcArgs a, int KC, float *__restrict__ Spart)
 {
     if (DROP && a.seed_dev) a.seed ^= *a.seed_dev;
+    using YC = YwCfg<CP>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    FwdSmem &sm = *reinterpret_cast<FwdSmem *>(smem_raw);
+    FwdSmem<CP> &sm = *reinterpret_cast<FwdSmem<CP> *>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g0 = blockIdx.y * KC;
     const int ng = min(KC, a.G - g0);
@@ -134,7 +150,7 @@ mlp_tc_fwd_kernel(TcArgs a, int KC, float *__restrict__ Spart)
     if (tid >= FWD_ROW_THREADS && tid < FWD_ROW_THREADS + PROD_THREADS) {   // zero the output-layer operands once (rows c >= C stay zero)
         const int pt = tid - FWD_ROW_THREADS;
         for (int s = 0; s < 2; ++s)
-            for (int i = pt; i < NY * HID; i += PROD_THREADS) sm.slot[s].yw[i] = 0.f;
+            for (int i = pt; i < YC::ROWS * HID; i += PROD_THREADS) sm.slot[s].yw[i] = 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -146,10 +162,10 @@ mlp_tc_fwd_kernel(TcArgs a, int KC, float *__restrict__ Spart)
         const int grp = (tid - FWD_ROW_THREADS - PROD_THREADS) >> 5;
         const uint32_t gbase = tmem + (uint32_t)grp * 256;
         const uint32_t colA_hi = 0, colA_lo = 64, colD = 128, colY = 192;
-        const uint32_t idesc = umma_idesc_tf32(128, 64), idesc_y = umma_idesc_tf32(128, NY);
+        const uint32_t idesc = umma_idesc_tf32(128, 64), idesc_y = umma_idesc_tf32(128, YC::N);
         for (int kk = 0; kk < ng; ++kk) {
             const int s = kk & 1, n = kk >> 1;
-            const FeatSlot &sl = sm.slot[s];
+            const FeatSlot<CP> &sl = sm.slot[s];
             mbar_wait(smem_u32(&sm.b_full[s]), n & 1);
             mbar_wait(smem_u32(&sm.a1_full[grp]), kk & 1);
             tc_fence_after();
@@ -181,6 +197,12 @@ mlp_tc_fwd_kernel(TcArgs a, int KC, float *__restrict__ Spart)
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks)
                         umma_tf32_ts(gbase + colY, gbase + colA_lo + ks * 8, umma_desc_kmajor(yw + ks * B_KSTEP, B_LBO, B_SBO), idesc_y, 1);
+                    if (CP > 8) {                            // the stacked form gets hi*lo from rows 8..15 of the same MMA
+                        const uint32_t ywl = yw + (uint32_t)YC::LO * 4u;
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks)
+                            umma_tf32_ts(gbase + colY, gbase + colA_hi + ks * 8, umma_desc_kmajor(ywl + ks * B_KSTEP, B_LBO, B_SBO), idesc_y, 1);
+                    }
                 }
                 umma_commit(smem_u32(&sm.dy_full[grp]));
                 umma_commit(smem_u32(&sm.b_empty[s]));       // the slot is free once this group's MMAs on it are done
@@ -195,7 +217,7 @@ mlp_tc_fwd_kernel(TcArgs a, int KC, float *__restrict__ Spart)
             const int s = kk & 1, n = kk >> 1;
             mbar_wait(smem_u32(&sm.b_empty[s]), (n & 1) ^ 1);
             bsum += produce_slot(sm.slot[s], a, g0 + kk, pt);
-            if (kk == ng - 1 && pt < CT_MAX) sm.bo_sum[pt] = bsum;
+            if (kk == ng - 1) sm.bo_sum[pt] = bsum;                  // PROD_THREADS == CF_MAX
             fence_async_smem();                      // make the generic-proxy writes visible to the tensor core
             mbar_arrive(smem_u32(&sm.b_full[s]));
         }
@@ -214,7 +236,7 @@ mlp_tc_fwd_kernel(TcArgs a, int KC, float *__restrict__ Spart)
 
         for (int kk = 0; kk < ng; ++kk) {
             const int s = kk & 1, n = kk >> 1, g = g0 + kk;
-            const FeatSlot &sl = sm.slot[s];
+            const FeatSlot<CP> &sl = sm.slot[s];
             const float x = x_next;
             if (kk + 1 < ng && row_ok) x_next = ldg_prefetch(a.u + row * a.ldu + g + 1);
             mbar_wait(smem_u32(&sm.b_full[s]), n & 1);
@@ -273,15 +295,32 @@ mlp_tc_fwd_kernel(TcArgs a, int KC, float *__restrict__ Spart)
         // ---- S[row, c] = Y + sum of output biases
         mbar_wait(smem_u32(&sm.dy_full[grp]), (ng - 1) & 1);
         tc_fence_after();
-        if (half == 0) {
-            uint32_t y[16];
-            tmem_ld16(lane_base + colY, y);
-            tmem_wait_ld();
-            if (row_ok) {
-                float *out = Spart + ((size_t)blockIdx.y * a.R + row) * a.C;
+        if (CP <= 8) {
+            if (half == 0) {
+                uint32_t y[16];
+                tmem_ld16(lane_base + colY, y);
+                tmem_wait_ld();
+                if (row_ok) {
+                    float *out = Spart + ((size_t)blockIdx.y * a.R + row) * a.C;
 #pragma unroll
-                for (int c = 0; c < CT_MAX; ++c)
-                    if (c < a.C) out[c] = (__uint_as_float(y[c]) + __uint_as_float(y[8 + c])) + sm.bo_sum[c];
+                    for (int c = 0; c < CT_MAX; ++c)
+                        if (c < a.C) out[c] = (__uint_as_float(y[c]) + __uint_as_float(y[8 + c])) + sm.bo_sum[c];
+                }
+            }
+        } else {
+            // 16-column chunks of Y alternate between the two column halves of the quadrant's warps
+#pragma unroll
+            for (int n0 = 0; n0 < CP; n0 += 16) {
+                if (((n0 >> 4) & 1) != half) continue;
+                uint32_t y[16];
+                tmem_ld16(lane_base + colY + n0, y);
+                tmem_wait_ld();
+                if (row_ok) {
+                    float *out = Spart + ((size_t)blockIdx.y * a.R + row) * a.C;
+#pragma unroll
+                    for (int c = 0; c < 16; ++c)
+                        if (n0 + c < a.C) out[n0 + c] = __uint_as_float(y[c]) + sm.bo_sum[n0 + c];
+                }
             }
         }
     }
@@ -395,8 +434,9 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
         ntiles = (nrow + ROWS - 1) / ROWS;
         ub = a.u + ebase;
         ustride = 1;
-        dS += ebase * a.C;
+        dS += ebase * a.Ctot;
     }
+    dS += a.c_off;
 
     if (warp == BWD_ROW_WARPS) tmem_alloc(smem_u32(&sm.tmem_base), 512);
     if (tid == 0) {
@@ -425,7 +465,7 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
             sm.b1[tid] = a.b1 ? __ldg(a.b1 + (size_t)g * HID + tid) : 0.f;
             sm.b2[tid] = a.bh ? __ldg(a.bh + (size_t)g * HID + tid) : 0.f;
             for (int c = 0; c < CT_MAX; ++c) {
-                const float v = c < a.C ? __ldg(a.wo + ((size_t)g * a.C + c) * HID + tid) : 0.f;
+                const float v = c < a.C ? __ldg(a.wo + ((size_t)g * a.Ctot + a.c_off + c) * HID + tid) : 0.f;
                 uint32_t h, l;
                 split_tf32(v, h, l);
                 const int o = (tid >> 3) * 64 + (c >> 2) * 32 + (tid & 7) * 4 + (c & 3);   // (n=tid, k=c): LBO 128 B, SBO 256 B
@@ -540,7 +580,7 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
             const bool ok = blockIdx.x < ntiles && row < nrow;
             x_n = ok ? __ldg(ub + row * ustride) : 0.f;
 #pragma unroll
-            for (int c = 0; c < CT; ++c) gv_n[c] = (ok && c < a.C && part == 0) ? __ldg(dS + row * a.C + c) : 0.f;
+            for (int c = 0; c < CT; ++c) gv_n[c] = (ok && c < a.C && part == 0) ? __ldg(dS + row * a.Ctot + c) : 0.f;
         }
         // dWo phase of tile `tp` (parity php): a1 recomputed from D1[php], staged to the scratch tile (sZ, free once MMA3 of
         // that tile is done), dWo[c][j] += g[r][c] a1[r][j]. Runs while the tensor core works on the NEXT tile's MMA1.
@@ -599,7 +639,7 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
 #pragma unroll
                 for (int c = 0; c < CT; ++c) {
                     gv_n[c] = 0.f;
-                    if (okn && c < a.C) gv_n[c] = ldg_prefetch(dS + rown * a.C + c);
+                    if (okn && c < a.C) gv_n[c] = ldg_prefetch(dS + rown * a.Ctot + c);
                 }
             }
             TC_PROF(9);
@@ -723,7 +763,7 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
             dwo_phase(tl, (it - 1) & 1);
         }
         // ---- write this CTA's partial gradients (everything but dW2)
-        const size_t off = (size_t)blockIdx.x * gp.chunk_stride;
+        const size_t off = (size_t)(blockIdx.x + a.chunk_off) * gp.chunk_stride;
         float *red = &sm.red[0][0];                        // red[warp][0..NC) and [NC..2NC)
         const int lc = lane & (NC - 1);
         // unit u = part*NC + lc lives in the four warps part*4 + q, q = 0..3
@@ -759,7 +799,7 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
                 const int c = idx >> 6, j = idx & 63;
                 float s = 0.f;
                 for (int k = 0; k < NRG; ++k) s += scr[(c * NRG + k) * HID + j];
-                gp.wo[off + (size_t)g * a.C * HID + idx] = s;
+                gp.wo[off + ((size_t)g * a.Ctot + a.c_off) * HID + idx] = s;
             }
         named_bar_sync(1, BWD_ROW_THREADS);
         // ---- dW2 = D3[lane j] + D3[lane 64 + j]  (hi and lo halves of the stacked A operand); all MMAs are complete (d3_full)
@@ -859,32 +899,46 @@ TcArgs make_tc_args(const float *u, int64_t R, int64_t ldu, const gnan_mlp_param
     a.single_pass = precision == GNAN_PREC_TF32;
     a.prof = (getenv("GNAN_TC_PROF") != nullptr ? 1 : 0) | (getenv("GNAN_TC_SKIP3") != nullptr ? 2 : 0);
     a.grp_ptr = nullptr;
+    a.Ctot = p->C; a.c_off = 0; a.chunk_off = 0;
     return a;
+}
+
+template <int CP>
+int launch_tc_fwd_cp(const TcArgs &a, const TcFwdPlan &pl, float *Spart, cudaStream_t st)
+{
+    const size_t smem = sizeof(FwdSmem<CP>) + 1024;
+    dim3 grid((unsigned)pl.ntile, (unsigned)pl.nchunk);
+    if (a.drop_thresh) {
+        GNAN_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<true, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mlp_tc_fwd_kernel<true, CP><<<grid, FWD_THREADS, smem, st>>>(a, pl.KC, Spart);
+    } else {
+        GNAN_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<false, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mlp_tc_fwd_kernel<false, CP><<<grid, FWD_THREADS, smem, st>>>(a, pl.KC, Spart);
+    }
+    GNAN_LAUNCH_OK();
+    return GNAN_OK;
 }
 
 int launch_tc_fwd(const TcArgs &a, const TcFwdPlan &pl, float *Spart, cudaStream_t st)
 {
-    const size_t smem = sizeof(FwdSmem) + 1024;
-    dim3 grid((unsigned)pl.ntile, (unsigned)pl.nchunk);
-    if (a.drop_thresh) {
-        GNAN_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mlp_tc_fwd_kernel<true><<<grid, FWD_THREADS, smem, st>>>(a, pl.KC, Spart);
-    } else {
-        GNAN_CUDA(cudaFuncSetAttribute(mlp_tc_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        mlp_tc_fwd_kernel<false><<<grid, FWD_THREADS, smem, st>>>(a, pl.KC, Spart);
-    }
-    GNAN_LAUNCH_OK();
-    return GNAN_OK;
+    if (a.C <= 8) return launch_tc_fwd_cp<8>(a, pl, Spart, st);
+    if (a.C <= 16) return launch_tc_fwd_cp<16>(a, pl, Spart, st);
+    if (a.C <= 32) return launch_tc_fwd_cp<32>(a, pl, Spart, st);
+    if (a.C <= 48) return launch_tc_fwd_cp<48>(a, pl, Spart, st);
+    return launch_tc_fwd_cp<64>(a, pl, Spart, st);
 }
 
 }  // namespace
 
 int gnan_mlp_tc_supported(const gnan_mlp_params *p, int precision)
 {
-    return (precision == GNAN_PREC_TF32X3 || precision == GNAN_PREC_TF32) && p->H == HID && p->n_layers == 3 && p->C <= CT_MAX;
+    return (precision == GNAN_PREC_TF32X3 || precision == GNAN_PREC_TF32) && p->H == HID && p->n_layers == 3 && p->C <= CF_MAX;
 }
 
 int gnan_mlp_tc_bwd_supported(const gnan_mlp_params *p, int precision) { return gnan_mlp_tc_supported(p, precision); }
+
+// backward passes over 8-channel slices
+static inline int tc_bwd_passes(const gnan_mlp_params *p) { return (p->C + CT_MAX - 1) / CT_MAX; }
 
 namespace {
 inline size_t pad4(size_t n) { return (n + 3) / 4 * 4; }
@@ -927,7 +981,8 @@ size_t gnan_mlp_tc_workspace_bytes(int64_t R, const gnan_mlp_params *p, int back
     (void)precision;
     if (backward) {
         const TcBwdPlan pl = plan_tc_bwd(R, p);
-        return pl.nchunk > 1 ? sizeof(float) * (size_t)pl.nchunk * tc_grad_floats(p) : 0;
+        const int slots = pl.nchunk * tc_bwd_passes(p);
+        return slots > 1 ? sizeof(float) * (size_t)slots * tc_grad_floats(p) : 0;
     }
     const TcFwdPlan pl = plan_tc_fwd(R, p);
     return pl.nchunk > 1 ? sizeof(float) * (size_t)pl.nchunk * R * p->C : 0;
@@ -961,9 +1016,10 @@ int gnan_mlp_tc_bwd_ex(const float *u, int64_t R, int64_t ldu, const gnan_mlp_pa
 {
     const TcBwdPlan pl = plan_tc_bwd(R, p);
     const size_t G = p->G, C = p->C, ntot = tc_grad_floats(p);
+    const int npass = tc_bwd_passes(p), slots = pl.nchunk * npass;
     TcGradPtrs gp;
-    if (pl.nchunk > 1) {
-        const size_t need = sizeof(float) * (size_t)pl.nchunk * ntot;
+    if (slots > 1) {
+        const size_t need = sizeof(float) * (size_t)slots * ntot;
         if (!ws || ws_bytes < need) {
             gnan_set_error("mlp_bwd(tc): workspace %zu < %zu bytes", ws_bytes, need);
             return GNAN_ERR_WORKSPACE;
@@ -983,19 +1039,26 @@ int gnan_mlp_tc_bwd_ex(const float *u, int64_t R, int64_t ldu, const gnan_mlp_pa
     TcArgs a = make_tc_args(u, R, ldu, p, dropout_p, seed, precision);
     a.grp_ptr = grp_ptr;
     a.seed_dev = seed_dev;
-    int rc;
-    if (p->C == 1) rc = launch_tc_bwd<1>(a, pl, dS, gp, st);
-    else if (p->C == 2) rc = launch_tc_bwd<2>(a, pl, dS, gp, st);
-    else if (p->C <= 4) rc = launch_tc_bwd<4>(a, pl, dS, gp, st);
-    else rc = launch_tc_bwd<8>(a, pl, dS, gp, st);
+    int rc = GNAN_OK;
+    if (npass > 1)     // a pass writes only its own channel slice of dWo: the other slots' slices must read as zero in the reduction
+        GNAN_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * (size_t)slots * ntot, st));
+    for (int ps = 0; ps < npass && !rc; ++ps) {
+        a.c_off = ps * CT_MAX;
+        a.C = std::min<int>(CT_MAX, (int)C - a.c_off);
+        a.chunk_off = ps * pl.nchunk;
+        if (a.C == 1) rc = launch_tc_bwd<1>(a, pl, dS, gp, st);
+        else if (a.C == 2) rc = launch_tc_bwd<2>(a, pl, dS, gp, st);
+        else if (a.C <= 4) rc = launch_tc_bwd<4>(a, pl, dS, gp, st);
+        else rc = launch_tc_bwd<8>(a, pl, dS, gp, st);
+    }
     if (rc) return rc;
-    if (pl.nchunk > 1) {
+    if (slots > 1) {
         struct Seg { const float *src; float *dst; size_t n; };
         const Seg segs[5] = {{gp.w1, grads->w1, G * HID}, {gp.b1, grads->b1, G * HID}, {gp.wh, grads->wh, G * HID * HID},
                              {gp.bh, grads->bh, G * HID}, {gp.wo, grads->wo, G * C * HID}};
         for (const Seg &sg : segs) {
             if (!sg.dst || sg.n == 0) continue;
-            rc = gnan_reduce_chunks(sg.src, pl.nchunk, sg.n, ntot, sg.dst, st);
+            rc = gnan_reduce_chunks(sg.src, slots, sg.n, ntot, sg.dst, st);
             if (rc) return rc;
         }
     }

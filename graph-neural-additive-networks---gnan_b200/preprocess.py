@@ -223,9 +223,27 @@ class PackedBatch:
                            self.max_nodes)
 
 
-def apsp_batched(edge_index, node_off, device="cuda", x=None, y=None, node_off_device=None, _level_table_width=48):
+def check_batched_status(status):
+    """Raise for a status word returned by apsp_batched(..., nbins=...) (one device read; call it once per epoch or when a
+    result looks wrong, not once per step)."""
+    st, over, _ = (int(v) for v in status.tolist())
+    _check_status(st)
+    if st & 2:
+        raise ValueError("duplicate edges in the batch: call apsp_batched without nbins (multi-edge emulation path)")
+    if over:
+        raise ValueError("a hop distance does not fit the fixed-width level table: pass a larger nbins")
+
+
+def apsp_batched(edge_index, node_off, device="cuda", x=None, y=None, node_off_device=None, _level_table_width=48, nbins=None,
+                 hop_off_device=None):
     """Hop blocks of B small graphs (<= 256 nodes each) in one launch. edge_index uses GLOBAL node ids of the
     concatenated node set; node_off [B+1] are the graph boundaries.
+
+    nbins: fixed level-table width (levels 0..nbins-2, last column = unreachable). The call then never synchronises with the
+    host (it can be captured in a CUDA graph with the rest of a training step); empty levels carry a zero count and
+    contribute nothing. The returned batch has `.status` (device int32 [3]: CSR status, overflow flag, largest hop) to be
+    checked lazily with check_batched_status. hop_off_device: optional int64 device copy of the block offsets
+    (cumsum of n_b^2, B+1 entries; with node_off_device it removes every host -> device copy from the call).
 
     Pass node_off as a HOST tensor / array (what a data loader has): block sizes and offsets are then computed on the host
     and the call synchronises exactly once, at the end (overflow flag + largest hop, which sizes the level table).
@@ -249,22 +267,28 @@ def apsp_batched(edge_index, node_off, device="cuda", x=None, y=None, node_off_d
     if node_off_device is None:
         node_off_device = torch.from_numpy(no_h.astype(np.int32)).to(device, non_blocking=True)
     node_off_d = node_off_device
-    hop_off = torch.from_numpy(hop_off_h).to(device, non_blocking=True)
+    hop_off = hop_off_device if hop_off_device is not None else torch.from_numpy(hop_off_h).to(device, non_blocking=True)
     st = torch.zeros(3, dtype=torch.int32, device=device)              # [csr status, overflow, largest finite hop]
     rowptr, col, _ = build_csr(edge_index, sumN, device, status=st[0:1])
     hop = torch.empty(max(total, 1), dtype=torch.uint8, device=device)
     nb_full = min(256, max_n + 1)                # a finite hop inside a graph is at most max_n - 1; last column = unreachable
     nb = min(nb_full, _level_table_width) if _level_table_width else nb_full
+    if nbins is not None:
+        nb = int(nbins)
     cnt = torch.empty(sumN, nb, dtype=torch.int32, device=device)
     with _timed("apsp_bfs_batched"):
         check(lib.gnan_apsp_bfs_batched_n(ptr(rowptr), ptr(col), ptr(node_off_d), ptr(hop_off), B, max_n, sumN, total, ptr(hop), ptr(cnt), nb,
                                           st.data_ptr() + 4, st.data_ptr() + 8, stream_handle()), "gnan_apsp_bfs_batched")
+    if nbins is not None:
+        pk = PackedBatch(x, hop, hop_off, node_off_d, cnt, y, max_n)
+        pk.status = st
+        return pk
     status, over, D = (int(v) for v in st.tolist()) if B > 0 else (0, 0, 0)
     _check_status(status)
     if status & 2:
         return _apsp_batched_multi_edges(edge_index, no_h, device, x, y)
     if over and nb < nb_full:                    # deeper than the narrow level table: once more with the full width
-        return apsp_batched(edge_index, node_off, device, x, y, node_off_device, _level_table_width=0)
+        return apsp_batched(edge_index, node_off, device, x, y, node_off_device, _level_table_width=0, hop_off_device=hop_off_device)
     if over:
         raise NotImplementedError("a hop distance > 254 does not fit the uint8 hop matrix")
     if sumN == 0:

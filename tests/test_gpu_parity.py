@@ -651,12 +651,14 @@ def test_large_row_block_vs_lut_oracle():
 
 # ---- tensor-core (tcgen05) path of the grouped MLP -------------------------------------------------------------------
 @pytest.mark.parametrize("precision,tol,gtol", [("tf32x3", 1e-5, 1e-5), ("tf32", 5e-3, 5e-2)])
-@pytest.mark.parametrize("R,G_,C", [(1, 1, 1), (128, 2, 3), (129, 9, 7), (300, 15, 1), (1000, 40, 4), (1100, 6, 7), (5000, 3, 8)])
+@pytest.mark.parametrize("R,G_,C", [(1, 1, 1), (128, 2, 3), (129, 9, 7), (300, 15, 1), (1000, 40, 4), (1100, 6, 7), (5000, 3, 8),
+                                    (700, 5, 9), (513, 4, 16), (900, 3, 40), (1300, 9, 33), (300, 2, 64)])
 def test_mlp_tensor_core_vs_oracle(R, G_, C, precision, tol, gtol):
     """Forward and backward on tcgen05. The 3xTF32 split keeps fp32-level accuracy: bound 1e-5 for outputs AND gradients
     (measured 7e-7 / 3e-6). Single-pass tf32 has the stated looser bounds 5e-3 (outputs) / 5e-2 (gradients: its 1e-3
     forward noise flips ReLU masks). Inputs are drawn with every float64 pre-activation at least 2e-5 from zero so that
-    no mask flips under the 1e-6 rounding differences of the split."""
+    no mask flips under the 1e-6 rounding differences of the split. C > 8: forward with an N = 16..64 output-layer MMA (separate
+    hi / lo operand blocks), backward as ceil(C/8) passes over 8-channel slices whose partial gradients add up."""
     from gnan_b200 import ops
     H, L = 64, 3
     rng = np.random.default_rng(R * 11 + G_)
