@@ -704,6 +704,9 @@ int gnan_mlp_tc_bwd_supported(const gnan_mlp_params *p, int precision);
 size_t gnan_mlp_tc_workspace_bytes(int64_t R, const gnan_mlp_params *p, int backward, int precision);
 int gnan_mlp_tc_fwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *p, float dropout_p, uint64_t seed,
                     int precision, float *S, void *ws, size_t ws_bytes, cudaStream_t st, const uint64_t *seed_dev);
+int gnan_mlp_tc_entries_fwd_supported(const gnan_mlp_params *p, int precision);
+int gnan_mlp_tc_entries_fwd(const float *val, const int64_t *grp_ptr, int64_t E, const int32_t *items, int64_t n_items,
+                            const gnan_mlp_params *p, int precision, float *Y, cudaStream_t st);
 int gnan_mlp_tc_bwd_ex(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *p, float dropout_p, uint64_t seed,
                        int precision, const float *dS, const gnan_mlp_grads *grads, void *ws, size_t ws_bytes, cudaStream_t st,
                        const int64_t *grp_ptr, const uint64_t *seed_dev);
@@ -870,10 +873,18 @@ extern "C" size_t gnan_mlp_entries_workspace_bytes(int64_t max_group_entries, co
 extern "C" int gnan_mlp_entries_fwd(const float *val, const int64_t *grp_ptr, int64_t E, const int32_t *items, int64_t n_items,
                                     const gnan_mlp_params *p, float *Y, gnan_stream_t stream)
 {
+    return gnan_mlp_entries_fwd_ex(val, grp_ptr, E, items, n_items, p, GNAN_PREC_FP32, Y, stream);
+}
+
+extern "C" int gnan_mlp_entries_fwd_ex(const float *val, const int64_t *grp_ptr, int64_t E, const int32_t *items, int64_t n_items,
+                                       const gnan_mlp_params *p, int precision, float *Y, gnan_stream_t stream)
+{
     int rc = check_entries(p, val, grp_ptr, E, "mlp_entries_fwd");
     if (rc) return rc;
     GNAN_REQUIRE(n_items >= 0 && (n_items == 0 || (items != nullptr && Y != nullptr)), "mlp_entries_fwd: NULL items or Y");
     if (n_items == 0) return GNAN_OK;
+    if (precision != GNAN_PREC_FP32 && gnan_mlp_tc_entries_fwd_supported(p, precision))      // tcgen05 kernel
+        return gnan_mlp_tc_entries_fwd(val, grp_ptr, E, items, n_items, p, precision, Y, (cudaStream_t)stream);
     MlpKArgs a = make_args(val, E, 1, p, 0.f, 0);
     a.grp_ptr = grp_ptr;
     a.items = items;

@@ -329,6 +329,222 @@ mlp_tc_fwd_kernel(TcArgs a, int KC, float *__restrict__ Spart)
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// ---- forward, entries mode (gnan_mlp_entries_fwd_ex) ----------------------------------------------------------------------
+// Y[e,:] = f_g(val[e]) per entry (no sum over groups: gnan_entries_to_rows does that). A work item = (group, 128-entry tile of
+// that group). The CTA is persistent; its two row groups consume DIFFERENT items (item 2i and 2i+1 of the CTA's stride), so each
+// row group has its own double-buffered weight slot, its own 64 producer threads and its own MMA-issuer warp; the pipeline per
+// item is the dense forward's (layer 1 -> TMEM, MMA1, a1 -> TMEM, output-layer MMA with hi|lo stacked along N), except that Y
+// starts from zero at every item and is read back one item later (while that item's layer 1 is generated). No dropout.
+constexpr int ENT_PROD_THREADS = FWD_GROUPS * PROD_THREADS;
+constexpr int ENT_THREADS = FWD_ROW_THREADS + ENT_PROD_THREADS + FWD_ISSUE_THREADS;
+
+struct EntSmem {
+    FeatSlot<8> slot[FWD_GROUPS][2];
+    uint64_t b_full[FWD_GROUPS][2], b_empty[FWD_GROUPS][2], a1_full[FWD_GROUPS], a2_full[FWD_GROUPS], d1_full[FWD_GROUPS], dy_full[FWD_GROUPS];
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(ENT_THREADS, 1)
+mlp_tc_entries_fwd_kernel(TcArgs a, const int32_t *__restrict__ items, int64_t n_items, float *__restrict__ Y)
+{
+    using YC = YwCfg<8>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    EntSmem &sm = *reinterpret_cast<EntSmem *>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t stride = (int64_t)gridDim.x * FWD_GROUPS;
+
+    if (warp == 0) tmem_alloc(smem_u32(&sm.tmem_base), 512);
+    if (tid == 32) {
+        for (int gI = 0; gI < FWD_GROUPS; ++gI) {
+            for (int s2 = 0; s2 < 2; ++s2) {
+                mbar_init(smem_u32(&sm.b_full[gI][s2]), PROD_THREADS);
+                mbar_init(smem_u32(&sm.b_empty[gI][s2]), 1);
+            }
+            mbar_init(smem_u32(&sm.a1_full[gI]), FWD_GROUP_THREADS);
+            mbar_init(smem_u32(&sm.a2_full[gI]), FWD_GROUP_THREADS);
+            mbar_init(smem_u32(&sm.d1_full[gI]), 1);
+            mbar_init(smem_u32(&sm.dy_full[gI]), 1);
+        }
+        mbar_init_fence();
+    }
+    if (tid >= FWD_ROW_THREADS && tid < FWD_ROW_THREADS + ENT_PROD_THREADS) {   // output-layer operand rows c >= C stay zero
+        const int pq = tid - FWD_ROW_THREADS;
+        for (int gI = 0; gI < FWD_GROUPS; ++gI)
+            for (int s2 = 0; s2 < 2; ++s2)
+                for (int i = pq; i < YC::ROWS * HID; i += ENT_PROD_THREADS) sm.slot[gI][s2].yw[i] = 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    if (tid >= FWD_ROW_THREADS + ENT_PROD_THREADS) {
+        // ===== MMA issuers: one warp per row group =====
+        const int grp = (tid - FWD_ROW_THREADS - ENT_PROD_THREADS) >> 5;
+        const uint32_t gbase = tmem + (uint32_t)grp * 256;
+        const uint32_t colA_hi = 0, colA_lo = 64, colD = 128, colY = 192;
+        const uint32_t idesc = umma_idesc_tf32(128, 64), idesc_y = umma_idesc_tf32(128, YC::N);
+        int kk = 0;
+        for (int64_t it = (int64_t)blockIdx.x * FWD_GROUPS + grp; it < n_items; it += stride, ++kk) {
+            const int s = kk & 1, n = kk >> 1;
+            const FeatSlot<8> &sl = sm.slot[grp][s];
+            mbar_wait(smem_u32(&sm.b_full[grp][s]), n & 1);
+            mbar_wait(smem_u32(&sm.a1_full[grp]), kk & 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t bh = smem_u32(sl.bhi), bl = smem_u32(sl.blo);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    umma_tf32_ts(gbase + colD, gbase + colA_hi + ks * 8, umma_desc_kmajor(bh + ks * B_KSTEP, B_LBO, B_SBO), idesc, ks > 0);
+                if (!a.single_pass) {
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        umma_tf32_ts(gbase + colD, gbase + colA_lo + ks * 8, umma_desc_kmajor(bh + ks * B_KSTEP, B_LBO, B_SBO), idesc, 1);
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        umma_tf32_ts(gbase + colD, gbase + colA_hi + ks * 8, umma_desc_kmajor(bl + ks * B_KSTEP, B_LBO, B_SBO), idesc, 1);
+                }
+                umma_commit(smem_u32(&sm.d1_full[grp]));
+            }
+            __syncwarp();
+            mbar_wait(smem_u32(&sm.a2_full[grp]), kk & 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t yw = smem_u32(sl.yw);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)
+                    umma_tf32_ts(gbase + colY, gbase + colA_hi + ks * 8, umma_desc_kmajor(yw + ks * B_KSTEP, B_LBO, B_SBO), idesc_y, ks > 0 ? 1u : 0u);
+                if (!a.single_pass) {
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        umma_tf32_ts(gbase + colY, gbase + colA_lo + ks * 8, umma_desc_kmajor(yw + ks * B_KSTEP, B_LBO, B_SBO), idesc_y, 1);
+                }
+                umma_commit(smem_u32(&sm.dy_full[grp]));
+                umma_commit(smem_u32(&sm.b_empty[grp][s]));
+            }
+            __syncwarp();
+        }
+    } else if (tid >= FWD_ROW_THREADS) {
+        // ===== producers: 64 threads per row group =====
+        const int pq = tid - FWD_ROW_THREADS, grp = pq >> 6, pt = pq & 63;
+        int kk = 0;
+        for (int64_t it = (int64_t)blockIdx.x * FWD_GROUPS + grp; it < n_items; it += stride, ++kk) {
+            const int s = kk & 1, n = kk >> 1;
+            const int g = __ldg(items + 2 * it);
+            mbar_wait(smem_u32(&sm.b_empty[grp][s]), (n & 1) ^ 1);
+            (void)produce_slot<8>(sm.slot[grp][s], a, g, pt);
+            fence_async_smem();
+            mbar_arrive(smem_u32(&sm.b_full[grp][s]));
+        }
+    } else {
+        // ===== row threads =====
+        const int grp = tid >> 8, wg = (tid >> 5) & 7;
+        const int q = wg & 3, half = wg >> 2;
+        const int rt = q * 32 + lane;
+        const int c0 = half * 32;
+        const uint32_t gbase = tmem + (uint32_t)grp * 256;
+        const uint32_t lane_base = gbase + ((uint32_t)(q * 32) << 16);
+        const uint32_t colA_hi = 0, colA_lo = 64, colD = 128, colY = 192;
+        // the item after the current one is resolved one iteration ahead (items -> grp_ptr -> val is a dependent load chain)
+        auto resolve = [&](int64_t it, int64_t &erow, float &x, int &g) {
+            erow = -1; x = 0.f; g = 0;
+            if (it < n_items) {
+                g = __ldg(items + 2 * it);
+                const int tile = __ldg(items + 2 * it + 1);
+                const int64_t eb = __ldg(a.grp_ptr + g), ne = __ldg(a.grp_ptr + g + 1) - eb;
+                const int64_t r = (int64_t)tile * ROWS + rt;
+                if (r < ne) { erow = eb + r; x = __ldg(a.u + erow); }
+            }
+        };
+        int64_t it = (int64_t)blockIdx.x * FWD_GROUPS + grp;
+        int64_t erow_n, erow_p = -1;
+        float x_n, bo_p[CT_MAX];
+        int g_n;
+        resolve(it, erow_n, x_n, g_n);
+        int kk = 0;
+        auto write_prev = [&]() {           // Y of the previous item (its output-layer MMAs are complete)
+            if (half == 0) {
+                uint32_t y[16];
+                tmem_ld16(lane_base + colY, y);
+                tmem_wait_ld();
+                if (erow_p >= 0) {
+                    float *out = Y + erow_p * a.C;
+#pragma unroll
+                    for (int c = 0; c < CT_MAX; ++c)
+                        if (c < a.C) out[c] = (__uint_as_float(y[c]) + __uint_as_float(y[8 + c])) + bo_p[c];
+                }
+            }
+        };
+        for (; it < n_items; it += stride, ++kk) {
+            const int s = kk & 1, n = kk >> 1;
+            const FeatSlot<8> &sl = sm.slot[grp][s];
+            const float x = x_n;
+            const int64_t erow = erow_n;
+            const int g = g_n;
+            mbar_wait(smem_u32(&sm.b_full[grp][s]), n & 1);
+            if (kk > 0) {
+                mbar_wait(smem_u32(&sm.dy_full[grp]), (kk - 1) & 1);
+                tc_fence_after();
+                write_prev();
+                tc_fence_before();
+            }
+            erow_p = erow;
+            if (half == 0) {
+#pragma unroll
+                for (int c = 0; c < CT_MAX; ++c) bo_p[c] = (a.bo && c < a.C) ? __ldg(a.bo + (size_t)g * a.C + c) : 0.f;
+            }
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int i4 = 0; i4 < 4; ++i4) {
+                    const float4 w = *reinterpret_cast<const float4 *>(sl.w1 + c0 + p * 16 + i4 * 4);
+                    const float4 b = *reinterpret_cast<const float4 *>(sl.b1 + c0 + p * 16 + i4 * 4);
+                    const float v[4] = {fmaxf(fmaf(x, w.x, b.x), 0.f), fmaxf(fmaf(x, w.y, b.y), 0.f),
+                                        fmaxf(fmaf(x, w.z, b.z), 0.f), fmaxf(fmaf(x, w.w, b.w), 0.f)};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) split_tf32(v[e], hi[i4 * 4 + e], lo[i4 * 4 + e]);
+                }
+                tmem_st16(lane_base + colA_hi + c0 + p * 16, hi);
+                if (!a.single_pass) tmem_st16(lane_base + colA_lo + c0 + p * 16, lo);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(smem_u32(&sm.a1_full[grp]));
+            resolve(it + stride, erow_n, x_n, g_n);            // under MMA1
+            mbar_wait(smem_u32(&sm.d1_full[grp]), kk & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                uint32_t d[16], hi[16], lo[16];
+                tmem_ld16(lane_base + colD + c0 + p * 16, d);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const float4 b = *reinterpret_cast<const float4 *>(sl.b2 + c0 + p * 16 + j4 * 4);
+                    const float h[4] = {fmaxf(__uint_as_float(d[j4 * 4 + 0]) + b.x, 0.f), fmaxf(__uint_as_float(d[j4 * 4 + 1]) + b.y, 0.f),
+                                        fmaxf(__uint_as_float(d[j4 * 4 + 2]) + b.z, 0.f), fmaxf(__uint_as_float(d[j4 * 4 + 3]) + b.w, 0.f)};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) split_tf32(h[e], hi[j4 * 4 + e], lo[j4 * 4 + e]);
+                }
+                tmem_st16(lane_base + colA_hi + c0 + p * 16, hi);
+                if (!a.single_pass) tmem_st16(lane_base + colA_lo + c0 + p * 16, lo);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(smem_u32(&sm.a2_full[grp]));
+        }
+        if (kk > 0) {
+            mbar_wait(smem_u32(&sm.dy_full[grp]), (kk - 1) & 1);
+            tc_fence_after();
+            write_prev();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 // ---- backward ---------------------------------------------------------------------------------------------------------
 // CTA <-> (feature g, row chunk), 16 row warps + 1 MMA warp. A row warp owns 32 rows (one TMEM lane quadrant) x 16 of the
 // 64 hidden units (warps w, w+4, w+8, w+12 share a quadrant). In entries mode (TcArgs::grp_ptr) the rows are the group's own
@@ -1006,6 +1222,25 @@ int gnan_mlp_tc_fwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_param
     int rc = launch_tc_fwd(a, pl, Spart, st);
     if (rc) return rc;
     if (pl.nchunk > 1) return gnan_reduce_chunks(Spart, pl.nchunk, (size_t)R * p->C, (size_t)R * p->C, S, st);
+    return GNAN_OK;
+}
+
+// entries-mode forward on tcgen05 (H = 64, 3 layers, C <= 8): Y[e,:] = f_g(val[e]); items [n_items][2] = (group, tile)
+int gnan_mlp_tc_entries_fwd_supported(const gnan_mlp_params *p, int precision)
+{
+    return gnan_mlp_tc_supported(p, precision) && p->C <= CT_MAX;
+}
+
+int gnan_mlp_tc_entries_fwd(const float *val, const int64_t *grp_ptr, int64_t E, const int32_t *items, int64_t n_items,
+                            const gnan_mlp_params *p, int precision, float *Y, cudaStream_t st)
+{
+    TcArgs a = make_tc_args(val, E, 1, p, 0.f, 0, precision);
+    a.grp_ptr = grp_ptr;
+    const size_t smem = sizeof(EntSmem) + 1024;
+    GNAN_CUDA(cudaFuncSetAttribute(mlp_tc_entries_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::min<int64_t>(gnan_sm_count(), ceil_div64(n_items, FWD_GROUPS));
+    mlp_tc_entries_fwd_kernel<<<grid, ENT_THREADS, smem, st>>>(a, items, n_items, Y);
+    GNAN_LAUNCH_OK();
     return GNAN_OK;
 }
 

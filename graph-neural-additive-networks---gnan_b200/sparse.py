@@ -198,8 +198,8 @@ def mlp_entries_fwd(val: Tensor, grp_ptr: Tensor, items: Tensor, w1: Tensor, b1:
     E = val.numel()
     Y = torch.empty(E, C, dtype=torch.float32, device=val.device)
     with ops._timed("mlp_entries_fwd"):
-        check(lib.gnan_mlp_entries_fwd(ptr(val), ptr(grp_ptr), E, ptr(items.contiguous()), items.shape[0], p, ptr(Y), stream_handle()),
-              "gnan_mlp_entries_fwd")
+        check(lib.gnan_mlp_entries_fwd_ex(ptr(val), ptr(grp_ptr), E, ptr(items.contiguous()), items.shape[0], p, precision, ptr(Y),
+                                          stream_handle()), "gnan_mlp_entries_fwd_ex")
     return Y
 
 
@@ -295,7 +295,7 @@ entries_to_rows.register_autograd(_e2r_backward, setup_context=_e2r_setup)
 
 def feature_sums(cx: CompressedFeatures, w1, b1, wh, bh, wo, bo, n_layers, precision="fp32") -> Tensor:
     """S [N,C] = sum_k f_k(x[:,k]) from the compressed form; differentiable w.r.t. the weights. `precision` selects the
-    backward kernel (fp32 FFMA, or the tcgen05 3xTF32 kernel for H = 64, 3 layers, C <= 8); the forward is fp32."""
+    kernels (fp32 FFMA, or the tcgen05 3xTF32 kernels for H = 64, 3 layers, C <= 8), forward and backward."""
     if wo.shape[0] != cx.num_features:
         raise ValueError(f"compressed x has {cx.num_features} features, the model {wo.shape[0]}")
     from ._lib import PRECISIONS

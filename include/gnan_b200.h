@@ -100,11 +100,14 @@ int gnan_mlp_bwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *
  * The caller lists the distinct work as val[E] grouped by feature, group g owning entries [grp_ptr[g], grp_ptr[g+1]);
  * Y[e,:] = f_g(val[e]) and the weight gradients given dY[E,C] come back; how entries map to rows of S is the caller's
  * business (gnan_b200/sparse.py). items [n_items,2] = (group, 128-entry tile index inside the group): one CTA per item.
- * Forward: fp32 kernels; backward: fp32 or the tcgen05 kernel (`precision`); n_layers >= 2; no dropout (the sharing would
+ * Forward: fp32 kernels (gnan_mlp_entries_fwd) or, with `precision` (gnan_mlp_entries_fwd_ex), the tcgen05 kernel for
+ * H = 64, 3 layers, C <= 8; backward: fp32 or the tcgen05 kernel (`precision`); n_layers >= 2; no dropout (the sharing would
  * be wrong with per-row masks). */
 size_t gnan_mlp_entries_workspace_bytes(int64_t max_group_entries, const gnan_mlp_params *p, int backward, int precision);
 int gnan_mlp_entries_fwd(const float *val, const int64_t *grp_ptr /* [G+1] */, int64_t E, const int32_t *items, int64_t n_items,
                          const gnan_mlp_params *p, float *Y /* [E,C] */, gnan_stream_t stream);
+int gnan_mlp_entries_fwd_ex(const float *val, const int64_t *grp_ptr /* [G+1] */, int64_t E, const int32_t *items, int64_t n_items,
+                            const gnan_mlp_params *p, int precision, float *Y /* [E,C] */, gnan_stream_t stream);
 int gnan_mlp_entries_bwd(const float *val, const int64_t *grp_ptr, int64_t E, int64_t max_group_entries,
                          const gnan_mlp_params *p, int precision /* backward may run on tcgen05 like gnan_mlp_bwd */,
                          const float *dY /* [E,C] */, const gnan_mlp_grads *grads, void *workspace, size_t workspace_bytes,
