@@ -483,7 +483,7 @@ def run_workload(args, env, name, *, steps, warmup, classes=0, compare_legs=Fals
                 e, no, ho, xx, yy, c = data                             # boundaries are host metadata of the loader, like the batch size
                 # fixed-width level table (48 levels; deeper batches raise the overflow flag, checked after the timed loop):
                 # no host synchronisation inside the step, so CSR build + BFS + model step replay as ONE CUDA graph
-                data = apsp_batched(e, node_off_h, device=dev, x=xx, y=yy, node_off_device=no, hop_off_device=ho, nbins=MOL_NBINS)
+                data = apsp_batched(e, node_off_h, device=dev, x=xx, y=yy, node_off_device=no, hop_off_device=ho, nbins=MOL_NBINS, rscale=True)
                 data.x_compressed = c
                 apsp_status[:] = [data.status]
             return loss_fn(model(data).flatten(), data.y)               # model(data): [B,1]

@@ -68,6 +68,12 @@ SIGNATURES = {
                                               c_void_p]),
     "gnan_aggregate_blockdiag_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int, c_int32, c_int32,
                                              c_void_p, c_void_p, c_int32, c_int, c_void_p, c_void_p]),
+    "gnan_aggregate_blockdiag_graph_supported": (c_int, [c_int32, c_int32, c_int32]),
+    "gnan_aggregate_blockdiag_graph_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_void_p, c_void_p,
+                                                   c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gnan_aggregate_blockdiag_graph_bwd_workspace_bytes": (c_size_t, [c_int32, c_int32]),
+    "gnan_aggregate_blockdiag_graph_bwd": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                   c_void_p, c_void_p, c_size_t, c_void_p]),
     "gnan_aggregate_blockdiag_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_int, c_int32, c_int32,
                                              c_void_p, c_void_p, c_int32, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gnan_build_csr_workspace_bytes": (c_size_t, [c_int32, c_int64]),
@@ -82,6 +88,8 @@ SIGNATURES = {
                                       c_void_p]),
     "gnan_apsp_bfs_batched_n": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int64, c_int64, c_void_p, c_void_p,
                                         c_int32, c_void_p, c_void_p, c_void_p]),
+    "gnan_apsp_bfs_batched_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int64, c_int64, c_void_p, c_void_p,
+                                         c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "gnan_hops_to_reference": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "gnan_hops_from_reference": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int32, c_void_p,
                                          c_void_p]),

@@ -121,15 +121,22 @@ __host__ __device__ inline size_t bv2_round16(size_t x) { return (x + 15) / 16 *
 __global__ void __launch_bounds__(256)
 apsp_batched_v2_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, const int32_t *__restrict__ node_off,
                        const int64_t *__restrict__ hop_off, int B, int max_n, int warps_per_cta, uint8_t *__restrict__ hop,
-                       int32_t *__restrict__ cnt, int nbins, int32_t *__restrict__ overflow, int32_t *__restrict__ max_level)
+                       int32_t *__restrict__ cnt, float *__restrict__ rscale, int nbins, int32_t *__restrict__ overflow,
+                       int32_t *__restrict__ max_level)
 {
     extern __shared__ __align__(16) uint8_t sm2[];
+    __shared__ float rcp_tab[256];
+    const bool levels = cnt != nullptr || rscale != nullptr;      // level sizes wanted (as counts and / or as 1/count)
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (rscale) {
+        for (int t = threadIdx.x; t < 256; t += blockDim.x) rcp_tab[t] = t > 0 ? 1.0f / (float)t : 0.f;   // as level_rscale_kernel
+        __syncthreads();
+    }
     if (w >= warps_per_cta) return;
     const int Wmax = (max_n + 31) / 32;
     const size_t hop_bytes = bv2_round16((size_t)max_n * max_n + 16);
     const size_t fr_bytes = bv2_round16((size_t)2 * max_n * Wmax * 4);        // keeps every warp's slice 16-byte aligned
-    const size_t cnt_bytes = cnt ? bv2_round16((size_t)max_n * nbins) : 0;
+    const size_t cnt_bytes = levels ? bv2_round16((size_t)max_n * nbins) : 0;
     uint8_t *wbase = sm2 + (size_t)w * (hop_bytes + fr_bytes + cnt_bytes);
     uint32_t *frs = reinterpret_cast<uint32_t *>(wbase + hop_bytes);          // [2][n][W]
     uint8_t *cs = wbase + hop_bytes + fr_bytes;                               // [n][nbins] level counts
@@ -146,7 +153,7 @@ apsp_batched_v2_kernel(const int32_t *__restrict__ rowptr, const int32_t *__rest
         __syncwarp();
         for (int t = lane * 16; t < total + 16; t += 512)
             *reinterpret_cast<uint4 *>(wbase + t) = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-        if (cnt)
+        if (levels)
             for (int t = lane * 16; t < n * nbins; t += 512) *reinterpret_cast<uint4 *>(cs + t) = make_uint4(0u, 0u, 0u, 0u);
         uint32_t vis[BV2_W][BV2_W];
         int e0[BV2_W], e1[BV2_W];
@@ -172,7 +179,7 @@ apsp_batched_v2_kernel(const int32_t *__restrict__ rowptr, const int32_t *__rest
             const int v = lane + 32 * k;
             if (v < n) {
                 hb[v * n + v] = 0;
-                if (cnt) cs[v * nbins] = 1;
+                if (levels) cs[v * nbins] = 1;
             }
         }
         for (int level = 1; level <= n; ++level) {
@@ -211,7 +218,7 @@ apsp_batched_v2_kernel(const int32_t *__restrict__ rowptr, const int32_t *__rest
                     if (newc) {
                         any = true;
                         if (level > 254 || level >= nbins - 1) atomicExch(overflow, 1);
-                        else if (cnt) cs[v * nbins + level] = (uint8_t)newc;
+                        else if (levels) cs[v * nbins + level] = (uint8_t)newc;
                     }
                 }
             }
@@ -219,7 +226,7 @@ apsp_batched_v2_kernel(const int32_t *__restrict__ rowptr, const int32_t *__rest
             if (!__any_sync(0xffffffffu, any)) break;
             lvl_max = max(lvl_max, level);
         }
-        if (cnt) {
+        if (levels) {
 #pragma unroll
             for (int k = 0; k < BV2_W; ++k) {
                 const int v = lane + 32 * k;
@@ -231,8 +238,14 @@ apsp_batched_v2_kernel(const int32_t *__restrict__ rowptr, const int32_t *__rest
                 }
             }
             __syncwarp();
-            int32_t *gc = cnt + (int64_t)n0 * nbins;                          // the graph's [n][nbins] block is contiguous
-            for (int t = lane; t < n * nbins; t += 32) gc[t] = cs[t];
+            if (cnt) {
+                int32_t *gc = cnt + (int64_t)n0 * nbins;                      // the graph's [n][nbins] block is contiguous
+                for (int t = lane; t < n * nbins; t += 32) gc[t] = cs[t];
+            }
+            if (rscale) {                                                      // 1/count (0 for empty levels): gnan_level_rscale fused
+                float *gr = rscale + (int64_t)n0 * nbins;                     // (the 256 possible quotients come from a table)
+                for (int t = lane; t < n * nbins; t += 32) gr[t] = rcp_tab[cs[t]];
+            }
         }
         __syncwarp();
         // copy out: head bytes up to the first 16-byte boundary, vector body, tail bytes
@@ -550,10 +563,24 @@ extern "C" int gnan_apsp_bfs_batched_n(const int32_t *rowptr, const int32_t *col
                                        int32_t B, int32_t max_n, int64_t total_nodes, int64_t total_hop_bytes, uint8_t *hop,
                                        int32_t *cnt, int32_t nbins, int32_t *overflow_flag, int32_t *max_level, gnan_stream_t stream)
 {
+    return gnan_apsp_bfs_batched_ex(rowptr, col, node_off, hop_off, B, max_n, total_nodes, total_hop_bytes, hop, cnt, nullptr, nbins,
+                                    overflow_flag, max_level, stream);
+}
+
+// rscale (optional): 1/count per (node, level) as fp32, what gnan_level_rscale would compute from cnt; cnt may then be NULL
+extern "C" int gnan_apsp_bfs_batched_ex(const int32_t *rowptr, const int32_t *col, const int32_t *node_off, const int64_t *hop_off,
+                                        int32_t B, int32_t max_n, int64_t total_nodes, int64_t total_hop_bytes, uint8_t *hop,
+                                        int32_t *cnt, float *rscale, int32_t nbins, int32_t *overflow_flag, int32_t *max_level,
+                                        gnan_stream_t stream)
+{
     GNAN_REQUIRE(B >= 0, "apsp_bfs_batched: negative batch");
     if (B == 0) return GNAN_OK;
     GNAN_REQUIRE(rowptr && node_off && hop_off && hop && overflow_flag, "apsp_bfs_batched: NULL pointer");
-    GNAN_REQUIRE(!cnt || (nbins >= 2 && nbins <= 256), "apsp_bfs_batched: nbins %d out of [2,256]", nbins);
+    GNAN_REQUIRE(!(cnt || rscale) || (nbins >= 2 && nbins <= 256), "apsp_bfs_batched: nbins %d out of [2,256]", nbins);
+    if (rscale && !(max_n <= 32 * BV2_W && total_nodes > 0)) {
+        gnan_set_error("apsp_bfs_batched: the fused 1/count output needs graphs of at most %d nodes and the totals", 32 * BV2_W);
+        return GNAN_ERR_UNSUPPORTED;
+    }
     if (max_n < 1 || max_n > 32 * BW_MAX) {
         gnan_set_error("apsp_bfs_batched: graphs with %d nodes unsupported (1..%d); use gnan_apsp_bfs", max_n, 32 * BW_MAX);
         return GNAN_ERR_UNSUPPORTED;
@@ -563,14 +590,14 @@ extern "C" int gnan_apsp_bfs_batched_n(const int32_t *rowptr, const int32_t *col
         // v2: hop blocks assembled in shared memory and written once (no memset of hop); only the level table is zero-filled
         const int Wmax = (max_n + 31) / 32;
         const size_t per_warp = bv2_round16((size_t)max_n * max_n + 16) + bv2_round16((size_t)2 * max_n * Wmax * 4) +
-                                (cnt ? bv2_round16((size_t)max_n * nbins) : 0);
+                                ((cnt || rscale) ? bv2_round16((size_t)max_n * nbins) : 0);
         int wpc = (int)std::min<size_t>(8, (100 * 1024) / per_warp);          // >= 2 CTAs per SM
         if (wpc < 1) wpc = 1;
         const size_t smem = per_warp * wpc;
         GNAN_CUDA(cudaFuncSetAttribute(apsp_batched_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int blocks = (int)std::min<int64_t>(ceil_div64(B, wpc), 16 * gnan_sm_count());
-        apsp_batched_v2_kernel<<<blocks, 32 * wpc, smem, st>>>(rowptr, col, node_off, hop_off, B, max_n, wpc, hop, cnt, cnt ? nbins : 256,
-                                                              overflow_flag, max_level);
+        apsp_batched_v2_kernel<<<blocks, 32 * wpc, smem, st>>>(rowptr, col, node_off, hop_off, B, max_n, wpc, hop, cnt, rscale,
+                                                              (cnt || rscale) ? nbins : 256, overflow_flag, max_level);
         GNAN_LAUNCH_OK();
         return GNAN_OK;
     }

@@ -32,20 +32,48 @@ __global__ void csr_fill_kernel(const int64_t *__restrict__ src, const int64_t *
     col[rowptr[s] + atomicAdd(cursor + s, 1)] = (int32_t)d;
 }
 
-// one warp per row: any repeated neighbour?
-__global__ void csr_duplicates_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, int32_t N,
-                                      int32_t *__restrict__ status)
+// any repeated neighbour in a row? Short rows (the bulk: molecules, citation graphs) are checked by ONE thread each; rows with
+// more than DUP_SHORT neighbours are queued and checked by a warp each in a second, persistent kernel.
+constexpr int DUP_SHORT = 16;
+__global__ void csr_duplicates_short_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, int32_t N,
+                                            int32_t *__restrict__ status, int32_t *__restrict__ queue, int32_t *__restrict__ nqueue)
+{
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= N) return;
+    const int b = rowptr[row], deg = rowptr[row + 1] - b;
+    if (deg < 2) return;
+    if (deg > DUP_SHORT) {
+        queue[atomicAdd(nqueue, 1)] = (int32_t)row;
+        return;
+    }
+    int v[DUP_SHORT];
+#pragma unroll
+    for (int p = 0; p < DUP_SHORT; ++p) v[p] = p < deg ? col[b + p] : -1 - p;      // distinct negative fillers
+    bool dup = false;
+#pragma unroll
+    for (int p = 0; p < DUP_SHORT; ++p)
+#pragma unroll
+        for (int q = p + 1; q < DUP_SHORT; ++q) dup |= v[p] == v[q];
+    if (dup) atomicOr(status, 2);
+}
+
+__global__ void csr_duplicates_long_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                           const int32_t *__restrict__ queue, const int32_t *__restrict__ nqueue,
+                                           int32_t *__restrict__ status)
 {
     const int lane = threadIdx.x & 31;
-    const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (row >= N) return;
-    const int b = rowptr[row], e = rowptr[row + 1];
-    bool dup = false;
-    for (int p = b; p < e && !dup; ++p) {
-        const int v = col[p];
-        for (int q = p + 1 + lane; q < e; q += 32) dup |= col[q] == v;
+    const int nq = *nqueue;
+    const int nw = (int)((gridDim.x * blockDim.x) >> 5);
+    for (int w = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5); w < nq; w += nw) {
+        const int row = queue[w];
+        const int b = rowptr[row], e = rowptr[row + 1];
+        bool dup = false;
+        for (int p = b; p < e && !dup; ++p) {
+            const int v = col[p];
+            for (int q = p + 1 + lane; q < e; q += 32) dup |= col[q] == v;
+        }
+        if (__any_sync(0xffffffffu, dup) && lane == 0) atomicOr(status, 2);
     }
-    if (__any_sync(0xffffffffu, dup) && lane == 0) atomicOr(status, 2);
 }
 
 }  // namespace
@@ -85,7 +113,10 @@ extern "C" int gnan_build_csr(const int64_t *src, const int64_t *dst, int64_t E,
     if (E) {
         csr_fill_kernel<<<(unsigned)ceil_div64(E, 256), 256, 0, st>>>(src, dst, E, N, rowptr, cursor, col);
         GNAN_LAUNCH_OK();
-        csr_duplicates_kernel<<<(unsigned)ceil_div64((int64_t)N * 32, 256), 256, 0, st>>>(rowptr, col, N, status);
+        // deg[] is free after the scan: it becomes the queue of long rows; cursor[N] (never touched by the fill) is its length
+        csr_duplicates_short_kernel<<<(unsigned)ceil_div64(N, 256), 256, 0, st>>>(rowptr, col, N, status, deg, cursor + N);
+        GNAN_LAUNCH_OK();
+        csr_duplicates_long_kernel<<<2 * gnan_sm_count(), 256, 0, st>>>(rowptr, col, deg, cursor + N, status);
         GNAN_LAUNCH_OK();
     }
     return GNAN_OK;

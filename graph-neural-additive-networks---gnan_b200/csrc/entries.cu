@@ -138,6 +138,34 @@ __global__ void gather_segment_sum_kernel(const float *__restrict__ src, const i
     if (lane == 0) out[w] = s;
 }
 
+// few, long segments (one-hot columns: a handful of distinct values shared by millions of entries): one CTA per (segment,
+// channel), fixed thread-strided partial sums + a fixed tree -> still deterministic
+__global__ void __launch_bounds__(512)
+gather_segment_sum_block_kernel(const float *__restrict__ src, const int64_t *__restrict__ order, const int64_t *__restrict__ seg_ptr,
+                                int C, float *__restrict__ out)
+{
+    __shared__ float red[512];
+    const int64_t sg = blockIdx.x / C;
+    const int c = (int)(blockIdx.x % C);
+    const int64_t k0 = seg_ptr[sg], k1 = seg_ptr[sg + 1];
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int64_t k = k0 + threadIdx.x;
+    for (; k + 3 * 512 < k1; k += 4 * 512) {
+        s0 += src[(order ? order[k] : k) * C + c];
+        s1 += src[(order ? order[k + 512] : k + 512) * C + c];
+        s2 += src[(order ? order[k + 1024] : k + 1024) * C + c];
+        s3 += src[(order ? order[k + 1536] : k + 1536) * C + c];
+    }
+    for (; k < k1; k += 512) s0 += src[(order ? order[k] : k) * C + c];
+    red[threadIdx.x] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    for (int w = 256; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = red[0];
+}
+
 }  // namespace
 
 extern "C" int gnan_gather_segment_sum(const float *src, const int64_t *order, const int64_t *seg_ptr, int64_t nseg, int32_t C,
@@ -146,7 +174,11 @@ extern "C" int gnan_gather_segment_sum(const float *src, const int64_t *order, c
     GNAN_REQUIRE(nseg >= 0 && C >= 1, "gather_segment_sum: bad sizes");
     if (nseg == 0) return GNAN_OK;
     GNAN_REQUIRE(src && seg_ptr && out, "gather_segment_sum: NULL pointer");
-    gather_segment_sum_kernel<<<(unsigned)ceil_div64(nseg * C * 32, 256), 256, 0, (cudaStream_t)stream>>>(src, order, seg_ptr, nseg, C, out);
+    // a warp per (segment, channel) starves the GPU when there are only a few (then necessarily long) segments
+    if (nseg * C <= 2 * gnan_sm_count())
+        gather_segment_sum_block_kernel<<<(unsigned)(nseg * C), 512, 0, (cudaStream_t)stream>>>(src, order, seg_ptr, C, out);
+    else
+        gather_segment_sum_kernel<<<(unsigned)ceil_div64(nseg * C * 32, 256), 256, 0, (cudaStream_t)stream>>>(src, order, seg_ptr, nseg, C, out);
     GNAN_LAUNCH_OK();
     return GNAN_OK;
 }

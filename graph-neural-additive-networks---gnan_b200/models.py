@@ -97,7 +97,9 @@ class TensorGNAN(_Base):
             pk = pk.to(dev)
         S = self._per_feature(pk.x.float().contiguous()) if self._readout else self._feature_sums(*self._features(pk))
         T = self._table(ops.rho_table_inputs(pk.nbins, dev))
-        rs = ops.level_rscale(pk.level_counts) if self.normalize_rho else None
+        rs = None
+        if self.normalize_rho:       # models.py:368-370; a batch straight from apsp_batched(..., rscale=True) carries it already
+            rs = pk.level_rscale if getattr(pk, "level_rscale", None) is not None else ops.level_rscale(pk.level_counts)
         out = ops.aggregate_blockdiag(pk.hop, pk.hop_off, pk.node_off, T, S, rscale=rs, reduce_graph=self.is_graph_task)
         return self.readout_nam(out) if self._readout else out                       # [B,K] -> [B,C]
 

@@ -333,7 +333,78 @@ def _bd_backward(ctx, g):
 agg_blockdiag_fwd.register_autograd(_bd_backward, setup_context=_bd_setup)
 
 
+# graph-level readout with a global table: one pass over the hop bytes for forward AND backward (csrc/agg_bd.cu)
+@torch.library.custom_op("gnan_b200::agg_bd_graph_fwd", mutates_args=())
+def agg_bd_graph_fwd(hop: Tensor, hop_off: Tensor, node_off: Tensor, T: Tensor, rscale: Optional[Tensor],
+                     S: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    lib = load()
+    T, S = _f32(T, "T"), _f32(S, "S")
+    rscale = None if rscale is None else _f32(rscale, "rscale")
+    if hop.dtype != torch.uint8 or hop_off.dtype != torch.int64 or node_off.dtype != torch.int32:
+        raise TypeError("hop uint8, hop_off int64, node_off int32 expected")
+    B = node_off.numel() - 1
+    N, C = S.shape
+    nbins, Cr = T.shape
+    if rscale is not None and tuple(rscale.shape) != (N, nbins):
+        raise ValueError(f"rscale must be [{N},{nbins}], got {tuple(rscale.shape)}")
+    out = torch.empty(B, C, dtype=torch.float32, device=S.device)
+    colw = torch.empty(N, Cr, dtype=torch.float32, device=S.device)
+    Q = torch.empty(B, nbins, C, dtype=torch.float32, device=S.device)
+    counter = torch.empty(1, dtype=torch.int32, device=S.device)
+    with _timed("aggregate_blockdiag_fwd"):
+        check(lib.gnan_aggregate_blockdiag_graph_fwd(ptr(hop), ptr(hop_off), ptr(node_off), B, ptr(T), nbins, Cr, ptr(rscale), ptr(S), C,
+                                                     ptr(out), ptr(colw), ptr(Q), ptr(counter), stream_handle()),
+              "gnan_aggregate_blockdiag_graph_fwd")
+    return out, colw, Q
+
+
+@agg_bd_graph_fwd.register_fake
+def _(hop, hop_off, node_off, T, rscale, S):
+    B = node_off.numel() - 1
+    return S.new_empty(B, S.shape[1]), S.new_empty(S.shape[0], T.shape[1]), S.new_empty(B, T.shape[0], S.shape[1])
+
+
+@torch.library.custom_op("gnan_b200::agg_bd_graph_bwd", mutates_args=())
+def agg_bd_graph_bwd(node_off: Tensor, g: Tensor, colw: Tensor, Q: Tensor) -> Tuple[Tensor, Tensor]:
+    lib = load()
+    g = _f32(g, "g")
+    B, nbins, C = Q.shape
+    N, Cr = colw.shape
+    dS = torch.empty(N, C, dtype=torch.float32, device=g.device)
+    dT = torch.empty(nbins, Cr, dtype=torch.float32, device=g.device)
+    ws = _ws(lib.gnan_aggregate_blockdiag_graph_bwd_workspace_bytes(nbins, C), g.device)
+    with _timed("aggregate_blockdiag_bwd"):
+        check(lib.gnan_aggregate_blockdiag_graph_bwd(ptr(node_off), B, nbins, Cr, C, ptr(g), ptr(colw), ptr(Q), ptr(dS), ptr(dT), ptr(ws),
+                                                     ws.numel(), stream_handle()), "gnan_aggregate_blockdiag_graph_bwd")
+    return dS, dT
+
+
+@agg_bd_graph_bwd.register_fake
+def _(node_off, g, colw, Q):
+    return g.new_empty(colw.shape[0], Q.shape[2]), g.new_empty(Q.shape[1], colw.shape[1])
+
+
+def _bdg_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[2], output[1], output[2])
+
+
+def _bdg_backward(ctx, g, _g_colw, _g_q):
+    node_off, colw, Q = ctx.saved_tensors
+    dS, dT = agg_bd_graph_bwd(node_off, g.contiguous(), colw, Q)
+    return None, None, None, dT, None, dS
+
+
+agg_bd_graph_fwd.register_autograd(_bdg_backward, setup_context=_bdg_setup)
+
+BLOCKDIAG_GRAPH_KERNEL = True     # tests switch it off to compare the two kernel families
+
+
 def aggregate_blockdiag(hop, hop_off, node_off, T, S, rscale=None, per_row=False, reduce_graph=True):
+    """Block-diagonal aggregation of a packed batch; see gnan_b200.h. A per-graph readout with a global table takes the one-pass
+    kernels of csrc/agg_bd.cu (forward statistics reused by the backward), everything else the general kernels."""
+    if (BLOCKDIAG_GRAPH_KERNEL and reduce_graph and not per_row and T.dim() == 2
+            and load().gnan_aggregate_blockdiag_graph_supported(T.shape[0], T.shape[1], S.shape[1])):
+        return agg_bd_graph_fwd(hop, hop_off, node_off, T, rscale, S)[0]
     return agg_blockdiag_fwd(hop, hop_off, node_off, T, rscale, S, bool(per_row), bool(reduce_graph))
 
 

@@ -195,9 +195,12 @@ class PackedBatch:
     hop_off int64 [B+1], level_counts int32 [sumN,nbins], batch_vector int64 [sumN] (kept for API parity), y.
     """
 
-    def __init__(self, x, hop, hop_off, node_off, level_counts, y=None, max_nodes=None):
+    def __init__(self, x, hop, hop_off, node_off, level_counts, y=None, max_nodes=None, level_rscale=None):
         self.x, self.hop, self.hop_off, self.node_off, self.level_counts, self.y = x, hop, hop_off, node_off, level_counts, y
         self.max_nodes = max_nodes
+        # optional fp32 [sumN,nbins] 1/level_counts (0 for empty levels), written by the batched BFS itself
+        # (apsp_batched(..., rscale=True)); level_counts may then be None
+        self.level_rscale = level_rscale
 
     @property
     def num_graphs(self):
@@ -205,7 +208,7 @@ class PackedBatch:
 
     @property
     def nbins(self):
-        return self.level_counts.shape[1]
+        return (self.level_counts if self.level_counts is not None else self.level_rscale).shape[1]
 
     @property
     def batch_vector(self):
@@ -215,12 +218,12 @@ class PackedBatch:
     def to(self, device):
         mv = lambda t: None if t is None else t.to(device, non_blocking=True)
         return PackedBatch(mv(self.x), mv(self.hop), mv(self.hop_off), mv(self.node_off), mv(self.level_counts), mv(self.y),
-                           self.max_nodes)
+                           self.max_nodes, mv(self.level_rscale))
 
     def pin_memory(self):
         pm = lambda t: None if t is None else t.pin_memory()
         return PackedBatch(pm(self.x), pm(self.hop), pm(self.hop_off), pm(self.node_off), pm(self.level_counts), pm(self.y),
-                           self.max_nodes)
+                           self.max_nodes, pm(self.level_rscale))
 
 
 def check_batched_status(status):
@@ -235,7 +238,7 @@ def check_batched_status(status):
 
 
 def apsp_batched(edge_index, node_off, device="cuda", x=None, y=None, node_off_device=None, _level_table_width=48, nbins=None,
-                 hop_off_device=None):
+                 hop_off_device=None, rscale=False):
     """Hop blocks of B small graphs (<= 256 nodes each) in one launch. edge_index uses GLOBAL node ids of the
     concatenated node set; node_off [B+1] are the graph boundaries.
 
@@ -244,6 +247,9 @@ def apsp_batched(edge_index, node_off, device="cuda", x=None, y=None, node_off_d
     contribute nothing. The returned batch has `.status` (device int32 [3]: CSR status, overflow flag, largest hop) to be
     checked lazily with check_batched_status. hop_off_device: optional int64 device copy of the block offsets
     (cumsum of n_b^2, B+1 entries; with node_off_device it removes every host -> device copy from the call).
+    rscale=True (fixed-width mode, graphs of at most 128 nodes): the BFS writes the output normaliser 1/level_counts
+    (`PackedBatch.level_rscale`, fp32) INSTEAD of the int32 level counts, which the output-normalised models
+    (models.TensorGNAN, normalize_rho=True) consume directly: one table written, none converted.
 
     Pass node_off as a HOST tensor / array (what a data loader has): block sizes and offsets are then computed on the host
     and the call synchronises exactly once, at the end (overflow flag + largest hop, which sizes the level table).
@@ -275,6 +281,17 @@ def apsp_batched(edge_index, node_off, device="cuda", x=None, y=None, node_off_d
     nb = min(nb_full, _level_table_width) if _level_table_width else nb_full
     if nbins is not None:
         nb = int(nbins)
+    if rscale:
+        if nbins is None or max_n > 128 or sumN == 0:
+            raise ValueError("rscale=True needs the fixed-width mode (nbins=...) and graphs of at most 128 nodes")
+        rs = torch.empty(sumN, nb, dtype=torch.float32, device=device)
+        with _timed("apsp_bfs_batched"):
+            check(lib.gnan_apsp_bfs_batched_ex(ptr(rowptr), ptr(col), ptr(node_off_d), ptr(hop_off), B, max_n, sumN, total, ptr(hop), None,
+                                               ptr(rs), nb, st.data_ptr() + 4, st.data_ptr() + 8, stream_handle()),
+                  "gnan_apsp_bfs_batched_ex")
+        pk = PackedBatch(x, hop, hop_off, node_off_d, None, y, max_n, level_rscale=rs)
+        pk.status = st
+        return pk
     cnt = torch.empty(sumN, nb, dtype=torch.int32, device=device)
     with _timed("apsp_bfs_batched"):
         check(lib.gnan_apsp_bfs_batched_n(ptr(rowptr), ptr(col), ptr(node_off_d), ptr(hop_off), B, max_n, sumN, total, ptr(hop), ptr(cnt), nb,

@@ -224,6 +224,23 @@ int gnan_aggregate_blockdiag_bwd(const uint8_t *hop, const int64_t *hop_off, con
                                  float *dT /* zero-initialised by the callee; global table grads are atomically added */,
                                  gnan_stream_t stream);
 
+/* Graph-level readout with a GLOBAL table (models.py:366-384 / GNAN.py:64-79 with is_graph_task; batched_pyg_main.py:154-181),
+ * csrc/agg_bd.cu: out[b,c] = sum_{i,j in b} T[d_ij,c'] rscale[i,d_ij] S[j,c] is bilinear in (T,S) given the pair statistics
+ * P[j,d] = sum_{i: d_ij = d} rscale[i,d]. The forward makes the ONLY pass over the hop bytes and saves
+ * colw[j,c'] = sum_d T[d,c'] P[j,d] ([sumN,Cr]) and Q[b,d,c] = sum_j S[j,c] P[j,d] ([B,nbins,C]); the backward is
+ * dS[j,c] = g[b,c] colw[j,c'], dT[d,c'] = sum_{b,c} g[b,c] Q[b,d,c] (both overwritten), without touching the hop bytes.
+ * Covers nbins <= 64, C <= 4 (see _supported); work_counter: one device int32 (zeroed by the callee; graphs are handed out
+ * to the warps dynamically). Deterministic. */
+int gnan_aggregate_blockdiag_graph_supported(int32_t nbins, int32_t Cr, int32_t C);
+int gnan_aggregate_blockdiag_graph_fwd(const uint8_t *hop, const int64_t *hop_off, const int32_t *node_off, int32_t B,
+                                       const float *T /* [nbins,Cr] */, int32_t nbins, int32_t Cr,
+                                       const float *rscale /* [sumN,nbins] or NULL */, const float *S, int32_t C,
+                                       float *out /* [B,C] */, float *colw, float *Q, int32_t *work_counter, gnan_stream_t stream);
+size_t gnan_aggregate_blockdiag_graph_bwd_workspace_bytes(int32_t nbins, int32_t C);
+int gnan_aggregate_blockdiag_graph_bwd(const int32_t *node_off, int32_t B, int32_t nbins, int32_t Cr, int32_t C,
+                                       const float *g /* [B,C] */, const float *colw, const float *Q, float *dS, float *dT,
+                                       void *workspace, size_t workspace_bytes, gnan_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * All-pairs hop distances (replaces scipy dijkstra + the per-element normaliser loop,
  * pre_process_datasets.py:109-121,128-140; networkx BFS of batched_pyg_main.py:36-44).
@@ -267,6 +284,13 @@ int gnan_apsp_bfs_batched(const int32_t *rowptr /* [sumN+1] */, const int32_t *c
 int gnan_apsp_bfs_batched_n(const int32_t *rowptr, const int32_t *col, const int32_t *node_off, const int64_t *hop_off,
                             int32_t B, int32_t max_n, int64_t total_nodes, int64_t total_hop_bytes, uint8_t *hop, int32_t *cnt,
                             int32_t nbins, int32_t *overflow_flag, int32_t *max_level, gnan_stream_t stream);
+
+/* same, with an optional fused normaliser output: rscale [sumN,nbins] fp32 = 1/count (0 for an empty level), i.e. what
+ * gnan_level_rscale computes from cnt (models.py:368-370 divides by the level size); cnt may then be NULL. Needs the totals
+ * and graphs of at most 128 nodes. */
+int gnan_apsp_bfs_batched_ex(const int32_t *rowptr, const int32_t *col, const int32_t *node_off, const int64_t *hop_off,
+                             int32_t B, int32_t max_n, int64_t total_nodes, int64_t total_hop_bytes, uint8_t *hop, int32_t *cnt,
+                             float *rscale, int32_t nbins, int32_t *overflow_flag, int32_t *max_level, gnan_stream_t stream);
 
 /* reference-format converters (pre_process_datasets.py:112-121): fp32 node_distances / normalization_matrix <-> hops */
 int gnan_hops_to_reference(const uint8_t *hop, int64_t R, int64_t N, int64_t ld_hop, const int32_t *cnt, int32_t nbins,
