@@ -38,21 +38,38 @@ struct BdgArgs {
     int32_t *next;      // work counter (graphs are handed out dynamically: their cost varies like n^2)
 };
 
-template <int CC>
+__device__ __forceinline__ float lds_f32(uint32_t a)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_v4(uint32_t a, float4 v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// VEC: the normaliser rows are staged with 16-byte loads (nbins % 4 == 0), else element by element.
+// The pair loop is branch free: rows past the end of the graph read zero normaliser rows, columns past the end add 0, and
+// the hop bytes + normaliser rows of row block k+1 are in flight (registers) while block k updates the bins.
+template <int CC, bool VEC>
 __global__ void __launch_bounds__(BDG_WARPS * 32)
 agg_bd_graph_fwd_kernel(BdgArgs a)
 {
     extern __shared__ __align__(16) float bdg_sm[];
+    constexpr int NPF = VEC ? BDG_RB * BDG_MAX_NBINS / 128 : BDG_RB * BDG_MAX_NBINS / 32;     // prefetch registers (float4 / float)
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int nb = a.nbins, nb1 = nb - 1;
     const int nT = nb * a.Cr, nT4 = (nT + 3) & ~3;
     float *sT = bdg_sm;                                               // [nbins*Cr] table copy, CTA wide
     float *P = bdg_sm + nT4 + (size_t)w * (nb * 32 + BDG_RB * nb);    // [nbins][32] lane-private bins of this warp
     float *rs = P + nb * 32;                                          // [RB][nbins] normaliser rows of the current row block
+    const uint32_t Pa = (uint32_t)__cvta_generic_to_shared(P) + 4u * lane, rsa = (uint32_t)__cvta_generic_to_shared(rs);
     for (int t = threadIdx.x; t < nT; t += blockDim.x) sT[t] = a.T[t];
     for (int d = 0; d < nb; ++d) P[d * 32 + lane] = 0.f;
     __syncthreads();
-    const bool vec4 = (nb & 3) == 0;
+    const int rsn = BDG_RB * nb;                                      // floats per staged block
     for (;;) {
         int b = 0;
         if (lane == 0) b = atomicAdd(a.next, 1);
@@ -68,34 +85,71 @@ agg_bd_graph_fwd_kernel(BdgArgs a)
         for (int jq = 0; jq < n; jq += 32) {
             const int j = jq + lane;
             const bool jv = j < n;
+            const float jvf = jv ? 1.f : 0.f;
+            const uint8_t *hp = hb + (jv ? j : 0);                   // hop column of this lane (any valid column when past the end)
             float sown[CC];
 #pragma unroll
             for (int c = 0; c < CC; ++c) sown[c] = (jv && c < a.C) ? a.S[(int64_t)(n0 + j) * a.C + c] : 0.f;
             int dmax = 0;
+            int hN[BDG_RB];
+            float4 rN4[VEC ? NPF : 1];
+            float rN1[VEC ? 1 : NPF];
+            auto prefetch = [&](int i0) {
+#pragma unroll
+                for (int u = 0; u < BDG_RB; ++u) hN[u] = i0 + u < n ? (int)hp[(i0 + u) * n] : 0;
+                if (rg) {
+                    const int e0 = i0 * nb;
+                    if (VEC) {
+#pragma unroll
+                        for (int k = 0; k < NPF; ++k) {
+                            const int e = lane * 4 + 128 * k;
+                            rN4[k] = (e < rsn && e0 + e < rtot) ? *reinterpret_cast<const float4 *>(rg + e0 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < NPF; ++k) {
+                            const int e = lane + 32 * k;
+                            rN1[k] = (e < rsn && e0 + e < rtot) ? rg[e0 + e] : 0.f;
+                        }
+                    }
+                }
+            };
+            prefetch(0);
             for (int i0 = 0; i0 < n; i0 += BDG_RB) {
                 int h[BDG_RB];
 #pragma unroll
-                for (int u = 0; u < BDG_RB; ++u) h[u] = (jv && i0 + u < n) ? (int)hb[(size_t)(i0 + u) * n + j] : -1;
-                if (rg) {                                             // rows i0..i0+RB-1 of the normaliser: contiguous in memory
-                    const int e0 = i0 * nb;
-                    if (vec4) {
-                        for (int e = lane * 4; e < BDG_RB * nb; e += 128) {
-                            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (e0 + e < rtot) v = *reinterpret_cast<const float4 *>(rg + e0 + e);
-                            *reinterpret_cast<float4 *>(rs + e) = v;
-                        }
+                for (int u = 0; u < BDG_RB; ++u) h[u] = hN[u];
+                if (rg) {
+                    if (VEC) {
+#pragma unroll
+                        for (int k = 0; k < NPF; ++k)
+                            if (lane * 4 + 128 * k < rsn) sts_v4(rsa + 16u * lane + 512u * k, rN4[k]);
                     } else {
-                        for (int e = lane; e < BDG_RB * nb; e += 32) rs[e] = e0 + e < rtot ? rg[e0 + e] : 0.f;
+#pragma unroll
+                        for (int k = 0; k < NPF; ++k)
+                            if (lane + 32 * k < rsn) sts_f32(rsa + 4u * lane + 128u * k, rN1[k]);
                     }
                     __syncwarp();
                 }
+                if (i0 + BDG_RB < n) prefetch(i0 + BDG_RB);
+                int d[BDG_RB];
+                float v[BDG_RB];
 #pragma unroll
                 for (int u = 0; u < BDG_RB; ++u) {
-                    if (h[u] >= 0) {
-                        const int d = min(h[u], nb1);
-                        dmax = max(dmax, d);
-                        P[d * 32 + lane] += rg ? rs[u * nb + d] : 1.f;
-                    }
+                    d[u] = min(h[u], nb1);
+                    dmax = max(dmax, d[u]);
+                    // rows past the end: zero normaliser row (or 0 without a normaliser); columns past the end: * 0
+                    v[u] = (rg ? rs[u * nb + d[u]] : (i0 + u < n ? 1.f : 0.f)) * jvf;
+                }
+                // bins are read-modify-written two rows at a time (both loads in flight; equal bins are chained in registers)
+#pragma unroll
+                for (int u = 0; u < BDG_RB; u += 2) {
+                    const uint32_t pa0 = Pa + 128u * (uint32_t)d[u], pa1 = Pa + 128u * (uint32_t)d[u + 1];
+                    const float p0 = lds_f32(pa0), p1 = lds_f32(pa1);
+                    const float n0v = p0 + v[u];
+                    const float n1v = (d[u + 1] == d[u] ? n0v : p1) + v[u + 1];
+                    sts_f32(pa0, n0v);
+                    sts_f32(pa1, n1v);
                 }
                 if (rg) __syncwarp();
             }
@@ -111,6 +165,7 @@ agg_bd_graph_fwd_kernel(BdgArgs a)
             // (bank (l + t) % 32: conflict free)
             const bool hi = dm >= 32;
             __syncwarp();
+#pragma unroll 4
             for (int l = 0; l < 32; ++l) {
                 const int jj = (l + lane) & 31;
                 const float p0 = lane <= dm ? P[lane * 32 + jj] : 0.f;
@@ -245,9 +300,10 @@ extern "C" int gnan_aggregate_blockdiag_graph_fwd(const uint8_t *hop, const int6
         GNAN_LAUNCH_OK();
         return GNAN_OK;
     };
-    if (C == 1) return launch(agg_bd_graph_fwd_kernel<1>);
-    if (C == 2) return launch(agg_bd_graph_fwd_kernel<2>);
-    return launch(agg_bd_graph_fwd_kernel<4>);
+    const bool vec = (nbins & 3) == 0;
+    if (C == 1) return vec ? launch(agg_bd_graph_fwd_kernel<1, true>) : launch(agg_bd_graph_fwd_kernel<1, false>);
+    if (C == 2) return vec ? launch(agg_bd_graph_fwd_kernel<2, true>) : launch(agg_bd_graph_fwd_kernel<2, false>);
+    return vec ? launch(agg_bd_graph_fwd_kernel<4, true>) : launch(agg_bd_graph_fwd_kernel<4, false>);
 }
 
 extern "C" size_t gnan_aggregate_blockdiag_graph_bwd_workspace_bytes(int32_t nbins, int32_t C)

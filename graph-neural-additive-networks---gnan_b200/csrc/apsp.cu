@@ -118,7 +118,124 @@ apsp_batched_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restric
 constexpr int BV2_W = 4;   // up to 128 nodes per graph
 __host__ __device__ inline size_t bv2_round16(size_t x) { return (x + 15) / 16 * 16; }
 
-__global__ void __launch_bounds__(256)
+// One graph on one warp, W = ceil(n/32) known at compile time (exact unrolling: a 20-node graph does 1/16 of the word work of
+// a 128-node one). Up to 8 neighbours of a vertex are cached as local-index bytes in two registers (no global load inside
+// the level loop; longer rows read the rest from the CSR), and the hop bytes of a level are scattered two bits per step
+// (lowest and highest new source).
+template <int W>
+__device__ __forceinline__ int bv2_graph(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, int n0, int n, int lane,
+                                         uint8_t *hb, uint32_t *frs, uint8_t *cs, int nbins, bool levels, int32_t *overflow)
+{
+    uint32_t vis[W][W], nb_lo[W], nb_hi[W];
+    int dg[W], e8[W], e1[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+        const int v = lane + 32 * k;
+        dg[k] = 0; e8[k] = e1[k] = 0;
+        nb_lo[k] = nb_hi[k] = 0xffffffffu;
+#pragma unroll
+        for (int ww = 0; ww < W; ++ww) vis[k][ww] = 0u;
+        if (v < n) {
+            const int eb = rowptr[n0 + v], ee = rowptr[n0 + v + 1];
+            int e = eb;
+            for (; e < ee && dg[k] < 8; ++e) {                      // neighbours outside the graph are ignored (as the CSR walk did)
+                const int u = __ldg(col + e) - n0;
+                if (u >= 0 && u < n) {
+                    const int sh = 8 * (dg[k] & 3);
+                    if (dg[k] < 4) nb_lo[k] = (nb_lo[k] & ~(0xffu << sh)) | ((uint32_t)u << sh);
+                    else nb_hi[k] = (nb_hi[k] & ~(0xffu << sh)) | ((uint32_t)u << sh);
+                    ++dg[k];
+                }
+            }
+            e8[k] = e; e1[k] = ee;
+#pragma unroll
+            for (int ww = 0; ww < W; ++ww) {
+                if (ww == k) vis[k][ww] = 1u << lane;
+                frs[v * W + ww] = ww == k ? 1u << lane : 0u;
+            }
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+        const int v = lane + 32 * k;
+        if (v < n) {
+            hb[v * n + v] = 0;
+            if (levels) cs[v * nbins] = 1;
+        }
+    }
+    int lvl_max = 0;
+    for (int level = 1; level <= n; ++level) {
+        const uint32_t *fc = frs + ((level - 1) & 1) * n * W;
+        uint32_t *fn = frs + (level & 1) * n * W;
+        const uint8_t lv = (uint8_t)min(level, 254);
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+            const int v = lane + 32 * k;
+            if (v < n) {
+                uint32_t acc[W];
+#pragma unroll
+                for (int ww = 0; ww < W; ++ww) acc[ww] = 0u;
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    if (t < dg[k]) {
+                        const uint32_t u = ((t < 4 ? nb_lo[k] : nb_hi[k]) >> (8 * (t & 3))) & 0xffu;
+#pragma unroll
+                        for (int ww = 0; ww < W; ++ww) acc[ww] |= fc[u * W + ww];
+                    }
+                }
+                for (int e = e8[k]; e < e1[k]; ++e) {               // rows with more than 8 neighbours
+                    const int u = __ldg(col + e) - n0;
+                    if (u >= 0 && u < n) {
+#pragma unroll
+                        for (int ww = 0; ww < W; ++ww) acc[ww] |= fc[u * W + ww];
+                    }
+                }
+                int newc = 0;
+#pragma unroll
+                for (int ww = 0; ww < W; ++ww) {
+                    const uint32_t nw = acc[ww] & ~vis[k][ww];
+                    vis[k][ww] |= nw;
+                    fn[v * W + ww] = nw;
+                    newc += __popc(nw);
+                    uint32_t m = nw;
+                    uint8_t *rowp = hb + v * n + ww * 32;
+                    while (m) {
+                        const int lo = __ffs(m) - 1, hi = 31 - __clz(m);
+                        rowp[lo] = lv;
+                        rowp[hi] = lv;
+                        m &= m - 1;
+                        m &= ~(1u << hi);
+                    }
+                }
+                if (newc) {
+                    any = true;
+                    if (level > 254 || level >= nbins - 1) atomicExch(overflow, 1);
+                    else if (levels) cs[v * nbins + level] = (uint8_t)newc;
+                }
+            }
+        }
+        __syncwarp();
+        if (!__any_sync(0xffffffffu, any)) break;
+        lvl_max = max(lvl_max, level);
+    }
+    if (levels) {
+#pragma unroll
+        for (int k = 0; k < W; ++k) {
+            const int v = lane + 32 * k;
+            if (v < n) {
+                int reached = 0;
+#pragma unroll
+                for (int ww = 0; ww < W; ++ww) reached += __popc(vis[k][ww]);
+                cs[v * nbins + nbins - 1] = (uint8_t)(n - reached);
+            }
+        }
+    }
+    return lvl_max;
+}
+
+__global__ void __launch_bounds__(512)
 apsp_batched_v2_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, const int32_t *__restrict__ node_off,
                        const int64_t *__restrict__ hop_off, int B, int max_n, int warps_per_cta, uint8_t *__restrict__ hop,
                        int32_t *__restrict__ cnt, float *__restrict__ rscale, int nbins, int32_t *__restrict__ overflow,
@@ -142,10 +259,10 @@ apsp_batched_v2_kernel(const int32_t *__restrict__ rowptr, const int32_t *__rest
     uint8_t *cs = wbase + hop_bytes + fr_bytes;                               // [n][nbins] level counts
     const int64_t warp = (int64_t)blockIdx.x * warps_per_cta + w;
     const int64_t nwarps = (int64_t)gridDim.x * warps_per_cta;
+    const bool vec_tab = (nbins & 3) == 0;
     int lvl_max = 0;
     for (int64_t b = warp; b < B; b += nwarps) {
         const int n0 = node_off[b], n = node_off[b + 1] - n0;
-        const int W = (n + 31) / 32;
         uint8_t *gb = hop + hop_off[b];
         const int pad = (int)(reinterpret_cast<uintptr_t>(gb) & 15);
         uint8_t *hb = wbase + pad;                                             // hb + k  ==  gb + k  (mod 16)
@@ -155,99 +272,40 @@ apsp_batched_v2_kernel(const int32_t *__restrict__ rowptr, const int32_t *__rest
             *reinterpret_cast<uint4 *>(wbase + t) = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
         if (levels)
             for (int t = lane * 16; t < n * nbins; t += 512) *reinterpret_cast<uint4 *>(cs + t) = make_uint4(0u, 0u, 0u, 0u);
-        uint32_t vis[BV2_W][BV2_W];
-        int e0[BV2_W], e1[BV2_W];
-#pragma unroll
-        for (int k = 0; k < BV2_W; ++k) {
-            const int v = lane + 32 * k;
-            e0[k] = e1[k] = 0;
-#pragma unroll
-            for (int ww = 0; ww < BV2_W; ++ww) vis[k][ww] = 0u;
-            if (v < n) {
-                e0[k] = rowptr[n0 + v];
-                e1[k] = rowptr[n0 + v + 1];
-#pragma unroll
-                for (int ww = 0; ww < BV2_W; ++ww) {
-                    if (ww == k) vis[k][ww] = 1u << lane;
-                    if (ww < W) frs[v * W + ww] = ww == k ? 1u << lane : 0u;
-                }
-            }
-        }
         __syncwarp();
-#pragma unroll
-        for (int k = 0; k < BV2_W; ++k) {
-            const int v = lane + 32 * k;
-            if (v < n) {
-                hb[v * n + v] = 0;
-                if (levels) cs[v * nbins] = 1;
-            }
-        }
-        for (int level = 1; level <= n; ++level) {
-            const uint32_t *fc = frs + ((level - 1) & 1) * n * W;
-            uint32_t *fn = frs + (level & 1) * n * W;
-            bool any = false;
-#pragma unroll
-            for (int k = 0; k < BV2_W; ++k) {
-                const int v = lane + 32 * k;
-                if (v < n) {
-                    uint32_t acc[BV2_W];
-#pragma unroll
-                    for (int ww = 0; ww < BV2_W; ++ww) acc[ww] = 0u;
-                    for (int e = e0[k]; e < e1[k]; ++e) {
-                        const int u = __ldg(col + e) - n0;
-                        if (u >= 0 && u < n) {
-#pragma unroll
-                            for (int ww = 0; ww < BV2_W; ++ww)
-                                if (ww < W) acc[ww] |= fc[u * W + ww];
-                        }
-                    }
-                    int newc = 0;
-#pragma unroll
-                    for (int ww = 0; ww < BV2_W; ++ww) {
-                        const uint32_t nw = acc[ww] & ~vis[k][ww];
-                        vis[k][ww] |= nw;
-                        if (ww < W) fn[v * W + ww] = nw;
-                        newc += __popc(nw);
-                        uint32_t m = nw;
-                        const uint8_t lv = (uint8_t)min(level, 254);
-                        while (m) {
-                            hb[v * n + ww * 32 + __ffs(m) - 1] = lv;
-                            m &= m - 1;
-                        }
-                    }
-                    if (newc) {
-                        any = true;
-                        if (level > 254 || level >= nbins - 1) atomicExch(overflow, 1);
-                        else if (levels) cs[v * nbins + level] = (uint8_t)newc;
-                    }
-                }
-            }
-            __syncwarp();
-            if (!__any_sync(0xffffffffu, any)) break;
-            lvl_max = max(lvl_max, level);
-        }
+        int lm;
+        if (n <= 32) lm = bv2_graph<1>(rowptr, col, n0, n, lane, hb, frs, cs, nbins, levels, overflow);
+        else if (n <= 64) lm = bv2_graph<2>(rowptr, col, n0, n, lane, hb, frs, cs, nbins, levels, overflow);
+        else if (n <= 96) lm = bv2_graph<3>(rowptr, col, n0, n, lane, hb, frs, cs, nbins, levels, overflow);
+        else lm = bv2_graph<4>(rowptr, col, n0, n, lane, hb, frs, cs, nbins, levels, overflow);
+        lvl_max = max(lvl_max, lm);
+        __syncwarp();
         if (levels) {
-#pragma unroll
-            for (int k = 0; k < BV2_W; ++k) {
-                const int v = lane + 32 * k;
-                if (v < n) {
-                    int reached = 0;
-#pragma unroll
-                    for (int ww = 0; ww < BV2_W; ++ww) reached += __popc(vis[k][ww]);
-                    cs[v * nbins + nbins - 1] = (uint8_t)(n - reached);
+            const int nt = n * nbins;                                         // the graph's [n][nbins] block is contiguous
+            if (cnt) {
+                int32_t *gc = cnt + (int64_t)n0 * nbins;
+                if (vec_tab) {
+                    for (int t = lane * 4; t < nt; t += 128) {
+                        const uint32_t c4 = *reinterpret_cast<const uint32_t *>(cs + t);
+                        *reinterpret_cast<int4 *>(gc + t) = make_int4(c4 & 0xff, (c4 >> 8) & 0xff, (c4 >> 16) & 0xff, c4 >> 24);
+                    }
+                } else {
+                    for (int t = lane; t < nt; t += 32) gc[t] = cs[t];
                 }
             }
-            __syncwarp();
-            if (cnt) {
-                int32_t *gc = cnt + (int64_t)n0 * nbins;                      // the graph's [n][nbins] block is contiguous
-                for (int t = lane; t < n * nbins; t += 32) gc[t] = cs[t];
-            }
-            if (rscale) {                                                      // 1/count (0 for empty levels): gnan_level_rscale fused
-                float *gr = rscale + (int64_t)n0 * nbins;                     // (the 256 possible quotients come from a table)
-                for (int t = lane; t < n * nbins; t += 32) gr[t] = rcp_tab[cs[t]];
+            if (rscale) {                       // 1/count (0 for empty levels): gnan_level_rscale fused; the 256 possible quotients come from a table
+                float *gr = rscale + (int64_t)n0 * nbins;
+                if (vec_tab) {
+                    for (int t = lane * 4; t < nt; t += 128) {
+                        const uint32_t c4 = *reinterpret_cast<const uint32_t *>(cs + t);
+                        *reinterpret_cast<float4 *>(gr + t) = make_float4(rcp_tab[c4 & 0xff], rcp_tab[(c4 >> 8) & 0xff],
+                                                                          rcp_tab[(c4 >> 16) & 0xff], rcp_tab[c4 >> 24]);
+                    }
+                } else {
+                    for (int t = lane; t < nt; t += 32) gr[t] = rcp_tab[cs[t]];
+                }
             }
         }
-        __syncwarp();
         // copy out: head bytes up to the first 16-byte boundary, vector body, tail bytes
         const int head = min(total, (16 - pad) & 15);
         if (lane < head) gb[lane] = hb[lane];
@@ -591,11 +649,16 @@ extern "C" int gnan_apsp_bfs_batched_ex(const int32_t *rowptr, const int32_t *co
         const int Wmax = (max_n + 31) / 32;
         const size_t per_warp = bv2_round16((size_t)max_n * max_n + 16) + bv2_round16((size_t)2 * max_n * Wmax * 4) +
                                 ((cnt || rscale) ? bv2_round16((size_t)max_n * nbins) : 0);
-        int wpc = (int)std::min<size_t>(8, (100 * 1024) / per_warp);          // >= 2 CTAs per SM
+        int wpc = (int)std::min<size_t>(16, (216 * 1024) / per_warp);         // one CTA per SM holding as many graphs (warps) as fit
+        if (wpc > 8 && (wpc & 1)) --wpc;
+        if (wpc >= 8 && 2 * per_warp * (wpc / 2) + 4096 <= 216 * 1024) wpc /= 2;      // two CTAs per SM when the halves fit too
         if (wpc < 1) wpc = 1;
         const size_t smem = per_warp * wpc;
         GNAN_CUDA(cudaFuncSetAttribute(apsp_batched_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int blocks = (int)std::min<int64_t>(ceil_div64(B, wpc), 16 * gnan_sm_count());
+        int per_sm = 1;
+        GNAN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, apsp_batched_v2_kernel, 32 * wpc, smem));
+        // persistent: every resident warp walks its share of the graphs (their cost varies like n^2 x depth: many per warp average out)
+        const int blocks = (int)std::min<int64_t>(ceil_div64(B, wpc), (int64_t)std::max(per_sm, 1) * gnan_sm_count());
         apsp_batched_v2_kernel<<<blocks, 32 * wpc, smem, st>>>(rowptr, col, node_off, hop_off, B, max_n, wpc, hop, cnt, rscale,
                                                               (cnt || rscale) ? nbins : 256, overflow_flag, max_level);
         GNAN_LAUNCH_OK();
