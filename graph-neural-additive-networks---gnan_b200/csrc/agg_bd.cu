@@ -85,61 +85,59 @@ agg_bd_graph_fwd_kernel(BdgArgs a)
         for (int jq = 0; jq < n; jq += 32) {
             const int j = jq + lane;
             const bool jv = j < n;
-            const float jvf = jv ? 1.f : 0.f;
-            const uint8_t *hp = hb + (jv ? j : 0);                   // hop column of this lane (any valid column when past the end)
+            const uint8_t *hp = hb + (jv ? j : 0);                   // hop column of this lane (column 0 when past the end)
             float sown[CC];
 #pragma unroll
             for (int c = 0; c < CC; ++c) sown[c] = (jv && c < a.C) ? a.S[(int64_t)(n0 + j) * a.C + c] : 0.f;
             int dmax = 0;
-            int hN[BDG_RB];
-            float4 rN4[VEC ? NPF : 1];
-            float rN1[VEC ? 1 : NPF];
-            auto prefetch = [&](int i0) {
+            // two register sets (A, B) of hop bytes + normaliser rows: block k+1 loads while block k updates the bins
+            int hA[BDG_RB], hB[BDG_RB];
+            float4 rA4[VEC ? NPF : 1], rB4[VEC ? NPF : 1];
+            float rA1[VEC ? 1 : NPF], rB1[VEC ? 1 : NPF];
+            const int nm1 = n - 1;
+            auto load = [&](int i0, int (&h)[BDG_RB], float4 (&r4)[VEC ? NPF : 1], float (&r1)[VEC ? 1 : NPF]) {
 #pragma unroll
-                for (int u = 0; u < BDG_RB; ++u) hN[u] = i0 + u < n ? (int)hp[(i0 + u) * n] : 0;
+                for (int u = 0; u < BDG_RB; ++u) h[u] = (int)hp[(uint32_t)(min(i0 + u, nm1) * n)];   // rows past the end: any row (they add 0)
                 if (rg) {
-                    const int e0 = i0 * nb;
+                    const int left = rtot - i0 * nb;                  // floats of the normaliser left from this block on
+                    const float *src = rg + i0 * nb;
                     if (VEC) {
 #pragma unroll
                         for (int k = 0; k < NPF; ++k) {
                             const int e = lane * 4 + 128 * k;
-                            rN4[k] = (e < rsn && e0 + e < rtot) ? *reinterpret_cast<const float4 *>(rg + e0 + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+                            r4[k] = (e < rsn && e < left) ? *reinterpret_cast<const float4 *>(src + e) : make_float4(0.f, 0.f, 0.f, 0.f);
                         }
                     } else {
 #pragma unroll
                         for (int k = 0; k < NPF; ++k) {
                             const int e = lane + 32 * k;
-                            rN1[k] = (e < rsn && e0 + e < rtot) ? rg[e0 + e] : 0.f;
+                            r1[k] = (e < rsn && e < left) ? src[e] : 0.f;
                         }
                     }
                 }
             };
-            prefetch(0);
-            for (int i0 = 0; i0 < n; i0 += BDG_RB) {
-                int h[BDG_RB];
-#pragma unroll
-                for (int u = 0; u < BDG_RB; ++u) h[u] = hN[u];
+            auto work = [&](int i0, const int (&h)[BDG_RB], const float4 (&r4)[VEC ? NPF : 1], const float (&r1)[VEC ? 1 : NPF]) {
                 if (rg) {
                     if (VEC) {
 #pragma unroll
                         for (int k = 0; k < NPF; ++k)
-                            if (lane * 4 + 128 * k < rsn) sts_v4(rsa + 16u * lane + 512u * k, rN4[k]);
+                            if (lane * 4 + 128 * k < rsn) sts_v4(rsa + 16u * lane + 512u * k, r4[k]);
                     } else {
 #pragma unroll
                         for (int k = 0; k < NPF; ++k)
-                            if (lane + 32 * k < rsn) sts_f32(rsa + 4u * lane + 128u * k, rN1[k]);
+                            if (lane + 32 * k < rsn) sts_f32(rsa + 4u * lane + 128u * k, r1[k]);
                     }
                     __syncwarp();
                 }
-                if (i0 + BDG_RB < n) prefetch(i0 + BDG_RB);
                 int d[BDG_RB];
                 float v[BDG_RB];
 #pragma unroll
                 for (int u = 0; u < BDG_RB; ++u) {
                     d[u] = min(h[u], nb1);
                     dmax = max(dmax, d[u]);
-                    // rows past the end: zero normaliser row (or 0 without a normaliser); columns past the end: * 0
-                    v[u] = (rg ? rs[u * nb + d[u]] : (i0 + u < n ? 1.f : 0.f)) * jvf;
+                    // rows past the end read a zero normaliser row (or add 0 without a normaliser). Lanes past the last column
+                    // walk column 0: their bins hold finite garbage that is multiplied by S = 0 / never written out.
+                    v[u] = rg ? lds_f32(rsa + 4u * (uint32_t)(u * nb + d[u])) : (i0 + u < n ? 1.f : 0.f);
                 }
                 // bins are read-modify-written two rows at a time (both loads in flight; equal bins are chained in registers)
 #pragma unroll
@@ -152,6 +150,16 @@ agg_bd_graph_fwd_kernel(BdgArgs a)
                     sts_f32(pa1, n1v);
                 }
                 if (rg) __syncwarp();
+            };
+            load(0, hA, rA4, rA1);
+            for (int i0 = 0; i0 < n; i0 += 2 * BDG_RB) {
+                const bool second = i0 + BDG_RB < n;
+                if (second) load(i0 + BDG_RB, hB, rB4, rB1);
+                work(i0, hA, rA4, rA1);
+                if (second) {
+                    if (i0 + 2 * BDG_RB < n) load(i0 + 2 * BDG_RB, hA, rA4, rA1);
+                    work(i0 + BDG_RB, hB, rB4, rB1);
+                }
             }
             // bins above the deepest level seen in this column block are untouched (still zero)
             const int dm = __reduce_max_sync(0xffffffffu, dmax);
@@ -292,9 +300,15 @@ extern "C" int gnan_aggregate_blockdiag_graph_fwd(const uint8_t *hop, const int6
     cudaStream_t st = (cudaStream_t)stream;
     GNAN_CUDA(cudaMemsetAsync(work_counter, 0, sizeof(int32_t), st));
     auto launch = [&](auto kernel) -> int {
-        GNAN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 1;
-        GNAN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, BDG_WARPS * 32, smem));
+        // attribute + occupancy are looked up once per (kernel, shared-memory size): the calls cost tens of microseconds of host time
+        static thread_local size_t cached_smem = 0;
+        static thread_local int cached_per_sm = 0;
+        if (cached_smem != smem || cached_per_sm == 0) {
+            GNAN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            GNAN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_per_sm, kernel, BDG_WARPS * 32, smem));
+            cached_smem = smem;
+        }
+        const int per_sm = cached_per_sm;
         const int blocks = (int)std::min<int64_t>(ceil_div64(B, BDG_WARPS), (int64_t)std::max(per_sm, 1) * gnan_sm_count());
         kernel<<<blocks, BDG_WARPS * 32, smem, st>>>(a);      // persistent: every resident warp pulls graphs until none is left
         GNAN_LAUNCH_OK();

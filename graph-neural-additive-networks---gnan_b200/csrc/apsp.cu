@@ -654,9 +654,14 @@ extern "C" int gnan_apsp_bfs_batched_ex(const int32_t *rowptr, const int32_t *co
         if (wpc >= 8 && 2 * per_warp * (wpc / 2) + 4096 <= 216 * 1024) wpc /= 2;      // two CTAs per SM when the halves fit too
         if (wpc < 1) wpc = 1;
         const size_t smem = per_warp * wpc;
-        GNAN_CUDA(cudaFuncSetAttribute(apsp_batched_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 1;
-        GNAN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, apsp_batched_v2_kernel, 32 * wpc, smem));
+        static thread_local size_t cached_smem = 0;       // attribute + occupancy once per configuration (host time)
+        static thread_local int cached_wpc = 0, cached_per_sm = 0;
+        if (cached_smem != smem || cached_wpc != wpc || cached_per_sm == 0) {
+            GNAN_CUDA(cudaFuncSetAttribute(apsp_batched_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            GNAN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_per_sm, apsp_batched_v2_kernel, 32 * wpc, smem));
+            cached_smem = smem; cached_wpc = wpc;
+        }
+        const int per_sm = cached_per_sm;
         // persistent: every resident warp walks its share of the graphs (their cost varies like n^2 x depth: many per warp average out)
         const int blocks = (int)std::min<int64_t>(ceil_div64(B, wpc), (int64_t)std::max(per_sm, 1) * gnan_sm_count());
         apsp_batched_v2_kernel<<<blocks, 32 * wpc, smem, st>>>(rowptr, col, node_off, hop_off, B, max_n, wpc, hop, cnt, rscale,
