@@ -371,8 +371,9 @@ KERNEL_NAMES = {
     "mlp_entries_bwd": "mlp_tc_bwd_kernel / mlp_bwd_kernel (entries mode)", "mlp_entries_fwd": "mlp_fwd_kernel (entries mode)",
     "aggregate_rows_fwd_save": "agg_tc_fwd_kernel (+ colmax / digits pre-pass) | agg_rows_bins_kernel",
     "aggregate_rows_bwd_saved": "agg_tc_ds_kernel (+ row compaction, digits, dT kernels) | agg_rows_ds_kernel",
-    "aggregate_blockdiag_fwd": "agg_blockdiag_fwd_kernel", "aggregate_blockdiag_bwd": "agg_blockdiag_bwd_global_kernel",
-    "apsp_bfs_batched": "apsp_bfs_batched_kernel", "build_csr": "csr_degree/fill/duplicates kernels + cub scan",
+    "aggregate_blockdiag_fwd": "agg_bd_graph_fwd_kernel | agg_blockdiag_fwd_rows_kernel",
+    "aggregate_blockdiag_bwd": "agg_bd_graph_ds/dt kernels | agg_blockdiag_bwd_global_kernel",
+    "apsp_bfs_batched": "apsp_batched_v2_kernel", "build_csr": "csr_degree/fill/duplicates kernels + cub scan",
 }
 COLLECTIVES = ("allgather_rows", "reduce_scatter_rows", "allreduce_gradients")
 
@@ -425,9 +426,9 @@ def run_workload(args, env, name, *, steps, warmup, classes=0, compare_legs=Fals
         n_train_local = int(idx_d.numel())
         x_d = x_h.to(dev)
         cx = compress_features(x_d) if model.dedup else None                           # once per dataset (per row shard), like the hop matrix
-        cx_h = None if cx is None else cx.to("cpu").pin_memory()
+        cx_h = None if cx is None else cx.compact_host().pin_memory()      # int32 index arrays on the host side
         data_d = SimpleNamespace(x=x_d, hop_data=hd, x_compressed=cx)
-        x_bytes = x_h.numel() * 4 if cx is None else cx.nbytes()
+        x_bytes = x_h.numel() * 4 if cx is None else cx_h.nbytes()
         h2d = x_bytes + (0 if big else hop_h.numel()) + cnt_h.numel() * 4
 
         def load_host():
@@ -454,10 +455,10 @@ def run_workload(args, env, name, *, steps, warmup, classes=0, compare_legs=Fals
         host = PackedBatch(wl.x.pin_memory(), pk.hop.cpu().pin_memory(), pk.hop_off.cpu().pin_memory(), pk.node_off.cpu().pin_memory(),
                            pk.level_counts.cpu().pin_memory(), wl.y.pin_memory(), pk.max_nodes)
         cx = compress_features(pk.x) if model.dedup else None
-        cx_h = None if cx is None else cx.to("cpu").pin_memory()
+        cx_h = None if cx is None else cx.compact_host().pin_memory()      # int32 index arrays on the host side
         pk.x_compressed = cx
         data_d = pk
-        x_bytes = host.x.numel() * 4 if cx is None else cx.nbytes()
+        x_bytes = host.x.numel() * 4 if cx is None else cx_h.nbytes()
         h2d = x_bytes + sum(t.numel() * t.element_size() for t in (host.hop, host.hop_off, host.node_off, host.level_counts, host.y))
         if in_step_apsp:                                                # the step starts from the raw edge list
             ei_d, noff_d, hoff_d, x_d, y_d = wl.edge_index.to(dev), pk.node_off, pk.hop_off, wl.x.to(dev), wl.y.to(dev)
@@ -695,15 +696,34 @@ def run_workload(args, env, name, *, steps, warmup, classes=0, compare_legs=Fals
                     "evaluations_per_launch": evals, "avg_launch_ms": dur_ms}
         elif dom == "aggregate_rows_bwd_saved":
             roof = hbm_roof(dom, float(n_train_local) * wl.n, "1 hop byte per (row with a loss, column): rows whose output gradient is zero are skipped")
-        elif dom in ("apsp_bfs_batched", "build_csr"):
-            roof = hbm_roof(dom, pairs if dom == "apsp_bfs_batched" else 16.0 * wl.edge_index.shape[1],
-                            "1 hop byte written per ordered pair" if dom == "apsp_bfs_batched" else "16 bytes read per edge")
+        elif dom == "apsp_bfs_batched":
+            # the kernel's outputs: the hop blocks and the fixed-width normaliser table (fp32 [nodes, MOL_NBINS], written in full)
+            roof = hbm_roof(dom, pairs + 4.0 * wl.n * MOL_NBINS, "1 hop byte written per ordered pair + 4 bytes per (node, level) of the "
+                            f"normaliser table ({MOL_NBINS} levels)")
+        elif dom == "build_csr":
+            roof = hbm_roof(dom, 16.0 * wl.edge_index.shape[1], "16 bytes read per edge")
+        elif dom == "aggregate_blockdiag_fwd" and in_step_apsp:
+            roof = hbm_roof(dom, pairs + 4.0 * wl.n * MOL_NBINS, "1 hop byte read per ordered pair + 4 bytes per (node, level) of the normaliser "
+                            "table; the backward reads neither (it reuses the forward's pair statistics)")
         else:
             roof = hbm_roof(dom, pairs, "1 hop byte per ordered pair per pass (SURVEY.md §8d)")
         roof["kernel_ms_per_step"] = per_step
         agg = None
         if wl.kind == "node":           # the hop-matrix passes of this step against the HBM roofline, whatever the dominant kernel is
-            agg = {"forward": hbm_roof("aggregate_rows_fwd_save", pairs, "1 hop byte per ordered pair"),
+            fwd = hbm_roof("aggregate_rows_fwd_save", pairs, "1 hop byte per ordered pair")
+            if wl.C >= 2 and fwd["avg_launch_ms"] > 0:
+                # tensor-core form (csrc/agg_tc.cu): every hop byte expands to NB one-hot int8 values contracted against NP digit
+                # columns of S; with many channels the int8 tensor pipe, not HBM, bounds the pass. Peak = 2x the measured bf16 rate.
+                nbv = int(hd.nbins)
+                nb_lanes = 8 if nbv <= 8 else (16 if nbv <= 16 else 32)
+                c4, c5 = -(-wl.C // 4), -(-wl.C // 5)
+                np_cols = 16 * c4 if c4 == c5 else 16 * c5
+                ops_exec = 2.0 * pairs * nb_lanes * np_cols
+                ach = ops_exec / (fwd["avg_launch_ms"] / 1e3) / 1e12
+                fwd["tensor_view"] = {"bound": "tensor (int8)", "executed_ops_per_launch": ops_exec, "achieved": ach, "unit": "TOP/s",
+                                      "peak": 2.0 * tflops, "frac": ach / (2.0 * tflops), "lanes_per_row": nb_lanes, "digit_columns": np_cols,
+                                      "note": "executed one-hot int8 MACs (not algorithmic FLOPs); see profiles/ for the ncu tensor-pipe utilisation"}
+            agg = {"forward": fwd,
                    "backward": hbm_roof("aggregate_rows_bwd_saved", float(n_train_local) * wl.n,
                                         "1 hop byte per (row with a loss, column); rows with zero output gradient are skipped"),
                    "rows_with_loss": n_train_local, "hop_bytes": pairs}

@@ -44,8 +44,13 @@ class ValueSharing:
         self.val, self.grp_ptr, self.items, self.inv, self.order, self.seg_ptr = val, grp_ptr, items, inv, order, seg_ptr
         self.max_group = int(max_group)
 
+    _I64 = ("grp_ptr", "inv", "order", "seg_ptr")        # kernel-side dtype of the index fields (a compact host copy may hold int32)
+
     def map(self, fn):
         return ValueSharing(*[fn(getattr(self, f)) for f in self._FIELDS], self.max_group)
+
+    def map_named(self, fn):
+        return ValueSharing(*[fn(f, getattr(self, f)) for f in self._FIELDS], self.max_group)
 
 
 class CompressedFeatures:
@@ -58,9 +63,24 @@ class CompressedFeatures:
         self.max_group = int(max_group)
         self.shared = shared            # ValueSharing or None
 
+    _I64 = ("grp_ptr", "ent_row", "csr_ptr", "csr_eid")
+
     def _map(self, fn):
         return CompressedFeatures(self.num_rows, *[fn(getattr(self, f)) for f in self._FIELDS], self.max_group,
                                   None if self.shared is None else self.shared.map(fn))
+
+    def _map_named(self, fn):
+        return CompressedFeatures(self.num_rows, *[fn(f, getattr(self, f)) for f in self._FIELDS], self.max_group,
+                                  None if self.shared is None else self.shared.map_named(fn))
+
+    def compact_host(self):
+        """Host-side copy for transfers: int64 index arrays are kept as int32 when every value fits (they are widened again on
+        the device by .to()). Halves the index bytes that cross PCIe with every batch."""
+        def shrink(t):
+            if t.dtype == torch.int64 and (t.numel() == 0 or (int(t.max()) < 2 ** 31 and int(t.min()) >= -2 ** 31)):
+                return t.to(torch.int32)
+            return t
+        return self._map(lambda t: shrink(t.cpu()))
 
     @property
     def num_evaluations(self):
@@ -92,7 +112,18 @@ class CompressedFeatures:
         return sum(t.numel() * t.element_size() for t in self._tensors())
 
     def to(self, device):
-        return self._map(lambda t: t.to(device, non_blocking=True))
+        on_gpu = torch.device(device).type == "cuda"
+
+        def move(own):
+            def f(name, t):
+                t = t.to(device, non_blocking=True)
+                if on_gpu and name in own._I64 and t.dtype != torch.int64:      # a compact host copy: widen on the device
+                    t = t.to(torch.int64)
+                return t
+            return f
+        sh = None if self.shared is None else self.shared.map_named(move(ValueSharing))
+        out = CompressedFeatures(self.num_rows, *[move(CompressedFeatures)(f, getattr(self, f)) for f in self._FIELDS], self.max_group, sh)
+        return out
 
     def pin_memory(self):
         return self._map(lambda t: t.pin_memory())

@@ -527,6 +527,40 @@ def test_aggregate_rows_tensor_core_vs_oracle(R, N, C, Cr, nbins, per_row, scale
         assert torch.equal(permuted, got.detach())
 
 
+@pytest.mark.parametrize("C", [5, 40])
+def test_aggregate_rows_tensor_core_backward_keeps_weight_gradient_accuracy(C):
+    """The quantisation error of T*g is shared by every column of a hop level, so sums of dS over many columns (what every
+    shape-function weight gradient is: d bo = sum_j dS[j]) amplify it by the level size. With 3 digits this was 1.4e-4 at
+    C = 5; the backward carries 4 digits. Checked: dS norm-wise AND its column sums against float64."""
+    from gnan_b200 import ops
+    rng = np.random.default_rng(C)
+    R = N = 3000
+    nbins = 9
+    p = np.array([0.0004, 0.004, 0.03, 0.15, 0.4, 0.3, 0.1, 0.0156, 0.0])        # level sizes like a small-world graph
+    h = rng.choice(nbins, size=(R, N), p=p / p.sum())
+    hop = ops.alloc_hop(R, N, DEV)
+    hop[:, :N] = torch.tensor(h.astype(np.uint8), device=DEV)
+    T = torch.tensor(rng.normal(size=(R, nbins, C))).float()
+    S = torch.tensor(rng.normal(size=(N, C))).float()
+    gO = torch.tensor(rng.normal(size=(R, C))).float()
+    gO[torch.tensor(rng.random(R) > 0.1)] = 0.0                                      # a 10 % train mask
+    idx = torch.tensor(h)
+    act = gO.abs().sum(1) > 0
+    W = torch.gather(T[act].double(), 1, idx[act].unsqueeze(-1).expand(-1, -1, C))   # [Ract, N, C]
+    dS64 = (W * gO[act].double().unsqueeze(1)).sum(0)                                # [N, C]
+    Tg, Sg = T.to(DEV).requires_grad_(True), S.to(DEV).requires_grad_(True)
+    got = ops.aggregate_rows(hop, Tg, Sg, per_row=True, algo="tc")
+    (got * gO.to(DEV)).sum().backward()
+    dS = Sg.grad.double().cpu()
+    W0 = torch.gather(T[:200].double(), 1, idx[:200].unsqueeze(-1).expand(-1, -1, C))
+    out64 = (W0 * S.double().unsqueeze(0)).sum(1)                                    # forward (3 digits of S at C = 5, 40), first rows
+    assert G.rel_err(got[:200].detach().double().cpu().numpy(), out64.numpy()) < TOL
+    assert G.rel_err(dS.numpy(), dS64.numpy()) < TOL
+    assert G.rel_err(dS.sum(0).numpy(), dS64.sum(0).numpy()) < TOL
+    wts = torch.tensor(rng.random(size=(N, 1))).double()                              # a positive-weight functional (like d wo)
+    assert G.rel_err((dS * wts).sum(0).numpy(), (dS64 * wts).sum(0).numpy()) < TOL
+
+
 def test_aggregate_rows_tensor_core_refuses_uncovered_shapes():
     from gnan_b200 import ops
     hop = ops.alloc_hop(8, 300, DEV)

@@ -187,6 +187,11 @@ def test_compress_features_structure_and_roundtrip():
     # work items: every (group, tile) exactly once
     want = [(k, t) for k in range(K) for t in range((gp[k + 1] - gp[k] + TILE - 1) // TILE)]
     assert [tuple(i) for i in cx.items.tolist()] == want and cx.max_group == max(gp[k + 1] - gp[k] for k in range(K))
+    # compact host copy (int32 index arrays for the PCIe transfer): same content, fewer bytes
+    ch = cx.compact_host()
+    assert ch.ent_row.dtype == torch.int32 and ch.csr_eid.dtype == torch.int32 and ch.nbytes() < cx.nbytes()
+    assert all(torch.equal(a.long(), b.long()) for a, b in zip(ch._tensors(), cx._tensors()))
+    assert torch.equal(ch.to_dense(), xt)
     assert compress_features(torch.tensor(rng.normal(size=(50, 4)).astype(np.float32))) is None      # dense data: not worth it
     assert compress_features(torch.tensor(rng.normal(size=(50, 4)).astype(np.float32)), max_density=None) is not None
 
