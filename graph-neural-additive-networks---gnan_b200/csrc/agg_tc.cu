@@ -154,9 +154,10 @@ struct AggTcArgs {
 
 // 8 hop bytes -> the two 4-selector words of one stream (selector k of a word in nibble k, upper 16 bits zero: prmt reads only
 // the low 16 bits of its selector operand); NB = bins per row slot
-template <int NB>
+template <int NBX>
 __device__ __forceinline__ uint2 pack8(uint2 w, int stream)
 {
+    constexpr int NB = NBX <= 8 ? 8 : (NBX <= 16 ? 16 : 32);      // selector width: 9..16 lanes per row use the 4-bit selectors
     uint32_t a = w.x, b = w.y;
     if (NB == 32) {
         const uint32_t q = 0x01010101u * (uint32_t)stream;
@@ -179,14 +180,20 @@ __device__ __forceinline__ uint2 pack8(uint2 w, int stream)
 
 constexpr int NBUF = 3;            // A-operand buffers per generator group in tensor memory
 
+// NB = TMEM lanes per hop row (bin slots). 8 / 16 / 32 tile the 128 lanes exactly; 10 / 12 / 14 (levels + unreachable of a
+// 9..15-bin table) leave 128 % NB lanes idle but put 128 / NB instead of 8 rows into every MMA: with many channels the pass
+// is bound by the int8 tensor pipe, whose work per hop byte is NB x digit columns.
 template <int NB, int NGR>
 struct TcCfg {
-    static constexpr int RG = 128 / NB;             // hop rows per generator group (one MMA: M = 128 = RG rows x NB bins)
+    static constexpr int RG = 128 / NB;             // hop rows per generator group (one MMA: M = 128 >= RG rows x NB bins)
     static constexpr int ROWS = RG * NGR;           // hop rows per CTA
-    static constexpr int NSTREAM = NB / 8;          // selector streams (one per group of 8 bins)
+    static constexpr int NBP = NB <= 8 ? 8 : (NB <= 16 ? 16 : 32);   // selector space (power of two)
+    static constexpr int NSTREAM = NBP / 8;         // selector streams (one per group of 8 bins)
     static constexpr int HOPB = ROWS * TCOLS;       // hop bytes per stage
-    static constexpr int NIB_BUF = NSTREAM * RG * 32;         // words per buffer: [stream][row][32 selector words]
-    static constexpr int NIB_WORDS = 2 * NIB_BUF;             // per group, double-buffered
+    static constexpr int RW = (32 % NB == 0) ? 32 / NB : 4;   // hop rows whose lanes fall into one generator warp (at most)
+    static constexpr int NIB_WARP = NSTREAM * RW * 32;        // words per warp and buffer: [stream][row of the warp][32 selector words]
+    static constexpr int NIB_BUF = 4 * NIB_WARP;              // per group: the four generator warps keep PRIVATE copies of their rows
+    static constexpr int NIB_WORDS = 2 * NIB_BUF;             // double-buffered
     static constexpr int ACC0 = NGR * NBUF * 32;    // TMEM: A buffers [g][buf] 32 columns each, then the accumulators
     static constexpr int THREADS = (NGR * 5 + 1) * 32;        // 4 generator warps + 1 MMA-issuer warp per group, 1 TMA producer warp
 };
@@ -282,11 +289,18 @@ agg_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, AggTcArgs a)
     if (warp < NGR * 4) {
         // ===== generators: thread m of group g owns TMEM lane m = (row r, bin slot) =====
         const int g = warp >> 2, m = tid & 127;
-        const int r = m / NB, slot = m % NB, strm = slot >> 3;
-        const uint32_t lut_lo = (slot & 7) < 4 ? 1u << (8 * (slot & 7)) : 0u;
-        const uint32_t lut_hi = (slot & 7) >= 4 ? 1u << (8 * ((slot & 7) - 4)) : 0u;
+        const int r = m / NB, slot = m % NB;
+        const bool lane_used = r < RG;                                // 128 % NB idle lanes store zeros
+        // selector value this lane answers to: its slot, except that the last slot is the unreachable bin (hop byte 255, whose
+        // low selector bits are all ones)
+        const int mv = slot == NB - 1 ? Cfg::NBP - 1 : slot;
+        const int strm = mv >> 3;
+        const uint32_t lut_lo = (lane_used && (mv & 7) < 4) ? 1u << (8 * (mv & 7)) : 0u;
+        const uint32_t lut_hi = (lane_used && (mv & 7) >= 4) ? 1u << (8 * ((mv & 7) - 4)) : 0u;
         const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        uint32_t *nib_g = nib_s + g * Cfg::NIB_WORDS;
+        const int wq = warp & 3;
+        const int r_lo = (wq * 32) / NB;                              // first hop row with a lane in this warp
+        uint32_t *nib_g = nib_s + g * Cfg::NIB_WORDS + wq * Cfg::NIB_WARP;
         int st = 0, buf = 0, prev_buf = 0;
         uint32_t fph = 0, eph = 1;                                   // eph: parity of the a_empty completion that frees `buf` (lap - 1)
         for (int s = 0; s < a.nblk; ++s) {
@@ -295,14 +309,13 @@ agg_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, AggTcArgs a)
             // 8 hop bytes -> two 4-selector words per stream, through a warp-private slice of shared memory (__syncwarp only)
             uint32_t *nb = nib_g + (s & 1) * Cfg::NIB_BUF;
             const uint8_t *hs = hop_s + (size_t)st * HOPB + (size_t)g * RG * TCOLS;
-            constexpr int CH_W = (32 / NB) * 16;                      // 8-byte chunks of this warp's rows
-            const int ch0 = (warp & 3) * CH_W;
+            constexpr int CH_W = Cfg::RW * 16;                        // 8-byte chunks of the rows this warp's lanes belong to
 #pragma unroll
             for (int cw = lane; cw < CH_W; cw += 32) {
-                const int ch = ch0 + cw;
-                const uint2 w = *reinterpret_cast<const uint2 *>(hs + ch * 8);
+                const int rl = cw >> 4, rr = min(r_lo + rl, RG - 1);  // (rows past the group: a copy of the last one, never read)
+                const uint2 w = *reinterpret_cast<const uint2 *>(hs + (rr * 16 + (cw & 15)) * 8);
 #pragma unroll
-                for (int q = 0; q < NSTREAM; ++q) *reinterpret_cast<uint2 *>(nb + q * (RG * 32) + ch * 2) = pack8<NB>(w, q);
+                for (int q = 0; q < NSTREAM; ++q) *reinterpret_cast<uint2 *>(nb + q * (Cfg::RW * 32) + cw * 2) = pack8<NB>(w, q);
             }
             if (s > 0) {                                              // the previous stage's TMEM store has had the pack to land
                 tmem_wait_st();
@@ -312,7 +325,7 @@ agg_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, AggTcArgs a)
             __syncwarp();
             mbar_wait(smem_u32(&pb.a_empty[g * NBUF + buf]), eph);   // first lap: a fresh barrier passes a wait on parity 1
             tc_fence_after();
-            const uint4 *src = reinterpret_cast<const uint4 *>(nb + strm * (RG * 32) + r * 32);
+            const uint4 *src = reinterpret_cast<const uint4 *>(nb + strm * (Cfg::RW * 32) + (min(r, RG - 1) - r_lo) * 32);
             uint32_t v[32];
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -334,7 +347,9 @@ agg_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, AggTcArgs a)
         const int64_t i = row0 + g * RG + r;
         const bool slot_ok = slot < a.nbins - 1 || slot == NB - 1;
         const int d = slot == NB - 1 ? a.nbins - 1 : slot;
-        const bool ok = i < a.R && slot_ok;
+        const bool ok = lane_used && i < a.R && slot_ok;
+        constexpr bool POW2 = (NB & (NB - 1)) == 0;
+        float *sc = reinterpret_cast<float *>(nib_s + g * Cfg::NIB_WORDS);   // the group's selector buffers are free now: [128][5] scratch
         const float rs = (ok && a.rscale) ? a.rscale[i * a.nbins + d] : 1.f;
         const float *Trow = a.T + ((a.per_row && ok) ? i * a.nbins * a.Cr : 0) + (ok ? d * a.Cr : 0);
         for (int n0 = 0; n0 < a.NP; n0 += 16) {
@@ -356,9 +371,28 @@ agg_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmap, AggTcArgs a)
                 const float bs = (float)ldexp((double)tot, -a.colsh[c]);
                 if (ok && a.Bsum) a.Bsum[(i * a.nbins + d) * a.C + c] = bs;
                 float o = ok ? Trow[a.Cr == 1 ? 0 : c] * rs * bs : 0.f;
+                if (POW2) {
 #pragma unroll
-                for (int sft = NB / 2; sft > 0; sft >>= 1) o += __shfl_xor_sync(0xffffffffu, o, sft);
-                if (slot == 0 && i < a.R) a.out[i * a.C + c] = o;
+                    for (int sft = NB / 2; sft > 0; sft >>= 1) o += __shfl_xor_sync(0xffffffffu, o, sft);
+                    if (slot == 0 && i < a.R) a.out[i * a.C + c] = o;
+                } else {
+                    sc[m * 5 + cc] = o;
+                }
+            }
+            if (!POW2) {                                              // a row's lanes straddle warps: sum them through shared memory
+                named_bar_sync(1 + g, 128);
+                if (m < RG * 5) {
+                    const int rr = m / 5, cc = m % 5;
+                    const int c = (n0 >> 4) * a.cpc + cc;
+                    const int64_t ii = row0 + g * RG + rr;
+                    if (cc < a.cpc && c < a.C && ii < a.R) {
+                        float o = 0.f;
+#pragma unroll
+                        for (int sl = 0; sl < NB; ++sl) o += sc[(rr * NB + sl) * 5 + cc];
+                        a.out[ii * a.C + c] = o;
+                    }
+                }
+                named_bar_sync(1 + g, 128);
             }
         }
         tc_fence_before();
@@ -729,6 +763,25 @@ int launch_fwd_nb(const CUtensorMap &map, const AggTcArgs &a, int ngr, cudaStrea
     return launch_fwd<NB, 1>(map, a, st);
 }
 
+// lanes per row = the bins actually present (even count 10 / 12 / 14): only instantiated for the tensor-bound shapes (NGR <= 3)
+template <int NB>
+int launch_fwd_exact(const CUtensorMap &map, const AggTcArgs &a, int ngr, cudaStream_t st)
+{
+    if (ngr == 3) return launch_fwd<NB, 3>(map, a, st);
+    if (ngr == 2) return launch_fwd<NB, 2>(map, a, st);
+    return launch_fwd<NB, 1>(map, a, st);
+}
+
+// lanes per hop row of the forward kernel. With >= 64 digit columns (C >= 13) the pass is bound by the int8 tensor pipe and the
+// bins that do not exist are pure waste: a 12-bin table (ogbn-arxiv shape) then puts 10 instead of 8 rows into every MMA.
+inline int fwd_lanes_per_row(int nbins, int NP)
+{
+    if (nbins <= 8) return 8;
+    if (nbins > 16) return 32;
+    const int even = (nbins + 1) & ~1;
+    return (NP >= 64 && even < 16) ? even : 16;
+}
+
 }  // namespace
 
 // 1 when the tensor-core path covers the shape (nbins <= 32, accumulator columns <= 256, a matrix worth a TMA pipeline)
@@ -779,11 +832,14 @@ extern "C" int gnan_aggregate_rows_fwd_ws(const uint8_t *hop, int64_t R, int64_t
 
     AggTcArgs a{R, N, nbins, C, Cr, table_per_row, p.ndig, p.cpc, p.NP, nblk, 0, T, rscale, w.colsh, w.dig, out, Bsum};
     const int ngr = groups_for(p.NP);
-    const int nb = nbins <= 8 ? 8 : (nbins <= 16 ? 16 : 32);
+    const int nb = fwd_lanes_per_row(nbins, p.NP);
     CUtensorMap map;
     int rc = make_hop_tmap(&map, hop, R, ld_hop, (128 / nb) * ngr);
     if (rc) return rc;
     if (nb == 8) return launch_fwd_nb<8>(map, a, ngr, st);
+    if (nb == 10) return launch_fwd_exact<10>(map, a, ngr, st);
+    if (nb == 12) return launch_fwd_exact<12>(map, a, ngr, st);
+    if (nb == 14) return launch_fwd_exact<14>(map, a, ngr, st);
     if (nb == 16) return launch_fwd_nb<16>(map, a, ngr, st);
     return launch_fwd_nb<32>(map, a, ngr, st);
 }

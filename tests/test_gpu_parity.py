@@ -492,7 +492,10 @@ def test_aggregate_rows_vs_oracle(R, N, C, Cr, nbins, per_row, scale):
 @pytest.mark.parametrize("R,N,C,Cr,nbins,per_row,scale", [
     (37, 300, 3, 3, 6, True, False), (64, 2500, 7, 7, 12, False, True), (33, 4099, 4, 1, 16, False, True),
     (20, 1000, 2, 2, 17, True, True), (129, 515, 40, 40, 9, False, False), (300, 700, 5, 1, 32, True, False),
-    (50, 260, 1, 1, 3, False, False), (70, 900, 64, 64, 14, True, True), (1, 256, 3, 3, 8, True, False)])
+    (50, 260, 1, 1, 3, False, False), (70, 900, 64, 64, 14, True, True), (1, 256, 3, 3, 8, True, False),
+    # 10 / 12 / 14 lanes per row (tensor-bound shapes: >= 64 digit columns), 1-3 generator groups, ragged row tiles
+    (200, 3000, 40, 40, 12, True, False), (91, 1500, 16, 16, 11, False, True), (45, 700, 20, 1, 13, True, True),
+    (23, 1029, 33, 33, 10, True, False)])
 def test_aggregate_rows_tensor_core_vs_oracle(R, N, C, Cr, nbins, per_row, scale):
     from gnan_b200 import ops
     rng = np.random.default_rng(R * 7 + N)
