@@ -385,6 +385,7 @@ def run_workload(args, env, name, *, steps, warmup, classes=0, compare_legs=Fals
     from gnan_b200.preprocess import HopData, PackedBatch, apsp, apsp_batched
     from gnan_b200.sparse import compress_features
     from gnan_b200.trainer import CapturedStep
+    from gnan_b200.optim import Adam as FusedAdam
     world, rank, dev, flush, lib = env.world, env.rank, env.dev, env.flush, env.lib
     barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
     wl = make_workload(name, seed=rank, classes=classes)
@@ -399,7 +400,7 @@ def run_workload(args, env, name, *, steps, warmup, classes=0, compare_legs=Fals
     model.fs.xavier_normal_(1.0); model.rho.xavier_normal_(1.0)
     model.precision = args.precision
     model.dedup = args.dedup == "on" and wl.name != "arxiv"         # arxiv features are continuous: nothing to share
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3, fused=True, capturable=True)
+    opt = FusedAdam(model.parameters(), lr=1e-3)               # torch.optim.Adam semantics, one launch for all tensors (csrc/train.cu)
     sharded = wl.name in ("pubmed", "arxiv") and world > 1
     scaling = "strong" if sharded else "weak"
     fg = gdist.FlatGradients(model.parameters()) if world > 1 and wl.name != "cora" else None
@@ -443,7 +444,8 @@ def run_workload(args, env, name, *, steps, warmup, classes=0, compare_legs=Fals
                 out = gdist.row_sharded_forward(model, data.x, data.hop_data, sizes, x_compressed=data.x_compressed)
             else:
                 out = model.forward(data)
-            return loss_fn(out.index_select(0, idx_d), yl_d) / n_train
+            # masked cross entropy: value and the [N,C] output gradient from one kernel (trainer.py:52-66)
+            return ops.cross_entropy_rows(out, yl_d, rows=idx_d, scale=1.0 / n_train)
         after_bwd = (lambda: fg.all_reduce()) if sharded else None
         rows_local = e0 - b0
         in_step_apsp = False
@@ -487,7 +489,7 @@ def run_workload(args, env, name, *, steps, warmup, classes=0, compare_legs=Fals
                 data = apsp_batched(e, node_off_h, device=dev, x=xx, y=yy, node_off_device=no, hop_off_device=ho, nbins=MOL_NBINS, rscale=True)
                 data.x_compressed = c
                 apsp_status[:] = [data.status]
-            return loss_fn(model(data).flatten(), data.y)               # model(data): [B,1]
+            return ops.bce_with_logits(model(data).flatten(), data.y)   # model(data): [B,1]; BCEWithLogitsLoss, value + gradient in one kernel
         after_bwd = (lambda: fg.all_reduce(average=True)) if world > 1 else None
         rows_local = wl.n
         n_train_local = None

@@ -90,6 +90,12 @@ SIGNATURES = {
                                         c_int32, c_void_p, c_void_p, c_void_p]),
     "gnan_apsp_bfs_batched_ex": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int64, c_int64, c_void_p, c_void_p,
                                          c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    "gnan_loss_workspace_bytes": (c_size_t, []),
+    "gnan_cross_entropy_rows": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_size_t, c_void_p]),
+    "gnan_bce_with_logits": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "gnan_adam_step": (c_int, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float,
+                               c_float, c_void_p]),
     "gnan_hops_to_reference": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "gnan_hops_from_reference": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int32, c_void_p,
                                          c_void_p]),

@@ -10,7 +10,8 @@ from torch import Tensor
 from . import _lib
 from ._lib import MlpGrads, MlpParams, check, load, ptr, stream_handle
 
-__all__ = ["mlp", "aggregate_rows", "aggregate_blockdiag", "rho_table_inputs", "level_rscale", "alloc_hop", "hop_ld"]
+__all__ = ["mlp", "aggregate_rows", "aggregate_blockdiag", "rho_table_inputs", "level_rscale", "alloc_hop", "hop_ld",
+           "cross_entropy_rows", "bce_with_logits"]
 
 
 # ---- optional per-call CUDA-event timing (bench.py): events are recorded on the launching stream ----------------------
@@ -468,3 +469,95 @@ def level_rscale(cnt: Tensor) -> Tensor:
     rs = torch.empty(cnt.shape, dtype=torch.float32, device=cnt.device)
     check(lib.gnan_level_rscale(ptr(cnt.contiguous()), cnt.shape[0], cnt.shape[1], ptr(rs), stream_handle()), "gnan_level_rscale")
     return rs
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# losses of the training step: value and gradient in one pass (csrc/train.cu; trainer.py:52-67)
+# ---------------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("gnan_b200::ce_rows", mutates_args=())
+def _ce_rows(logits: Tensor, rows: Optional[Tensor], labels: Tensor, scale: float, want_grad: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    lib = load()
+    logits = _f32(logits, "logits")
+    if labels.dtype != torch.int64 or (rows is not None and rows.dtype != torch.int64):
+        raise TypeError("labels / rows must be int64")
+    N, C = logits.shape
+    M = labels.numel()
+    if rows is not None and rows.numel() != M:
+        raise ValueError("rows and labels must have the same length")
+    if rows is None and M != N:
+        raise ValueError("labels must have one entry per row of logits")
+    loss = torch.empty((), dtype=torch.float32, device=logits.device)
+    d = torch.empty_like(logits) if want_grad else torch.empty(0, device=logits.device)
+    bad = torch.zeros(1, dtype=torch.int32, device=logits.device)
+    ws = _ws(lib.gnan_loss_workspace_bytes(), logits.device)
+    with _timed("loss"):
+        check(lib.gnan_cross_entropy_rows(ptr(logits), N, C, ptr(rows), ptr(labels.contiguous()), M, float(scale), ptr(loss),
+                                          ptr(d) if want_grad else None, ptr(bad), ptr(ws), ws.numel(), stream_handle()),
+              "gnan_cross_entropy_rows")
+    return loss, d, bad
+
+
+@_ce_rows.register_fake
+def _(logits, rows, labels, scale, want_grad):
+    return logits.new_empty(()), torch.empty_like(logits) if want_grad else logits.new_empty(0), logits.new_empty(1, dtype=torch.int32)
+
+
+def _ce_setup(ctx, inputs, output):
+    ctx.save_for_backward(output[1])
+
+
+def _ce_backward(ctx, g, _gd, _gb):
+    (d,) = ctx.saved_tensors
+    return d * g, None, None, None, None
+
+
+_ce_rows.register_autograd(_ce_backward, setup_context=_ce_setup)
+
+
+def cross_entropy_rows(logits, labels, rows=None, reduction="mean", return_flag=False, scale=None):
+    """CrossEntropyLoss of logits[rows] (all rows when rows is None) against int64 labels: the loss AND its gradient w.r.t. the
+    whole [N,C] logits come out of one kernel (rows without a loss get a zero gradient). `rows` must not repeat an index.
+    return_flag: also return the device int32 flag that is set by an out-of-range row / label (checked lazily by the caller)."""
+    M = labels.numel()
+    if scale is None:                # explicit scale: e.g. 1 / (global number of training rows) on a row shard
+        scale = 1.0 / max(M, 1) if reduction == "mean" else 1.0
+    loss, _, bad = _ce_rows(logits, None if rows is None else rows.contiguous(), labels, scale, bool(torch.is_grad_enabled() and logits.requires_grad))
+    return (loss, bad) if return_flag else loss
+
+
+@torch.library.custom_op("gnan_b200::bce_logits", mutates_args=())
+def _bce_logits(logits: Tensor, targets: Tensor, scale: float, want_grad: bool) -> Tuple[Tensor, Tensor]:
+    lib = load()
+    logits, targets = _f32(logits, "logits"), _f32(targets, "targets")
+    if logits.shape != targets.shape:
+        raise ValueError("logits and targets must have the same shape")
+    loss = torch.empty((), dtype=torch.float32, device=logits.device)
+    d = torch.empty_like(logits) if want_grad else torch.empty(0, device=logits.device)
+    ws = _ws(lib.gnan_loss_workspace_bytes(), logits.device)
+    with _timed("loss"):
+        check(lib.gnan_bce_with_logits(ptr(logits), ptr(targets), logits.numel(), float(scale), ptr(loss), ptr(d) if want_grad else None,
+                                       ptr(ws), ws.numel(), stream_handle()), "gnan_bce_with_logits")
+    return loss, d
+
+
+@_bce_logits.register_fake
+def _(logits, targets, scale, want_grad):
+    return logits.new_empty(()), torch.empty_like(logits) if want_grad else logits.new_empty(0)
+
+
+def _bce_setup(ctx, inputs, output):
+    ctx.save_for_backward(output[1])
+
+
+def _bce_backward(ctx, g, _gd):
+    (d,) = ctx.saved_tensors
+    return d * g, None, None, None
+
+
+_bce_logits.register_autograd(_bce_backward, setup_context=_bce_setup)
+
+
+def bce_with_logits(logits, targets, reduction="mean"):
+    """BCEWithLogitsLoss (value + gradient in one kernel); logits and targets of equal shape, any rank."""
+    scale = 1.0 / max(logits.numel(), 1) if reduction == "mean" else 1.0
+    return _bce_logits(logits.contiguous(), targets.contiguous(), scale, bool(torch.is_grad_enabled() and logits.requires_grad))[0]

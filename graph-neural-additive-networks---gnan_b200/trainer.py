@@ -99,10 +99,26 @@ def _forward_item(model, data, labels, device, mask_name, is_graph_task):
     return outputs, labels
 
 
+def _fused_loss(loss_fn, outputs, labels):
+    """The two losses the reference trains with (main.py: CrossEntropyLoss / BCEWithLogitsLoss with default arguments), as one
+    kernel each that returns the value and the gradient (gnan_b200.ops, csrc/train.cu); None when `loss_fn` is anything else."""
+    if not (outputs.is_cuda and outputs.dtype == torch.float32 and labels.numel() > 0 and labels.is_cuda):
+        return None
+    from . import ops
+    if (type(loss_fn) is torch.nn.CrossEntropyLoss and loss_fn.weight is None and loss_fn.label_smoothing == 0.0
+            and loss_fn.reduction in ("mean", "sum") and outputs.dim() == 2 and labels.dtype == torch.int64 and labels.dim() == 1):
+        return ops.cross_entropy_rows(outputs.contiguous(), labels, reduction=loss_fn.reduction)
+    if (type(loss_fn) is torch.nn.BCEWithLogitsLoss and loss_fn.weight is None and loss_fn.pos_weight is None
+            and loss_fn.reduction in ("mean", "sum") and labels.is_floating_point() and outputs.shape == labels.shape):
+        return ops.bce_with_logits(outputs, labels.float(), reduction=loss_fn.reduction)
+    return None
+
+
 def _loss(loss_fn, outputs, labels):
     if outputs.dim() == 2 and outputs.shape[-1] == 1:
-        return loss_fn(outputs.flatten(), labels.float())                   # trainer.py:61-62
-    return loss_fn(outputs, labels)
+        outputs, labels = outputs.flatten(), labels.float()                 # trainer.py:61-62
+    fused = _fused_loss(loss_fn, outputs, labels)
+    return fused if fused is not None else loss_fn(outputs, labels)
 
 
 class _Running:

@@ -242,6 +242,29 @@ int gnan_aggregate_blockdiag_graph_bwd(const int32_t *node_off, int32_t B, int32
                                        void *workspace, size_t workspace_bytes, gnan_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * The tail of the training step (csrc/train.cu; replaces trainer.py:52-67 and torch.optim.Adam.step, main.py:141).
+ * Losses: *loss (device float, overwritten) = scale * sum of the per-sample terms (scale = 1/M for the reference's mean
+ * reduction) and, when dlogits != NULL, d(loss)/d(logits) for an upstream gradient of 1 in the same pass.
+ *   cross_entropy_rows: samples are the rows rows[m] (NULL: row m) of logits [N,C] with class labels[m]; dlogits is the FULL
+ *     [N,C] gradient, zero on the rows without a loss (what the aggregation backward skips). An index outside [0,N) / label
+ *     outside [0,C) sets *bad_index_flag (device int32, zero-initialised by the caller) and that sample is ignored.
+ *   bce_with_logits: torch.nn.BCEWithLogitsLoss on logits [M], targets [M] in [0,1].
+ * workspace: gnan_loss_workspace_bytes(). Deterministic (fixed summation order; unique rows).
+ * adam_step: torch.optim.Adam semantics (no amsgrad, L2 weight_decay added to the gradient) for n_tensors fp32 tensors in one
+ * launch: HOST arrays of device pointers / element counts; state = 3 device floats {step, 1-beta1^step, sqrt(1-beta2^step)},
+ * zero-initialised by the caller and advanced by the call (so a captured CUDA graph keeps counting).
+ * ---------------------------------------------------------------------------------------------- */
+size_t gnan_loss_workspace_bytes(void);
+int gnan_cross_entropy_rows(const float *logits, int64_t N, int32_t C, const int64_t *rows /* [M] or NULL */, const int64_t *labels,
+                            int64_t M, float scale, float *loss, float *dlogits /* [N,C] or NULL */, int32_t *bad_index_flag,
+                            void *workspace, size_t workspace_bytes, gnan_stream_t stream);
+int gnan_bce_with_logits(const float *logits, const float *targets, int64_t M, float scale, float *loss, float *dlogits /* [M] or NULL */,
+                         void *workspace, size_t workspace_bytes, gnan_stream_t stream);
+int gnan_adam_step(int32_t n_tensors, float *const *params, const float *const *grads, float *const *exp_avg, float *const *exp_avg_sq,
+                   const int64_t *numel, float *state /* [3] device */, float lr, float beta1, float beta2, float eps, float weight_decay,
+                   gnan_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * All-pairs hop distances (replaces scipy dijkstra + the per-element normaliser loop,
  * pre_process_datasets.py:109-121,128-140; networkx BFS of batched_pyg_main.py:36-44).
  * Directed CSR (edges followed src -> dst), simple graph, unit weights. hop bytes: level, 255 = unreachable;

@@ -175,3 +175,60 @@ def test_duplicate_detection_short_and_long_rows():
     assert int(build_csr(torch.tensor(np.concatenate([base, hub[:, 123:124]], axis=1)), n, DEV)[2].item()) == 2    # long row
     short = ei[:, ei[0] != 7][:, 5:6]
     assert int(build_csr(torch.tensor(np.concatenate([base, short], axis=1)), n, DEV)[2].item()) == 2             # short row
+
+
+# ---- the tail of the training step (csrc/train.cu): fused losses and the one-launch Adam ----------------------------------
+@pytest.mark.parametrize("N,C,frac", [(2708, 7, 0.05), (300, 40, 1.0), (5, 3, 0.6)])
+def test_fused_cross_entropy_rows_vs_torch(N, C, frac):
+    from gnan_b200 import ops
+    g = torch.Generator(device=DEV).manual_seed(N)
+    logits = (torch.randn(N, C, device=DEV, generator=g) * 3).requires_grad_(True)
+    rows = torch.nonzero(torch.rand(N, device=DEV, generator=g) < frac).flatten()
+    if rows.numel() == 0:
+        rows = torch.tensor([0], device=DEV)
+    labels = torch.randint(0, C, (rows.numel(),), device=DEV, generator=g)
+    for reduction in ("mean", "sum"):
+        ref = torch.nn.functional.cross_entropy(logits.double()[rows], labels, reduction=reduction)
+        (gref,) = torch.autograd.grad(ref * 1.7, logits)
+        got, bad = ops.cross_entropy_rows(logits, labels, rows=rows, reduction=reduction, return_flag=True)
+        (ggot,) = torch.autograd.grad(got * 1.7, logits)
+        assert int(bad.item()) == 0
+        assert abs(float(got) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
+        assert G.rel_err(ggot.cpu().numpy(), gref.cpu().numpy()) < TOL
+    full = ops.cross_entropy_rows(logits, torch.randint(0, C, (N,), device=DEV, generator=g))         # every row, no index list
+    assert torch.isfinite(full)
+    _, bad = ops.cross_entropy_rows(logits, torch.full((1,), C, device=DEV), rows=torch.zeros(1, dtype=torch.long, device=DEV), return_flag=True)
+    assert int(bad.item()) == 1                                                                       # label out of range is reported
+
+
+def test_fused_bce_with_logits_vs_torch():
+    from gnan_b200 import ops
+    g = torch.Generator(device=DEV).manual_seed(1)
+    x = (torch.randn(4337, device=DEV, generator=g) * 4).requires_grad_(True)
+    t = (torch.rand(4337, device=DEV, generator=g) < 0.4).float()
+    for reduction in ("mean", "sum"):
+        ref = torch.nn.functional.binary_cross_entropy_with_logits(x.double(), t.double(), reduction=reduction)
+        (gref,) = torch.autograd.grad(ref, x)
+        got = ops.bce_with_logits(x, t, reduction=reduction)
+        (ggot,) = torch.autograd.grad(got, x)
+        assert abs(float(got) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
+        assert G.rel_err(ggot.cpu().numpy(), gref.cpu().numpy()) < TOL
+
+
+@pytest.mark.parametrize("wd", [0.0, 5e-4])
+def test_one_launch_adam_follows_torch_adam(wd):
+    """gnan_b200.optim.Adam against torch.optim.Adam over 25 steps on tensors of odd sizes (incl. > 24 tensors: two launches)."""
+    from gnan_b200.optim import Adam
+    g = torch.Generator(device=DEV).manual_seed(3)
+    shapes = [(1434, 64), (64,), (1, 1434, 64, 64)[1:], (7,), (3, 5, 1025)] + [(k + 1,) for k in range(26)]
+    pa = [torch.randn(*s, device=DEV, generator=g).requires_grad_(True) for s in shapes]
+    pb = [p.detach().clone().requires_grad_(True) for p in pa]
+    oa, ob = Adam(pa, lr=3e-3, weight_decay=wd), torch.optim.Adam(pb, lr=3e-3, weight_decay=wd)
+    for step in range(25):
+        for a, b in zip(pa, pb):
+            gr = torch.randn(a.shape, device=DEV, generator=g) * (0.1 + step % 3)
+            a.grad = gr.clone(); b.grad = gr.clone()
+        oa.step(); ob.step()
+    for a, b in zip(pa, pb):
+        assert G.rel_err(a.detach().cpu().numpy(), b.detach().cpu().numpy()) < 2e-6
+    assert float(oa.param_groups[0]["state_buf"][0]) == 25.0
