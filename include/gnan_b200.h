@@ -313,7 +313,9 @@ int gnan_apsp_bfs_batched_n(const int32_t *rowptr, const int32_t *col, const int
  * and graphs of at most 128 nodes. */
 int gnan_apsp_bfs_batched_ex(const int32_t *rowptr, const int32_t *col, const int32_t *node_off, const int64_t *hop_off,
                              int32_t B, int32_t max_n, int64_t total_nodes, int64_t total_hop_bytes, uint8_t *hop, int32_t *cnt,
-                             float *rscale, int32_t nbins, int32_t *overflow_flag, int32_t *max_level, gnan_stream_t stream);
+                             float *rscale, int32_t nbins, int32_t *overflow_flag, int32_t *max_level,
+                             int32_t *order_ws /* [B] scratch or NULL: graphs are then processed grouped by size class */,
+                             gnan_stream_t stream);
 
 /* reference-format converters (pre_process_datasets.py:112-121): fp32 node_distances / normalization_matrix <-> hops */
 int gnan_hops_to_reference(const uint8_t *hop, int64_t R, int64_t N, int64_t ld_hop, const int32_t *cnt, int32_t nbins,
