@@ -44,6 +44,7 @@ SIGNATURES = {
                                      ctypes.POINTER(MlpGrads), c_void_p, c_size_t, c_void_p]),
     "gnan_entries_to_rows": (c_int, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p]),
+    "gnan_rows_to_entries_scratch_floats": (c_size_t, [c_int32, c_int32, c_int64]),
     "gnan_rows_to_entries": (c_int, [c_void_p, c_int64, c_int32, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gnan_gather_segment_sum": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
     "gnan_rho_table_inputs": (c_int, [c_void_p, c_int64, c_int32, c_int, c_void_p, c_void_p]),

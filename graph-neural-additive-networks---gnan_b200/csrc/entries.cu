@@ -102,6 +102,43 @@ __global__ void rows_to_baselines_kernel(const float *__restrict__ dS, int G, in
     if (threadIdx.x == 0) dY[e0 * C + c] = dStot[c] - red[0];
 }
 
+// long groups (one-hot columns: a feature with ~1e5 exceptions): partial[slab][g*C+c] = sum of dS over the exceptions of slab
+// `slab` of group g (fixed thread-strided order + tree), then dY[base] = dStot - sum of the slabs in order. Deterministic.
+constexpr int BASE_SLAB = 8192;
+__global__ void __launch_bounds__(256)
+rows_to_baselines_partial_kernel(const float *__restrict__ dS, int C, const int64_t *__restrict__ grp_ptr,
+                                 const int64_t *__restrict__ ent_row, float *__restrict__ partial)
+{
+    __shared__ float red[256];
+    const int g = blockIdx.x / C, c = blockIdx.x % C;
+    const int64_t e0 = grp_ptr[g] + 1 + (int64_t)blockIdx.y * BASE_SLAB, e1 = min(grp_ptr[g + 1], e0 + BASE_SLAB);
+    float s0 = 0.f, s1 = 0.f;
+    int64_t e = e0 + threadIdx.x;
+    for (; e + 256 < e1; e += 512) {
+        s0 += dS[ent_row[e] * C + c];
+        s1 += dS[ent_row[e + 256] * C + c];
+    }
+    if (e < e1) s0 += dS[ent_row[e] * C + c];
+    red[threadIdx.x] = s0 + s1;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if ((int)threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = red[0];
+}
+
+__global__ void rows_to_baselines_final_kernel(int GC, int C, int nslab, const int64_t *__restrict__ grp_ptr,
+                                               const float *__restrict__ partial, const float *__restrict__ dStot, float *__restrict__ dY)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= GC) return;
+    const int g = t / C, c = t % C;
+    float s = 0.f;
+    for (int k = 0; k < nslab; ++k) s += partial[(size_t)k * GC + t];
+    dY[grp_ptr[g] * C + c] = dStot[c] - s;
+}
+
 // out[s,:] = sum over k in [seg_ptr[s], seg_ptr[s+1]) of src[order[k],:]; one warp per (segment, channel block of 32 lanes is
 // not needed: lanes stride over the segment's elements, one channel at a time), fixed order -> deterministic
 __global__ void gather_segment_sum_kernel(const float *__restrict__ src, const int64_t *__restrict__ order,
@@ -199,6 +236,12 @@ extern "C" int gnan_entries_to_rows(const float *Y, int64_t N, int32_t G, int32_
     return GNAN_OK;
 }
 
+// floats of scratch behind dStot: 65*C for the column sums + the slab partial sums of long groups
+extern "C" size_t gnan_rows_to_entries_scratch_floats(int32_t G, int32_t C, int64_t E)
+{
+    return 65 * (size_t)C + (size_t)ceil_div64(E, BASE_SLAB) * (size_t)G * (size_t)C;
+}
+
 extern "C" int gnan_rows_to_entries(const float *dS, int64_t N, int32_t G, int32_t C, const int64_t *grp_ptr, int64_t E,
                                     const int64_t *ent_row, float *dStot, float *dY, gnan_stream_t stream)
 {
@@ -212,8 +255,16 @@ extern "C" int gnan_rows_to_entries(const float *dS, int64_t N, int32_t G, int32
     GNAN_LAUNCH_OK();
     rows_to_exceptions_kernel<<<(unsigned)ceil_div64(E * C, 256), 256, 0, st>>>(dS, E, C, ent_row, dY);
     GNAN_LAUNCH_OK();
-    const int bt = (E / G) > 2048 ? 512 : 64;          // long groups (few features, many exceptions) get wide blocks
-    rows_to_baselines_kernel<<<(unsigned)(G * C), bt, 0, st>>>(dS, G, C, grp_ptr, ent_row, dStot, dY);
+    if ((E / G) > 2048) {                               // long groups (few features, many exceptions): slabs of 8192 entries in parallel
+        const int nslab = (int)ceil_div64(E, BASE_SLAB);
+        float *partial = dStot + 65 * (size_t)C;       // [nslab][G*C]
+        rows_to_baselines_partial_kernel<<<dim3((unsigned)(G * C), (unsigned)nslab), 256, 0, st>>>(dS, C, grp_ptr, ent_row, partial);
+        GNAN_LAUNCH_OK();
+        rows_to_baselines_final_kernel<<<(unsigned)ceil_div64((int64_t)G * C, 128), 128, 0, st>>>(G * C, C, nslab, grp_ptr, partial, dStot, dY);
+        GNAN_LAUNCH_OK();
+        return GNAN_OK;
+    }
+    rows_to_baselines_kernel<<<(unsigned)(G * C), 64, 0, st>>>(dS, G, C, grp_ptr, ent_row, dStot, dY);
     GNAN_LAUNCH_OK();
     return GNAN_OK;
 }

@@ -299,7 +299,7 @@ def rows_to_entries(dS: Tensor, grp_ptr: Tensor, ent_row: Tensor) -> Tensor:
     N, C = dS.shape
     G, E = grp_ptr.numel() - 1, ent_row.numel()
     dY = torch.empty(E, C, dtype=torch.float32, device=dS.device)
-    tot = torch.empty(65 * C, dtype=torch.float32, device=dS.device)
+    tot = torch.empty(lib.gnan_rows_to_entries_scratch_floats(G, C, E), dtype=torch.float32, device=dS.device)
     with ops._timed("rows_to_entries"):
         check(lib.gnan_rows_to_entries(ptr(dS), N, G, C, ptr(grp_ptr), E, ptr(ent_row), ptr(tot), ptr(dY), stream_handle()),
               "gnan_rows_to_entries")

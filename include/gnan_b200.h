@@ -116,13 +116,14 @@ int gnan_mlp_entries_bwd(const float *val, const int64_t *grp_ptr, int64_t E, in
 /* Entry values <-> node rows (deterministic, no atomics). Group g's FIRST entry is the feature's baseline value, shared by
  * every row not listed among its exceptions:  S[r,:] = sum_g Y[base_g,:] + sum_{e in exceptions of row r} (Y[e,:] - Y[base_g(e),:]).
  * csr_ptr/csr_eid list the exception entries of each row, ent_grp[e] / ent_row[e] are an entry's group and row (-1 for a
- * baseline). S0 [C] and dStot [65*C] are scratch outputs (sum of the baselines; sum of all dS rows in the first C floats,
- * slab partial sums behind). */
+ * baseline). S0 [C] and dStot [gnan_rows_to_entries_scratch_floats(G,C,E)] are scratch outputs (sum of the baselines; sum of
+ * all dS rows in the first C floats, slab partial sums behind). */
+size_t gnan_rows_to_entries_scratch_floats(int32_t G, int32_t C, int64_t E);
 int gnan_entries_to_rows(const float *Y /* [E,C] */, int64_t N, int32_t G, int32_t C, const int64_t *grp_ptr,
                          const int64_t *csr_ptr /* [N+1] */, const int64_t *csr_eid, const int32_t *ent_grp /* [E] */,
                          float *S0 /* [C] */, float *S /* [N,C] */, gnan_stream_t stream);
 int gnan_rows_to_entries(const float *dS /* [N,C] */, int64_t N, int32_t G, int32_t C, const int64_t *grp_ptr, int64_t E,
-                         const int64_t *ent_row /* [E] */, float *dStot /* [65*C] */, float *dY /* [E,C] */, gnan_stream_t stream);
+                         const int64_t *ent_row /* [E] */, float *dStot /* scratch, see above */, float *dY /* [E,C] */, gnan_stream_t stream);
 
 /* out[s,:] = sum_{k in [seg_ptr[s], seg_ptr[s+1])} src[order[k],:]  — the deterministic backward of a row gather T = Tq[inv]
  * (the per-row rho inputs 1/((1+d)*cnt) of GNAN.py:65-67 take few distinct values: rho runs once per distinct value). */
