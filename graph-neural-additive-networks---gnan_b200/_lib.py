@@ -97,6 +97,14 @@ SIGNATURES = {
     "gnan_bce_with_logits": (c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "gnan_adam_step": (c_int, [c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_float, c_float, c_float,
                                c_float, c_void_p]),
+    "gnan_apsp_bfs16_workspace_bytes": (c_size_t, [c_int32, c_int32]),
+    "gnan_apsp_bfs16": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_size_t,
+                                c_void_p]),
+    "gnan_level_counts16": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int32, c_void_p]),
+    "gnan_aggregate_rows16_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int32, c_int32, c_void_p, c_void_p,
+                                          c_int32, c_void_p, c_void_p]),
+    "gnan_aggregate_rows16_bwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int, c_int32, c_int32, c_void_p, c_void_p,
+                                          c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gnan_hops_to_reference": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "gnan_hops_from_reference": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int32, c_void_p,
                                          c_void_p]),

@@ -184,8 +184,8 @@ def mlp_per_group(u, w1, b1, wh, bh, wo, bo, n_layers, dropout_p=0.0, seed=0, pr
 # dense row-block aggregation
 # ---------------------------------------------------------------------------------------------------------------------
 def _agg_dims(hop, T, S, per_row):
-    if hop.dtype != torch.uint8 or hop.dim() != 2:
-        raise TypeError("hop must be a uint8 [R, ld] matrix")
+    if hop.dtype not in (torch.uint8, torch.int16) or hop.dim() != 2:
+        raise TypeError("hop must be a uint8 (or, for deep graphs, int16) [R, ld] matrix")
     R, ld = hop.shape
     N, C = S.shape
     nbins, Cr = T.shape[-2], T.shape[-1]
@@ -263,8 +263,64 @@ agg_rows_fwd.register_autograd(_agg_backward, setup_context=_agg_setup)
 AGG_ALGO = "auto"      # "auto" | "cuda" | "tc": kernel family of aggregate_rows (gnan_b200.h: GNAN_AGG_*); tests force each
 
 
+# deep graphs: int16 hops (-1 = unreachable), direct kernels of csrc/wide.cu
+@torch.library.custom_op("gnan_b200::agg_rows16_fwd", mutates_args=())
+def agg_rows16_fwd(hop: Tensor, T: Tensor, rscale: Optional[Tensor], S: Tensor, per_row: bool) -> Tensor:
+    lib = load()
+    T, S = _f32(T, "T"), _f32(S, "S")
+    rscale = None if rscale is None else _f32(rscale, "rscale")
+    R, ld, N, C, nbins, Cr = _agg_dims(hop, T, S, per_row)
+    out = torch.empty(R, C, dtype=torch.float32, device=S.device)
+    with _timed("aggregate_rows_fwd_save"):
+        check(lib.gnan_aggregate_rows16_fwd(ptr(hop), R, N, ld, ptr(T), int(per_row), nbins, Cr, ptr(rscale), ptr(S), C, ptr(out),
+                                            stream_handle()), "gnan_aggregate_rows16_fwd")
+    return out
+
+
+@agg_rows16_fwd.register_fake
+def _(hop, T, rscale, S, per_row):
+    return S.new_empty(hop.shape[0], S.shape[1])
+
+
+@torch.library.custom_op("gnan_b200::agg_rows16_bwd", mutates_args=())
+def agg_rows16_bwd(hop: Tensor, T: Tensor, rscale: Optional[Tensor], S: Tensor, per_row: bool, g: Tensor) -> Tuple[Tensor, Tensor]:
+    lib = load()
+    T, S, g = _f32(T, "T"), _f32(S, "S"), _f32(g, "g")
+    rscale = None if rscale is None else _f32(rscale, "rscale")
+    R, ld, N, C, nbins, Cr = _agg_dims(hop, T, S, per_row)
+    dS, dT = torch.empty_like(S), torch.empty_like(T)
+    flags = torch.empty(max(R, 1), dtype=torch.uint8, device=S.device)
+    with _timed("aggregate_rows_bwd_saved"):
+        check(lib.gnan_aggregate_rows16_bwd(ptr(hop), R, N, ld, ptr(T), int(per_row), nbins, Cr, ptr(rscale), ptr(S), C, ptr(g), ptr(dS),
+                                            ptr(dT), ptr(flags), stream_handle()), "gnan_aggregate_rows16_bwd")
+    return dS, dT
+
+
+@agg_rows16_bwd.register_fake
+def _(hop, T, rscale, S, per_row, g):
+    return torch.empty_like(S), torch.empty_like(T)
+
+
+def _agg16_setup(ctx, inputs, output):
+    hop, T, rscale, S, per_row = inputs
+    ctx.save_for_backward(hop, T, rscale, S)
+    ctx.per_row = per_row
+
+
+def _agg16_backward(ctx, g):
+    hop, T, rscale, S = ctx.saved_tensors
+    dS, dT = agg_rows16_bwd(hop, T, rscale, S, ctx.per_row, g.contiguous())
+    return None, dT, None, dS, None
+
+
+agg_rows16_fwd.register_autograd(_agg16_backward, setup_context=_agg16_setup)
+
+
 def aggregate_rows(hop, T, S, rscale=None, per_row=False, algo=None):
-    """out[i,c] = sum_j T[(i,) b(hop[i,j]), c'] * rscale[i,b] * S[j,c] over a [R, ld] uint8 hop block; see gnan_b200.h."""
+    """out[i,c] = sum_j T[(i,) b(hop[i,j]), c'] * rscale[i,b] * S[j,c] over a [R, ld] uint8 hop block; see gnan_b200.h.
+    An int16 hop block (deep graphs, preprocess.apsp's fallback for hop distances > 254) takes the direct kernels of csrc/wide.cu."""
+    if hop.dtype == torch.int16:
+        return agg_rows16_fwd(hop, T, rscale, S, bool(per_row))
     save = torch.is_grad_enabled() and (T.requires_grad or S.requires_grad)
     return agg_rows_fwd(hop, T, rscale, S, bool(per_row), bool(save), _lib.AGG_ALGOS[algo or AGG_ALGO])[0]
 

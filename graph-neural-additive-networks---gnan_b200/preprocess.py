@@ -23,6 +23,7 @@ class HopData:
     """Compact distance data of one graph (or a row shard [row_begin, row_begin+R) of it).
 
     hop          uint8 [R, ld]  hop count, 255 = unreachable; columns >= N are padding
+                 (deep graphs, a hop distance > 254: int16 [R, ld], -1 = unreachable; see csrc/wide.cu and `wide`)
     level_counts int32 [R, nbins]  cnt[i,d] = #{j : hop[i,j] = d}, last column = #unreachable; nbins = D+2
     """
 
@@ -40,6 +41,11 @@ class HopData:
     def rows(self):
         return self.hop.shape[0]
 
+    @property
+    def wide(self):
+        """True for the int16 form (hop distances beyond 254)"""
+        return self.hop.dtype == torch.int16
+
     def to(self, device):
         return HopData(self.hop.to(device, non_blocking=True), self.level_counts.to(device, non_blocking=True),
                        self.num_nodes, self.row_begin)
@@ -48,6 +54,11 @@ class HopData:
         """(node_distances, normalization_matrix) as fp32 [R,N], bit-identical to pre_process_datasets.py:112-121."""
         lib = load()
         R, N = self.rows, self.num_nodes
+        if self.wide:                                     # deep graphs: same arithmetic (fp32 division) with device tensor ops
+            h = self.hop[:, :N].long()
+            nd = torch.where(h < 0, torch.zeros((), device=h.device), 1.0 / (h.float() + 1.0))
+            b = torch.where(h < 0, torch.full_like(h, self.nbins - 1), h.clamp(max=self.nbins - 1))
+            return nd, torch.gather(self.level_counts, 1, b).float()
         nd = torch.empty(R, N, dtype=torch.float32, device=self.hop.device)
         nm = torch.empty(R, N, dtype=torch.float32, device=self.hop.device)
         check(lib.gnan_hops_to_reference(ptr(self.hop), R, N, self.hop.shape[1], ptr(self.level_counts), self.nbins,
@@ -66,7 +77,7 @@ def from_reference_format(node_distances, normalization_matrix=None):
     pos = nd[nd > 0]
     dmax = int(torch.round(1.0 / pos.min() - 1.0).item()) if pos.numel() else 0
     if dmax > 254:
-        raise NotImplementedError(f"hop distance {dmax} > 254 does not fit the uint8 hop matrix")
+        return _from_reference_wide(nd, normalization_matrix, dmax)
     nbins = dmax + 2
     hop = torch.empty(R, hop_ld(N), dtype=torch.uint8, device=dev)
     cnt = torch.zeros(R, nbins, dtype=torch.int32, device=dev)
@@ -75,6 +86,47 @@ def from_reference_format(node_distances, normalization_matrix=None):
     check(lib.gnan_hops_from_reference(ptr(nd), ptr(nm), R, N, ptr(hop), hop.shape[1], ptr(cnt), nbins, ptr(flag),
                                        stream_handle()), "gnan_hops_from_reference")
     return HopData(hop, cnt, N)
+
+
+WIDE_MAX_LEVEL = 32766      # deepest level of the int16 hop matrix
+
+
+def _from_reference_wide(nd, normalization_matrix, dmax):
+    """from_reference_format for hop distances beyond 254: int16 hops (-1 = unreachable)"""
+    if dmax > WIDE_MAX_LEVEL:
+        raise NotImplementedError(f"hop distance {dmax} > {WIDE_MAX_LEVEL} does not fit the int16 hop matrix")
+    lib = load()
+    R, N = nd.shape
+    nbins = dmax + 2
+    hop = torch.full((R, hop_ld(N)), -1, dtype=torch.int16, device=nd.device)
+    h = torch.where(nd > 0, torch.round(1.0 / nd - 1.0), torch.full_like(nd, -1.0))
+    hop[:, :N] = h.to(torch.int16)
+    cnt = torch.zeros(R, nbins, dtype=torch.int32, device=nd.device)
+    if normalization_matrix is None:
+        check(lib.gnan_level_counts16(ptr(hop), R, N, hop.shape[1], ptr(cnt), nbins, stream_handle()), "gnan_level_counts16")
+    else:                                                  # the counts are whatever the caller's normaliser says (as the uint8 converter)
+        b = torch.where(h < 0, torch.full_like(h, float(nbins - 1)), h).long()
+        cnt.scatter_(1, b, torch.round(normalization_matrix.float()).to(torch.int32))
+    return HopData(hop, cnt, N)
+
+
+def _apsp_wide(rowptr, col, N, row_begin, row_end, device):
+    """Rows [row_begin,row_end) of the hop matrix of a graph whose diameter exceeds 254: int16 hops by a warp-per-source BFS,
+    then the level histogram sized by the deepest level found (one device sync)."""
+    lib = load()
+    R = row_end - row_begin
+    hop = torch.empty(R, hop_ld(N), dtype=torch.int16, device=device)
+    st = torch.zeros(2, dtype=torch.int32, device=device)              # [overflow, deepest level]
+    ws = torch.empty(max(lib.gnan_apsp_bfs16_workspace_bytes(N, R), 1), dtype=torch.uint8, device=device)
+    with _timed("apsp_bfs"):
+        check(lib.gnan_apsp_bfs16(ptr(rowptr), ptr(col), N, row_begin, row_end, ptr(hop), hop.shape[1], st.data_ptr(), st.data_ptr() + 4,
+                                  ptr(ws), ws.numel(), stream_handle()), "gnan_apsp_bfs16")
+    over, D = (int(v) for v in st.tolist())
+    if over:
+        raise NotImplementedError(f"a hop distance > {WIDE_MAX_LEVEL} does not fit the int16 hop matrix")
+    cnt = torch.empty(R, D + 2, dtype=torch.int32, device=device)
+    check(lib.gnan_level_counts16(ptr(hop), R, N, hop.shape[1], ptr(cnt), D + 2, stream_handle()), "gnan_level_counts16")
+    return HopData(hop, cnt, N, row_begin)
 
 
 def build_csr(edge_index, num_nodes, device, status=None):
@@ -179,11 +231,13 @@ def apsp(edge_index, num_nodes, device="cuda", row_begin=0, row_end=None, method
     if status & 2 and not _expanded:                                   # duplicate edges: weight-k emulation, then drop the virtual nodes
         ei2, n2 = _expand_multi_edges(edge_index, N, device)
         big = apsp(ei2, n2, device=device, row_begin=row_begin, row_end=row_end, method=method, _expanded=True)
+        if big.wide:
+            raise NotImplementedError("duplicate edges in a graph with hop distances > 254 are not supported")
         hop = torch.full((R, hop_ld(N)), _lib.HOP_UNREACHABLE, dtype=torch.uint8, device=device)
         hop[:, :N] = big.hop[:, :N]
         return HopData(hop, _trim_counts(_recount_levels(hop, N)) if R else cnt[:, :2], N, row_begin)
-    if R and over:
-        raise NotImplementedError("a hop distance > 254 does not fit the uint8 hop matrix")
+    if R and over:                                         # a level beyond 254: once more with int16 hops (csrc/wide.cu)
+        return _apsp_wide(rowptr, col, N, row_begin, row_end, device)
     return HopData(hop, _trim_counts(cnt) if R else cnt[:, :2], N, row_begin)
 
 

@@ -318,6 +318,25 @@ int gnan_apsp_bfs_batched_ex(const int32_t *rowptr, const int32_t *col, const in
                              int32_t *order_ws /* [B] scratch or NULL: graphs are then processed grouped by size class */,
                              gnan_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Deep graphs (csrc/wide.cu): hop distances > 254. The reference has no depth limit (pre_process_datasets.py:109-121), so the
+ * same path exists with an int16 hop matrix (-1 = unreachable, levels 0..32766): warp-per-source BFS (no level table: the depth
+ * is not known in advance; *max_level, zero-initialised by the caller, receives it and gnan_level_counts16 then builds the
+ * [R, nbins] histogram, last column = unreachable), and the aggregation in its direct form (table lookups per pair, float atomics
+ * for dT: not bit-reproducible). Slower than the uint8 kernels by design: taken only when the uint8 BFS reports an overflow.
+ * ---------------------------------------------------------------------------------------------- */
+size_t gnan_apsp_bfs16_workspace_bytes(int32_t N, int32_t n_sources);
+int gnan_apsp_bfs16(const int32_t *rowptr, const int32_t *col, int32_t N, int32_t src_begin, int32_t src_end, int16_t *hop,
+                    int64_t ld_hop, int32_t *overflow_flag, int32_t *max_level, void *workspace, size_t workspace_bytes,
+                    gnan_stream_t stream);
+int gnan_level_counts16(const int16_t *hop, int64_t R, int64_t N, int64_t ld_hop, int32_t *cnt, int32_t nbins, gnan_stream_t stream);
+int gnan_aggregate_rows16_fwd(const int16_t *hop, int64_t R, int64_t N, int64_t ld_hop, const float *T, int table_per_row,
+                              int32_t nbins, int32_t Cr, const float *rscale, const float *S, int32_t C, float *out,
+                              gnan_stream_t stream);
+int gnan_aggregate_rows16_bwd(const int16_t *hop, int64_t R, int64_t N, int64_t ld_hop, const float *T, int table_per_row,
+                              int32_t nbins, int32_t Cr, const float *rscale, const float *S, int32_t C, const float *g, float *dS,
+                              float *dT, uint8_t *row_flags_ws /* [R] scratch */, gnan_stream_t stream);
+
 /* reference-format converters (pre_process_datasets.py:112-121): fp32 node_distances / normalization_matrix <-> hops */
 int gnan_hops_to_reference(const uint8_t *hop, int64_t R, int64_t N, int64_t ld_hop, const int32_t *cnt, int32_t nbins,
                            float *node_distances, float *normalization_matrix, gnan_stream_t stream);

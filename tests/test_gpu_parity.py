@@ -138,8 +138,8 @@ def test_apsp_vs_oracle_random(n, deg, directed, method):
 
 @pytest.mark.parametrize("method", ["warp", "msbfs"])
 def test_apsp_path_graph_depth_limit(method):
-    """uint8 hop matrix: depth 254 is representable, 255 is refused loudly (the reference has no such limit, its fp32
-    matrices just do not fit any GPU at that size)."""
+    """uint8 hop matrix: depth 254 is the last one it represents; a deeper graph comes back in the int16 form (csrc/wide.cu; the
+    reference has no depth limit)."""
     from gnan_b200.preprocess import apsp
 
     def path(n):
@@ -149,8 +149,11 @@ def test_apsp_path_graph_depth_limit(method):
     i = torch.arange(255, device=DEV)
     assert torch.equal(hd.hop[:, :255].long(), (i[:, None] - i[None, :]).abs())
     assert hd.nbins == 256 and int(hd.level_counts[0, 254]) == 1 and int(hd.level_counts[:, -1].sum()) == 0
-    with pytest.raises(NotImplementedError):
-        apsp(path(256), 256, device=DEV, method=method)
+    deep = apsp(path(256), 256, device=DEV, method=method)
+    j = torch.arange(256, device=DEV)
+    assert deep.wide and deep.hop.dtype == torch.int16 and deep.nbins == 257
+    assert torch.equal(deep.hop[:, :256].long(), (j[:, None] - j[None, :]).abs())
+    assert int(deep.level_counts[0, 255]) == 1 and int(deep.level_counts[:, -1].sum()) == 0
 
 
 @pytest.mark.parametrize("G_,H,C,L", [(5, 64, 3, 3), (7, 16, 2, 2), (3, 32, 4, 4), (4, 8, 2, 1)])
