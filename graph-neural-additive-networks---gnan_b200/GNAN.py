@@ -30,7 +30,10 @@ class _Base(nn.Module):
 
     def _seed(self):
         self._calls = getattr(self, "_calls", 0) + 1
-        return (torch.initial_seed() * 0x9E3779B97F4A7C15 + self._calls * 0xD1B54A32D192ED03) & (2 ** 63 - 1)
+        # _seed_salt: the first global row of a row shard (dist.row_sharded_forward): the kernels key a mask on the LOCAL row
+        # index, so shards that share torch's seed would otherwise drop the same (local row, unit) pairs
+        salt = int(getattr(self, "_seed_salt", 0))
+        return (torch.initial_seed() * 0x9E3779B97F4A7C15 + self._calls * 0xD1B54A32D192ED03 + salt * 0xC2B2AE3D27D4EB4F) & (2 ** 63 - 1)
 
     def _seed_word(self):
         """Device-side half of the dropout seed: a counter advanced ON THE DEVICE by every dropout forward and snapshotted for

@@ -195,7 +195,11 @@ def row_sharded_forward(model, x_local: torch.Tensor, hop_data, sizes: Sequence[
     from . import ops
     dev = hop_data.hop.device
     cx = x_compressed if (x_compressed is not None and model._dedup_ok()) else None     # sparse.compress_features(x_local), built once
-    s_local = model._feature_sums(x_local, cx)                                  # [|V_r|, C]
+    model._seed_salt = int(getattr(hop_data, "row_begin", 0))                   # dropout masks differ between row shards
+    try:
+        s_local = model._feature_sums(x_local, cx)                              # [|V_r|, C]
+    finally:
+        model._seed_salt = 0
     s_full = all_gather_rows(s_local, sizes, group)                             # [N, C]
     flavor_input_norm = model.__class__.__module__.endswith(".GNAN") and model.__class__.__name__ == "TensorGNAN"
     if model.normalize_rho and flavor_input_norm:                               # GNAN.py:65-67

@@ -67,7 +67,7 @@ class TensorGNAN(_Base):
             raise ValueError(f"x has {x.shape[1]} features, model was built for {self.fs.groups}")
         p = self.fs.dropout if self.training else 0.0
         return ops.mlp_per_group(x, *self.fs.kernel_args(), dropout_p=p, seed=self._seed() if p > 0 else 0,
-                                 precision=self.precision).squeeze(-1)               # [N,K,1] -> [N,K]
+                                 precision=self.precision, seed_dev=self._seed_word() if p > 0 else None).squeeze(-1)   # [N,K,1] -> [N,K]
 
     def forward(self, inputs):
         if isinstance(inputs, PackedBatch):

@@ -150,7 +150,7 @@ def mlp(u, w1, b1, wh, bh, wo, bo, n_layers, dropout_p=0.0, seed=0, precision="f
 MAX_KERNEL_CHANNELS = 64      # gnan_mlp_* limit on C
 
 
-def mlp_per_group(u, w1, b1, wh, bh, wo, bo, n_layers, dropout_p=0.0, seed=0, precision="fp32"):
+def mlp_per_group(u, w1, b1, wh, bh, wo, bo, n_layers, dropout_p=0.0, seed=0, precision="fp32", seed_dev=None):
     """Y[r,g,:] = f_g(u[r,g]) WITHOUT the sum over groups -> [R,G,C] (the reference's `fx`, GNAN.py:57-62, which the NAM
     readout, models.py:374-381, and the interpretability plots need per feature).
 
@@ -175,7 +175,7 @@ def mlp_per_group(u, w1, b1, wh, bh, wo, bo, n_layers, dropout_p=0.0, seed=0, pr
         y = mlp(u[:, g0:g1].contiguous(), w1[g0:g1] if hid else w1, b1[g0:g1] if hid else b1,
                 wh[:, g0:g1].contiguous() if hid else wh, bh[:, g0:g1].contiguous() if hid else bh,
                 wo_x.view(gc, gc * C, -1), bo_x.view(gc, gc * C), n_layers, dropout_p=dropout_p,
-                seed=(seed + g0) if dropout_p > 0 else 0, precision=precision)
+                seed=(seed + g0) if dropout_p > 0 else 0, precision=precision, seed_dev=seed_dev if dropout_p > 0 else None)
         outs.append(y.view(R, gc, C))
     return outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)
 
