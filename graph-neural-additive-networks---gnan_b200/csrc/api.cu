@@ -56,3 +56,29 @@ int gnan_reduce_chunks(const float *part, int nchunk, size_t n, size_t stride, f
     GNAN_LAUNCH_OK();
     return GNAN_OK;
 }
+
+// the same for up to 6 (src, dst, n) segments that share chunk count and stride (the gradient arrays of one MLP backward): ONE launch
+__global__ void gnan_reduce_chunks_multi_kernel(GnanReduceSegs sg, int nchunk, size_t stride)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t step = (size_t)gridDim.x * blockDim.x;
+    for (; i < sg.total; i += step) {
+        int k = 0;
+        size_t off = i;
+        while (k + 1 < sg.count && off >= sg.n[k]) { off -= sg.n[k]; ++k; }
+        const float *src = sg.src[k] + off;
+        float s = 0.f;
+        for (int c = 0; c < nchunk; ++c) s += src[(size_t)c * stride];
+        sg.dst[k][off] = s;
+    }
+}
+
+int gnan_reduce_chunks_multi(const GnanReduceSegs &sg, int nchunk, size_t stride, cudaStream_t st)
+{
+    if (sg.count == 0 || sg.total == 0) return GNAN_OK;
+    size_t blocks = (sg.total + 255) / 256;
+    if (blocks > (size_t)gnan_sm_count() * 8) blocks = (size_t)gnan_sm_count() * 8;
+    gnan_reduce_chunks_multi_kernel<<<(unsigned)blocks, 256, 0, st>>>(sg, nchunk, stride);
+    GNAN_LAUNCH_OK();
+    return GNAN_OK;
+}

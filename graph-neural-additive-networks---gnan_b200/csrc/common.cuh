@@ -36,6 +36,18 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 // B200: 148 SMs. Queried once; used to size persistent grids.
 int gnan_sm_count();
 int gnan_reduce_chunks(const float *part, int nchunk, size_t n, size_t stride, float *out, cudaStream_t st);
+struct GnanReduceSegs {
+    const float *src[6];
+    float *dst[6];
+    size_t n[6], total;
+    int count;
+    void add(const float *s, float *d, size_t len)
+    {
+        if (!d || len == 0) return;
+        src[count] = s; dst[count] = d; n[count] = len; total += len; ++count;
+    }
+};
+int gnan_reduce_chunks_multi(const GnanReduceSegs &sg, int nchunk, size_t stride, cudaStream_t st);
 
 // Counter-based dropout mask: splitmix64 finaliser over (seed, flat element index). keep-probability 1-p.
 __device__ __forceinline__ uint32_t gnan_hash32(uint64_t seed, uint64_t idx)

@@ -833,14 +833,11 @@ extern "C" int gnan_mlp_bwd(const float *u, int64_t R, int64_t ldu, const gnan_m
     }
     if (rc) return rc;
     if (pl.nchunk > 1) {
-        struct Seg { const float *src; float *dst; size_t n; };
-        const Seg segs[6] = {{gp.w1, grads->w1, G * H}, {gp.b1, grads->b1, G * H}, {gp.wh, grads->wh, nh * G * H * H},
-                             {gp.bh, grads->bh, nh * G * H}, {gp.wo, grads->wo, G * C * H}, {gp.bo, grads->bo, G * C}};
-        for (const Seg &s : segs) {
-            if (!s.dst || s.n == 0) continue;
-            rc = gnan_reduce_chunks(s.src, pl.nchunk, s.n, ntot, s.dst, st);
-            if (rc) return rc;
-        }
+        GnanReduceSegs sg{};                                    // all six gradient arrays in one launch
+        sg.add(gp.w1, grads->w1, G * H); sg.add(gp.b1, grads->b1, G * H); sg.add(gp.wh, grads->wh, nh * G * H * H);
+        sg.add(gp.bh, grads->bh, nh * G * H); sg.add(gp.wo, grads->wo, G * C * H); sg.add(gp.bo, grads->bo, G * C);
+        rc = gnan_reduce_chunks_multi(sg, pl.nchunk, ntot, st);
+        if (rc) return rc;
     }
     return GNAN_OK;
 }
@@ -947,14 +944,11 @@ extern "C" int gnan_mlp_entries_bwd(const float *val, const int64_t *grp_ptr, in
     }
     if (rc) return rc;
     if (pl.nchunk > 1) {
-        struct Seg { const float *src; float *dst; size_t n; };
-        const Seg segs[6] = {{gp.w1, grads->w1, G * H}, {gp.b1, grads->b1, G * H}, {gp.wh, grads->wh, nh * G * H * H},
-                             {gp.bh, grads->bh, nh * G * H}, {gp.wo, grads->wo, G * C * H}, {gp.bo, grads->bo, G * C}};
-        for (const Seg &sg : segs) {
-            if (!sg.dst || sg.n == 0) continue;
-            rc = gnan_reduce_chunks(sg.src, pl.nchunk, sg.n, ntot, sg.dst, st);
-            if (rc) return rc;
-        }
+        GnanReduceSegs sg{};
+        sg.add(gp.w1, grads->w1, G * H); sg.add(gp.b1, grads->b1, G * H); sg.add(gp.wh, grads->wh, nh * G * H * H);
+        sg.add(gp.bh, grads->bh, nh * G * H); sg.add(gp.wo, grads->wo, G * C * H); sg.add(gp.bo, grads->bo, G * C);
+        rc = gnan_reduce_chunks_multi(sg, pl.nchunk, ntot, st);
+        if (rc) return rc;
     }
     return GNAN_OK;
 }

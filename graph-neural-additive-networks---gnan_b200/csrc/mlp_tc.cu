@@ -1288,14 +1288,11 @@ int gnan_mlp_tc_bwd_ex(const float *u, int64_t R, int64_t ldu, const gnan_mlp_pa
     }
     if (rc) return rc;
     if (slots > 1) {
-        struct Seg { const float *src; float *dst; size_t n; };
-        const Seg segs[5] = {{gp.w1, grads->w1, G * HID}, {gp.b1, grads->b1, G * HID}, {gp.wh, grads->wh, G * HID * HID},
-                             {gp.bh, grads->bh, G * HID}, {gp.wo, grads->wo, G * C * HID}};
-        for (const Seg &sg : segs) {
-            if (!sg.dst || sg.n == 0) continue;
-            rc = gnan_reduce_chunks(sg.src, slots, sg.n, ntot, sg.dst, st);
-            if (rc) return rc;
-        }
+        GnanReduceSegs sg{};                                    // the five gradient arrays in one launch
+        sg.add(gp.w1, grads->w1, G * HID); sg.add(gp.b1, grads->b1, G * HID); sg.add(gp.wh, grads->wh, G * HID * HID);
+        sg.add(gp.bh, grads->bh, G * HID); sg.add(gp.wo, grads->wo, G * C * HID);
+        rc = gnan_reduce_chunks_multi(sg, slots, ntot, st);
+        if (rc) return rc;
     }
     if (grads->bo) {
         if (grp_ptr) dbo_entries_kernel<<<(unsigned)ceil_div64((int64_t)G * C * 32, 256), 256, 0, st>>>(dS, grp_ptr, (int)G, (int)C, grads->bo);
