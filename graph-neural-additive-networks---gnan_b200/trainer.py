@@ -195,6 +195,23 @@ test_epoch.__test__ = False     # not a pytest test
 # ---------------------------------------------------------------------------------------------------------------------
 # the whole step as one CUDA graph
 # ---------------------------------------------------------------------------------------------------------------------
+class _no_gc_during_capture:
+    """Python's cyclic garbage collector may free an old torch.cuda.CUDAGraph (or any object whose destructor calls into CUDA) at an
+    arbitrary allocation; inside a stream capture that call is illegal and invalidates the capture ("operation not permitted when
+    stream is capturing"). Collect before, keep the collector off while capturing."""
+
+    def __enter__(self):
+        import gc
+        gc.collect()
+        self._was = gc.isenabled()
+        gc.disable()
+
+    def __exit__(self, *exc):
+        import gc
+        if self._was:
+            gc.enable()
+
+
 class CapturedStep:
     """forward + loss + backward + optimizer step of a FIXED-SHAPE input captured into one CUDA graph and replayed.
 
@@ -234,7 +251,7 @@ class CapturedStep:
         lib = load()
         n0 = lib.gnan_launch_count()
         # thread_local: the NCCL watchdog thread polls CUDA events while this thread captures
-        with torch.cuda.graph(self.graph, capture_error_mode="thread_local" if after_backward is not None else "global"):
+        with _no_gc_during_capture(), torch.cuda.graph(self.graph, capture_error_mode="thread_local" if after_backward is not None else "global"):
             self.loss = self._eager()
         self.kernel_launches = int(lib.gnan_launch_count() - n0)     # gnan_b200 kernels per replay (the counter is host-side)
 
@@ -337,7 +354,7 @@ class SizeBucketedSteps:
             torch.cuda.synchronize()
             e.graph = torch.cuda.CUDAGraph()
             opt.zero_grad(set_to_none=True)
-            with torch.cuda.graph(e.graph):
+            with _no_gc_during_capture(), torch.cuda.graph(e.graph):
                 body()
         finally:
             model.dedup = old_dedup

@@ -249,3 +249,23 @@ def test_value_sharing_of_compressed_features_cpu():
     moved = cx.clone_tensors()
     moved.copy_tensors_(cx)
     assert torch.equal(moved.shared.inv, sh.inv) and moved.nbytes() == cx.nbytes()
+
+
+def test_round2_host_logic_without_a_gpu():
+    """PackedBatch carrying only the fused normaliser; the optimizer and the fused losses refuse CPU tensors (no fallback)."""
+    import pytest
+    from gnan_b200 import _lib
+    from gnan_b200.optim import Adam
+    from gnan_b200.preprocess import PackedBatch
+    pk = PackedBatch(None, torch.zeros(4, dtype=torch.uint8), torch.tensor([0, 4]), torch.tensor([0, 2], dtype=torch.int32), None,
+                     level_rscale=torch.ones(2, 48))
+    assert pk.nbins == 48 and pk.num_graphs == 1 and pk.to("cpu").level_rscale.shape == (2, 48)
+    p = torch.nn.Parameter(torch.zeros(3))
+    p.grad = torch.ones(3)
+    with pytest.raises((TypeError, _lib.GnanError)):
+        Adam([p], lr=1e-3).step()
+    with pytest.raises(ValueError):
+        Adam([p], lr=-1.0)
+    from gnan_b200 import ops
+    with pytest.raises(_lib.GnanError):
+        ops.bce_with_logits(torch.zeros(3, requires_grad=True), torch.zeros(3))
