@@ -247,7 +247,7 @@ agg_bd_graph_dt_partial_kernel(int B, int nbins, int C, const float *__restrict_
             s3 = fmaf(g[(int64_t)(b + 3) * C + c], Q[(int64_t)(b + 3) * ne + e], s3);
         }
         for (; b < b1; ++b) s0 = fmaf(g[(int64_t)b * C + c], Q[(int64_t)b * ne + e], s0);
-        partial[(int64_t)blockIdx.x * ne + e] = (s0 + s1) + (s2 + s3);
+        partial[(int64_t)e * gridDim.x + blockIdx.x] = (s0 + s1) + (s2 + s3);      // [entry][slab]: the final sum reads it coalesced
     }
 }
 
@@ -262,11 +262,12 @@ agg_bd_graph_dt_final_kernel(int nslab, int nbins, int Cr, int C, const float *_
     const int d = t / Cr, cr = t % Cr;
     const int ne = nbins * C;
     float s = 0.f;
+    (void)ne;
     for (int sl = lane; sl < nslab; sl += 32) {
         if (Cr == 1) {
-            for (int c = 0; c < C; ++c) s += partial[(int64_t)sl * ne + d * C + c];
+            for (int c = 0; c < C; ++c) s += partial[(int64_t)(d * C + c) * nslab + sl];
         } else {
-            s += partial[(int64_t)sl * ne + d * C + cr];
+            s += partial[(int64_t)(d * C + cr) * nslab + sl];
         }
     }
 #pragma unroll

@@ -236,7 +236,7 @@ __device__ __forceinline__ int bv2_graph(const int32_t *__restrict__ rowptr, con
     return lvl_max;
 }
 
-// Graphs ordered by word count W = ceil(n/32), largest first (stable counting sort, one CTA): the warps of a CTA then run the
+// Graphs ordered by word count W = ceil(n/32), largest first (counting sort, one CTA): the warps of a CTA then run the
 // same instantiation of bv2_graph side by side (the four instantiations do not fit the instruction cache together: 25 % of the
 // stall samples were instruction fetches) and the expensive graphs start first.
 struct Cnt4 {
@@ -250,9 +250,8 @@ bv2_order_kernel(const int32_t *__restrict__ node_off, int B, int32_t *__restric
     using Scan = cub::BlockScan<Cnt4, 1024>;
     __shared__ typename Scan::TempStorage tmp;
     const int t = threadIdx.x;
-    const int per = (B + 1023) / 1024, b0 = min(B, t * per), b1 = min(B, b0 + per);
     Cnt4 mine{{0, 0, 0, 0}};
-    for (int b = b0; b < b1; ++b) {
+    for (int b = t; b < B; b += 1024) {                            // thread-strided: coalesced reads (the order inside a class is free)
         const int n = node_off[b + 1] - node_off[b];
         ++mine.c[3 - min(3, max(0, (n - 1) >> 5))];               // class 0 = the largest graphs
     }
@@ -263,7 +262,7 @@ bv2_order_kernel(const int32_t *__restrict__ node_off, int B, int32_t *__restric
     off[1] = total.c[0] + before.c[1];
     off[2] = total.c[0] + total.c[1] + before.c[2];
     off[3] = total.c[0] + total.c[1] + total.c[2] + before.c[3];
-    for (int b = b0; b < b1; ++b) {
+    for (int b = t; b < B; b += 1024) {
         const int n = node_off[b + 1] - node_off[b];
         order[off[3 - min(3, max(0, (n - 1) >> 5))]++] = b;
     }
