@@ -162,6 +162,44 @@ def test_pubmed_shaped_row_block_vs_float64_oracle(pubmed_case, dedup, precision
             kink_tol=KINK_TOL if (precision == "tf32x3" and not dedup) else None)
 
 
+# ---- ogbn-arxiv-like: 40 classes, dense continuous features (no shared evaluations), a row block of a larger graph ---------------
+@pytest.fixture(scope="module")
+def arxiv_like_case():
+    """The ogbn-arxiv configuration of bench.py at a size the float64 oracle finishes in seconds: 129 continuous features, 40
+    classes (the tcgen05 MLP's 64-column output layer and its five 8-channel backward passes, the 3-digit / 12-lane tensor-core
+    aggregation forward, the 4-digit backward over the rows with a loss), hop rows [0, 512) of a 4000-node graph."""
+    from gnan_b200.GNAN import TensorGNAN
+    from gnan_b200.preprocess import apsp
+    rng = np.random.default_rng(7)
+    n, K, C, R = 4000, 129, 40, 512
+    x = np.concatenate([rng.normal(size=(n, K - 1)).astype(np.float32), np.ones((n, 1), np.float32)], 1)
+    ei = bench.random_simple_graph(rng, n, 13800, 0)
+    wl = SimpleNamespace(n=n, K=K, C=C, x=torch.from_numpy(x), edge_index=torch.from_numpy(ei), y=torch.from_numpy(rng.integers(0, C, size=n)))
+    torch.manual_seed(0)
+    model = TensorGNAN(K, C, bench.L, bench.H, normalize_rho=True, is_graph_task=False, device=DEV).to(DEV)
+    model.fs.xavier_normal_(1.0); model.rho.xavier_normal_(1.0)
+    hd = apsp(wl.edge_index, n, device=DEV, row_begin=0, row_end=R)
+    idx = torch.randperm(R, generator=torch.Generator().manual_seed(1))[:200].sort().values
+    y = wl.y[:R][idx]
+    hop = torch.tensor(oapsp.apsp_rows(ei, n, R)).long()
+    cnt = torch.tensor(oapsp.level_counts(hop.numpy().astype(np.int32), hd.nbins)).long()
+    assert torch.equal(cnt.int(), hd.level_counts.cpu())
+    fs, rho = oracle_params(model, K, True)
+    S = feature_sums_chunked(fs, wl.x.double(), chunk=16)
+    W = gnan_lut.pair_weights(rho, hop, cnt, "input")
+    want = (W * S.unsqueeze(0)).sum(dim=1)
+    loss = torch.nn.functional.cross_entropy(want[idx], y, reduction="sum") / float(idx.numel())
+    loss.backward()
+    return SimpleNamespace(wl=wl, model=model, hd=hd, idx=idx, y=y, want=want.detach().numpy(), loss=float(loss.detach()), grads=want_grads_of(fs, rho))
+
+
+@pytest.mark.parametrize("precision,algo", [("fp32", "auto"), ("tf32x3", "auto"), ("fp32", "cuda")])
+def test_arxiv_like_row_block_vs_float64_oracle(arxiv_like_case, precision, algo):
+    out, grads = run_node(arxiv_like_case, False, precision, algo)
+    compare(f"arxiv-like[512 rows of 4000, C=40] {precision} agg={algo}", out, grads, arxiv_like_case.want, arxiv_like_case.grads, TOL[precision],
+            kink_tol=KINK_TOL if precision == "tf32x3" else None)
+
+
 # ---- graph task ----------------------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def mutag_case():
