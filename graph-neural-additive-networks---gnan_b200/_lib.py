@@ -37,6 +37,9 @@ SIGNATURES = {
                              c_void_p, c_size_t, c_void_p]),
     "gnan_mlp_bwd": (c_int, [c_void_p, c_int64, c_int64, ctypes.POINTER(MlpParams), c_float, c_uint64, c_void_p, c_int, c_void_p,
                              ctypes.POINTER(MlpGrads), c_void_p, c_size_t, c_void_p]),
+    "gnan_mlp_bwd_ext_supported": (c_int, [ctypes.POINTER(MlpParams), c_int]),
+    "gnan_mlp_bwd_ext": (c_int, [c_void_p, c_int64, c_int64, ctypes.POINTER(MlpParams), c_float, c_uint64, c_void_p, c_int, c_void_p,
+                                 c_void_p, c_void_p, ctypes.POINTER(MlpGrads), c_void_p, c_size_t, c_void_p]),
     "gnan_mlp_entries_workspace_bytes": (c_size_t, [c_int64, ctypes.POINTER(MlpParams), c_int, c_int]),
     "gnan_mlp_entries_fwd": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, ctypes.POINTER(MlpParams), c_void_p, c_void_p]),
     "gnan_mlp_entries_fwd_ex": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, ctypes.POINTER(MlpParams), c_int, c_void_p, c_void_p]),

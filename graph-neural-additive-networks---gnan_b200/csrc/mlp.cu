@@ -709,7 +709,7 @@ int gnan_mlp_tc_entries_fwd(const float *val, const int64_t *grp_ptr, int64_t E,
                             const gnan_mlp_params *p, int precision, float *Y, cudaStream_t st);
 int gnan_mlp_tc_bwd_ex(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *p, float dropout_p, uint64_t seed,
                        int precision, const float *dS, const gnan_mlp_grads *grads, void *ws, size_t ws_bytes, cudaStream_t st,
-                       const int64_t *grp_ptr, const uint64_t *seed_dev);
+                       const int64_t *grp_ptr, const uint64_t *seed_dev, const float *dh_ext, float *a1_ext);
 
 extern "C" size_t gnan_mlp_workspace_bytes(int64_t R, const gnan_mlp_params *p, int backward, int precision)
 {
@@ -770,9 +770,36 @@ extern "C" int gnan_mlp_fwd(const float *u, int64_t R, int64_t ldu, const gnan_m
     return GNAN_OK;
 }
 
+static int mlp_bwd_impl(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *p, float dropout_p,
+                        uint64_t seed, const uint64_t *seed_dev, int precision, const float *dS, const gnan_mlp_grads *grads,
+                        void *workspace, size_t workspace_bytes, gnan_stream_t stream, const float *dh_ext, float *a1_ext);
+
 extern "C" int gnan_mlp_bwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *p, float dropout_p,
                             uint64_t seed, const uint64_t *seed_dev, int precision, const float *dS, const gnan_mlp_grads *grads,
                             void *workspace, size_t workspace_bytes, gnan_stream_t stream)
+{
+    return mlp_bwd_impl(u, R, ldu, p, dropout_p, seed, seed_dev, precision, dS, grads, workspace, workspace_bytes, stream, nullptr, nullptr);
+}
+
+// 1 when gnan_mlp_bwd_ext covers the shape: the tcgen05 backward (H = 64, 3 layers) with more than 8 output channels
+extern "C" int gnan_mlp_bwd_ext_supported(const gnan_mlp_params *p, int precision)
+{
+    return p && precision != GNAN_PREC_FP32 && gnan_mlp_tc_bwd_supported(p, precision) && p->C > 8;
+}
+
+extern "C" int gnan_mlp_bwd_ext(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *p, float dropout_p, uint64_t seed,
+                                const uint64_t *seed_dev, int precision, const float *dS, const float *dh, float *a1,
+                                const gnan_mlp_grads *grads, void *workspace, size_t workspace_bytes, gnan_stream_t stream)
+{
+    GNAN_REQUIRE(p && gnan_mlp_bwd_ext_supported(p, precision), "mlp_bwd_ext: needs the tensor-core backward (H = 64, 3 layers, precision != fp32) and C > 8");
+    GNAN_REQUIRE(grads && grads->du == nullptr && grads->wo == nullptr, "mlp_bwd_ext: du is not available and dWo is the caller's GEMM (pass NULL)");
+    GNAN_REQUIRE(R == 0 || (dh && a1), "mlp_bwd_ext: NULL dh / a1");
+    return mlp_bwd_impl(u, R, ldu, p, dropout_p, seed, seed_dev, precision, dS, grads, workspace, workspace_bytes, stream, dh, a1);
+}
+
+static int mlp_bwd_impl(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *p, float dropout_p,
+                        uint64_t seed, const uint64_t *seed_dev, int precision, const float *dS, const gnan_mlp_grads *grads,
+                        void *workspace, size_t workspace_bytes, gnan_stream_t stream, const float *dh_ext, float *a1_ext)
 {
     int rc = check_params(p, R, ldu);
     if (rc) return rc;
@@ -803,7 +830,7 @@ extern "C" int gnan_mlp_bwd(const float *u, int64_t R, int64_t ldu, const gnan_m
         return GNAN_OK;
     }
     if (precision != GNAN_PREC_FP32 && !grads->du && gnan_mlp_tc_bwd_supported(p, precision))   // input gradients: fp32 kernel only
-        return gnan_mlp_tc_bwd_ex(u, R, ldu, p, dropout_p, seed, precision, dS, grads, workspace, workspace_bytes, st, nullptr, a.seed_dev);
+        return gnan_mlp_tc_bwd_ex(u, R, ldu, p, dropout_p, seed, precision, dS, grads, workspace, workspace_bytes, st, nullptr, a.seed_dev, dh_ext, a1_ext);
     const BwdPlan pl = plan_bwd(R, p);
     MlpGradPtrs gp;
     const size_t ntot = grad_floats(p);
@@ -911,7 +938,7 @@ extern "C" int gnan_mlp_entries_bwd(const float *val, const int64_t *grp_ptr, in
     cudaStream_t st = (cudaStream_t)stream;
     if (E > 0 && precision != GNAN_PREC_FP32 && gnan_mlp_tc_bwd_supported(p, precision))      // tcgen05 kernel, per-group row space
         return gnan_mlp_tc_bwd_ex(val, std::max<int64_t>(max_group_entries, 1), 1, p, 0.f, 0, precision, dY, grads, workspace,
-                                  workspace_bytes, st, grp_ptr, nullptr);
+                                  workspace_bytes, st, grp_ptr, nullptr, nullptr, nullptr);
     MlpKArgs a = make_args(val, E, 1, p, 0.f, 0);
     a.grp_ptr = grp_ptr;
     const size_t G = p->G, H = p->H, C = p->C, nh = p->n_layers - 2;

@@ -73,6 +73,10 @@ struct TcArgs {
     // backward over a channel slice [c_off, c_off + C) of Ctot channels (C > 8 runs as ceil(C/8) passes whose gradients add up:
     // everything downstream of dh = sum_c g_c wo_c is linear in g); chunk_off = first partial-gradient slot of the pass
     int Ctot, c_off, chunk_off;
+    // backward with the output layer outside the kernel (EXT: any C in ONE pass): dh_ext [R][G][HID] = dS Wo_g is read instead of
+    // contracted here, a1_ext [R][G][HID] (the last hidden activation) is written for the caller's dWo GEMM
+    const float *dh_ext;
+    float *a1_ext;
 };
 
 __device__ __forceinline__ uint64_t tc_drop_key(const TcArgs &a, int layer, int g, int64_t row, int unit)
@@ -630,7 +634,7 @@ __device__ long long g_tc_prof[16];
 #define TC_PROF(slot) do { } while (0)
 #endif
 
-template <int CT, bool DROP>
+template <int CT, bool DROP, bool EXT = false>
 __global__ void __launch_bounds__(BWD_THREADS, 1)   // 17 warps occupy 20 warp slots (5 per scheduler): 96 registers is the cap
 mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t ntiles)
 {
@@ -721,12 +725,14 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
                     for (int ks = 0; ks < 8; ++ks)
                         umma_tf32_ts(d1, tmem + colA_hi + ks * 8, umma_desc_kmajor(bl + ks * B_KSTEP, B_LBO, B_SBO), idesc, 1);
                 }
-                // dh[r][j] = sum_c g[r][c] wo[c][j]: one K-step (K = 8 channels) per split term
-                const uint32_t wkh = smem_u32(sm.wok_hi), wkl = smem_u32(sm.wok_lo);
-                umma_tf32_ts(tmem + colDH, tmem + colG_hi, umma_desc_kmajor(wkh, 128, 256), idesc, 0);
-                if (!a.single_pass) {
-                    umma_tf32_ts(tmem + colDH, tmem + colG_lo, umma_desc_kmajor(wkh, 128, 256), idesc, 1);
-                    umma_tf32_ts(tmem + colDH, tmem + colG_hi, umma_desc_kmajor(wkl, 128, 256), idesc, 1);
+                // dh[r][j] = sum_c g[r][c] wo[c][j]: one K-step (K = 8 channels) per split term (EXT: dh comes from global memory)
+                if (!EXT) {
+                    const uint32_t wkh = smem_u32(sm.wok_hi), wkl = smem_u32(sm.wok_lo);
+                    umma_tf32_ts(tmem + colDH, tmem + colG_hi, umma_desc_kmajor(wkh, 128, 256), idesc, 0);
+                    if (!a.single_pass) {
+                        umma_tf32_ts(tmem + colDH, tmem + colG_lo, umma_desc_kmajor(wkh, 128, 256), idesc, 1);
+                        umma_tf32_ts(tmem + colDH, tmem + colG_hi, umma_desc_kmajor(wkl, 128, 256), idesc, 1);
+                    }
                 }
                 umma_commit(smem_u32(&sm.d1_full));
             }
@@ -796,7 +802,7 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
             const bool ok = blockIdx.x < ntiles && row < nrow;
             x_n = ok ? __ldg(ub + row * ustride) : 0.f;
 #pragma unroll
-            for (int c = 0; c < CT; ++c) gv_n[c] = (ok && c < a.C && part == 0) ? __ldg(dS + row * a.Ctot + c) : 0.f;
+            for (int c = 0; c < CT; ++c) gv_n[c] = (!EXT && ok && c < a.C && part == 0) ? __ldg(dS + row * a.Ctot + c) : 0.f;
         }
         // dWo phase of tile `tp` (parity php): a1 recomputed from D1[php], staged to the scratch tile (sZ, free once MMA3 of
         // that tile is done), dWo[c][j] += g[r][c] a1[r][j]. Runs while the tensor core works on the NEXT tile's MMA1.
@@ -842,7 +848,7 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
             const bool okn = tn < ntiles && rown < nrow;
             x_n = 0.f;
             if (okn) x_n = ldg_prefetch(ub + rown * ustride);
-            if (part == 0) {                                   // only these threads need dS: stage it for the dh MMA and the dWo phase
+            if (!EXT && part == 0) {                           // only these threads need dS: stage it for the dh MMA and the dWo phase
                 uint32_t gh[CT_MAX], gl[CT_MAX];
 #pragma unroll
                 for (int c = 0; c < CT_MAX; ++c) {
@@ -893,16 +899,26 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
                 sm.sH_hi[tidx(c0 + i, r)] = __uint_as_float(hi[i]);
                 sm.sH_lo[tidx(c0 + i, r)] = __uint_as_float(lo[i]);
             }
-            if (it > 0) dwo_phase(t - gridDim.x, ph ^ 1);
+            if (!EXT && it > 0) dwo_phase(t - gridDim.x, ph ^ 1);
             TC_PROF(6);
             // ---- [D] epiC
+            uint32_t dhv[NC];
+            if (EXT) {                                         // dh of this (row, feature) straight from the caller's GEMM; the loads
+                const float4 *src = reinterpret_cast<const float4 *>(a.dh_ext + ((size_t)row * a.G + g) * HID + c0);   // fly under MMA1
+#pragma unroll
+                for (int j4 = 0; j4 < NC / 4; ++j4) {
+                    const float4 v = row < nrow ? __ldg(src + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    dhv[j4 * 4 + 0] = __float_as_uint(v.x); dhv[j4 * 4 + 1] = __float_as_uint(v.y);
+                    dhv[j4 * 4 + 2] = __float_as_uint(v.z); dhv[j4 * 4 + 3] = __float_as_uint(v.w);
+                }
+            }
             mbar_wait(smem_u32(&sm.d1_full), ph);
             tc_fence_after();
             TC_PROF(1);
             {
-                uint32_t d[NC], dhv[NC];
+                uint32_t d[NC];
                 IO::ld(lane_base + (ph ? colD1b : colD1) + c0, d);
-                IO::ld(lane_base + colDH + c0, dhv);
+                if (!EXT) IO::ld(lane_base + colDH + c0, dhv);
                 tmem_wait_ld();
                 float dz[NC];
 #pragma unroll
@@ -917,7 +933,15 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
                         if (DROP) m *= gnan_dropout_mul(a.seed, tc_drop_key(a, 1, g, row, c0 + jj), a.drop_thresh, a.drop_scale);
                         dz[jj] = __uint_as_float(dhv[jj]) * m;
                         split_tf32(dz[jj], hi[jj], lo[jj]);
+                        if (EXT) d[jj] = __float_as_uint(act * m);           // a1 (after dropout) for the caller's dWo GEMM
                     }
+                }
+                if (EXT && row < nrow) {
+                    float4 *dst = reinterpret_cast<float4 *>(a.a1_ext + ((size_t)row * a.G + g) * HID + c0);
+#pragma unroll
+                    for (int j4 = 0; j4 < NC / 4; ++j4)
+                        dst[j4] = make_float4(__uint_as_float(d[j4 * 4 + 0]), __uint_as_float(d[j4 * 4 + 1]),
+                                              __uint_as_float(d[j4 * 4 + 2]), __uint_as_float(d[j4 * 4 + 3]));
                 }
                 IO::st(lane_base + colA_hi + c0, hi);
                 if (!a.single_pass) IO::st(lane_base + colA_lo + c0, lo);
@@ -976,7 +1000,7 @@ mlp_tc_bwd_kernel(TcArgs a, const float *__restrict__ dS, TcGradPtrs gp, int64_t
             const int64_t tl = (int64_t)blockIdx.x + (int64_t)(it - 1) * gridDim.x;
             mbar_wait(smem_u32(&sm.d3_full), (it - 1) & 1);
             tc_fence_after();
-            dwo_phase(tl, (it - 1) & 1);
+            if (!EXT) dwo_phase(tl, (it - 1) & 1);
         }
         // ---- write this CTA's partial gradients (everything but dW2)
         const size_t off = (size_t)(blockIdx.x + a.chunk_off) * gp.chunk_stride;
@@ -1116,6 +1140,7 @@ TcArgs make_tc_args(const float *u, int64_t R, int64_t ldu, const gnan_mlp_param
     a.prof = (getenv("GNAN_TC_PROF") != nullptr ? 1 : 0) | (getenv("GNAN_TC_SKIP3") != nullptr ? 2 : 0);
     a.grp_ptr = nullptr;
     a.Ctot = p->C; a.c_off = 0; a.chunk_off = 0;
+    a.dh_ext = nullptr; a.a1_ext = nullptr;
     return a;
 }
 
@@ -1175,6 +1200,21 @@ TcBwdPlan plan_tc_bwd(int64_t R, const gnan_mlp_params *p)
     pl.nchunk = std::max(nchunk, 1);
     return pl;
 }
+int launch_tc_bwd_ext(const TcArgs &a, const TcBwdPlan &pl, const float *dS, const TcGradPtrs &gp, cudaStream_t st)
+{
+    const size_t smem = sizeof(BwdSmem) + 1024;
+    dim3 grid((unsigned)pl.nchunk, (unsigned)a.G);
+    if (a.drop_thresh) {
+        GNAN_CUDA(cudaFuncSetAttribute(mlp_tc_bwd_kernel<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mlp_tc_bwd_kernel<1, true, true><<<grid, BWD_THREADS, smem, st>>>(a, dS, gp, pl.ntile);
+    } else {
+        GNAN_CUDA(cudaFuncSetAttribute(mlp_tc_bwd_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mlp_tc_bwd_kernel<1, false, true><<<grid, BWD_THREADS, smem, st>>>(a, dS, gp, pl.ntile);
+    }
+    GNAN_LAUNCH_OK();
+    return GNAN_OK;
+}
+
 template <int CT>
 int launch_tc_bwd(const TcArgs &a, const TcBwdPlan &pl, const float *dS, const TcGradPtrs &gp, cudaStream_t st)
 {
@@ -1247,11 +1287,12 @@ int gnan_mlp_tc_entries_fwd(const float *val, const int64_t *grp_ptr, int64_t E,
 // grp_ptr != NULL: entries mode, u = val[E], R = the largest group (sizes the row chunks), dS = dY[E,C]
 int gnan_mlp_tc_bwd_ex(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *p, float dropout_p, uint64_t seed,
                        int precision, const float *dS, const gnan_mlp_grads *grads, void *ws, size_t ws_bytes, cudaStream_t st,
-                       const int64_t *grp_ptr, const uint64_t *seed_dev)
+                       const int64_t *grp_ptr, const uint64_t *seed_dev, const float *dh_ext, float *a1_ext)
 {
     const TcBwdPlan pl = plan_tc_bwd(R, p);
     const size_t G = p->G, C = p->C, ntot = tc_grad_floats(p);
-    const int npass = tc_bwd_passes(p), slots = pl.nchunk * npass;
+    const bool ext = dh_ext != nullptr && a1_ext != nullptr && grp_ptr == nullptr;      // output layer outside: one pass for any C
+    const int npass = ext ? 1 : tc_bwd_passes(p), slots = pl.nchunk * npass;
     TcGradPtrs gp;
     if (slots > 1) {
         const size_t need = sizeof(float) * (size_t)slots * ntot;
@@ -1277,7 +1318,12 @@ int gnan_mlp_tc_bwd_ex(const float *u, int64_t R, int64_t ldu, const gnan_mlp_pa
     int rc = GNAN_OK;
     if (npass > 1)     // a pass writes only its own channel slice of dWo: the other slots' slices must read as zero in the reduction
         GNAN_CUDA(cudaMemsetAsync(ws, 0, sizeof(float) * (size_t)slots * ntot, st));
-    for (int ps = 0; ps < npass && !rc; ++ps) {
+    if (ext) {
+        a.dh_ext = dh_ext; a.a1_ext = a1_ext;
+        gp.wo = nullptr;                                        // dWo = dS^T a1 is the caller's GEMM
+        rc = launch_tc_bwd_ext(a, pl, dS, gp, st);
+    }
+    for (int ps = 0; ps < npass && !rc && !ext; ++ps) {
         a.c_off = ps * CT_MAX;
         a.C = std::min<int>(CT_MAX, (int)C - a.c_off);
         a.chunk_off = ps * pl.nchunk;
@@ -1290,7 +1336,8 @@ int gnan_mlp_tc_bwd_ex(const float *u, int64_t R, int64_t ldu, const gnan_mlp_pa
     if (slots > 1) {
         GnanReduceSegs sg{};                                    // the five gradient arrays in one launch
         sg.add(gp.w1, grads->w1, G * HID); sg.add(gp.b1, grads->b1, G * HID); sg.add(gp.wh, grads->wh, G * HID * HID);
-        sg.add(gp.bh, grads->bh, G * HID); sg.add(gp.wo, grads->wo, G * C * HID);
+        sg.add(gp.bh, grads->bh, G * HID);
+        if (!ext) sg.add(gp.wo, grads->wo, G * C * HID);
         rc = gnan_reduce_chunks_multi(sg, slots, ntot, st);
         if (rc) return rc;
     }

@@ -64,6 +64,20 @@ def _f32(t: Tensor, name: str) -> Tensor:
     return t.contiguous()
 
 
+MLP_EXT_MAX_BYTES = 24 << 30      # dh + a1 buffers of the one-pass backward for C > 8 (beyond this the channel-slice passes run)
+
+
+class _fp32_matmul:
+    """torch.matmul in full fp32 (the GEMMs around gnan_mlp_bwd_ext must not drop to TF32 even if the caller enabled it globally)"""
+
+    def __enter__(self):
+        self._was = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self._was
+
+
 def _mlp_params(w1, b1, wh, bh, wo, bo, n_layers):
     G, C = wo.shape[0], wo.shape[1]
     H = wo.shape[2] if n_layers >= 2 else 0
@@ -106,8 +120,19 @@ def mlp_bwd(u: Tensor, w1: Tensor, b1: Tensor, wh: Tensor, bh: Tensor, wo: Tenso
     R = u.shape[0]
     outs = [torch.empty_like(t) for t in (w1, b1, wh, bh, wo, bo)]
     outs.append(torch.empty((R, G) if need_du else (0,), dtype=torch.float32, device=u.device))
-    g = MlpGrads(*[ptr(t) for t in outs[:6]], ptr(outs[6]) if need_du else None)
     ws = _ws(lib.gnan_mlp_workspace_bytes(R, p, 1, precision), u.device)
+    if (not need_du and R > 0 and lib.gnan_mlp_bwd_ext_supported(p, precision) and 2 * R * G * H * 4 <= MLP_EXT_MAX_BYTES):
+        # more than 8 output channels on the tensor-core path: the output layer runs as two plain GEMMs around ONE pass of the
+        # kernel (dh = dS Wo in, a1 out, dWo = dS^T a1) instead of ceil(C/8) passes that each repeat the recompute
+        with _timed("mlp_bwd"), _fp32_matmul():
+            dh = torch.matmul(dS, wo.permute(1, 0, 2).reshape(C, G * H))                       # [R, G*H]
+            a1 = torch.empty(R, G * H, dtype=torch.float32, device=u.device)
+            g = MlpGrads(ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), ptr(outs[3]), None, ptr(outs[5]), None)
+            check(lib.gnan_mlp_bwd_ext(ptr(u), R, u.shape[1], p, float(dropout_p), int(seed) & (2 ** 64 - 1), ptr(seed_dev), precision,
+                                       ptr(dS), ptr(dh), ptr(a1), g, ptr(ws), ws.numel(), stream_handle()), "gnan_mlp_bwd_ext")
+            outs[4].copy_(torch.matmul(dS.t(), a1).view(C, G, H).permute(1, 0, 2))             # dWo[g,c,:] = sum_r dS[r,c] a1[r,g,:]
+        return tuple(outs)
+    g = MlpGrads(*[ptr(t) for t in outs[:6]], ptr(outs[6]) if need_du else None)
     with _timed("mlp_bwd"):
         check(lib.gnan_mlp_bwd(ptr(u), R, u.shape[1], p, float(dropout_p), int(seed) & (2 ** 64 - 1), ptr(seed_dev), precision, ptr(dS),
                                g, ptr(ws), ws.numel(), stream_handle()), "gnan_mlp_bwd")

@@ -94,6 +94,17 @@ int gnan_mlp_bwd(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *
                  const uint64_t *seed_dev, int precision, const float *dS /* [R,C] */, const gnan_mlp_grads *grads,
                  void *workspace, size_t workspace_bytes, gnan_stream_t stream);
 
+/* gnan_mlp_bwd with the OUTPUT LAYER outside the kernel, for more than 8 output channels on the tensor-core path (H = 64, 3
+ * layers, precision != fp32): the caller supplies dh [R,G,64] = dS Wo_g (one plain GEMM: [R,C] x [C, G*64]) and receives
+ * a1 [R,G,64], the last hidden activation, from which dWo_g = dS^T a1_g is a second plain GEMM; everything else (d bo included)
+ * comes back in `grads` (grads->wo and grads->du must be NULL). One pass over the rows for any C instead of ceil(C/8):
+ * models.py / GNAN.py shape functions with 40 classes (ogbn-arxiv), GNAN.py:57-62 backward. */
+int gnan_mlp_bwd_ext_supported(const gnan_mlp_params *p, int precision);
+int gnan_mlp_bwd_ext(const float *u, int64_t R, int64_t ldu, const gnan_mlp_params *p, float dropout_p, uint64_t seed,
+                     const uint64_t *seed_dev, int precision, const float *dS, const float *dh /* [R,G,64] */,
+                     float *a1 /* [R,G,64] out */, const gnan_mlp_grads *grads, void *workspace, size_t workspace_bytes,
+                     gnan_stream_t stream);
+
 /* Entries mode: the shape functions on a COMPRESSED feature matrix (same reference lines as gnan_mlp_fwd/bwd). When
  * dropout is off, rows that carry the same value in a feature column share one evaluation of that feature's MLP (the zeros
  * of a bag-of-words matrix, the off entries of a one-hot encoding, the constant column: datasets.py:94).

@@ -698,7 +698,7 @@ def test_mlp_tensor_core_vs_oracle(R, G_, C, precision, tol, gtol):
     (measured 7e-7 / 3e-6). Single-pass tf32 has the stated looser bounds 5e-3 (outputs) / 5e-2 (gradients: its 1e-3
     forward noise flips ReLU masks). Inputs are drawn with every float64 pre-activation at least 2e-5 from zero so that
     no mask flips under the 1e-6 rounding differences of the split. C > 8: forward with an N = 16..64 output-layer MMA (separate
-    hi / lo operand blocks), backward as ceil(C/8) passes over 8-channel slices whose partial gradients add up."""
+    hi / lo operand blocks), backward in ONE pass with the output layer as two plain GEMMs around the kernel (gnan_mlp_bwd_ext)."""
     from gnan_b200 import ops
     H, L = 64, 3
     rng = np.random.default_rng(R * 11 + G_)
@@ -750,6 +750,50 @@ def test_mlp_tensor_core_backward_with_dropout_matches_fp32_path():
     from gnan_b200 import ops
     rng = np.random.default_rng(6)
     R, G_, H, C, L = 900, 6, 64, 7, 3
+    p = rand_mlp(rng, G_, H, C, L)
+    u = torch.tensor(rng.normal(size=(R, G_))).float().to(DEV)
+    dS = torch.tensor(rng.normal(size=(R, C))).float().to(DEV)
+    grads = {}
+    for prec in ("fp32", "tf32x3"):
+        d = {k: v.to(DEV).requires_grad_(True) for k, v in p.items()}
+        out = ops.mlp(u, d["w1"], d["b1"], d["wh"], d["bh"], d["wo"], d["bo"], L, dropout_p=0.3, seed=5, precision=prec)
+        (out * dS).sum().backward()
+        grads[prec] = {k: v.grad.cpu().numpy() for k, v in d.items()}
+    for k in p:
+        assert G.rel_err(grads["tf32x3"][k], grads["fp32"][k]) < 2e-4, k     # same masks; a kink may flip under different rounding
+
+
+@pytest.mark.parametrize("R,G_,C", [(700, 5, 9), (900, 3, 40), (300, 2, 64)])
+def test_mlp_tensor_core_backward_channel_slices_match_one_pass(R, G_, C, monkeypatch):
+    """C > 8 has two tensor-core backward routes: gnan_mlp_bwd_ext (one pass, output layer as GEMMs outside; the default) and
+    gnan_mlp_bwd's ceil(C/8) channel-slice passes (taken when the dh / a1 buffers would exceed ops.MLP_EXT_MAX_BYTES). Both
+    against the float64 oracle at 1e-5, and against each other."""
+    from gnan_b200 import ops
+    H, L = 64, 3
+    rng = np.random.default_rng(R + C)
+    p = rand_mlp(rng, G_, H, C, L)
+    u = kink_free_inputs(rng, p, R, G_, 2e-5, L)
+    dS = torch.tensor(rng.normal(size=(R, C))).float()
+    q = oracle_params(p, L)
+    (gnan_lut.feature_sums(q, u.double()) * dS.double()).sum().backward()
+    grads = {}
+    for route, cap in (("ext", ops.MLP_EXT_MAX_BYTES), ("slices", 0)):
+        monkeypatch.setattr(ops, "MLP_EXT_MAX_BYTES", cap)
+        d = {k: v.to(DEV).requires_grad_(True) for k, v in p.items()}
+        out = ops.mlp(u.to(DEV), d["w1"], d["b1"], d["wh"], d["bh"], d["wo"], d["bo"], L, precision="tf32x3")
+        (out * dS.to(DEV)).sum().backward()
+        grads[route] = {k: v.grad.cpu().numpy() for k, v in d.items()}
+        for k in p:
+            assert G.rel_err(grads[route][k], q[k].grad.numpy()) < TOL, (route, k)
+    for k in p:
+        assert G.rel_err(grads["ext"][k], grads["slices"][k]) < TOL, k
+
+
+def test_mlp_tensor_core_one_pass_backward_with_dropout_matches_fp32_path():
+    """gnan_mlp_bwd_ext with dropout: a1 leaves the kernel AFTER the mask, so dWo = dS^T a1 sees the same masks as the fp32 kernels"""
+    from gnan_b200 import ops
+    rng = np.random.default_rng(16)
+    R, G_, H, C, L = 900, 6, 64, 40, 3
     p = rand_mlp(rng, G_, H, C, L)
     u = torch.tensor(rng.normal(size=(R, G_))).float().to(DEV)
     dS = torch.tensor(rng.normal(size=(R, C))).float().to(DEV)
