@@ -382,8 +382,9 @@ def run_workload(args, env, name, *, steps, warmup, classes=0, compare_legs=Fals
     import torch.distributed as dist
     from gnan_b200 import ops
     from gnan_b200 import dist as gdist
-    from gnan_b200.preprocess import HopData, PackedBatch, apsp, apsp_batched
+    from gnan_b200.preprocess import HopData, LocalEdges, PackedBatch, apsp, apsp_batched
     from gnan_b200.sparse import compress_features
+    from gnan_b200.packed import HostBundle
     from gnan_b200.trainer import CapturedStep
     from gnan_b200.optim import Adam as FusedAdam
     world, rank, dev, flush, lib = env.world, env.rank, env.dev, env.flush, env.lib
@@ -417,27 +418,32 @@ def run_workload(args, env, name, *, steps, warmup, classes=0, compare_legs=Fals
         else:
             b0, e0, sizes = 0, wl.n, [wl.n]
             hd = apsp(wl.edge_index, wl.n, device=dev)                  # GPU preprocessing (not part of the timed step)
-        x_h = wl.x[b0:e0].contiguous().pin_memory()
+        x_h = wl.x[b0:e0].contiguous()
         big = hd.hop.numel() > (2 << 30)            # do not stage tens of GB in pinned host memory: no hop copy in the e2e leg
-        hop_h = None if big else hd.hop.cpu().pin_memory()
-        cnt_h = hd.level_counts.cpu().pin_memory()
+        hop_h = None if big else hd.hop.cpu()
+        cnt_h = hd.level_counts.cpu()
         idx_d = wl.train_mask[b0:e0].nonzero().flatten().to(dev)
         yl_d = wl.y[b0:e0].to(dev)[idx_d]
         n_train = float(wl.train_mask.sum())
         n_train_local = int(idx_d.numel())
         x_d = x_h.to(dev)
         cx = compress_features(x_d) if model.dedup else None                           # once per dataset (per row shard), like the hop matrix
-        cx_h = None if cx is None else cx.compact_host().pin_memory()      # int32 index arrays on the host side
+        cx_h = None if cx is None else cx.compact_host()      # narrow index arrays on the host side
         data_d = SimpleNamespace(x=x_d, hop_data=hd, x_compressed=cx)
         x_bytes = x_h.numel() * 4 if cx is None else cx_h.nbytes()
         h2d = x_bytes + (0 if big else hop_h.numel()) + cnt_h.numel() * 4
 
-        def load_host():
-            hop_d = hd.hop if big else hop_h.to(dev, non_blocking=True)
-            h = HopData(hop_d, cnt_h.to(dev, non_blocking=True), wl.n, b0)
-            if cx is None:
-                return SimpleNamespace(x=x_h.to(dev, non_blocking=True), hop_data=h, x_compressed=None)
-            return SimpleNamespace(x=None, hop_data=h, x_compressed=cx_h.to(dev))
+        host_parts = ([x_h] if cx is None else cx_h._tensors()) + ([] if big else [hop_h]) + [cnt_h]
+
+        def assemble(views):                                           # the step's input object over typed views of a staging buffer
+            it = iter(views)
+            xx = next(it) if cx is None else None
+            c = None if cx is None else cx_h._map(lambda t: next(it))
+            hop_d = hd.hop if big else next(it)
+            return SimpleNamespace(x=xx, hop_data=HopData(hop_d, next(it), wl.n, b0), x_compressed=c)
+
+        def widen(d):                                                  # eager steps read the compact copy through widened tensors
+            return d if d.x_compressed is None else SimpleNamespace(x=d.x, hop_data=d.hop_data, x_compressed=d.x_compressed.to(dev))
 
         def loss_of(data):
             if sharded:
@@ -454,32 +460,48 @@ def run_workload(args, env, name, *, steps, warmup, classes=0, compare_legs=Fals
         in_step_apsp = wl.name == "mol"
         node_off_h = wl.node_off.numpy()
         pk = apsp_batched(wl.edge_index, node_off_h, device=dev, x=wl.x.to(dev), y=wl.y.to(dev))
-        host = PackedBatch(wl.x.pin_memory(), pk.hop.cpu().pin_memory(), pk.hop_off.cpu().pin_memory(), pk.node_off.cpu().pin_memory(),
-                           pk.level_counts.cpu().pin_memory(), wl.y.pin_memory(), pk.max_nodes)
+        host = PackedBatch(wl.x, pk.hop.cpu(), pk.hop_off.cpu(), pk.node_off.cpu(),
+                           pk.level_counts.cpu(), wl.y, pk.max_nodes)
         cx = compress_features(pk.x) if model.dedup else None
-        cx_h = None if cx is None else cx.compact_host().pin_memory()      # int32 index arrays on the host side
+        cx_h = None if cx is None else cx.compact_host()      # narrow index arrays on the host side
         pk.x_compressed = cx
         data_d = pk
         x_bytes = host.x.numel() * 4 if cx is None else cx_h.nbytes()
         h2d = x_bytes + sum(t.numel() * t.element_size() for t in (host.hop, host.hop_off, host.node_off, host.level_counts, host.y))
         if in_step_apsp:                                                # the step starts from the raw edge list
             ei_d, noff_d, hoff_d, x_d, y_d = wl.edge_index.to(dev), pk.node_off, pk.hop_off, wl.x.to(dev), wl.y.to(dev)
-            ei_h, noff_h, hoff_h = wl.edge_index.pin_memory(), pk.node_off.cpu().pin_memory(), pk.hop_off.cpu().pin_memory()
+            # host form of the edge list: uint8 endpoints inside their graph + per-graph edge offsets (2 bytes per directed edge
+            # cross PCIe; gnan_edges_from_local rebuilds the int64 [2,E] edge_index on the device inside the timed step)
+            ei_h = LocalEdges.from_edge_index(wl.edge_index, node_off_h)
+            noff_h, hoff_h = pk.node_off.cpu(), pk.hop_off.cpu()
             data_d = (ei_d, noff_d, hoff_d, x_d, y_d, cx)
-            h2d = x_bytes + sum(t.numel() * t.element_size() for t in (ei_h, noff_h, hoff_h, host.y))
+            h2d = x_bytes + ei_h.nbytes() + sum(t.numel() * t.element_size() for t in (noff_h, hoff_h, host.y))
             apsp_status = []
 
-        def load_host():
-            c = None if cx is None else cx_h.to(dev)
-            xx = host.x.to(dev, non_blocking=True) if cx is None else None
+        feat_parts = [host.x] if cx is None else cx_h._tensors()
+        if in_step_apsp:
+            host_parts = [ei_h.src, ei_h.dst, ei_h.edge_off, noff_h, hoff_h] + feat_parts + [host.y]
+        else:
+            host_parts = feat_parts + [host.hop, host.hop_off, host.node_off, host.level_counts, host.y]
+
+        def assemble(views):
+            it = iter(views)
             if in_step_apsp:
-                return (ei_h.to(dev, non_blocking=True), noff_h.to(dev, non_blocking=True), hoff_h.to(dev, non_blocking=True), xx,
-                        host.y.to(dev, non_blocking=True), c)
-            b = PackedBatch(xx, host.hop.to(dev, non_blocking=True), host.hop_off.to(dev, non_blocking=True),
-                            host.node_off.to(dev, non_blocking=True), host.level_counts.to(dev, non_blocking=True),
-                            host.y.to(dev, non_blocking=True), host.max_nodes)
+                le, no, ho = LocalEdges(next(it), next(it), next(it)), next(it), next(it)
+            xx = next(it) if cx is None else None
+            c = None if cx is None else cx_h._map(lambda t: next(it))
+            if in_step_apsp:
+                return (le, no, ho, xx, next(it), c)
+            b = PackedBatch(xx, next(it), next(it), next(it), next(it), next(it), host.max_nodes)
             b.x_compressed = c
             return b
+
+        def widen(d):
+            if in_step_apsp:
+                return d if not isinstance(d[0], LocalEdges) else (d[0].expand(d[1]), d[1], d[2], d[3], d[4], None if d[5] is None else d[5].to(dev))
+            if getattr(d, "x_compressed", None) is not None:
+                d.x_compressed = d.x_compressed.to(dev)
+            return d
 
         def loss_of(data):
             if in_step_apsp:                                            # GPU BFS of the batch (pre_process_datasets.py:106-122); the graph
@@ -534,14 +556,19 @@ def run_workload(args, env, name, *, steps, warmup, classes=0, compare_legs=Fals
             graphed = None
             torch.cuda.synchronize()
 
+    inputs_consumed = torch.cuda.Event()                            # recorded once a step no longer reads the tensors handed to it
+
     def run_step(data):
         if graphed is None:
-            return step(data)
+            out = step(widen(data))
+            inputs_consumed.record()
+            return out
         cap, sin = graphed
         if data is not sin and in_step_apsp:                        # e2e leg: refresh the static inputs from the fresh copies
-            for dst, src in zip(sin[:5], data[:5]):
+            for dst, src in zip(sin[1:5], data[1:5]):
                 if dst is not None:
                     dst.copy_(src, non_blocking=True)
+            data[0].expand(sin[1], out=sin[0])                      # LocalEdges -> int64 [2,E]
             if sin[5] is not None:
                 sin[5].copy_tensors_(data[5])
         elif data is not sin:
@@ -556,6 +583,7 @@ def run_workload(args, env, name, *, steps, warmup, classes=0, compare_legs=Fals
             else:
                 for f in ("hop", "hop_off", "node_off", "level_counts", "y"):
                     getattr(sin, f).copy_(getattr(data, f), non_blocking=True)
+        inputs_consumed.record()                                    # the replay reads the static inputs only
         return cap()
     if graphed is not None:
         data_d = graphed[1]
@@ -634,27 +662,48 @@ def run_workload(args, env, name, *, steps, warmup, classes=0, compare_legs=Fals
     # Every step's inputs are copied host -> device inside the timed region and its loss is read back; the copy of step i+1
     # is issued on a second stream before the host blocks on step i's loss, so PCIe transfers overlap the previous step's
     # kernels (double-buffered inputs; CUDA streams + events, no host-side prefetch outside the timed region).
+    # The host side of a batch is ONE pinned buffer (packed.HostBundle): one cudaMemcpyAsync per step into one of two device
+    # staging buffers; run_step then refreshes the captured step's static inputs from typed views of it (widening the compact
+    # index types on the way).
     copy_stream = torch.cuda.Stream()
+    loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    bundle = HostBundle(host_parts)
+    assert bundle.payload_bytes == h2d, (bundle.payload_bytes, h2d)
+    stage_bufs = [bundle.device_buffer(dev) for _ in range(2)]
+    staged = [assemble(bundle.views(b)) for b in stage_bufs]
+    copies = [0]
 
     def issue_copy():
+        k = copies[0] & 1
+        copies[0] += 1
         with torch.cuda.stream(copy_stream):
-            d = load_host()
+            copy_stream.wait_event(inputs_consumed)                 # staging buffer k was last read by the step before last
+            bundle.copy_to(stage_bufs[k])
             e = torch.cuda.Event()
             e.record(copy_stream)
-        return d, e
+        return staged[k], e
 
     def e2e_loop(n):
+        """Software pipeline of depth 2: while step i runs, the host has already issued the copy of step i+1 and reads the loss
+        of step i-1 (its 4 bytes were copied to pinned host memory right behind that step; every step's loss is read)."""
         nxt = issue_copy()
-        last = 0.0
+        last, pending = 0.0, None
         for i in range(n):
             d, e = nxt
             torch.cuda.current_stream().wait_event(e)
             loss = run_step(d)
+            hb, done = loss_host[i & 1], torch.cuda.Event()
+            hb.copy_(loss.detach().reshape(1), non_blocking=True)   # device -> host read of this step's loss
+            done.record()
             if i + 1 < n:
                 nxt = issue_copy()                                  # overlaps this step's kernels
-            last = float(loss.item())                               # loss read back every step (trainer.py:72)
+            if pending is not None:
+                pending[1].synchronize()
+                last = float(pending[0][0])
+            pending = (hb, done)
             del d
-        return last
+        pending[1].synchronize()
+        return float(pending[0][0])
 
     e2e_loop(3)
     barrier(); torch.cuda.synchronize()

@@ -76,7 +76,37 @@ __global__ void csr_duplicates_long_kernel(const int32_t *__restrict__ rowptr, c
     }
 }
 
+// edge list of a batch of small graphs from its compact transfer form: endpoints as uint8 indices inside their graph, the graph
+// of edge e found by a binary search in the per-graph edge offsets (B + 1 int32 values: L1 / L2 resident)
+__global__ void edges_from_local_kernel(const uint8_t *__restrict__ src, const uint8_t *__restrict__ dst,
+                                        const int32_t *__restrict__ edge_off, const int32_t *__restrict__ node_off, int32_t B, int64_t E,
+                                        int64_t *__restrict__ out)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    int lo = 0, hi = B;                                   // largest g with edge_off[g] <= e
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(edge_off + mid) <= e) lo = mid; else hi = mid;
+    }
+    const int64_t base = __ldg(node_off + lo);
+    out[e] = base + src[e];
+    out[E + e] = base + dst[e];
+}
+
 }  // namespace
+
+extern "C" int gnan_edges_from_local(const uint8_t *src, const uint8_t *dst, const int32_t *edge_off, const int32_t *node_off, int32_t B,
+                                     int64_t E, int64_t *edge_index, gnan_stream_t stream)
+{
+    GNAN_REQUIRE(B >= 0 && E >= 0, "edges_from_local: negative sizes");
+    GNAN_REQUIRE(E == 0 || (B > 0 && src && dst && edge_off && node_off && edge_index), "edges_from_local: NULL pointer");
+    if (E) {
+        edges_from_local_kernel<<<(unsigned)ceil_div64(E, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, edge_off, node_off, B, E, edge_index);
+        GNAN_LAUNCH_OK();
+    }
+    return GNAN_OK;
+}
 
 extern "C" size_t gnan_build_csr_workspace_bytes(int32_t N, int64_t E)
 {

@@ -23,6 +23,42 @@ FORMAT = "gnan_b200.packed"
 VERSION = 1
 
 
+class HostBundle:
+    """All host tensors of one batch in ONE pinned byte buffer: a batch then crosses PCIe as a single copy (one
+    cudaMemcpyAsync instead of one per tensor; twenty small copies cost more host time than a 0.2 ms training step), and the
+    device side sees typed views of the staging buffer it was copied into. Offsets are 256-byte aligned."""
+    ALIGN = 256
+
+    def __init__(self, tensors: Sequence[torch.Tensor], pin: bool = True):
+        self.meta, off = [], 0
+        for t in tensors:
+            if t.is_cuda:
+                raise TypeError("HostBundle takes host tensors")
+            nb = t.numel() * t.element_size()
+            self.meta.append((off, nb, t.dtype, tuple(t.shape)))
+            off = (off + nb + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.payload_bytes = sum(m[1] for m in self.meta)
+        self.host = torch.empty(max(off, 1), dtype=torch.uint8)
+        if pin:
+            self.host = self.host.pin_memory()
+        for t, v in zip(tensors, self.views(self.host)):
+            v.copy_(t)
+
+    def views(self, buf: torch.Tensor):
+        """typed views of `buf` (the pinned buffer itself or a device buffer of the same size), in constructor order"""
+        if buf.dtype != torch.uint8 or buf.numel() != self.host.numel():
+            raise TypeError("HostBundle.views: need a uint8 buffer of the bundle's size")
+        return [buf[o:o + nb].view(dt).view(sh) for o, nb, dt, sh in self.meta]
+
+    def device_buffer(self, device):
+        return torch.empty(self.host.numel(), dtype=torch.uint8, device=device)
+
+    def copy_to(self, buf: torch.Tensor):
+        """the one host -> device copy (asynchronous on the current stream when the bundle is pinned)"""
+        buf.copy_(self.host, non_blocking=True)
+        return buf
+
+
 def _ranges(starts, sizes):
     """concat_b arange(starts[b], starts[b] + sizes[b]) on the device, without a host loop."""
     total = int(sizes.sum().item())

@@ -280,6 +280,67 @@ class PackedBatch:
                            self.max_nodes, pm(self.level_rscale))
 
 
+class LocalEdges:
+    """The edge list of a batch of small graphs as it should cross PCIe: src / dst uint8 [E] = node indices INSIDE the edge's
+    graph, edge_off int32 [B+1] = first edge of every graph (edges grouped by graph). 2 bytes per directed edge instead of the
+    16 of PyG's int64 [2,E] (batched_pyg_main.py:54-91 hands the model the latter). `expand` rebuilds the global int64
+    edge_index on the device (gnan_edges_from_local), bit-identical up to the order of the graphs' edge groups."""
+
+    def __init__(self, src, dst, edge_off):
+        self.src, self.dst, self.edge_off = src, dst, edge_off
+
+    @classmethod
+    def from_edge_index(cls, edge_index, node_off):
+        """Host-side, once per batch / dataset. edge_index int64 [2,E] with global ids, node_off [B+1]. Edges are grouped by the
+        graph of their source (stable: the order inside a graph is kept); an edge across graphs or a graph of more than 256
+        nodes raises."""
+        import numpy as np
+        ei = torch.as_tensor(edge_index).cpu().numpy().astype(np.int64)
+        no = np.asarray(torch.as_tensor(node_off).cpu().numpy(), dtype=np.int64)
+        B = no.shape[0] - 1
+        if B > 0 and int((no[1:] - no[:-1]).max()) > 256:
+            raise ValueError("LocalEdges: graphs of more than 256 nodes")
+        g = np.searchsorted(no, ei[0], side="right") - 1
+        if ei.shape[1] and (ei.min() < 0 or ei.max() >= no[-1] or np.any(np.searchsorted(no, ei[1], side="right") - 1 != g)):
+            raise ValueError("LocalEdges: an edge leaves its graph or the node range")
+        if np.any(g[1:] < g[:-1]):
+            perm = np.argsort(g, kind="stable")
+            ei, g = ei[:, perm], g[perm]
+        edge_off = np.zeros(B + 1, dtype=np.int64)
+        np.cumsum(np.bincount(g, minlength=B), out=edge_off[1:])
+        base = no[g]
+        return cls(torch.from_numpy((ei[0] - base).astype(np.uint8)), torch.from_numpy((ei[1] - base).astype(np.uint8)),
+                   torch.from_numpy(edge_off.astype(np.int32)))
+
+    @property
+    def num_edges(self):
+        return self.src.numel()
+
+    def nbytes(self):
+        return self.src.numel() + self.dst.numel() + 4 * self.edge_off.numel()
+
+    def to(self, device):
+        return LocalEdges(*[t.to(device, non_blocking=True) for t in (self.src, self.dst, self.edge_off)])
+
+    def pin_memory(self):
+        return LocalEdges(self.src.pin_memory(), self.dst.pin_memory(), self.edge_off.pin_memory())
+
+    def expand(self, node_off, out=None):
+        """int64 [2,E] global edge_index on the device (node_off: int32 device tensor [B+1]); `out` = a preallocated result
+        (the static input of a captured step)"""
+        lib = load()
+        E, B = self.num_edges, self.edge_off.numel() - 1
+        if not self.src.is_cuda or node_off.dtype != torch.int32 or node_off.numel() != B + 1:
+            raise TypeError("LocalEdges.expand: tensors must be on the GPU, node_off int32 [B+1]")
+        if out is None:
+            out = torch.empty(2, E, dtype=torch.int64, device=self.src.device)
+        elif out.shape != (2, E) or out.dtype != torch.int64 or not out.is_contiguous():
+            raise TypeError("LocalEdges.expand: out must be contiguous int64 [2,E]")
+        check(lib.gnan_edges_from_local(ptr(self.src), ptr(self.dst), ptr(self.edge_off), ptr(node_off.contiguous()), B, E, ptr(out),
+                                        stream_handle()), "gnan_edges_from_local")
+        return out
+
+
 def check_batched_status(status):
     """Raise for a status word returned by apsp_batched(..., nbins=...) (one device read; call it once per epoch or when a
     result looks wrong, not once per step)."""

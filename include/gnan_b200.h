@@ -291,6 +291,13 @@ size_t gnan_build_csr_workspace_bytes(int32_t N, int64_t E);
 int gnan_build_csr(const int64_t *src, const int64_t *dst, int64_t E, int32_t N, int32_t *rowptr, int32_t *col, int32_t *status,
                    void *workspace, size_t workspace_bytes, gnan_stream_t stream);
 
+/* Edge list of a batch of B small graphs (<= 256 nodes each) from its compact TRANSFER form: src / dst [E] are uint8 node indices
+ * INSIDE the edge's graph, edge_off [B+1] (int32) the first edge of each graph (edges grouped by graph), node_off [B+1] the graph
+ * boundaries in the concatenated node set. Writes the PyG edge_index int64 [2,E] with global node ids (what gnan_build_csr
+ * takes): 2 bytes per directed edge cross PCIe instead of 16 (batched_pyg_main.py:54-91 loader output). */
+int gnan_edges_from_local(const uint8_t *src, const uint8_t *dst, const int32_t *edge_off, const int32_t *node_off, int32_t B,
+                          int64_t E, int64_t *edge_index, gnan_stream_t stream);
+
 size_t gnan_apsp_bfs_workspace_bytes(int32_t N, int32_t n_sources);
 
 /* sources [src_begin, src_end) of one graph with N nodes -> hop rows [src_end-src_begin, N] (row stride ld_hop). */

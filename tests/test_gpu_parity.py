@@ -807,6 +807,67 @@ def test_mlp_tensor_core_one_pass_backward_with_dropout_matches_fp32_path():
         assert G.rel_err(grads["tf32x3"][k], grads["fp32"][k]) < 2e-4, k     # same masks; a kink may flip under different rounding
 
 
+# ---- compact transfer forms (what crosses PCIe in bench.py's end-to-end leg) -------------------------------------------
+def test_local_edges_expand_rebuilds_edge_index():
+    """preprocess.LocalEdges: uint8 local endpoints + per-graph edge offsets -> gnan_edges_from_local -> the int64 edge_index,
+    bit-exact (edge groups in graph order), and the batched BFS of it equals the BFS of the original list."""
+    from gnan_b200.preprocess import LocalEdges, apsp_batched
+    rng = np.random.default_rng(3)
+    sizes = rng.integers(1, 257, size=300)
+    sizes[5] = 256; sizes[6] = 1
+    node_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    src, dst = [], []
+    for b, n in enumerate(sizes):
+        m = int(rng.integers(0, 3 * n))
+        src.append(node_off[b] + rng.integers(0, n, m)); dst.append(node_off[b] + rng.integers(0, n, m))
+    ei = np.stack([np.concatenate(src), np.concatenate(dst)])
+    und = np.unique(ei[:, ei[0] != ei[1]].T, axis=0).T                         # simple directed graph, sorted by source
+    perm = rng.permutation(und.shape[1])                                       # shuffled: from_edge_index regroups it
+    le = LocalEdges.from_edge_index(torch.tensor(und[:, perm]), node_off)
+    no_d = torch.tensor(node_off, dtype=torch.int32, device=DEV)
+    got = le.to(DEV).expand(no_d)
+    assert got.dtype == torch.int64 and got.shape == (2, und.shape[1])
+    g = np.searchsorted(node_off, und[0, perm], side="right") - 1
+    want = und[:, perm][:, np.argsort(g, kind="stable")]
+    assert np.array_equal(got.cpu().numpy(), want)
+    out = torch.zeros_like(got)
+    assert le.to(DEV).expand(no_d, out=out) is out and torch.equal(out, got)
+    small = sizes <= 128                                                        # BFS equality on the graphs the batched kernel takes
+    keep_g = np.nonzero(small)[0][:40]
+    sel = np.isin(g, keep_g)
+    remap = np.concatenate([[0], np.cumsum(sizes[keep_g])])
+    def sub(e):
+        gg = np.searchsorted(node_off, e[0], side="right") - 1
+        pos = np.searchsorted(keep_g, gg)
+        return torch.tensor(e - node_off[gg] + remap[pos])
+    a = apsp_batched(sub(und[:, perm][:, sel]), remap, device=DEV)
+    le2 = LocalEdges.from_edge_index(sub(und[:, perm][:, sel]), remap).to(DEV)
+    b = apsp_batched(le2.expand(torch.tensor(remap, dtype=torch.int32, device=DEV)), remap, device=DEV)
+    assert torch.equal(a.hop, b.hop) and torch.equal(a.level_counts, b.level_counts)
+
+
+def test_compact_compressed_features_refresh_static_inputs():
+    """CompressedFeatures.compact_host() (narrow index types, per-entry values dropped when values are shared) moved raw to the
+    device and widened by copy_tensors_ into a step's static tensors: every tensor equals the original; .to(device) alone too."""
+    from gnan_b200.sparse import compress_features
+    rng = np.random.default_rng(8)
+    N, K = 5000, 15
+    x = np.zeros((N, K), np.float32)
+    x[np.arange(N), rng.integers(0, 14, N)] = 1.0
+    x[:, 14] = 1.0
+    cx = compress_features(torch.tensor(x).to(DEV))
+    assert cx.shared is not None
+    ch = cx.compact_host()
+    assert ch.val.numel() == 0 and ch.shared.inv.dtype == torch.uint8 and ch.nbytes() < 0.55 * cx.nbytes()
+    static = cx.clone_tensors()
+    for t in static._tensors():
+        t.zero_()
+    static.copy_tensors_(ch.to(DEV, raw=True))
+    wide = ch.to(DEV)
+    for a, b, c in zip(static._tensors(), cx._tensors(), wide._tensors()):
+        assert a.dtype == b.dtype == c.dtype and torch.equal(a, b) and torch.equal(c, b)
+
+
 # ---- training loop around the path (SURVEY §8f-1) ----------------------------------------------------------------------
 def _trainer_items(z, graph_task, n_items):
     from gnan_b200.preprocess import apsp

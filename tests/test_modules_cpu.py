@@ -187,13 +187,50 @@ def test_compress_features_structure_and_roundtrip():
     # work items: every (group, tile) exactly once
     want = [(k, t) for k in range(K) for t in range((gp[k + 1] - gp[k] + TILE - 1) // TILE)]
     assert [tuple(i) for i in cx.items.tolist()] == want and cx.max_group == max(gp[k + 1] - gp[k] for k in range(K))
-    # compact host copy (int32 index arrays for the PCIe transfer): same content, fewer bytes
+    # compact host copy (narrow index arrays for the PCIe transfer, per-entry values dropped when values are shared): same
+    # content, fewer bytes
     ch = cx.compact_host()
-    assert ch.ent_row.dtype == torch.int32 and ch.csr_eid.dtype == torch.int32 and ch.nbytes() < cx.nbytes()
-    assert all(torch.equal(a.long(), b.long()) for a, b in zip(ch._tensors(), cx._tensors()))
+    assert ch.ent_row.dtype == torch.int32 and ch.csr_eid.dtype == torch.int32 and ch.ent_grp.dtype == torch.uint8
+    assert cx.shared is not None and ch.val.numel() == 0 and ch.shared.inv.dtype in (torch.uint8, torch.int16)
+    assert ch.nbytes() < 0.6 * cx.nbytes()
+    assert all(torch.equal(a.long(), b.long()) for a, b in zip(ch._tensors(), cx._tensors()) if a.numel() == b.numel() and not a.dtype.is_floating_point)
+    assert torch.equal(ch.shared.val, cx.shared.val) and torch.equal(ch.base, cx.base)
     assert torch.equal(ch.to_dense(), xt)
+    plain = compress_features(xt, max_density=0.5, share_values=False).compact_host()      # no sharing: the values travel
+    assert plain.val.numel() == plain.ent_row.numel() and torch.equal(plain.to_dense(), xt)
     assert compress_features(torch.tensor(rng.normal(size=(50, 4)).astype(np.float32))) is None      # dense data: not worth it
     assert compress_features(torch.tensor(rng.normal(size=(50, 4)).astype(np.float32)), max_density=None) is not None
+
+
+def test_local_edges_host_form():
+    """preprocess.LocalEdges.from_edge_index: uint8 endpoints inside the graph + per-graph edge offsets; unsorted edge lists are
+    grouped by graph (stable); cross-graph edges and graphs of more than 256 nodes raise."""
+    from gnan_b200.preprocess import LocalEdges
+    node_off = np.array([0, 3, 3, 8, 264])
+    ei = torch.tensor([[4, 0, 263, 1, 7, 8], [5, 2, 8, 0, 3, 263]])
+    le = LocalEdges.from_edge_index(ei, node_off)
+    assert le.src.dtype == torch.uint8 and le.edge_off.dtype == torch.int32 and le.nbytes() == 12 + 20
+    assert le.edge_off.tolist() == [0, 2, 2, 4, 6]
+    assert le.src.tolist() == [0, 1, 1, 4, 255, 0] and le.dst.tolist() == [2, 0, 2, 0, 0, 255]
+    with pytest.raises(ValueError):
+        LocalEdges.from_edge_index(torch.tensor([[0], [3]]), node_off)                 # leaves its graph
+    with pytest.raises(ValueError):
+        LocalEdges.from_edge_index(torch.tensor([[0], [1]]), np.array([0, 300]))       # too large for uint8 indices
+
+
+def test_host_bundle_views_roundtrip():
+    """packed.HostBundle: tensors of mixed dtypes / shapes (empty ones included) in one byte buffer, typed views give them back"""
+    from gnan_b200.packed import HostBundle
+    ts = [torch.arange(7, dtype=torch.uint8), torch.randn(3, 5), torch.zeros(0, dtype=torch.int64), torch.arange(-3, 9, dtype=torch.int16),
+          torch.arange(6, dtype=torch.int64).reshape(2, 3), torch.tensor([1.5])]
+    hb = HostBundle(ts, pin=False)
+    assert hb.payload_bytes == sum(t.numel() * t.element_size() for t in ts) and hb.host.numel() % HostBundle.ALIGN == 0
+    other = torch.zeros_like(hb.host)
+    hb.copy_to(other)
+    for t, v in zip(ts, hb.views(other)):
+        assert v.dtype == t.dtype and v.shape == t.shape and torch.equal(v, t)
+    with pytest.raises(TypeError):
+        hb.views(torch.zeros(3, dtype=torch.uint8))
 
 
 def test_feature_compression_policy():
