@@ -356,6 +356,295 @@ apsp_batched_v2_kernel(const int32_t *__restrict__ rowptr, const int32_t *__rest
     }
 }
 
+// ---- batched small graphs, v3: a GROUP of 4 warps per graph slot -----------------------------------------------------------
+// v2 is bound by the latency of ONE warp's dependent instruction stream per graph (a lane walks up to 4 vertices one after the
+// other, 10-12 graphs in flight per SM). Here a lane owns ONE vertex and the warps of a group advance a level together
+// (named barrier with an OR reduction = "did anybody reach a new vertex"): graphs of 65..128 nodes take the 4 warps of a group,
+// graphs of 33..64 nodes run two at a time on warp pairs, graphs of up to 32 nodes four at a time on single warps, each in its
+// share of the group's shared-memory slice. Same data flow as v2 otherwise (hop block assembled in shared memory, written
+// once; level sizes through a uint8 table).
+constexpr int BV3_GW = 4;                                  // warps per group
+constexpr int BV3_MAX_GROUPS = 5;                          // groups per CTA (3 named barriers each: ids 1..15)
+
+__host__ __device__ inline size_t bv3_hop_bytes(int cap) { return bv2_round16((size_t)cap * cap + 16); }
+__host__ __device__ constexpr int bv3_ws(int W) { return W == 3 ? 4 : W; }         // frontier row stride in words: 16-byte rows for W = 3
+__host__ __device__ inline size_t bv3_fr_bytes(int cap, int W) { return bv2_round16((size_t)2 * cap * bv3_ws(W) * 4); }
+
+// frontier rows move as ONE shared-memory access (LDS.128 / LDS.64 instead of W scalar loads per neighbour)
+template <int W>
+__device__ __forceinline__ void bv3_or_row(const uint32_t *row, uint32_t (&acc)[W])
+{
+    if (W >= 3) {
+        const uint4 q = *reinterpret_cast<const uint4 *>(row);
+        acc[0] |= q.x; acc[1] |= q.y; acc[2] |= q.z;
+        if (W == 4) acc[W - 1] |= q.w;
+    } else if (W == 2) {
+        const uint2 q = *reinterpret_cast<const uint2 *>(row);
+        acc[0] |= q.x; acc[1] |= q.y;
+    } else {
+        acc[0] |= row[0];
+    }
+}
+template <int W>
+__device__ __forceinline__ void bv3_store_row(uint32_t *row, const uint32_t (&w)[W])
+{
+    if (W >= 3) *reinterpret_cast<uint4 *>(row) = make_uint4(w[0], w[1], w[2], W == 4 ? w[W - 1] : 0u);
+    else if (W == 2) *reinterpret_cast<uint2 *>(row) = make_uint2(w[0], w[1]);
+    else row[0] = w[0];
+}
+__host__ __device__ inline size_t bv3_need(int cap, int W, int nbins, bool levels)
+{
+    return bv3_hop_bytes(cap) + bv3_fr_bytes(cap, W) + (levels ? bv2_round16((size_t)cap * nbins) : 0);
+}
+
+template <int G>
+__device__ __forceinline__ void bv3_sync(int bar)
+{
+    if (G == 1) __syncwarp();
+    else asm volatile("barrier.sync %0, %1;" :: "r"(bar), "n"(32 * G) : "memory");
+}
+
+template <int G>
+__device__ __forceinline__ bool bv3_any(int bar, bool p)
+{
+    if (G == 1) {
+        __syncwarp();
+        return __any_sync(0xffffffffu, p);
+    }
+    uint32_t r;
+    asm volatile("{\n\t.reg .pred pi, po;\n\tsetp.ne.u32 pi, %3, 0;\n\tbarrier.red.or.pred po, %1, %2, pi;\n\tselp.u32 %0, 1, 0, po;\n\t}"
+                 : "=r"(r) : "r"(bar), "n"(32 * G), "r"((uint32_t)p) : "memory");
+    return r != 0;
+}
+
+// one graph on G warps, W = ceil(n/32) <= G words per vertex; thread ts = wsub * 32 + lane owns vertex ts
+template <int W, int G>
+__device__ __forceinline__ int bv3_graph(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, int n0, int n, int ts,
+                                         int bar, uint8_t *hb, uint32_t *frs, uint8_t *cs, int nbins, bool levels, int32_t *overflow)
+{
+    constexpr int WS = bv3_ws(W);
+    const int v = ts, lane = ts & 31, wsub = ts >> 5;
+    const bool mine = v < n;
+    uint32_t vis[W], nb_lo = 0xffffffffu, nb_hi = 0xffffffffu;
+    int dg = 0, e8 = 0, e1 = 0;
+#pragma unroll
+    for (int ww = 0; ww < W; ++ww) vis[ww] = 0u;
+    if (mine) {
+        const int eb = rowptr[n0 + v], ee = rowptr[n0 + v + 1];
+        int e = eb;
+        for (; e < ee && dg < 8; ++e) {                              // neighbours outside the graph are ignored
+            const int u = __ldg(col + e) - n0;
+            if (u >= 0 && u < n) {
+                const int sh = 8 * (dg & 3);
+                if (dg < 4) nb_lo = (nb_lo & ~(0xffu << sh)) | ((uint32_t)u << sh);
+                else nb_hi = (nb_hi & ~(0xffu << sh)) | ((uint32_t)u << sh);
+                ++dg;
+            }
+        }
+        e8 = e; e1 = ee;
+#pragma unroll
+        for (int ww = 0; ww < W; ++ww) vis[ww] = ww == wsub ? 1u << lane : 0u;
+        bv3_store_row<W>(frs + v * WS, vis);
+        hb[v * n + v] = 0;
+        if (levels) cs[v * nbins] = 1;
+    }
+    bv3_sync<G>(bar);
+    int lvl_max = 0;
+    for (int level = 1; level <= n; ++level) {
+        const uint32_t *fc = frs + ((level - 1) & 1) * n * WS;
+        uint32_t *fn = frs + (level & 1) * n * WS;
+        const uint8_t lv = (uint8_t)min(level, 254);
+        bool any = false;
+        if (mine) {
+            uint32_t acc[W];
+#pragma unroll
+            for (int ww = 0; ww < W; ++ww) acc[ww] = 0u;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                if (t < dg) {
+                    const uint32_t u = ((t < 4 ? nb_lo : nb_hi) >> (8 * (t & 3))) & 0xffu;
+                    bv3_or_row<W>(fc + u * WS, acc);
+                }
+            }
+            for (int e = e8; e < e1; ++e) {                          // rows with more than 8 neighbours
+                const int u = __ldg(col + e) - n0;
+                if (u >= 0 && u < n) bv3_or_row<W>(fc + u * WS, acc);
+            }
+            int newc = 0;
+#pragma unroll
+            for (int ww = 0; ww < W; ++ww) {
+                acc[ww] &= ~vis[ww];
+                vis[ww] |= acc[ww];
+                newc += __popc(acc[ww]);
+            }
+            bv3_store_row<W>(fn + v * WS, acc);
+#pragma unroll
+            for (int ww = 0; ww < W; ++ww) {
+                uint32_t m = acc[ww];
+                uint8_t *rowp = hb + v * n + ww * 32;
+                while (m) {
+                    const int lo = __ffs(m) - 1, hi = 31 - __clz(m);
+                    rowp[lo] = lv;
+                    rowp[hi] = lv;
+                    m &= m - 1;
+                    m &= ~(1u << hi);
+                }
+            }
+            if (newc) {
+                any = true;
+                if (level > 254 || level >= nbins - 1) atomicExch(overflow, 1);
+                else if (levels) cs[v * nbins + level] = (uint8_t)newc;
+            }
+        }
+        if (!bv3_any<G>(bar, any)) break;
+        lvl_max = level;
+    }
+    if (levels && mine) {
+        int reached = 0;
+#pragma unroll
+        for (int ww = 0; ww < W; ++ww) reached += __popc(vis[ww]);
+        cs[v * nbins + nbins - 1] = (uint8_t)(n - reached);
+    }
+    return lvl_max;
+}
+
+// graphs by word-count class (0 = 97..128 nodes ... 3 = up to 32), one thread per graph, warp-aggregated counters:
+// cls[0..4) = class sizes (zeroed by the caller), cls[4 + c * B ...) = the graphs of class c in arbitrary order
+__global__ void bv3_classify_kernel(const int32_t *__restrict__ node_off, int B, int32_t *__restrict__ cls)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = b < B;
+    int c = 4;
+    if (ok) c = 3 - min(3, max(0, (node_off[b + 1] - node_off[b] - 1) >> 5));
+    const uint32_t peers = __match_any_sync(0xffffffffu, c);
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    int base = 0;
+    if (ok && lane == leader) base = atomicAdd(cls + c, __popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (ok) cls[4 + (size_t)c * B + base + __popc(peers & ((1u << lane) - 1))] = b;
+}
+
+struct Bv3Out {
+    uint8_t *hop;
+    int32_t *cnt;
+    float *rscale;
+    const float *rcp_tab;
+    int nbins;
+};
+
+// graph b on the G warps of a sub-group: fill the slice, BFS, write the level table and the hop block out
+template <int W, int G>
+__device__ __forceinline__ int bv3_run(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                       const int32_t *__restrict__ node_off, const int64_t *__restrict__ hop_off, int64_t b, int cap,
+                                       int ts, int bar, uint8_t *slice, const Bv3Out &o, bool levels, int32_t *overflow)
+{
+    constexpr int T = 32 * G;
+    const int n0 = node_off[b], n = node_off[b + 1] - n0, nbins = o.nbins;
+    uint8_t *gb = o.hop + hop_off[b];
+    const int pad = (int)(reinterpret_cast<uintptr_t>(gb) & 15);
+    uint8_t *hb = slice + pad;                                                  // hb + k  ==  gb + k  (mod 16)
+    uint32_t *frs = reinterpret_cast<uint32_t *>(slice + bv3_hop_bytes(cap));  // [2][n][W]
+    uint8_t *cs = slice + bv3_hop_bytes(cap) + bv3_fr_bytes(cap, W);           // [n][nbins]
+    const int total = n * n;
+    for (int t = ts * 16; t < total + 16; t += T * 16)
+        *reinterpret_cast<uint4 *>(slice + t) = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    if (levels)
+        for (int t = ts * 16; t < n * nbins; t += T * 16) *reinterpret_cast<uint4 *>(cs + t) = make_uint4(0u, 0u, 0u, 0u);
+    bv3_sync<G>(bar);
+    const int lm = bv3_graph<W, G>(rowptr, col, n0, n, ts, bar, hb, frs, cs, nbins, levels, overflow);
+    bv3_sync<G>(bar);
+    if (levels) {
+        const int nt = n * nbins;                                               // the graph's [n][nbins] block is contiguous
+        const bool vec_tab = (nbins & 3) == 0;
+        if (o.cnt) {
+            int32_t *gc = o.cnt + (int64_t)n0 * nbins;
+            if (vec_tab) {
+                for (int t = ts * 4; t < nt; t += T * 4) {
+                    const uint32_t c4 = *reinterpret_cast<const uint32_t *>(cs + t);
+                    *reinterpret_cast<int4 *>(gc + t) = make_int4(c4 & 0xff, (c4 >> 8) & 0xff, (c4 >> 16) & 0xff, c4 >> 24);
+                }
+            } else {
+                for (int t = ts; t < nt; t += T) gc[t] = cs[t];
+            }
+        }
+        if (o.rscale) {                              // 1/count (0 for empty levels): gnan_level_rscale fused
+            float *gr = o.rscale + (int64_t)n0 * nbins;
+            if (vec_tab) {
+                for (int t = ts * 4; t < nt; t += T * 4) {
+                    const uint32_t c4 = *reinterpret_cast<const uint32_t *>(cs + t);
+                    *reinterpret_cast<float4 *>(gr + t) = make_float4(o.rcp_tab[c4 & 0xff], o.rcp_tab[(c4 >> 8) & 0xff],
+                                                                      o.rcp_tab[(c4 >> 16) & 0xff], o.rcp_tab[c4 >> 24]);
+                }
+            } else {
+                for (int t = ts; t < nt; t += T) gr[t] = o.rcp_tab[cs[t]];
+            }
+        }
+    }
+    // copy out: head bytes up to the first 16-byte boundary, vector body, tail bytes
+    const int head = min(total, (16 - pad) & 15);
+    if (ts < head) gb[ts] = hb[ts];
+    const int body = (total - head) / 16;
+    for (int t = ts; t < body; t += T)
+        *reinterpret_cast<uint4 *>(gb + head + t * 16) = *reinterpret_cast<const uint4 *>(hb + head + t * 16);
+    const int tail0 = head + body * 16;
+    if (ts < 16 && tail0 + ts < total) gb[tail0 + ts] = hb[tail0 + ts];
+    return lm;
+}
+
+// order = the output of bv3_classify_kernel
+__global__ void __launch_bounds__(32 * BV3_GW * BV3_MAX_GROUPS, 2)
+apsp_batched_v3_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, const int32_t *__restrict__ node_off,
+                       const int64_t *__restrict__ hop_off, int B, int max_n, int groups_per_cta, int slice_bytes, uint8_t *__restrict__ hop,
+                       int32_t *__restrict__ cnt, float *__restrict__ rscale, int nbins, int32_t *__restrict__ overflow,
+                       int32_t *__restrict__ max_level, const int32_t *__restrict__ order)
+{
+    extern __shared__ __align__(16) uint8_t sm3[];
+    __shared__ float rcp_tab[256];
+    const bool levels = cnt != nullptr || rscale != nullptr;
+    if (rscale) {
+        for (int t = threadIdx.x; t < 256; t += blockDim.x) rcp_tab[t] = t > 0 ? 1.0f / (float)t : 0.f;   // as level_rscale_kernel
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = warp / BV3_GW, wq = warp % BV3_GW;
+    uint8_t *gslice = sm3 + (size_t)g * slice_bytes;
+    const int bar_group = 1 + 3 * g;
+    const Bv3Out out{hop, cnt, rscale, rcp_tab, nbins};
+    const int c0 = order[0], c_big = c0 + order[1], c2 = order[2], c3 = order[3];
+    const int32_t *ord0 = order + 4, *ord1 = ord0 + B, *ord2 = ord1 + B, *ord3 = ord2 + B;
+    const int items2 = (c2 + 1) / 2, items1 = (c3 + 3) / 4;
+    const int64_t n_items = (int64_t)c_big + items2 + items1, stride = (int64_t)gridDim.x * groups_per_cta;
+    const int cap2 = min(max_n, 64), cap1 = min(max_n, 32);
+    const int half = (slice_bytes / 2) & ~15, quarter = (slice_bytes / 4) & ~15;
+    int lvl_max = 0;
+    for (int64_t t = (int64_t)blockIdx.x * groups_per_cta + g; t < n_items; t += stride) {
+        if (t < c_big) {                                             // 65..128 nodes: the whole group
+            const int64_t b = t < c0 ? ord0[t] : ord1[t - c0];
+            const int n = node_off[b + 1] - node_off[b];
+            const int ts = wq * 32 + lane;
+            const int lm = n <= 96 ? bv3_run<3, 4>(rowptr, col, node_off, hop_off, b, max_n, ts, bar_group, gslice, out, levels, overflow)
+                                   : bv3_run<4, 4>(rowptr, col, node_off, hop_off, b, max_n, ts, bar_group, gslice, out, levels, overflow);
+            lvl_max = max(lvl_max, lm);
+        } else if (t < c_big + items2) {                             // 33..64 nodes: two graphs on the two warp pairs
+            const int pr = wq >> 1;
+            const int64_t idx = 2 * (t - c_big) + pr;
+            if (idx < c2)
+                lvl_max = max(lvl_max, bv3_run<2, 2>(rowptr, col, node_off, hop_off, ord2[idx], cap2, (wq & 1) * 32 + lane,
+                                                     bar_group + 1 + pr, gslice + (size_t)pr * half, out, levels, overflow));
+        } else {                                                     // up to 32 nodes: four graphs, a warp each
+            const int64_t idx = 4 * (t - c_big - items2) + wq;
+            if (idx < c3)
+                lvl_max = max(lvl_max, bv3_run<1, 1>(rowptr, col, node_off, hop_off, ord3[idx], cap1, lane, 0,
+                                                     gslice + (size_t)wq * quarter, out, levels, overflow));
+        }
+        bv3_sync<BV3_GW>(bar_group);                                 // the slice is re-partitioned / refilled by the next item
+    }
+    if (max_level) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lvl_max = max(lvl_max, __shfl_xor_sync(0xffffffffu, lvl_max, o));
+        if (lane == 0 && lvl_max > 0) atomicMax(max_level, lvl_max);
+    }
+}
+
 // ---- one large graph: one warp per source, queue + bitmap in the workspace -----------------------------------------
 __global__ void __launch_bounds__(256)
 apsp_bfs_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, int N, int src_begin, int src_end,
@@ -679,7 +968,36 @@ extern "C" int gnan_apsp_bfs_batched_ex(const int32_t *rowptr, const int32_t *co
     }
     cudaStream_t st = (cudaStream_t)stream;
     if (max_n <= 32 * BV2_W && total_nodes > 0) {
-        // v2: hop blocks assembled in shared memory and written once (no memset of hop); only the level table is zero-filled
+        const bool levels = cnt || rscale;
+        const int nb = levels ? nbins : 256;
+        static const bool force_v2 = getenv("GNAN_BFS_V2") != nullptr;
+        if (order_ws && !force_v2) {
+            // v3: groups of 4 warps; the group's slice holds one graph of 65..128 nodes, two of 33..64 or four of up to 32
+            const int Wmax = (max_n + 31) / 32;
+            size_t slice = 4 * bv3_need(std::min(max_n, 32), 1, nb, levels);
+            if (Wmax >= 2) slice = std::max(slice, 2 * bv3_need(std::min(max_n, 64), 2, nb, levels));
+            if (Wmax >= 3) slice = std::max(slice, bv3_need(max_n, Wmax, nb, levels));
+            const int gpc = (int)std::min<size_t>(BV3_MAX_GROUPS, (112 * 1024) / slice);     // two CTAs per SM
+            if (gpc >= 1) {
+                const size_t smem3 = slice * gpc;
+                static thread_local size_t cached_smem3 = 0;
+                static thread_local int cached_gpc = 0, cached_per_sm3 = 0;
+                if (cached_smem3 != smem3 || cached_gpc != gpc || cached_per_sm3 == 0) {
+                    GNAN_CUDA(cudaFuncSetAttribute(apsp_batched_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+                    GNAN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_per_sm3, apsp_batched_v3_kernel, 32 * BV3_GW * gpc, smem3));
+                    cached_smem3 = smem3; cached_gpc = gpc;
+                }
+                const int blocks3 = (int)std::min<int64_t>(ceil_div64(B, gpc), (int64_t)std::max(cached_per_sm3, 1) * gnan_sm_count());
+                GNAN_CUDA(cudaMemsetAsync(order_ws, 0, 4 * sizeof(int32_t), st));
+                bv3_classify_kernel<<<(unsigned)ceil_div64(B, 256), 256, 0, st>>>(node_off, B, order_ws);
+                GNAN_LAUNCH_OK();
+                apsp_batched_v3_kernel<<<blocks3, 32 * BV3_GW * gpc, smem3, st>>>(rowptr, col, node_off, hop_off, B, max_n, gpc, (int)slice, hop,
+                                                                                 cnt, rscale, nb, overflow_flag, max_level, order_ws);
+                GNAN_LAUNCH_OK();
+                return GNAN_OK;
+            }
+        }
+        // v2: one warp per graph; hop blocks assembled in shared memory and written once (no memset of hop)
         const int Wmax = (max_n + 31) / 32;
         const size_t per_warp = bv2_round16((size_t)max_n * max_n + 16) + bv2_round16((size_t)2 * max_n * Wmax * 4) +
                                 ((cnt || rscale) ? bv2_round16((size_t)max_n * nbins) : 0);

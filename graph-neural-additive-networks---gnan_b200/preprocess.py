@@ -400,7 +400,7 @@ def apsp_batched(edge_index, node_off, device="cuda", x=None, y=None, node_off_d
         if nbins is None or max_n > 128 or sumN == 0:
             raise ValueError("rscale=True needs the fixed-width mode (nbins=...) and graphs of at most 128 nodes")
         rs = torch.empty(sumN, nb, dtype=torch.float32, device=device)
-        order_ws = torch.empty(max(B, 1), dtype=torch.int32, device=device)
+        order_ws = torch.empty(4 * B + 4, dtype=torch.int32, device=device)
         with _timed("apsp_bfs_batched"):
             check(lib.gnan_apsp_bfs_batched_ex(ptr(rowptr), ptr(col), ptr(node_off_d), ptr(hop_off), B, max_n, sumN, total, ptr(hop), None,
                                                ptr(rs), nb, st.data_ptr() + 4, st.data_ptr() + 8, ptr(order_ws), stream_handle()),
@@ -409,7 +409,7 @@ def apsp_batched(edge_index, node_off, device="cuda", x=None, y=None, node_off_d
         pk.status = st
         return pk
     cnt = torch.empty(sumN, nb, dtype=torch.int32, device=device)
-    order_ws = torch.empty(max(B, 1), dtype=torch.int32, device=device)     # graphs are processed grouped by size class
+    order_ws = torch.empty(4 * B + 4, dtype=torch.int32, device=device)     # graphs are processed grouped by size class
     with _timed("apsp_bfs_batched"):
         check(lib.gnan_apsp_bfs_batched_ex(ptr(rowptr), ptr(col), ptr(node_off_d), ptr(hop_off), B, max_n, sumN, total, ptr(hop), ptr(cnt), None,
                                            nb, st.data_ptr() + 4, st.data_ptr() + 8, ptr(order_ws), stream_handle()), "gnan_apsp_bfs_batched")

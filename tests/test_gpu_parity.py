@@ -296,6 +296,45 @@ def test_apsp_batched_odd_maximum_sizes(max_n):
         assert np.array_equal(got, oapsp.apsp(eis[i], n)), i
 
 
+@pytest.mark.parametrize("directed,lo,hi", [(False, 1, 128), (True, 1, 128), (False, 1, 32), (False, 30, 64), (False, 60, 100)])
+def test_apsp_batched_grouped_warps_many_graphs(directed, lo, hi):
+    """The 4-warp-group kernel (graphs of 65..128 nodes on a whole group, 33..64 on warp pairs, <= 32 on single warps) on a batch
+    with odd class sizes, hubs of more than 8 neighbours and isolated vertices: hop blocks and level sizes against the C oracle,
+    and the fused 1/count table (fixed-width mode) against the counts."""
+    from gnan_b200.preprocess import apsp_batched, check_batched_status
+    rng = np.random.default_rng(lo * 1000 + hi + int(directed))
+    sizes = [int(v) for v in rng.integers(lo, hi + 1, size=301)] + [hi, lo]
+    node_off = np.concatenate([[0], np.cumsum(sizes)])
+    eis = []
+    for n in sizes:
+        e = random_graph(rng, n, 2.6, directed, n_isolated=1 if n > 4 else 0)
+        if n > 12:                                                  # a hub: vertex 0 linked to 11 others (rows longer than the register cache)
+            tgt = rng.choice(np.arange(1, n), size=11, replace=False)
+            hub = np.stack([np.zeros(11, dtype=np.int64), tgt])
+            e = np.unique(np.concatenate([e, hub, hub[::-1]] if not directed else [e, hub], axis=1).T, axis=0).T
+        eis.append(e)
+    ei = torch.tensor(np.concatenate([e + node_off[i] for i, e in enumerate(eis)], axis=1))
+    pk = apsp_batched(ei, node_off, device=DEV)
+    hop, cnt, ho = pk.hop.cpu().numpy(), pk.level_counts.cpu().numpy(), pk.hop_off.cpu().numpy()
+    for i, n in enumerate(sizes):
+        want = oapsp.apsp(eis[i], n)
+        got = hop[ho[i]:ho[i + 1]].reshape(n, n).astype(np.int32)
+        got[got == 255] = -1
+        assert np.array_equal(got, want), i
+        wc = oapsp.level_counts(want)
+        full = np.zeros((n, cnt.shape[1]), dtype=np.int32)
+        full[:, :wc.shape[1] - 1] = wc[:, :-1]; full[:, -1] = wc[:, -1]
+        assert np.array_equal(cnt[node_off[i]:node_off[i + 1]], full), i
+    fx = apsp_batched(ei, node_off, device=DEV, nbins=130, rscale=True)
+    check_batched_status(fx.status)
+    assert torch.equal(fx.hop, pk.hop)
+    wide = torch.zeros(cnt.shape[0], 130, dtype=torch.float32)
+    c = torch.tensor(cnt).float()
+    wide[:, :cnt.shape[1] - 1] = c[:, :-1]; wide[:, -1] = c[:, -1]
+    want_rs = torch.where(wide > 0, 1.0 / wide, torch.zeros_like(wide))
+    assert torch.equal(fx.level_rscale.cpu(), want_rs)
+
+
 def test_apsp_batched_vs_oracle():
     from gnan_b200.preprocess import apsp_batched
     rng = np.random.default_rng(5)
