@@ -373,7 +373,7 @@ KERNEL_NAMES = {
     "aggregate_rows_bwd_saved": "agg_tc_ds_kernel (+ row compaction, digits, dT kernels) | agg_rows_ds_kernel",
     "aggregate_blockdiag_fwd": "agg_bd_graph_fwd_kernel | agg_blockdiag_fwd_rows_kernel",
     "aggregate_blockdiag_bwd": "agg_bd_graph_ds/dt kernels | agg_blockdiag_bwd_global_kernel",
-    "apsp_bfs_batched": "apsp_batched_v2_kernel", "build_csr": "csr_degree/fill/duplicates kernels + cub scan",
+    "apsp_bfs_batched": "apsp_batched_v3_kernel (+ bv3_classify_kernel)", "build_csr": "csr_degree/fill/duplicates kernels + cub scan",
 }
 COLLECTIVES = ("allgather_rows", "reduce_scatter_rows", "allreduce_gradients")
 
