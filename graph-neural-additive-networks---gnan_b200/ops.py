@@ -67,15 +67,34 @@ def _f32(t: Tensor, name: str) -> Tensor:
 MLP_EXT_MAX_BYTES = 24 << 30      # dh + a1 buffers of the one-pass backward for C > 8 (beyond this the channel-slice passes run)
 
 
-class _fp32_matmul:
-    """torch.matmul in full fp32 (the GEMMs around gnan_mlp_bwd_ext must not drop to TF32 even if the caller enabled it globally)"""
+class _matmul_tf32:
+    """torch.matmul with TF32 tensor cores forced on / off for the GEMMs around gnan_mlp_bwd_ext, whatever the caller set globally"""
+
+    def __init__(self, allow: bool):
+        self._allow = allow
 
     def __enter__(self):
         self._was = torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = self._allow
 
     def __exit__(self, *exc):
         torch.backends.cuda.matmul.allow_tf32 = self._was
+
+
+def _split_tf32(t: Tensor):
+    """t = hi + lo with hi rounded to TF32 (10 mantissa bits, round half away) and lo = t - hi exact in fp32"""
+    hi = ((t.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    return hi, t - hi
+
+
+def _matmul_3xtf32(a: Tensor, b: Tensor) -> Tensor:
+    """a @ b at fp32-level accuracy on the TF32 tensor cores: the three split terms a_hi b_hi + a_lo b_hi + a_hi b_lo as ONE GEMM
+    over a K dimension concatenated three times (fp32 accumulation; the result is written once). For a short K (the class
+    dimension) and a large result: the plain-fp32 SIMT GEMM is compute bound there, this one is bound by writing the result."""
+    ah, al = _split_tf32(a)
+    bh, bl = _split_tf32(b)
+    with _matmul_tf32(True):
+        return torch.matmul(torch.cat([ah, al, ah], dim=1), torch.cat([bh, bh, bl], dim=0))
 
 
 def _mlp_params(w1, b1, wh, bh, wo, bo, n_layers):
@@ -124,8 +143,8 @@ def mlp_bwd(u: Tensor, w1: Tensor, b1: Tensor, wh: Tensor, bh: Tensor, wo: Tenso
     if (not need_du and R > 0 and lib.gnan_mlp_bwd_ext_supported(p, precision) and 2 * R * G * H * 4 <= MLP_EXT_MAX_BYTES):
         # more than 8 output channels on the tensor-core path: the output layer runs as two plain GEMMs around ONE pass of the
         # kernel (dh = dS Wo in, a1 out, dWo = dS^T a1) instead of ceil(C/8) passes that each repeat the recompute
-        with _timed("mlp_bwd"), _fp32_matmul():
-            dh = torch.matmul(dS, wo.permute(1, 0, 2).reshape(C, G * H))                       # [R, G*H]
+        with _timed("mlp_bwd"), _matmul_tf32(False):
+            dh = _matmul_3xtf32(dS, wo.permute(1, 0, 2).reshape(C, G * H))                      # [R, G*H]
             a1 = torch.empty(R, G * H, dtype=torch.float32, device=u.device)
             g = MlpGrads(ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), ptr(outs[3]), None, ptr(outs[5]), None)
             check(lib.gnan_mlp_bwd_ext(ptr(u), R, u.shape[1], p, float(dropout_p), int(seed) & (2 ** 64 - 1), ptr(seed_dev), precision,
