@@ -469,10 +469,14 @@ def run_workload(args, env, name, *, steps, warmup, classes=0, compare_legs=Fals
         x_bytes = host.x.numel() * 4 if cx is None else cx_h.nbytes()
         h2d = x_bytes + sum(t.numel() * t.element_size() for t in (host.hop, host.hop_off, host.node_off, host.level_counts, host.y))
         if in_step_apsp:                                                # the step starts from the raw edge list
-            ei_d, noff_d, hoff_d, x_d, y_d = wl.edge_index.to(dev), pk.node_off, pk.hop_off, wl.x.to(dev), wl.y.to(dev)
-            # host form of the edge list: uint8 endpoints inside their graph + per-graph edge offsets (2 bytes per directed edge
-            # cross PCIe; gnan_edges_from_local rebuilds the int64 [2,E] edge_index on the device inside the timed step)
+            noff_d, hoff_d, x_d, y_d = pk.node_off, pk.hop_off, wl.x.to(dev), wl.y.to(dev)
+            # the batch's edge list in its transfer form: uint8 endpoints inside their graph + per-graph edge offsets (2 bytes per
+            # directed edge cross PCIe). --edge-format local (default): the step consumes it as it is (the BFS kernel builds each
+            # graph's adjacency in shared memory: no CSR builder); int64: the step starts from PyG's int64 [2,E] edge_index
+            # (gnan_edges_from_local rebuilds it on the device in the e2e leg, then gnan_build_csr + BFS)
             ei_h = LocalEdges.from_edge_index(wl.edge_index, node_off_h)
+            local_edges = args.edge_format == "local"
+            ei_d = ei_h.to(dev) if local_edges else wl.edge_index.to(dev)
             noff_h, hoff_h = pk.node_off.cpu(), pk.hop_off.cpu()
             data_d = (ei_d, noff_d, hoff_d, x_d, y_d, cx)
             h2d = x_bytes + ei_h.nbytes() + sum(t.numel() * t.element_size() for t in (noff_h, hoff_h, host.y))
@@ -498,7 +502,8 @@ def run_workload(args, env, name, *, steps, warmup, classes=0, compare_legs=Fals
 
         def widen(d):
             if in_step_apsp:
-                return d if not isinstance(d[0], LocalEdges) else (d[0].expand(d[1]), d[1], d[2], d[3], d[4], None if d[5] is None else d[5].to(dev))
+                e = d[0].expand(d[1]) if isinstance(d[0], LocalEdges) and not local_edges else d[0]
+                return (e, d[1], d[2], d[3], d[4], None if d[5] is None else d[5].to(dev))
             if getattr(d, "x_compressed", None) is not None:
                 d.x_compressed = d.x_compressed.to(dev)
             return d
@@ -540,7 +545,8 @@ def run_workload(args, env, name, *, steps, warmup, classes=0, compare_legs=Fals
                 static_hop.static_level_counts = True          # the level counts are refreshed with the same values only (see trainer.CapturedStep)
                 static_in = SimpleNamespace(x=None if cx is not None else data_d.x.clone(), hop_data=static_hop, x_compressed=scx)
             elif in_step_apsp:
-                static_in = (ei_d.clone(), noff_d.clone(), hoff_d.clone(), None if cx is not None else x_d.clone(), y_d.clone(), scx)
+                ei_s = LocalEdges(ei_d.src.clone(), ei_d.dst.clone(), ei_d.edge_off.clone()) if local_edges else ei_d.clone()
+                static_in = (ei_s, noff_d.clone(), hoff_d.clone(), None if cx is not None else x_d.clone(), y_d.clone(), scx)
             else:
                 static_in = PackedBatch(None if cx is not None else data_d.x.clone(), data_d.hop.clone(), data_d.hop_off.clone(),
                                         data_d.node_off.clone(), data_d.level_counts.clone(), data_d.y.clone(), data_d.max_nodes)
@@ -568,7 +574,11 @@ def run_workload(args, env, name, *, steps, warmup, classes=0, compare_legs=Fals
             for dst, src in zip(sin[1:5], data[1:5]):
                 if dst is not None:
                     dst.copy_(src, non_blocking=True)
-            data[0].expand(sin[1], out=sin[0])                      # LocalEdges -> int64 [2,E]
+            if local_edges:
+                for dst, src in zip((sin[0].src, sin[0].dst, sin[0].edge_off), (data[0].src, data[0].dst, data[0].edge_off)):
+                    dst.copy_(src, non_blocking=True)
+            else:
+                data[0].expand(sin[1], out=sin[0])                  # LocalEdges -> int64 [2,E]
             if sin[5] is not None:
                 sin[5].copy_tensors_(data[5])
         elif data is not sin:
@@ -784,7 +794,9 @@ def run_workload(args, env, name, *, steps, warmup, classes=0, compare_legs=Fals
             "vs_baseline": None,
             "dtype": {"fp32": "f32", "tf32x3": "f32 (shape-function hidden layers as 3xTF32 split on tcgen05, fp32 accumulate; aggregation: exact int32 "
                       "accumulation of 8-bit digits of S on tcgen05 kind::i8)", "tf32": "tf32"}[args.precision],
-            "data": "synthetic", "config": workload_config(wl, "gpu", world),
+            "data": "synthetic", "config": dict(workload_config(wl, "gpu", world), **({"edge_input": (
+                "LocalEdges (uint8 endpoints inside their graph + per-graph edge offsets): the BFS kernel builds each graph's adjacency itself"
+                if local_edges else "int64 [2,E] edge_index: gnan_build_csr + BFS")} if in_step_apsp else {})),
             "e2e": {"value": e2e_val, "unit": wl.unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "note": "hop matrix kept device-resident in the e2e leg (too large to stage in pinned host memory)" if (wl.kind == "node" and big) else None},
             "gpu_launches": int(launches), "cuda_graph": graphed is not None,
@@ -881,6 +893,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="gnan_b200", choices=["gnan_b200", "reference"])
+    ap.add_argument("--edge-format", default="local", choices=["local", "int64"],
+                    help="molecule workload: the step's edge-list input (LocalEdges transfer form, or PyG's int64 edge_index)")
     ap.add_argument("--workload", default=None, choices=["mol", "mutag", "cora", "pubmed", "arxiv"],
                     help="one workload only; default: headline = mol plus sub-records for the other BASELINE configs")
     ap.add_argument("--classes", type=int, default=0, help="override the number of classes (arxiv: 40, or 1 = the reference's hard-coded value)")

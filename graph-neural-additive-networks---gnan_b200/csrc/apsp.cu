@@ -368,7 +368,8 @@ constexpr int BV3_MAX_GROUPS = 5;                          // groups per CTA (3 
 
 __host__ __device__ inline size_t bv3_hop_bytes(int cap) { return bv2_round16((size_t)cap * cap + 16); }
 __host__ __device__ constexpr int bv3_ws(int W) { return W == 3 ? 4 : W; }         // frontier row stride in words: 16-byte rows for W = 3
-__host__ __device__ inline size_t bv3_fr_bytes(int cap, int W) { return bv2_round16((size_t)2 * cap * bv3_ws(W) * 4); }
+// two frontier buffers [n][WS] (+ the adjacency bit matrix [n][WS] when the kernel builds it from the edge segment itself)
+__host__ __device__ inline size_t bv3_fr_bytes(int cap, int W, bool local = false) { return bv2_round16((size_t)(local ? 3 : 2) * cap * bv3_ws(W) * 4); }
 
 // frontier rows move as ONE shared-memory access (LDS.128 / LDS.64 instead of W scalar loads per neighbour)
 template <int W>
@@ -392,9 +393,9 @@ __device__ __forceinline__ void bv3_store_row(uint32_t *row, const uint32_t (&w)
     else if (W == 2) *reinterpret_cast<uint2 *>(row) = make_uint2(w[0], w[1]);
     else row[0] = w[0];
 }
-__host__ __device__ inline size_t bv3_need(int cap, int W, int nbins, bool levels)
+__host__ __device__ inline size_t bv3_need(int cap, int W, int nbins, bool levels, bool local = false)
 {
-    return bv3_hop_bytes(cap) + bv3_fr_bytes(cap, W) + (levels ? bv2_round16((size_t)cap * nbins) : 0);
+    return bv3_hop_bytes(cap) + bv3_fr_bytes(cap, W, local) + (levels ? bv2_round16((size_t)cap * nbins) : 0);
 }
 
 template <int G>
@@ -417,10 +418,13 @@ __device__ __forceinline__ bool bv3_any(int bar, bool p)
     return r != 0;
 }
 
-// one graph on G warps, W = ceil(n/32) <= G words per vertex; thread ts = wsub * 32 + lane owns vertex ts
-template <int W, int G>
+// one graph on G warps, W = ceil(n/32) <= G words per vertex; thread ts = wsub * 32 + lane owns vertex ts.
+// LOCAL: the out-neighbours come from the adjacency bit matrix adj [n][WS] in shared memory (built by bv3_run from the graph's own
+// edge segment) instead of the CSR.
+template <int W, int G, bool LOCAL>
 __device__ __forceinline__ int bv3_graph(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, int n0, int n, int ts,
-                                         int bar, uint8_t *hb, uint32_t *frs, uint8_t *cs, int nbins, bool levels, int32_t *overflow)
+                                         int bar, uint8_t *hb, uint32_t *frs, const uint32_t *adj, uint8_t *cs, int nbins, bool levels,
+                                         int32_t *overflow)
 {
     constexpr int WS = bv3_ws(W);
     const int v = ts, lane = ts & 31, wsub = ts >> 5;
@@ -430,18 +434,37 @@ __device__ __forceinline__ int bv3_graph(const int32_t *__restrict__ rowptr, con
 #pragma unroll
     for (int ww = 0; ww < W; ++ww) vis[ww] = 0u;
     if (mine) {
-        const int eb = rowptr[n0 + v], ee = rowptr[n0 + v + 1];
-        int e = eb;
-        for (; e < ee && dg < 8; ++e) {                              // neighbours outside the graph are ignored
-            const int u = __ldg(col + e) - n0;
-            if (u >= 0 && u < n) {
-                const int sh = 8 * (dg & 3);
-                if (dg < 4) nb_lo = (nb_lo & ~(0xffu << sh)) | ((uint32_t)u << sh);
-                else nb_hi = (nb_hi & ~(0xffu << sh)) | ((uint32_t)u << sh);
-                ++dg;
+        auto keep = [&](uint32_t u) {
+            const int sh = 8 * (dg & 3);
+            if (dg < 4) nb_lo = (nb_lo & ~(0xffu << sh)) | (u << sh);
+            else nb_hi = (nb_hi & ~(0xffu << sh)) | (u << sh);
+            ++dg;
+        };
+        if (LOCAL) {
+            int deg = 0;
+#pragma unroll
+            for (int ww = 0; ww < W; ++ww) deg += __popc(adj[v * WS + ww]);
+            if (deg <= 8) {
+#pragma unroll
+                for (int ww = 0; ww < W; ++ww) {
+                    uint32_t m = adj[v * WS + ww];
+                    while (m) {
+                        keep((uint32_t)(ww * 32 + __ffs(m) - 1));
+                        m &= m - 1;
+                    }
+                }
+            } else {
+                e1 = 1;                                              // more than 8 neighbours: the level loop walks the adjacency row
             }
+        } else {
+            const int eb = rowptr[n0 + v], ee = rowptr[n0 + v + 1];
+            int e = eb;
+            for (; e < ee && dg < 8; ++e) {                          // neighbours outside the graph are ignored
+                const int u = __ldg(col + e) - n0;
+                if (u >= 0 && u < n) keep((uint32_t)u);
+            }
+            e8 = e; e1 = ee;
         }
-        e8 = e; e1 = ee;
 #pragma unroll
         for (int ww = 0; ww < W; ++ww) vis[ww] = ww == wsub ? 1u << lane : 0u;
         bv3_store_row<W>(frs + v * WS, vis);
@@ -466,9 +489,22 @@ __device__ __forceinline__ int bv3_graph(const int32_t *__restrict__ rowptr, con
                     bv3_or_row<W>(fc + u * WS, acc);
                 }
             }
-            for (int e = e8; e < e1; ++e) {                          // rows with more than 8 neighbours
-                const int u = __ldg(col + e) - n0;
-                if (u >= 0 && u < n) bv3_or_row<W>(fc + u * WS, acc);
+            if (LOCAL) {
+                if (e1) {                                            // rows with more than 8 neighbours
+#pragma unroll
+                    for (int ww = 0; ww < W; ++ww) {
+                        uint32_t m = adj[v * WS + ww];
+                        while (m) {
+                            bv3_or_row<W>(fc + (ww * 32 + __ffs(m) - 1) * WS, acc);
+                            m &= m - 1;
+                        }
+                    }
+                }
+            } else {
+                for (int e = e8; e < e1; ++e) {                      // rows with more than 8 neighbours
+                    const int u = __ldg(col + e) - n0;
+                    if (u >= 0 && u < n) bv3_or_row<W>(fc + u * WS, acc);
+                }
             }
             int newc = 0;
 #pragma unroll
@@ -530,10 +566,15 @@ struct Bv3Out {
     float *rscale;
     const float *rcp_tab;
     int nbins;
+    // LOCAL: the batch's edges grouped by graph, endpoints as indices inside the graph; *status |= 1 for an endpoint >= n (edge
+    // dropped), |= 2 for a repeated (src,dst) pair (gnan_build_csr's status bits)
+    const uint8_t *lsrc, *ldst;
+    const int32_t *edge_off;
+    int32_t *status;
 };
 
 // graph b on the G warps of a sub-group: fill the slice, BFS, write the level table and the hop block out
-template <int W, int G>
+template <int W, int G, bool LOCAL>
 __device__ __forceinline__ int bv3_run(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                                        const int32_t *__restrict__ node_off, const int64_t *__restrict__ hop_off, int64_t b, int cap,
                                        int ts, int bar, uint8_t *slice, const Bv3Out &o, bool levels, int32_t *overflow)
@@ -543,15 +584,33 @@ __device__ __forceinline__ int bv3_run(const int32_t *__restrict__ rowptr, const
     uint8_t *gb = o.hop + hop_off[b];
     const int pad = (int)(reinterpret_cast<uintptr_t>(gb) & 15);
     uint8_t *hb = slice + pad;                                                  // hb + k  ==  gb + k  (mod 16)
-    uint32_t *frs = reinterpret_cast<uint32_t *>(slice + bv3_hop_bytes(cap));  // [2][n][W]
-    uint8_t *cs = slice + bv3_hop_bytes(cap) + bv3_fr_bytes(cap, W);           // [n][nbins]
+    constexpr int WS = bv3_ws(W);
+    uint32_t *frs = reinterpret_cast<uint32_t *>(slice + bv3_hop_bytes(cap));  // [2][n][WS] (+ adjacency [n][WS])
+    uint32_t *adj = frs + 2 * n * WS;
+    uint8_t *cs = slice + bv3_hop_bytes(cap) + bv3_fr_bytes(cap, W, LOCAL);    // [n][nbins]
     const int total = n * n;
     for (int t = ts * 16; t < total + 16; t += T * 16)
         *reinterpret_cast<uint4 *>(slice + t) = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
     if (levels)
         for (int t = ts * 16; t < n * nbins; t += T * 16) *reinterpret_cast<uint4 *>(cs + t) = make_uint4(0u, 0u, 0u, 0u);
+    if (LOCAL) {
+        for (int t = ts; t < n * WS; t += T) adj[t] = 0u;
+        bv3_sync<G>(bar);
+        const int e0 = o.edge_off[b], e1 = o.edge_off[b + 1];
+        int flags = 0;
+        for (int e = e0 + ts; e < e1; e += T) {
+            const uint32_t s = o.lsrc[e], d = o.ldst[e];
+            if (s < (uint32_t)n && d < (uint32_t)n) {
+                const uint32_t bit = 1u << (d & 31);
+                if (atomicOr(adj + s * WS + (d >> 5), bit) & bit) flags |= 2;
+            } else {
+                flags |= 1;
+            }
+        }
+        if (flags) atomicOr(o.status, flags);
+    }
     bv3_sync<G>(bar);
-    const int lm = bv3_graph<W, G>(rowptr, col, n0, n, ts, bar, hb, frs, cs, nbins, levels, overflow);
+    const int lm = bv3_graph<W, G, LOCAL>(rowptr, col, n0, n, ts, bar, hb, frs, adj, cs, nbins, levels, overflow);
     bv3_sync<G>(bar);
     if (levels) {
         const int nt = n * nbins;                                               // the graph's [n][nbins] block is contiguous
@@ -591,12 +650,20 @@ __device__ __forceinline__ int bv3_run(const int32_t *__restrict__ rowptr, const
     return lm;
 }
 
+// the batch's edge list in its transfer form (LOCAL instantiation: no CSR; rowptr / col are NULL)
+struct Bv3Edges {
+    const uint8_t *src, *dst;
+    const int32_t *edge_off;
+    int32_t *status;
+};
+
 // order = the output of bv3_classify_kernel
+template <bool LOCAL>
 __global__ void __launch_bounds__(32 * BV3_GW * BV3_MAX_GROUPS, 2)
 apsp_batched_v3_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, const int32_t *__restrict__ node_off,
                        const int64_t *__restrict__ hop_off, int B, int max_n, int groups_per_cta, int slice_bytes, uint8_t *__restrict__ hop,
                        int32_t *__restrict__ cnt, float *__restrict__ rscale, int nbins, int32_t *__restrict__ overflow,
-                       int32_t *__restrict__ max_level, const int32_t *__restrict__ order)
+                       int32_t *__restrict__ max_level, const int32_t *__restrict__ order, Bv3Edges le)
 {
     extern __shared__ __align__(16) uint8_t sm3[];
     __shared__ float rcp_tab[256];
@@ -608,7 +675,7 @@ apsp_batched_v3_kernel(const int32_t *__restrict__ rowptr, const int32_t *__rest
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = warp / BV3_GW, wq = warp % BV3_GW;
     uint8_t *gslice = sm3 + (size_t)g * slice_bytes;
     const int bar_group = 1 + 3 * g;
-    const Bv3Out out{hop, cnt, rscale, rcp_tab, nbins};
+    const Bv3Out out{hop, cnt, rscale, rcp_tab, nbins, le.src, le.dst, le.edge_off, le.status};
     const int c0 = order[0], c_big = c0 + order[1], c2 = order[2], c3 = order[3];
     const int32_t *ord0 = order + 4, *ord1 = ord0 + B, *ord2 = ord1 + B, *ord3 = ord2 + B;
     const int items2 = (c2 + 1) / 2, items1 = (c3 + 3) / 4;
@@ -621,19 +688,19 @@ apsp_batched_v3_kernel(const int32_t *__restrict__ rowptr, const int32_t *__rest
             const int64_t b = t < c0 ? ord0[t] : ord1[t - c0];
             const int n = node_off[b + 1] - node_off[b];
             const int ts = wq * 32 + lane;
-            const int lm = n <= 96 ? bv3_run<3, 4>(rowptr, col, node_off, hop_off, b, max_n, ts, bar_group, gslice, out, levels, overflow)
-                                   : bv3_run<4, 4>(rowptr, col, node_off, hop_off, b, max_n, ts, bar_group, gslice, out, levels, overflow);
+            const int lm = n <= 96 ? bv3_run<3, 4, LOCAL>(rowptr, col, node_off, hop_off, b, max_n, ts, bar_group, gslice, out, levels, overflow)
+                                   : bv3_run<4, 4, LOCAL>(rowptr, col, node_off, hop_off, b, max_n, ts, bar_group, gslice, out, levels, overflow);
             lvl_max = max(lvl_max, lm);
         } else if (t < c_big + items2) {                             // 33..64 nodes: two graphs on the two warp pairs
             const int pr = wq >> 1;
             const int64_t idx = 2 * (t - c_big) + pr;
             if (idx < c2)
-                lvl_max = max(lvl_max, bv3_run<2, 2>(rowptr, col, node_off, hop_off, ord2[idx], cap2, (wq & 1) * 32 + lane,
+                lvl_max = max(lvl_max, bv3_run<2, 2, LOCAL>(rowptr, col, node_off, hop_off, ord2[idx], cap2, (wq & 1) * 32 + lane,
                                                      bar_group + 1 + pr, gslice + (size_t)pr * half, out, levels, overflow));
         } else {                                                     // up to 32 nodes: four graphs, a warp each
             const int64_t idx = 4 * (t - c_big - items2) + wq;
             if (idx < c3)
-                lvl_max = max(lvl_max, bv3_run<1, 1>(rowptr, col, node_off, hop_off, ord3[idx], cap1, lane, 0,
+                lvl_max = max(lvl_max, bv3_run<1, 1, LOCAL>(rowptr, col, node_off, hop_off, ord3[idx], cap1, lane, 0,
                                                      gslice + (size_t)wq * quarter, out, levels, overflow));
         }
         bv3_sync<BV3_GW>(bar_group);                                 // the slice is re-partitioned / refilled by the next item
@@ -939,6 +1006,36 @@ extern "C" int gnan_apsp_msbfs(const int32_t *rowptr, const int32_t *col, int32_
     return GNAN_OK;
 }
 
+// v3 launch: groups of 4 warps; the group's slice holds one graph of 65..128 nodes, two of 33..64 or four of up to 32
+template <bool LOCAL>
+static int launch_bv3(const int32_t *rowptr, const int32_t *col, const int32_t *node_off, const int64_t *hop_off, int32_t B, int32_t max_n,
+                      uint8_t *hop, int32_t *cnt, float *rscale, int nb, bool levels, int32_t *overflow_flag, int32_t *max_level,
+                      int32_t *order_ws, Bv3Edges le, cudaStream_t st)
+{
+    const int Wmax = (max_n + 31) / 32;
+    size_t slice = 4 * bv3_need(std::min(max_n, 32), 1, nb, levels, LOCAL);
+    if (Wmax >= 2) slice = std::max(slice, 2 * bv3_need(std::min(max_n, 64), 2, nb, levels, LOCAL));
+    if (Wmax >= 3) slice = std::max(slice, bv3_need(max_n, Wmax, nb, levels, LOCAL));
+    const int gpc = (int)std::min<size_t>(BV3_MAX_GROUPS, (112 * 1024) / slice);     // two CTAs per SM
+    if (gpc < 1) return GNAN_ERR_UNSUPPORTED;
+    const size_t smem3 = slice * gpc;
+    static thread_local size_t cached_smem3 = 0;
+    static thread_local int cached_gpc = 0, cached_per_sm3 = 0;
+    if (cached_smem3 != smem3 || cached_gpc != gpc || cached_per_sm3 == 0) {
+        GNAN_CUDA(cudaFuncSetAttribute(apsp_batched_v3_kernel<LOCAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        GNAN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_per_sm3, apsp_batched_v3_kernel<LOCAL>, 32 * BV3_GW * gpc, smem3));
+        cached_smem3 = smem3; cached_gpc = gpc;
+    }
+    const int blocks3 = (int)std::min<int64_t>(ceil_div64(B, gpc), (int64_t)std::max(cached_per_sm3, 1) * gnan_sm_count());
+    GNAN_CUDA(cudaMemsetAsync(order_ws, 0, 4 * sizeof(int32_t), st));
+    bv3_classify_kernel<<<(unsigned)ceil_div64(B, 256), 256, 0, st>>>(node_off, B, order_ws);
+    GNAN_LAUNCH_OK();
+    apsp_batched_v3_kernel<LOCAL><<<blocks3, 32 * BV3_GW * gpc, smem3, st>>>(rowptr, col, node_off, hop_off, B, max_n, gpc, (int)slice, hop, cnt,
+                                                                            rscale, nb, overflow_flag, max_level, order_ws, le);
+    GNAN_LAUNCH_OK();
+    return GNAN_OK;
+}
+
 // max_n is needed to size shared memory; exported variant with it explicit (the header-declared entry derives it on the host side)
 extern "C" int gnan_apsp_bfs_batched_n(const int32_t *rowptr, const int32_t *col, const int32_t *node_off, const int64_t *hop_off,
                                        int32_t B, int32_t max_n, int64_t total_nodes, int64_t total_hop_bytes, uint8_t *hop,
@@ -972,30 +1069,9 @@ extern "C" int gnan_apsp_bfs_batched_ex(const int32_t *rowptr, const int32_t *co
         const int nb = levels ? nbins : 256;
         static const bool force_v2 = getenv("GNAN_BFS_V2") != nullptr;
         if (order_ws && !force_v2) {
-            // v3: groups of 4 warps; the group's slice holds one graph of 65..128 nodes, two of 33..64 or four of up to 32
-            const int Wmax = (max_n + 31) / 32;
-            size_t slice = 4 * bv3_need(std::min(max_n, 32), 1, nb, levels);
-            if (Wmax >= 2) slice = std::max(slice, 2 * bv3_need(std::min(max_n, 64), 2, nb, levels));
-            if (Wmax >= 3) slice = std::max(slice, bv3_need(max_n, Wmax, nb, levels));
-            const int gpc = (int)std::min<size_t>(BV3_MAX_GROUPS, (112 * 1024) / slice);     // two CTAs per SM
-            if (gpc >= 1) {
-                const size_t smem3 = slice * gpc;
-                static thread_local size_t cached_smem3 = 0;
-                static thread_local int cached_gpc = 0, cached_per_sm3 = 0;
-                if (cached_smem3 != smem3 || cached_gpc != gpc || cached_per_sm3 == 0) {
-                    GNAN_CUDA(cudaFuncSetAttribute(apsp_batched_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-                    GNAN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_per_sm3, apsp_batched_v3_kernel, 32 * BV3_GW * gpc, smem3));
-                    cached_smem3 = smem3; cached_gpc = gpc;
-                }
-                const int blocks3 = (int)std::min<int64_t>(ceil_div64(B, gpc), (int64_t)std::max(cached_per_sm3, 1) * gnan_sm_count());
-                GNAN_CUDA(cudaMemsetAsync(order_ws, 0, 4 * sizeof(int32_t), st));
-                bv3_classify_kernel<<<(unsigned)ceil_div64(B, 256), 256, 0, st>>>(node_off, B, order_ws);
-                GNAN_LAUNCH_OK();
-                apsp_batched_v3_kernel<<<blocks3, 32 * BV3_GW * gpc, smem3, st>>>(rowptr, col, node_off, hop_off, B, max_n, gpc, (int)slice, hop,
-                                                                                 cnt, rscale, nb, overflow_flag, max_level, order_ws);
-                GNAN_LAUNCH_OK();
-                return GNAN_OK;
-            }
+            const int rc3 = launch_bv3<false>(rowptr, col, node_off, hop_off, B, max_n, hop, cnt, rscale, nb, levels, overflow_flag, max_level,
+                                              order_ws, Bv3Edges{nullptr, nullptr, nullptr, nullptr}, st);
+            if (rc3 != GNAN_ERR_UNSUPPORTED) return rc3;
         }
         // v2: one warp per graph; hop blocks assembled in shared memory and written once (no memset of hop)
         const int Wmax = (max_n + 31) / 32;
@@ -1040,6 +1116,31 @@ extern "C" int gnan_apsp_bfs_batched_ex(const int32_t *rowptr, const int32_t *co
                                                    cnt ? nbins : 256, overflow_flag, prefilled, max_level);
     GNAN_LAUNCH_OK();
     return GNAN_OK;
+}
+
+// The batched BFS straight from the batch's edge list in its transfer form (no CSR): see include/gnan_b200.h
+extern "C" int gnan_apsp_bfs_batched_local(const uint8_t *src, const uint8_t *dst, const int32_t *edge_off, const int32_t *node_off,
+                                           const int64_t *hop_off, int32_t B, int32_t max_n, uint8_t *hop, int32_t *cnt, float *rscale,
+                                           int32_t nbins, int32_t *status, int32_t *overflow_flag, int32_t *max_level, int32_t *order_ws,
+                                           gnan_stream_t stream)
+{
+    GNAN_REQUIRE(B >= 0, "apsp_bfs_batched_local: negative batch");
+    GNAN_REQUIRE(status != nullptr, "apsp_bfs_batched_local: NULL status");
+    cudaStream_t st = (cudaStream_t)stream;
+    GNAN_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
+    if (B == 0) return GNAN_OK;
+    GNAN_REQUIRE(edge_off && node_off && hop_off && hop && overflow_flag && order_ws, "apsp_bfs_batched_local: NULL pointer");
+    GNAN_REQUIRE(!(cnt || rscale) || (nbins >= 2 && nbins <= 256), "apsp_bfs_batched_local: nbins %d out of [2,256]", nbins);
+    if (max_n < 1 || max_n > 32 * BV2_W) {
+        gnan_set_error("apsp_bfs_batched_local: graphs with %d nodes unsupported (1..%d); expand the edges and use gnan_apsp_bfs_batched_ex",
+                       max_n, 32 * BV2_W);
+        return GNAN_ERR_UNSUPPORTED;
+    }
+    const bool levels = cnt || rscale;
+    const int rc = launch_bv3<true>(nullptr, nullptr, node_off, hop_off, B, max_n, hop, cnt, rscale, levels ? nbins : 256, levels, overflow_flag,
+                                    max_level, order_ws, Bv3Edges{src, dst, edge_off, status}, st);
+    if (rc == GNAN_ERR_UNSUPPORTED) gnan_set_error("apsp_bfs_batched_local: level table too wide for the shared-memory slice");
+    return rc;
 }
 
 extern "C" int gnan_apsp_bfs_batched(const int32_t *rowptr, const int32_t *col, const int32_t *node_off, const int64_t *hop_off,

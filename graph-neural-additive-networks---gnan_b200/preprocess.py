@@ -355,7 +355,10 @@ def check_batched_status(status):
 def apsp_batched(edge_index, node_off, device="cuda", x=None, y=None, node_off_device=None, _level_table_width=48, nbins=None,
                  hop_off_device=None, rscale=False):
     """Hop blocks of B small graphs (<= 256 nodes each) in one launch. edge_index uses GLOBAL node ids of the
-    concatenated node set; node_off [B+1] are the graph boundaries.
+    concatenated node set; node_off [B+1] are the graph boundaries. edge_index may also be a `LocalEdges` (the batch's edge list
+    in its transfer form): batches of graphs with at most 128 nodes then skip the CSR builder altogether — every 4-warp group of
+    the BFS kernel builds its graph's adjacency bit matrix in shared memory from the graph's own edge segment
+    (gnan_apsp_bfs_batched_local); other batches expand it to the int64 list first.
 
     nbins: fixed level-table width (levels 0..nbins-2, last column = unreachable). The call then never synchronises with the
     host (it can be captured in a CUDA graph with the rest of a training step); empty levels carry a zero count and
@@ -390,8 +393,27 @@ def apsp_batched(edge_index, node_off, device="cuda", x=None, y=None, node_off_d
     node_off_d = node_off_device
     hop_off = hop_off_device if hop_off_device is not None else torch.from_numpy(hop_off_h).to(device, non_blocking=True)
     st = torch.zeros(3, dtype=torch.int32, device=device)              # [csr status, overflow, largest finite hop]
-    rowptr, col, _ = build_csr(edge_index, sumN, device, status=st[0:1])
+    local = None
+    if isinstance(edge_index, LocalEdges):
+        if not edge_index.src.is_cuda:
+            edge_index = edge_index.to(device)
+        if max_n <= 128 and sumN > 0 and B > 0:
+            local = edge_index
+        else:
+            edge_index = edge_index.expand(node_off_d)
+    if local is None:
+        rowptr, col, _ = build_csr(edge_index, sumN, device, status=st[0:1])
     hop = torch.empty(max(total, 1), dtype=torch.uint8, device=device)
+
+    def bfs(cnt_t, rs_t, order_ws):
+        if local is not None:
+            check(lib.gnan_apsp_bfs_batched_local(ptr(local.src), ptr(local.dst), ptr(local.edge_off), ptr(node_off_d), ptr(hop_off), B, max_n,
+                                                  ptr(hop), ptr(cnt_t), ptr(rs_t), nb, st.data_ptr(), st.data_ptr() + 4, st.data_ptr() + 8,
+                                                  ptr(order_ws), stream_handle()), "gnan_apsp_bfs_batched_local")
+        else:
+            check(lib.gnan_apsp_bfs_batched_ex(ptr(rowptr), ptr(col), ptr(node_off_d), ptr(hop_off), B, max_n, sumN, total, ptr(hop), ptr(cnt_t),
+                                               ptr(rs_t), nb, st.data_ptr() + 4, st.data_ptr() + 8, ptr(order_ws), stream_handle()),
+                  "gnan_apsp_bfs_batched_ex")
     nb_full = min(256, max_n + 1)                # a finite hop inside a graph is at most max_n - 1; last column = unreachable
     nb = min(nb_full, _level_table_width) if _level_table_width else nb_full
     if nbins is not None:
@@ -402,17 +424,14 @@ def apsp_batched(edge_index, node_off, device="cuda", x=None, y=None, node_off_d
         rs = torch.empty(sumN, nb, dtype=torch.float32, device=device)
         order_ws = torch.empty(4 * B + 4, dtype=torch.int32, device=device)
         with _timed("apsp_bfs_batched"):
-            check(lib.gnan_apsp_bfs_batched_ex(ptr(rowptr), ptr(col), ptr(node_off_d), ptr(hop_off), B, max_n, sumN, total, ptr(hop), None,
-                                               ptr(rs), nb, st.data_ptr() + 4, st.data_ptr() + 8, ptr(order_ws), stream_handle()),
-                  "gnan_apsp_bfs_batched_ex")
+            bfs(None, rs, order_ws)
         pk = PackedBatch(x, hop, hop_off, node_off_d, None, y, max_n, level_rscale=rs)
         pk.status = st
         return pk
     cnt = torch.empty(sumN, nb, dtype=torch.int32, device=device)
     order_ws = torch.empty(4 * B + 4, dtype=torch.int32, device=device)     # graphs are processed grouped by size class
     with _timed("apsp_bfs_batched"):
-        check(lib.gnan_apsp_bfs_batched_ex(ptr(rowptr), ptr(col), ptr(node_off_d), ptr(hop_off), B, max_n, sumN, total, ptr(hop), ptr(cnt), None,
-                                           nb, st.data_ptr() + 4, st.data_ptr() + 8, ptr(order_ws), stream_handle()), "gnan_apsp_bfs_batched")
+        bfs(cnt, None, order_ws)
     if nbins is not None:
         pk = PackedBatch(x, hop, hop_off, node_off_d, cnt, y, max_n)
         pk.status = st
@@ -420,6 +439,8 @@ def apsp_batched(edge_index, node_off, device="cuda", x=None, y=None, node_off_d
     status, over, D = (int(v) for v in st.tolist()) if B > 0 else (0, 0, 0)
     _check_status(status)
     if status & 2:
+        if isinstance(edge_index, LocalEdges):
+            edge_index = edge_index.expand(node_off_d)
         return _apsp_batched_multi_edges(edge_index, no_h, device, x, y)
     if over and nb < nb_full:                    # deeper than the narrow level table: once more with the full width
         return apsp_batched(edge_index, node_off, device, x, y, node_off_device, _level_table_width=0, hop_off_device=hop_off_device)

@@ -336,6 +336,17 @@ int gnan_apsp_bfs_batched_ex(const int32_t *rowptr, const int32_t *col, const in
                              int32_t *order_ws /* [4*B+4] scratch or NULL. With it the graphs are grouped by size class and a group of 4 warps works on one graph of 65..128 nodes, two of 33..64 or four of up to 32 nodes at a time; NULL = one warp per graph */,
                              gnan_stream_t stream);
 
+/* gnan_apsp_bfs_batched_ex WITHOUT a CSR: the batch's edges in their transfer form (gnan_edges_from_local: src / dst uint8 indices
+ * inside the graph, edge_off [B+1], edges grouped by graph). Every 4-warp group builds its graph's adjacency bit matrix in shared
+ * memory from the graph's own edge segment; gnan_build_csr (and its ~0.1 ms per 4 M edges) drops out of a training step that
+ * preprocesses its batch. Graphs of at most 128 nodes; order_ws [4*B+4] is required. *status (device int32, zeroed here) gets
+ * gnan_build_csr's bits: 1 = an endpoint >= the graph's node count (edge dropped), 2 = a repeated (src,dst) pair (the reference
+ * sums those into weight-2 edges: the caller must take the multi-edge path). pre_process_datasets.py:106-122 per graph. */
+int gnan_apsp_bfs_batched_local(const uint8_t *src, const uint8_t *dst, const int32_t *edge_off, const int32_t *node_off,
+                                const int64_t *hop_off, int32_t B, int32_t max_n, uint8_t *hop, int32_t *cnt, float *rscale,
+                                int32_t nbins, int32_t *status, int32_t *overflow_flag, int32_t *max_level, int32_t *order_ws,
+                                gnan_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Deep graphs (csrc/wide.cu): hop distances > 254. The reference has no depth limit (pre_process_datasets.py:109-121), so the
  * same path exists with an int16 hop matrix (-1 = unreachable, levels 0..32766): warp-per-source BFS (no level table: the depth

@@ -333,6 +333,36 @@ def test_apsp_batched_grouped_warps_many_graphs(directed, lo, hi):
     wide[:, :cnt.shape[1] - 1] = c[:, :-1]; wide[:, -1] = c[:, -1]
     want_rs = torch.where(wide > 0, 1.0 / wide, torch.zeros_like(wide))
     assert torch.equal(fx.level_rscale.cpu(), want_rs)
+    # the same batch from its transfer form (no CSR: adjacency bit matrices built in shared memory from the edge segments)
+    from gnan_b200.preprocess import LocalEdges
+    le = LocalEdges.from_edge_index(ei, node_off).to(DEV)
+    lp = apsp_batched(le, node_off, device=DEV)
+    assert torch.equal(lp.hop, pk.hop) and torch.equal(lp.level_counts, pk.level_counts)
+    lf = apsp_batched(le, node_off, device=DEV, nbins=130, rscale=True)
+    check_batched_status(lf.status)
+    assert torch.equal(lf.hop, pk.hop) and torch.equal(lf.level_rscale, fx.level_rscale)
+
+
+def test_apsp_batched_local_edges_flags_duplicates_and_bad_endpoints():
+    """gnan_apsp_bfs_batched_local reports gnan_build_csr's status bits: a repeated (src,dst) pair (the caller then takes the
+    multi-edge path and reproduces the reference's summed weights) and an endpoint outside the graph (edge dropped)."""
+    from gnan_b200.preprocess import LocalEdges, apsp_batched
+    rng = np.random.default_rng(12)
+    sizes = [12, 40, 7, 100]
+    node_off = np.concatenate([[0], np.cumsum(sizes)])
+    eis = [random_graph(rng, n, 2.2, False, n_isolated=1) for n in sizes]
+    eis[1] = np.concatenate([eis[1], eis[1][:, :3]], axis=1)                      # three edges of graph 1 twice
+    ei = torch.tensor(np.concatenate([e + node_off[i] for i, e in enumerate(eis)], axis=1))
+    a = apsp_batched(ei, node_off, device=DEV)
+    b = apsp_batched(LocalEdges.from_edge_index(ei, node_off), node_off, device=DEV)
+    assert torch.equal(a.hop, b.hop) and torch.equal(a.level_counts, b.level_counts)
+    fx = apsp_batched(LocalEdges.from_edge_index(ei, node_off), node_off, device=DEV, nbins=48)
+    assert int(fx.status[0]) & 2                                                  # duplicates flagged in the sync-free mode
+    clean = torch.tensor(np.concatenate([e + node_off[i] for i, e in enumerate(eis) if i != 1], axis=1))
+    le = LocalEdges.from_edge_index(clean, node_off)
+    le.dst[0] = 200                                                               # endpoint beyond its graph's 12 nodes
+    fx = apsp_batched(le, node_off, device=DEV, nbins=48)
+    assert int(fx.status[0]) == 1
 
 
 def test_apsp_batched_vs_oracle():
