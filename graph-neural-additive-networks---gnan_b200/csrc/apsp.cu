@@ -369,7 +369,11 @@ constexpr int BV3_MAX_GROUPS = 5;                          // groups per CTA (3 
 __host__ __device__ inline size_t bv3_hop_bytes(int cap) { return bv2_round16((size_t)cap * cap + 16); }
 __host__ __device__ constexpr int bv3_ws(int W) { return W == 3 ? 4 : W; }         // frontier row stride in words: 16-byte rows for W = 3
 // two frontier buffers [n][WS] (+ the adjacency bit matrix [n][WS] when the kernel builds it from the edge segment itself)
-__host__ __device__ inline size_t bv3_fr_bytes(int cap, int W, bool local = false) { return bv2_round16((size_t)(local ? 3 : 2) * cap * bv3_ws(W) * 4); }
+// with pair statistics: + two fp32 [n] buffers of 1/count of the current level (by level parity)
+__host__ __device__ inline size_t bv3_fr_bytes(int cap, int W, bool local = false, bool pst = false)
+{
+    return bv2_round16((size_t)(local ? 3 : 2) * cap * bv3_ws(W) * 4 + (pst ? (size_t)2 * cap * 4 : 0));
+}
 
 // frontier rows move as ONE shared-memory access (LDS.128 / LDS.64 instead of W scalar loads per neighbour)
 template <int W>
@@ -393,9 +397,9 @@ __device__ __forceinline__ void bv3_store_row(uint32_t *row, const uint32_t (&w)
     else if (W == 2) *reinterpret_cast<uint2 *>(row) = make_uint2(w[0], w[1]);
     else row[0] = w[0];
 }
-__host__ __device__ inline size_t bv3_need(int cap, int W, int nbins, bool levels, bool local = false)
+__host__ __device__ inline size_t bv3_need(int cap, int W, int nbins, bool levels, bool local = false, bool pst = false)
 {
-    return bv3_hop_bytes(cap) + bv3_fr_bytes(cap, W, local) + (levels ? bv2_round16((size_t)cap * nbins) : 0);
+    return bv3_hop_bytes(cap) + bv3_fr_bytes(cap, W, local, pst) + (levels ? bv2_round16((size_t)cap * nbins) : 0);
 }
 
 template <int G>
@@ -421,10 +425,16 @@ __device__ __forceinline__ bool bv3_any(int bar, bool p)
 // one graph on G warps, W = ceil(n/32) <= G words per vertex; thread ts = wsub * 32 + lane owns vertex ts.
 // LOCAL: the out-neighbours come from the adjacency bit matrix adj [n][WS] in shared memory (built by bv3_run from the graph's own
 // edge segment) instead of the CSR.
-template <int W, int G, bool LOCAL>
+// PST (undirected graphs only): also the pair statistics P[d,v] = sum_{i: hop(i,v) = d} 1/count(i,d) of the output-normalised graph
+// readout (models.py:366-384), written LEVEL-MAJOR into the graph's block `pgraph` [nbins][n] (rows 0..deepest level and the
+// last one, the unreachable bin; the rows in between are never written nor read). By symmetry the vertices at distance d from v are v's own new
+// sources at level d, and count(i,d) is vertex i's popcount at that level: every lane publishes 1/count of the level in shared
+// memory (rcl, by level parity) and, after the level's barrier, sums it over its new bits in the same loop that scatters the hop
+// bytes. The aggregation forward then never reads the hop bytes or a normaliser table.
+template <int W, int G, bool LOCAL, bool PST>
 __device__ __forceinline__ int bv3_graph(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, int n0, int n, int ts,
                                          int bar, uint8_t *hb, uint32_t *frs, const uint32_t *adj, uint8_t *cs, int nbins, bool levels,
-                                         int32_t *overflow)
+                                         int32_t *overflow, float *rcl, float *pgraph)
 {
     constexpr int WS = bv3_ws(W);
     const int v = ts, lane = ts & 31, wsub = ts >> 5;
@@ -472,6 +482,8 @@ __device__ __forceinline__ int bv3_graph(const int32_t *__restrict__ rowptr, con
         if (levels) cs[v * nbins] = 1;
     }
     bv3_sync<G>(bar);
+    uint32_t nw[PST ? W : 1];                                     // PST: the new bits of the level, scattered after its barrier
+    if (PST && mine) pgraph[v] = 1.f;                             // level 0: v itself, count 1
     int lvl_max = 0;
     for (int level = 1; level <= n; ++level) {
         const uint32_t *fc = frs + ((level - 1) & 1) * n * WS;
@@ -514,17 +526,23 @@ __device__ __forceinline__ int bv3_graph(const int32_t *__restrict__ rowptr, con
                 newc += __popc(acc[ww]);
             }
             bv3_store_row<W>(fn + v * WS, acc);
+            if (!PST) {
 #pragma unroll
-            for (int ww = 0; ww < W; ++ww) {
-                uint32_t m = acc[ww];
-                uint8_t *rowp = hb + v * n + ww * 32;
-                while (m) {
-                    const int lo = __ffs(m) - 1, hi = 31 - __clz(m);
-                    rowp[lo] = lv;
-                    rowp[hi] = lv;
-                    m &= m - 1;
-                    m &= ~(1u << hi);
+                for (int ww = 0; ww < W; ++ww) {
+                    uint32_t m = acc[ww];
+                    uint8_t *rowp = hb + v * n + ww * 32;
+                    while (m) {
+                        const int lo = __ffs(m) - 1, hi = 31 - __clz(m);
+                        rowp[lo] = lv;
+                        rowp[hi] = lv;
+                        m &= m - 1;
+                        m &= ~(1u << hi);
+                    }
                 }
+            } else {
+                rcl[(level & 1) * n + v] = newc ? __frcp_rn((float)newc) : 0.f;
+#pragma unroll
+                for (int ww = 0; ww < W; ++ww) nw[ww] = acc[ww];
             }
             if (newc) {
                 any = true;
@@ -534,12 +552,50 @@ __device__ __forceinline__ int bv3_graph(const int32_t *__restrict__ rowptr, con
         }
         if (!bv3_any<G>(bar, any)) break;
         lvl_max = level;
-    }
-    if (levels && mine) {
-        int reached = 0;
+        if (PST && mine) {                                       // after the barrier: everybody's 1/count of this level is visible
+            const float *rc = rcl + (level & 1) * n;
+            float ps = 0.f, ps2 = 0.f;                            // two independent chains (lowest / highest new source)
 #pragma unroll
-        for (int ww = 0; ww < W; ++ww) reached += __popc(vis[ww]);
-        cs[v * nbins + nbins - 1] = (uint8_t)(n - reached);
+            for (int ww = 0; ww < W; ++ww) {
+                uint32_t m = nw[ww];
+                uint8_t *rowp = hb + v * n + ww * 32;
+                const float *rcw = rc + ww * 32;
+                while (m) {
+                    const int lo = __ffs(m) - 1, hi = 31 - __clz(m);
+                    rowp[lo] = lv;
+                    rowp[hi] = lv;
+                    ps += rcw[lo];
+                    ps2 += hi != lo ? rcw[hi] : 0.f;
+                    m &= m - 1;
+                    m &= ~(1u << hi);
+                }
+            }
+            if (level < nbins - 1) pgraph[level * n + v] = ps + ps2;   // level-major: a warp writes 32 consecutive floats
+        }
+    }
+    int reached = 0;
+#pragma unroll
+    for (int ww = 0; ww < W; ++ww) reached += __popc(vis[ww]);
+    if (levels && mine) cs[v * nbins + nbins - 1] = (uint8_t)(n - reached);
+    if (PST) {
+        // unreachable bin: sum over the vertices outside v's component of 1/(their unreachable count); skipped for connected graphs
+        float U = 0.f;
+        if (bv3_any<G>(bar, mine && reached < n)) {
+            if (mine) rcl[v] = reached < n ? __frcp_rn((float)(n - reached)) : 0.f;
+            bv3_sync<G>(bar);
+            if (mine) {
+#pragma unroll
+                for (int ww = 0; ww < W; ++ww) {
+                    const int left = n - ww * 32;
+                    uint32_t m = ~vis[ww] & (left >= 32 ? 0xffffffffu : (left > 0 ? (1u << left) - 1u : 0u));
+                    while (m) {
+                        U += rcl[ww * 32 + __ffs(m) - 1];
+                        m &= m - 1;
+                    }
+                }
+            }
+        }
+        if (mine) pgraph[(nbins - 1) * n + v] = U;
     }
     return lvl_max;
 }
@@ -571,10 +627,12 @@ struct Bv3Out {
     const uint8_t *lsrc, *ldst;
     const int32_t *edge_off;
     int32_t *status;
+    float *pstat;        // PST: pair statistics, graph b's level-major block [nbins][n_b] at n0_b * nbins (status |= 4 when a graph's
+    int32_t *pdepth;     // adjacency is not symmetric); pdepth[b] = deepest level written
 };
 
 // graph b on the G warps of a sub-group: fill the slice, BFS, write the level table and the hop block out
-template <int W, int G, bool LOCAL>
+template <int W, int G, bool LOCAL, bool PST>
 __device__ __forceinline__ int bv3_run(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                                        const int32_t *__restrict__ node_off, const int64_t *__restrict__ hop_off, int64_t b, int cap,
                                        int ts, int bar, uint8_t *slice, const Bv3Out &o, bool levels, int32_t *overflow)
@@ -587,7 +645,8 @@ __device__ __forceinline__ int bv3_run(const int32_t *__restrict__ rowptr, const
     constexpr int WS = bv3_ws(W);
     uint32_t *frs = reinterpret_cast<uint32_t *>(slice + bv3_hop_bytes(cap));  // [2][n][WS] (+ adjacency [n][WS])
     uint32_t *adj = frs + 2 * n * WS;
-    uint8_t *cs = slice + bv3_hop_bytes(cap) + bv3_fr_bytes(cap, W, LOCAL);    // [n][nbins]
+    float *rcl = reinterpret_cast<float *>(adj + n * WS);                      // PST: [2][n] 1/count of the current level
+    uint8_t *cs = slice + bv3_hop_bytes(cap) + bv3_fr_bytes(cap, W, LOCAL, PST);   // [n][nbins]
     const int total = n * n;
     for (int t = ts * 16; t < total + 16; t += T * 16)
         *reinterpret_cast<uint4 *>(slice + t) = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
@@ -607,10 +666,19 @@ __device__ __forceinline__ int bv3_run(const int32_t *__restrict__ rowptr, const
                 flags |= 1;
             }
         }
+        if (PST) {                                               // the pair statistics rely on hop(i,j) = hop(j,i)
+            bv3_sync<G>(bar);
+            for (int e = e0 + ts; e < e1; e += T) {
+                const uint32_t s = o.lsrc[e], d = o.ldst[e];
+                if (s < (uint32_t)n && d < (uint32_t)n && !((adj[d * WS + (s >> 5)] >> (s & 31)) & 1u)) flags |= 4;
+            }
+        }
         if (flags) atomicOr(o.status, flags);
     }
     bv3_sync<G>(bar);
-    const int lm = bv3_graph<W, G, LOCAL>(rowptr, col, n0, n, ts, bar, hb, frs, adj, cs, nbins, levels, overflow);
+    const int lm = bv3_graph<W, G, LOCAL, PST>(rowptr, col, n0, n, ts, bar, hb, frs, adj, cs, nbins, levels, overflow, rcl,
+                                               PST ? o.pstat + (int64_t)n0 * nbins : nullptr);
+    if (PST && ts == 0) o.pdepth[b] = min(lm, nbins - 2);
     bv3_sync<G>(bar);
     if (levels) {
         const int nt = n * nbins;                                               // the graph's [n][nbins] block is contiguous
@@ -655,11 +723,14 @@ struct Bv3Edges {
     const uint8_t *src, *dst;
     const int32_t *edge_off;
     int32_t *status;
+    float *pstat;
+    int32_t *pdepth;
 };
 
 // order = the output of bv3_classify_kernel
-template <bool LOCAL>
-__global__ void __launch_bounds__(32 * BV3_GW * BV3_MAX_GROUPS, 2)
+// (the pair-statistics instantiation keeps the level's new bits across the barrier: 4 groups per CTA give it 64 registers)
+template <bool LOCAL, bool PST>
+__global__ void __launch_bounds__(32 * BV3_GW * (PST ? BV3_MAX_GROUPS - 1 : BV3_MAX_GROUPS), 2)
 apsp_batched_v3_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, const int32_t *__restrict__ node_off,
                        const int64_t *__restrict__ hop_off, int B, int max_n, int groups_per_cta, int slice_bytes, uint8_t *__restrict__ hop,
                        int32_t *__restrict__ cnt, float *__restrict__ rscale, int nbins, int32_t *__restrict__ overflow,
@@ -675,7 +746,7 @@ apsp_batched_v3_kernel(const int32_t *__restrict__ rowptr, const int32_t *__rest
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = warp / BV3_GW, wq = warp % BV3_GW;
     uint8_t *gslice = sm3 + (size_t)g * slice_bytes;
     const int bar_group = 1 + 3 * g;
-    const Bv3Out out{hop, cnt, rscale, rcp_tab, nbins, le.src, le.dst, le.edge_off, le.status};
+    const Bv3Out out{hop, cnt, rscale, rcp_tab, nbins, le.src, le.dst, le.edge_off, le.status, le.pstat, le.pdepth};
     const int c0 = order[0], c_big = c0 + order[1], c2 = order[2], c3 = order[3];
     const int32_t *ord0 = order + 4, *ord1 = ord0 + B, *ord2 = ord1 + B, *ord3 = ord2 + B;
     const int items2 = (c2 + 1) / 2, items1 = (c3 + 3) / 4;
@@ -688,19 +759,19 @@ apsp_batched_v3_kernel(const int32_t *__restrict__ rowptr, const int32_t *__rest
             const int64_t b = t < c0 ? ord0[t] : ord1[t - c0];
             const int n = node_off[b + 1] - node_off[b];
             const int ts = wq * 32 + lane;
-            const int lm = n <= 96 ? bv3_run<3, 4, LOCAL>(rowptr, col, node_off, hop_off, b, max_n, ts, bar_group, gslice, out, levels, overflow)
-                                   : bv3_run<4, 4, LOCAL>(rowptr, col, node_off, hop_off, b, max_n, ts, bar_group, gslice, out, levels, overflow);
+            const int lm = n <= 96 ? bv3_run<3, 4, LOCAL, PST>(rowptr, col, node_off, hop_off, b, max_n, ts, bar_group, gslice, out, levels, overflow)
+                                   : bv3_run<4, 4, LOCAL, PST>(rowptr, col, node_off, hop_off, b, max_n, ts, bar_group, gslice, out, levels, overflow);
             lvl_max = max(lvl_max, lm);
         } else if (t < c_big + items2) {                             // 33..64 nodes: two graphs on the two warp pairs
             const int pr = wq >> 1;
             const int64_t idx = 2 * (t - c_big) + pr;
             if (idx < c2)
-                lvl_max = max(lvl_max, bv3_run<2, 2, LOCAL>(rowptr, col, node_off, hop_off, ord2[idx], cap2, (wq & 1) * 32 + lane,
+                lvl_max = max(lvl_max, bv3_run<2, 2, LOCAL, PST>(rowptr, col, node_off, hop_off, ord2[idx], cap2, (wq & 1) * 32 + lane,
                                                      bar_group + 1 + pr, gslice + (size_t)pr * half, out, levels, overflow));
         } else {                                                     // up to 32 nodes: four graphs, a warp each
             const int64_t idx = 4 * (t - c_big - items2) + wq;
             if (idx < c3)
-                lvl_max = max(lvl_max, bv3_run<1, 1, LOCAL>(rowptr, col, node_off, hop_off, ord3[idx], cap1, lane, 0,
+                lvl_max = max(lvl_max, bv3_run<1, 1, LOCAL, PST>(rowptr, col, node_off, hop_off, ord3[idx], cap1, lane, 0,
                                                      gslice + (size_t)wq * quarter, out, levels, overflow));
         }
         bv3_sync<BV3_GW>(bar_group);                                 // the slice is re-partitioned / refilled by the next item
@@ -1007,30 +1078,30 @@ extern "C" int gnan_apsp_msbfs(const int32_t *rowptr, const int32_t *col, int32_
 }
 
 // v3 launch: groups of 4 warps; the group's slice holds one graph of 65..128 nodes, two of 33..64 or four of up to 32
-template <bool LOCAL>
+template <bool LOCAL, bool PST>
 static int launch_bv3(const int32_t *rowptr, const int32_t *col, const int32_t *node_off, const int64_t *hop_off, int32_t B, int32_t max_n,
                       uint8_t *hop, int32_t *cnt, float *rscale, int nb, bool levels, int32_t *overflow_flag, int32_t *max_level,
                       int32_t *order_ws, Bv3Edges le, cudaStream_t st)
 {
     const int Wmax = (max_n + 31) / 32;
-    size_t slice = 4 * bv3_need(std::min(max_n, 32), 1, nb, levels, LOCAL);
-    if (Wmax >= 2) slice = std::max(slice, 2 * bv3_need(std::min(max_n, 64), 2, nb, levels, LOCAL));
-    if (Wmax >= 3) slice = std::max(slice, bv3_need(max_n, Wmax, nb, levels, LOCAL));
-    const int gpc = (int)std::min<size_t>(BV3_MAX_GROUPS, (112 * 1024) / slice);     // two CTAs per SM
+    size_t slice = 4 * bv3_need(std::min(max_n, 32), 1, nb, levels, LOCAL, PST);
+    if (Wmax >= 2) slice = std::max(slice, 2 * bv3_need(std::min(max_n, 64), 2, nb, levels, LOCAL, PST));
+    if (Wmax >= 3) slice = std::max(slice, bv3_need(max_n, Wmax, nb, levels, LOCAL, PST));
+    const int gpc = (int)std::min<size_t>(PST ? BV3_MAX_GROUPS - 1 : BV3_MAX_GROUPS, (112 * 1024) / slice);     // two CTAs per SM
     if (gpc < 1) return GNAN_ERR_UNSUPPORTED;
     const size_t smem3 = slice * gpc;
     static thread_local size_t cached_smem3 = 0;
     static thread_local int cached_gpc = 0, cached_per_sm3 = 0;
     if (cached_smem3 != smem3 || cached_gpc != gpc || cached_per_sm3 == 0) {
-        GNAN_CUDA(cudaFuncSetAttribute(apsp_batched_v3_kernel<LOCAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-        GNAN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_per_sm3, apsp_batched_v3_kernel<LOCAL>, 32 * BV3_GW * gpc, smem3));
+        GNAN_CUDA(cudaFuncSetAttribute(apsp_batched_v3_kernel<LOCAL, PST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        GNAN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_per_sm3, apsp_batched_v3_kernel<LOCAL, PST>, 32 * BV3_GW * gpc, smem3));
         cached_smem3 = smem3; cached_gpc = gpc;
     }
     const int blocks3 = (int)std::min<int64_t>(ceil_div64(B, gpc), (int64_t)std::max(cached_per_sm3, 1) * gnan_sm_count());
     GNAN_CUDA(cudaMemsetAsync(order_ws, 0, 4 * sizeof(int32_t), st));
     bv3_classify_kernel<<<(unsigned)ceil_div64(B, 256), 256, 0, st>>>(node_off, B, order_ws);
     GNAN_LAUNCH_OK();
-    apsp_batched_v3_kernel<LOCAL><<<blocks3, 32 * BV3_GW * gpc, smem3, st>>>(rowptr, col, node_off, hop_off, B, max_n, gpc, (int)slice, hop, cnt,
+    apsp_batched_v3_kernel<LOCAL, PST><<<blocks3, 32 * BV3_GW * gpc, smem3, st>>>(rowptr, col, node_off, hop_off, B, max_n, gpc, (int)slice, hop, cnt,
                                                                             rscale, nb, overflow_flag, max_level, order_ws, le);
     GNAN_LAUNCH_OK();
     return GNAN_OK;
@@ -1069,8 +1140,8 @@ extern "C" int gnan_apsp_bfs_batched_ex(const int32_t *rowptr, const int32_t *co
         const int nb = levels ? nbins : 256;
         static const bool force_v2 = getenv("GNAN_BFS_V2") != nullptr;
         if (order_ws && !force_v2) {
-            const int rc3 = launch_bv3<false>(rowptr, col, node_off, hop_off, B, max_n, hop, cnt, rscale, nb, levels, overflow_flag, max_level,
-                                              order_ws, Bv3Edges{nullptr, nullptr, nullptr, nullptr}, st);
+            const int rc3 = launch_bv3<false, false>(rowptr, col, node_off, hop_off, B, max_n, hop, cnt, rscale, nb, levels, overflow_flag,
+                                                     max_level, order_ws, Bv3Edges{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, st);
             if (rc3 != GNAN_ERR_UNSUPPORTED) return rc3;
         }
         // v2: one warp per graph; hop blocks assembled in shared memory and written once (no memset of hop)
@@ -1121,8 +1192,8 @@ extern "C" int gnan_apsp_bfs_batched_ex(const int32_t *rowptr, const int32_t *co
 // The batched BFS straight from the batch's edge list in its transfer form (no CSR): see include/gnan_b200.h
 extern "C" int gnan_apsp_bfs_batched_local(const uint8_t *src, const uint8_t *dst, const int32_t *edge_off, const int32_t *node_off,
                                            const int64_t *hop_off, int32_t B, int32_t max_n, uint8_t *hop, int32_t *cnt, float *rscale,
-                                           int32_t nbins, int32_t *status, int32_t *overflow_flag, int32_t *max_level, int32_t *order_ws,
-                                           gnan_stream_t stream)
+                                           float *pstat, int32_t *pdepth, int32_t nbins, int32_t *status, int32_t *overflow_flag,
+                                           int32_t *max_level, int32_t *order_ws, gnan_stream_t stream)
 {
     GNAN_REQUIRE(B >= 0, "apsp_bfs_batched_local: negative batch");
     GNAN_REQUIRE(status != nullptr, "apsp_bfs_batched_local: NULL status");
@@ -1130,15 +1201,20 @@ extern "C" int gnan_apsp_bfs_batched_local(const uint8_t *src, const uint8_t *ds
     GNAN_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), st));
     if (B == 0) return GNAN_OK;
     GNAN_REQUIRE(edge_off && node_off && hop_off && hop && overflow_flag && order_ws, "apsp_bfs_batched_local: NULL pointer");
-    GNAN_REQUIRE(!(cnt || rscale) || (nbins >= 2 && nbins <= 256), "apsp_bfs_batched_local: nbins %d out of [2,256]", nbins);
+    GNAN_REQUIRE(!(cnt || rscale || pstat) || (nbins >= 2 && nbins <= 256), "apsp_bfs_batched_local: nbins %d out of [2,256]", nbins);
+    GNAN_REQUIRE(!pstat == !pdepth, "apsp_bfs_batched_local: pstat and pdepth go together");
     if (max_n < 1 || max_n > 32 * BV2_W) {
         gnan_set_error("apsp_bfs_batched_local: graphs with %d nodes unsupported (1..%d); expand the edges and use gnan_apsp_bfs_batched_ex",
                        max_n, 32 * BV2_W);
         return GNAN_ERR_UNSUPPORTED;
     }
     const bool levels = cnt || rscale;
-    const int rc = launch_bv3<true>(nullptr, nullptr, node_off, hop_off, B, max_n, hop, cnt, rscale, levels ? nbins : 256, levels, overflow_flag,
-                                    max_level, order_ws, Bv3Edges{src, dst, edge_off, status}, st);
+    const int nb = (levels || pstat) ? nbins : 256;
+    const Bv3Edges le{src, dst, edge_off, status, pstat, pdepth};
+    const int rc = pstat ? launch_bv3<true, true>(nullptr, nullptr, node_off, hop_off, B, max_n, hop, cnt, rscale, nb, levels, overflow_flag,
+                                                  max_level, order_ws, le, st)
+                         : launch_bv3<true, false>(nullptr, nullptr, node_off, hop_off, B, max_n, hop, cnt, rscale, nb, levels, overflow_flag,
+                                                   max_level, order_ws, le, st);
     if (rc == GNAN_ERR_UNSUPPORTED) gnan_set_error("apsp_bfs_batched_local: level table too wide for the shared-memory slice");
     return rc;
 }

@@ -248,6 +248,12 @@ int gnan_aggregate_blockdiag_graph_fwd(const uint8_t *hop, const int64_t *hop_of
                                        const float *T /* [nbins,Cr] */, int32_t nbins, int32_t Cr,
                                        const float *rscale /* [sumN,nbins] or NULL */, const float *S, int32_t C,
                                        float *out /* [B,C] */, float *colw, float *Q, int32_t *work_counter, gnan_stream_t stream);
+/* The same forward from the pair statistics (pstat, pdepth) that gnan_apsp_bfs_batched_local accumulated inside the BFS
+ * (output-normalised readout of undirected graphs): no pass over the hop bytes at all; same out / colw / Q, same backward. */
+int gnan_aggregate_blockdiag_graph_fwd_pairs(const float *pstat, const int32_t *pdepth, const int32_t *node_off, int32_t B,
+                                             const float *T, int32_t nbins,
+                                             int32_t Cr, const float *S, int32_t C, float *out, float *colw, float *Q,
+                                             gnan_stream_t stream);
 size_t gnan_aggregate_blockdiag_graph_bwd_workspace_bytes(int32_t nbins, int32_t C);
 int gnan_aggregate_blockdiag_graph_bwd(const int32_t *node_off, int32_t B, int32_t nbins, int32_t Cr, int32_t C,
                                        const float *g /* [B,C] */, const float *colw, const float *Q, float *dS, float *dT,
@@ -341,11 +347,17 @@ int gnan_apsp_bfs_batched_ex(const int32_t *rowptr, const int32_t *col, const in
  * memory from the graph's own edge segment; gnan_build_csr (and its ~0.1 ms per 4 M edges) drops out of a training step that
  * preprocesses its batch. Graphs of at most 128 nodes; order_ws [4*B+4] is required. *status (device int32, zeroed here) gets
  * gnan_build_csr's bits: 1 = an endpoint >= the graph's node count (edge dropped), 2 = a repeated (src,dst) pair (the reference
- * sums those into weight-2 edges: the caller must take the multi-edge path). pre_process_datasets.py:106-122 per graph. */
+ * sums those into weight-2 edges: the caller must take the multi-edge path). pre_process_datasets.py:106-122 per graph.
+ * pstat + pdepth (optional, UNDIRECTED graphs): the pair statistics of the output-normalised graph readout,
+ * P_b[d,j] = sum_{i: hop(i,j) = d} 1/cnt[i,d], accumulated inside the BFS level loop. pstat: sumN*nbins floats, graph b's block at
+ * node_off[b]*nbins, LEVEL-MAJOR [nbins][n_b]: rows 0..pdepth[b] (the graph's deepest level) and row nbins-1 (the unreachable bin)
+ * are written, the rows in between are left untouched and must not be read; pdepth: int32 [B].
+ * gnan_aggregate_blockdiag_graph_fwd_pairs consumes them instead of the hop bytes + the normaliser table. A graph whose edge
+ * list is not symmetric sets status bit 4 (its block of pstat is then meaningless). */
 int gnan_apsp_bfs_batched_local(const uint8_t *src, const uint8_t *dst, const int32_t *edge_off, const int32_t *node_off,
                                 const int64_t *hop_off, int32_t B, int32_t max_n, uint8_t *hop, int32_t *cnt, float *rscale,
-                                int32_t nbins, int32_t *status, int32_t *overflow_flag, int32_t *max_level, int32_t *order_ws,
-                                gnan_stream_t stream);
+                                float *pstat, int32_t *pdepth, int32_t nbins, int32_t *status, int32_t *overflow_flag,
+                                int32_t *max_level, int32_t *order_ws, gnan_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Deep graphs (csrc/wide.cu): hop distances > 254. The reference has no depth limit (pre_process_datasets.py:109-121), so the
