@@ -460,8 +460,10 @@ def run_workload(args, env, name, *, steps, warmup, classes=0, compare_legs=Fals
         in_step_apsp = wl.name == "mol"
         node_off_h = wl.node_off.numpy()
         pk = apsp_batched(wl.edge_index, node_off_h, device=dev, x=wl.x.to(dev), y=wl.y.to(dev))
-        host = PackedBatch(wl.x, pk.hop.cpu(), pk.hop_off.cpu(), pk.node_off.cpu(),
-                           pk.level_counts.cpu(), wl.y, pk.max_nodes)
+        lc_h = pk.level_counts.cpu()
+        lc_max = int(lc_h.max()) if lc_h.numel() else 0                 # the level sizes cross PCIe in the narrowest type that holds them
+        lc_h = lc_h.to(torch.uint8 if lc_max < 256 else torch.int16 if lc_max < 32768 else torch.int32)
+        host = PackedBatch(wl.x, pk.hop.cpu(), pk.hop_off.cpu(), pk.node_off.cpu(), lc_h, wl.y, pk.max_nodes)
         cx = compress_features(pk.x) if model.dedup else None
         cx_h = None if cx is None else cx.compact_host()      # narrow index arrays on the host side
         pk.x_compressed = cx
@@ -507,6 +509,8 @@ def run_workload(args, env, name, *, steps, warmup, classes=0, compare_legs=Fals
                 return (e, d[1], d[2], d[3], d[4], None if d[5] is None else d[5].to(dev))
             if getattr(d, "x_compressed", None) is not None:
                 d.x_compressed = d.x_compressed.to(dev)
+            if d.level_counts is not None and d.level_counts.dtype != torch.int32:
+                d.level_counts = d.level_counts.to(torch.int32)
             return d
 
         def loss_of(data):
