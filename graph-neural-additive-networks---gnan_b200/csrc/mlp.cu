@@ -579,6 +579,171 @@ __global__ void linear1_du_kernel(MlpKArgs a, const float *__restrict__ dS)
 inline size_t pad4(size_t n) { return (n + 3) / 4 * 4; }
 
 // floats of one partial-gradient chunk; every segment starts 16-byte aligned (the kernel stores float4s)
+// ---- entries mode, SMALL groups (bag-of-words columns: a few dozen distinct values per feature): one CTA per feature ----------
+// The tcgen05 backward stages 64 KB of split weights, allocates tensor memory and drains its pipeline once per (feature, tile):
+// with ~35 rows per feature that set-up is the whole cost (Cora shape: 1 434 CTAs, one per SM at a time, 15 us each). Here a
+// feature is a 256-thread CTA with 46 KB of shared memory (4-5 CTAs per SM overlap each other's latencies), plain fp32 FMAs:
+// 32-row tiles, W2 in shared memory with an odd row stride (65: conflict free along rows and columns), dW2 as a 4x4 register
+// block per thread, every gradient of the feature written straight to its place (no partial chunks, no reduction kernel).
+constexpr int SG_RT = 32, SG_LD = 65, SG_THREADS = 256, SG_H = 64, SG_C = 8;
+constexpr int SG_AVG_MAX = 96;                           // used when a feature has at most this many entries on average
+
+__global__ void __launch_bounds__(SG_THREADS, 3)
+mlp_entries_bwd_small_kernel(MlpKArgs a, const float *__restrict__ dY, MlpGradPtrs gp)
+{
+    __shared__ float sW[SG_H * SG_LD], sA0[SG_RT * SG_LD], sA1[SG_RT * SG_LD], sDz[SG_RT * SG_LD];
+    __shared__ float sG[SG_RT * SG_C], sX[SG_RT], sW1[SG_H], sB1[SG_H], sB2[SG_H], sWo[SG_C * SG_H];
+    const int tid = threadIdx.x, t16 = tid & 15, r2 = tid >> 4, g = blockIdx.x, C = a.C;
+    const int64_t ebase = a.grp_ptr[g], nrow = a.grp_ptr[g + 1] - ebase;
+    {
+        const float *W = a.wh + (size_t)g * SG_H * SG_H;
+        for (int idx = tid; idx < SG_H * SG_H; idx += SG_THREADS) sW[(idx >> 6) * SG_LD + (idx & 63)] = __ldg(W + idx);
+        if (tid < SG_H) {
+            sW1[tid] = __ldg(a.w1 + (size_t)g * SG_H + tid);
+            sB1[tid] = a.b1 ? __ldg(a.b1 + (size_t)g * SG_H + tid) : 0.f;
+            sB2[tid] = a.bh ? __ldg(a.bh + (size_t)g * SG_H + tid) : 0.f;
+        }
+        for (int idx = tid; idx < SG_C * SG_H; idx += SG_THREADS) {
+            const int c = idx >> 6;
+            sWo[idx] = c < C ? __ldg(a.wo + ((size_t)g * C + c) * SG_H + (idx & 63)) : 0.f;
+        }
+    }
+    float accW[4][4];                                    // dW2[r2*4 + q][t16 + 16 p]
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int pp = 0; pp < 4; ++pp) accW[q][pp] = 0.f;
+    float wo0 = 0.f, wo1 = 0.f;                          // dWo[c = warp][lane], [lane + 32]
+    float pb2 = 0.f, pw1 = 0.f, pb1 = 0.f, pbo = 0.f;    // column sums owned by tid < 64 (bo: tid 64..71)
+    const int rA = 2 * r2, rB = rA + 1;
+    for (int64_t row0 = 0; row0 < nrow; row0 += SG_RT) {
+        __syncthreads();                                 // previous tile consumed (first pass: the weights are staged)
+        if (tid < SG_RT) sX[tid] = row0 + tid < nrow ? __ldg(a.u + ebase + row0 + tid) : 0.f;
+        {
+            const int r = tid >> 3, c = tid & 7;
+            sG[tid] = (row0 + r < nrow && c < C) ? __ldg(dY + (ebase + row0 + r) * C + c) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < SG_RT * SG_H / SG_THREADS; ++e) {
+            const int idx = tid + SG_THREADS * e, r = idx >> 6, i = idx & 63;
+            sA0[r * SG_LD + i] = relu(fmaf(sX[r], sW1[i], sB1[i]));
+        }
+        __syncthreads();
+        {   // z2 = a0 W2^T + b2 for rows rA, rB and units t16 + 16 q; then a1, dh = g Wo, dz2
+            float acc[2][4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[0][q] = acc[1][q] = sB2[t16 + 16 * q];
+#pragma unroll 8
+            for (int i = 0; i < SG_H; ++i) {
+                const float xa = sA0[rA * SG_LD + i], xb = sA0[rB * SG_LD + i];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float w = sW[(t16 + 16 * q) * SG_LD + i];
+                    acc[0][q] = fmaf(xa, w, acc[0][q]);
+                    acc[1][q] = fmaf(xb, w, acc[1][q]);
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int r = rA + h;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int j = t16 + 16 * q;
+                    float dh = 0.f;
+#pragma unroll
+                    for (int c = 0; c < SG_C; ++c) dh = fmaf(sG[r * SG_C + c], sWo[c * SG_H + j], dh);
+                    const float z = acc[h][q];
+                    sA1[r * SG_LD + j] = relu(z);
+                    sDz[r * SG_LD + j] = z > 0.f ? dh : 0.f;
+                }
+            }
+        }
+        __syncthreads();
+        // dW2[j][i] += sum_r dz2[r][j] a0[r][i]
+#pragma unroll 4
+        for (int r = 0; r < SG_RT; ++r) {
+            float dz[4], av[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { dz[q] = sDz[r * SG_LD + r2 * 4 + q]; av[q] = sA0[r * SG_LD + t16 + 16 * q]; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int pp = 0; pp < 4; ++pp) accW[q][pp] = fmaf(dz[q], av[pp], accW[q][pp]);
+        }
+        {   // dWo[c][j] += sum_r g[r][c] a1[r][j]: a warp per channel
+            const int c = tid >> 5, jj = tid & 31;
+#pragma unroll 8
+            for (int r = 0; r < SG_RT; ++r) {
+                const float gv = sG[r * SG_C + c];
+                wo0 = fmaf(gv, sA1[r * SG_LD + jj], wo0);
+                wo1 = fmaf(gv, sA1[r * SG_LD + jj + 32], wo1);
+            }
+        }
+        if (tid < SG_H) {
+#pragma unroll 8
+            for (int r = 0; r < SG_RT; ++r) pb2 += sDz[r * SG_LD + tid];
+        } else if (tid < SG_H + SG_C) {
+#pragma unroll 8
+            for (int r = 0; r < SG_RT; ++r) pbo += sG[r * SG_C + tid - SG_H];
+        }
+        float dz1[2][4];
+        {   // da0 = dz2 W2 for rows rA, rB and units t16 + 16 q; dz1 = da0 * 1[a0 > 0]
+            float acc[2][4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[0][q] = acc[1][q] = 0.f;
+#pragma unroll 8
+            for (int j = 0; j < SG_H; ++j) {
+                const float da = sDz[rA * SG_LD + j], db = sDz[rB * SG_LD + j];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float w = sW[j * SG_LD + t16 + 16 * q];
+                    acc[0][q] = fmaf(da, w, acc[0][q]);
+                    acc[1][q] = fmaf(db, w, acc[1][q]);
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) dz1[h][q] = sA0[(rA + h) * SG_LD + t16 + 16 * q] > 0.f ? acc[h][q] : 0.f;
+        }
+        __syncthreads();                                 // a1 (dWo) and dz2 are consumed: a1's buffer takes dz1
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sA1[(rA + h) * SG_LD + t16 + 16 * q] = dz1[h][q];
+        __syncthreads();
+        if (tid < SG_H) {
+#pragma unroll 8
+            for (int r = 0; r < SG_RT; ++r) {
+                const float d = sA1[r * SG_LD + tid];
+                pw1 = fmaf(d, sX[r], pw1);
+                pb1 += d;
+            }
+        }
+    }
+    if (gp.wh) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp) gp.wh[((size_t)g * SG_H + r2 * 4 + q) * SG_H + t16 + 16 * pp] = accW[q][pp];
+    }
+    {
+        const int c = tid >> 5, jj = tid & 31;
+        if (gp.wo && c < C) {
+            gp.wo[((size_t)g * C + c) * SG_H + jj] = wo0;
+            gp.wo[((size_t)g * C + c) * SG_H + jj + 32] = wo1;
+        }
+    }
+    if (tid < SG_H) {
+        if (gp.bh) gp.bh[(size_t)g * SG_H + tid] = pb2;
+        if (gp.w1) gp.w1[(size_t)g * SG_H + tid] = pw1;
+        if (gp.b1) gp.b1[(size_t)g * SG_H + tid] = pb1;
+    } else if (tid < SG_H + C) {
+        if (gp.bo) gp.bo[(size_t)g * C + tid - SG_H] = pbo;
+    }
+}
+
 size_t grad_floats(const gnan_mlp_params *p)
 {
     const size_t G = p->G, H = p->H, C = p->C, nh = p->n_layers - 2;
@@ -936,6 +1101,18 @@ extern "C" int gnan_mlp_entries_bwd(const float *val, const int64_t *grp_ptr, in
     GNAN_REQUIRE(grads->du == nullptr, "mlp_entries_bwd: input gradients are not available in entries mode");
     GNAN_REQUIRE(max_group_entries >= 0 && max_group_entries <= E, "mlp_entries_bwd: bad max_group_entries");
     cudaStream_t st = (cudaStream_t)stream;
+    static const bool no_small = getenv("GNAN_NO_SMALL_GROUPS") != nullptr;
+    if (E > 0 && p->H == SG_H && p->n_layers == 3 && p->C <= SG_C && E <= (int64_t)SG_AVG_MAX * p->G && !no_small) {
+        // few rows per feature (bag-of-words columns): a CTA per feature on the CUDA cores, fp32 (both precision modes)
+        MlpKArgs a = make_args(val, E, 1, p, 0.f, 0);
+        a.grp_ptr = grp_ptr;
+        MlpGradPtrs gp;
+        gp.w1 = grads->w1; gp.b1 = grads->b1; gp.wh = grads->wh; gp.bh = grads->bh; gp.wo = grads->wo; gp.bo = grads->bo;
+        gp.chunk_stride = 0;
+        mlp_entries_bwd_small_kernel<<<(unsigned)p->G, SG_THREADS, 0, st>>>(a, dY, gp);
+        GNAN_LAUNCH_OK();
+        return GNAN_OK;
+    }
     if (E > 0 && precision != GNAN_PREC_FP32 && gnan_mlp_tc_bwd_supported(p, precision))      // tcgen05 kernel, per-group row space
         return gnan_mlp_tc_bwd_ex(val, std::max<int64_t>(max_group_entries, 1), 1, p, 0.f, 0, precision, dY, grads, workspace,
                                   workspace_bytes, st, grp_ptr, nullptr, nullptr, nullptr);

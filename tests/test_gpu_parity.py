@@ -876,6 +876,43 @@ def test_mlp_tensor_core_one_pass_backward_with_dropout_matches_fp32_path():
         assert G.rel_err(grads["tf32x3"][k], grads["fp32"][k]) < 2e-4, k     # same masks; a kink may flip under different rounding
 
 
+@pytest.mark.parametrize("G_,C,bias,precision", [(200, 7, True, "fp32"), (64, 1, True, "tf32x3"), (33, 8, False, "fp32"), (120, 3, True, "tf32x3")])
+def test_mlp_entries_small_groups_vs_float64(G_, C, bias, precision):
+    """Entries mode with a few dozen rows per feature (bag-of-words columns): forward + the CTA-per-feature fp32 backward
+    (mlp_entries_bwd_small_kernel, taken in both precision modes when a feature has <= 96 entries on average), incl. single-entry
+    groups, groups longer than one 32-row tile and an empty tail, against float64 on kink-free inputs: 1e-5."""
+    from gnan_b200 import sparse
+    H, L = 64, 3
+    rng = np.random.default_rng(G_ * 10 + C)
+    p = rand_mlp(rng, G_, H, C, L, bias=bias)
+    R = 140
+    u = kink_free_inputs(rng, p, R, G_, 2e-5, L)
+    sizes = rng.integers(1, 91, size=G_)
+    sizes[0], sizes[1], sizes[2] = 1, 140, 33
+    rows = [np.sort(rng.choice(R, size=int(n), replace=False)) for n in sizes]
+    grp_ptr = torch.tensor(np.concatenate([[0], np.cumsum(sizes)]), dtype=torch.int64)
+    val = torch.cat([u[torch.tensor(r), g] for g, r in enumerate(rows)])
+    E = val.numel()
+    dY = torch.tensor(rng.normal(size=(E, C))).float()
+    # float64 restatement per entry
+    q = oracle_params(p, L)
+    grp = torch.repeat_interleave(torch.arange(G_), torch.tensor(sizes))
+    a0 = torch.relu(val.double().unsqueeze(1) * q["w1"][grp] + q["b1"][grp])
+    a1 = torch.relu(torch.einsum("ei,eji->ej", a0, q["wh"][0][grp]) + q["bh"][0][grp])
+    want = torch.einsum("ej,ecj->ec", a1, q["wo"][grp]) + q["bo"][grp]
+    (want * dY.double()).sum().backward()
+    from gnan_b200._lib import PRECISIONS
+    d = {k: v.to(DEV).requires_grad_(True) for k, v in p.items()}
+    items = sparse._tiles_of(torch.tensor(sizes).to(DEV), G_, DEV)
+    got = sparse.mlp_entries_fwd(val.to(DEV), grp_ptr.to(DEV), items, d["w1"], d["b1"], d["wh"], d["bh"], d["wo"], d["bo"], L, int(sizes.max()),
+                                 PRECISIONS[precision])
+    (got * dY.to(DEV)).sum().backward()
+    assert G.rel_err(got.detach().cpu().numpy(), want.detach().numpy()) < TOL
+    for k in p:
+        if bias or k in ("w1", "wh", "wo"):
+            assert G.rel_err(d[k].grad.cpu().numpy(), q[k].grad.numpy()) < TOL, k
+
+
 # ---- compact transfer forms (what crosses PCIe in bench.py's end-to-end leg) -------------------------------------------
 def test_local_edges_expand_rebuilds_edge_index():
     """preprocess.LocalEdges: uint8 local endpoints + per-graph edge offsets -> gnan_edges_from_local -> the int64 edge_index,
