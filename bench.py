@@ -368,7 +368,7 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------------------
 KERNEL_NAMES = {
     "mlp_bwd": "mlp_tc_bwd_kernel / mlp_bwd_kernel", "mlp_fwd": "mlp_tc_fwd_kernel / mlp_fwd_kernel",
-    "mlp_entries_bwd": "mlp_tc_bwd_kernel / mlp_bwd_kernel (entries mode)", "mlp_entries_fwd": "mlp_fwd_kernel (entries mode)",
+    "mlp_entries_bwd": "mlp_entries_bwd_small_kernel (<= 96 entries per feature on average) | mlp_tc_bwd_kernel / mlp_bwd_kernel (entries mode)", "mlp_entries_fwd": "mlp_fwd_kernel (entries mode)",
     "aggregate_rows_fwd_save": "agg_tc_fwd_kernel (+ colmax / digits pre-pass) | agg_rows_bins_kernel",
     "aggregate_rows_bwd_saved": "agg_tc_ds_kernel (+ row compaction, digits, dT kernels) | agg_rows_ds_kernel",
     "aggregate_blockdiag_fwd": "agg_bd_graph_fwd_kernel | agg_blockdiag_fwd_rows_kernel",
