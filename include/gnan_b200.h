@@ -339,8 +339,10 @@ int gnan_apsp_bfs_batched_n(const int32_t *rowptr, const int32_t *col, const int
 int gnan_apsp_bfs_batched_ex(const int32_t *rowptr, const int32_t *col, const int32_t *node_off, const int64_t *hop_off,
                              int32_t B, int32_t max_n, int64_t total_nodes, int64_t total_hop_bytes, uint8_t *hop, int32_t *cnt,
                              float *rscale, int32_t nbins, int32_t *overflow_flag, int32_t *max_level,
-                             int32_t *order_ws /* [4*B+4] scratch or NULL. With it the graphs are grouped by size class and a group of 4 warps works on one graph of 65..128 nodes, two of 33..64 or four of up to 32 nodes at a time; NULL = one warp per graph */,
-                             gnan_stream_t stream);
+                             int32_t *order_ws /* [4*B+4] scratch or NULL, see below */, gnan_stream_t stream);
+/* order_ws: with it the graphs are grouped by size class and a GROUP OF 4 WARPS works on one graph of 65..128 nodes, two of 33..64
+ * or four of up to 32 nodes at a time (one vertex per lane, a named barrier with an OR reduction per BFS level); NULL = the
+ * older kernel, one warp per graph. */
 
 /* gnan_apsp_bfs_batched_ex WITHOUT a CSR: the batch's edges in their transfer form (gnan_edges_from_local: src / dst uint8 indices
  * inside the graph, edge_off [B+1], edges grouped by graph). Every 4-warp group builds its graph's adjacency bit matrix in shared
