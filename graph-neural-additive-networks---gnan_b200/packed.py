@@ -251,7 +251,10 @@ def load_node(path, device="cuda"):
     if d.get("version") != VERSION:
         raise ValueError(f"{path}: format version {d.get('version')} (this build reads {VERSION})")
     N = int(d["num_nodes"])
-    hop = torch.full((d["hop"].shape[0], hop_ld(N)), 255, dtype=torch.uint8)         # row stride padded for 16-byte loads
+    wide = d["hop"].dtype == torch.int16                                             # deep graphs: int16 hops, -1 = unreachable
+    if d["hop"].dtype not in (torch.uint8, torch.int16):
+        raise ValueError(f"{path}: hop matrix of dtype {d['hop'].dtype}")
+    hop = torch.full((d["hop"].shape[0], hop_ld(N)), -1 if wide else 255, dtype=d["hop"].dtype)   # row stride padded for 16-byte loads
     hop[:, :N] = d["hop"]
     out = SimpleNamespace(x=d["x"].to(device), hop_data=HopData(hop.to(device), d["level_counts"].to(device), N, int(d["row_begin"])))
     for k in _NODE_EXTRAS:

@@ -306,3 +306,38 @@ def test_round2_host_logic_without_a_gpu():
     from gnan_b200 import ops
     with pytest.raises(_lib.GnanError):
         ops.bce_with_logits(torch.zeros(3, requires_grad=True), torch.zeros(3))
+
+
+@pytest.mark.parametrize("wide", [False, True])
+def test_node_file_roundtrip_keeps_hop_dtype_and_padding(tmp_path, wide):
+    """packed.save_node / load_node on host tensors: the uint8 form (255 = unreachable) and the int16 form of deep graphs
+    (-1 = unreachable) both come back with their dtype, their unreachable marker in the padding columns and a 16-element row stride."""
+    from types import SimpleNamespace
+
+    from gnan_b200.ops import hop_ld
+    from gnan_b200.packed import load_node, save_node
+    from gnan_b200.preprocess import HopData
+    N, R = 21, 5
+    g = torch.Generator().manual_seed(3)
+    if wide:
+        hop = torch.randint(0, 400, (R, hop_ld(N)), generator=g).to(torch.int16)
+        hop[1, 3] = -1
+    else:
+        hop = torch.randint(0, 9, (R, hop_ld(N)), generator=g).to(torch.uint8)
+        hop[1, 3] = 255
+    cnt = torch.randint(0, 5, (R, 11), generator=g).to(torch.int32)
+    data = SimpleNamespace(x=torch.randn(R, 4, generator=g), hop_data=HopData(hop, cnt, N, row_begin=16), y=torch.arange(R),
+                           train_mask=torch.tensor([True, False, True, False, True]))
+    path = tmp_path / "node.gnan_b200.pt"
+    save_node(data, path)
+    back = load_node(path, device="cpu")
+    hd = back.hop_data
+    assert hd.hop.dtype == hop.dtype and hd.wide == wide and hd.hop.shape == (R, hop_ld(N))
+    assert torch.equal(hd.hop[:, :N], hop[:, :N]) and bool((hd.hop[:, N:] == (-1 if wide else 255)).all())
+    assert torch.equal(hd.level_counts, cnt) and hd.num_nodes == N and hd.row_begin == 16
+    assert torch.equal(back.x, data.x) and torch.equal(back.y, data.y) and torch.equal(back.train_mask, data.train_mask)
+    assert not hasattr(back, "val_mask")
+    torch.save({"format": "gnan_b200.node", "version": 1, "x": data.x, "hop": hop[:, :N].float(), "level_counts": cnt,
+                "num_nodes": N, "row_begin": 0}, tmp_path / "bad.pt")
+    with pytest.raises(ValueError):
+        load_node(tmp_path / "bad.pt", device="cpu")
