@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from ._inputs import compressed_of, resolve
+from ._inputs import _version, compressed_of, resolve
 from ._stacked import StackedMLP
 from .preprocess import PackedBatch
 
@@ -99,7 +99,7 @@ def _unique_inputs(holder, u, cnt=None):
     """(unique values, inverse, sort order, segment offsets) of the per-row rho inputs u [R,nbins]; they depend only on the
     BFS level sizes, so they are computed once per hop-data object and cached on it."""
     # keyed on the level-count tensor's identity AND version: an in-place refresh of the counts invalidates the mapping
-    key = (tuple(u.shape), str(u.device)) + ((cnt.data_ptr(), cnt._version) if cnt is not None else ())
+    key = (tuple(u.shape), str(u.device)) + ((cnt.data_ptr(), _version(cnt)) if cnt is not None else ())
     cache = getattr(holder, "_gnan_b200_rho_unique", None)
     if cache is not None and cache[0] == key:
         return cache[1]

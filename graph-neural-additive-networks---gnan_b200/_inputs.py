@@ -10,6 +10,14 @@ from .preprocess import HopData, from_reference_format
 AUTO_DEDUP_MIN_EVALUATIONS = 1 << 16     # below this many (row, feature) pairs the dense kernels are a single small launch
 
 
+def _version(t):
+    """in-place modification counter of a tensor (inference tensors have none: they cannot be modified in place either)"""
+    try:
+        return t._version
+    except RuntimeError:
+        return 0
+
+
 def compressed_of(holder, x, device, enabled=True):
     """CompressedFeatures to use for `holder`, or None for the dense kernels.
 
@@ -30,7 +38,7 @@ def compressed_of(holder, x, device, enabled=True):
             return None
         if x.shape[0] * x.shape[1] < AUTO_DEDUP_MIN_EVALUATIONS:
             return None
-        key = (x.data_ptr(), x._version, tuple(x.shape))
+        key = (x.data_ptr(), _version(x), tuple(x.shape))
         cache = getattr(holder, "_gnan_b200_cx_cache", None)
         if cache is not None and cache[0] == key:
             cx = cache[1]
@@ -60,11 +68,12 @@ def resolve(inputs, device, need_x=True):
         nd = getattr(inputs, "node_distances", None)
         if nd is None:
             raise AttributeError("inputs needs .hop_data (gnan_b200.preprocess) or .node_distances/.normalization_matrix")
-        key = (nd.data_ptr(), tuple(nd.shape))
+        nm = getattr(inputs, "normalization_matrix", None)
+        # identity AND version of both matrices: an in-place refresh (copy_) must not hit the converted copy of the old values
+        key = (nd.data_ptr(), _version(nd), tuple(nd.shape)) + (() if nm is None else (nm.data_ptr(), _version(nm)))
         if cache is not None and cache[0] == key:
             hd = cache[1]
         else:
-            nm = getattr(inputs, "normalization_matrix", None)
             hd = from_reference_format(nd.to(device, non_blocking=True).float(),
                                        None if nm is None else nm.to(device, non_blocking=True))
             try:
