@@ -73,7 +73,8 @@ enum {
     GNAN_PREC_TF32X3 = 1,   /* tcgen05 kind::tf32, 3-term split (hi*hi + lo*hi + hi*lo), fp32 accumulate in TMEM:
                                fp32-level accuracy (~1e-6 norm-wise); needs H == 64 */
     GNAN_PREC_TF32 = 2      /* tcgen05 single-pass tf32 (~1e-3), stated looser bound */
-};                          /* shapes the tensor-core path does not cover (H != 64, n_layers != 3, C > 8) run the fp32 kernel */
+};                          /* shapes the tensor-core path does not cover (H != 64, n_layers != 3, C > 64) run the fp32 kernel;
+                               gnan_mlp_bwd with 8 < C <= 64 makes ceil(C/8) passes over 8-channel slices (or see gnan_mlp_bwd_ext) */
 
 size_t gnan_mlp_workspace_bytes(int64_t R, const gnan_mlp_params *p, int backward, int precision);
 
