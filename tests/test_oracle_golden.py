@@ -1,5 +1,7 @@
 """CPU: pin the oracle (oracle/gnan_port.py, oracle/gnan_lut.py, oracle/apsp_oracle.c) against the golden
 vectors produced by the unmodified reference (oracle/make_golden.py)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -120,3 +122,34 @@ def test_apsp_oracle_bit_exact(name):
     assert np.array_equal(z["x_out"][:, :-1], z["x"]) and np.all(z["x_out"][:, -1] == 1.0)   # :108 / :127
     assert cnt.sum(axis=1).tolist() == [n] * n
     del node_task
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/GNAN.py"), reason="the unmodified reference is only present in the build container")
+def test_golden_files_regenerate_bit_exactly_from_the_reference(tmp_path):
+    """The committed fixtures ARE the reference's outputs: oracle/make_golden.py (unmodified GNAN.py / models.py / pre_process_datasets.py /
+    trainer.py through the torch_geometric stub) rewrites every file of tests/golden/ bit for bit."""
+    import contextlib
+    import glob
+    import io
+
+    import oracle.make_golden as mg
+    old = mg.OUT
+    mg.OUT = str(tmp_path)
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            mg.main()
+            mg.trainer_cases()
+    finally:
+        mg.OUT = old
+    files = sorted(glob.glob(os.path.join(old, "*.npz")))
+    assert len(files) >= 23
+    for f in files:
+        g = os.path.join(str(tmp_path), os.path.basename(f))
+        assert os.path.exists(g), f"{os.path.basename(f)} is not produced by make_golden.py"
+        a, b = np.load(f, allow_pickle=True), np.load(g, allow_pickle=True)
+        assert set(a.files) == set(b.files), os.path.basename(f)
+        for k in a.files:
+            if a[k].dtype == object:
+                assert str(a[k]) == str(b[k]), (os.path.basename(f), k)
+            else:
+                assert a[k].dtype == b[k].dtype and np.array_equal(a[k], b[k]), (os.path.basename(f), k)
