@@ -192,7 +192,7 @@ def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured (MEASURED_PEAKS.json, sustained bf16)"
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured (MEASURED_PEAKS.json: hbm_gbs for HBM-bound kernels, bf16_tflops_sustained for tensor-bound ones)"
     return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
