@@ -341,3 +341,38 @@ def test_node_file_roundtrip_keeps_hop_dtype_and_padding(tmp_path, wide):
                 "num_nodes": N, "row_begin": 0}, tmp_path / "bad.pt")
     with pytest.raises(ValueError):
         load_node(tmp_path / "bad.pt", device="cpu")
+
+
+def test_reference_format_inputs_are_converted_once_and_again_after_an_in_place_refresh(monkeypatch):
+    """_inputs.resolve caches the compact hop data of a reference-style Data object (fp32 node_distances / normalization_matrix) on
+    the object; the cache key carries both tensors' version counters, so `copy_` into either matrix triggers a new conversion, and
+    inference tensors (no version counter) are accepted."""
+    from types import SimpleNamespace
+
+    from gnan_b200 import _inputs
+    from gnan_b200.preprocess import HopData
+    calls = []
+
+    def fake_convert(nd, nm):
+        calls.append((nd.clone(), None if nm is None else nm.clone()))
+        return HopData(torch.zeros(nd.shape[0], 16, dtype=torch.uint8), torch.zeros(nd.shape[0], 3, dtype=torch.int32), nd.shape[1])
+    monkeypatch.setattr(_inputs, "from_reference_format", fake_convert)
+    nd, nm = torch.rand(4, 4), torch.ones(4, 4)
+    data = SimpleNamespace(x=torch.rand(4, 2), node_distances=nd, normalization_matrix=nm)
+    _, hd1 = _inputs.resolve(data, "cpu")
+    _, hd2 = _inputs.resolve(data, "cpu")
+    assert hd1 is hd2 and len(calls) == 1
+    nd.copy_(torch.rand(4, 4))
+    _, hd3 = _inputs.resolve(data, "cpu")
+    assert hd3 is not hd1 and len(calls) == 2 and torch.equal(calls[1][0], nd)
+    nm.mul_(2.0)
+    _inputs.resolve(data, "cpu")
+    assert len(calls) == 3 and torch.equal(calls[2][1], nm)
+    _inputs.resolve(data, "cpu")
+    assert len(calls) == 3
+    with torch.inference_mode():
+        frozen = SimpleNamespace(x=torch.rand(4, 2), node_distances=torch.rand(4, 4), normalization_matrix=None)
+    _inputs.resolve(frozen, "cpu"); _inputs.resolve(frozen, "cpu")
+    assert len(calls) == 4
+    with pytest.raises(AttributeError):
+        _inputs.resolve(SimpleNamespace(x=torch.rand(4, 2)), "cpu")
