@@ -153,3 +153,37 @@ def test_golden_files_regenerate_bit_exactly_from_the_reference(tmp_path):
                 assert str(a[k]) == str(b[k]), (os.path.basename(f), k)
             else:
                 assert a[k].dtype == b[k].dtype and np.array_equal(a[k], b[k]), (os.path.basename(f), k)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_apsp_oracle_matches_scipy_dijkstra_on_random_graphs(seed):
+    """The C oracle against the library call the reference makes (scipy.sparse.csgraph.dijkstra on the unit-weight directed adjacency,
+    pre_process_datasets.py:109-110,128-129) and a numpy restatement of its normaliser (:112-121), on random directed / undirected
+    graphs with isolated nodes, self loops and several components: hops, level counts and both fp32 matrices bit for bit."""
+    import scipy.sparse
+    from scipy.sparse.csgraph import dijkstra
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(2, 70))
+    m = int(rng.integers(0, 3 * n))
+    src, dst = rng.integers(0, n, size=m), rng.integers(0, n, size=m)
+    if seed % 2 == 0:                                                     # undirected: both directions
+        src, dst = np.concatenate([src, dst]), np.concatenate([dst, src])
+    ei = np.unique(np.stack([src, dst]), axis=1).astype(np.int64)         # simple (no repeated pairs); self loops stay
+    adj = scipy.sparse.coo_matrix((np.ones(ei.shape[1]), (ei[0], ei[1])), shape=(n, n))
+    d = dijkstra(scipy.sparse.lil_matrix(adj))
+    want_hop = np.where(np.isinf(d), -1, d).astype(np.int64)
+    hop = oapsp.apsp(ei, n)
+    assert np.array_equal(np.asarray(hop, dtype=np.int64), want_hop)
+    cnt = oapsp.level_counts(hop)
+    D = int(want_hop.max())
+    assert cnt.shape == (n, D + 2) and cnt.sum(axis=1).tolist() == [n] * n
+    for lvl in range(D + 1):
+        assert np.array_equal(cnt[:, lvl], (want_hop == lvl).sum(axis=1))
+    assert np.array_equal(cnt[:, -1], (want_hop < 0).sum(axis=1))
+    nd, nm = oapsp.reference_format(hop, cnt)
+    want_nd = (1.0 / (torch.nan_to_num(torch.from_numpy(d).float(), posinf=np.inf) + 1)).numpy()      # :112-115
+    assert nd.dtype == np.float32 and np.array_equal(nd, want_nd)
+    want_nm = np.stack([(want_nd[i][None, :] == want_nd[i][:, None]).sum(axis=1) for i in range(n)]).astype(np.float32)   # :117-121
+    assert np.array_equal(nm, want_nm)
+    rows = min(n, 5)
+    assert np.array_equal(oapsp.apsp_rows(ei, n, rows), np.asarray(hop)[:rows])
