@@ -74,9 +74,8 @@ def lut_mode(z):
     return "input" if z["variant"] == "gnanpy_tensor" else "output"
 
 
-@pytest.mark.parametrize("name", [n for n in G.MODEL_CASES if "readout" not in n] + G.BATCHED_CASES)
-def test_lut_restatement_matches_reference(name):
-    z = G.load(name)
+def run_lut(z):
+    """float64 table restatement (oracle/gnan_lut.py) of a loaded case -> (out, fs, rho) after backward of sum(out * out_weight)"""
     dt = torch.float64
     fs = gnan_port.to_torch(z["fs"], dt, True)
     rho = gnan_port.to_torch(z["rho"], dt, True)
@@ -90,7 +89,6 @@ def test_lut_restatement_matches_reference(name):
         # the reference's normalisation matrix is exactly the gathered level sizes
         idx = torch.where(hop < 0, torch.full_like(hop, cnt.shape[1] - 1), hop)
         assert torch.equal(torch.gather(cnt, 1, idx).float(), torch.tensor(z["normalization_matrix"]))
-    rows = forward = None
     if z["variant"] == "gnan_loop" and "node_ids" in z:
         ids = torch.tensor(z["node_ids"])
         hop, cnt = hop[ids], cnt[ids]
@@ -101,9 +99,16 @@ def test_lut_restatement_matches_reference(name):
             out = torch.zeros(B, out.shape[1], dtype=dt).index_add(0, torch.tensor(z["batch_vector"]), out)
     elif z["is_graph_task"]:
         out = out.sum(0).view(-1, 1)
+    (out * torch.tensor(z["out_weight"]).to(dt)).sum().backward()
+    return out, fs, rho
+
+
+@pytest.mark.parametrize("name", [n for n in G.MODEL_CASES if "readout" not in n] + G.BATCHED_CASES)
+def test_lut_restatement_matches_reference(name):
+    z = G.load(name)
+    out, fs, rho = run_lut(z)
     assert out.shape == z["out"].shape
     assert G.rel_err(out.detach().numpy(), z["out"]) < TOL_LUT
-    (out * torch.tensor(z["out_weight"]).to(dt)).sum().backward()
     check_grads(z, fs, "grad_fs", 2e-5)
     check_grads(z, rho, "grad_rho", 2e-5)
 
@@ -187,3 +192,54 @@ def test_apsp_oracle_matches_scipy_dijkstra_on_random_graphs(seed):
     assert np.array_equal(nm, want_nm)
     rows = min(n, 5)
     assert np.array_equal(oapsp.apsp_rows(ei, n, rows), np.asarray(hop)[:rows])
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/GNAN.py"), reason="the unmodified reference is only present in the build container")
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6, 7, 8, 14, 33])     # 14 and 33: ill-conditioned draws (see below)
+def test_oracle_matches_the_live_reference_on_fresh_random_cases(tmp_path, monkeypatch, seed):
+    """Beyond the committed fixtures: NEW random configurations (sizes, widths, depths, switches drawn from the seed) are run through the
+    unmodified reference classes here, and both restatements (fp32 port in the reference's op order, float64 table form) must reproduce
+    outputs and all parameter gradients — the oracle is pinned to the reference itself, not only to 23 files."""
+    import contextlib
+    import io
+
+    import oracle.make_golden as mg
+    gnan_py, models_py, pre_py, batched_cls = mg.import_reference()
+    rng = np.random.default_rng(9000 + seed)
+    monkeypatch.setattr(mg, "OUT", str(tmp_path))
+    monkeypatch.setattr(G, "GOLDEN_DIR", str(tmp_path))
+    pick = lambda *v: v[int(rng.integers(0, len(v)))]
+    names = []
+    with contextlib.redirect_stdout(io.StringIO()):
+        for variant, cls, kw in (("gnanpy_tensor", gnan_py.TensorGNAN, {}), ("models_tensor", models_py.TensorGNAN, {}),
+                                 ("gnan_loop", pick(gnan_py.GNAN, models_py.GNAN), {})):
+            graph = bool(rng.integers(0, 2)) and variant != "gnan_loop"
+            name = f"{variant if variant != 'gnan_loop' else 'gnan_loop'}_live{seed}"
+            if variant == "gnan_loop":
+                kw = dict(layers_kw="n_layers" if cls is gnan_py.GNAN else "num_layers", rho_per_feature=bool(rng.integers(0, 2)),
+                          node_ids=pick(None, [2, 0, 5]))
+            elif variant == "models_tensor":
+                kw = dict(rho_per_feature=bool(rng.integers(0, 2)) and not graph)
+            mg.model_case(name, cls, variant, rng, pre_py, N=int(rng.integers(8, 30)), K_raw=int(rng.integers(2, 7)),
+                          C=1 if graph else int(rng.integers(1, 6)), H=pick(8, 16, 32, 64), L=pick(1, 2, 3, 4) if variant == "gnanpy_tensor" else pick(2, 3),
+                          is_graph_task=graph, normalize_rho=bool(rng.integers(0, 2)), n_isolated=int(rng.integers(0, 3)),
+                          directed=bool(rng.integers(0, 2)), bias=bool(rng.integers(0, 4)), **kw)
+            names.append(name)
+        mg.batched_case(f"batched_live{seed}", batched_cls, rng, B=int(rng.integers(2, 6)), K=int(rng.integers(2, 6)), C=int(rng.integers(1, 5)),
+                        H=pick(8, 16), is_graph_task=bool(rng.integers(0, 2)))
+        names.append(f"batched_live{seed}")
+    for name in names:
+        test_port_matches_reference(name)                    # fp32 port in the reference's op order == the fp32 reference
+        # the table form against the SAME op order carried in float64: a random case may be ill-conditioned (outputs that are small
+        # differences of O(1) terms), where the reference's own fp32 rounding exceeds any fixed bound against float64; the algebra
+        # is checked where rounding does not enter (left: the fp32 rounding of the 1/(1+d) inputs the port is fed, 6e-8, which such a
+        # case amplifies: hence 1e-6 on outputs and 2e-5 on gradients; 40 seeds were tried when the test was written)
+        z = G.load(name)
+        out_l, fs_l, rho_l = run_lut(z)
+        out_p, fs_p, rho_p, _ = run_port(z, torch.float64)
+        assert G.rel_err(out_l.detach().numpy(), out_p.detach().numpy()) < 1e-6, name
+        for got, want in ((fs_l, fs_p), (rho_l, rho_p)):
+            for k in ("w1", "b1", "wh", "bh", "wo", "bo"):
+                if want[k] is None or want[k].grad is None or got[k].grad is None or float(want[k].grad.norm()) == 0:
+                    continue
+                assert G.rel_err(got[k].grad.numpy(), want[k].grad.numpy()) < 2e-5, (name, k)
