@@ -587,6 +587,7 @@ inline size_t pad4(size_t n) { return (n + 3) / 4 * 4; }
 // block per thread, every gradient of the feature written straight to its place (no partial chunks, no reduction kernel).
 constexpr int SG_RT = 32, SG_LD = 65, SG_THREADS = 256, SG_H = 64, SG_C = 8;
 constexpr int SG_AVG_MAX = 96;                           // used when a feature has at most this many entries on average
+constexpr int SG_GROUP_MAX = 32 * SG_AVG_MAX;            // ... and no single feature more than this (one CTA walks a feature's tiles serially)
 
 __global__ void __launch_bounds__(SG_THREADS, 3)
 mlp_entries_bwd_small_kernel(MlpKArgs a, const float *__restrict__ dY, MlpGradPtrs gp)
@@ -1102,7 +1103,7 @@ extern "C" int gnan_mlp_entries_bwd(const float *val, const int64_t *grp_ptr, in
     GNAN_REQUIRE(max_group_entries >= 0 && max_group_entries <= E, "mlp_entries_bwd: bad max_group_entries");
     cudaStream_t st = (cudaStream_t)stream;
     static const bool no_small = getenv("GNAN_NO_SMALL_GROUPS") != nullptr;
-    if (E > 0 && p->H == SG_H && p->n_layers == 3 && p->C <= SG_C && E <= (int64_t)SG_AVG_MAX * p->G && !no_small) {
+    if (E > 0 && p->H == SG_H && p->n_layers == 3 && p->C <= SG_C && E <= (int64_t)SG_AVG_MAX * p->G && max_group_entries <= SG_GROUP_MAX && !no_small) {
         // few rows per feature (bag-of-words columns): a CTA per feature on the CUDA cores, fp32 (both precision modes)
         MlpKArgs a = make_args(val, E, 1, p, 0.f, 0);
         a.grp_ptr = grp_ptr;
