@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from ._inputs import _version, compressed_of, resolve
+from ._inputs import _version, capturing, compressed_of, resolve
 from ._stacked import StackedMLP
 from .preprocess import PackedBatch
 
@@ -80,7 +80,7 @@ class _Base(nn.Module):
         1/((1+d) * cnt) takes few distinct values (small integers): rho runs once per distinct value, rows gather."""
         if not self.dedup:
             return self._table(u)
-        if torch.cuda.is_current_stream_capturing() and not getattr(holder, "static_level_counts", False):
+        if capturing() and not getattr(holder, "static_level_counts", False):
             # a captured step would bake the value -> row mapping of THIS call's level counts into the graph; an in-place
             # refresh of the counts between replays would then silently gather the wrong table rows. Only objects that
             # declare their level counts immutable (holder.static_level_counts = True) keep the shared evaluation.

@@ -18,6 +18,11 @@ def _version(t):
         return 0
 
 
+def capturing():
+    """True while the current CUDA stream is being captured into a graph (False where there is no CUDA device at all)"""
+    return torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+
+
 def compressed_of(holder, x, device, enabled=True):
     """CompressedFeatures to use for `holder`, or None for the dense kernels.
 
@@ -29,7 +34,7 @@ def compressed_of(holder, x, device, enabled=True):
     if not enabled:
         return None
     cx = getattr(holder, "x_compressed", None)
-    if cx is None and x is not None and torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+    if cx is None and x is not None and capturing():
         return None        # an implicit (cached) compressed form would be baked into the CUDA graph and go stale when x is
                            # refreshed in place between replays; pass x_compressed explicitly to share evaluations there
     if cx is None and x is not None:

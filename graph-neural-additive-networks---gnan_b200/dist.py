@@ -153,7 +153,8 @@ class FlatGradients:
             off += k
 
     def zero(self):
-        if any(p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + self.flat.element_size() * o for p, o in zip(self.params, self._offsets())):
+        if any(p.grad is None or (p.numel() and p.grad.data_ptr() != self.flat.data_ptr() + self.flat.element_size() * o)
+               for p, o in zip(self.params, self._offsets())):      # (an empty parameter's view has no address to compare)
             self.attach()
         self.flat.zero_()
 
