@@ -9,8 +9,9 @@ import torch
 from tests.test_dist_cpu import run_world
 
 
-def _install_torch_ops():
-    """dense torch definitions of the ops the modules call (include/gnan_b200.h semantics)"""
+def _install_torch_ops(setter=setattr):
+    """dense torch definitions of the ops the modules call (include/gnan_b200.h semantics); setter: setattr in a spawned worker,
+    monkeypatch.setattr inside the pytest process"""
     from gnan_b200 import ops
 
     def mlp(u, w1, b1, wh, bh, wo, bo, n_layers, dropout_p=0.0, seed=0, precision="fp32", seed_dev=None):
@@ -55,9 +56,9 @@ def _install_torch_ops():
             outs.append(o.sum(0, keepdim=True) if reduce_graph else o)
         return torch.cat(outs)
 
-    ops.mlp, ops.rho_table_inputs, ops.level_rscale = mlp, rho_table_inputs, level_rscale
-    ops.aggregate_rows, ops.aggregate_blockdiag = aggregate_rows, aggregate_blockdiag
-    ops.gather_rows = lambda tq, inv, order, seg_ptr: tq[inv]
+    for name, fn in (("mlp", mlp), ("rho_table_inputs", rho_table_inputs), ("level_rscale", level_rscale), ("aggregate_rows", aggregate_rows),
+                     ("aggregate_blockdiag", aggregate_blockdiag), ("gather_rows", lambda tq, inv, order, seg_ptr: tq[inv])):
+        setter(ops, name, fn)
 
 
 def _node_problem():
@@ -119,10 +120,10 @@ def _sharded(rank, world, flavour):
 
 
 @pytest.mark.parametrize("flavour", ["gnanpy_tensor", "models_tensor", "gnan_loop"])
-def test_row_sharded_modules_equal_single_process_and_oracle(flavour):
+def test_row_sharded_modules_equal_single_process_and_oracle(flavour, monkeypatch):
     import functools
     res = run_world(functools.partial(_sharded, flavour=flavour), 2)
-    _install_torch_ops()
+    _install_torch_ops(monkeypatch.setattr)
     from types import SimpleNamespace
 
     from oracle import gnan_lut, gnan_port, params as P
@@ -203,9 +204,9 @@ def _dp_step(rank, world):
     return out.detach(), fg.flat.clone(), {k: v.detach().clone() for k, v in model.state_dict().items()}, (b, e)
 
 
-def test_data_parallel_packed_batches_equal_single_process():
+def test_data_parallel_packed_batches_equal_single_process(monkeypatch):
     res = run_world(_dp_step, 2)
-    _install_torch_ops()
+    _install_torch_ops(monkeypatch.setattr)
     from gnan_b200 import models as mo
     from gnan_b200.dist import FlatGradients
     graphs = _graph_problem()
