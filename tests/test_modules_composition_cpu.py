@@ -67,3 +67,49 @@ def test_module_composition_matches_reference_golden(name, dedup, monkeypatch):
     if "grad_readout" in z:
         _check(z, _grads(m.readout_nam.fs), z["grad_readout"], "readout")
     assert ops.mlp.__module__ == __name__.replace("test_modules_composition_cpu", "test_dist_modules_cpu")   # the stand-ins really ran
+
+
+@pytest.mark.parametrize("name", ["trainer_graph_bce", "trainer_node_ce"])
+def test_trainer_epochs_match_reference_trainer_on_cpu(name, monkeypatch):
+    """gnan_b200.trainer.train_epoch / test_epoch (label handling, masks, [C,1] -> logits row, per-epoch accumulation, AUC) around the
+    real models.TensorGNAN with the stand-in ops, against the UNMODIFIED trainer.py + models.TensorGNAN + Adam runs recorded in
+    tests/golden/trainer_*.npz: every epoch's (loss, accuracy, auc) tuple and the final weights. CPU twin of the GPU test of the same name."""
+    from gnan_b200 import _inputs, trainer
+    from gnan_b200.models import TensorGNAN
+    from oracle import apsp as oapsp
+    _install_torch_ops(monkeypatch.setattr)
+    z = dict(np.load(f"{G.GOLDEN_DIR}/{name}.npz"))
+    graph_task, n_items, K, C, H, epochs, compute_auc, _ = [int(t) for t in z["meta"]]
+    lr, wd = [float(t) for t in z["hyper"]]
+    m = TensorGNAN(K, C, 3, H, is_graph_task=bool(graph_task), readout_n_layers=0)
+    m.load_state_dict({k[4:]: torch.tensor(v) for k, v in z.items() if k.startswith("sd0.")}, strict=True)
+    items = []
+    for i in range(n_items):
+        x = torch.tensor(z[f"item{i}.x"])
+        ei = z[f"item{i}.edge_index"]
+        hop = np.asarray(oapsp.apsp(ei, x.shape[0]))
+        nd, _nm = oapsp.reference_format(hop, oapsp.level_counts(hop))
+        d = SimpleNamespace(x=x, edge_index=torch.tensor(ei), hop_data=_from_reference_format(torch.tensor(nd)), y=torch.tensor(z[f"item{i}.y"]))
+        if not graph_task:
+            for mk in ("train_mask", "val_mask", "test_mask"):
+                setattr(d, mk, torch.tensor(z[f"item{i}.{mk}"]))
+        items.append(d)
+    loss_fn = torch.nn.BCEWithLogitsLoss() if graph_task else torch.nn.CrossEntropyLoss()
+    opt = torch.optim.Adam(params=m.parameters(), lr=lr, weight_decay=wd)
+    hist = []
+    for _ in range(epochs):
+        tr = trainer.train_epoch(m, dloader=items, loss_fn=loss_fn, optimizer=opt, classify=True, device="cpu", compute_auc=bool(compute_auc),
+                                 is_graph_task=bool(graph_task))
+        va = trainer.test_epoch(m, dloader=items, loss_fn=loss_fn, classify=True, device="cpu", val_mask=True, compute_auc=bool(compute_auc),
+                                is_graph_task=bool(graph_task))
+        m.train()
+        hist.append(list(tr) + list(va))
+    hist, want = np.array(hist, dtype=np.float64), z["history"]
+    assert hist.shape == want.shape
+    assert np.allclose(hist[:, [0, 3]], want[:, [0, 3]], rtol=1e-4, atol=0), (hist[:, [0, 3]], want[:, [0, 3]])   # losses
+    assert np.allclose(hist[:, [1, 4]], want[:, [1, 4]], atol=1e-6)                                              # accuracies
+    assert np.allclose(hist[:, [2, 5]], want[:, [2, 5]], atol=1e-6)                                              # auc / -1
+    sd = m.state_dict()
+    for k, v in z.items():
+        if k.startswith("sd1."):
+            assert G.rel_err(sd[k[4:]].numpy(), v) < 2e-3, k
