@@ -119,10 +119,19 @@ def _sharded(rank, world, flavour):
     return out.detach(), {k: p.grad.clone() for k, p in model.named_parameters()}, (b, e)
 
 
-@pytest.mark.parametrize("flavour", ["gnanpy_tensor", "models_tensor", "gnan_loop"])
+FLAVOURS = ["gnanpy_tensor", "models_tensor", "gnan_loop"]
+_WORLD_CACHE = {}
+
+
+def _sharded_all(rank, world):
+    return {f: _sharded(rank, world, f) for f in FLAVOURS}
+
+
+@pytest.mark.parametrize("flavour", FLAVOURS)
 def test_row_sharded_modules_equal_single_process_and_oracle(flavour, monkeypatch):
-    import functools
-    res = run_world(functools.partial(_sharded, flavour=flavour), 2)
+    if "res" not in _WORLD_CACHE:                      # one world-size-2 launch serves the three flavours (spawning costs ~12 s)
+        _WORLD_CACHE["res"] = run_world(_sharded_all, 2)
+    res = {r: _WORLD_CACHE["res"][r][flavour] for r in range(2)}
     _install_torch_ops(monkeypatch.setattr)
     from types import SimpleNamespace
 
