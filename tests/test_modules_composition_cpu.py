@@ -113,3 +113,29 @@ def test_trainer_epochs_match_reference_trainer_on_cpu(name, monkeypatch):
     for k, v in z.items():
         if k.startswith("sd1."):
             assert G.rel_err(sd[k[4:]].numpy(), v) < 2e-3, k
+
+
+@pytest.mark.parametrize("name", ["gnanpy_tensor_graph", "models_tensor_node_shared_rho", "gnan_loop_shared_rho", "batched_graph", "gnanpy_tensor_node_l1"])
+def test_interpretability_tables_on_cpu(name, monkeypatch):
+    """interpret.shape_function_table / distance_function_table / heatmap (bulk evaluation through the grouped-MLP op with a
+    block-diagonal output layer) against the per-point `model.fs[k](t)` / `model.rho(t)` calls of the notebook (cells 4-9), on the
+    golden weights of the reference. CPU twin of the GPU test; the accessors themselves are checked against the live reference
+    modules in tests/test_modules_cpu.py."""
+    from gnan_b200 import interpret
+    _install_torch_ops(monkeypatch.setattr)
+    z = G.load(name)
+    m = build_module(z).eval()
+    grid = torch.linspace(-2.0, 2.0, 11)
+    got = interpret.shape_function_table(m, grid)
+    assert got.shape == (11, z["K"], m.fs.out_channels)
+    with torch.no_grad():
+        for k in range(z["K"]):
+            assert torch.allclose(got[:, k], m.fs[k](grid.view(-1, 1)), atol=1e-5), k
+        D = 6
+        raw = z["variant"] == "batched"
+        r = interpret.distance_function_table(m, D)
+        u = torch.arange(D + 1, dtype=torch.float32) if raw else 1.0 / (1.0 + torch.arange(D + 1, dtype=torch.float32))
+        assert torch.allclose(r, m.rho(u.view(-1, 1)), atol=1e-5)
+        hm = interpret.heatmap(m, D)
+        f1 = torch.stack([m.fs[k](torch.ones(1, 1))[0, 0] for k in range(z["K"])])
+        assert hm.shape == (z["K"], D + 1) and torch.allclose(hm, torch.outer(f1, r[:, 0]), atol=1e-5)
