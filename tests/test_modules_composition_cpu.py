@@ -139,3 +139,54 @@ def test_interpretability_tables_on_cpu(name, monkeypatch):
         hm = interpret.heatmap(m, D)
         f1 = torch.stack([m.fs[k](torch.ones(1, 1))[0, 0] for k in range(z["K"])])
         assert hm.shape == (z["K"], D + 1) and torch.allclose(hm, torch.outer(f1, r[:, 0]), atol=1e-5)
+
+
+def _install_torch_entries_ops(setter):
+    """dense torch definitions of the compressed-feature ops (gnan_b200.sparse): one evaluation per entry, rows rebuilt as
+    baseline sum + exceptions"""
+    from gnan_b200 import ops, sparse
+
+    def mlp_entries_fwd(val, grp_ptr, items, w1, b1, wh, bh, wo, bo, n_layers, max_group, precision):
+        grp = torch.repeat_interleave(torch.arange(grp_ptr.numel() - 1), grp_ptr[1:] - grp_ptr[:-1])
+        if n_layers == 1:
+            return val[:, None] * wo[grp, :, 0] + bo[grp]
+        h = torch.relu(val[:, None] * w1[grp] + b1[grp])
+        for l in range(n_layers - 2):
+            h = torch.relu(torch.einsum("ei,eji->ej", h, wh[l][grp]) + bh[l][grp])
+        return torch.einsum("eh,ech->ec", h, wo[grp]) + bo[grp]
+
+    def entries_to_rows(Y, grp_ptr, csr_ptr, csr_eid, ent_grp, ent_row):
+        base = Y[grp_ptr[:-1]]                                        # [K,C]: every feature's baseline evaluation
+        S = base.sum(0, keepdim=True).repeat(csr_ptr.numel() - 1, 1)
+        rows = torch.repeat_interleave(torch.arange(csr_ptr.numel() - 1), csr_ptr[1:] - csr_ptr[:-1])
+        return S.index_add(0, rows, Y[csr_eid] - base[ent_grp[csr_eid].long()])
+
+    setter(sparse, "mlp_entries_fwd", mlp_entries_fwd)
+    setter(sparse, "entries_to_rows", entries_to_rows)
+    del ops
+
+
+@pytest.mark.parametrize("share", [True, False], ids=["shared_values", "per_entry"])
+@pytest.mark.parametrize("name", [n for n in G.MODEL_CASES if "readout" not in n])
+def test_compressed_feature_path_matches_reference_golden(name, share, monkeypatch):
+    """The shared-evaluation path (inputs.x_compressed: baseline value per column + exceptions, optionally one evaluation per distinct
+    (feature, value) pair) through the real modules against the golden outputs and gradients of the unmodified reference, which
+    evaluates every (node, feature) pair: the algebra of DESIGN.md §2 and the CompressedFeatures structures, on the CPU."""
+    from gnan_b200 import _inputs, sparse
+    _install_torch_ops(monkeypatch.setattr)
+    _install_torch_entries_ops(monkeypatch.setattr)
+    monkeypatch.setattr(_inputs, "from_reference_format", _from_reference_format)
+    monkeypatch.setattr(sparse, "MAX_SHARED_FRACTION", 1.0)           # share whatever coincides, however little
+    z = G.load(name)
+    m = build_module(z).eval()
+    x = torch.tensor(z["x"])
+    cx = sparse.compress_features(x, max_density=None, share_values=share)
+    assert torch.equal(cx.to_dense(), x) and (cx.shared is not None) == share
+    data = SimpleNamespace(x=None if m.fs.n_layers >= 2 else x, x_compressed=cx,      # a single Linear(1,C) has no shared-evaluation path (dense x needed)
+                           edge_index=torch.tensor(z["edge_index"]), node_distances=torch.tensor(z["node_distances"]),
+                           normalization_matrix=torch.tensor(z["normalization_matrix"]))
+    out = m.forward(data, z["node_ids"].tolist()) if (z["variant"] == "gnan_loop" and "node_ids" in z) else m.forward(data)
+    (out * torch.tensor(z["out_weight"])).sum().backward()
+    assert tuple(out.shape) == z["out"].shape and G.rel_err(out.detach().numpy(), z["out"]) < TOL
+    _check(z, _grads(m.fs), z["grad_fs"], "fs")
+    _check(z, _grads(m.rho), z["grad_rho"], "rho")
