@@ -420,3 +420,31 @@ def test_checkpoints_round_trip_with_the_unmodified_reference_modules(variant):
     back = ours.state_dict()
     for k_, v in ref.state_dict().items():
         assert torch.equal(back[k_], v), k_
+
+
+def test_product_package_never_imports_the_oracle_or_the_tests():
+    """The oracle is test infrastructure: nothing under the package directory (nor the import alias) may import `oracle`, `tests`, `baseline`
+    or the reference's module names; bench.py may, and only inside its reference / cpu_baseline functions."""
+    import ast
+    import glob
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = glob.glob(os.path.join(root, "graph-neural-additive-networks---gnan_b200", "*.py")) + glob.glob(os.path.join(root, "gnan_b200", "*.py"))
+    assert len(files) >= 15
+    banned = {"oracle", "tests", "baseline", "pre_process_datasets", "batched_pyg_main", "scipy", "networkx"}
+    for f in files:
+        for node in ast.walk(ast.parse(open(f).read())):
+            mods = []
+            if isinstance(node, ast.Import):
+                mods = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom) and node.level == 0 and node.module:
+                mods = [node.module]
+            for mname in mods:
+                assert mname.split(".")[0] not in banned, (os.path.basename(f), mname)
+    bench = ast.parse(open(os.path.join(root, "bench.py")).read())
+    allowed = {"reference_step_fn", "reference_apsp_record"}
+    for fn in [n for n in ast.walk(bench) if isinstance(n, ast.FunctionDef)]:
+        for node in ast.walk(fn):
+            if isinstance(node, ast.ImportFrom) and node.module and node.module.split(".")[0] == "oracle":
+                assert fn.name in allowed, fn.name
+    assert not [n for n in bench.body if isinstance(n, (ast.Import, ast.ImportFrom)) and "oracle" in ast.dump(n)]
