@@ -113,7 +113,9 @@ int gnan_mlp_bwd_ext(const float *u, int64_t R, int64_t ldu, const gnan_mlp_para
  * Y[e,:] = f_g(val[e]) and the weight gradients given dY[E,C] come back; how entries map to rows of S is the caller's
  * business (gnan_b200/sparse.py). items [n_items,2] = (group, 128-entry tile index inside the group): one CTA per item.
  * Forward: fp32 kernels (gnan_mlp_entries_fwd) or, with `precision` (gnan_mlp_entries_fwd_ex), the tcgen05 kernel for
- * H = 64, 3 layers, C <= 8; backward: fp32 or the tcgen05 kernel (`precision`); n_layers >= 2; no dropout (the sharing would
+ * H = 64, 3 layers, C <= 8; backward: fp32 or the tcgen05 kernel (`precision`), or — H = 64, 3 layers, C <= 8, at most 96 entries per
+ * feature on average and 3 072 in any one — a CTA per feature on the CUDA cores in fp32 under either `precision` (bag-of-words columns:
+ * a few dozen entries per feature, where a tensor-core tile would be a quarter full); n_layers >= 2; no dropout (the sharing would
  * be wrong with per-row masks). */
 size_t gnan_mlp_entries_workspace_bytes(int64_t max_group_entries, const gnan_mlp_params *p, int backward, int precision);
 int gnan_mlp_entries_fwd(const float *val, const int64_t *grp_ptr /* [G+1] */, int64_t E, const int32_t *items, int64_t n_items,
