@@ -347,6 +347,7 @@ def time_reference(wl, steps, warmup, budget_s, group=1):
         if len(times) >= 2 and time.perf_counter() - t_begin > budget_s:
             break
     ms = 1e3 * sum(times) / len(times)
+    extras = {}                                        # side figures merged into the cpu_baseline record
     if wl.kind == "graph":
         # the shipped trainer wraps every epoch in torch.autograd.set_detect_anomaly(True) (trainer.py:24): the same steps as the
         # reference really runs them, reported next to the plain figure; `value` stays the faster, plain one
@@ -356,11 +357,8 @@ def time_reference(wl, steps, warmup, budget_s, group=1):
             t0 = time.perf_counter()
             for _ in range(n_an):
                 step1()
-            LAST_EXTRAS["value_with_anomaly_mode"] = n_an * (units // group) / (time.perf_counter() - t0)
-    return units / (ms / 1e3), ms, len(times), w_done, threads, note, kind
-
-
-LAST_EXTRAS = {}       # side figures of the last time_reference call (anomaly-mode rate of graph tasks), merged by with_apsp
+            extras["value_with_anomaly_mode"] = n_an * (units // group) / (time.perf_counter() - t0)
+    return units / (ms / 1e3), ms, len(times), w_done, threads, note, kind, extras
 
 
 def reference_apsp_record(wl, n_graphs=100):
@@ -392,9 +390,7 @@ def reference_apsp_record(wl, n_graphs=100):
 
 def with_apsp(rec, wl):
     """adds the reference's preprocessing rate and the combined rate (model step + preprocessing per graph) to a cpu_baseline record,
-    and the anomaly-mode rate of the last time_reference call"""
-    rec.update(LAST_EXTRAS)
-    LAST_EXTRAS.clear()
+    (on top of time_reference's side figures, already merged by the caller)"""
     try:
         ap = reference_apsp_record(wl) if wl.name == "mol" else None
     except Exception as exc:                                   # an extra figure: never costs the line
@@ -408,8 +404,8 @@ def with_apsp(rec, wl):
 
 def cpu_baseline_record(wl, budget_s):
     graph = wl.kind == "graph"
-    val, ms, n, w, threads, note, kind = time_reference(wl, 50 if graph else 2, 5 if graph else 1, budget_s)
-    return with_apsp({"value": val, "unit": wl.unit if wl.name in ("cora", "mutag", "mol") else "rows/s", "cores": threads, "kind": kind,
+    val, ms, n, w, threads, note, kind, extras = time_reference(wl, 50 if graph else 2, 5 if graph else 1, budget_s)
+    return with_apsp({**extras, "value": val, "unit": wl.unit if wl.name in ("cora", "mutag", "mol") else "rows/s", "cores": threads, "kind": kind,
                       "sample": f"{n} timed steps after {w} warm-up ({ms:.1f} ms each): {note}"}, wl)
 
 
@@ -418,12 +414,12 @@ def run_reference(args):
         return
     wl = make_workload(args.workload or "mol", classes=args.classes)
     # graph tasks: the reference trains one graph at a time (a few ms each); a bench step is a bounded sample of 50 of them
-    val, ms, n, w, threads, note, kind = time_reference(wl, max(args.steps, 2), max(args.warmup, 1), 300.0, group=50 if wl.kind == "graph" else 1)
+    val, ms, n, w, threads, note, kind, extras = time_reference(wl, max(args.steps, 2), max(args.warmup, 1), 300.0, group=50 if wl.kind == "graph" else 1)
     print(json.dumps({
         "impl": "reference", "metric": f"GNAN fwd+bwd {wl.unit} ({wl.name}-shape TensorGNAN)", "value": val, "unit": wl.unit,
         "n_gpus": args.gpus, "steps": n, "warmup": w, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(wl, "cpu"),
-        "cpu_baseline": with_apsp({"value": val, "unit": wl.unit, "cores": threads, "kind": kind,
+        "cpu_baseline": with_apsp({**extras, "value": val, "unit": wl.unit, "cores": threads, "kind": kind,
                                    "sample": f"{n} steps after {w} warm-up: {note}"}, wl),
         "e2e": {"value": val, "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
