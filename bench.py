@@ -405,8 +405,8 @@ def with_apsp(rec, wl):
 def cpu_baseline_record(wl, budget_s):
     graph = wl.kind == "graph"
     val, ms, n, w, threads, note, kind, extras = time_reference(wl, 50 if graph else 2, 5 if graph else 1, budget_s)
-    return with_apsp({**extras, "value": val, "unit": wl.unit if wl.name in ("cora", "mutag", "mol") else "rows/s", "cores": threads, "kind": kind,
-                      "sample": f"{n} timed steps after {w} warm-up ({ms:.1f} ms each): {note}"}, wl)
+    return with_apsp({"value": val, "unit": wl.unit if wl.name in ("cora", "mutag", "mol") else "rows/s", "cores": threads, "kind": kind,
+                      "sample": f"{n} timed steps after {w} warm-up ({ms:.1f} ms each): {note}", **extras}, wl)
 
 
 def run_reference(args):
@@ -419,8 +419,8 @@ def run_reference(args):
         "impl": "reference", "metric": f"GNAN fwd+bwd {wl.unit} ({wl.name}-shape TensorGNAN)", "value": val, "unit": wl.unit,
         "n_gpus": args.gpus, "steps": n, "warmup": w, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(wl, "cpu"),
-        "cpu_baseline": with_apsp({**extras, "value": val, "unit": wl.unit, "cores": threads, "kind": kind,
-                                   "sample": f"{n} steps after {w} warm-up: {note}"}, wl),
+        "cpu_baseline": with_apsp({"value": val, "unit": wl.unit, "cores": threads, "kind": kind,
+                                   "sample": f"{n} steps after {w} warm-up: {note}", **extras}, wl),
         "e2e": {"value": val, "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), flush=True)
 
