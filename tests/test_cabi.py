@@ -97,3 +97,45 @@ def test_c99_consumer_compiles_against_the_header_and_calls_the_library(lib_path
     # and as C++ (the reference-side binding may be either)
     subprocess.run(["g++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", "-I", os.path.join(ROOT, "include"), str(src)],
                    check=True, capture_output=True, text=True)
+
+
+def _header_prototypes():
+    """{name: (return type, [parameter types])} parsed from include/gnan_b200.h (comments stripped, parameter names dropped)"""
+    src = open(os.path.join(ROOT, "include", "gnan_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = {}
+    for ret, name, args in re.findall(r"^\s*((?:const\s+)?[A-Za-z_][A-Za-z0-9_]*(?:\s*\*)?)\s*(gnan_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.M | re.S):
+        params = []
+        for a in [x.strip() for x in args.replace("\n", " ").split(",")]:
+            if a in ("void", ""):
+                continue
+            a = re.sub(r"\s+", " ", a)
+            if "*" in a:
+                params.append("ptr")
+            else:
+                params.append(a.rsplit(" ", 1)[0].replace("const ", "").strip())     # drop the parameter name
+        protos[name] = (re.sub(r"\s+", " ", ret).strip(), params)
+    return protos
+
+
+def test_ctypes_signatures_match_the_header_type_by_type():
+    """Every entry of gnan_b200._lib.SIGNATURES against the prototype in the header: same number of parameters, and each scalar type
+    of the same width and kind (a 32-bit slot declared for an int64_t argument would pass small values by luck and corrupt large ones)."""
+    from gnan_b200 import _lib
+    C = ctypes
+    scalar = {"int64_t": C.c_int64, "int32_t": C.c_int32, "int": C.c_int, "float": C.c_float, "size_t": C.c_size_t, "uint64_t": C.c_uint64,
+              "gnan_stream_t": C.c_void_p}
+    protos = _header_prototypes()
+    assert sorted(protos) == sorted(_lib.SIGNATURES)
+    for name, (res, args) in _lib.SIGNATURES.items():
+        ret, params = protos[name]
+        assert len(params) == len(args), (name, len(params), len(args))
+        for i, (want, got) in enumerate(zip(params, args)):
+            if want == "ptr":
+                assert got is C.c_void_p or issubclass(got, C._Pointer), (name, i, got)
+            else:
+                assert got is scalar[want], (name, i, want, got)
+        if "*" in ret:
+            assert res in (C.c_char_p, C.c_void_p), (name, ret, res)
+        else:
+            assert res is scalar[ret], (name, ret, res)
