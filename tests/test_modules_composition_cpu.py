@@ -190,3 +190,32 @@ def test_compressed_feature_path_matches_reference_golden(name, share, monkeypat
     assert tuple(out.shape) == z["out"].shape and G.rel_err(out.detach().numpy(), z["out"]) < TOL
     _check(z, _grads(m.fs), z["grad_fs"], "fs")
     _check(z, _grads(m.rho), z["grad_rho"], "rho")
+
+
+def test_packed_dataset_round_trips_the_reference_preprocessing(monkeypatch, tmp_path):
+    """packed.PackedDataset.from_reference on the outputs of the unmodified pre_process (golden preprocess_* files: fp32 node_distances
+    / normalization_matrix per graph) -> packed uint8 blocks + level table widened to a common depth -> save / load -> to_reference():
+    bit-identical fp32 matrices, for whole sets and gathered mini-batches (host logic of the format, CPU; the GPU converter is replaced
+    by the oracle's)."""
+    from gnan_b200 import packed
+    monkeypatch.setattr(packed, "from_reference_format", _from_reference_format)
+    names = [n for n in G.PREPROCESS_CASES if "node_task" not in n]
+    graphs = []
+    for i, n in enumerate(names):
+        z = G.load(n)
+        graphs.append(SimpleNamespace(x=torch.tensor(z["x_out"]), node_distances=torch.tensor(z["node_distances"]),
+                                      normalization_matrix=torch.tensor(z["normalization_matrix"]), y=torch.tensor([float(i % 2)])))
+    ds = packed.PackedDataset.from_reference(graphs, device="cpu")
+    assert len(ds) == len(graphs) and ds.hop.dtype == torch.uint8 and ds.hop.numel() == sum(g.x.shape[0] ** 2 for g in graphs)
+    assert ds.nbytes() < sum(2 * 4 * g.x.shape[0] ** 2 for g in graphs)            # 1 byte per pair (+ the level table) instead of 8
+    path = tmp_path / "set.gnan_b200.pt"
+    ds.save(path)
+    back = packed.PackedDataset.load(path, device=None)
+    for got, g in zip(back.to_reference(), graphs):
+        assert torch.equal(got.node_distances, g.node_distances) and torch.equal(got.normalization_matrix, g.normalization_matrix)
+        assert torch.equal(got.x, g.x) and torch.equal(got.y, g.y)
+    ids = [len(graphs) - 1, 0, 0]
+    pk = back.batch(ids)
+    sub = packed.PackedDataset(pk.x, pk.node_off, pk.hop, pk.hop_off, pk.level_counts, pk.y, pk.max_nodes)
+    for got, i in zip(sub.to_reference(), ids):
+        assert torch.equal(got.node_distances, graphs[i].node_distances) and torch.equal(got.normalization_matrix, graphs[i].normalization_matrix)
